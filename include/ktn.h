@@ -1,0 +1,191 @@
+/* ktn.h -- C ABI of the B200 separation-round library (libktn.so).
+ *
+ * This is the drop-in boundary for ONE path of lanl-ansi/Katana.jl: the ECP
+ * separation round (evaluate g(x*), reverse-mode sparse Jacobian rows, violation
+ * test, first-order cut emission).  Every entry point names the reference
+ * interface it replaces (paths relative to the reference repository root).
+ * The Julia host reaches these by `ccall`, the Python mirror by `ctypes`;
+ * INTEGRATION.md shows both bindings.  The CPU oracle (oracle/ktn_oracle.c)
+ * exports the same symbols so tests can drive either library.
+ *
+ * Conventions: plain pointers and sizes only; caller-owned HOST buffers unless a
+ * name says `_device`; 0-based indices on the wire (int32 columns, int64 rows /
+ * row pointers); every function returns an int status: 0 = OK, < 0 = usage /
+ * CUDA / NCCL error (message via ktn_last_error), > 0 = numeric condition.
+ * No exception crosses the ABI.  A handle is not thread-safe.
+ */
+#ifndef KTN_H
+#define KTN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- expression wire format (MathProgBase `constr_expr` / `obj_expr` flattened) ----
+ * One expression = its nodes in PREFIX (pre-order) order.  For node i:
+ *   op[i]  one of KTN_OP_*
+ *   arg[i] KTN_OP_VAR: 0-based variable index; call nodes: number of children; CONST: 0
+ *   val[i] KTN_OP_CONST: the value; otherwise ignored
+ * expr_ptr[r] .. expr_ptr[r+1] delimits row r's nodes (offsets relative to the batch).
+ * Semantics of evaluation and of the reverse sweep follow JuMP 0.18's
+ * ReverseDiffSparse tape interpreter (forward_eval / reverse_eval / reverse_extract),
+ * which is what `eval_g` / `eval_jac_g` run at reference src/separators.jl:112-113.
+ */
+enum {
+    KTN_OP_CONST = 0,
+    KTN_OP_VAR   = 1,
+    KTN_OP_ADD   = 2,  /* n-ary, summed left to right starting from 0.0 */
+    KTN_OP_SUB   = 3,  /* binary */
+    KTN_OP_MUL   = 4,  /* n-ary */
+    KTN_OP_DIV   = 5,  /* binary */
+    KTN_OP_POW   = 6,  /* binary: base ^ exponent */
+    KTN_OP_NEG   = 7,  /* unary minus */
+    KTN_OP_EXP   = 8,
+    KTN_OP_LOG   = 9,
+    KTN_OP_SQRT  = 10,
+    KTN_OP_ABS   = 11,
+    KTN_OP__COUNT = 12
+};
+
+/* per-row flags */
+enum {
+    KTN_ROW_NL    = 1, /* row is in `nlconstr_ixs` (reference src/model.jl:120,148): tested every round */
+    KTN_ROW_DENSE = 2  /* Jacobian row lists every column 0..num_var-1 (the epigraph row, src/nlpeval.jl:49-54) */
+};
+
+/* status codes */
+enum {
+    KTN_OK = 0,
+    KTN_NUMERIC_NONFINITE = 1,  /* a selected cut had a non-finite coefficient: reference `m.status = :Error` (src/model.jl:69-73) */
+    KTN_ERR_USAGE = -1,
+    KTN_ERR_CUDA = -2,
+    KTN_ERR_NCCL = -3,
+    KTN_ERR_UNSUPPORTED = -4,
+    KTN_ERR_NOMEM = -5
+};
+
+typedef struct ktn_handle ktn_handle;
+
+/* Mirrors the fields of KatanaModelParams the round reads (reference src/Katana.jl:12-19,
+ * src/solver.jl:34-43): f_tol (src/model.jl:273) and cut_coef_rng (src/model.jl:276).
+ * topk is a build extension: 0 = every violated row becomes a cut (reference behaviour). */
+typedef struct ktn_options {
+    int32_t struct_size;   /* sizeof(ktn_options), for versioning */
+    int32_t device;        /* CUDA device ordinal; -1 = current device */
+    double  f_tol;         /* default 1e-6 */
+    double  cut_coef_rng;  /* default 1e9 */
+    int64_t topk;          /* 0 = all violated rows */
+    int32_t flags;         /* reserved, 0 */
+    int32_t reserved;
+} ktn_options;
+
+typedef struct ktn_timings {
+    double h2d_ms;        /* x* upload */
+    double kernel_ms;     /* separation kernels, CUDA events on the library stream */
+    double exchange_ms;   /* NCCL allgather of compacted cuts (0 when not sharded) */
+    double d2h_ms;        /* cut download in ktn_fetch_cuts */
+    int64_t launches;     /* kernels launched by this library since creation */
+    int64_t rounds;       /* separation rounds run since creation */
+} ktn_timings;
+
+/* lifetime -- replaces constructing KatanaFirstOrderSeparator() (src/separators.jl:58-77). */
+int  ktn_create(const ktn_options* opts, ktn_handle** out);
+void ktn_destroy(ktn_handle* h);
+const char* ktn_last_error(ktn_handle* h);
+/* "cuda" for libktn.so, "oracle" for the CPU restatement. */
+const char* ktn_backend(void);
+int  ktn_set_params(ktn_handle* h, double f_tol, double cut_coef_rng, int64_t topk);
+
+/* problem loading -- replaces initialize!(sep, linear_model, num_var, num_constr, oracle)
+ * (src/separators.jl:81-107): MathProgBase.initialize + jac_structure + per-row bucketing.
+ * May be called again on the same handle (test/runtests.jl:24 reuses one solver): a new
+ * ktn_load_begin frees the previous problem.  Rows may be added in batches, in ascending
+ * row order; `first_row` is the 0-based global index of the batch's first row. */
+int ktn_load_begin(ktn_handle* h, int64_t num_var, int64_t num_constr);
+int ktn_add_rows(ktn_handle* h, int64_t first_row, int64_t nrows,
+                 const int64_t* expr_ptr, const int32_t* op, const int32_t* arg, const double* val,
+                 const double* lb, const double* ub, const uint8_t* flags);
+int ktn_load_end(ktn_handle* h);
+/* Replace every loaded row's (lb, ub).  In the reference the bounds are model state passed to
+ * isconstrsat / gencut per call (src/model.jl:273-277), not separator state. */
+int ktn_set_bounds(ktn_handle* h, const double* lb, const double* ub);
+
+/* Jacobian structure of the loaded rows -- replaces MathProgBase.jac_structure as consumed by
+ * src/separators.jl:92-100: per row, the column list in evaluator entry order (ascending
+ * unique columns for tape rows; 0..num_var-1 for KTN_ROW_DENSE rows).
+ * row_ptr has (rows loaded)+1 entries; pass cols = NULL to query sizes only. */
+int ktn_jac_structure(ktn_handle* h, int64_t* row_ptr, int32_t* cols);
+int64_t ktn_num_rows(ktn_handle* h);
+int64_t ktn_jac_nnz(ktn_handle* h);
+
+/* One separation round at x* (HOST pointer, num_var doubles) -- replaces the loop body
+ * src/model.jl:265-283: precompute! (src/separators.jl:111-116), isconstrsat (:120) for each
+ * i in nlconstr_ixs ascending, gencut -> linear_oa_cut (src/algorithms.jl:3-18), round_coefs
+ * (src/model.jl:200-207), _addcut's finiteness check and bound shift (src/model.jl:68-79).
+ * Returns KTN_NUMERIC_NONFINITE when a selected row had a non-finite coefficient; cuts of
+ * the selected rows BEFORE that row are still delivered (the reference adds them before
+ * it returns :Error), and *err_row receives the offending row (else -1). */
+int ktn_separate(ktn_handle* h, const double* xstar, int64_t* n_cuts, int64_t* nnz_cuts, int64_t* err_row);
+
+/* Unconditional cuts for the listed rows (ascending 0-based indices) -- replaces the gencut
+ * calls of loadproblem! on linear rows, the linear objective row and the initial vertex cut
+ * (src/model.jl:115-118,129,160-163) and boundroutine's per-row gencut.  round_coefs != 0
+ * applies src/model.jl:200-207 (the reference does so only for the vertex cut, :162). */
+int ktn_gencut_rows(ktn_handle* h, const double* x, const int64_t* rows, int64_t nrows, int round_coefs,
+                    int64_t* n_cuts, int64_t* nnz_cuts, int64_t* err_row);
+
+/* Download the cuts of the last ktn_separate / ktn_gencut_rows.  Cut c (ascending row order):
+ *   row_id[c]                      0-based constraint index
+ *   row_ptr[c] .. row_ptr[c+1]     its entries in col[] / val[]   (row_ptr has n_cuts+1 entries)
+ *   lo[c], hi[c]                   LP row bounds lb - b, ub - b   (src/model.jl:74-75)
+ *   g[c], viol[c]                  g_i(x*) and max(lb - g, g - ub)
+ * Any output pointer may be NULL to skip that array. */
+int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val,
+                   double* lo, double* hi, double* g, double* viol);
+
+/* All constraint values of the last round (sep.g, src/separators.jl:113) -- backs the
+ * per-row isconstrsat(sep, i, lb, ub, f_tol) compatibility hook (src/separators.jl:120). */
+int ktn_get_g(ktn_handle* h, double* g_out);
+/* eval_g at an arbitrary point, all loaded rows (debug / parity). */
+int ktn_eval_g(ktn_handle* h, const double* x, double* g_out);
+
+int ktn_timings_get(ktn_handle* h, ktn_timings* out);
+
+/* ---- device-resident round (benchmarks, GPU-side LP masters) ---- */
+/* Use an external CUDA stream (cudaStream_t cast to void*); NULL restores the library stream. */
+int ktn_set_stream(ktn_handle* h, void* cuda_stream);
+/* Enqueue one round on the stream with x* already in device memory; does not synchronise. */
+int ktn_separate_device_async(ktn_handle* h, const double* d_xstar);
+/* Wait for the last enqueued round and read its counts. */
+int ktn_sync_counts(ktn_handle* h, int64_t* n_cuts, int64_t* nnz_cuts, int64_t* err_row);
+/* Algorithmic bytes of one round (SURVEY.md section 8d formula) for the last synced round. */
+int64_t ktn_algorithmic_bytes(ktn_handle* h);
+
+/* ---- sharded operation: one handle per GPU / process, rows [row_begin,row_end) each ---- */
+/* 128-byte NCCL unique id, created on rank 0 and broadcast by the host's own plumbing. */
+int ktn_comm_unique_id(void* id128);
+int ktn_comm_init(ktn_handle* h, int32_t nranks, int32_t rank, const void* id128);
+/* Combine every rank's compacted cuts (rank-major = ascending row order) on every GPU over
+ * NCCL/NVLink; enqueued on the stream after the last round.  Totals are returned after a sync. */
+int ktn_allgather_cuts_async(ktn_handle* h);
+int ktn_sync_gathered(ktn_handle* h, int64_t* total_cuts, int64_t* total_nnz);
+int ktn_fetch_gathered(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val,
+                       double* lo, double* hi, double* g, double* viol);
+
+/* ---- deterministic synthetic instances (test / bench support) ----
+ * kind: 0 = sparse convex QCQP (config 2), 1 = log-sum-exp (config 3), 2 = SOC-like risk rows (config 4).
+ * Two-call protocol: call with op = NULL to get *n_nodes, then with caller buffers
+ * (expr_ptr: nrows+1, op/arg/val: n_nodes, lb/ub: nrows, flags: nrows, xstar: num_var).
+ * Rows [row_begin, row_begin+nrows) of the instance (num_var, seed) are produced; a row's
+ * content depends only on (seed, global row index), so shards agree with the whole. */
+int ktn_synth_rows(int32_t kind, uint64_t seed, int64_t num_var, int64_t row_begin, int64_t nrows,
+                   int64_t* n_nodes, int64_t* expr_ptr, int32_t* op, int32_t* arg, double* val,
+                   double* lb, double* ub, uint8_t* flags);
+int ktn_synth_point(int32_t kind, uint64_t seed, int64_t num_var, double* xstar);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KTN_H */

@@ -1,0 +1,7 @@
+"""katana.jl_b200 -- B200-native ECP separation round behind Katana.jl's separator API.
+
+Import as `katana_jl_b200` (the repo-root shim `katana_jl_b200.py` registers this
+directory, whose name is not a valid Python identifier, under that module name).
+"""
+from . import binding, expr  # noqa: F401
+from .binding import CutBatch, KtnError, KtnLibrary, WireRows, load_cuda_library  # noqa: F401

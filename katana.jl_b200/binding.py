@@ -1,0 +1,323 @@
+"""ctypes binding of the C ABI in include/ktn.h.
+
+The same binding drives the CUDA library (the product) and, from tests only, the CPU
+oracle: both export identical symbols.  `load_cuda_library()` is the only loader the
+product uses; it fails loudly when libktn.so is missing -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CUDA_LIB_PATH = os.path.join(_HERE, "libktn.so")
+
+# wire-format constants (include/ktn.h)
+OP_CONST, OP_VAR, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_NEG, OP_EXP, OP_LOG, OP_SQRT, OP_ABS = range(12)
+ROW_NL, ROW_DENSE = 1, 2
+KTN_OK, KTN_NUMERIC_NONFINITE = 0, 1
+SYNTH_QCQP, SYNTH_LSE, SYNTH_SOC = 0, 1, 2
+
+
+class KtnError(RuntimeError):
+    pass
+
+
+class ktn_options(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("f_tol", C.c_double),
+                ("cut_coef_rng", C.c_double), ("topk", C.c_int64), ("flags", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ktn_timings(C.Structure):
+    _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("exchange_ms", C.c_double),
+                ("d2h_ms", C.c_double), ("launches", C.c_int64), ("rounds", C.c_int64)]
+
+
+_P = C.c_void_p
+_SIGS = {
+    "ktn_create": (C.c_int, [C.POINTER(ktn_options), C.POINTER(_P)]),
+    "ktn_destroy": (None, [_P]),
+    "ktn_last_error": (C.c_char_p, [_P]),
+    "ktn_backend": (C.c_char_p, []),
+    "ktn_set_params": (C.c_int, [_P, C.c_double, C.c_double, C.c_int64]),
+    "ktn_load_begin": (C.c_int, [_P, C.c_int64, C.c_int64]),
+    "ktn_add_rows": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "ktn_load_end": (C.c_int, [_P]),
+    "ktn_set_bounds": (C.c_int, [_P, _P, _P]),
+    "ktn_jac_structure": (C.c_int, [_P, _P, _P]),
+    "ktn_num_rows": (C.c_int64, [_P]),
+    "ktn_jac_nnz": (C.c_int64, [_P]),
+    "ktn_separate": (C.c_int, [_P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ktn_gencut_rows": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ktn_fetch_cuts": (C.c_int, [_P] + [_P] * 8),
+    "ktn_get_g": (C.c_int, [_P, _P]),
+    "ktn_eval_g": (C.c_int, [_P, _P, _P]),
+    "ktn_timings_get": (C.c_int, [_P, C.POINTER(ktn_timings)]),
+    "ktn_set_stream": (C.c_int, [_P, _P]),
+    "ktn_separate_device_async": (C.c_int, [_P, _P]),
+    "ktn_sync_counts": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ktn_algorithmic_bytes": (C.c_int64, [_P]),
+    "ktn_comm_unique_id": (C.c_int, [_P]),
+    "ktn_comm_init": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "ktn_allgather_cuts_async": (C.c_int, [_P]),
+    "ktn_sync_gathered": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ktn_fetch_gathered": (C.c_int, [_P] + [_P] * 8),
+}
+# exported by the CUDA library only (test / bench support, include/ktn.h bottom)
+_SYNTH_SIGS = {
+    "ktn_synth_rows": (C.c_int, [C.c_int32, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int64)] + [_P] * 7),
+    "ktn_synth_point": (C.c_int, [C.c_int32, C.c_uint64, C.c_int64, _P]),
+}
+ABI_SYMBOLS = sorted(list(_SIGS) + list(_SYNTH_SIGS))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_P)
+
+
+class KtnLibrary:
+    """A loaded shared library exporting include/ktn.h."""
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise KtnError(f"shared library not found: {path} (run `python -c 'import __graft_entry__ as g; g.build()'`)")
+        self.path = path
+        self.dll = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(self.dll, name)
+            fn.restype, fn.argtypes = res, args
+        self.has_synth = hasattr(self.dll, "ktn_synth_rows")
+        if self.has_synth:
+            for name, (res, args) in _SYNTH_SIGS.items():
+                fn = getattr(self.dll, name)
+                fn.restype, fn.argtypes = res, args
+        self.backend = self.dll.ktn_backend().decode()
+
+    def create(self, f_tol=1e-6, cut_coef_rng=1e9, topk=0, device=-1):
+        return Handle(self, f_tol, cut_coef_rng, topk, device)
+
+    # ---- synthetic instances ----
+    def synth_rows(self, kind, seed, num_var, row_begin, nrows):
+        """Rows [row_begin, row_begin+nrows) of a synthetic instance as a WireRows batch."""
+        nn = C.c_int64(0)
+        rc = self.dll.ktn_synth_rows(kind, seed, num_var, row_begin, nrows, C.byref(nn), None, None, None, None, None, None, None)
+        if rc != 0:
+            raise KtnError(f"ktn_synth_rows failed: {rc}")
+        n = nn.value
+        w = WireRows(np.empty(nrows + 1, np.int64), np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float64),
+                     np.empty(nrows, np.float64), np.empty(nrows, np.float64), np.empty(nrows, np.uint8))
+        rc = self.dll.ktn_synth_rows(kind, seed, num_var, row_begin, nrows, C.byref(nn), _ptr(w.expr_ptr), _ptr(w.op), _ptr(w.arg),
+                                     _ptr(w.val), _ptr(w.lb), _ptr(w.ub), _ptr(w.flags))
+        if rc != 0:
+            raise KtnError(f"ktn_synth_rows failed: {rc}")
+        return w
+
+    def synth_point(self, kind, seed, num_var):
+        x = np.empty(num_var, np.float64)
+        rc = self.dll.ktn_synth_point(kind, seed, num_var, _ptr(x))
+        if rc != 0:
+            raise KtnError(f"ktn_synth_point failed: {rc}")
+        return x
+
+
+@dataclass
+class WireRows:
+    """A batch of rows in the expression wire format of include/ktn.h."""
+    expr_ptr: np.ndarray  # int64 [nrows+1]
+    op: np.ndarray        # int32 [n_nodes]
+    arg: np.ndarray       # int32 [n_nodes]
+    val: np.ndarray       # float64 [n_nodes]
+    lb: np.ndarray        # float64 [nrows]
+    ub: np.ndarray        # float64 [nrows]
+    flags: np.ndarray     # uint8 [nrows]
+
+    @property
+    def nrows(self):
+        return len(self.lb)
+
+
+@dataclass
+class CutBatch:
+    """Cuts of one round in CSR form (ascending row order); see ktn_fetch_cuts."""
+    status: int
+    err_row: int
+    row_id: np.ndarray
+    row_ptr: np.ndarray
+    col: np.ndarray
+    val: np.ndarray
+    lo: np.ndarray
+    hi: np.ndarray
+    g: np.ndarray
+    viol: np.ndarray
+
+    @property
+    def n_cuts(self):
+        return len(self.row_id)
+
+    def row(self, c):
+        s, e = self.row_ptr[c], self.row_ptr[c + 1]
+        return self.col[s:e], self.val[s:e]
+
+
+class Handle:
+    def __init__(self, lib, f_tol, cut_coef_rng, topk, device):
+        self.lib, self.dll = lib, lib.dll
+        o = ktn_options(C.sizeof(ktn_options), device, f_tol, cut_coef_rng, topk, 0, 0)
+        p = _P()
+        rc = self.dll.ktn_create(C.byref(o), C.byref(p))
+        if rc != 0 or not p:
+            raise KtnError(f"ktn_create failed with status {rc} ({lib.backend})")
+        self.h = p
+        self.num_var = self.num_constr = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.dll.ktn_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what, numeric_ok=False):
+        if rc < 0 or (rc > 0 and not numeric_ok):
+            msg = self.dll.ktn_last_error(self.h)
+            raise KtnError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+        return rc
+
+    def set_params(self, f_tol, cut_coef_rng, topk=0):
+        self._ck(self.dll.ktn_set_params(self.h, f_tol, cut_coef_rng, topk), "ktn_set_params")
+
+    # ---- loading ----
+    def load_begin(self, num_var, num_constr):
+        self.num_var, self.num_constr = int(num_var), int(num_constr)
+        self._ck(self.dll.ktn_load_begin(self.h, num_var, num_constr), "ktn_load_begin")
+
+    def add_rows(self, first_row, w):
+        for a, t in ((w.expr_ptr, np.int64), (w.op, np.int32), (w.arg, np.int32), (w.val, np.float64),
+                     (w.lb, np.float64), (w.ub, np.float64), (w.flags, np.uint8)):
+            assert a.dtype == t and a.flags.c_contiguous
+        self._ck(self.dll.ktn_add_rows(self.h, first_row, w.nrows, _ptr(w.expr_ptr), _ptr(w.op), _ptr(w.arg), _ptr(w.val),
+                                       _ptr(w.lb), _ptr(w.ub), _ptr(w.flags)), "ktn_add_rows")
+
+    def load_end(self):
+        self._ck(self.dll.ktn_load_end(self.h), "ktn_load_end")
+
+    def load(self, num_var, w):
+        self.load_begin(num_var, w.nrows)
+        self.add_rows(0, w)
+        self.load_end()
+
+    def set_bounds(self, lb, ub):
+        lb = np.ascontiguousarray(lb, np.float64); ub = np.ascontiguousarray(ub, np.float64)
+        assert len(lb) == self.num_constr == len(ub)
+        self._ck(self.dll.ktn_set_bounds(self.h, _ptr(lb), _ptr(ub)), "ktn_set_bounds")
+
+    def jac_structure(self):
+        m = self.dll.ktn_num_rows(self.h)
+        rp = np.empty(m + 1, np.int64)
+        self._ck(self.dll.ktn_jac_structure(self.h, _ptr(rp), None), "ktn_jac_structure")
+        cols = np.empty(int(rp[-1]), np.int32)
+        self._ck(self.dll.ktn_jac_structure(self.h, _ptr(rp), _ptr(cols)), "ktn_jac_structure")
+        return rp, cols
+
+    # ---- rounds ----
+    def _fetch(self, status, nc, nz, err, gathered=False):
+        b = CutBatch(status, err, np.empty(nc, np.int64), np.empty(nc + 1, np.int64), np.empty(nz, np.int32), np.empty(nz, np.float64),
+                     np.empty(nc, np.float64), np.empty(nc, np.float64), np.empty(nc, np.float64), np.empty(nc, np.float64))
+        fn = self.dll.ktn_fetch_gathered if gathered else self.dll.ktn_fetch_cuts
+        self._ck(fn(self.h, _ptr(b.row_id), _ptr(b.row_ptr), _ptr(b.col), _ptr(b.val), _ptr(b.lo), _ptr(b.hi), _ptr(b.g), _ptr(b.viol)),
+                 "ktn_fetch_cuts")
+        return b
+
+    def separate(self, xstar, fetch=True):
+        x = np.ascontiguousarray(xstar, np.float64)
+        assert len(x) == self.num_var
+        nc, nz, er = C.c_int64(), C.c_int64(), C.c_int64()
+        st = self._ck(self.dll.ktn_separate(self.h, _ptr(x), C.byref(nc), C.byref(nz), C.byref(er)), "ktn_separate", numeric_ok=True)
+        if not fetch:
+            return st, nc.value, nz.value, er.value
+        return self._fetch(st, nc.value, nz.value, er.value)
+
+    def gencut_rows(self, x, rows, round_coefs=False):
+        x = np.ascontiguousarray(x, np.float64); rows = np.ascontiguousarray(rows, np.int64)
+        assert len(x) == self.num_var
+        nc, nz, er = C.c_int64(), C.c_int64(), C.c_int64()
+        st = self._ck(self.dll.ktn_gencut_rows(self.h, _ptr(x), _ptr(rows), len(rows), int(bool(round_coefs)),
+                                               C.byref(nc), C.byref(nz), C.byref(er)), "ktn_gencut_rows", numeric_ok=True)
+        return self._fetch(st, nc.value, nz.value, er.value)
+
+    def get_g(self):
+        g = np.empty(self.num_constr, np.float64)
+        self._ck(self.dll.ktn_get_g(self.h, _ptr(g)), "ktn_get_g")
+        return g
+
+    def eval_g(self, x):
+        x = np.ascontiguousarray(x, np.float64); g = np.empty(self.num_constr, np.float64)
+        self._ck(self.dll.ktn_eval_g(self.h, _ptr(x), _ptr(g)), "ktn_eval_g")
+        return g
+
+    def timings(self):
+        t = ktn_timings()
+        self._ck(self.dll.ktn_timings_get(self.h, C.byref(t)), "ktn_timings_get")
+        return {k: getattr(t, k) for k, _ in ktn_timings._fields_}
+
+    def algorithmic_bytes(self):
+        return int(self.dll.ktn_algorithmic_bytes(self.h))
+
+    # ---- device-resident / sharded ----
+    def set_stream(self, stream_ptr):
+        self._ck(self.dll.ktn_set_stream(self.h, _P(stream_ptr)), "ktn_set_stream")
+
+    def separate_device_async(self, d_x_ptr):
+        self._ck(self.dll.ktn_separate_device_async(self.h, _P(d_x_ptr)), "ktn_separate_device_async")
+
+    def sync_counts(self):
+        nc, nz, er = C.c_int64(), C.c_int64(), C.c_int64()
+        st = self._ck(self.dll.ktn_sync_counts(self.h, C.byref(nc), C.byref(nz), C.byref(er)), "ktn_sync_counts", numeric_ok=True)
+        return st, nc.value, nz.value, er.value
+
+    def fetch_last(self):
+        st, nc, nz, er = self.sync_counts()
+        return self._fetch(st, nc, nz, er)
+
+    def comm_init(self, nranks, rank, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._ck(self.dll.ktn_comm_init(self.h, nranks, rank, buf), "ktn_comm_init")
+
+    def allgather_cuts_async(self):
+        self._ck(self.dll.ktn_allgather_cuts_async(self.h), "ktn_allgather_cuts_async")
+
+    def sync_gathered(self):
+        nc, nz = C.c_int64(), C.c_int64()
+        self._ck(self.dll.ktn_sync_gathered(self.h, C.byref(nc), C.byref(nz)), "ktn_sync_gathered")
+        return nc.value, nz.value
+
+    def fetch_gathered(self):
+        nc, nz = self.sync_gathered()
+        return self._fetch(0, nc, nz, -1, gathered=True)
+
+
+def comm_unique_id(lib):
+    buf = C.create_string_buffer(128)
+    rc = lib.dll.ktn_comm_unique_id(buf)
+    if rc != 0:
+        raise KtnError(f"ktn_comm_unique_id failed: {rc}")
+    return buf.raw
+
+
+_cuda_lib = None
+
+
+def load_cuda_library():
+    """The product's only backend.  Raises if libktn.so has not been built; never falls back to a CPU path."""
+    global _cuda_lib
+    if _cuda_lib is None:
+        lib = KtnLibrary(CUDA_LIB_PATH)
+        if lib.backend != "cuda":
+            raise KtnError(f"{CUDA_LIB_PATH} is not the CUDA backend (got {lib.backend!r})")
+        _cuda_lib = lib
+    return _cuda_lib

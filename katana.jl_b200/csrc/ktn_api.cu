@@ -1,0 +1,361 @@
+// ktn_api.cu -- the C ABI of include/ktn.h on top of the tape compiler and the sm_100a kernels.
+// Host-side counterpart of KatanaFirstOrderSeparator's state (reference src/separators.jl:58-77):
+// the handle owns the compiled problem, device buffers, a stream and pinned staging.
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/ktn.h"
+#include "ktn_compile.h"
+#include "ktn_kernels.cuh"
+
+#define KTN_LANE_LIMIT 1536u   // max per-lane shared-memory bytes of a regular (shared-memory staged) shape
+
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    cudaError_t alloc(size_t n) { release(); bytes = n; if (n == 0) return cudaSuccess; return cudaMalloc(&p, n); }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct ktn_handle {
+    ktn_options opt;
+    int device = 0, num_sms = 0, max_smem = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    KtnProblem prob;
+    bool loading = false, loaded = false, round_pending = false, have_round = false;
+    DevBuf chunks, shapes, prog, blob, chunk_rows, chunk_lb, chunk_ub, jac_ptr, jac_col, row_lb, row_ub;
+    DevBuf x, force, g_row, b_row, sel, stage_val, big_scratch, ticket, blk_cnt, blk_nnz, counts;
+    DevBuf out_row, out_ptr, out_col, out_val, out_lo, out_hi, out_g, out_viol;
+    double* h_x = nullptr;                 // pinned
+    unsigned long long* h_counts = nullptr;  // pinned [8]
+    int64_t n_cuts = 0, nnz_cuts = 0, err_row = -1;
+    uint32_t warp_bytes = 0, blob_cap = 0;
+    ktn_timings tm;
+    std::string err;
+    // sharding (ktn_comm.cpp)
+    void* comm = nullptr; int nranks = 1, rank = 0;
+};
+
+static int fail(ktn_handle* h, int code, const char* fmt, ...) {
+    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+#define CK(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(h, KTN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+
+extern "C" const char* ktn_backend(void) { return "cuda"; }
+extern "C" const char* ktn_last_error(ktn_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+static void free_problem(ktn_handle* h) {
+    DevBuf* all[] = {&h->chunks, &h->shapes, &h->prog, &h->blob, &h->chunk_rows, &h->chunk_lb, &h->chunk_ub, &h->jac_ptr, &h->jac_col,
+                     &h->row_lb, &h->row_ub, &h->x, &h->force, &h->g_row, &h->b_row, &h->sel, &h->stage_val, &h->big_scratch,
+                     &h->blk_cnt, &h->blk_nnz, &h->out_row, &h->out_ptr, &h->out_col, &h->out_val, &h->out_lo, &h->out_hi, &h->out_g, &h->out_viol};
+    for (DevBuf* b : all) b->release();
+    if (h->h_x) { cudaFreeHost(h->h_x); h->h_x = nullptr; }
+    h->prob = KtnProblem();
+    h->loaded = h->loading = h->round_pending = h->have_round = false;
+    h->n_cuts = h->nnz_cuts = 0; h->err_row = -1;
+}
+
+extern "C" int ktn_create(const ktn_options* o, ktn_handle** out) {
+    if (!out) return KTN_ERR_USAGE;
+    *out = nullptr;
+    ktn_handle* h = new (std::nothrow) ktn_handle();
+    if (!h) return KTN_ERR_NOMEM;
+    memset(&h->opt, 0, sizeof h->opt); memset(&h->tm, 0, sizeof h->tm);
+    h->opt.f_tol = 1e-6; h->opt.cut_coef_rng = 1e9; h->opt.device = -1;
+    if (o) memcpy(&h->opt, o, (size_t)o->struct_size < sizeof(ktn_options) ? (size_t)o->struct_size : sizeof(ktn_options));
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {   // no CPU fallback: the product path fails loudly without a GPU
+        fprintf(stderr, "libktn: no CUDA device available (%s); this library has no CPU path\n", cudaGetErrorString(e));
+        delete h; return KTN_ERR_CUDA;
+    }
+    if (h->opt.device >= 0) { if (cudaSetDevice(h->opt.device) != cudaSuccess) { delete h; return KTN_ERR_CUDA; } }
+    cudaGetDevice(&h->device);
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
+    cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
+    h->stream = h->own_stream;
+    cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
+    if (cudaMallocHost(&h->h_counts, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
+    if (h->ticket.alloc(16) != cudaSuccess || h->counts.alloc(8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
+    cudaMemset(h->ticket.p, 0, 16); cudaMemset(h->counts.p, 0, 64);
+    if (ktn_kernels_configure(h->max_smem) != cudaSuccess) { fprintf(stderr, "libktn: kernel configuration failed (is this an sm_100a device?)\n"); delete h; return KTN_ERR_CUDA; }
+    *out = h;
+    return KTN_OK;
+}
+
+extern "C" void ktn_destroy(ktn_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_problem(h);
+    h->ticket.release(); h->counts.release();
+    if (h->h_counts) cudaFreeHost(h->h_counts);
+    if (h->ev0) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3); }
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+extern "C" int ktn_set_params(ktn_handle* h, double f_tol, double rng, int64_t topk) {
+    if (!h) return KTN_ERR_USAGE;
+    if (topk != 0) return fail(h, KTN_ERR_UNSUPPORTED, "topk > 0 is not implemented in the CUDA backend yet");
+    h->opt.f_tol = f_tol; h->opt.cut_coef_rng = rng; h->opt.topk = topk;
+    return KTN_OK;
+}
+
+extern "C" int ktn_load_begin(ktn_handle* h, int64_t num_var, int64_t num_constr) {
+    if (!h || num_var < 0 || num_constr < 0 || num_constr > 0x7fffff00ll || num_var > 0x7fffff00ll) return fail(h, KTN_ERR_USAGE, "bad problem sizes");
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_problem(h);
+    h->prob.reset(num_var, num_constr);
+    h->loading = true;
+    return KTN_OK;
+}
+
+extern "C" int ktn_add_rows(ktn_handle* h, int64_t first_row, int64_t nrows, const int64_t* eptr, const int32_t* op,
+                            const int32_t* arg, const double* val, const double* lb, const double* ub, const uint8_t* flags) {
+    if (!h || !h->loading) return fail(h, KTN_ERR_USAGE, "ktn_add_rows before ktn_load_begin");
+    int rc = h->prob.add_rows(first_row, nrows, eptr, op, arg, val, lb, ub, flags);
+    if (rc != KTN_OK) h->err = h->prob.err;
+    return rc;
+}
+
+template <class T> static cudaError_t upload(DevBuf& b, const std::vector<T>& v, size_t extra = 0) {
+    cudaError_t e = b.alloc((v.size() + extra) * sizeof(T) + 16);
+    if (e != cudaSuccess) return e;
+    if (!v.empty()) e = cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+extern "C" int ktn_load_end(ktn_handle* h) {
+    if (!h || !h->loading) return fail(h, KTN_ERR_USAGE, "ktn_load_end before ktn_load_begin");
+    cudaSetDevice(h->device);
+    KtnProblem& P = h->prob;
+    int64_t sigma = 8192;
+    if (const char* s = getenv("KTN_SIGMA")) sigma = atoll(s);
+    int rc = P.finalize(sigma, KTN_LANE_LIMIT);
+    if (rc != KTN_OK) { h->err = P.err; return rc; }
+    // shared-memory plan of the regular kernel
+    uint32_t blob_cap = 0, scratch_cap = 0;
+    for (const KtnShapeDesc& s : P.shapes) if (!(s.flags & KTN_SH_BIG)) {
+        uint32_t sec_col = (8u * s.n_const * 32u + 15u) & ~15u, sec_ord = (sec_col + 4u * s.n_uniq * 32u + 15u) & ~15u;
+        uint32_t bytes = (sec_ord + s.order_bytes * s.n_uniq * 32u + 15u) & ~15u;
+        if (bytes > blob_cap) blob_cap = bytes;
+        if (s.n_scratch * 256u > scratch_cap) scratch_cap = s.n_scratch * 256u;
+    }
+    blob_cap = (blob_cap + 127u) & ~127u;
+    h->blob_cap = blob_cap; h->warp_bytes = 128u + blob_cap + ((scratch_cap + 127u) & ~127u);
+    const size_t m = (size_t)P.num_constr, N = (size_t)P.jac_ptr[m];
+    CK(h, upload(h->chunks, P.chunks)); CK(h, upload(h->shapes, P.shapes)); CK(h, upload(h->prog, P.prog));
+    CK(h, upload(h->blob, P.blob)); CK(h, upload(h->chunk_rows, P.chunk_rows));
+    CK(h, upload(h->chunk_lb, P.chunk_lb)); CK(h, upload(h->chunk_ub, P.chunk_ub));
+    CK(h, upload(h->jac_ptr, P.jac_ptr)); CK(h, upload(h->jac_col, P.jac_col));
+    CK(h, upload(h->row_lb, P.lb)); CK(h, upload(h->row_ub, P.ub));
+    CK(h, h->x.alloc(8 * ((size_t)P.num_var + 1))); CK(h, h->force.alloc(m + 16));
+    CK(h, h->g_row.alloc(8 * (m + 1))); CK(h, h->b_row.alloc(8 * (m + 1))); CK(h, h->sel.alloc(4 * (m + 1)));
+    CK(h, cudaMemset(h->sel.p, 0, 4 * (m + 1))); CK(h, cudaMemset(h->g_row.p, 0, 8 * (m + 1)));
+    CK(h, h->stage_val.alloc(8 * (N + 1))); CK(h, h->big_scratch.alloc(8 * (P.big_scratch_doubles + 1)));
+    const size_t nblk = (m + 1023) / 1024 + 1;
+    CK(h, h->blk_cnt.alloc(4 * nblk)); CK(h, h->blk_nnz.alloc(8 * nblk));
+    CK(h, h->out_row.alloc(4 * (m + 1))); CK(h, h->out_ptr.alloc(8 * (m + 2))); CK(h, h->out_col.alloc(4 * (N + 1))); CK(h, h->out_val.alloc(8 * (N + 1)));
+    CK(h, h->out_lo.alloc(8 * (m + 1))); CK(h, h->out_hi.alloc(8 * (m + 1))); CK(h, h->out_g.alloc(8 * (m + 1))); CK(h, h->out_viol.alloc(8 * (m + 1)));
+    CK(h, cudaMallocHost(&h->h_x, 8 * ((size_t)P.num_var + 1)));
+    // the packed blob lives on the device now
+    std::vector<uint8_t>().swap(P.blob);
+    h->loading = false; h->loaded = true;
+    return KTN_OK;
+}
+
+extern "C" int ktn_set_bounds(ktn_handle* h, const double* lb, const double* ub) {
+    if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
+    cudaSetDevice(h->device);
+    KtnProblem& P = h->prob;
+    P.lb.assign(lb, lb + P.num_constr); P.ub.assign(ub, ub + P.num_constr);
+    P.repack_bounds();
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaMemcpy(h->row_lb.p, P.lb.data(), 8 * P.lb.size(), cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(h->row_ub.p, P.ub.data(), 8 * P.ub.size(), cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(h->chunk_lb.p, P.chunk_lb.data(), 8 * P.chunk_lb.size(), cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(h->chunk_ub.p, P.chunk_ub.data(), 8 * P.chunk_ub.size(), cudaMemcpyHostToDevice));
+    return KTN_OK;
+}
+
+extern "C" int64_t ktn_num_rows(ktn_handle* h) { return h ? h->prob.rows_loaded : 0; }
+extern "C" int64_t ktn_jac_nnz(ktn_handle* h) { return (h && !h->prob.jac_ptr.empty()) ? h->prob.jac_ptr.back() : 0; }
+extern "C" int ktn_jac_structure(ktn_handle* h, int64_t* row_ptr, int32_t* cols) {
+    if (!h || h->prob.jac_ptr.empty()) return fail(h, KTN_ERR_USAGE, "no problem");
+    if (row_ptr) memcpy(row_ptr, h->prob.jac_ptr.data(), 8 * h->prob.jac_ptr.size());
+    if (cols) memcpy(cols, h->prob.jac_col.data(), 4 * h->prob.jac_col.size());
+    return KTN_OK;
+}
+
+static KtnRoundParams make_params(ktn_handle* h, const double* d_x, int mode, int do_round) {
+    KtnRoundParams p; memset(&p, 0, sizeof p);
+    p.chunks = h->chunks.as<KtnChunkDesc>(); p.shapes = h->shapes.as<KtnShapeDesc>(); p.prog = h->prog.as<KtnIns>();
+    p.blob = h->blob.as<uint8_t>(); p.chunk_rows = h->chunk_rows.as<int32_t>();
+    p.chunk_lb = h->chunk_lb.as<double>(); p.chunk_ub = h->chunk_ub.as<double>();
+    p.jac_ptr = h->jac_ptr.as<int64_t>(); p.jac_col = h->jac_col.as<int32_t>();
+    p.row_lb = h->row_lb.as<double>(); p.row_ub = h->row_ub.as<double>();
+    p.x = d_x; p.force = h->force.as<uint8_t>();
+    p.f_tol = h->opt.f_tol; p.rng = h->opt.cut_coef_rng; p.mode = mode; p.do_round = do_round;
+    p.num_var = h->prob.num_var; p.num_rows = h->prob.num_constr;
+    p.warp_bytes = h->warp_bytes; p.blob_cap = h->blob_cap;
+    p.g_row = h->g_row.as<double>(); p.b_row = h->b_row.as<double>(); p.sel = h->sel.as<uint32_t>();
+    p.stage_val = h->stage_val.as<double>(); p.big_scratch = h->big_scratch.as<double>(); p.ticket = h->ticket.as<unsigned int>();
+    p.blk_cnt = h->blk_cnt.as<uint32_t>(); p.blk_nnz = h->blk_nnz.as<unsigned long long>(); p.counts = h->counts.as<unsigned long long>();
+    p.out_row = h->out_row.as<int32_t>(); p.out_ptr = h->out_ptr.as<int64_t>(); p.out_col = h->out_col.as<int32_t>(); p.out_val = h->out_val.as<double>();
+    p.out_lo = h->out_lo.as<double>(); p.out_hi = h->out_hi.as<double>(); p.out_g = h->out_g.as<double>(); p.out_viol = h->out_viol.as<double>();
+    return p;
+}
+
+static int enqueue_round(ktn_handle* h, const double* d_x, int mode, int do_round) {
+    KtnRoundParams p = make_params(h, d_x, mode, do_round);
+    cudaError_t e = cudaSuccess;
+    CK(h, cudaEventRecord(h->ev1, h->stream));
+    int n = ktn_launch_round(p, h->prob.n_regular_chunks, (uint32_t)h->prob.chunks.size(), h->num_sms, h->max_smem, h->stream, &e);
+    h->tm.launches += n;
+    if (e != cudaSuccess) return fail(h, KTN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    CK(h, cudaEventRecord(h->ev2, h->stream));
+    CK(h, cudaMemcpyAsync(h->h_counts, h->counts.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    h->round_pending = true; h->tm.rounds++;
+    return KTN_OK;
+}
+
+static int finish_round(ktn_handle* h, int64_t* n_cuts, int64_t* nnz, int64_t* err_row) {
+    if (!h->round_pending) return fail(h, KTN_ERR_USAGE, "no round is pending");
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->round_pending = false; h->have_round = true;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev1, h->ev2) == cudaSuccess) h->tm.kernel_ms = ms;
+    h->n_cuts = (int64_t)h->h_counts[0]; h->nnz_cuts = (int64_t)h->h_counts[1];
+    h->err_row = h->h_counts[2] == ~0ull ? -1 : (int64_t)h->h_counts[2] - 1;
+    if (n_cuts) *n_cuts = h->n_cuts;
+    if (nnz) *nnz = h->nnz_cuts;
+    if (err_row) *err_row = h->err_row;
+    return h->err_row >= 0 ? KTN_NUMERIC_NONFINITE : KTN_OK;
+}
+
+static int upload_x(ktn_handle* h, const double* x) {
+    memcpy(h->h_x, x, 8 * (size_t)h->prob.num_var);
+    CK(h, cudaEventRecord(h->ev0, h->stream));
+    CK(h, cudaMemcpyAsync(h->x.p, h->h_x, 8 * (size_t)h->prob.num_var, cudaMemcpyHostToDevice, h->stream));
+    return KTN_OK;
+}
+
+extern "C" int ktn_separate(ktn_handle* h, const double* xstar, int64_t* n_cuts, int64_t* nnz, int64_t* err_row) {
+    if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
+    cudaSetDevice(h->device);
+    int rc = upload_x(h, xstar); if (rc) return rc;
+    rc = enqueue_round(h, h->x.as<double>(), KTN_MODE_SEPARATE, 1); if (rc) return rc;
+    rc = finish_round(h, n_cuts, nnz, err_row);
+    float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->tm.h2d_ms = ms;
+    return rc;
+}
+
+extern "C" int ktn_gencut_rows(ktn_handle* h, const double* x, const int64_t* rows, int64_t nrows, int do_round,
+                               int64_t* n_cuts, int64_t* nnz, int64_t* err_row) {
+    if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
+    cudaSetDevice(h->device);
+    const int64_t m = h->prob.num_constr;
+    std::vector<uint8_t> mask((size_t)m + 1, 0);
+    for (int64_t j = 0; j < nrows; ++j) {
+        if (rows[j] < 0 || rows[j] >= m || (j && rows[j] <= rows[j - 1])) return fail(h, KTN_ERR_USAGE, "rows must be ascending and in range");
+        mask[rows[j]] = 1;
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaMemcpy(h->force.p, mask.data(), (size_t)m, cudaMemcpyHostToDevice));
+    int rc = upload_x(h, x); if (rc) return rc;
+    rc = enqueue_round(h, h->x.as<double>(), KTN_MODE_FORCE, do_round ? 1 : 0); if (rc) return rc;
+    return finish_round(h, n_cuts, nnz, err_row);
+}
+
+extern "C" int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val,
+                              double* lo, double* hi, double* g, double* viol) {
+    if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
+    if (h->round_pending) { int rc = finish_round(h, nullptr, nullptr, nullptr); if (rc < 0) return rc; }
+    cudaSetDevice(h->device);
+    const size_t nc = (size_t)h->n_cuts, nz = (size_t)h->nnz_cuts;
+    CK(h, cudaEventRecord(h->ev2, h->stream));
+    if (row_id && nc) {
+        std::vector<int32_t> tmp(nc);
+        CK(h, cudaMemcpyAsync(tmp.data(), h->out_row.p, 4 * nc, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        for (size_t i = 0; i < nc; ++i) row_id[i] = tmp[i];
+    }
+    if (row_ptr) { if (nc) CK(h, cudaMemcpyAsync(row_ptr, h->out_ptr.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream)); }
+    if (col && nz) CK(h, cudaMemcpyAsync(col, h->out_col.p, 4 * nz, cudaMemcpyDeviceToHost, h->stream));
+    if (val && nz) CK(h, cudaMemcpyAsync(val, h->out_val.p, 8 * nz, cudaMemcpyDeviceToHost, h->stream));
+    if (lo && nc) CK(h, cudaMemcpyAsync(lo, h->out_lo.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+    if (hi && nc) CK(h, cudaMemcpyAsync(hi, h->out_hi.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+    if (g && nc) CK(h, cudaMemcpyAsync(g, h->out_g.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+    if (viol && nc) CK(h, cudaMemcpyAsync(viol, h->out_viol.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaEventRecord(h->ev3, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (row_ptr) row_ptr[nc] = (int64_t)nz;   // the device array ends at the untruncated total
+    float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev2, h->ev3) == cudaSuccess) h->tm.d2h_ms = ms;
+    return KTN_OK;
+}
+
+extern "C" int ktn_get_g(ktn_handle* h, double* g_out) {
+    if (!h || !h->have_round) return fail(h, KTN_ERR_USAGE, "no round has run");
+    cudaSetDevice(h->device);
+    CK(h, cudaMemcpyAsync(g_out, h->g_row.p, 8 * (size_t)h->prob.num_constr, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return KTN_OK;
+}
+
+extern "C" int ktn_eval_g(ktn_handle* h, const double* x, double* g_out) {
+    if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
+    cudaSetDevice(h->device);
+    int rc = upload_x(h, x); if (rc) return rc;
+    KtnRoundParams p = make_params(h, h->x.as<double>(), KTN_MODE_SEPARATE, 0);
+    cudaError_t e = cudaSuccess;
+    h->tm.launches += ktn_launch_eval(p, h->prob.n_regular_chunks, (uint32_t)h->prob.chunks.size(), h->num_sms, h->max_smem, h->stream, &e);
+    if (e != cudaSuccess) return fail(h, KTN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    CK(h, cudaMemcpyAsync(g_out, h->g_row.p, 8 * (size_t)h->prob.num_constr, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return KTN_OK;
+}
+
+extern "C" int ktn_timings_get(ktn_handle* h, ktn_timings* out) { if (!h || !out) return KTN_ERR_USAGE; *out = h->tm; return KTN_OK; }
+
+extern "C" int ktn_set_stream(ktn_handle* h, void* s) {
+    if (!h) return KTN_ERR_USAGE;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return KTN_OK;
+}
+
+extern "C" int ktn_separate_device_async(ktn_handle* h, const double* d_x) {
+    if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
+    cudaSetDevice(h->device);
+    return enqueue_round(h, d_x, KTN_MODE_SEPARATE, 1);
+}
+
+extern "C" int ktn_sync_counts(ktn_handle* h, int64_t* n_cuts, int64_t* nnz, int64_t* err_row) {
+    if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
+    cudaSetDevice(h->device);
+    return finish_round(h, n_cuts, nnz, err_row);
+}
+
+extern "C" int64_t ktn_algorithmic_bytes(ktn_handle* h) {
+    if (!h || !h->loaded) return 0;
+    return h->prob.alg_bytes_static + 12 * h->nnz_cuts + 28 * h->n_cuts;
+}
+
+// ---- sharded operation: see ktn_comm.cpp (NCCL is loaded lazily so the library works without it) ----
+extern "C" int ktn_comm_unique_id(void* id128) { (void)id128; return KTN_ERR_UNSUPPORTED; }
+extern "C" int ktn_comm_init(ktn_handle* h, int32_t nranks, int32_t rank, const void* id) { (void)nranks; (void)rank; (void)id; return fail(h, KTN_ERR_UNSUPPORTED, "sharded operation not built yet"); }
+extern "C" int ktn_allgather_cuts_async(ktn_handle* h) { return fail(h, KTN_ERR_UNSUPPORTED, "sharded operation not built yet"); }
+extern "C" int ktn_sync_gathered(ktn_handle* h, int64_t* a, int64_t* b) { (void)a; (void)b; return fail(h, KTN_ERR_UNSUPPORTED, "sharded operation not built yet"); }
+extern "C" int ktn_fetch_gathered(ktn_handle* h, int64_t* a, int64_t* b, int32_t* c, double* d, double* e, double* f, double* g, double* v) {
+    (void)a; (void)b; (void)c; (void)d; (void)e; (void)f; (void)g; (void)v; return fail(h, KTN_ERR_UNSUPPORTED, "sharded operation not built yet"); }

@@ -1,0 +1,430 @@
+// ktn_compile.cpp -- tape compiler: prefix expression arrays -> shape programs + packed chunks.
+//
+// Replaces, for the GPU path, what MathProgBase.initialize(oracle, [:Grad,:Jac]) and
+// jac_structure do for the reference separator (src/separators.jl:88-100): build one tape per
+// constraint and the per-row Jacobian column lists.  Here rows with the same expression
+// STRUCTURE share one program ("shape"); constants and column indices become per-row data
+// packed structure-of-arrays in warp-sized chunks (SELL-32-sigma: rows are bucketed by shape
+// inside windows of sigma consecutive rows).
+//
+// The generated programs perform exactly the arithmetic of the ReverseDiffSparse-style
+// interpreter restated in oracle/ktn_oracle.c (forward_row / reverse_row), in the same order.
+#include "ktn_compile.h"
+#include <algorithm>
+#include <cstring>
+#include <cstdio>
+#include "../../include/ktn.h"
+
+namespace {
+
+struct Src { uint8_t kind; uint32_t idx; };
+
+struct TNode {
+    int op, nc, send, parent;
+    bool has_var = false, is_leaf = false, need_value = false, has_val = false;
+    Src val{KTN_K_NONE, 0};  // where the node's forward value can be read (leaf, or persisted slot)
+    int pslot = -1;          // saved partial d parent / d this (products, divisions, general powers)
+    int expclass = 0;        // CONST exponent of POW: 1 -> ==1.0, 2 -> ==2.0 (structural)
+    int cslot = -1, uslot = -1;
+};
+
+static int arity(int op) {
+    switch (op) {
+        case KTN_OP_CONST: case KTN_OP_VAR: return 0;
+        case KTN_OP_ADD: case KTN_OP_MUL: return -1;
+        case KTN_OP_SUB: case KTN_OP_DIV: case KTN_OP_POW: return 2;
+        case KTN_OP_NEG: case KTN_OP_EXP: case KTN_OP_LOG: case KTN_OP_SQRT: case KTN_OP_ABS: return 1;
+        default: return -2;
+    }
+}
+
+struct ShapeCompiler {
+    std::vector<TNode>& t;
+    std::vector<KtnIns> code;
+    uint32_t nu, next_slot;
+    std::vector<uint32_t> temp_slot;  // spilled temporaries by depth (depth >= 2)
+    int temp_depth = 0;
+    std::vector<char> jseen;
+    std::string err;
+
+    ShapeCompiler(std::vector<TNode>& nodes, uint32_t n_uniq) : t(nodes), nu(n_uniq), next_slot(2 * n_uniq), jseen(n_uniq, 0) {}
+
+    void emit(uint8_t op, Src s = Src{KTN_K_NONE, 0}, uint16_t n = 0) { code.push_back(KtnIns{op, s.kind, n, s.idx}); }
+    Src push_temp() {
+        int d = temp_depth++;
+        if (d == 0) return Src{KTN_K_R1, 0};
+        if (d == 1) return Src{KTN_K_R2, 0};
+        if ((size_t)(d - 2) >= temp_slot.size()) temp_slot.push_back(next_slot++);
+        return Src{KTN_K_S, temp_slot[d - 2]};
+    }
+    void pop_temp() { --temp_depth; }
+    Src new_slot() { return Src{KTN_K_S, next_slot++}; }
+    std::vector<int> children(int k) const { std::vector<int> c; int j = k + 1; for (int i = 0; i < t[k].nc; ++i) { c.push_back(j); j = t[j].send; } return c; }
+
+    // ---- analysis: which forward values the reverse sweep reads ----
+    void analyse() {
+        for (int k = (int)t.size() - 1; k >= 0; --k) {
+            TNode& n = t[k];
+            if (n.op == KTN_OP_VAR) n.has_var = true;
+            else if (n.op != KTN_OP_CONST) for (int c : children(k)) n.has_var = n.has_var || t[c].has_var;
+        }
+        for (int k = 0; k < (int)t.size(); ++k) {
+            TNode& n = t[k];
+            if (!n.has_var || n.is_leaf) continue;
+            std::vector<int> ch = children(k);
+            switch (n.op) {
+                case KTN_OP_EXP: case KTN_OP_SQRT: n.need_value = true; break;
+                case KTN_OP_LOG: case KTN_OP_ABS: t[ch[0]].need_value = true; break;
+                case KTN_OP_POW: if (t[ch[1]].expclass == 2 && t[ch[0]].has_var) t[ch[0]].need_value = true; break;
+                case KTN_OP_MUL:
+                    if (n.nc == 2) { if (t[ch[0]].has_var) t[ch[1]].need_value = true; if (t[ch[1]].has_var) t[ch[0]].need_value = true; }
+                    else if (n.nc > 2) for (int c : ch) t[c].need_value = true;  // all factors are re-read for the partials
+                    break;
+                default: break;
+            }
+        }
+    }
+
+    // ---- forward ----
+    void persist(int k) {  // after the node's value is in acc
+        TNode& n = t[k];
+        if (n.need_value && !n.has_val) { n.val = new_slot(); n.has_val = true; emit(KF_STORE, n.val); }
+    }
+    // acc = acc (op) value(c) for a commutative op, value(c) possibly complex
+    void combine_commutative(uint8_t fop, int c) {
+        if (t[c].is_leaf) { emit(fop, t[c].val); return; }
+        Src T = push_temp(); emit(KF_STORE, T);
+        gen_fwd(c);
+        emit(fop, T); pop_temp();
+    }
+    void gen_binary(int k, uint8_t fop, uint8_t rop) {  // acc = L (op) R, non-commutative
+        std::vector<int> ch = children(k); int L = ch[0], R = ch[1];
+        if (t[R].is_leaf) { gen_fwd(L); emit(fop, t[R].val); }
+        else if (t[L].is_leaf) { gen_fwd(R); emit(rop, t[L].val); }
+        else if (t[L].need_value) { gen_fwd(L); gen_fwd(R); emit(rop, t[L].val); }
+        else { gen_fwd(L); Src T = push_temp(); emit(KF_STORE, T); gen_fwd(R); emit(rop, T); pop_temp(); }
+    }
+    void gen_fwd(int k) {
+        TNode& n = t[k];
+        if (!err.empty()) return;
+        if (n.is_leaf) { emit(KF_LOAD, n.val); return; }
+        std::vector<int> ch = children(k);
+        switch (n.op) {
+            case KTN_OP_ADD:
+                gen_fwd(ch[0]); emit(KF_ADDZ);
+                for (size_t i = 1; i < ch.size(); ++i) combine_commutative(KF_ADD, ch[i]);
+                break;
+            case KTN_OP_SUB: gen_binary(k, KF_SUB, KF_RSUB); break;
+            case KTN_OP_MUL:
+                if (n.nc <= 2 || !n.has_var) {
+                    gen_fwd(ch[0]);
+                    for (size_t i = 1; i < ch.size(); ++i) combine_commutative(KF_MUL, ch[i]);
+                } else {
+                    // every factor is persisted (need_value), then p and the "all but one" partials
+                    for (int c : ch) if (!t[c].is_leaf) gen_fwd(c);
+                    emit(KF_LOAD, t[ch[0]].val);
+                    for (size_t i = 1; i < ch.size(); ++i) emit(KF_MUL, t[ch[i]].val);
+                    Src P = new_slot(); emit(KF_STORE, P);
+                    Src A = new_slot();
+                    for (size_t i = 0; i < ch.size(); ++i) {
+                        if (!t[ch[i]].has_var) continue;
+                        // alt = product of the others (only needed in lanes where p == 0)
+                        uint16_t nalt = (uint16_t)ch.size();  // LOAD + (nc-2) MUL + STORE
+                        emit(KF_SKIPNZ, P, nalt);
+                        bool first = true;
+                        for (size_t j = 0; j < ch.size(); ++j) { if (j == i) continue; emit(first ? KF_LOAD : KF_MUL, t[ch[j]].val); first = false; }
+                        emit(KF_STORE, A);
+                        emit(KF_LOAD, P); emit(KF_FDIV, t[ch[i]].val); emit(KF_LDAUX, A); emit(KF_SELZ, P);
+                        Src ps = new_slot(); t[ch[i]].pslot = (int)ps.idx; emit(KF_STORE, ps);
+                    }
+                    emit(KF_LOAD, P);
+                }
+                break;
+            case KTN_OP_DIV: {
+                gen_binary(k, KF_DIV, KF_RDIV);
+                if (t[ch[0]].has_var) { Src s = new_slot(); t[ch[0]].pslot = (int)s.idx; emit(KF_STAUX, Src{KTN_K_NONE, s.idx}); }
+                if (t[ch[1]].has_var) { Src s = new_slot(); t[ch[1]].pslot = (int)s.idx; emit(KF_DENP, Src{KTN_K_NONE, s.idx}); }
+                break; }
+            case KTN_OP_POW: {
+                int B = ch[0], E = ch[1];
+                if (t[E].expclass == 2) { gen_fwd(B); emit(KF_POW2); }
+                else if (t[E].expclass == 1) { gen_fwd(B); }
+                else {
+                    if (t[E].is_leaf) { gen_fwd(B); emit(KF_LDAUX, t[E].val); }
+                    else { gen_fwd(E); Src T = push_temp(); emit(KF_STORE, T); gen_fwd(B); emit(KF_LDAUX, T); pop_temp(); }
+                    if (t[B].has_var) { Src s = new_slot(); t[B].pslot = (int)s.idx; emit(KF_POWPB, Src{KTN_K_NONE, s.idx}); }
+                    if (t[E].has_var) { Src s = new_slot(); t[E].pslot = (int)s.idx; emit(KF_POWPE, Src{KTN_K_NONE, s.idx}); }
+                    emit(KF_POWG);
+                }
+                break; }
+            case KTN_OP_NEG: gen_fwd(ch[0]); emit(KF_NEG); break;
+            case KTN_OP_EXP: gen_fwd(ch[0]); emit(KF_EXP); break;
+            case KTN_OP_LOG: gen_fwd(ch[0]); emit(KF_LOG); break;
+            case KTN_OP_SQRT: gen_fwd(ch[0]); emit(KF_SQRT); break;
+            case KTN_OP_ABS: gen_fwd(ch[0]); emit(KF_ABS); break;
+            default: err = "unknown op in gen_fwd";
+        }
+        persist(k);
+    }
+
+    // ---- reverse: acc holds adj(k) on entry ----
+    void gen_rev(int k) {
+        TNode& n = t[k];
+        if (n.op == KTN_OP_VAR) {
+            emit(jseen[n.uslot] ? KR_JACC : KR_JSET, Src{KTN_K_NONE, (uint32_t)n.uslot});
+            jseen[n.uslot] = 1; return;
+        }
+        if (!n.has_var) return;
+        std::vector<int> ch = children(k), H;
+        for (int c : ch) if (t[c].has_var) H.push_back(c);
+        Src T{KTN_K_NONE, 0};
+        if (H.size() > 1) { T = push_temp(); emit(KF_STORE, T); }
+        for (size_t j = 0; j < H.size(); ++j) {
+            int c = H[j];
+            if (j > 0) emit(KF_LOAD, T);
+            size_t ci = 0; while (ch[ci] != c) ++ci;
+            switch (n.op) {
+                case KTN_OP_ADD: break;
+                case KTN_OP_SUB: if (ci == 1) emit(KR_NEG); break;
+                case KTN_OP_NEG: emit(KR_NEG); break;
+                case KTN_OP_MUL:
+                    if (n.nc == 2) emit(KR_MUL, t[ch[1 - ci]].val);
+                    else if (n.nc > 2) emit(KR_MUL, Src{KTN_K_S, (uint32_t)t[c].pslot});
+                    break;
+                case KTN_OP_DIV: emit(KR_MUL, Src{KTN_K_S, (uint32_t)t[c].pslot}); break;
+                case KTN_OP_POW:
+                    if (t[ch[1]].expclass == 2) emit(KR_MUL2, t[ch[0]].val);
+                    else if (t[ch[1]].expclass == 1) {}
+                    else emit(KR_MUL, Src{KTN_K_S, (uint32_t)t[c].pslot});
+                    break;
+                case KTN_OP_EXP: emit(KR_MUL, n.val); break;
+                case KTN_OP_LOG: emit(KR_MULRCP, t[c].val); break;
+                case KTN_OP_SQRT: emit(KR_MULHRCP, n.val); break;
+                case KTN_OP_ABS: emit(KR_MULSGN, t[c].val); break;
+                default: err = "unknown op in gen_rev";
+            }
+            gen_rev(c);
+        }
+        if (H.size() > 1) pop_temp();
+    }
+};
+
+static uint64_t fnv1a(const uint8_t* p, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+static void put32(std::vector<uint8_t>& v, uint32_t x) { for (int i = 0; i < 4; ++i) v.push_back((uint8_t)(x >> (8 * i))); }
+static uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+void KtnProblem::reset(int64_t nvar, int64_t nconstr) {
+    *this = KtnProblem();
+    num_var = nvar; num_constr = nconstr;
+    lb.reserve(nconstr); ub.reserve(nconstr); flags.reserve(nconstr);
+    jac_ptr.assign(1, 0);
+    row_const_off.assign(1, 0); row_col_off.assign(1, 0);
+}
+
+int KtnProblem::add_rows(int64_t first_row, int64_t nrows, const int64_t* eptr, const int32_t* op, const int32_t* arg,
+                         const double* val, const double* lbv, const double* ubv, const uint8_t* fl) {
+    if (first_row != rows_loaded || first_row + nrows > num_constr) { err = "rows must be added in ascending order"; return KTN_ERR_USAGE; }
+    std::vector<TNode> t;
+    std::vector<uint8_t> sig;
+    std::vector<std::pair<int32_t, int32_t>> occ;  // (col, occurrence order)
+    std::vector<int> stk_node, stk_rem;
+    char msg[256];
+    for (int64_t r = 0; r < nrows; ++r) {
+        const int64_t row = first_row + r, b = eptr[r], n = eptr[r + 1] - b;
+        if (n <= 0) { snprintf(msg, sizeof msg, "row %lld has an empty expression", (long long)row); err = msg; return KTN_ERR_USAGE; }
+        if (n > 0x7fffff00) { err = "expression too long"; return KTN_ERR_USAGE; }
+        t.assign((size_t)n, TNode());
+        stk_node.clear(); stk_rem.clear();
+        uint32_t nconst_wire = 0;
+        for (int64_t k = 0; k < n; ++k) {
+            TNode& nd = t[k];
+            nd.op = op[b + k];
+            int a = arity(nd.op);
+            if (a == -2) { snprintf(msg, sizeof msg, "row %lld: unknown op %d", (long long)row, nd.op); err = msg; return KTN_ERR_USAGE; }
+            nd.nc = a == 0 ? 0 : arg[b + k];
+            if ((a > 0 && nd.nc != a) || (a == -1 && nd.nc < 1)) { snprintf(msg, sizeof msg, "row %lld: op %d has %d children", (long long)row, nd.op, nd.nc); err = msg; return KTN_ERR_USAGE; }
+            nd.is_leaf = a == 0;
+            if (nd.op == KTN_OP_CONST) ++nconst_wire;
+            if (nd.op == KTN_OP_VAR && (arg[b + k] < 0 || arg[b + k] >= num_var)) { snprintf(msg, sizeof msg, "row %lld: variable index out of range", (long long)row); err = msg; return KTN_ERR_USAGE; }
+            if (stk_node.empty()) { if (k != 0) { snprintf(msg, sizeof msg, "row %lld: more than one root", (long long)row); err = msg; return KTN_ERR_USAGE; } nd.parent = -1; }
+            else { nd.parent = stk_node.back(); if (--stk_rem.back() == 0) { stk_node.pop_back(); stk_rem.pop_back(); } }
+            if (nd.nc > 0) { stk_node.push_back((int)k); stk_rem.push_back(nd.nc); }
+        }
+        if (!stk_node.empty()) { snprintf(msg, sizeof msg, "row %lld: truncated expression", (long long)row); err = msg; return KTN_ERR_USAGE; }
+        for (int64_t k = n - 1; k >= 0; --k) { int c = (int)k + 1; for (int i = 0; i < t[k].nc; ++i) c = t[c].send; t[k].send = c; }
+        // structural exponent constants
+        for (int64_t k = 0; k < n; ++k) if (t[k].op == KTN_OP_POW) {
+            int e = t[k + 1].send;
+            if (t[e].op == KTN_OP_CONST) { double v = val[b + e]; t[e].expclass = v == 2.0 ? 2 : v == 1.0 ? 1 : 0; }
+        }
+        // unique variable slots in first-occurrence order
+        occ.clear();
+        for (int64_t k = 0; k < n; ++k) if (t[k].op == KTN_OP_VAR) occ.emplace_back(arg[b + k], (int32_t)k);
+        std::vector<std::pair<int32_t, int32_t>> byc = occ;
+        std::sort(byc.begin(), byc.end());
+        std::vector<std::pair<int32_t, int32_t>> firsts;  // (first node, col)
+        for (size_t i = 0; i < byc.size(); ++i) if (i == 0 || byc[i].first != byc[i - 1].first) firsts.emplace_back(byc[i].second, byc[i].first);
+        std::sort(firsts.begin(), firsts.end());
+        const uint32_t nu = (uint32_t)firsts.size();
+        // col -> slot via binary search on a sorted (col, slot) list
+        std::vector<std::pair<int32_t, int32_t>> col2slot(nu);
+        for (uint32_t s = 0; s < nu; ++s) col2slot[s] = {firsts[s].second, (int32_t)s};
+        std::sort(col2slot.begin(), col2slot.end());
+        uint32_t ncst = 0;
+        for (int64_t k = 0; k < n; ++k) {
+            if (t[k].op == KTN_OP_VAR) {
+                auto it = std::lower_bound(col2slot.begin(), col2slot.end(), std::make_pair(arg[b + k], (int32_t)-1));
+                t[k].uslot = it->second; t[k].val = Src{KTN_K_S, (uint32_t)t[k].uslot}; t[k].has_val = true;
+            } else if (t[k].op == KTN_OP_CONST && t[k].expclass == 0) {
+                t[k].cslot = (int)ncst++; t[k].val = Src{KTN_K_C, (uint32_t)t[k].cslot}; t[k].has_val = true;
+            }
+        }
+        // signature
+        sig.clear();
+        sig.push_back(fl[r] & (KTN_ROW_NL | KTN_ROW_DENSE));
+        for (int64_t k = 0; k < n; ++k) {
+            sig.push_back((uint8_t)t[k].op);
+            if (t[k].op == KTN_OP_VAR) put32(sig, (uint32_t)t[k].uslot);
+            else if (t[k].op == KTN_OP_CONST) sig.push_back((uint8_t)t[k].expclass);
+            else put32(sig, (uint32_t)t[k].nc);
+        }
+        uint64_t h = fnv1a(sig.data(), sig.size());
+        uint32_t sid = UINT32_MAX;
+        auto& cand = shape_by_hash[h];
+        for (uint32_t s : cand) if (shape_sig[s] == sig) { sid = s; break; }
+        if (sid == UINT32_MAX) {
+            ShapeCompiler sc(t, nu);
+            sc.analyse();
+            sc.gen_fwd(0);
+            uint32_t nfwd = (uint32_t)sc.code.size();
+            sc.temp_depth = 0;
+            sc.emit(KR_ONE);
+            sc.gen_rev(0);
+            sc.emit(K_END);
+            if (!sc.err.empty()) { err = sc.err; return KTN_ERR_USAGE; }
+            KtnShapeDesc sd; memset(&sd, 0, sizeof sd);
+            sd.prog_off = (uint32_t)prog.size(); sd.n_fwd = nfwd; sd.n_ins = (uint32_t)sc.code.size();
+            sd.n_uniq = nu; sd.n_const = ncst; sd.n_scratch = sc.next_slot;
+            sd.flags = ((fl[r] & KTN_ROW_NL) ? KTN_SH_NL : 0) | ((fl[r] & KTN_ROW_DENSE) ? (KTN_SH_DENSE | KTN_SH_BIG) : 0);
+            sd.order_bytes = nu <= 256 ? 1 : nu <= 65536 ? 2 : 4;
+            prog.insert(prog.end(), sc.code.begin(), sc.code.end());
+            sid = (uint32_t)shapes.size();
+            shapes.push_back(sd); shape_sig.push_back(sig); cand.push_back(sid);
+        }
+        // per-row data
+        row_shape.push_back(sid);
+        row_nconst_wire.push_back(nconst_wire);
+        for (int64_t k = 0; k < n; ++k) if (t[k].cslot >= 0) rd_const.push_back(val[b + k]);
+        row_const_off.push_back(rd_const.size());
+        for (uint32_t s = 0; s < nu; ++s) rd_col.push_back(firsts[s].second);
+        for (uint32_t p = 0; p < nu; ++p) rd_order.push_back((uint32_t)col2slot[p].second);
+        row_col_off.push_back(rd_col.size());
+        lb.push_back(lbv[r]); ub.push_back(ubv[r]); flags.push_back(fl[r]);
+        if (fl[r] & KTN_ROW_DENSE) { for (int64_t c = 0; c < num_var; ++c) jac_col.push_back((int32_t)c); }
+        else for (uint32_t p = 0; p < nu; ++p) jac_col.push_back(col2slot[p].first);
+        jac_ptr.push_back((int64_t)jac_col.size());
+    }
+    rows_loaded += nrows;
+    return KTN_OK;
+}
+
+void KtnProblem::repack_bounds() {
+    chunk_lb.assign(chunk_rows.size(), 0.0); chunk_ub.assign(chunk_rows.size(), 0.0);
+    for (size_t i = 0; i < chunk_rows.size(); ++i) if (chunk_rows[i] >= 0) { chunk_lb[i] = lb[chunk_rows[i]]; chunk_ub[i] = ub[chunk_rows[i]]; }
+}
+
+int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit) {
+    if (rows_loaded != num_constr) { err = "not all rows were loaded"; return KTN_ERR_USAGE; }
+    if (sigma < 32) sigma = 32;
+    // classify shapes
+    max_lane_bytes = 0;
+    for (auto& s : shapes) {
+        if (ktn_shape_lane_bytes(s) > lane_limit) s.flags |= KTN_SH_BIG;
+        if (!(s.flags & KTN_SH_BIG)) max_lane_bytes = std::max(max_lane_bytes, ktn_shape_lane_bytes(s));
+    }
+    chunks.clear(); blob.clear(); chunk_rows.clear(); big_scratch_doubles = 0;
+    std::vector<KtnChunkDesc> big;
+    std::vector<std::vector<int32_t>> big_rows;
+    std::vector<std::pair<uint32_t, int32_t>> win;  // (shape, row)
+    alg_bytes_static = 8 * num_var;
+    for (int64_t i = 0; i < num_constr; ++i) if (flags[i] & KTN_ROW_NL)
+        alg_bytes_static += 4 * (jac_ptr[i + 1] - jac_ptr[i]) + 8 * (int64_t)row_nconst_wire[i] + 16;
+
+    auto pack_chunk = [&](uint32_t sid, const int32_t* rows, int nr, bool isbig) {
+        const KtnShapeDesc& s = shapes[sid];
+        KtnChunkDesc cd; memset(&cd, 0, sizeof cd);
+        const uint32_t L = (isbig && nr == 1) ? 1u : 32u;
+        cd.shape = sid; cd.nrows = (uint16_t)nr; cd.stride = (uint16_t)L;
+        uint64_t off = align_up(blob.size(), 128);
+        uint64_t sec_c = 0, sec_col = align_up(sec_c + 8ull * s.n_const * L, 16), sec_ord = align_up(sec_col + 4ull * s.n_uniq * L, 16);
+        uint64_t bytes = align_up(sec_ord + (uint64_t)s.order_bytes * s.n_uniq * L, 16);
+        cd.blob_off = off; cd.blob_bytes = (uint32_t)bytes;
+        blob.resize(off + bytes, 0);
+        uint8_t* base = blob.data() + off;
+        for (uint32_t lane = 0; lane < L; ++lane) {
+            int32_t row = rows[lane < (uint32_t)nr ? lane : 0];  // idle lanes replay lane 0's (valid) data
+            const double* rc = rd_const.data() + row_const_off[row];
+            const int32_t* rcol = rd_col.data() + row_col_off[row];
+            const uint32_t* rord = rd_order.data() + row_col_off[row];
+            double* dc = (double*)(base + sec_c);
+            for (uint32_t c = 0; c < s.n_const; ++c) dc[(uint64_t)c * L + lane] = rc[c];
+            int32_t* dcol = (int32_t*)(base + sec_col);
+            for (uint32_t u = 0; u < s.n_uniq; ++u) dcol[(uint64_t)u * L + lane] = rcol[u];
+            uint8_t* dord = base + sec_ord;
+            for (uint32_t p = 0; p < s.n_uniq; ++p) {
+                uint64_t e = (uint64_t)p * L + lane;
+                if (s.order_bytes == 1) dord[e] = (uint8_t)rord[p];
+                else if (s.order_bytes == 2) ((uint16_t*)dord)[e] = (uint16_t)rord[p];
+                else ((uint32_t*)dord)[e] = rord[p];
+            }
+        }
+        return cd;
+    };
+
+    std::vector<int32_t> rowbuf;
+    for (int64_t w0 = 0; w0 < num_constr; w0 += sigma) {
+        int64_t w1 = std::min(num_constr, w0 + sigma);
+        win.clear();
+        for (int64_t i = w0; i < w1; ++i) win.emplace_back(row_shape[i], (int32_t)i);
+        std::stable_sort(win.begin(), win.end(), [](const std::pair<uint32_t, int32_t>& a, const std::pair<uint32_t, int32_t>& b) { return a.first < b.first; });
+        size_t i = 0;
+        while (i < win.size()) {
+            uint32_t sid = win[i].first; size_t j = i;
+            while (j < win.size() && win[j].first == sid) ++j;
+            bool isbig = shapes[sid].flags & KTN_SH_BIG;
+            for (size_t c0 = i; c0 < j; c0 += 32) {
+                int nr = (int)std::min<size_t>(32, j - c0);
+                rowbuf.clear();
+                for (int q = 0; q < nr; ++q) rowbuf.push_back(win[c0 + q].second);
+                KtnChunkDesc cd = pack_chunk(sid, rowbuf.data(), nr, isbig);
+                if (isbig) { big.push_back(cd); big_rows.push_back(rowbuf); }
+                else {
+                    cd.row_slot = (uint32_t)chunk_rows.size();
+                    for (int q = 0; q < 32; ++q) chunk_rows.push_back(q < nr ? rowbuf[q] : -1);
+                    chunks.push_back(cd);
+                }
+            }
+            i = j;
+        }
+    }
+    n_regular_chunks = (uint32_t)chunks.size();
+    for (size_t c = 0; c < big.size(); ++c) {
+        KtnChunkDesc cd = big[c];
+        cd.row_slot = (uint32_t)chunk_rows.size();
+        for (int q = 0; q < 32; ++q) chunk_rows.push_back(q < cd.nrows ? big_rows[c][q] : -1);
+        cd.scratch_off = big_scratch_doubles;
+        big_scratch_doubles += (uint64_t)shapes[cd.shape].n_scratch * cd.stride;
+        chunks.push_back(cd);
+    }
+    blob.resize(align_up(blob.size(), 128) + 128, 0);
+    repack_bounds();
+    // the ragged per-row staging is no longer needed
+    std::vector<double>().swap(rd_const); std::vector<int32_t>().swap(rd_col); std::vector<uint32_t>().swap(rd_order);
+    return KTN_OK;
+}

@@ -1,0 +1,53 @@
+// ktn_kernels.cuh -- launch interface of the sm_100a separation kernels (ktn_kernels.cu).
+#ifndef KTN_KERNELS_CUH
+#define KTN_KERNELS_CUH
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ktn_program.h"
+
+enum { KTN_MODE_SEPARATE = 0, KTN_MODE_FORCE = 1 };
+
+struct KtnRoundParams {
+    // compiled problem (device)
+    const KtnChunkDesc* chunks;
+    const KtnShapeDesc* shapes;
+    const KtnIns* prog;
+    const uint8_t* blob;
+    const int32_t* chunk_rows;
+    const double* chunk_lb;
+    const double* chunk_ub;
+    const int64_t* jac_ptr;    // row -> first entry of the row in the static Jacobian CSR (= staging layout)
+    const int32_t* jac_col;
+    const double* row_lb;
+    const double* row_ub;
+    // round inputs
+    const double* x;
+    const uint8_t* force;      // KTN_MODE_FORCE: per-row mask
+    double f_tol, rng;
+    int32_t mode, do_round;
+    int64_t num_var, num_rows;
+    uint32_t chunk_begin, chunk_end;   // chunk range this launch covers
+    uint32_t warp_bytes;               // shared-memory bytes per warp (regular kernel)
+    uint32_t blob_cap;                 // bytes reserved for the blob inside a warp's region
+    // round outputs
+    double* g_row;             // g_i(x*) for every evaluated row (sep.g)
+    double* b_row;             // cut constant of selected rows
+    uint32_t* sel;             // 0 = not selected, else nnz | KTN_SEL_ERRBIT
+    double* stage_val;         // cut coefficients in the static CSR layout
+    double* big_scratch;
+    unsigned int* ticket;      // dynamic chunk scheduler [0] regular, [1] big
+    // compaction
+    uint32_t* blk_cnt; unsigned long long* blk_nnz;   // per 1024-row block
+    unsigned long long* counts;   // [0] n_cuts [1] nnz [2] err_row+1 (0 = none) [3] n_cuts_total [4] nnz_total
+    int32_t* out_row; int64_t* out_ptr; int32_t* out_col; double* out_val;
+    double* out_lo; double* out_hi; double* out_g; double* out_viol;
+};
+
+// Launches the kernels of one round on `stream`; returns the number of kernels launched.
+int ktn_launch_round(const KtnRoundParams& p, uint32_t n_regular, uint32_t n_total_chunks, int num_sms,
+                     int max_smem_optin, cudaStream_t stream, cudaError_t* err);
+// forward evaluation only (ktn_eval_g): writes g_row for every row
+int ktn_launch_eval(const KtnRoundParams& p, uint32_t n_regular, uint32_t n_total_chunks, int num_sms,
+                    int max_smem_optin, cudaStream_t stream, cudaError_t* err);
+cudaError_t ktn_kernels_configure(int max_smem_optin);
+#endif

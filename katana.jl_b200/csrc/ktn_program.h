@@ -1,0 +1,97 @@
+// ktn_program.h -- the tape ISA shared by the host compiler (ktn_compile.cpp) and the
+// sm_100a interpreter (ktn_kernels.cu).
+//
+// A SHAPE is the structure of a constraint expression with constants and variable
+// indices abstracted away (reference: one ReverseDiffSparse node tape per constraint,
+// interpreted node by node at src/separators.jl:112-113).  All rows of a shape share one
+// straight-line PROGRAM for a per-lane accumulator machine; per-row data is packed
+// structure-of-arrays in CHUNKS of up to 32 rows so a warp runs 32 rows in lock step.
+//
+// Per-lane machine state
+//   acc          forward accumulator / reverse adjoint
+//   aux          second operand / by-product (reciprocal of a division)
+//   R1, R2       two temporaries (running sums, saved adjoints)
+//   C[c]         per-row constants               (chunk blob, read-only)
+//   S[s]         scratch slots: S[0..nu) = gathered x* values XV, S[nu..2nu) = Jacobian
+//                accumulators J, then saved forward values / partials / spilled temporaries
+// Arithmetic order is exactly the oracle's (oracle/ktn_oracle.c); no op is fused.
+#ifndef KTN_PROGRAM_H
+#define KTN_PROGRAM_H
+#include <stdint.h>
+
+struct KtnIns {
+    uint8_t op;
+    uint8_t kind;   // operand kind (KTN_K_*)
+    uint16_t n;     // small immediate (skip count)
+    uint32_t idx;   // operand index
+};
+
+enum { KTN_K_NONE = 0, KTN_K_C = 1, KTN_K_S = 2, KTN_K_R1 = 3, KTN_K_R2 = 4 };
+
+enum {
+    // ---- forward: acc machine ----
+    KF_LOAD = 0,   // acc = src
+    KF_ADD,        // acc = acc + src
+    KF_ADDZ,       // acc = 0.0 + acc            (n-ary sum starts from zero(T))
+    KF_SUB,        // acc = acc - src
+    KF_RSUB,       // acc = src - acc
+    KF_MUL,        // acc = acc * src
+    KF_DIV,        // aux = 1/src;  acc = acc * aux      (numerator in acc)
+    KF_RDIV,       // aux = 1/acc;  acc = src * aux      (denominator in acc)
+    KF_FDIV,       // acc = acc / src                   (true division: n-ary product partials)
+    KF_POW2,       // acc = acc * acc
+    KF_NEG, KF_EXP, KF_LOG, KF_SQRT, KF_ABS,
+    KF_STORE,      // dst(kind, idx) = acc      kind in {S, R1, R2}
+    KF_LDAUX,      // aux = src
+    KF_STAUX,      // S[idx] = aux
+    KF_DENP,       // S[idx] = (-acc) * aux             (d/d denominator after KF_DIV / KF_RDIV)
+    KF_POWG,       // acc = pow(acc, aux)
+    KF_POWPB,      // S[idx] = aux * pow(acc, aux - 1)  (d/d base; before KF_POWG)
+    KF_POWPE,      // S[idx] = pow(acc, aux) * log(acc) (d/d exponent; before KF_POWG)
+    KF_SELZ,       // acc = (src == 0) ? aux : acc
+    KF_SKIPNZ,     // if no lane of the warp has src == 0: skip the next n instructions
+    // ---- reverse: acc holds the adjoint; revmul(a, p) = (a == 0 && !finite(p)) ? a : a * p ----
+    KR_ONE,        // acc = 1.0
+    KR_MUL,        // acc = revmul(acc, src)
+    KR_NEG,        // acc = revmul(acc, -1.0) = -acc
+    KR_MUL2,       // acc = revmul(acc, 2.0 * src)
+    KR_MULRCP,     // acc = revmul(acc, 1.0 / src)
+    KR_MULHRCP,    // acc = revmul(acc, 0.5 / src)
+    KR_MULSGN,     // acc = revmul(acc, src >= 0 ? 1.0 : -1.0)
+    KR_JSET,       // J[idx] = 0.0 + acc
+    KR_JACC,       // J[idx] = J[idx] + acc
+    K_END,
+    K__COUNT
+};
+
+// shape flags
+enum { KTN_SH_NL = 1, KTN_SH_DENSE = 2, KTN_SH_BIG = 4 };
+
+struct KtnShapeDesc {
+    uint32_t prog_off;     // first instruction in the program array
+    uint32_t n_fwd;        // forward instructions (then the reverse part follows)
+    uint32_t n_ins;        // total instructions
+    uint32_t n_uniq;       // unique variables = Jacobian entries of a (non-dense) row
+    uint32_t n_const;      // per-row constants
+    uint32_t n_scratch;    // scratch slots (incl. XV and J)
+    uint32_t flags;        // KTN_SH_*
+    uint32_t order_bytes;  // bytes per `order` entry: 1 (n_uniq <= 256), 2 or 4
+    // byte offsets of the blob sections of one chunk (lane stride L rows):
+    //   consts: n_const * L doubles | cols: n_uniq * L int32 | order: n_uniq * L * order_bytes
+    uint32_t pad[4];
+};
+
+struct KtnChunkDesc {
+    uint64_t blob_off;     // byte offset of the chunk's blob (16-byte aligned)
+    uint64_t scratch_off;  // BIG chunks: offset in doubles into the global scratch arena
+    uint32_t shape;
+    uint32_t blob_bytes;   // multiple of 16
+    uint16_t nrows;        // valid lanes
+    uint16_t stride;       // lane stride L of the SoA sections (32 for regular chunks)
+    uint32_t row_slot;     // index of the chunk's first lane in chunk_rows[] (= chunk * 32)
+};
+
+// per-row result flags written by the round kernel
+#define KTN_SEL_ERRBIT 0x40000000u
+
+#endif

@@ -1,0 +1,145 @@
+// ktn_emu.cpp -- TEST-ONLY host emulator of the CUDA round kernels.
+// Runs the SAME compiled artefacts (shape programs, packed chunk blobs, sort orders) that the
+// sm_100a kernels consume, lane by lane on the CPU, through the same interpreter core
+// (csrc/ktn_interp.h).  It lets the CPU test-suite check the tape compiler and the chunk packing
+// against the oracle without a GPU.  It is not part of the product and is never shipped in libktn.so.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/ktn.h"
+#include "../../katana.jl_b200/csrc/ktn_compile.h"
+#include "../../katana.jl_b200/csrc/ktn_interp.h"
+
+struct ktn_handle {
+    ktn_options opt; KtnProblem prob; bool loaded = false, have_round = false;
+    std::vector<double> g_row, b_row, stage_val; std::vector<uint32_t> sel;
+    std::vector<int64_t> c_row, c_ptr; std::vector<int32_t> c_col; std::vector<double> c_val, c_lo, c_hi, c_g, c_viol;
+    int64_t err_row = -1; std::string err;
+};
+extern "C" {
+const char* ktn_backend(void) { return "emu"; }
+const char* ktn_last_error(ktn_handle* h) { return h ? h->err.c_str() : "null"; }
+int ktn_create(const ktn_options* o, ktn_handle** out) { ktn_handle* h = new ktn_handle(); h->opt = *o; *out = h; return 0; }
+void ktn_destroy(ktn_handle* h) { delete h; }
+int ktn_set_params(ktn_handle* h, double f, double r, int64_t k) { h->opt.f_tol = f; h->opt.cut_coef_rng = r; h->opt.topk = k; return 0; }
+int ktn_load_begin(ktn_handle* h, int64_t n, int64_t m) { h->prob.reset(n, m); h->loaded = false; return 0; }
+int ktn_add_rows(ktn_handle* h, int64_t first, int64_t nrows, const int64_t* ep, const int32_t* op, const int32_t* arg, const double* val,
+                 const double* lb, const double* ub, const uint8_t* fl) {
+    int rc = h->prob.add_rows(first, nrows, ep, op, arg, val, lb, ub, fl); if (rc) h->err = h->prob.err; return rc; }
+int ktn_load_end(ktn_handle* h) {
+    int64_t sigma = 8192; if (const char* s = getenv("KTN_SIGMA")) sigma = atoll(s);
+    uint32_t limit = 1536; if (const char* s = getenv("KTN_EMU_LANE_LIMIT")) limit = (uint32_t)atoi(s);
+    int rc = h->prob.finalize(sigma, limit); if (rc) { h->err = h->prob.err; return rc; }
+    size_t m = (size_t)h->prob.num_constr;
+    h->g_row.assign(m, 0.0); h->b_row.assign(m, 0.0); h->sel.assign(m, 0u); h->stage_val.assign((size_t)h->prob.jac_ptr[m], 0.0);
+    h->loaded = true; return 0; }
+int ktn_set_bounds(ktn_handle* h, const double* lb, const double* ub) { h->prob.lb.assign(lb, lb + h->prob.num_constr); h->prob.ub.assign(ub, ub + h->prob.num_constr); h->prob.repack_bounds(); return 0; }
+int64_t ktn_num_rows(ktn_handle* h) { return h->prob.rows_loaded; }
+int64_t ktn_jac_nnz(ktn_handle* h) { return h->prob.jac_ptr.back(); }
+int ktn_jac_structure(ktn_handle* h, int64_t* rp, int32_t* cols) {
+    if (rp) memcpy(rp, h->prob.jac_ptr.data(), 8 * h->prob.jac_ptr.size());
+    if (cols) memcpy(cols, h->prob.jac_col.data(), 4 * h->prob.jac_col.size()); return 0; }
+}
+
+static uint32_t ord_at(const uint8_t* ord, uint32_t ob, size_t e) { return ob == 1 ? ord[e] : ob == 2 ? ((const uint16_t*)ord)[e] : ((const uint32_t*)ord)[e]; }
+
+// mode 0 = separate, 1 = force(mask), 2 = eval only
+static void run_chunks(ktn_handle* h, const double* x, int mode, const std::vector<uint8_t>& force, int do_round) {
+    KtnProblem& P = h->prob;
+    std::vector<double> S;
+    for (size_t c = 0; c < P.chunks.size(); ++c) {
+        const KtnChunkDesc& cd = P.chunks[c]; const KtnShapeDesc& sd = P.shapes[cd.shape];
+        const uint32_t L = cd.stride, nu = sd.n_uniq;
+        const uint8_t* blob = P.blob.data() + cd.blob_off;
+        const size_t sec_col = ((size_t)8 * sd.n_const * L + 15) & ~(size_t)15, sec_ord = (sec_col + (size_t)4 * nu * L + 15) & ~(size_t)15;
+        const int32_t* cols = (const int32_t*)(blob + sec_col); const uint8_t* ord = blob + sec_ord;
+        S.assign((size_t)sd.n_scratch * L, 0.0);
+        for (uint32_t lane = 0; lane < cd.nrows; ++lane) {
+            const int32_t row = P.chunk_rows[cd.row_slot + lane];
+            if (mode == 0 && !(sd.flags & KTN_SH_NL)) { h->sel[row] = 0; continue; }
+            for (uint32_t u = 0; u < nu; ++u) S[(size_t)u * L + lane] = x[cols[(size_t)u * L + lane]];
+            GlobalMem m{(const double*)blob, S.data(), lane, L};
+            const KtnIns* prog = P.prog.data() + sd.prog_off;
+            const double g = run_program(prog, 0, sd.n_fwd, m, nu, 0u);
+            h->g_row[row] = g;
+            if (mode == 2) continue;
+            const double lb = P.chunk_lb[cd.row_slot + lane], ub = P.chunk_ub[cd.row_slot + lane];
+            bool selected = mode == 1 ? force[row] != 0 : !((g >= lb - h->opt.f_tol) && (g <= ub + h->opt.f_tol));
+            if (!selected) { h->sel[row] = 0; continue; }
+            run_program(prog, sd.n_fwd, sd.n_ins, m, nu, 0u);
+            const int64_t base = P.jac_ptr[row];
+            if (!(sd.flags & KTN_SH_DENSE)) {
+                double b = g, mx = 0.0;
+                for (uint32_t q = 0; q < nu; ++q) { uint32_t u = ord_at(ord, sd.order_bytes, (size_t)q * L + lane); double jv = S[(size_t)(nu + u) * L + lane], xv = S[(size_t)u * L + lane]; b = b + (-xv) * jv; mx = q == 0 ? jv : ktn_jlmax(mx, jv); }
+                bool bad = false;
+                for (uint32_t q = 0; q < nu; ++q) { uint32_t u = ord_at(ord, sd.order_bytes, (size_t)q * L + lane); double jv = S[(size_t)(nu + u) * L + lane]; if (do_round && jv + h->opt.cut_coef_rng < mx) jv = 0.0; bad = bad || !ktn_isfinite(jv); h->stage_val[base + q] = jv; }
+                h->b_row[row] = b; h->sel[row] = nu | (bad ? KTN_SEL_ERRBIT : 0u);
+            } else {
+                const int64_t n = P.num_var; double* out = h->stage_val.data() + base;
+                for (int64_t j = 0; j < n; ++j) out[j] = 0.0;
+                for (uint32_t u = 0; u < nu; ++u) out[cols[(size_t)u * L + lane]] = S[(size_t)(nu + u) * L + lane];
+                double b = g, mx = -ktn_inf();
+                for (int64_t j = 0; j < n; ++j) { b = b + (-x[j]) * out[j]; mx = ktn_jlmax(mx, out[j]); }
+                bool bad = false;
+                for (int64_t j = 0; j < n; ++j) { double jv = out[j]; if (do_round && jv + h->opt.cut_coef_rng < mx) jv = 0.0; bad = bad || !ktn_isfinite(jv); out[j] = jv; }
+                h->b_row[row] = b; h->sel[row] = (uint32_t)n | (bad ? KTN_SEL_ERRBIT : 0u);
+            }
+        }
+    }
+}
+
+static int compact(ktn_handle* h, int64_t* n_cuts, int64_t* nnz, int64_t* err_row) {
+    KtnProblem& P = h->prob;
+    h->c_row.clear(); h->c_ptr.assign(1, 0); h->c_col.clear(); h->c_val.clear(); h->c_lo.clear(); h->c_hi.clear(); h->c_g.clear(); h->c_viol.clear();
+    h->err_row = -1;
+    for (int64_t i = 0; i < P.num_constr; ++i) {
+        uint32_t s = h->sel[i]; if (!s) continue;
+        if (s & KTN_SEL_ERRBIT) { h->err_row = i; break; }
+        const int64_t base = P.jac_ptr[i];
+        for (uint32_t q = 0; q < s; ++q) { h->c_col.push_back(P.jac_col[base + q]); h->c_val.push_back(h->stage_val[base + q]); }
+        h->c_row.push_back(i); h->c_ptr.push_back((int64_t)h->c_col.size());
+        const double g = h->g_row[i], b = h->b_row[i];
+        h->c_lo.push_back(P.lb[i] - b); h->c_hi.push_back(P.ub[i] - b); h->c_g.push_back(g);
+        const double v1 = P.lb[i] - g, v2 = g - P.ub[i]; h->c_viol.push_back(g == g ? (v1 > v2 ? v1 : v2) : g);
+    }
+    if (n_cuts) *n_cuts = (int64_t)h->c_row.size();
+    if (nnz) *nnz = (int64_t)h->c_col.size();
+    if (err_row) *err_row = h->err_row;
+    h->have_round = true;
+    return h->err_row >= 0 ? KTN_NUMERIC_NONFINITE : KTN_OK;
+}
+
+extern "C" {
+int ktn_separate(ktn_handle* h, const double* x, int64_t* nc, int64_t* nz, int64_t* er) { run_chunks(h, x, 0, {}, 1); return compact(h, nc, nz, er); }
+int ktn_gencut_rows(ktn_handle* h, const double* x, const int64_t* rows, int64_t nrows, int do_round, int64_t* nc, int64_t* nz, int64_t* er) {
+    std::vector<uint8_t> mask((size_t)h->prob.num_constr, 0); for (int64_t j = 0; j < nrows; ++j) mask[rows[j]] = 1;
+    run_chunks(h, x, 1, mask, do_round); return compact(h, nc, nz, er); }
+int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val, double* lo, double* hi, double* g, double* viol) {
+    size_t nc = h->c_row.size(), nz = h->c_col.size();
+    if (row_id && nc) memcpy(row_id, h->c_row.data(), 8 * nc);
+    if (row_ptr) memcpy(row_ptr, h->c_ptr.data(), 8 * (nc + 1));
+    if (col && nz) memcpy(col, h->c_col.data(), 4 * nz);
+    if (val && nz) memcpy(val, h->c_val.data(), 8 * nz);
+    if (lo && nc) memcpy(lo, h->c_lo.data(), 8 * nc);
+    if (hi && nc) memcpy(hi, h->c_hi.data(), 8 * nc);
+    if (g && nc) memcpy(g, h->c_g.data(), 8 * nc);
+    if (viol && nc) memcpy(viol, h->c_viol.data(), 8 * nc);
+    return 0; }
+int ktn_get_g(ktn_handle* h, double* g) { memcpy(g, h->g_row.data(), 8 * h->g_row.size()); return 0; }
+int ktn_eval_g(ktn_handle* h, const double* x, double* g) { run_chunks(h, x, 2, {}, 0); memcpy(g, h->g_row.data(), 8 * h->g_row.size()); return 0; }
+int ktn_timings_get(ktn_handle*, ktn_timings* t) { memset(t, 0, sizeof *t); return 0; }
+int64_t ktn_algorithmic_bytes(ktn_handle* h) { return h->prob.alg_bytes_static + 12 * (int64_t)h->c_col.size() + 28 * (int64_t)h->c_row.size(); }
+// number of shapes / chunks, for tests of the packing
+int64_t ktn_emu_num_shapes(ktn_handle* h) { return (int64_t)h->prob.shapes.size(); }
+int64_t ktn_emu_num_chunks(ktn_handle* h) { return (int64_t)h->prob.chunks.size(); }
+int64_t ktn_emu_num_big_chunks(ktn_handle* h) { return (int64_t)h->prob.chunks.size() - h->prob.n_regular_chunks; }
+int ktn_set_stream(ktn_handle*, void*) { return KTN_ERR_UNSUPPORTED; }
+int ktn_separate_device_async(ktn_handle*, const double*) { return KTN_ERR_UNSUPPORTED; }
+int ktn_sync_counts(ktn_handle*, int64_t*, int64_t*, int64_t*) { return KTN_ERR_UNSUPPORTED; }
+int ktn_comm_unique_id(void*) { return KTN_ERR_UNSUPPORTED; }
+int ktn_comm_init(ktn_handle*, int32_t, int32_t, const void*) { return KTN_ERR_UNSUPPORTED; }
+int ktn_allgather_cuts_async(ktn_handle*) { return KTN_ERR_UNSUPPORTED; }
+int ktn_sync_gathered(ktn_handle*, int64_t*, int64_t*) { return KTN_ERR_UNSUPPORTED; }
+int ktn_fetch_gathered(ktn_handle*, int64_t*, int64_t*, int32_t*, double*, double*, double*, double*, double*) { return KTN_ERR_UNSUPPORTED; }
+}
