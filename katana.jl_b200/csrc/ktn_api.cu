@@ -29,12 +29,12 @@ struct ktn_handle {
     KtnProblem prob;
     bool loading = false, loaded = false, round_pending = false, have_round = false;
     DevBuf chunks, shapes, prog, blob, chunk_rows, chunk_lb, chunk_ub, jac_ptr, jac_col, row_lb, row_ub;
-    DevBuf x, force, g_row, b_row, sel, stage_val, big_scratch, ticket, blk_cnt, blk_nnz, counts;
+    DevBuf x, force, g_row, b_row, sel, stage_val, big_scratch, ticket, st_flag, st_cnt, st_nnz, counts, table;
     DevBuf out_row, out_ptr, out_col, out_val, out_lo, out_hi, out_g, out_viol;
     double* h_x = nullptr;                 // pinned
     unsigned long long* h_counts = nullptr;  // pinned [8]
     int64_t n_cuts = 0, nnz_cuts = 0, err_row = -1;
-    uint32_t warp_bytes = 0, blob_cap = 0;
+    uint32_t warp_bytes = 0, blob_cap = 0, table_bytes = 0, table_prog_off = 0, epoch = 0;
     ktn_timings tm;
     std::string err;
     // sharding (ktn_comm.cpp)
@@ -54,7 +54,7 @@ extern "C" const char* ktn_last_error(ktn_handle* h) { return h ? h->err.c_str()
 static void free_problem(ktn_handle* h) {
     DevBuf* all[] = {&h->chunks, &h->shapes, &h->prog, &h->blob, &h->chunk_rows, &h->chunk_lb, &h->chunk_ub, &h->jac_ptr, &h->jac_col,
                      &h->row_lb, &h->row_ub, &h->x, &h->force, &h->g_row, &h->b_row, &h->sel, &h->stage_val, &h->big_scratch,
-                     &h->blk_cnt, &h->blk_nnz, &h->out_row, &h->out_ptr, &h->out_col, &h->out_val, &h->out_lo, &h->out_hi, &h->out_g, &h->out_viol};
+                     &h->st_flag, &h->st_cnt, &h->st_nnz, &h->table, &h->out_row, &h->out_ptr, &h->out_col, &h->out_val, &h->out_lo, &h->out_hi, &h->out_g, &h->out_viol};
     for (DevBuf* b : all) b->release();
     if (h->h_x) { cudaFreeHost(h->h_x); h->h_x = nullptr; }
     h->prob = KtnProblem();
@@ -85,7 +85,8 @@ extern "C" int ktn_create(const ktn_options* o, ktn_handle** out) {
     cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
     if (cudaMallocHost(&h->h_counts, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
     if (h->ticket.alloc(16) != cudaSuccess || h->counts.alloc(8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
-    cudaMemset(h->ticket.p, 0, 16); cudaMemset(h->counts.p, 0, 64);
+    cudaMemset(h->ticket.p, 0, 16);
+    { unsigned long long init[8] = {0, 0, ~0ull, ~0ull, 0, 0, ~0ull, 0}; cudaMemcpy(h->counts.p, init, 64, cudaMemcpyHostToDevice); }
     if (ktn_kernels_configure(h->max_smem) != cudaSuccess) { fprintf(stderr, "libktn: kernel configuration failed (is this an sm_100a device?)\n"); delete h; return KTN_ERR_CUDA; }
     *out = h;
     return KTN_OK;
@@ -143,7 +144,25 @@ extern "C" int ktn_load_end(ktn_handle* h) {
     if (const char* s = getenv("KTN_SIGMA")) sigma = atoll(s);
     int rc = P.finalize(sigma, KTN_LANE_LIMIT);
     if (rc != KTN_OK) { h->err = P.err; return rc; }
-    // shared-memory plan of the regular kernel
+    // block-shared table (shape descriptors + programs of the regular shapes) and the shared-memory plan.
+    // If the table would not fit beside the warp regions every shape falls back to the global-memory kernel.
+    std::vector<unsigned char> table;
+    {
+        std::vector<KtnShapeDesc> sh = P.shapes;
+        std::vector<KtnIns> pr;
+        for (KtnShapeDesc& s : sh) if (!(s.flags & KTN_SH_BIG)) { const uint32_t off = (uint32_t)pr.size(); pr.insert(pr.end(), P.prog.begin() + s.prog_off, P.prog.begin() + s.prog_off + s.n_ins); s.prog_off = off; }
+        const size_t sb = (sh.size() * sizeof(KtnShapeDesc) + 15) & ~(size_t)15;
+        if (sb + pr.size() * sizeof(KtnIns) > 32768 && P.n_regular_chunks > 0) {
+            for (KtnShapeDesc& s : P.shapes) s.flags |= KTN_SH_BIG;
+            rc = P.finalize(sigma, 0);
+            if (rc != KTN_OK) { h->err = P.err; return rc; }
+            sh = P.shapes; pr.clear();
+        }
+        table.assign(sb + pr.size() * sizeof(KtnIns) + 16, 0);
+        memcpy(table.data(), sh.data(), sh.size() * sizeof(KtnShapeDesc));
+        if (!pr.empty()) memcpy(table.data() + sb, pr.data(), pr.size() * sizeof(KtnIns));
+        h->table_prog_off = (uint32_t)sb; h->table_bytes = (uint32_t)((sb + pr.size() * sizeof(KtnIns) + 15) & ~(size_t)15);
+    }
     uint32_t blob_cap = 0, scratch_cap = 0;
     for (const KtnShapeDesc& s : P.shapes) if (!(s.flags & KTN_SH_BIG)) {
         uint32_t sec_col = (8u * s.n_const * 32u + 15u) & ~15u, sec_ord = (sec_col + 4u * s.n_uniq * 32u + 15u) & ~15u;
@@ -164,7 +183,9 @@ extern "C" int ktn_load_end(ktn_handle* h) {
     CK(h, cudaMemset(h->sel.p, 0, 4 * (m + 1))); CK(h, cudaMemset(h->g_row.p, 0, 8 * (m + 1)));
     CK(h, h->stage_val.alloc(8 * (N + 1))); CK(h, h->big_scratch.alloc(8 * (P.big_scratch_doubles + 1)));
     const size_t nblk = (m + 1023) / 1024 + 1;
-    CK(h, h->blk_cnt.alloc(4 * nblk)); CK(h, h->blk_nnz.alloc(8 * nblk));
+    CK(h, h->st_flag.alloc(4 * nblk)); CK(h, h->st_cnt.alloc(8 * nblk)); CK(h, h->st_nnz.alloc(16 * nblk));
+    CK(h, cudaMemset(h->st_flag.p, 0, 4 * nblk));
+    CK(h, upload(h->table, table));
     CK(h, h->out_row.alloc(4 * (m + 1))); CK(h, h->out_ptr.alloc(8 * (m + 2))); CK(h, h->out_col.alloc(4 * (N + 1))); CK(h, h->out_val.alloc(8 * (N + 1)));
     CK(h, h->out_lo.alloc(8 * (m + 1))); CK(h, h->out_hi.alloc(8 * (m + 1))); CK(h, h->out_g.alloc(8 * (m + 1))); CK(h, h->out_viol.alloc(8 * (m + 1)));
     CK(h, cudaMallocHost(&h->h_x, 8 * ((size_t)P.num_var + 1)));
@@ -210,17 +231,20 @@ static KtnRoundParams make_params(ktn_handle* h, const double* d_x, int mode, in
     p.warp_bytes = h->warp_bytes; p.blob_cap = h->blob_cap;
     p.g_row = h->g_row.as<double>(); p.b_row = h->b_row.as<double>(); p.sel = h->sel.as<uint32_t>();
     p.stage_val = h->stage_val.as<double>(); p.big_scratch = h->big_scratch.as<double>(); p.ticket = h->ticket.as<unsigned int>();
-    p.blk_cnt = h->blk_cnt.as<uint32_t>(); p.blk_nnz = h->blk_nnz.as<unsigned long long>(); p.counts = h->counts.as<unsigned long long>();
+    p.st_flag = h->st_flag.as<uint32_t>(); p.st_cnt = h->st_cnt.as<uint32_t>(); p.st_nnz = h->st_nnz.as<unsigned long long>();
+    p.counts = h->counts.as<unsigned long long>();
+    p.table = h->table.as<unsigned char>(); p.table_bytes = h->table_bytes; p.table_prog_off = h->table_prog_off; p.epoch = h->epoch;
     p.out_row = h->out_row.as<int32_t>(); p.out_ptr = h->out_ptr.as<int64_t>(); p.out_col = h->out_col.as<int32_t>(); p.out_val = h->out_val.as<double>();
     p.out_lo = h->out_lo.as<double>(); p.out_hi = h->out_hi.as<double>(); p.out_g = h->out_g.as<double>(); p.out_viol = h->out_viol.as<double>();
     return p;
 }
 
 static int enqueue_round(ktn_handle* h, const double* d_x, int mode, int do_round) {
+    h->epoch = (h->epoch % 0x3ffffff0u) + 1u;
     KtnRoundParams p = make_params(h, d_x, mode, do_round);
     cudaError_t e = cudaSuccess;
     CK(h, cudaEventRecord(h->ev1, h->stream));
-    int n = ktn_launch_round(p, h->prob.n_regular_chunks, (uint32_t)h->prob.chunks.size(), h->num_sms, h->max_smem, h->stream, &e);
+    int n = ktn_launch_round(p, h->prob.n_regular_chunks, (uint32_t)h->prob.chunks.size(), h->num_sms, h->max_smem, h->epoch, h->stream, &e);
     h->tm.launches += n;
     if (e != cudaSuccess) return fail(h, KTN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     CK(h, cudaEventRecord(h->ev2, h->stream));
@@ -236,7 +260,7 @@ static int finish_round(ktn_handle* h, int64_t* n_cuts, int64_t* nnz, int64_t* e
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev1, h->ev2) == cudaSuccess) h->tm.kernel_ms = ms;
     h->n_cuts = (int64_t)h->h_counts[0]; h->nnz_cuts = (int64_t)h->h_counts[1];
-    h->err_row = h->h_counts[2] == ~0ull ? -1 : (int64_t)h->h_counts[2] - 1;
+    h->err_row = h->h_counts[6] == ~0ull ? -1 : (int64_t)h->h_counts[6] - 1;
     if (n_cuts) *n_cuts = h->n_cuts;
     if (nnz) *nnz = h->nnz_cuts;
     if (err_row) *err_row = h->err_row;

@@ -47,9 +47,69 @@ struct ShapeCompiler {
     std::vector<char> jseen;
     std::string err;
 
-    ShapeCompiler(std::vector<TNode>& nodes, uint32_t n_uniq) : t(nodes), nu(n_uniq), next_slot(2 * n_uniq), jseen(n_uniq, 0) {}
+    bool alias;   // Jacobian accumulators and exp saves live in dead constant slots of the (shared-memory) blob
+    ShapeCompiler(std::vector<TNode>& nodes, uint32_t n_uniq, bool alias_) : t(nodes), nu(n_uniq), next_slot(alias_ ? n_uniq : 2 * n_uniq), jseen(n_uniq, 0), alias(alias_) {}
 
-    void emit(uint8_t op, Src s = Src{KTN_K_NONE, 0}, uint16_t n = 0) { code.push_back(KtnIns{op, s.kind, n, s.idx}); }
+    void emit(uint8_t op, Src s = Src{KTN_K_NONE, 0}, uint16_t n = 0) { code.push_back(KtnIns{op, s.kind, n, s.idx, 0u, 0u}); }
+    void emit_terms(uint8_t op, uint8_t tk_flags, uint32_t n, uint32_t c0, uint32_t u0, uint32_t s0) { code.push_back(KtnIns{op, tk_flags, (uint16_t)n, c0, u0, s0}); }
+
+    // ---- fused term runs inside n-ary sums ----
+    struct Run { size_t pos; uint32_t n; int tk; uint32_t c0, u0, s0; };
+    std::unordered_map<int, std::vector<Run>> runs;   // ADD node -> runs over its children
+    static int term_cstride(int tk) { return tk == KTN_T_EXP_AFF ? 2 : (tk == KTN_T_X || tk == KTN_T_SQ) ? 0 : 1; }
+    bool is_data_const(int k) const { return t[k].op == KTN_OP_CONST && t[k].cslot >= 0; }
+    bool is_sq_exp(int k) const { return t[k].op == KTN_OP_CONST && t[k].expclass == 2; }
+    // recognises the canonical term forms; returns the term kind or -1
+    int match_term(int k, int& c0, int& u) const {
+        const TNode& n = t[k];
+        c0 = 0; u = -1;
+        if (n.op == KTN_OP_VAR) { u = n.uslot; return KTN_T_X; }
+        if (n.op == KTN_OP_MUL && n.nc == 2) {
+            int a = k + 1, b = t[a].send;
+            if (is_data_const(a) && t[b].op == KTN_OP_VAR) { c0 = t[a].cslot; u = t[b].uslot; return KTN_T_MULC_X; }
+            if (is_data_const(a) && t[b].op == KTN_OP_POW && t[b + 1].op == KTN_OP_VAR && is_sq_exp(t[b + 1].send)) { c0 = t[a].cslot; u = t[b + 1].uslot; return KTN_T_MULC_SQ; }
+            return -1;
+        }
+        if (n.op == KTN_OP_POW) {
+            int b = k + 1, e = t[b].send;
+            if (!is_sq_exp(e)) return -1;
+            if (t[b].op == KTN_OP_VAR) { u = t[b].uslot; return KTN_T_SQ; }
+            if (t[b].op == KTN_OP_MUL && t[b].nc == 2 && is_data_const(b + 1) && t[t[b + 1].send].op == KTN_OP_VAR) { c0 = t[b + 1].cslot; u = t[t[b + 1].send].uslot; return KTN_T_SQ_MULC; }
+            return -1;
+        }
+        if (n.op == KTN_OP_EXP) {
+            int a = k + 1;                                  // ADD(MUL(c, x), d)
+            if (t[a].op != KTN_OP_ADD || t[a].nc != 2) return -1;
+            int mnode = a + 1, d = t[mnode].send;
+            if (t[mnode].op != KTN_OP_MUL || t[mnode].nc != 2 || !is_data_const(mnode + 1) || t[t[mnode + 1].send].op != KTN_OP_VAR || !is_data_const(d)) return -1;
+            if (t[d].cslot != t[mnode + 1].cslot + 1) return -1;
+            c0 = t[mnode + 1].cslot; u = t[t[mnode + 1].send].uslot; return KTN_T_EXP_AFF;
+        }
+        return -1;
+    }
+    void find_runs(int k, const std::vector<int>& ch) {
+        std::vector<Run> rs;
+        size_t i = 0;
+        while (i < ch.size()) {
+            int c0, u; int tk = match_term(ch[i], c0, u);
+            if (tk < 0) { ++i; continue; }
+            size_t j = i + 1;
+            const int cs = term_cstride(tk);
+            while (j < ch.size() && j - i < 60000) {
+                int c1, u1; int tk1 = match_term(ch[j], c1, u1);
+                if (tk1 != tk || u1 != u + (int)(j - i) || (cs && c1 != c0 + cs * (int)(j - i))) break;
+                ++j;
+            }
+            const uint32_t n = (uint32_t)(j - i);
+            if (n >= 2 || tk == KTN_T_EXP_AFF) {
+                Run r{i, n, tk, (uint32_t)c0, (uint32_t)u, 0u};
+                if (tk == KTN_T_EXP_AFF && !alias) { r.s0 = next_slot; next_slot += n; }
+                rs.push_back(r);
+            }
+            i = j;
+        }
+        if (!rs.empty()) runs[k] = rs;
+    }
     Src push_temp() {
         int d = temp_depth++;
         if (d == 0) return Src{KTN_K_R1, 0};
@@ -110,10 +170,22 @@ struct ShapeCompiler {
         if (n.is_leaf) { emit(KF_LOAD, n.val); return; }
         std::vector<int> ch = children(k);
         switch (n.op) {
-            case KTN_OP_ADD:
-                gen_fwd(ch[0]); emit(KF_ADDZ);
-                for (size_t i = 1; i < ch.size(); ++i) combine_commutative(KF_ADD, ch[i]);
-                break;
+            case KTN_OP_ADD: {
+                find_runs(k, ch);
+                const std::vector<Run>* rs = runs.count(k) ? &runs[k] : nullptr;
+                size_t ri = 0;
+                for (size_t i = 0; i < ch.size();) {
+                    if (rs && ri < rs->size() && (*rs)[ri].pos == i) {
+                        const Run& r = (*rs)[ri++];
+                        emit_terms(KF_TERMS, (uint8_t)(r.tk | (i == 0 ? KTN_TF_FIRST : 0) | (alias && r.tk == KTN_T_EXP_AFF ? KTN_TF_SAVEBLOB : 0)), r.n, r.c0, r.u0, r.s0);
+                        i += r.n;
+                    } else {
+                        if (i == 0) { gen_fwd(ch[0]); emit(KF_ADDZ); }
+                        else combine_commutative(KF_ADD, ch[i]);
+                        ++i;
+                    }
+                }
+                break; }
             case KTN_OP_SUB: gen_binary(k, KF_SUB, KF_RSUB); break;
             case KTN_OP_MUL:
                 if (n.nc <= 2 || !n.has_var) {
@@ -179,6 +251,34 @@ struct ShapeCompiler {
         for (int c : ch) if (t[c].has_var) H.push_back(c);
         Src T{KTN_K_NONE, 0};
         if (H.size() > 1) { T = push_temp(); emit(KF_STORE, T); }
+        if (n.op == KTN_OP_ADD && runs.count(k)) {
+            const std::vector<Run>& rs = runs[k];
+            size_t ri = 0; bool acc_is_adj = true;
+            for (size_t i = 0; i < ch.size();) {
+                if (ri < rs.size() && rs[ri].pos == i) {
+                    const Run& r = rs[ri++];
+                    if (!acc_is_adj) { emit(KF_LOAD, T); acc_is_adj = true; }
+                    const int cs = term_cstride(r.tk);
+                    for (uint32_t t0 = 0; t0 < r.n;) {      // split where set / accumulate changes
+                        const bool seen = jseen[r.u0 + t0];
+                        uint32_t t1 = t0 + 1;
+                        while (t1 < r.n && (bool)jseen[r.u0 + t1] == seen) ++t1;
+                        emit_terms(KR_TERMS, (uint8_t)(r.tk | (seen ? KTN_TF_JACC : 0) | (alias && r.tk == KTN_T_EXP_AFF ? KTN_TF_SAVEBLOB : 0)), t1 - t0, r.c0 + cs * t0, r.u0 + t0, r.s0 + t0);
+                        for (uint32_t q = t0; q < t1; ++q) jseen[r.u0 + q] = 1;
+                        t0 = t1;
+                    }
+                    i += r.n;
+                } else {
+                    if (t[ch[i]].has_var) {
+                        if (!acc_is_adj) emit(KF_LOAD, T);
+                        gen_rev(ch[i]); acc_is_adj = false;
+                    }
+                    ++i;
+                }
+            }
+            if (H.size() > 1) pop_temp();
+            return;
+        }
         for (size_t j = 0; j < H.size(); ++j) {
             int c = H[j];
             if (j > 0) emit(KF_LOAD, T);
@@ -299,21 +399,46 @@ int KtnProblem::add_rows(int64_t first_row, int64_t nrows, const int64_t* eptr, 
         auto& cand = shape_by_hash[h];
         for (uint32_t s : cand) if (shape_sig[s] == sig) { sid = s; break; }
         if (sid == UINT32_MAX) {
-            ShapeCompiler sc(t, nu);
-            sc.analyse();
-            sc.gen_fwd(0);
-            uint32_t nfwd = (uint32_t)sc.code.size();
-            sc.temp_depth = 0;
-            sc.emit(KR_ONE);
-            sc.gen_rev(0);
-            sc.emit(K_END);
-            if (!sc.err.empty()) { err = sc.err; return KTN_ERR_USAGE; }
+            const bool dense = (fl[r] & KTN_ROW_DENSE) != 0;
             KtnShapeDesc sd; memset(&sd, 0, sizeof sd);
-            sd.prog_off = (uint32_t)prog.size(); sd.n_fwd = nfwd; sd.n_ins = (uint32_t)sc.code.size();
-            sd.n_uniq = nu; sd.n_const = ncst; sd.n_scratch = sc.next_slot;
-            sd.flags = ((fl[r] & KTN_ROW_NL) ? KTN_SH_NL : 0) | ((fl[r] & KTN_ROW_DENSE) ? (KTN_SH_DENSE | KTN_SH_BIG) : 0);
-            sd.order_bytes = nu <= 256 ? 1 : nu <= 65536 ? 2 : 4;
-            prog.insert(prog.end(), sc.code.begin(), sc.code.end());
+            std::vector<KtnIns> code;
+            // pass 0: plain layout.  pass 1 (if eligible): J accumulators / exp saves aliased into dead constants.
+            for (int pass = 0; pass < 2; ++pass) {
+                std::vector<TNode> tc = t;
+                ShapeCompiler sc(tc, nu, pass == 1);
+                sc.analyse();
+                sc.gen_fwd(0);
+                const uint32_t nfwd = (uint32_t)sc.code.size();
+                sc.temp_depth = 0;
+                sc.emit(KR_ONE);
+                sc.gen_rev(0);
+                sc.emit(K_END);
+                if (!sc.err.empty()) { err = sc.err; return KTN_ERR_USAGE; }
+                sd.n_fwd = nfwd; sd.n_ins = (uint32_t)sc.code.size();
+                sd.n_uniq = nu; sd.n_const = ncst; sd.n_scratch = sc.next_slot;
+                sd.flags = ((fl[r] & KTN_ROW_NL) ? KTN_SH_NL : 0) | (dense ? (KTN_SH_DENSE | KTN_SH_BIG) : 0);
+                sd.order_bytes = nu <= 256 ? 1 : nu <= 65536 ? 2 : 4;
+                code = sc.code;
+                if (pass == 1) break;
+                sd.j_base = nu; sd.j_stride = 1; sd.j_in_blob = 0;
+                // eligibility: shared-memory staged shape whose every Jacobian entry is first written by ONE fused
+                // reverse run (set, not accumulate) over u = 0..nu-1 whose terms own at least one constant.
+                if (dense || nu == 0 || ktn_shape_lane_bytes(sd) > lane_limit_hint) break;
+                bool ok = true; int found = -1;
+                for (size_t q = nfwd; q < code.size() && ok; ++q) {
+                    const KtnIns& in = code[q];
+                    if (in.op == KR_JSET) ok = false;
+                    if (in.op == KR_TERMS && !(in.kind & KTN_TF_JACC)) {
+                        const int tk = in.kind & 0xf, cs = ShapeCompiler::term_cstride(tk);
+                        if (found >= 0 || cs == 0 || in.a != 0 || in.n != nu) ok = false; else found = (int)q;
+                    }
+                }
+                if (!ok || found < 0) break;
+                const int cs = ShapeCompiler::term_cstride(code[found].kind & 0xf);
+                sd.j_in_blob = 1; sd.j_base = code[found].idx + cs - 1; sd.j_stride = cs;
+            }
+            sd.prog_off = (uint32_t)prog.size();
+            prog.insert(prog.end(), code.begin(), code.end());
             sid = (uint32_t)shapes.size();
             shapes.push_back(sd); shape_sig.push_back(sig); cand.push_back(sid);
         }
@@ -342,6 +467,7 @@ void KtnProblem::repack_bounds() {
 int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit) {
     if (rows_loaded != num_constr) { err = "not all rows were loaded"; return KTN_ERR_USAGE; }
     if (sigma < 32) sigma = 32;
+    lane_limit_hint = lane_limit;
     // classify shapes
     max_lane_bytes = 0;
     for (auto& s : shapes) {
@@ -354,7 +480,7 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit) {
     std::vector<std::pair<uint32_t, int32_t>> win;  // (shape, row)
     alg_bytes_static = 8 * num_var;
     for (int64_t i = 0; i < num_constr; ++i) if (flags[i] & KTN_ROW_NL)
-        alg_bytes_static += 4 * (jac_ptr[i + 1] - jac_ptr[i]) + 8 * (int64_t)row_nconst_wire[i] + 16;
+        alg_bytes_static += 4 * (jac_ptr[i + 1] - jac_ptr[i]) + 8 * (int64_t)shapes[row_shape[i]].n_const + 16;   // C_i = per-row fp64 constants
 
     auto pack_chunk = [&](uint32_t sid, const int32_t* rows, int nr, bool isbig) {
         const KtnShapeDesc& s = shapes[sid];

@@ -37,6 +37,7 @@ struct KtnProblem {
     uint64_t big_scratch_doubles = 0;       // global scratch arena for BIG chunks
     uint32_t max_lane_bytes = 0;            // per-lane shared-memory need of the largest regular shape
     int64_t alg_bytes_static = 0;           // sum_NL (4 nnz + 8 C + 16) + 8 n
+    uint32_t lane_limit_hint = 1536;       // shapes above this never alias (they run from global memory)
     std::string err;
 
     void reset(int64_t nvar, int64_t nconstr);

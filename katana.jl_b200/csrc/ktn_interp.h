@@ -7,7 +7,7 @@
 #include "ktn_math.h"
 #include "ktn_program.h"
 
-struct KtnInsWord { uint32_t x, y; };
+struct KtnInsWord { uint32_t x, y, z, w; };
 #if defined(__CUDACC__)
 #define KTN_HDM __host__ __device__ __forceinline__
 #define KTN_HD_NOINLINE __host__ __device__ __noinline__
@@ -22,13 +22,19 @@ struct KtnInsWord { uint32_t x, y; };
 #endif
 KTN_HD KtnInsWord ktn_fetch_ins(const KtnIns* p) {
 #if defined(__CUDA_ARCH__)
-    const uint2 w = __ldg(reinterpret_cast<const uint2*>(p)); return KtnInsWord{w.x, w.y};
+    const uint4 w = *reinterpret_cast<const uint4*>(p); return KtnInsWord{w.x, w.y, w.z, w.w};   // shared (K1) or global (BIG) program
 #else
-    KtnInsWord w; memcpy(&w, p, 8); return w;
+    KtnInsWord w; memcpy(&w, p, 16); return w;
 #endif
 }
 
-KTN_HD double revmul(double a, double p) { return (a == 0.0 && !ktn_isfinite(p)) ? a : a * p; }
+// reverse_eval's product rule: a * p, except a zero adjoint stays zero under a non-finite partial.
+// a * p is NaN in exactly those cases (and when a NaN is genuinely propagated), so only NaN results re-check.
+KTN_HD double revmul(double a, double p) {
+    double r = a * p;
+    if (r != r) r = (a == 0.0 && !ktn_isfinite(p)) ? a : r;
+    return r;
+}
 
 // reference forward rule for `^` (ReverseDiffSparse forward_eval): exponent 2 and 1 are special-cased at run time
 KTN_HD_NOINLINE double pow_value(double base, double ex) { return ex == 2.0 ? base * base : ex == 1.0 ? base : ktn_pow(base, ex); }
@@ -36,28 +42,136 @@ KTN_HD_NOINLINE double pow_dbase(double base, double ex) { return ex == 2.0 ? 2.
 
 // regular chunks: SoA sections with lane stride 32 in shared memory
 struct SmemMem {
-    const double* C; double* S; uint32_t lane;
-    KTN_HDM double c(uint32_t i) const { return C[i * 32 + lane]; }
-    KTN_HDM double lds(uint32_t i) const { return S[i * 32 + lane]; }
-    KTN_HDM void sts(uint32_t i, double v) { S[i * 32 + lane] = v; }
+    double* C; double* S; double* Jp; uint32_t jmul, lane;   // C, S, Jp already include the lane offset
+    KTN_HDM double c(uint32_t i) const { return C[i * 32]; }
+    KTN_HDM void cst(uint32_t i, double v) { C[i * 32] = v; }
+    KTN_HDM double lds(uint32_t i) const { return S[i * 32]; }
+    KTN_HDM void sts(uint32_t i, double v) { S[i * 32] = v; }
+    KTN_HDM double jld(uint32_t u) const { return Jp[u * jmul]; }
+    KTN_HDM void jst(uint32_t u, double v) { Jp[u * jmul] = v; }
+    KTN_HDM size_t stride() const { return 32; }
+    KTN_HDM size_t jstride() const { return jmul; }
+    KTN_HDM double* caddr(uint32_t i) const { return C + i * 32; }
+    KTN_HDM double* saddr(uint32_t i) const { return S + i * 32; }
+    KTN_HDM double* jaddr(uint32_t u) const { return Jp + u * jmul; }
 };
 // BIG chunks: constants straight from the blob in global memory, scratch in a global arena
 struct GlobalMem {
-    const double* C; double* S; uint32_t lane, L;
+    const double* C; double* S; double* Jp; size_t jmul; uint32_t lane, L;
     KTN_HDM double c(uint32_t i) const { return C[(size_t)i * L + lane]; }
+    KTN_HDM void cst(uint32_t, double) {}   // BIG shapes never alias into the (persistent) global blob
     KTN_HDM double lds(uint32_t i) const { return S[(size_t)i * L + lane]; }
     KTN_HDM void sts(uint32_t i, double v) { S[(size_t)i * L + lane] = v; }
+    KTN_HDM double jld(uint32_t u) const { return Jp[(size_t)u * jmul]; }
+    KTN_HDM void jst(uint32_t u, double v) { Jp[(size_t)u * jmul] = v; }
+    KTN_HDM size_t stride() const { return L; }
+    KTN_HDM size_t jstride() const { return jmul; }
+    KTN_HDM double* caddr(uint32_t i) const { return const_cast<double*>(C) + (size_t)i * L + lane; }   // never written for BIG shapes
+    KTN_HDM double* saddr(uint32_t i) const { return S + (size_t)i * L + lane; }
+    KTN_HDM double* jaddr(uint32_t u) const { return Jp + (size_t)u * jmul; }
 };
+
+// ---- fused term runs (KF_TERMS / KR_TERMS) ----
+// Each case restates, op for op, what the primitive program for the term would do:
+//   c*x        LOAD c; MUL x                      x^2       LOAD x; POW2
+//   c*x^2      LOAD x; POW2; MUL c                (c*x)^2   LOAD c; MUL x; POW2
+//   exp(c*x+d) LOAD c; MUL x; ADDZ; ADD d; EXP
+// and the n-ary sum around them:  acc = 0.0 + t0 (first child) ; acc = acc + t_k.
+// Memory is addressed through strided lane pointers so the loops compile to pointer bumps.
+#define KTN_SUM_STEP(v) { acc = first ? 0.0 + (v) : acc + (v); first = false; }
+template <class M>
+KTN_HD double terms_fwd(M& m, uint32_t tk, uint32_t n, uint32_t c0, uint32_t u0, uint32_t s0, bool first, bool saveblob, double acc) {
+    const size_t st = m.stride();
+    const double* xp = m.saddr(u0);
+    switch (tk) {
+        case KTN_T_X:
+            for (uint32_t t = 0; t < n; ++t, xp += st) KTN_SUM_STEP(*xp)
+            break;
+        case KTN_T_MULC_X: {
+            const double* cp = m.caddr(c0);
+            for (uint32_t t = 0; t < n; ++t, xp += st, cp += st) KTN_SUM_STEP(*cp * *xp)
+            break; }
+        case KTN_T_SQ:
+            for (uint32_t t = 0; t < n; ++t, xp += st) { const double x = *xp; KTN_SUM_STEP(x * x) }
+            break;
+        case KTN_T_MULC_SQ: {
+            const double* cp = m.caddr(c0);
+            for (uint32_t t = 0; t < n; ++t, xp += st, cp += st) { const double x = *xp; KTN_SUM_STEP((x * x) * *cp) }
+            break; }
+        case KTN_T_SQ_MULC: {
+            const double* cp = m.caddr(c0);
+            for (uint32_t t = 0; t < n; ++t, xp += st, cp += st) { const double q = *cp * *xp; KTN_SUM_STEP(q * q) }
+            break; }
+        case KTN_T_EXP_AFF: {
+            double* cp = m.caddr(c0);
+            double* sp = saveblob ? cp + st : m.saddr(s0);       // exp values: the term's dead `d` slot, or scratch
+            const size_t ss = saveblob ? 2 * st : st;
+            uint32_t t = 0;
+            for (; t + 2 <= n; t += 2, xp += 2 * st, cp += 4 * st, sp += 2 * ss) {   // two independent exp chains in flight
+                const double a0 = (0.0 + cp[0] * xp[0]) + cp[st];
+                const double a1 = (0.0 + cp[2 * st] * xp[st]) + cp[3 * st];
+                const double v0 = ktn_exp(a0), v1 = ktn_exp(a1);
+                sp[0] = v0; sp[ss] = v1;
+                KTN_SUM_STEP(v0)
+                acc = acc + v1;
+            }
+            if (t < n) {
+                const double v = ktn_exp((0.0 + cp[0] * xp[0]) + cp[st]);
+                sp[0] = v;
+                KTN_SUM_STEP(v)
+            }
+            break; }
+        default: break;
+    }
+    return acc;
+}
+
+template <class M>
+KTN_HD void terms_rev(M& m, uint32_t tk, uint32_t n, uint32_t c0, uint32_t u0, uint32_t s0, bool jacc, bool saveblob, double adj) {
+    const size_t st = m.stride(), js = m.jstride();
+    const double* xp = m.saddr(u0);
+    double* jp = m.jaddr(u0);
+#define KTN_J_STEP(a) { const double a_ = (a); *jp = jacc ? *jp + a_ : 0.0 + a_; }
+    switch (tk) {
+        case KTN_T_X:
+            for (uint32_t t = 0; t < n; ++t, jp += js) KTN_J_STEP(adj)
+            break;
+        case KTN_T_MULC_X: {
+            const double* cp = m.caddr(c0);
+            for (uint32_t t = 0; t < n; ++t, jp += js, cp += st) KTN_J_STEP(revmul(adj, *cp))
+            break; }
+        case KTN_T_SQ:
+            for (uint32_t t = 0; t < n; ++t, jp += js, xp += st) KTN_J_STEP(revmul(adj, 2.0 * *xp))
+            break;
+        case KTN_T_MULC_SQ: {
+            const double* cp = m.caddr(c0);
+            for (uint32_t t = 0; t < n; ++t, jp += js, xp += st, cp += st) KTN_J_STEP(revmul(revmul(adj, *cp), 2.0 * *xp))
+            break; }
+        case KTN_T_SQ_MULC: {
+            const double* cp = m.caddr(c0);
+            for (uint32_t t = 0; t < n; ++t, jp += js, xp += st, cp += st) { const double c = *cp; KTN_J_STEP(revmul(revmul(adj, 2.0 * (c * *xp)), c)) }
+            break; }
+        case KTN_T_EXP_AFF: {
+            const double* cp = m.caddr(c0);
+            const double* sp = saveblob ? cp + st : m.saddr(s0);
+            const size_t ss = saveblob ? 2 * st : st;
+            for (uint32_t t = 0; t < n; ++t, jp += js, cp += 2 * st, sp += ss) KTN_J_STEP(revmul(revmul(adj, *sp), *cp))
+            break; }
+        default: break;
+    }
+#undef KTN_J_STEP
+}
+#undef KTN_SUM_STEP
 
 // The tape interpreter.  Warp-uniform control flow: every active lane executes the same op.
 template <class M>
-KTN_HD double run_program(const KtnIns* prog, uint32_t pc, uint32_t end, M& m, uint32_t nu, unsigned mask) {
+KTN_HD double run_program(const KtnIns* prog, uint32_t pc, uint32_t end, M& m, unsigned mask) {
     double acc = 0.0, aux = 0.0, r1 = 0.0, r2 = 0.0;
     for (; pc < end; ++pc) {
         const KtnInsWord w = ktn_fetch_ins(prog + pc);
         const uint32_t op = w.x & 0xffu, kind = (w.x >> 8) & 0xffu, idx = w.y;
         double src = 0.0;
-        switch (kind) {
+        switch ((op == KF_TERMS || op == KR_TERMS) ? (uint32_t)KTN_K_NONE : kind) {
             case KTN_K_C: src = m.c(idx); break;
             case KTN_K_S: if (op != KF_STORE) src = m.lds(idx); break;
             case KTN_K_R1: src = r1; break;
@@ -98,8 +212,10 @@ KTN_HD double run_program(const KtnIns* prog, uint32_t pc, uint32_t end, M& m, u
             case KR_MULRCP: acc = revmul(acc, 1.0 / src); break;
             case KR_MULHRCP: acc = revmul(acc, 0.5 / src); break;
             case KR_MULSGN: acc = revmul(acc, src >= 0.0 ? 1.0 : -1.0); break;
-            case KR_JSET: m.sts(nu + idx, 0.0 + acc); break;
-            case KR_JACC: m.sts(nu + idx, m.lds(nu + idx) + acc); break;
+            case KR_JSET: m.jst(idx, 0.0 + acc); break;
+            case KR_JACC: m.jst(idx, m.jld(idx) + acc); break;
+            case KF_TERMS: acc = terms_fwd(m, kind & 0xfu, w.x >> 16, idx, w.z, w.w, (kind & KTN_TF_FIRST) != 0, (kind & KTN_TF_SAVEBLOB) != 0, acc); break;
+            case KR_TERMS: terms_rev(m, kind & 0xfu, w.x >> 16, idx, w.z, w.w, (kind & KTN_TF_JACC) != 0, (kind & KTN_TF_SAVEBLOB) != 0, acc); break;
             default: break;
         }
     }

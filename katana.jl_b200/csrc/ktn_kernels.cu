@@ -5,22 +5,25 @@
 // constraint (src/separators.jl:111-116), then tests each NL row (src/separators.jl:120) and
 // builds a cut per violated row (src/algorithms.jl:3-18, src/model.jl:200-207, :68-79).
 //
-// Here: one WARP runs 32 rows of the same shape in lock step (thread-per-constraint inside a
-// chunk).  Per chunk:
-//   1. one elected lane issues a TMA bulk copy (cp.async.bulk, mbarrier completion) of the
-//      chunk's SoA blob (constants, column ids, sort order) into the warp's shared memory;
-//   2. x* values are gathered once per unique column into shared-memory scratch;
-//   3. the shape's forward program runs (acc machine, operands from shared memory) -> g;
-//   4. violation test; if any lane is violated the reverse program runs -> Jacobian row;
-//   5. violated lanes build the cut row (constant b, round_coefs, finiteness) and store the
-//      coefficients at the row's slot of the static Jacobian CSR layout.
-// A second phase (count / scan / scatter) compacts the selected rows, in ascending row order,
-// into the CSR the host LP consumes.  All arithmetic is fp64, unfused, in the oracle's order.
+// Here a round is two launches:
+//   K1 ktn_round_kernel   one WARP runs 32 rows of the same shape in lock step.  Per chunk:
+//        1. an elected lane issues a TMA bulk copy (cp.async.bulk + mbarrier) of the chunk's SoA
+//           blob (constants, column ids, sort order) into the warp's shared memory; the next
+//           chunk's ticket and descriptor are fetched while the current chunk computes;
+//        2. x* is gathered once per unique column into shared-memory scratch;
+//        3. the shape's forward program (block-shared copy in shared memory) runs -> g;
+//        4. violation test; if any lane is violated the reverse program runs -> Jacobian row
+//           (accumulators aliased into dead constant slots of the blob where the compiler could);
+//        5. violated lanes build the cut row (constant b, round_coefs, finiteness) and store the
+//           coefficients at the row's slot of the static Jacobian CSR layout.
+//   K2 ktn_compact_kernel single-pass (decoupled look-back) ordered stream compaction of the
+//        selected rows into the CSR the host LP consumes, ascending row order, coalesced copies.
+// BIG shapes (long tapes, the dense epigraph row) take ktn_big_kernel with global scratch.
+// All arithmetic is fp64, unfused, in the oracle's order.
 #include "ktn_kernels.cuh"
 #include "ktn_math.h"
 #include "ktn_interp.h"
 
-#define KTN_WARPS_PER_BLOCK 4
 #define KTN_CBLOCK 1024   // rows per compaction block
 
 namespace {
@@ -46,83 +49,126 @@ __device__ __forceinline__ bool row_selected(const KtnRoundParams& p, double g, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// regular chunks: shared-memory staged, one warp per chunk, dynamic chunk tickets
+// K1: regular chunks, shared-memory staged, one warp per chunk, dynamic chunk tickets
 // ---------------------------------------------------------------------------------------------
 template <bool EVAL_ONLY>
-__global__ void __launch_bounds__(KTN_WARPS_PER_BLOCK * 32) ktn_round_kernel(const KtnRoundParams p) {
+__global__ void __launch_bounds__(512, 1) ktn_round_kernel(const KtnRoundParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
+    // block-shared shape descriptors + programs of the regular shapes
+    for (uint32_t i = threadIdx.x; i < p.table_bytes / 16u; i += blockDim.x)
+        reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(p.table) + i);
+    const KtnShapeDesc* sh_shapes = reinterpret_cast<const KtnShapeDesc*>(smem);
+    const KtnIns* sh_prog = reinterpret_cast<const KtnIns*>(smem + p.table_prog_off);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* wbase = smem + (size_t)warp * p.warp_bytes;
+    unsigned char* wbase = smem + ((p.table_bytes + 127u) & ~127u) + (size_t)warp * p.warp_bytes;
     uint64_t* bar = reinterpret_cast<uint64_t*>(wbase);
     unsigned char* blobbuf = wbase + 128;
-    double* S = reinterpret_cast<double*>(blobbuf + p.blob_cap);
+    double* Sl = reinterpret_cast<double*>(blobbuf + p.blob_cap) + lane;    // scratch, lane offset applied
+    double* Cl = reinterpret_cast<double*>(blobbuf) + lane;                 // constants, lane offset applied
     if (lane == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    __syncwarp();
+    __syncthreads();
     uint32_t parity = 0;
-    for (;;) {
-        uint32_t c = 0;
-        if (lane == 0) c = p.chunk_begin + atomicAdd(&p.ticket[0], 1u);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        if (c >= p.chunk_end) break;
-        const KtnChunkDesc cd = p.chunks[c];
-        const KtnShapeDesc sd = p.shapes[cd.shape];
+
+    uint32_t c_cur = 0, c_nxt = 0;
+    if (lane == 0) { c_cur = atomicAdd(&p.ticket[0], 1u); c_nxt = atomicAdd(&p.ticket[0], 1u); }
+    c_cur = p.chunk_begin + __shfl_sync(0xffffffffu, c_cur, 0);
+    c_nxt = p.chunk_begin + __shfl_sync(0xffffffffu, c_nxt, 0);
+    KtnChunkDesc cd, cdn;
+    bool have = c_cur < p.chunk_end, cand = false;
+    if (have) {
+        cd = p.chunks[c_cur];
+        cand = EVAL_ONLY || p.mode != KTN_MODE_SEPARATE || (sh_shapes[cd.shape].flags & KTN_SH_NL);
+        if (cand && lane == 0) { mbar_expect(bar, cd.blob_bytes); bulk_g2s(blobbuf, p.blob + cd.blob_off, cd.blob_bytes, bar); }
+    }
+    while (have) {
+        // next-next ticket and next descriptor travel while this chunk computes
+        uint32_t c_n2 = 0;
+        if (lane == 0) c_n2 = atomicAdd(&p.ticket[0], 1u);
+        const bool have_nxt = c_nxt < p.chunk_end;
+        if (have_nxt) cdn = p.chunks[c_nxt];
         const int32_t row = p.chunk_rows[cd.row_slot + lane];
-        if (!EVAL_ONLY && p.mode == KTN_MODE_SEPARATE && !(sd.flags & KTN_SH_NL)) {   // rows outside nlconstr_ixs are never tested
+        if (!cand) {   // rows outside nlconstr_ixs are never tested (src/model.jl:272)
             if (row >= 0) p.sel[row] = 0u;
-            continue;
-        }
-        if (lane == 0) { mbar_expect(bar, cd.blob_bytes); bulk_g2s(blobbuf, p.blob + cd.blob_off, cd.blob_bytes, bar); }
-        const double lb = p.chunk_lb[cd.row_slot + lane], ub = p.chunk_ub[cd.row_slot + lane];
-        const uint32_t nu = sd.n_uniq;
-        const uint32_t sec_col = (8u * sd.n_const * 32u + 15u) & ~15u;
-        const uint32_t sec_ord = (sec_col + 4u * nu * 32u + 15u) & ~15u;
-        mbar_wait(bar, parity); parity ^= 1u;
-        const int32_t* cols = reinterpret_cast<const int32_t*>(blobbuf + sec_col);
-        const uint8_t* ord = blobbuf + sec_ord;
-        // gather x* once per unique column (precompute! reads xstar through the evaluator)
-        {
-            uint32_t u = 0;
-            for (; u + 4 <= nu; u += 4) {
-                const double a0 = __ldg(p.x + cols[(u + 0) * 32 + lane]), a1 = __ldg(p.x + cols[(u + 1) * 32 + lane]);
-                const double a2 = __ldg(p.x + cols[(u + 2) * 32 + lane]), a3 = __ldg(p.x + cols[(u + 3) * 32 + lane]);
-                S[(u + 0) * 32 + lane] = a0; S[(u + 1) * 32 + lane] = a1; S[(u + 2) * 32 + lane] = a2; S[(u + 3) * 32 + lane] = a3;
+        } else {
+            const double lb = p.chunk_lb[cd.row_slot + lane], ub = p.chunk_ub[cd.row_slot + lane];
+            const KtnShapeDesc& sd = sh_shapes[cd.shape];
+            const uint32_t nu = sd.n_uniq;
+            const uint32_t sec_col = (8u * sd.n_const * 32u + 15u) & ~15u;
+            const uint32_t sec_ord = (sec_col + 4u * nu * 32u + 15u) & ~15u;
+            const int32_t* cols = reinterpret_cast<const int32_t*>(blobbuf + sec_col) + lane;
+            const uint8_t* ord = blobbuf + sec_ord;
+            mbar_wait(bar, parity); parity ^= 1u;
+            // gather x* once per unique column (precompute! reads xstar through the evaluator)
+            {
+                uint32_t u = 0;
+                for (; u + 4 <= nu; u += 4) {
+                    const double a0 = __ldg(p.x + cols[(u + 0) * 32]), a1 = __ldg(p.x + cols[(u + 1) * 32]);
+                    const double a2 = __ldg(p.x + cols[(u + 2) * 32]), a3 = __ldg(p.x + cols[(u + 3) * 32]);
+                    Sl[(u + 0) * 32] = a0; Sl[(u + 1) * 32] = a1; Sl[(u + 2) * 32] = a2; Sl[(u + 3) * 32] = a3;
+                }
+                for (; u < nu; ++u) Sl[u * 32] = __ldg(p.x + cols[u * 32]);
             }
-            for (; u < nu; ++u) S[u * 32 + lane] = __ldg(p.x + cols[u * 32 + lane]);
-        }
-        SmemMem m{reinterpret_cast<const double*>(blobbuf), S, lane};
-        const KtnIns* prog = p.prog + sd.prog_off;
-        const double g = run_program(prog, 0, sd.n_fwd, m, nu, 0xffffffffu);
-        if (row >= 0) p.g_row[row] = g;
-        if (!EVAL_ONLY) {
-            const bool selected = row >= 0 && row_selected(p, g, lb, ub, row);
-            if (__any_sync(0xffffffffu, selected)) {
-                run_program(prog, sd.n_fwd, sd.n_ins, m, nu, 0xffffffffu);
-                if (selected) {
-                    // linear_oa_cut (src/algorithms.jl:8-16): b = g; b += -xstar[col]*partial, Jacobian-entry order
-                    double b = g, mx = 0.0;
-                    for (uint32_t q = 0; q < nu; ++q) {
-                        const uint32_t u = load_order(ord, sd.order_bytes, (size_t)q * 32 + lane);
-                        const double jv = S[(nu + u) * 32 + lane], xv = S[u * 32 + lane];
-                        const double t = (-xv) * jv;
-                        b = b + t;
-                        mx = q == 0 ? jv : ktn_jlmax(mx, jv);
+            SmemMem m{Cl, Sl, (sd.j_in_blob ? Cl : Sl) + sd.j_base * 32u, sd.j_stride * 32u, lane};
+            const KtnIns* prog = sh_prog + sd.prog_off;
+            const double g = run_program(prog, 0, sd.n_fwd, m, 0xffffffffu);
+            if (row >= 0) p.g_row[row] = g;
+            if (!EVAL_ONLY) {
+                const bool selected = row >= 0 && row_selected(p, g, lb, ub, row);
+                uint32_t selv = 0u;
+                if (__any_sync(0xffffffffu, selected)) {
+                    run_program(prog, sd.n_fwd, sd.n_ins, m, 0xffffffffu);
+                    if (selected) {
+                        // linear_oa_cut (src/algorithms.jl:8-16): b = g; b += -xstar[col]*partial in Jacobian-entry order.
+                        // max() of round_coefs (src/model.jl:201) is NaN-propagating: fmax ignores NaN, so track it.
+                        double b = g, mx = -ktn_inf();
+                        bool anynan = false, bad = false;
+                        double* out = p.stage_val + p.jac_ptr[row];
+                        if (sd.order_bytes == 1) {
+                            const uint8_t* o8 = ord + lane;
+                            for (uint32_t q = 0; q < nu; ++q) {
+                                const uint32_t u = o8[q * 32];
+                                const double jv = m.jld(u), xv = Sl[u * 32];
+                                b = b + (-xv) * jv;
+                                mx = fmax(mx, jv); anynan = anynan || (jv != jv);
+                            }
+                            if (anynan) mx = ktn_nan();
+                            // round_coefs (src/model.jl:202-206) then _addcut's finiteness test (src/model.jl:69)
+                            for (uint32_t q = 0; q < nu; ++q) {
+                                double jv = m.jld(o8[q * 32]);
+                                if (p.do_round && (jv + p.rng < mx)) jv = 0.0;
+                                bad = bad || !(fabs(jv) <= 1.7976931348623157e308);
+                                out[q] = jv;
+                            }
+                        } else {
+                            for (uint32_t q = 0; q < nu; ++q) {
+                                const uint32_t u = load_order(ord, sd.order_bytes, (size_t)q * 32 + lane);
+                                const double jv = m.jld(u), xv = Sl[u * 32];
+                                b = b + (-xv) * jv;
+                                mx = fmax(mx, jv); anynan = anynan || (jv != jv);
+                            }
+                            if (anynan) mx = ktn_nan();
+                            for (uint32_t q = 0; q < nu; ++q) {
+                                double jv = m.jld(load_order(ord, sd.order_bytes, (size_t)q * 32 + lane));
+                                if (p.do_round && (jv + p.rng < mx)) jv = 0.0;
+                                bad = bad || !(fabs(jv) <= 1.7976931348623157e308);
+                                out[q] = jv;
+                            }
+                        }
+                        selv = nu | (bad ? KTN_SEL_ERRBIT : 0u);
+                        p.b_row[row] = b;
+                        if (bad) atomicMin(&p.counts[2 + (p.epoch & 1u)], (unsigned long long)row + 1ull);
                     }
-                    // round_coefs (src/model.jl:200-207) then _addcut's finiteness test (src/model.jl:69)
-                    const int64_t base = p.jac_ptr[row];
-                    bool bad = false;
-                    for (uint32_t q = 0; q < nu; ++q) {
-                        const uint32_t u = load_order(ord, sd.order_bytes, (size_t)q * 32 + lane);
-                        double jv = S[(nu + u) * 32 + lane];
-                        if (p.do_round && (jv + p.rng < mx)) jv = 0.0;
-                        bad = bad || !ktn_isfinite(jv);
-                        p.stage_val[base + q] = jv;
-                    }
-                    p.b_row[row] = b;
-                    p.sel[row] = nu | (bad ? KTN_SEL_ERRBIT : 0u);
-                } else if (row >= 0) p.sel[row] = 0u;
-            } else if (row >= 0) p.sel[row] = 0u;
+                }
+                if (row >= 0) p.sel[row] = selv;
+            }
+            __syncwarp();   // every lane is done with the blob before the next bulk copy overwrites it
         }
-        __syncwarp();   // every lane is done with the blob before the next bulk copy overwrites it
+        c_cur = c_nxt; cd = cdn; have = have_nxt;
+        c_nxt = p.chunk_begin + __shfl_sync(0xffffffffu, c_n2, 0);
+        if (have) {
+            cand = EVAL_ONLY || p.mode != KTN_MODE_SEPARATE || (sh_shapes[cd.shape].flags & KTN_SH_NL);
+            if (cand && lane == 0) { mbar_expect(bar, cd.blob_bytes); bulk_g2s(blobbuf, p.blob + cd.blob_off, cd.blob_bytes, bar); }
+        }
     }
 }
 
@@ -145,19 +191,21 @@ __global__ void __launch_bounds__(128) ktn_big_kernel(const KtnRoundParams p) {
         const int32_t* cols = reinterpret_cast<const int32_t*>(blob + sec_col);
         const uint8_t* ord = blob + sec_ord;
         double* S = p.big_scratch + cd.scratch_off;
+        double* J = S + (size_t)sd.j_base * L;     // BIG shapes keep their accumulators in scratch (j_in_blob == 0)
+        const size_t jmul = (size_t)L * sd.j_stride;
         double g = 0.0; bool selected = false;
         const bool active = lane < cd.nrows;
         const unsigned amask = __ballot_sync(0xffffffffu, active);
         if (active) {
             for (uint32_t u = 0; u < nu; ++u) S[(size_t)u * L + lane] = __ldg(p.x + cols[(size_t)u * L + lane]);
-            GlobalMem m{reinterpret_cast<const double*>(blob), S, lane, L};
+            GlobalMem m{reinterpret_cast<const double*>(blob), S, J + lane, jmul, lane, L};
             const KtnIns* prog = p.prog + sd.prog_off;
-            g = run_program(prog, 0, sd.n_fwd, m, nu, amask);
+            g = run_program(prog, 0, sd.n_fwd, m, amask);
             p.g_row[row] = g;
             if (!EVAL_ONLY) {
                 const double lb = p.chunk_lb[cd.row_slot + lane], ub = p.chunk_ub[cd.row_slot + lane];
                 selected = row_selected(p, g, lb, ub, row);
-                if (__any_sync(amask, selected)) run_program(prog, sd.n_fwd, sd.n_ins, m, nu, amask);
+                if (__any_sync(amask, selected)) run_program(prog, sd.n_fwd, sd.n_ins, m, amask);
             }
         }
         if (EVAL_ONLY) continue;
@@ -166,7 +214,7 @@ __global__ void __launch_bounds__(128) ktn_big_kernel(const KtnRoundParams p) {
                 double b = g, mx = 0.0;
                 for (uint32_t q = 0; q < nu; ++q) {
                     const uint32_t u = load_order(ord, sd.order_bytes, (size_t)q * L + lane);
-                    const double jv = S[(size_t)(nu + u) * L + lane], xv = S[(size_t)u * L + lane];
+                    const double jv = J[(size_t)u * jmul + lane], xv = S[(size_t)u * L + lane];
                     b = b + (-xv) * jv;
                     mx = q == 0 ? jv : ktn_jlmax(mx, jv);
                 }
@@ -174,13 +222,14 @@ __global__ void __launch_bounds__(128) ktn_big_kernel(const KtnRoundParams p) {
                 bool bad = false;
                 for (uint32_t q = 0; q < nu; ++q) {
                     const uint32_t u = load_order(ord, sd.order_bytes, (size_t)q * L + lane);
-                    double jv = S[(size_t)(nu + u) * L + lane];
+                    double jv = J[(size_t)u * jmul + lane];
                     if (p.do_round && (jv + p.rng < mx)) jv = 0.0;
                     bad = bad || !ktn_isfinite(jv);
                     p.stage_val[base + q] = jv;
                 }
                 p.b_row[row] = b;
                 p.sel[row] = nu | (bad ? KTN_SEL_ERRBIT : 0u);
+                if (bad) atomicMin(&p.counts[2 + (p.epoch & 1u)], (unsigned long long)row + 1ull);
             } else if (row >= 0) p.sel[row] = 0u;
         } else {
             // dense row: every column 0..num_var-1 is an entry (src/nlpeval.jl:49-54); columns the
@@ -196,7 +245,7 @@ __global__ void __launch_bounds__(128) ktn_big_kernel(const KtnRoundParams p) {
                 double* out = p.stage_val + base;
                 for (int64_t j = lane; j < n; j += 32) out[j] = 0.0;
                 __syncwarp();
-                for (uint32_t u = lane; u < nu; u += 32) out[cols[(size_t)u * L + r]] = S[(size_t)(nu + u) * L + r];
+                for (uint32_t u = lane; u < nu; u += 32) out[cols[(size_t)u * L + r]] = J[(size_t)u * jmul + r];
                 __syncwarp();
                 // b = g + sum_j -x_j * J_j in column order, exactly: blocks of 32 columns whose terms are all
                 // +-0 leave a non-zero b unchanged and are skipped; any other block is added lane by lane.
@@ -222,7 +271,10 @@ __global__ void __launch_bounds__(128) ktn_big_kernel(const KtnRoundParams p) {
                     out[j] = jv;
                 }
                 bad = __any_sync(0xffffffffu, bad);
-                if (lane == 0) { p.b_row[rrow] = b; p.sel[rrow] = (uint32_t)n | (bad ? KTN_SEL_ERRBIT : 0u); }
+                if (lane == 0) {
+                    p.b_row[rrow] = b; p.sel[rrow] = (uint32_t)n | (bad ? KTN_SEL_ERRBIT : 0u);
+                    if (bad) atomicMin(&p.counts[2 + (p.epoch & 1u)], (unsigned long long)rrow + 1ull);
+                }
                 __syncwarp();
             }
         }
@@ -230,8 +282,8 @@ __global__ void __launch_bounds__(128) ktn_big_kernel(const KtnRoundParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// ordered compaction: selected rows -> CSR in ascending row order (the loop order of
-// src/model.jl:272).  count -> scan -> scatter over blocks of KTN_CBLOCK rows.
+// K2: ordered stream compaction, single pass with decoupled look-back.
+// Selected rows -> CSR in ascending row order (the loop order of src/model.jl:272).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void block_scan2(uint32_t& a, unsigned long long& b, uint32_t& ta, unsigned long long& tb) {
     // exclusive scan of (a, b) over a 1024-thread block; totals in (ta, tb)
@@ -263,80 +315,90 @@ __device__ __forceinline__ void block_scan2(uint32_t& a, unsigned long long& b, 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(KTN_CBLOCK) ktn_count_kernel(const KtnRoundParams p) {
-    const int64_t i = (int64_t)blockIdx.x * KTN_CBLOCK + threadIdx.x;
-    const uint32_t s = i < p.num_rows ? p.sel[i] : 0u;
-    uint32_t a = s ? 1u : 0u; unsigned long long b = s & ~KTN_SEL_ERRBIT;
-    if (s & KTN_SEL_ERRBIT) atomicMin(&p.counts[2], (unsigned long long)i + 1ull);
-    uint32_t ta; unsigned long long tb;
-    block_scan2(a, b, ta, tb);
-    if (threadIdx.x == 0) { p.blk_cnt[blockIdx.x] = ta; p.blk_nnz[blockIdx.x] = tb; }
-}
-
-__global__ void __launch_bounds__(KTN_CBLOCK) ktn_scan_kernel(const KtnRoundParams p, uint32_t nblocks) {
-    __shared__ uint32_t carry_a; __shared__ unsigned long long carry_b;
-    if (threadIdx.x == 0) { carry_a = 0; carry_b = 0; }
+// look-back state of block k: st_flag[k] = (epoch << 2) | {1: aggregate ready, 2: inclusive prefix ready};
+// aggregates live in st_cnt / st_nnz [k], inclusive prefixes in [nblocks + k].
+// One block = KTN_CBLOCK threads x KTN_CRPT consecutive rows per thread.
+#define KTN_CRPT 4
+#define KTN_CROWS (KTN_CBLOCK * KTN_CRPT)
+__global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRoundParams p, uint32_t nblocks, uint32_t epoch) {
+    __shared__ uint32_t s_bid, s_cnt_base; __shared__ unsigned long long s_nnz_base;
+    __shared__ uint32_t s_off[KTN_CROWS + 1];        // exclusive nnz offsets of the block's selected rows (compact list)
+    __shared__ uint16_t s_rowl[KTN_CROWS];           // block-local row index of each selected row
+    if (threadIdx.x == 0) s_bid = atomicAdd(&p.ticket[2], 1u);
     __syncthreads();
-    for (uint32_t b0 = 0; b0 < nblocks; b0 += KTN_CBLOCK) {
-        const uint32_t i = b0 + threadIdx.x;
-        uint32_t a = i < nblocks ? p.blk_cnt[i] : 0u; unsigned long long b = i < nblocks ? p.blk_nnz[i] : 0ull;
-        uint32_t ta; unsigned long long tb;
-        block_scan2(a, b, ta, tb);
-        if (i < nblocks) { p.blk_cnt[i] = carry_a + a; p.blk_nnz[i] = carry_b + b; }
-        __syncthreads();
-        if (threadIdx.x == 0) { carry_a += ta; carry_b += tb; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        p.counts[3] = carry_a; p.counts[4] = carry_b;
-        if (p.counts[2] == ~0ull) { p.counts[0] = carry_a; p.counts[1] = carry_b; }   // no error row: totals stand
-        p.out_ptr[carry_a] = (int64_t)carry_b;
-        p.ticket[0] = 0u; p.ticket[1] = 0u;                                           // re-arm the chunk scheduler
-    }
-}
-
-__global__ void __launch_bounds__(KTN_CBLOCK) ktn_scatter_kernel(const KtnRoundParams p) {
-    __shared__ int32_t big_row[64]; __shared__ uint32_t big_cnt;
-    if (threadIdx.x == 0) big_cnt = 0;
-    const int64_t i = (int64_t)blockIdx.x * KTN_CBLOCK + threadIdx.x;
-    const uint32_t s = i < p.num_rows ? p.sel[i] : 0u;
-    const uint32_t nnz = s & ~KTN_SEL_ERRBIT;
-    uint32_t a = s ? 1u : 0u; unsigned long long b = nnz;
+    const uint32_t bid = s_bid;
+    const int64_t row0 = (int64_t)bid * KTN_CROWS, i0 = row0 + (int64_t)threadIdx.x * KTN_CRPT;
+    uint32_t sv[KTN_CRPT];
+    if (i0 + KTN_CRPT <= p.num_rows) { const uint4 q = *reinterpret_cast<const uint4*>(p.sel + i0); sv[0] = q.x; sv[1] = q.y; sv[2] = q.z; sv[3] = q.w; }
+    else for (int r = 0; r < KTN_CRPT; ++r) sv[r] = (i0 + r < p.num_rows) ? p.sel[i0 + r] : 0u;
+    uint32_t a = 0; unsigned long long b = 0;
+    for (int r = 0; r < KTN_CRPT; ++r) { a += sv[r] ? 1u : 0u; b += sv[r] & ~KTN_SEL_ERRBIT; }
     uint32_t ta; unsigned long long tb;
     block_scan2(a, b, ta, tb);
-    int64_t cidx = -1, o = 0, base = 0;
-    if (s) {
-        cidx = (int64_t)p.blk_cnt[blockIdx.x] + a; o = (int64_t)(p.blk_nnz[blockIdx.x] + b); base = p.jac_ptr[i];
+    if (threadIdx.x < 32) {   // warp 0: publish the aggregate, then look back 32 predecessors per probe
+        volatile uint32_t* flag = p.st_flag; volatile uint32_t* scnt = p.st_cnt; volatile unsigned long long* snnz = p.st_nnz;
+        const uint32_t lane = threadIdx.x;
+        uint32_t cb = 0; unsigned long long nb = 0;
+        if (bid > 0) {
+            if (lane == 0) { scnt[bid] = ta; snnz[bid] = tb; __threadfence(); flag[bid] = (epoch << 2) | 1u; }
+            int64_t wnd = (int64_t)bid - 1;      // lane l inspects block wnd - l
+            for (;;) {
+                const int64_t k = wnd - lane;
+                uint32_t f = 2u;                  // blocks before the first count as an (empty) inclusive prefix
+                if (k >= 0) { while (((f = flag[k]) >> 2) != epoch) __nanosleep(20); f &= 3u; }
+                __threadfence();
+                const unsigned pm = __ballot_sync(0xffffffffu, f == 2u);
+                const int first = pm ? __ffs(pm) - 1 : 32;          // nearest predecessor holding an inclusive prefix
+                uint32_t vc = 0; unsigned long long vn = 0;
+                if (k >= 0 && (int)lane <= first) { const size_t src = (size_t)k + (f == 2u ? nblocks : 0u); vc = scnt[src]; vn = snnz[src]; }
+                for (int o = 16; o > 0; o >>= 1) { vc += __shfl_xor_sync(0xffffffffu, vc, o); vn += __shfl_xor_sync(0xffffffffu, vn, o); }
+                cb += vc; nb += vn;
+                if (pm) break;
+                wnd -= 32;
+            }
+        }
+        if (lane == 0) {
+            scnt[nblocks + bid] = cb + ta; snnz[nblocks + bid] = nb + tb; __threadfence(); flag[bid] = (epoch << 2) | 2u;
+            s_cnt_base = cb; s_nnz_base = nb;
+            if (bid == nblocks - 1) {   // totals, and re-arm the per-round device state
+                const unsigned long long err = p.counts[2 + (epoch & 1u)];   // written by this round's K1 only
+                p.counts[4] = cb + ta; p.counts[5] = nb + tb; p.counts[6] = err;
+                p.counts[2 + ((epoch & 1u) ^ 1u)] = ~0ull;                    // re-arm the slot the NEXT round's K1 uses
+                if (err == ~0ull) { p.counts[0] = cb + ta; p.counts[1] = nb + tb; }
+                p.out_ptr[cb + ta] = (int64_t)(nb + tb);
+                p.ticket[0] = 0u; p.ticket[1] = 0u; p.ticket[2] = 0u;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t cbase = s_cnt_base; const unsigned long long nbase = s_nnz_base;
+    for (int r = 0; r < KTN_CRPT; ++r) {
+        const uint32_t s = sv[r];
+        if (!s) continue;
+        const int64_t i = i0 + r;
+        const int64_t cidx = (int64_t)cbase + a, o = (int64_t)(nbase + b);
+        s_off[a] = (uint32_t)b; s_rowl[a] = (uint16_t)(threadIdx.x * KTN_CRPT + r);
         const double g = p.g_row[i], bc = p.b_row[i], lb = p.row_lb[i], ub = p.row_ub[i];
         p.out_row[cidx] = (int32_t)i; p.out_ptr[cidx] = o;
         p.out_lo[cidx] = lb - bc; p.out_hi[cidx] = ub - bc;     // src/model.jl:74-75
         p.out_g[cidx] = g;
         const double v1 = lb - g, v2 = g - ub;
         p.out_viol[cidx] = (g == g) ? (v1 > v2 ? v1 : v2) : g;
-        if ((unsigned long long)i + 1ull == p.counts[2]) { p.counts[0] = (unsigned long long)cidx; p.counts[1] = (unsigned long long)o; }
+        // the reference stops at the first non-finite cut (src/model.jl:278): cuts before it stand
+        if ((s & KTN_SEL_ERRBIT) && (unsigned long long)i + 1ull == p.counts[2 + (epoch & 1u)]) { p.counts[0] = (unsigned long long)cidx; p.counts[1] = (unsigned long long)o; }
+        a += 1u; b += s & ~KTN_SEL_ERRBIT;
     }
-    // rows with few entries are copied by their thread; long rows by the whole block
-    bool deferred = false;
-    if (s && nnz > 64u) { const uint32_t k = atomicAdd(&big_cnt, 1u); if (k < 64u) { big_row[k] = threadIdx.x; deferred = true; } }
-    if (s && !deferred) for (uint32_t q = 0; q < nnz; ++q) { p.out_col[o + q] = p.jac_col[base + q]; p.out_val[o + q] = p.stage_val[base + q]; }
-    __shared__ int64_t sh_o[KTN_CBLOCK / 16]; __shared__ int64_t sh_base[KTN_CBLOCK / 16]; __shared__ uint32_t sh_n[KTN_CBLOCK / 16];
+    if (threadIdx.x == 0) s_off[ta] = (uint32_t)tb;
     __syncthreads();
-    const uint32_t nb = big_cnt < 64u ? big_cnt : 64u;
-    for (uint32_t k = 0; k < nb; ++k) {
-        if ((int32_t)threadIdx.x == big_row[k]) { sh_o[k] = o; sh_base[k] = base; sh_n[k] = nnz; }
-    }
-    __syncthreads();
-    for (uint32_t k = 0; k < nb; ++k) {
-        const int64_t oo = sh_o[k], bb = sh_base[k]; const uint32_t nn = sh_n[k];
-        for (uint32_t q = threadIdx.x; q < nn; q += KTN_CBLOCK) { p.out_col[oo + q] = p.jac_col[bb + q]; p.out_val[oo + q] = p.stage_val[bb + q]; }
+    // expand: one thread per output entry, coalesced writes; the owning row is found by binary search
+    for (unsigned long long e = threadIdx.x; e < tb; e += KTN_CBLOCK) {
+        uint32_t lo = 0, hi = ta;   // largest k with s_off[k] <= e
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= e) lo = mid; else hi = mid; }
+        const int64_t src = p.jac_ptr[row0 + s_rowl[lo]] + (int64_t)(e - s_off[lo]);
+        p.out_col[nbase + e] = p.jac_col[src];
+        p.out_val[nbase + e] = p.stage_val[src];
     }
 }
-
-__global__ void ktn_reset_kernel(const KtnRoundParams p) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { p.counts[0] = 0; p.counts[1] = 0; p.counts[2] = ~0ull; p.counts[3] = 0; p.counts[4] = 0; p.ticket[0] = 0u; p.ticket[1] = 0u; }
-}
-
-int regular_blocks_per_sm = 1;
 
 }  // namespace
 
@@ -346,21 +408,41 @@ cudaError_t ktn_kernels_configure(int max_smem_optin) {
     return cudaFuncSetAttribute(ktn_round_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
 }
 
+// warps per block x blocks per SM that maximise resident warps for the given per-warp shared-memory need
+void ktn_plan_occupancy(uint32_t table_bytes, uint32_t warp_bytes, int max_smem_optin, int* wpb_out, int* bps_out) {
+    const size_t sm_total = (size_t)max_smem_optin + 1024;   // per-SM carve-out incl. the 1 KB per-block reserve
+    int best_w = 1, best_b = 1, best = 0;
+    const size_t tb = (table_bytes + 127u) & ~127u;
+    static int regs = 0;
+    if (!regs) { cudaFuncAttributes fa; regs = (cudaFuncGetAttributes(&fa, ktn_round_kernel<false>) == cudaSuccess && fa.numRegs > 0) ? fa.numRegs : 128; }
+    const int regs_alloc = (regs + 7) / 8 * 8;
+    int max_warps = 65536 / (regs_alloc * 32);
+    if (max_warps > 48) max_warps = 48;
+    for (int w = 1; w <= 16; ++w) {
+        const size_t blk = tb + (size_t)w * warp_bytes;
+        if (blk > (size_t)max_smem_optin) break;
+        int b = (int)(sm_total / (blk + 1024));
+        if (b > 32) b = 32;
+        while (b * w > max_warps) --b;              // register file
+        if (b < 1) continue;
+        if (b * w > best || (b * w == best && w > best_w)) { best = b * w; best_w = w; best_b = b; }
+    }
+    *wpb_out = best_w; *bps_out = best_b;
+}
+
 template <bool EVAL>
 static int launch_eval_part(const KtnRoundParams& p0, uint32_t n_regular, uint32_t n_total, int num_sms, int max_smem_optin,
                             cudaStream_t stream, cudaError_t* err) {
     int launches = 0;
     KtnRoundParams p = p0;
     if (n_regular > 0) {
-        const size_t smem = (size_t)KTN_WARPS_PER_BLOCK * p.warp_bytes;
-        int per_sm = (int)((size_t)(max_smem_optin + 1024) / (smem + 1024));
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > 16) per_sm = 16;
-        uint32_t blocks = (uint32_t)(num_sms * per_sm);
-        const uint32_t need = (n_regular + KTN_WARPS_PER_BLOCK - 1) / KTN_WARPS_PER_BLOCK;
+        int wpb, bps; ktn_plan_occupancy(p.table_bytes, p.warp_bytes, max_smem_optin, &wpb, &bps);
+        const size_t smem = ((p.table_bytes + 127u) & ~127u) + (size_t)wpb * p.warp_bytes;
+        uint32_t blocks = (uint32_t)(num_sms * bps);
+        const uint32_t need = (n_regular + wpb - 1) / wpb;
         if (blocks > need) blocks = need;
         p.chunk_begin = 0; p.chunk_end = n_regular;
-        ktn_round_kernel<EVAL><<<blocks, KTN_WARPS_PER_BLOCK * 32, smem, stream>>>(p);
+        ktn_round_kernel<EVAL><<<blocks, wpb * 32, smem, stream>>>(p);
         ++launches;
     }
     if (n_total > n_regular) {
@@ -375,17 +457,13 @@ static int launch_eval_part(const KtnRoundParams& p0, uint32_t n_regular, uint32
 }
 
 int ktn_launch_round(const KtnRoundParams& p, uint32_t n_regular, uint32_t n_total, int num_sms, int max_smem_optin,
-                     cudaStream_t stream, cudaError_t* err) {
-    int launches = 0;
-    ktn_reset_kernel<<<1, 32, 0, stream>>>(p); ++launches;
-    launches += launch_eval_part<false>(p, n_regular, n_total, num_sms, max_smem_optin, stream, err);
+                     uint32_t epoch, cudaStream_t stream, cudaError_t* err) {
+    int launches = launch_eval_part<false>(p, n_regular, n_total, num_sms, max_smem_optin, stream, err);
     if (*err != cudaSuccess) return launches;
-    const uint32_t nblocks = (uint32_t)((p.num_rows + KTN_CBLOCK - 1) / KTN_CBLOCK);
+    const uint32_t nblocks = (uint32_t)((p.num_rows + KTN_CROWS - 1) / KTN_CROWS);
     if (nblocks > 0) {
-        ktn_count_kernel<<<nblocks, KTN_CBLOCK, 0, stream>>>(p);
-        ktn_scan_kernel<<<1, KTN_CBLOCK, 0, stream>>>(p, nblocks);
-        ktn_scatter_kernel<<<nblocks, KTN_CBLOCK, 0, stream>>>(p);
-        launches += 3;
+        ktn_compact_kernel<<<nblocks, KTN_CBLOCK, 0, stream>>>(p, nblocks, epoch);
+        ++launches;
     }
     *err = cudaGetLastError();
     return launches;
@@ -393,8 +471,7 @@ int ktn_launch_round(const KtnRoundParams& p, uint32_t n_regular, uint32_t n_tot
 
 int ktn_launch_eval(const KtnRoundParams& p, uint32_t n_regular, uint32_t n_total, int num_sms, int max_smem_optin,
                     cudaStream_t stream, cudaError_t* err) {
-    int launches = 0;
-    ktn_reset_kernel<<<1, 32, 0, stream>>>(p); ++launches;
-    launches += launch_eval_part<true>(p, n_regular, n_total, num_sms, max_smem_optin, stream, err);
+    int launches = launch_eval_part<true>(p, n_regular, n_total, num_sms, max_smem_optin, stream, err);
+    if (*err == cudaSuccess) *err = cudaMemsetAsync(p.ticket, 0, 16, stream);   // the eval path has no K2 to re-arm the tickets
     return launches;
 }

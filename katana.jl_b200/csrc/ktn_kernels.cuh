@@ -35,17 +35,23 @@ struct KtnRoundParams {
     uint32_t* sel;             // 0 = not selected, else nnz | KTN_SEL_ERRBIT
     double* stage_val;         // cut coefficients in the static CSR layout
     double* big_scratch;
-    unsigned int* ticket;      // dynamic chunk scheduler [0] regular, [1] big
-    // compaction
-    uint32_t* blk_cnt; unsigned long long* blk_nnz;   // per 1024-row block
-    unsigned long long* counts;   // [0] n_cuts [1] nnz [2] err_row+1 (0 = none) [3] n_cuts_total [4] nnz_total
+    unsigned int* ticket;      // [0] K1 chunk scheduler, [2] K2 block order
+    // block-shared table of the regular kernel: shape descriptors, then the programs of the regular shapes
+    const unsigned char* table; uint32_t table_bytes, table_prog_off;
+    uint32_t epoch;                    // round counter (>= 1): look-back flags and error slots are epoch-stamped
+    // compaction (decoupled look-back state per 1024-row block; no per-round reset)
+    uint32_t* st_flag; uint32_t* st_cnt; unsigned long long* st_nnz;
+    // [0] n_cuts [1] nnz (both truncated at the first non-finite row) [2],[3] first-error row + 1 of even / odd epochs
+    // (~0 = none) [4] n_cuts_total [5] nnz_total [6] first-error row + 1 of the last round
+    unsigned long long* counts;
     int32_t* out_row; int64_t* out_ptr; int32_t* out_col; double* out_val;
     double* out_lo; double* out_hi; double* out_g; double* out_viol;
 };
 
 // Launches the kernels of one round on `stream`; returns the number of kernels launched.
 int ktn_launch_round(const KtnRoundParams& p, uint32_t n_regular, uint32_t n_total_chunks, int num_sms,
-                     int max_smem_optin, cudaStream_t stream, cudaError_t* err);
+                     int max_smem_optin, uint32_t epoch, cudaStream_t stream, cudaError_t* err);
+void ktn_plan_occupancy(uint32_t table_bytes, uint32_t warp_bytes, int max_smem_optin, int* warps_per_block, int* blocks_per_sm);
 // forward evaluation only (ktn_eval_g): writes g_row for every row
 int ktn_launch_eval(const KtnRoundParams& p, uint32_t n_regular, uint32_t n_total_chunks, int num_sms,
                     int max_smem_optin, cudaStream_t stream, cudaError_t* err);

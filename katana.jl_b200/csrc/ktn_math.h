@@ -65,15 +65,8 @@ KTN_HD double ktn_pow2i(int k) { return ktn_bits2d((uint64_t)(k + 1023) << 52); 
 
 // exp(x).  k = round(x/ln2); r = x - k ln2 (two fma steps); exp(r) = 1 + r + r^2 q(r),
 // q = sum_{j=0..11} r^j/(j+2)!  split into even/odd halves for ILP; result scaled by 2^k.
-KTN_HD double ktn_exp(double x) {
-    if (!(x == x)) return x + x;
-    if (x > 709.782712893384) return ktn_inf();
-    if (x < -745.1332191019412) return 0.0;
-    const double SHIFT = 6755399441055744.0; /* 1.5 * 2^52 */
-    double t = x * KTN_INV_LN2;
-    double kd = (t + SHIFT) - SHIFT;
-    double r = ktn_fma(-kd, KTN_LN2_HI, x);
-    r = ktn_fma(-kd, KTN_LN2_LO, r);
+// Full-range path: NaN, +-inf, overflow, gradual underflow.
+KTN_HD double ktn_exp_poly(double r) {
     double z = r * r;
     // even part A(z): 1/2!, 1/4!, 1/6!, 1/8!, 1/10!, 1/12!
     double a = 2.08767569878680989792e-09;              /* 1/12! */
@@ -91,11 +84,40 @@ KTN_HD double ktn_exp(double x) {
     b = ktn_fma(b, z, 1.66666666666666666667e-01);      /* 1/3!  */
     double q = ktn_fma(b, r, a);
     double s = ktn_fma(z, q, r);
-    double y = 1.0 + s;
+    return 1.0 + s;
+}
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+static
+#endif
+double ktn_exp_slow(double x) {
+    if (!(x == x)) return x + x;
+    if (x > 709.782712893384) return ktn_inf();
+    if (x < -745.1332191019412) return 0.0;
+    const double SHIFT = 6755399441055744.0; /* 1.5 * 2^52 */
+    double t = x * KTN_INV_LN2;
+    double kd = (t + SHIFT) - SHIFT;
+    double r = ktn_fma(-kd, KTN_LN2_HI, x);
+    r = ktn_fma(-kd, KTN_LN2_LO, r);
+    double y = ktn_exp_poly(r);
     int k = (int)kd;
     if (k > 1023) return (y * ktn_pow2i(k - 1)) * 2.0;
     if (k < -1021) return (y * ktn_pow2i(k + 54)) * 5.5511151231257827e-17; /* 2^-54: one rounding into the subnormals */
     return y * ktn_pow2i(k);
+}
+// Fast path for |x| <= 708 (result is a normal number): identical arithmetic, k is read from the low
+// word of (t + SHIFT) and added to the exponent field, which equals the multiplication by 2^k bit for bit.
+KTN_HD double ktn_exp(double x) {
+    if (!(ktn_fabs(x) <= 708.0)) return ktn_exp_slow(x);
+    const double SHIFT = 6755399441055744.0;
+    double ts = x * KTN_INV_LN2 + SHIFT;
+    double kd = ts - SHIFT;
+    double r = ktn_fma(-kd, KTN_LN2_HI, x);
+    r = ktn_fma(-kd, KTN_LN2_LO, r);
+    double y = ktn_exp_poly(r);
+    int64_t k = (int64_t)(int32_t)(uint32_t)ktn_d2bits(ts);
+    return ktn_bits2d(ktn_d2bits(y) + ((uint64_t)k << 52));
 }
 
 // Taylor tail of 2*atanh(s) = 2s + s*z*P(z), z = s^2, P(z) = sum_{n>=1} 2/(2n+1) z^(n-1), n = 1..11

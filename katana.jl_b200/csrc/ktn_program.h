@@ -19,11 +19,13 @@
 #define KTN_PROGRAM_H
 #include <stdint.h>
 
-struct KtnIns {
+struct KtnIns {     // 16 bytes, fetched with one 128-bit load
     uint8_t op;
-    uint8_t kind;   // operand kind (KTN_K_*)
-    uint16_t n;     // small immediate (skip count)
-    uint32_t idx;   // operand index
+    uint8_t kind;   // operand kind (KTN_K_*); fused term ops: term kind | flags
+    uint16_t n;     // small immediate (skip count, term count)
+    uint32_t idx;   // operand index; fused term ops: first constant slot
+    uint32_t a;     // fused term ops: first unique-variable slot
+    uint32_t b;     // fused term ops: first save slot
 };
 
 enum { KTN_K_NONE = 0, KTN_K_C = 1, KTN_K_S = 2, KTN_K_R1 = 3, KTN_K_R2 = 4 };
@@ -60,9 +62,26 @@ enum {
     KR_MULSGN,     // acc = revmul(acc, src >= 0 ? 1.0 : -1.0)
     KR_JSET,       // J[idx] = 0.0 + acc
     KR_JACC,       // J[idx] = J[idx] + acc
+    // ---- fused runs of identical terms inside an n-ary sum: the same arithmetic as the primitive
+    //      ops above in the same order, executed by one hand-written loop instead of 4-6 dispatches
+    //      per term.  Term t of the run uses constants idx + t*cstride.., variable slot a + t, save slot b + t.
+    KF_TERMS,      // acc = (FIRST ? 0.0 : acc) + term_0 + term_1 + ...
+    KR_TERMS,      // J[a + t] (=|+=) d term_t / d x * acc        (acc = adjoint of the sum, unchanged)
     K_END,
     K__COUNT
 };
+
+// fused term kinds (low nibble of KtnIns.kind) and flags (high nibble)
+enum {
+    KTN_T_X = 0,        // x
+    KTN_T_MULC_X,       // c * x
+    KTN_T_SQ,           // x ^ 2
+    KTN_T_MULC_SQ,      // c * x ^ 2
+    KTN_T_SQ_MULC,      // (c * x) ^ 2
+    KTN_T_EXP_AFF,      // exp(c * x + d)         saves exp value in S[b + t]
+    KTN_T__COUNT
+};
+enum { KTN_TF_FIRST = 0x10, KTN_TF_JACC = 0x20, KTN_TF_SAVEBLOB = 0x40 };   // SAVEBLOB: exp values are kept in the term's dead `d` constant slot
 
 // shape flags
 enum { KTN_SH_NL = 1, KTN_SH_DENSE = 2, KTN_SH_BIG = 4 };
@@ -76,9 +95,12 @@ struct KtnShapeDesc {
     uint32_t n_scratch;    // scratch slots (incl. XV and J)
     uint32_t flags;        // KTN_SH_*
     uint32_t order_bytes;  // bytes per `order` entry: 1 (n_uniq <= 256), 2 or 4
-    // byte offsets of the blob sections of one chunk (lane stride L rows):
+    // Jacobian accumulator of unique variable u lives at slot j_base + u * j_stride of the scratch
+    // area, or -- when j_in_blob -- of the chunk's constant area (a constant that is dead by then).
+    uint32_t j_base, j_stride, j_in_blob;
+    uint32_t pad;
+    // blob sections of one chunk (lane stride L rows):
     //   consts: n_const * L doubles | cols: n_uniq * L int32 | order: n_uniq * L * order_bytes
-    uint32_t pad[4];
 };
 
 struct KtnChunkDesc {

@@ -472,7 +472,14 @@ int64_t ktn_algorithmic_bytes(ktn_handle* h) {
     int64_t by = 8 * h->num_var;
     for (int64_t i = 0; i < h->num_constr; ++i) {
         if (!(h->flags[i] & KTN_ROW_NL)) continue;
-        int64_t C = 0; for (int64_t k = h->expr_ptr[i]; k < h->expr_ptr[i + 1]; ++k) C += (h->op[k] == KTN_OP_CONST);
+        int64_t C = 0, b0 = h->expr_ptr[i];
+        for (int64_t k = b0; k < h->expr_ptr[i + 1]; ++k) {
+            if (h->op[k] != KTN_OP_CONST) continue;
+            /* the literal exponent of x^2 / x^1 is structure (ReverseDiffSparse special-cases it), not per-row data */
+            int32_t pk = h->parent[k];
+            if (pk >= 0 && h->op[b0 + pk] == KTN_OP_POW && b0 + h->send[pk + 1] == k && (h->val[k] == 2.0 || h->val[k] == 1.0)) continue;
+            ++C;
+        }
         by += 4 * (h->jac_ptr[i + 1] - h->jac_ptr[i]) + 8 * C + 16;
     }
     by += 12 * h->nnz_cuts + 28 * h->n_cuts;

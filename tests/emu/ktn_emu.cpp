@@ -59,26 +59,38 @@ static void run_chunks(ktn_handle* h, const double* x, int mode, const std::vect
             const int32_t row = P.chunk_rows[cd.row_slot + lane];
             if (mode == 0 && !(sd.flags & KTN_SH_NL)) { h->sel[row] = 0; continue; }
             for (uint32_t u = 0; u < nu; ++u) S[(size_t)u * L + lane] = x[cols[(size_t)u * L + lane]];
-            GlobalMem m{(const double*)blob, S.data(), lane, L};
+            // aliased shapes write into their constants: work on a private copy of the chunk blob, as the kernel's
+            // shared-memory staging does
+            std::vector<uint8_t> blobcopy(blob, blob + cd.blob_bytes);
+            double* Cc = (double*)blobcopy.data();
+            double* Jb = sd.j_in_blob ? Cc : S.data();
+            struct EmuMem { double* C; double* S; double* Jp; size_t jmul; uint32_t lane, L;
+                double c(uint32_t i) const { return C[(size_t)i * L + lane]; } void cst(uint32_t i, double v) { C[(size_t)i * L + lane] = v; }
+                double lds(uint32_t i) const { return S[(size_t)i * L + lane]; } void sts(uint32_t i, double v) { S[(size_t)i * L + lane] = v; }
+                double jld(uint32_t u) const { return Jp[(size_t)u * jmul]; } void jst(uint32_t u, double v) { Jp[(size_t)u * jmul] = v; }
+                size_t stride() const { return L; } size_t jstride() const { return jmul; }
+                double* caddr(uint32_t i) const { return C + (size_t)i * L + lane; } double* saddr(uint32_t i) const { return S + (size_t)i * L + lane; }
+                double* jaddr(uint32_t u) const { return Jp + (size_t)u * jmul; } };
+            EmuMem m{Cc, S.data(), Jb + (size_t)sd.j_base * L + lane, (size_t)L * sd.j_stride, lane, L};
             const KtnIns* prog = P.prog.data() + sd.prog_off;
-            const double g = run_program(prog, 0, sd.n_fwd, m, nu, 0u);
+            const double g = run_program(prog, 0, sd.n_fwd, m, 0u);
             h->g_row[row] = g;
             if (mode == 2) continue;
             const double lb = P.chunk_lb[cd.row_slot + lane], ub = P.chunk_ub[cd.row_slot + lane];
             bool selected = mode == 1 ? force[row] != 0 : !((g >= lb - h->opt.f_tol) && (g <= ub + h->opt.f_tol));
             if (!selected) { h->sel[row] = 0; continue; }
-            run_program(prog, sd.n_fwd, sd.n_ins, m, nu, 0u);
+            run_program(prog, sd.n_fwd, sd.n_ins, m, 0u);
             const int64_t base = P.jac_ptr[row];
             if (!(sd.flags & KTN_SH_DENSE)) {
                 double b = g, mx = 0.0;
-                for (uint32_t q = 0; q < nu; ++q) { uint32_t u = ord_at(ord, sd.order_bytes, (size_t)q * L + lane); double jv = S[(size_t)(nu + u) * L + lane], xv = S[(size_t)u * L + lane]; b = b + (-xv) * jv; mx = q == 0 ? jv : ktn_jlmax(mx, jv); }
+                for (uint32_t q = 0; q < nu; ++q) { uint32_t u = ord_at(ord, sd.order_bytes, (size_t)q * L + lane); double jv = m.jld(u), xv = S[(size_t)u * L + lane]; b = b + (-xv) * jv; mx = q == 0 ? jv : ktn_jlmax(mx, jv); }
                 bool bad = false;
-                for (uint32_t q = 0; q < nu; ++q) { uint32_t u = ord_at(ord, sd.order_bytes, (size_t)q * L + lane); double jv = S[(size_t)(nu + u) * L + lane]; if (do_round && jv + h->opt.cut_coef_rng < mx) jv = 0.0; bad = bad || !ktn_isfinite(jv); h->stage_val[base + q] = jv; }
+                for (uint32_t q = 0; q < nu; ++q) { uint32_t u = ord_at(ord, sd.order_bytes, (size_t)q * L + lane); double jv = m.jld(u); if (do_round && jv + h->opt.cut_coef_rng < mx) jv = 0.0; bad = bad || !ktn_isfinite(jv); h->stage_val[base + q] = jv; }
                 h->b_row[row] = b; h->sel[row] = nu | (bad ? KTN_SEL_ERRBIT : 0u);
             } else {
                 const int64_t n = P.num_var; double* out = h->stage_val.data() + base;
                 for (int64_t j = 0; j < n; ++j) out[j] = 0.0;
-                for (uint32_t u = 0; u < nu; ++u) out[cols[(size_t)u * L + lane]] = S[(size_t)(nu + u) * L + lane];
+                for (uint32_t u = 0; u < nu; ++u) out[cols[(size_t)u * L + lane]] = m.jld(u);
                 double b = g, mx = -ktn_inf();
                 for (int64_t j = 0; j < n; ++j) { b = b + (-x[j]) * out[j]; mx = ktn_jlmax(mx, out[j]); }
                 bool bad = false;
@@ -143,3 +155,10 @@ int ktn_allgather_cuts_async(ktn_handle*) { return KTN_ERR_UNSUPPORTED; }
 int ktn_sync_gathered(ktn_handle*, int64_t*, int64_t*) { return KTN_ERR_UNSUPPORTED; }
 int ktn_fetch_gathered(ktn_handle*, int64_t*, int64_t*, int32_t*, double*, double*, double*, double*, double*) { return KTN_ERR_UNSUPPORTED; }
 }
+extern "C" int ktn_emu_shape_info(ktn_handle* h, int64_t sid, uint32_t* out /* n_fwd, n_ins, n_uniq, n_const, n_scratch, flags */) {
+    if (sid < 0 || sid >= (int64_t)h->prob.shapes.size()) return -1;
+    const KtnShapeDesc& s = h->prob.shapes[sid];
+    out[0] = s.n_fwd; out[1] = s.n_ins; out[2] = s.n_uniq; out[3] = s.n_const; out[4] = s.n_scratch; out[5] = s.flags; out[6] = s.j_in_blob; out[7] = s.j_base; out[8] = s.j_stride; return 0; }
+extern "C" int ktn_emu_shape_prog(ktn_handle* h, int64_t sid, uint32_t* out /* 4 words per instruction */) {
+    const KtnShapeDesc& s = h->prob.shapes[sid];
+    memcpy(out, h->prob.prog.data() + s.prog_off, 16 * (size_t)s.n_ins); return 0; }
