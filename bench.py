@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the ECP separation round (BASELINE.json metric: nonlinear constraints linearised per second
+per separation round) on synthetic instances of SURVEY.md section 8d.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (N > 1: launched by torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle restatement)
+
+A step is one separation round over the workload: evaluate g(x*) and the Jacobian rows of every nonlinear row,
+test violation, emit the violated rows' cuts as CSR (and, for N > 1, combine all ranks' cuts over NCCL).
+`value`: rounds with x* already resident in HBM, CUDA-event timed on the launching stream.
+`e2e`:   the same round through the reference-facing separator call with HOST buffers (x* upload and cut
+         download inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (synth kind, seed, description)
+    "lse": (1, 20260002, "configs[2]: synthetic log-sum-exp rows log sum_k exp(a_k x_jk + b_k), K in 4..16"),
+    "qcqp": (0, 20260001, "configs[1] family: sparse convex QCQP rows sum a x^2 + sum b x, 8 columns per row"),
+    "soc": (2, 20260003, "configs[3] NL rows: sqrt(sum (s x)^2) - t"),
+}
+METRIC = "nonlinear cons linearised/sec per separation round"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Polls SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop = [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4, "hw_power_brake": 0x80}
+        while not self.stop:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        if self.nv:
+            self.t.join(timeout=1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_instance(lib, kind, seed, nv, row_begin, nrows):
+    w = lib.synth_rows(kind, seed, nv, row_begin, nrows)
+    x0 = lib.synth_point(kind, seed, nv)
+    return w, x0
+
+
+def cpu_rounds(oracle, w, x0, nv, ub, threads, seconds_budget, min_rounds=2):
+    """Times the oracle's separation round (the reference algorithm, all rows, full Jacobian) on host cores."""
+    os.environ["KTN_ORACLE_THREADS"] = str(threads)
+    h = oracle.create()
+    h.load(nv, w)
+    h.set_bounds(w.lb, ub)
+    h.separate(x0, fetch=False)
+    ts = []
+    t_end = time.perf_counter() + seconds_budget
+    while len(ts) < min_rounds or (time.perf_counter() < t_end and len(ts) < 50):
+        t0 = time.perf_counter()
+        st, nc, nz, er = h.separate(x0, fetch=False)
+        ts.append(time.perf_counter() - t0)
+    h.close()
+    return float(np.median(ts)), len(ts), nc
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm for the path.  The reference is Julia over un-vendored
+    packages and cannot be built or run here, so this arm times the oracle (its C restatement) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import katana_jl_b200  # noqa: F401
+    from katana_jl_b200.binding import CUDA_LIB_PATH, KtnLibrary
+    synth = KtnLibrary(CUDA_LIB_PATH)      # generators only
+    oracle = KtnLibrary(os.path.join(ROOT, "oracle", "libktn_oracle.so"))
+    kind, seed, desc = WORKLOADS[args.workload]
+    nv = args.vars
+    rows = args.rows                      # the CPU arm processes one GPU's share of the weak-scaling workload per step
+    w, x0 = make_instance(synth, kind, seed, nv, 0, rows)
+    h = oracle.create(); h.load(nv, w); g = h.eval_g(x0); h.close()
+    ub = np.full(rows, np.quantile(g, 1 - args.v))
+    threads = os.cpu_count() or 1
+    os.environ["KTN_ORACLE_THREADS"] = str(threads)
+    h = oracle.create(); h.load(nv, w); h.set_bounds(w.lb, ub)
+    for _ in range(args.warmup):
+        h.separate(x0, fetch=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st, nc, nz, er = h.separate(x0, fetch=False)
+    dt = time.perf_counter() - t0
+    value = rows * args.steps / dt
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "constraints/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}; m={rows} rows, n={nv} vars, violated fraction {args.v}", "rows_per_step": rows},
+        "cpu_baseline": {"value": value, "unit": "constraints/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} full rounds over {rows} rows (C restatement of the Katana.jl separator, OpenMP over rows; not Julia)"},
+        "e2e": {"value": value, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lse", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=1000000, help="nonlinear rows per GPU (weak scaling)")
+    ap.add_argument("--vars", type=int, default=100000)
+    ap.add_argument("--v", type=float, default=0.1, help="violated fraction of the rows at x*")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import katana_jl_b200  # noqa: F401
+    from katana_jl_b200.binding import KtnLibrary, comm_unique_id, load_cuda_library
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = load_cuda_library()              # fails loudly if libktn.so is missing: there is no CPU fallback
+    kind, seed, desc = WORKLOADS[args.workload]
+    nv, rows = args.vars, args.rows
+    row_begin = rank * rows               # weak scaling: every GPU owns `rows` rows of an instance with world*rows rows
+    w, x0 = make_instance(lib, kind, seed, nv, row_begin, rows)
+    h = lib.create(device=local)
+    h.load(nv, w)
+    h.set_row_offset(row_begin)
+    g = h.eval_g(x0)
+    ub = np.full(rows, np.quantile(g, 1 - args.v))
+    h.set_bounds(w.lb, ub)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(comm_unique_id(lib)), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        h.comm_init(world, rank, bytes(idt.cpu().numpy().tobytes()))
+    stream = torch.cuda.current_stream()
+    h.set_stream(stream.cuda_stream)
+    dx = torch.from_numpy(x0).cuda()
+
+    def step():
+        h.separate_device_async(dx.data_ptr())
+        if world > 1:
+            h.allgather_cuts_async()       # pack + sizes + grouped broadcasts over NVLink (host reads the sizes)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident rounds -------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    st, n_cuts, nnz, err = h.sync_counts()
+    t_before = h.timings()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    t_after = h.timings()
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * rows / (ms_per_step * 1e-3)
+    launches = t_after["launches"] - t_before["launches"]
+    timed = max(1, t_after["rounds_timed"] - t_before["rounds_timed"])
+    k1_ms = (t_after["eval_ms_sum"] - t_before["eval_ms_sum"]) / timed
+    k2_ms = (t_after["compact_ms_sum"] - t_before["compact_ms_sum"]) / timed
+
+    # ---- e2e: the separator call a Katana user makes, host buffers in and out ------------------------------------
+    h.set_stream(0)
+    from katana_jl_b200.separators import KatanaGPUSeparator
+    sep = KatanaGPUSeparator(); sep.handle = h; sep.num_var, sep.num_constr = nv, rows
+    x_host = x0.copy()
+    for _ in range(3):
+        batch = sep.separate(x_host)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        batch = sep.separate(x_host)
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_value = world * rows * e2e_steps / e2e_dt
+    h2d_bytes = 8 * nv
+    d2h_bytes = 64 + batch.n_cuts * (4 + 8 + 5 * 8) + len(batch.col) * 12
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (K1) and of the whole round ---------------------------------------------
+    peak, peak_src = load_peaks()
+    alg_round = h.algorithmic_bytes()                      # sum_NL(4 nnz + 8 C + 16) + 8 n + sum_sel(12 nnz + 28)
+    alg_k1 = alg_round - 4 * nnz - 20 * n_cuts             # K1 reads the inputs and writes coefficient values + constant of the selected rows
+    achieved = alg_k1 / (k1_ms * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}; m={rows} rows/GPU, n={nv} vars, violated fraction {args.v}, f_tol 1e-6",
+                   "rows_per_gpu": rows, "num_var": nv, "violated_fraction": args.v, "cuts_per_round_per_gpu": n_cuts, "cut_nnz_per_round_per_gpu": nnz,
+                   "l2": f"no flush needed: one round streams {alg_round / 1e6:.0f} MB of inputs > 126 MB L2",
+                   "exchange": "none" if world == 1 else "NCCL: sizes allgather + one grouped broadcast per rank of the packed cut blob"},
+        "roofline": {"bound": "hbm", "kernel": "ktn_round_kernel (K1: evaluate, test, reverse sweep, cut rows)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_k1, "ms_per_launch": k1_ms,
+                     "round": {"algorithmic_bytes": alg_round, "ms": k1_ms + k2_ms, "frac": alg_round / ((k1_ms + k2_ms) * 1e-3) / 1e9 / peak,
+                               "k2_compact_ms": k2_ms}},
+        "e2e": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": 1e3 * e2e_dt / e2e_steps, "steps": e2e_steps, "call": "KatanaGPUSeparator.separate(xstar) -> CutBatch (ktn_separate + ktn_fetch_cuts)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+    }
+    traffic_file = os.path.join(ROOT, "profiles", "k1_dram_traffic.json")
+    if os.path.exists(traffic_file):
+        tr = json.load(open(traffic_file)).get(args.workload)
+        if tr and tr.get("rows") == rows and abs(tr.get("v", -1) - args.v) < 1e-9:
+            out["roofline"]["traffic"] = tr["dram_bytes"]
+
+    # ---- cpu_baseline: the reference algorithm on this box's host cores (N = 1 only) -----------------------------
+    if world == 1 and not args.no_cpu:
+        oracle = KtnLibrary(os.path.join(ROOT, "oracle", "libktn_oracle.so"))
+        sample_rows = min(rows, 1000000)
+        ws, _ = (w, None) if sample_rows == rows else make_instance(lib, kind, seed, nv, 0, sample_rows)
+        med1, n1, nc1 = cpu_rounds(oracle, ws, x0, nv, ub[:sample_rows], 1, args.cpu_seconds)
+        cores = os.cpu_count() or 1
+        medn, nn, _ = cpu_rounds(oracle, ws, x0, nv, ub[:sample_rows], cores, args.cpu_seconds / 3)
+        out["cpu_baseline"] = {"value": sample_rows / med1, "unit": "constraints/s", "cores": 1, "kind": "port",
+                               "sample": f"median of {n1} rounds over {sample_rows} rows of the same workload, 1 thread (the reference is single-threaded); "
+                                         "C restatement of the Katana.jl separator, not Julia",
+                               "all_cores": {"value": sample_rows / medn, "cores": cores, "rounds": nn}}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

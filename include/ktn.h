@@ -88,6 +88,11 @@ typedef struct ktn_timings {
     double d2h_ms;        /* cut download in ktn_fetch_cuts */
     int64_t launches;     /* kernels launched by this library since creation */
     int64_t rounds;       /* separation rounds run since creation */
+    double eval_ms;       /* last round: evaluation kernel(s) (K1) */
+    double compact_ms;    /* last round: compaction kernel (K2) */
+    double eval_ms_sum;   /* sums over every round timed since creation (CUDA events on the round's stream) */
+    double compact_ms_sum;
+    int64_t rounds_timed;
 } ktn_timings;
 
 /* lifetime -- replaces constructing KatanaFirstOrderSeparator() (src/separators.jl:58-77). */
@@ -141,9 +146,10 @@ int ktn_gencut_rows(ktn_handle* h, const double* x, const int64_t* rows, int64_t
  *   row_ptr[c] .. row_ptr[c+1]     its entries in col[] / val[]   (row_ptr has n_cuts+1 entries)
  *   lo[c], hi[c]                   LP row bounds lb - b, ub - b   (src/model.jl:74-75)
  *   g[c], viol[c]                  g_i(x*) and max(lb - g, g - ub)
+ *   bconst[c]                      the AffExpr constant b of src/algorithms.jl:8-17 (lo = lb - b, hi = ub - b)
  * Any output pointer may be NULL to skip that array. */
 int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val,
-                   double* lo, double* hi, double* g, double* viol);
+                   double* lo, double* hi, double* g, double* viol, double* bconst);
 
 /* All constraint values of the last round (sep.g, src/separators.jl:113) -- backs the
  * per-row isconstrsat(sep, i, lb, ub, f_tol) compatibility hook (src/separators.jl:120). */
@@ -167,12 +173,14 @@ int64_t ktn_algorithmic_bytes(ktn_handle* h);
 /* 128-byte NCCL unique id, created on rank 0 and broadcast by the host's own plumbing. */
 int ktn_comm_unique_id(void* id128);
 int ktn_comm_init(ktn_handle* h, int32_t nranks, int32_t rank, const void* id128);
+/* Global index of this handle's first row: row ids delivered by ktn_fetch_cuts / ktn_fetch_gathered are shifted by it. */
+int ktn_set_row_offset(ktn_handle* h, int64_t first_global_row);
 /* Combine every rank's compacted cuts (rank-major = ascending row order) on every GPU over
  * NCCL/NVLink; enqueued on the stream after the last round.  Totals are returned after a sync. */
 int ktn_allgather_cuts_async(ktn_handle* h);
 int ktn_sync_gathered(ktn_handle* h, int64_t* total_cuts, int64_t* total_nnz);
 int ktn_fetch_gathered(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val,
-                       double* lo, double* hi, double* g, double* viol);
+                       double* lo, double* hi, double* g, double* viol, double* bconst);
 
 /* ---- deterministic synthetic instances (test / bench support) ----
  * kind: 0 = sparse convex QCQP (config 2), 1 = log-sum-exp (config 3), 2 = SOC-like risk rows (config 4).

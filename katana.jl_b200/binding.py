@@ -31,7 +31,8 @@ class ktn_options(C.Structure):
 
 class ktn_timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("exchange_ms", C.c_double),
-                ("d2h_ms", C.c_double), ("launches", C.c_int64), ("rounds", C.c_int64)]
+                ("d2h_ms", C.c_double), ("launches", C.c_int64), ("rounds", C.c_int64), ("eval_ms", C.c_double), ("compact_ms", C.c_double),
+                ("eval_ms_sum", C.c_double), ("compact_ms_sum", C.c_double), ("rounds_timed", C.c_int64)]
 
 
 _P = C.c_void_p
@@ -50,7 +51,7 @@ _SIGS = {
     "ktn_jac_nnz": (C.c_int64, [_P]),
     "ktn_separate": (C.c_int, [_P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ktn_gencut_rows": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
-    "ktn_fetch_cuts": (C.c_int, [_P] + [_P] * 8),
+    "ktn_fetch_cuts": (C.c_int, [_P] + [_P] * 9),
     "ktn_get_g": (C.c_int, [_P, _P]),
     "ktn_eval_g": (C.c_int, [_P, _P, _P]),
     "ktn_timings_get": (C.c_int, [_P, C.POINTER(ktn_timings)]),
@@ -60,9 +61,10 @@ _SIGS = {
     "ktn_algorithmic_bytes": (C.c_int64, [_P]),
     "ktn_comm_unique_id": (C.c_int, [_P]),
     "ktn_comm_init": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "ktn_set_row_offset": (C.c_int, [_P, C.c_int64]),
     "ktn_allgather_cuts_async": (C.c_int, [_P]),
     "ktn_sync_gathered": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
-    "ktn_fetch_gathered": (C.c_int, [_P] + [_P] * 8),
+    "ktn_fetch_gathered": (C.c_int, [_P] + [_P] * 9),
 }
 # exported by the CUDA library only (test / bench support, include/ktn.h bottom)
 _SYNTH_SIGS = {
@@ -150,6 +152,7 @@ class CutBatch:
     hi: np.ndarray
     g: np.ndarray
     viol: np.ndarray
+    bconst: np.ndarray
 
     @property
     def n_cuts(self):
@@ -227,9 +230,9 @@ class Handle:
     # ---- rounds ----
     def _fetch(self, status, nc, nz, err, gathered=False):
         b = CutBatch(status, err, np.empty(nc, np.int64), np.empty(nc + 1, np.int64), np.empty(nz, np.int32), np.empty(nz, np.float64),
-                     np.empty(nc, np.float64), np.empty(nc, np.float64), np.empty(nc, np.float64), np.empty(nc, np.float64))
+                     np.empty(nc, np.float64), np.empty(nc, np.float64), np.empty(nc, np.float64), np.empty(nc, np.float64), np.empty(nc, np.float64))
         fn = self.dll.ktn_fetch_gathered if gathered else self.dll.ktn_fetch_cuts
-        self._ck(fn(self.h, _ptr(b.row_id), _ptr(b.row_ptr), _ptr(b.col), _ptr(b.val), _ptr(b.lo), _ptr(b.hi), _ptr(b.g), _ptr(b.viol)),
+        self._ck(fn(self.h, _ptr(b.row_id), _ptr(b.row_ptr), _ptr(b.col), _ptr(b.val), _ptr(b.lo), _ptr(b.hi), _ptr(b.g), _ptr(b.viol), _ptr(b.bconst)),
                  "ktn_fetch_cuts")
         return b
 
@@ -287,6 +290,9 @@ class Handle:
     def comm_init(self, nranks, rank, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)
         self._ck(self.dll.ktn_comm_init(self.h, nranks, rank, buf), "ktn_comm_init")
+
+    def set_row_offset(self, first_global_row):
+        self._ck(self.dll.ktn_set_row_offset(self.h, first_global_row), "ktn_set_row_offset")
 
     def allgather_cuts_async(self):
         self._ck(self.dll.ktn_allgather_cuts_async(self.h), "ktn_allgather_cuts_async")

@@ -8,45 +8,9 @@
 #include <cstring>
 #include <string>
 #include <vector>
-#include "../../include/ktn.h"
-#include "ktn_compile.h"
-#include "ktn_kernels.cuh"
+#include "ktn_handle.h"
 
-#define KTN_LANE_LIMIT 1536u   // max per-lane shared-memory bytes of a regular (shared-memory staged) shape
-
-struct DevBuf {
-    void* p = nullptr; size_t bytes = 0;
-    cudaError_t alloc(size_t n) { release(); bytes = n; if (n == 0) return cudaSuccess; return cudaMalloc(&p, n); }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
-    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-struct ktn_handle {
-    ktn_options opt;
-    int device = 0, num_sms = 0, max_smem = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
-    KtnProblem prob;
-    bool loading = false, loaded = false, round_pending = false, have_round = false;
-    DevBuf chunks, shapes, prog, blob, chunk_rows, chunk_lb, chunk_ub, jac_ptr, jac_col, row_lb, row_ub;
-    DevBuf x, force, g_row, b_row, sel, stage_val, big_scratch, ticket, st_flag, st_cnt, st_nnz, counts, table;
-    DevBuf out_row, out_ptr, out_col, out_val, out_lo, out_hi, out_g, out_viol;
-    double* h_x = nullptr;                 // pinned
-    unsigned long long* h_counts = nullptr;  // pinned [8]
-    int64_t n_cuts = 0, nnz_cuts = 0, err_row = -1;
-    uint32_t warp_bytes = 0, blob_cap = 0, table_bytes = 0, table_prog_off = 0, epoch = 0;
-    ktn_timings tm;
-    std::string err;
-    // sharding (ktn_comm.cpp)
-    void* comm = nullptr; int nranks = 1, rank = 0;
-};
-
-static int fail(ktn_handle* h, int code, const char* fmt, ...) {
-    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
-    if (h) h->err = buf;
-    return code;
-}
-#define CK(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(h, KTN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+void ktn_comm_release(ktn_handle* h);
 
 extern "C" const char* ktn_backend(void) { return "cuda"; }
 extern "C" const char* ktn_last_error(ktn_handle* h) { return h ? h->err.c_str() : "null handle"; }
@@ -54,7 +18,7 @@ extern "C" const char* ktn_last_error(ktn_handle* h) { return h ? h->err.c_str()
 static void free_problem(ktn_handle* h) {
     DevBuf* all[] = {&h->chunks, &h->shapes, &h->prog, &h->blob, &h->chunk_rows, &h->chunk_lb, &h->chunk_ub, &h->jac_ptr, &h->jac_col,
                      &h->row_lb, &h->row_ub, &h->x, &h->force, &h->g_row, &h->b_row, &h->sel, &h->stage_val, &h->big_scratch,
-                     &h->st_flag, &h->st_cnt, &h->st_nnz, &h->table, &h->out_row, &h->out_ptr, &h->out_col, &h->out_val, &h->out_lo, &h->out_hi, &h->out_g, &h->out_viol};
+                     &h->st_flag, &h->st_cnt, &h->st_nnz, &h->table, &h->out_row, &h->out_ptr, &h->out_col, &h->out_val, &h->out_lo, &h->out_hi, &h->out_g, &h->out_viol, &h->out_b};
     for (DevBuf* b : all) b->release();
     if (h->h_x) { cudaFreeHost(h->h_x); h->h_x = nullptr; }
     h->prob = KtnProblem();
@@ -83,6 +47,8 @@ extern "C" int ktn_create(const ktn_options* o, ktn_handle** out) {
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
     h->stream = h->own_stream;
     cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
+    cudaEventCreate(&h->evx0); cudaEventCreate(&h->evx1);
+    for (int i = 0; i < ktn_handle::RING; ++i) for (int j = 0; j < 3; ++j) cudaEventCreate(&h->ring[i][j]);
     if (cudaMallocHost(&h->h_counts, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
     if (h->ticket.alloc(16) != cudaSuccess || h->counts.alloc(8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
     cudaMemset(h->ticket.p, 0, 16);
@@ -99,7 +65,12 @@ extern "C" void ktn_destroy(ktn_handle* h) {
     free_problem(h);
     h->ticket.release(); h->counts.release();
     if (h->h_counts) cudaFreeHost(h->h_counts);
-    if (h->ev0) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3); }
+    ktn_comm_release(h);
+    if (h->ev0) {
+        cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
+        cudaEventDestroy(h->evx0); cudaEventDestroy(h->evx1);
+        for (int i = 0; i < ktn_handle::RING; ++i) for (int j = 0; j < 3; ++j) cudaEventDestroy(h->ring[i][j]);
+    }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -187,7 +158,7 @@ extern "C" int ktn_load_end(ktn_handle* h) {
     CK(h, cudaMemset(h->st_flag.p, 0, 4 * nblk));
     CK(h, upload(h->table, table));
     CK(h, h->out_row.alloc(4 * (m + 1))); CK(h, h->out_ptr.alloc(8 * (m + 2))); CK(h, h->out_col.alloc(4 * (N + 1))); CK(h, h->out_val.alloc(8 * (N + 1)));
-    CK(h, h->out_lo.alloc(8 * (m + 1))); CK(h, h->out_hi.alloc(8 * (m + 1))); CK(h, h->out_g.alloc(8 * (m + 1))); CK(h, h->out_viol.alloc(8 * (m + 1)));
+    CK(h, h->out_lo.alloc(8 * (m + 1))); CK(h, h->out_hi.alloc(8 * (m + 1))); CK(h, h->out_g.alloc(8 * (m + 1))); CK(h, h->out_viol.alloc(8 * (m + 1))); CK(h, h->out_b.alloc(8 * (m + 1)));
     CK(h, cudaMallocHost(&h->h_x, 8 * ((size_t)P.num_var + 1)));
     // the packed blob lives on the device now
     std::vector<uint8_t>().swap(P.blob);
@@ -218,7 +189,7 @@ extern "C" int ktn_jac_structure(ktn_handle* h, int64_t* row_ptr, int32_t* cols)
     return KTN_OK;
 }
 
-static KtnRoundParams make_params(ktn_handle* h, const double* d_x, int mode, int do_round) {
+KtnRoundParams ktn_make_params(ktn_handle* h, const double* d_x, int mode, int do_round) {
     KtnRoundParams p; memset(&p, 0, sizeof p);
     p.chunks = h->chunks.as<KtnChunkDesc>(); p.shapes = h->shapes.as<KtnShapeDesc>(); p.prog = h->prog.as<KtnIns>();
     p.blob = h->blob.as<uint8_t>(); p.chunk_rows = h->chunk_rows.as<int32_t>();
@@ -233,21 +204,39 @@ static KtnRoundParams make_params(ktn_handle* h, const double* d_x, int mode, in
     p.stage_val = h->stage_val.as<double>(); p.big_scratch = h->big_scratch.as<double>(); p.ticket = h->ticket.as<unsigned int>();
     p.st_flag = h->st_flag.as<uint32_t>(); p.st_cnt = h->st_cnt.as<uint32_t>(); p.st_nnz = h->st_nnz.as<unsigned long long>();
     p.counts = h->counts.as<unsigned long long>();
+    p.row_offset = h->row_offset;
     p.table = h->table.as<unsigned char>(); p.table_bytes = h->table_bytes; p.table_prog_off = h->table_prog_off; p.epoch = h->epoch;
     p.out_row = h->out_row.as<int32_t>(); p.out_ptr = h->out_ptr.as<int64_t>(); p.out_col = h->out_col.as<int32_t>(); p.out_val = h->out_val.as<double>();
-    p.out_lo = h->out_lo.as<double>(); p.out_hi = h->out_hi.as<double>(); p.out_g = h->out_g.as<double>(); p.out_viol = h->out_viol.as<double>();
+    p.out_lo = h->out_lo.as<double>(); p.out_hi = h->out_hi.as<double>(); p.out_g = h->out_g.as<double>(); p.out_viol = h->out_viol.as<double>(); p.out_b = h->out_b.as<double>();
     return p;
+}
+
+static void drain_ring(ktn_handle* h, bool all) {
+    while (h->ring_tail != h->ring_head) {
+        cudaEvent_t* e = h->ring[h->ring_tail % ktn_handle::RING];
+        if (!all && cudaEventQuery(e[2]) != cudaSuccess) break;
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, e[0], e[1]) == cudaSuccess && cudaEventElapsedTime(&b, e[1], e[2]) == cudaSuccess) {
+            h->eval_ms_sum += a; h->compact_ms_sum += b; h->rounds_timed++;
+            h->tm.kernel_ms = a + b; h->tm.eval_ms = a; h->tm.compact_ms = b;
+        }
+        h->ring_tail++;
+    }
 }
 
 static int enqueue_round(ktn_handle* h, const double* d_x, int mode, int do_round) {
     h->epoch = (h->epoch % 0x3ffffff0u) + 1u;
-    KtnRoundParams p = make_params(h, d_x, mode, do_round);
+    KtnRoundParams p = ktn_make_params(h, d_x, mode, do_round);
     cudaError_t e = cudaSuccess;
-    CK(h, cudaEventRecord(h->ev1, h->stream));
-    int n = ktn_launch_round(p, h->prob.n_regular_chunks, (uint32_t)h->prob.chunks.size(), h->num_sms, h->max_smem, h->epoch, h->stream, &e);
+    if (h->ring_head - h->ring_tail >= ktn_handle::RING) drain_ring(h, false);
+    if (h->ring_head - h->ring_tail >= ktn_handle::RING) { CK(h, cudaEventSynchronize(h->ring[h->ring_tail % ktn_handle::RING][2])); drain_ring(h, false); }
+    cudaEvent_t* ev = h->ring[h->ring_head % ktn_handle::RING];
+    CK(h, cudaEventRecord(ev[0], h->stream));
+    int n = ktn_launch_round(p, h->prob.n_regular_chunks, (uint32_t)h->prob.chunks.size(), h->num_sms, h->max_smem, h->epoch, h->stream, ev[1], &e);
     h->tm.launches += n;
     if (e != cudaSuccess) return fail(h, KTN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
-    CK(h, cudaEventRecord(h->ev2, h->stream));
+    CK(h, cudaEventRecord(ev[2], h->stream));
+    h->ring_head++;
     CK(h, cudaMemcpyAsync(h->h_counts, h->counts.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     h->round_pending = true; h->tm.rounds++;
     return KTN_OK;
@@ -257,8 +246,7 @@ static int finish_round(ktn_handle* h, int64_t* n_cuts, int64_t* nnz, int64_t* e
     if (!h->round_pending) return fail(h, KTN_ERR_USAGE, "no round is pending");
     CK(h, cudaStreamSynchronize(h->stream));
     h->round_pending = false; h->have_round = true;
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, h->ev1, h->ev2) == cudaSuccess) h->tm.kernel_ms = ms;
+    drain_ring(h, true);
     h->n_cuts = (int64_t)h->h_counts[0]; h->nnz_cuts = (int64_t)h->h_counts[1];
     h->err_row = h->h_counts[6] == ~0ull ? -1 : (int64_t)h->h_counts[6] - 1;
     if (n_cuts) *n_cuts = h->n_cuts;
@@ -302,7 +290,7 @@ extern "C" int ktn_gencut_rows(ktn_handle* h, const double* x, const int64_t* ro
 }
 
 extern "C" int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val,
-                              double* lo, double* hi, double* g, double* viol) {
+                              double* lo, double* hi, double* g, double* viol, double* bconst) {
     if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
     if (h->round_pending) { int rc = finish_round(h, nullptr, nullptr, nullptr); if (rc < 0) return rc; }
     cudaSetDevice(h->device);
@@ -312,7 +300,7 @@ extern "C" int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, 
         std::vector<int32_t> tmp(nc);
         CK(h, cudaMemcpyAsync(tmp.data(), h->out_row.p, 4 * nc, cudaMemcpyDeviceToHost, h->stream));
         CK(h, cudaStreamSynchronize(h->stream));
-        for (size_t i = 0; i < nc; ++i) row_id[i] = tmp[i];
+        for (size_t i = 0; i < nc; ++i) row_id[i] = tmp[i] + h->row_offset;
     }
     if (row_ptr) { if (nc) CK(h, cudaMemcpyAsync(row_ptr, h->out_ptr.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream)); }
     if (col && nz) CK(h, cudaMemcpyAsync(col, h->out_col.p, 4 * nz, cudaMemcpyDeviceToHost, h->stream));
@@ -321,6 +309,7 @@ extern "C" int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, 
     if (hi && nc) CK(h, cudaMemcpyAsync(hi, h->out_hi.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
     if (g && nc) CK(h, cudaMemcpyAsync(g, h->out_g.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
     if (viol && nc) CK(h, cudaMemcpyAsync(viol, h->out_viol.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+    if (bconst && nc) CK(h, cudaMemcpyAsync(bconst, h->out_b.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaEventRecord(h->ev3, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     if (row_ptr) row_ptr[nc] = (int64_t)nz;   // the device array ends at the untruncated total
@@ -340,7 +329,7 @@ extern "C" int ktn_eval_g(ktn_handle* h, const double* x, double* g_out) {
     if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
     cudaSetDevice(h->device);
     int rc = upload_x(h, x); if (rc) return rc;
-    KtnRoundParams p = make_params(h, h->x.as<double>(), KTN_MODE_SEPARATE, 0);
+    KtnRoundParams p = ktn_make_params(h, h->x.as<double>(), KTN_MODE_SEPARATE, 0);
     cudaError_t e = cudaSuccess;
     h->tm.launches += ktn_launch_eval(p, h->prob.n_regular_chunks, (uint32_t)h->prob.chunks.size(), h->num_sms, h->max_smem, h->stream, &e);
     if (e != cudaSuccess) return fail(h, KTN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -349,7 +338,14 @@ extern "C" int ktn_eval_g(ktn_handle* h, const double* x, double* g_out) {
     return KTN_OK;
 }
 
-extern "C" int ktn_timings_get(ktn_handle* h, ktn_timings* out) { if (!h || !out) return KTN_ERR_USAGE; *out = h->tm; return KTN_OK; }
+extern "C" int ktn_timings_get(ktn_handle* h, ktn_timings* out) {
+    if (!h || !out) return KTN_ERR_USAGE;
+    cudaSetDevice(h->device);
+    drain_ring(h, false);
+    h->tm.eval_ms_sum = h->eval_ms_sum; h->tm.compact_ms_sum = h->compact_ms_sum; h->tm.rounds_timed = h->rounds_timed;
+    *out = h->tm;
+    return KTN_OK;
+}
 
 extern "C" int ktn_set_stream(ktn_handle* h, void* s) {
     if (!h) return KTN_ERR_USAGE;
@@ -376,10 +372,3 @@ extern "C" int64_t ktn_algorithmic_bytes(ktn_handle* h) {
     return h->prob.alg_bytes_static + 12 * h->nnz_cuts + 28 * h->n_cuts;
 }
 
-// ---- sharded operation: see ktn_comm.cpp (NCCL is loaded lazily so the library works without it) ----
-extern "C" int ktn_comm_unique_id(void* id128) { (void)id128; return KTN_ERR_UNSUPPORTED; }
-extern "C" int ktn_comm_init(ktn_handle* h, int32_t nranks, int32_t rank, const void* id) { (void)nranks; (void)rank; (void)id; return fail(h, KTN_ERR_UNSUPPORTED, "sharded operation not built yet"); }
-extern "C" int ktn_allgather_cuts_async(ktn_handle* h) { return fail(h, KTN_ERR_UNSUPPORTED, "sharded operation not built yet"); }
-extern "C" int ktn_sync_gathered(ktn_handle* h, int64_t* a, int64_t* b) { (void)a; (void)b; return fail(h, KTN_ERR_UNSUPPORTED, "sharded operation not built yet"); }
-extern "C" int ktn_fetch_gathered(ktn_handle* h, int64_t* a, int64_t* b, int32_t* c, double* d, double* e, double* f, double* g, double* v) {
-    (void)a; (void)b; (void)c; (void)d; (void)e; (void)f; (void)g; (void)v; return fail(h, KTN_ERR_UNSUPPORTED, "sharded operation not built yet"); }

@@ -1,0 +1,157 @@
+// ktn_comm.cu -- sharded operation: every GPU separates its contiguous slice of the constraint rows, then the
+// compacted cuts of all ranks are combined on every GPU over NCCL / NVLink.
+// Rank-major concatenation is ascending row order, the reference's emission order (src/model.jl:272).
+// NCCL is loaded lazily with dlopen so libktn.so has no link-time dependency on it.
+#include <dlfcn.h>
+#include <cstring>
+#include "ktn_handle.h"
+
+KtnRoundParams ktn_make_params(ktn_handle* h, const double* d_x, int mode, int do_round);
+
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclUint8 = 1, ncclUint64 = 5 };
+struct Nccl {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+} N;
+
+bool load_nccl(std::string* why) {
+    if (N.ok) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) { N.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (N.lib) break; }
+    if (!N.lib) { *why = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+#define SYM(f) *(void**)(&N.f) = dlsym(N.lib, "nccl" #f); if (!N.f) { *why = "missing symbol nccl" #f; return false; }
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(AllGather) SYM(Broadcast) SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString)
+#undef SYM
+    N.ok = true;
+    return true;
+}
+}  // namespace
+
+#define NK(h, call) do { ncclResult_t r__ = (call); if (r__ != 0) return fail(h, KTN_ERR_NCCL, "%s failed: %s", #call, N.GetErrorString(r__)); } while (0)
+
+void ktn_comm_release(ktn_handle* h) {
+    if (h->comm && N.ok) N.CommDestroy((ncclComm_t)h->comm);
+    h->comm = nullptr;
+    h->sendbuf.release(); h->gathered.release(); h->all_counts.release();
+    if (h->h_all_counts) { cudaFreeHost(h->h_all_counts); h->h_all_counts = nullptr; }
+}
+
+extern "C" int ktn_comm_unique_id(void* id128) {
+    std::string why;
+    if (!id128 || !load_nccl(&why)) { fprintf(stderr, "libktn: %s\n", why.c_str()); return KTN_ERR_NCCL; }
+    ncclUniqueId id; if (N.GetUniqueId(&id) != 0) return KTN_ERR_NCCL;
+    memcpy(id128, &id, 128);
+    return KTN_OK;
+}
+
+extern "C" int ktn_comm_init(ktn_handle* h, int32_t nranks, int32_t rank, const void* id128) {
+    if (!h || nranks < 1 || rank < 0 || rank >= nranks || !id128) return fail(h, KTN_ERR_USAGE, "bad communicator arguments");
+    std::string why;
+    if (!load_nccl(&why)) return fail(h, KTN_ERR_NCCL, "%s", why.c_str());
+    cudaSetDevice(h->device);
+    ktn_comm_release(h);
+    ncclUniqueId id; memcpy(&id, id128, 128);
+    ncclComm_t c = nullptr;
+    NK(h, N.CommInitRank(&c, nranks, id, rank));
+    h->comm = c; h->nranks = nranks; h->rank = rank;
+    CK(h, h->all_counts.alloc(16 * (size_t)nranks + 64));
+    CK(h, cudaMallocHost(&h->h_all_counts, 16 * (size_t)nranks + 64));
+    h->g_cuts.assign(nranks, 0); h->g_nnz.assign(nranks, 0); h->g_off.assign(nranks + 1, 0);
+    return KTN_OK;
+}
+
+extern "C" int ktn_set_row_offset(ktn_handle* h, int64_t first_global_row) {
+    if (!h) return KTN_ERR_USAGE;
+    h->row_offset = first_global_row;
+    return KTN_OK;
+}
+
+// Enqueue pack + exchange after the last round.  The sizes travel first (16 bytes per rank); the host reads them
+// to place every rank's blob, then one grouped broadcast per rank moves the payload over NVLink.
+extern "C" int ktn_allgather_cuts_async(ktn_handle* h) {
+    if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
+    if (!h->comm) return fail(h, KTN_ERR_USAGE, "ktn_comm_init has not been called");
+    cudaSetDevice(h->device);
+    ncclComm_t comm = (ncclComm_t)h->comm;
+    const size_t m = (size_t)h->prob.num_constr, NZ = (size_t)h->prob.jac_ptr[m];
+    const size_t cap = ktn_pack_layout(m, NZ).total;
+    if (h->sendbuf.bytes < cap) CK(h, h->sendbuf.alloc(cap));
+    CK(h, cudaEventRecord(h->evx0, h->stream));
+    KtnRoundParams p = ktn_make_params(h, nullptr, 0, 0);
+    ktn_launch_pack(p, h->sendbuf.as<unsigned char>(), h->num_sms, h->stream);
+    h->tm.launches += 1;
+    NK(h, N.AllGather(h->counts.p, h->all_counts.p, 2, ncclUint64, comm, h->stream));
+    CK(h, cudaMemcpyAsync(h->h_all_counts, h->all_counts.p, 16 * (size_t)h->nranks, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    size_t off = 0;
+    for (int r = 0; r < h->nranks; ++r) {
+        h->g_cuts[r] = (int64_t)h->h_all_counts[2 * r]; h->g_nnz[r] = (int64_t)h->h_all_counts[2 * r + 1];
+        h->g_off[r] = (int64_t)off;
+        off += ktn_pack_layout(h->g_cuts[r], h->g_nnz[r]).total;
+    }
+    h->g_off[h->nranks] = (int64_t)off; h->gathered_bytes = (int64_t)off;
+    if (h->gathered.bytes < off) CK(h, h->gathered.alloc(off + off / 4));
+    NK(h, N.GroupStart());
+    for (int r = 0; r < h->nranks; ++r) {
+        const size_t bytes = (size_t)(h->g_off[r + 1] - h->g_off[r]);
+        NK(h, N.Broadcast(h->sendbuf.p, h->gathered.as<unsigned char>() + h->g_off[r], bytes, ncclUint8, r, comm, h->stream));
+    }
+    NK(h, N.GroupEnd());
+    CK(h, cudaEventRecord(h->evx1, h->stream));
+    h->gather_pending = true;
+    return KTN_OK;
+}
+
+extern "C" int ktn_sync_gathered(ktn_handle* h, int64_t* total_cuts, int64_t* total_nnz) {
+    if (!h || !h->comm) return fail(h, KTN_ERR_USAGE, "no communicator");
+    cudaSetDevice(h->device);
+    if (h->gather_pending) {
+        CK(h, cudaStreamSynchronize(h->stream));
+        h->gather_pending = false;
+        float ms = 0.f; if (cudaEventElapsedTime(&ms, h->evx0, h->evx1) == cudaSuccess) h->tm.exchange_ms = ms;
+    }
+    int64_t c = 0, z = 0;
+    for (int r = 0; r < h->nranks; ++r) { c += h->g_cuts[r]; z += h->g_nnz[r]; }
+    if (total_cuts) *total_cuts = c;
+    if (total_nnz) *total_nnz = z;
+    return KTN_OK;
+}
+
+// Unpacks the gathered blobs into one CSR; row ids carry each rank's global row offset (exchanged in the header).
+extern "C" int ktn_fetch_gathered(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val,
+                                  double* lo, double* hi, double* g, double* viol, double* bconst) {
+    int rc = ktn_sync_gathered(h, nullptr, nullptr); if (rc) return rc;
+    std::vector<unsigned char> host((size_t)h->gathered_bytes + 16);
+    CK(h, cudaMemcpy(host.data(), h->gathered.p, (size_t)h->gathered_bytes, cudaMemcpyDeviceToHost));
+    int64_t co = 0, zo = 0;
+    if (row_ptr) row_ptr[0] = 0;
+    for (int r = 0; r < h->nranks; ++r) {
+        const unsigned char* b = host.data() + h->g_off[r];
+        const unsigned long long* hd = reinterpret_cast<const unsigned long long*>(b);
+        const int64_t n = (int64_t)hd[0], nz = (int64_t)hd[1], base = (int64_t)hd[4];
+        const KtnPackLayout L = ktn_pack_layout(n, nz);
+        if (row_id) { const int32_t* s = reinterpret_cast<const int32_t*>(b + L.row_id); for (int64_t i = 0; i < n; ++i) row_id[co + i] = s[i] + base; }
+        if (row_ptr) { const int64_t* s = reinterpret_cast<const int64_t*>(b + L.row_ptr); for (int64_t i = 0; i < n; ++i) row_ptr[co + i + 1] = s[i + 1] + zo; }
+        if (lo) memcpy(lo + co, b + L.lo, 8 * (size_t)n);
+        if (hi) memcpy(hi + co, b + L.hi, 8 * (size_t)n);
+        if (g) memcpy(g + co, b + L.g, 8 * (size_t)n);
+        if (viol) memcpy(viol + co, b + L.viol, 8 * (size_t)n);
+        if (bconst) memcpy(bconst + co, b + L.b, 8 * (size_t)n);
+        if (col) memcpy(col + zo, b + L.col, 4 * (size_t)nz);
+        if (val) memcpy(val + zo, b + L.val, 8 * (size_t)nz);
+        co += n; zo += nz;
+    }
+    return KTN_OK;
+}

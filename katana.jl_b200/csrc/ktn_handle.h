@@ -1,0 +1,60 @@
+// ktn_handle.h -- the handle behind the C ABI (shared by ktn_api.cu and ktn_comm.cu).
+#ifndef KTN_HANDLE_H
+#define KTN_HANDLE_H
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/ktn.h"
+#include "ktn_compile.h"
+#include "ktn_kernels.cuh"
+
+#define KTN_LANE_LIMIT 1536u   // max per-lane shared-memory bytes of a regular (shared-memory staged) shape
+
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    cudaError_t alloc(size_t n) { release(); bytes = n; if (n == 0) return cudaSuccess; return cudaMalloc(&p, n); }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct ktn_handle {
+    ktn_options opt;
+    int device = 0, num_sms = 0, max_smem = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    // per-round kernel timing: ring of (start, after K1, after K2) events, drained by ktn_timings_get
+    static const int RING = 128;
+    cudaEvent_t ring[RING][3];
+    int ring_head = 0, ring_tail = 0;      // [tail, head) not yet drained
+    double eval_ms_sum = 0, compact_ms_sum = 0; int64_t rounds_timed = 0;
+    KtnProblem prob;
+    bool loading = false, loaded = false, round_pending = false, have_round = false;
+    DevBuf chunks, shapes, prog, blob, chunk_rows, chunk_lb, chunk_ub, jac_ptr, jac_col, row_lb, row_ub;
+    DevBuf x, force, g_row, b_row, sel, stage_val, big_scratch, ticket, st_flag, st_cnt, st_nnz, counts, table;
+    DevBuf out_row, out_ptr, out_col, out_val, out_lo, out_hi, out_g, out_viol, out_b;
+    double* h_x = nullptr;                 // pinned
+    unsigned long long* h_counts = nullptr;  // pinned [8]
+    int64_t n_cuts = 0, nnz_cuts = 0, err_row = -1;
+    uint32_t warp_bytes = 0, blob_cap = 0, table_bytes = 0, table_prog_off = 0, epoch = 0;
+    ktn_timings tm;
+    std::string err;
+    // sharding (ktn_comm.cu): NCCL communicator, packed send buffer, gathered buffer
+    void* comm = nullptr; int nranks = 1, rank = 0;
+    DevBuf sendbuf, gathered, all_counts;
+    unsigned long long* h_all_counts = nullptr;   // pinned [2 * nranks]
+    std::vector<int64_t> g_cuts, g_nnz, g_off;    // per rank, after ktn_sync_gathered
+    bool gather_pending = false; int64_t gathered_bytes = 0, row_offset = 0;
+    cudaEvent_t evx0 = nullptr, evx1 = nullptr;
+};
+
+static inline int fail(ktn_handle* h, int code, const char* fmt, ...) {
+    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+#define CK(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(h, KTN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+
+
+#endif

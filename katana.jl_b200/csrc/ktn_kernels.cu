@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
         const double g = p.g_row[i], bc = p.b_row[i], lb = p.row_lb[i], ub = p.row_ub[i];
         p.out_row[cidx] = (int32_t)i; p.out_ptr[cidx] = o;
         p.out_lo[cidx] = lb - bc; p.out_hi[cidx] = ub - bc;     // src/model.jl:74-75
-        p.out_g[cidx] = g;
+        p.out_g[cidx] = g; p.out_b[cidx] = bc;
         const double v1 = lb - g, v2 = g - ub;
         p.out_viol[cidx] = (g == g) ? (v1 > v2 ? v1 : v2) : g;
         // the reference stops at the first non-finite cut (src/model.jl:278): cuts before it stand
@@ -400,7 +400,34 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3 (sharded runs only): pack the compacted cuts of this rank into ONE contiguous blob so the exchange over
+// NVLink is a single message per rank.  Layout (ktn_pack_layout): 64-byte header {n_cuts, nnz, first-error row + 1},
+// then row_id | row_ptr | lo | hi | g | viol | b | col | val, each section 16-byte aligned.
+// ---------------------------------------------------------------------------------------------
+template <class T> __device__ __forceinline__ void pack_copy(unsigned char* dst, const T* src, unsigned long long n) {
+    T* d = reinterpret_cast<T*>(dst);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) d[i] = src[i];
+}
+__global__ void __launch_bounds__(256) ktn_pack_kernel(const KtnRoundParams p, unsigned char* out) {
+    const unsigned long long n = p.counts[0], nz = p.counts[1];
+    KtnPackLayout L = ktn_pack_layout(n, nz);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long* h = reinterpret_cast<unsigned long long*>(out);
+        h[0] = n; h[1] = nz; h[2] = p.counts[6]; h[3] = L.total; h[4] = (unsigned long long)p.row_offset;
+    }
+    pack_copy(out + L.row_id, p.out_row, n);
+    pack_copy(out + L.row_ptr, p.out_ptr, n + 1);
+    pack_copy(out + L.lo, p.out_lo, n); pack_copy(out + L.hi, p.out_hi, n);
+    pack_copy(out + L.g, p.out_g, n); pack_copy(out + L.viol, p.out_viol, n); pack_copy(out + L.b, p.out_b, n);
+    pack_copy(out + L.col, p.out_col, nz); pack_copy(out + L.val, p.out_val, nz);
+}
+
 }  // namespace
+
+void ktn_launch_pack(const KtnRoundParams& p, unsigned char* sendbuf, int num_sms, cudaStream_t stream) {
+    ktn_pack_kernel<<<num_sms * 4, 256, 0, stream>>>(p, sendbuf);
+}
 
 cudaError_t ktn_kernels_configure(int max_smem_optin) {
     cudaError_t e = cudaFuncSetAttribute(ktn_round_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
@@ -457,9 +484,10 @@ static int launch_eval_part(const KtnRoundParams& p0, uint32_t n_regular, uint32
 }
 
 int ktn_launch_round(const KtnRoundParams& p, uint32_t n_regular, uint32_t n_total, int num_sms, int max_smem_optin,
-                     uint32_t epoch, cudaStream_t stream, cudaError_t* err) {
+                     uint32_t epoch, cudaStream_t stream, cudaEvent_t after_eval, cudaError_t* err) {
     int launches = launch_eval_part<false>(p, n_regular, n_total, num_sms, max_smem_optin, stream, err);
     if (*err != cudaSuccess) return launches;
+    if (after_eval) cudaEventRecord(after_eval, stream);
     const uint32_t nblocks = (uint32_t)((p.num_rows + KTN_CROWS - 1) / KTN_CROWS);
     if (nblocks > 0) {
         ktn_compact_kernel<<<nblocks, KTN_CBLOCK, 0, stream>>>(p, nblocks, epoch);

@@ -25,7 +25,7 @@ struct KtnRoundParams {
     const uint8_t* force;      // KTN_MODE_FORCE: per-row mask
     double f_tol, rng;
     int32_t mode, do_round;
-    int64_t num_var, num_rows;
+    int64_t num_var, num_rows, row_offset;
     uint32_t chunk_begin, chunk_end;   // chunk range this launch covers
     uint32_t warp_bytes;               // shared-memory bytes per warp (regular kernel)
     uint32_t blob_cap;                 // bytes reserved for the blob inside a warp's region
@@ -45,15 +45,36 @@ struct KtnRoundParams {
     // (~0 = none) [4] n_cuts_total [5] nnz_total [6] first-error row + 1 of the last round
     unsigned long long* counts;
     int32_t* out_row; int64_t* out_ptr; int32_t* out_col; double* out_val;
-    double* out_lo; double* out_hi; double* out_g; double* out_viol;
+    double* out_lo; double* out_hi; double* out_g; double* out_viol; double* out_b;
 };
 
 // Launches the kernels of one round on `stream`; returns the number of kernels launched.
 int ktn_launch_round(const KtnRoundParams& p, uint32_t n_regular, uint32_t n_total_chunks, int num_sms,
-                     int max_smem_optin, uint32_t epoch, cudaStream_t stream, cudaError_t* err);
+                     int max_smem_optin, uint32_t epoch, cudaStream_t stream, cudaEvent_t after_eval, cudaError_t* err);
 void ktn_plan_occupancy(uint32_t table_bytes, uint32_t warp_bytes, int max_smem_optin, int* warps_per_block, int* blocks_per_sm);
 // forward evaluation only (ktn_eval_g): writes g_row for every row
 int ktn_launch_eval(const KtnRoundParams& p, uint32_t n_regular, uint32_t n_total_chunks, int num_sms,
                     int max_smem_optin, cudaStream_t stream, cudaError_t* err);
 cudaError_t ktn_kernels_configure(int max_smem_optin);
+
+// packed per-rank cut blob exchanged between GPUs (byte offsets of the sections)
+struct KtnPackLayout { unsigned long long row_id, row_ptr, lo, hi, g, viol, b, col, val, total; };
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline KtnPackLayout ktn_pack_layout(unsigned long long n, unsigned long long nz) {
+    KtnPackLayout L; unsigned long long o = 64;
+    L.row_id = o; o = (o + 4 * n + 15) & ~15ull;
+    L.row_ptr = o; o = (o + 8 * (n + 1) + 15) & ~15ull;
+    L.lo = o; o = (o + 8 * n + 15) & ~15ull;
+    L.hi = o; o = (o + 8 * n + 15) & ~15ull;
+    L.g = o; o = (o + 8 * n + 15) & ~15ull;
+    L.viol = o; o = (o + 8 * n + 15) & ~15ull;
+    L.b = o; o = (o + 8 * n + 15) & ~15ull;
+    L.col = o; o = (o + 4 * nz + 15) & ~15ull;
+    L.val = o; o = (o + 8 * nz + 15) & ~15ull;
+    L.total = o;
+    return L;
+}
+void ktn_launch_pack(const KtnRoundParams& p, unsigned char* sendbuf, int num_sms, cudaStream_t stream);
 #endif

@@ -1,0 +1,108 @@
+"""Separator plugin API and the B200 separator.
+
+Mirrors reference src/separators.jl: `AbstractKatanaSeparator` with the four hooks
+initialize! / precompute! / isconstrsat / gencut (src/separators.jl:23,34,43,53), and, in place of
+`KatanaFirstOrderSeparator` (src/separators.jl:58-120), `KatanaGPUSeparator`, which keeps the same
+state (g, Jacobian rows, xstar) on the device behind the C ABI of include/ktn.h.
+"""
+import numpy as np
+
+from .binding import KTN_NUMERIC_NONFINITE, load_cuda_library
+from .nlpeval import rows_to_wire
+
+
+class AffExpr:
+    """The JuMP.AffExpr the reference's gencut returns: sum coeffs[k] * x[vars[k]] + constant."""
+    __slots__ = ("vars", "coeffs", "constant")
+
+    def __init__(self, vars_, coeffs, constant):
+        self.vars, self.coeffs, self.constant = np.asarray(vars_, np.int64), np.asarray(coeffs, np.float64), float(constant)
+
+
+class AbstractKatanaSeparator:
+    def initialize(self, linear_model, num_var, num_constr, oracle):          # src/separators.jl:23
+        raise NotImplementedError("Not implemented: Katana.initialize!")
+
+    def gencut(self, xstar, bounds, i):                                       # src/separators.jl:34
+        raise NotImplementedError("Not implemented: Katana.gencut!")
+
+    def isconstrsat(self, i, lb, ub, f_tol):                                  # src/separators.jl:43
+        raise NotImplementedError("Not implemented: Katana.isconstrsat")
+
+    def precompute(self, xstar):                                              # src/separators.jl:53
+        return None
+
+    def set_bounds(self, l_constr, u_constr):
+        """Added hook (default no-op): lets a batched separator test all rows in one device pass."""
+        return None
+
+
+class KatanaGPUSeparator(AbstractKatanaSeparator):
+    """First-order separator whose precompute! is one device round (include/ktn.h: ktn_separate).
+
+    The batched `separate()` is what optimize! uses; `isconstrsat` / `gencut` stay available with
+    the reference's per-row semantics and answer from the last round.
+    `library` defaults to the CUDA library; there is no CPU path in the product (tests may pass
+    another implementation of the same C ABI as the checker).
+    """
+
+    def __init__(self, library=None, topk=0):
+        self._lib = library
+        self.topk = topk
+        self.handle = None
+        self.last = None           # CutBatch of the last precompute!
+        self.xstar = None
+        self.g = None
+
+    # initialize!(sep, linear_model, num_var, num_constr, oracle)  -- src/separators.jl:81-107
+    def initialize(self, linear_model, num_var, num_constr, oracle, f_tol=1e-6, cut_coef_rng=1e9):
+        lib = self._lib if self._lib is not None else load_cuda_library()
+        self.linear_model, self.oracle = linear_model, oracle
+        oracle.initialize(["ExprGraph"])                       # MathProgBase.initialize(oracle, ...) :88
+        if self.handle is not None:                            # one separator is reused across models (test/runtests.jl:24)
+            self.handle.close()
+        self.handle = lib.create(f_tol=f_tol, cut_coef_rng=cut_coef_rng, topk=self.topk)
+        self.num_var, self.num_constr = num_var, num_constr
+        lb = np.full(num_constr, -np.inf); ub = np.full(num_constr, np.inf)
+        self.handle.load(num_var, rows_to_wire(oracle, num_constr, lb, ub))
+        self.l_constr, self.u_constr = lb, ub
+        self.last = self.g = self.xstar = None
+
+    def set_params(self, f_tol, cut_coef_rng):
+        self.handle.set_params(f_tol, cut_coef_rng, self.topk)
+
+    def set_bounds(self, l_constr, u_constr):
+        self.l_constr = np.asarray(l_constr, np.float64).copy(); self.u_constr = np.asarray(u_constr, np.float64).copy()
+        self.handle.set_bounds(self.l_constr, self.u_constr)
+
+    # precompute!(sep, xstar) -- src/separators.jl:111-116
+    def precompute(self, xstar):
+        self.xstar = np.asarray(xstar, np.float64)
+        self.last = self.handle.separate(self.xstar)
+        self.g = None
+
+    def separate(self, xstar):
+        """Batched round: every violated NL row as a CSR cut batch (ascending row order)."""
+        self.precompute(xstar)
+        return self.last
+
+    # isconstrsat(sep, i, lb, ub, f_tol) -- src/separators.jl:120
+    def isconstrsat(self, i, lb, ub, f_tol):
+        if self.g is None:
+            self.g = self.handle.get_g()
+        return bool((self.g[i] >= lb - f_tol) and (self.g[i] <= ub + f_tol))
+
+    # gencut(sep, xstar, bounds, i) -> AffExpr -- src/separators.jl:118, src/algorithms.jl:3-18
+    def gencut(self, xstar, bounds, i):
+        b = self.handle.gencut_rows(self.xstar if self.xstar is not None else xstar, np.array([i], np.int64), round_coefs=False)
+        if b.n_cuts != 1:
+            cols = self.handle.jac_structure()
+            s, e = cols[0][i], cols[0][i + 1]
+            return AffExpr(cols[1][s:e], np.full(e - s, np.nan), np.nan)     # non-finite row: _addcut will flag :Error
+        cols, vals = b.row(0)
+        return AffExpr(cols, vals, b.bconst[0])
+
+
+def linear_oa_cut(sep, a, b, i):
+    """Name kept from src/algorithms.jl:3: the first-order cut of row i at the precomputed point."""
+    return sep.gencut(a, b, i)

@@ -1,0 +1,34 @@
+"""Row sharding across GPUs.
+
+Constraints are independent given x*, so the NL rows are split into contiguous ranges, one per
+rank (one process per GPU).  Every rank separates its slice; concatenating the per-rank cut
+batches in rank order IS ascending row order, the reference's emission order (src/model.jl:272),
+so the combined cut set is identical for any GPU count.
+"""
+import numpy as np
+
+from .binding import CutBatch
+
+
+def shard_range(num_rows, world_size, rank):
+    """Contiguous, balanced [begin, end) of rank `rank`."""
+    base, rem = divmod(num_rows, world_size)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def combine_rank_major(parts):
+    """parts: list over ranks of (row_begin, CutBatch with shard-local row ids).  Returns one CutBatch
+    with global row ids; stops at the first rank that reported a non-finite row (src/model.jl:278)."""
+    row_id, col, val, lo, hi, g, viol, bc, ptr = [], [], [], [], [], [], [], [], [np.zeros(1, np.int64)]
+    status, err_row, off = 0, -1, 0
+    for row_begin, b in parts:
+        row_id.append(b.row_id + row_begin); col.append(b.col); val.append(b.val)
+        lo.append(b.lo); hi.append(b.hi); g.append(b.g); viol.append(b.viol); bc.append(b.bconst)
+        ptr.append(b.row_ptr[1:] + off); off += int(b.row_ptr[-1])
+        if b.status != 0:
+            status, err_row = b.status, b.err_row + row_begin
+            break
+    cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dt)
+    return CutBatch(status, err_row, cat(row_id, np.int64), np.concatenate(ptr), cat(col, np.int32), cat(val, np.float64),
+                    cat(lo, np.float64), cat(hi, np.float64), cat(g, np.float64), cat(viol, np.float64), cat(bc, np.float64))

@@ -51,7 +51,7 @@ struct ktn_handle {
     /* last cut batch */
     int64_t n_cuts, nnz_cuts, err_row;
     int64_t* c_row; int64_t* c_ptr; int32_t* c_col; double* c_val;
-    double* c_lo; double* c_hi; double* c_g; double* c_viol;
+    double* c_lo; double* c_hi; double* c_g; double* c_viol; double* c_b;
     int64_t cap_cuts, cap_nnz;
     int threads;
     ktn_timings tm;
@@ -71,11 +71,11 @@ static void free_problem(ktn_handle* h) {
     free(h->lb); free(h->ub); free(h->flags); free(h->jac_ptr); free(h->jac_col);
     free(h->g); free(h->jac); free(h->xstar);
     free(h->c_row); free(h->c_ptr); free(h->c_col); free(h->c_val);
-    free(h->c_lo); free(h->c_hi); free(h->c_g); free(h->c_viol);
+    free(h->c_lo); free(h->c_hi); free(h->c_g); free(h->c_viol); free(h->c_b);
     h->expr_ptr = NULL; h->op = NULL; h->arg = NULL; h->val = NULL; h->parent = NULL; h->send = NULL;
     h->lb = h->ub = NULL; h->flags = NULL; h->jac_ptr = NULL; h->jac_col = NULL;
     h->g = h->jac = h->xstar = NULL;
-    h->c_row = h->c_ptr = NULL; h->c_col = NULL; h->c_val = h->c_lo = h->c_hi = h->c_g = h->c_viol = NULL;
+    h->c_row = h->c_ptr = NULL; h->c_col = NULL; h->c_val = h->c_lo = h->c_hi = h->c_g = h->c_viol = h->c_b = NULL;
     h->cap_cuts = h->cap_nnz = 0; h->n_nodes = h->cap_nodes = 0; h->rows_loaded = 0; h->jac_cap = 0;
     h->have_round = 0; h->n_cuts = h->nnz_cuts = 0; h->err_row = -1; h->max_nodes = 0;
 }
@@ -321,7 +321,7 @@ static void reserve_cuts(ktn_handle* h, int64_t nc, int64_t nz) {
         int64_t c = (nc + 1) * 3 / 2 + 16;
         h->c_row = (int64_t*)realloc(h->c_row, 8 * (size_t)c); h->c_ptr = (int64_t*)realloc(h->c_ptr, 8 * (size_t)(c + 1));
         h->c_lo = (double*)realloc(h->c_lo, 8 * (size_t)c); h->c_hi = (double*)realloc(h->c_hi, 8 * (size_t)c);
-        h->c_g = (double*)realloc(h->c_g, 8 * (size_t)c); h->c_viol = (double*)realloc(h->c_viol, 8 * (size_t)c);
+        h->c_g = (double*)realloc(h->c_g, 8 * (size_t)c); h->c_viol = (double*)realloc(h->c_viol, 8 * (size_t)c); h->c_b = (double*)realloc(h->c_b, 8 * (size_t)c);
         h->cap_cuts = c;
     }
     if (nz > h->cap_nnz) {
@@ -355,7 +355,7 @@ static int emit_cut(ktn_handle* h, int64_t i, int do_round) {
     int64_t c = h->n_cuts;
     h->c_row[c] = i; h->c_ptr[c] = o; h->c_ptr[c + 1] = o + nz;
     h->c_lo[c] = h->lb[i] - b; h->c_hi[c] = h->ub[i] - b;  /* model.jl:74-75 */
-    h->c_g[c] = h->g[i];
+    h->c_g[c] = h->g[i]; h->c_b[c] = b;
     double v1 = h->lb[i] - h->g[i], v2 = h->g[i] - h->ub[i];
     h->c_viol[c] = (h->g[i] == h->g[i]) ? (v1 > v2 ? v1 : v2) : h->g[i];
     h->n_cuts = c + 1; h->nnz_cuts = o + nz;
@@ -423,7 +423,7 @@ int ktn_gencut_rows(ktn_handle* h, const double* x, const int64_t* rows, int64_t
 }
 
 int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val,
-                   double* lo, double* hi, double* g, double* viol) {
+                   double* lo, double* hi, double* g, double* viol, double* bconst) {
     if (!h) return KTN_ERR_USAGE;
     size_t nc = (size_t)h->n_cuts, nz = (size_t)h->nnz_cuts;
     if (row_ptr) { if (h->c_ptr) memcpy(row_ptr, h->c_ptr, 8 * (nc + 1)); else row_ptr[0] = 0; }
@@ -434,6 +434,7 @@ int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* co
     if (hi && nc) memcpy(hi, h->c_hi, 8 * nc);
     if (g && nc) memcpy(g, h->c_g, 8 * nc);
     if (viol && nc) memcpy(viol, h->c_viol, 8 * nc);
+    if (bconst && nc) memcpy(bconst, h->c_b, 8 * nc);
     return KTN_OK;
 }
 
@@ -492,7 +493,8 @@ int ktn_separate_device_async(ktn_handle* h, const double* d) { (void)d; return 
 int ktn_sync_counts(ktn_handle* h, int64_t* a, int64_t* b, int64_t* c) { (void)a; (void)b; (void)c; return fail(h, KTN_ERR_UNSUPPORTED, "oracle has no device path"); }
 int ktn_comm_unique_id(void* id) { (void)id; return KTN_ERR_UNSUPPORTED; }
 int ktn_comm_init(ktn_handle* h, int32_t n, int32_t r, const void* id) { (void)n; (void)r; (void)id; return fail(h, KTN_ERR_UNSUPPORTED, "oracle is single process"); }
+int ktn_set_row_offset(ktn_handle* h, int64_t r) { (void)r; return fail(h, KTN_ERR_UNSUPPORTED, "oracle is single process"); }
 int ktn_allgather_cuts_async(ktn_handle* h) { return fail(h, KTN_ERR_UNSUPPORTED, "oracle is single process"); }
 int ktn_sync_gathered(ktn_handle* h, int64_t* a, int64_t* b) { (void)a; (void)b; return fail(h, KTN_ERR_UNSUPPORTED, "oracle is single process"); }
-int ktn_fetch_gathered(ktn_handle* h, int64_t* a, int64_t* b, int32_t* c, double* d, double* e, double* f, double* g, double* v) {
-    (void)a; (void)b; (void)c; (void)d; (void)e; (void)f; (void)g; (void)v; return fail(h, KTN_ERR_UNSUPPORTED, "oracle is single process"); }
+int ktn_fetch_gathered(ktn_handle* h, int64_t* a, int64_t* b, int32_t* c, double* d, double* e, double* f, double* g, double* v, double* w) {
+    (void)w; (void)a; (void)b; (void)c; (void)d; (void)e; (void)f; (void)g; (void)v; return fail(h, KTN_ERR_UNSUPPORTED, "oracle is single process"); }

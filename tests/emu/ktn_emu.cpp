@@ -14,7 +14,7 @@
 struct ktn_handle {
     ktn_options opt; KtnProblem prob; bool loaded = false, have_round = false;
     std::vector<double> g_row, b_row, stage_val; std::vector<uint32_t> sel;
-    std::vector<int64_t> c_row, c_ptr; std::vector<int32_t> c_col; std::vector<double> c_val, c_lo, c_hi, c_g, c_viol;
+    std::vector<int64_t> c_row, c_ptr; std::vector<int32_t> c_col; std::vector<double> c_val, c_lo, c_hi, c_g, c_viol, c_b;
     int64_t err_row = -1; std::string err;
 };
 extern "C" {
@@ -103,7 +103,7 @@ static void run_chunks(ktn_handle* h, const double* x, int mode, const std::vect
 
 static int compact(ktn_handle* h, int64_t* n_cuts, int64_t* nnz, int64_t* err_row) {
     KtnProblem& P = h->prob;
-    h->c_row.clear(); h->c_ptr.assign(1, 0); h->c_col.clear(); h->c_val.clear(); h->c_lo.clear(); h->c_hi.clear(); h->c_g.clear(); h->c_viol.clear();
+    h->c_row.clear(); h->c_ptr.assign(1, 0); h->c_col.clear(); h->c_val.clear(); h->c_lo.clear(); h->c_hi.clear(); h->c_g.clear(); h->c_viol.clear(); h->c_b.clear();
     h->err_row = -1;
     for (int64_t i = 0; i < P.num_constr; ++i) {
         uint32_t s = h->sel[i]; if (!s) continue;
@@ -112,7 +112,7 @@ static int compact(ktn_handle* h, int64_t* n_cuts, int64_t* nnz, int64_t* err_ro
         for (uint32_t q = 0; q < s; ++q) { h->c_col.push_back(P.jac_col[base + q]); h->c_val.push_back(h->stage_val[base + q]); }
         h->c_row.push_back(i); h->c_ptr.push_back((int64_t)h->c_col.size());
         const double g = h->g_row[i], b = h->b_row[i];
-        h->c_lo.push_back(P.lb[i] - b); h->c_hi.push_back(P.ub[i] - b); h->c_g.push_back(g);
+        h->c_lo.push_back(P.lb[i] - b); h->c_hi.push_back(P.ub[i] - b); h->c_g.push_back(g); h->c_b.push_back(b);
         const double v1 = P.lb[i] - g, v2 = g - P.ub[i]; h->c_viol.push_back(g == g ? (v1 > v2 ? v1 : v2) : g);
     }
     if (n_cuts) *n_cuts = (int64_t)h->c_row.size();
@@ -127,7 +127,7 @@ int ktn_separate(ktn_handle* h, const double* x, int64_t* nc, int64_t* nz, int64
 int ktn_gencut_rows(ktn_handle* h, const double* x, const int64_t* rows, int64_t nrows, int do_round, int64_t* nc, int64_t* nz, int64_t* er) {
     std::vector<uint8_t> mask((size_t)h->prob.num_constr, 0); for (int64_t j = 0; j < nrows; ++j) mask[rows[j]] = 1;
     run_chunks(h, x, 1, mask, do_round); return compact(h, nc, nz, er); }
-int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val, double* lo, double* hi, double* g, double* viol) {
+int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val, double* lo, double* hi, double* g, double* viol, double* bconst) {
     size_t nc = h->c_row.size(), nz = h->c_col.size();
     if (row_id && nc) memcpy(row_id, h->c_row.data(), 8 * nc);
     if (row_ptr) memcpy(row_ptr, h->c_ptr.data(), 8 * (nc + 1));
@@ -137,6 +137,7 @@ int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* co
     if (hi && nc) memcpy(hi, h->c_hi.data(), 8 * nc);
     if (g && nc) memcpy(g, h->c_g.data(), 8 * nc);
     if (viol && nc) memcpy(viol, h->c_viol.data(), 8 * nc);
+    if (bconst && nc) memcpy(bconst, h->c_b.data(), 8 * nc);
     return 0; }
 int ktn_get_g(ktn_handle* h, double* g) { memcpy(g, h->g_row.data(), 8 * h->g_row.size()); return 0; }
 int ktn_eval_g(ktn_handle* h, const double* x, double* g) { run_chunks(h, x, 2, {}, 0); memcpy(g, h->g_row.data(), 8 * h->g_row.size()); return 0; }
@@ -151,9 +152,10 @@ int ktn_separate_device_async(ktn_handle*, const double*) { return KTN_ERR_UNSUP
 int ktn_sync_counts(ktn_handle*, int64_t*, int64_t*, int64_t*) { return KTN_ERR_UNSUPPORTED; }
 int ktn_comm_unique_id(void*) { return KTN_ERR_UNSUPPORTED; }
 int ktn_comm_init(ktn_handle*, int32_t, int32_t, const void*) { return KTN_ERR_UNSUPPORTED; }
+int ktn_set_row_offset(ktn_handle*, int64_t) { return KTN_ERR_UNSUPPORTED; }
 int ktn_allgather_cuts_async(ktn_handle*) { return KTN_ERR_UNSUPPORTED; }
 int ktn_sync_gathered(ktn_handle*, int64_t*, int64_t*) { return KTN_ERR_UNSUPPORTED; }
-int ktn_fetch_gathered(ktn_handle*, int64_t*, int64_t*, int32_t*, double*, double*, double*, double*, double*) { return KTN_ERR_UNSUPPORTED; }
+int ktn_fetch_gathered(ktn_handle*, int64_t*, int64_t*, int32_t*, double*, double*, double*, double*, double*, double*) { return KTN_ERR_UNSUPPORTED; }
 }
 extern "C" int ktn_emu_shape_info(ktn_handle* h, int64_t sid, uint32_t* out /* n_fwd, n_ins, n_uniq, n_const, n_scratch, flags */) {
     if (sid < 0 || sid >= (int64_t)h->prob.shapes.size()) return -1;
@@ -162,3 +164,7 @@ extern "C" int ktn_emu_shape_info(ktn_handle* h, int64_t sid, uint32_t* out /* n
 extern "C" int ktn_emu_shape_prog(ktn_handle* h, int64_t sid, uint32_t* out /* 4 words per instruction */) {
     const KtnShapeDesc& s = h->prob.shapes[sid];
     memcpy(out, h->prob.prog.data() + s.prog_off, 16 * (size_t)s.n_ins); return 0; }
+// vectorised access to the shared math header for tests/test_math.py
+extern "C" void ktn_test_exp(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ktn_exp(x[i]); }
+extern "C" void ktn_test_log(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ktn_log(x[i]); }
+extern "C" void ktn_test_pow(const double* x, const double* p, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ktn_pow(x[i], p[i]); }

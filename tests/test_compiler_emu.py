@@ -1,0 +1,138 @@
+"""The tape compiler + chunk packing + interpreter core (the exact artefacts and code the sm_100a
+kernels run) against the oracle, bit for bit, on the CPU through the test-only host emulator."""
+import numpy as np
+import pytest
+
+from helpers import assert_batches_identical, bits_equal, kat_problem, random_tree
+from katana_jl_b200 import expr as E
+from katana_jl_b200.binding import ROW_DENSE, ROW_NL
+
+
+def both(oracle_lib, emu_lib, nvar, w, **kw):
+    ho, he = oracle_lib.create(**kw), emu_lib.create(**kw)
+    ho.load(nvar, w); he.load(nvar, w)
+    return ho, he
+
+
+def test_jac_structure_sorted_unique(oracle_lib, emu_lib):
+    nvar, w, _ = kat_problem()
+    ho, he = both(oracle_lib, emu_lib, nvar, w)
+    (rp0, c0), (rp1, c1) = ho.jac_structure(), he.jac_structure()
+    assert np.array_equal(rp0, rp1) and np.array_equal(c0, c1)
+    for r in range(w.nrows):
+        cols = c0[rp0[r]:rp0[r + 1]]
+        assert np.all(np.diff(cols) > 0)
+
+
+def test_kat_rounds_identical(oracle_lib, emu_lib):
+    nvar, w, pts = kat_problem()
+    ho, he = both(oracle_lib, emu_lib, nvar, w)
+    for p in pts:
+        assert_batches_identical(ho.separate(p), he.separate(p), f"separate at {p}")
+        assert bits_equal(ho.eval_g(p), he.eval_g(p))
+        rows = np.arange(w.nrows, dtype=np.int64)
+        assert_batches_identical(ho.gencut_rows(p, rows, False), he.gencut_rows(p, rows, False), f"gencut at {p}")
+        assert_batches_identical(ho.gencut_rows(p, rows[::3], True), he.gencut_rows(p, rows[::3], True), f"gencut+round at {p}")
+
+
+@pytest.mark.parametrize("kind,nv,nr", [(0, 1000, 3000), (1, 5000, 6000), (2, 2000, 2500)])
+def test_synthetic_families_identical(oracle_lib, emu_lib, synth_lib, kind, nv, nr):
+    w = synth_lib.synth_rows(kind, 20260001 + kind, nv, 0, nr)
+    x0 = synth_lib.synth_point(kind, 20260001 + kind, nv)
+    ho, he = both(oracle_lib, emu_lib, nv, w)
+    g = ho.eval_g(x0)
+    assert bits_equal(g, he.eval_g(x0))
+    for v in (0.0, 0.01, 0.1, 1.0):
+        ub = np.full(nr, np.quantile(g, 1 - v) if v > 0 else g.max() + 1.0)
+        ho.set_bounds(w.lb, ub); he.set_bounds(w.lb, ub)
+        bo, be = ho.separate(x0), he.separate(x0)
+        assert_batches_identical(bo, be, f"kind {kind} v {v}")
+        assert abs(bo.n_cuts - v * nr) <= max(2, 0.01 * nr)
+        assert ho.algorithmic_bytes() == he.algorithmic_bytes()
+
+
+def test_fused_shapes_use_few_instructions(emu_lib, synth_lib):
+    """The benchmark families compile to fused term runs (a handful of instructions per shape)."""
+    import ctypes as C
+    for kind in (0, 1, 2):
+        w = synth_lib.synth_rows(kind, 7, 1000, 0, 256)
+        h = emu_lib.create(); h.load(1000, w)
+        for sid in range(emu_lib.dll.ktn_emu_num_shapes(h.h)):
+            info = np.zeros(9, np.uint32)
+            emu_lib.dll.ktn_emu_shape_info(h.h, C.c_int64(sid), info.ctypes.data_as(C.c_void_p))
+            assert info[1] <= 16, (kind, sid, info)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_expression_trees(oracle_lib, emu_lib, seed):
+    """Every operator, arbitrary nesting, repeated variables, NaN / inf producing points."""
+    rng = np.random.default_rng(seed)
+    nvar = 6
+    exprs = [random_tree(rng, nvar, int(rng.integers(1, 6))) for _ in range(300)]
+    exprs = [e if E.variables(e) else e + E.var(0) for e in exprs]
+    m = len(exprs)
+    w = E.to_wire(exprs, np.full(m, -np.inf), rng.uniform(-1, 1, m), [ROW_NL] * m)
+    ho, he = both(oracle_lib, emu_lib, nvar, w)
+    for _ in range(4):
+        x = np.round(rng.uniform(-2, 2, nvar), 2)
+        rows = np.arange(m, dtype=np.int64)
+        assert bits_equal(ho.eval_g(x), he.eval_g(x))
+        # row by row, so non-finite rows (which stop a batch, src/model.jl:278) do not hide later rows
+        for r0 in range(0, m, 50):
+            sub = rows[r0:r0 + 50]
+            bo, be = ho.gencut_rows(x, sub, True), he.gencut_rows(x, sub, True)
+            while True:
+                assert_batches_identical(bo, be, f"seed {seed} rows {sub[0]}..")
+                if bo.status == 0 or bo.err_row == sub[-1]:
+                    break
+                sub = sub[sub > bo.err_row]
+                bo, be = ho.gencut_rows(x, sub, True), he.gencut_rows(x, sub, True)
+        assert_batches_identical(ho.separate(x), he.separate(x), f"seed {seed} separate")
+
+
+def test_edge_cases(oracle_lib, emu_lib):
+    x0, x1 = E.var(0), E.var(1)
+    # single row; row touching one variable many times; constant-only subtree; ragged chunk (33 rows of one shape)
+    exprs = [x0 * x0 * x0 + x0 / x0 - x0, (E.const(2.0) * E.const(3.0)) * x1] + [E.const(float(k)) * x0**2 + x1 for k in range(33)]
+    m = len(exprs)
+    w = E.to_wire(exprs, np.full(m, -np.inf), np.zeros(m), [ROW_NL] * m)
+    ho, he = both(oracle_lib, emu_lib, 2, w)
+    for x in ([1.0, 1.0], [0.0, -1.0], [-3.0, 2.0]):
+        assert_batches_identical(ho.separate(np.array(x)), he.separate(np.array(x)), str(x))
+    # rows that are not NL are never selected; two-sided bounds; equality rows
+    w2 = E.to_wire([x0 + x1, x0**2, x1**2], [0.0, -np.inf, 1.0], [1.0, 4.0, 1.0], [0, ROW_NL, ROW_NL])
+    ho, he = both(oracle_lib, emu_lib, 2, w2)
+    for x in ([5.0, 5.0], [1.0, 1.0], [3.0, 0.5]):
+        bo = ho.separate(np.array(x)); assert_batches_identical(bo, he.separate(np.array(x)), str(x))
+        assert 0 not in bo.row_id
+
+
+def test_big_shapes_and_dense_rows(oracle_lib, emu_lib, monkeypatch):
+    """Shapes over the shared-memory budget and the dense epigraph row take the global-scratch path."""
+    monkeypatch.setenv("KTN_EMU_LANE_LIMIT", "200")
+    rng = np.random.default_rng(5)
+    nvar = 40
+    exprs = [E.sum_([E.exp(E.const(float(rng.uniform(-1, 1))) * E.var(int(j)) + float(rng.uniform(-1, 1))) for j in rng.choice(nvar, 30, replace=False)]) for _ in range(70)]
+    exprs.append(E.sum_([(E.var(j) - 0.5)**2 for j in range(0, nvar - 1, 2)]) - E.var(nvar - 1))
+    m = len(exprs)
+    w = E.to_wire(exprs, np.full(m, -np.inf), np.full(m, 20.0), [ROW_NL] * (m - 1) + [ROW_NL | ROW_DENSE])
+    ho, he = both(oracle_lib, emu_lib, nvar, w)
+    assert emu_lib.dll.ktn_emu_num_big_chunks(he.h) >= 3
+    for _ in range(3):
+        x = rng.uniform(-1, 2, nvar)
+        bo = ho.separate(x)
+        assert_batches_identical(bo, he.separate(x))
+        assert bo.n_cuts > 0 and bo.row_ptr[-1] >= nvar
+
+
+def test_reload_on_same_handle(oracle_lib, emu_lib):
+    """initialize! is called repeatedly on one separator (test/runtests.jl:24)."""
+    nvar, w, pts = kat_problem()
+    he, ho = emu_lib.create(), oracle_lib.create()
+    for _ in range(2):
+        he.load(nvar, w); ho.load(nvar, w)
+        assert_batches_identical(ho.separate(pts[1]), he.separate(pts[1]))
+    x0 = E.var(0)
+    w2 = E.to_wire([x0**2], [-np.inf], [1.0], [ROW_NL])
+    he.load(1, w2); ho.load(1, w2)
+    assert_batches_identical(ho.separate(np.array([3.0])), he.separate(np.array([3.0])))

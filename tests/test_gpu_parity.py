@@ -1,0 +1,190 @@
+"""GPU parity: the CUDA library (through the C ABI) against the CPU oracle, bit for bit.
+Small seeded cases the oracle finishes in seconds, the committed golden vectors, edge cases, and the
+BASELINE.json sizes (10^6 rows) checked both against the oracle and through size-independent
+properties.  Run on the B200 box:  python -m pytest tests -m gpu"""
+import json
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from helpers import BATCH_FIELDS, assert_batches_identical, bits_equal, kat_problem, random_tree
+from katana_jl_b200 import expr as E
+from katana_jl_b200.binding import KTN_NUMERIC_NONFINITE, ROW_DENSE, ROW_NL
+
+pytestmark = pytest.mark.gpu
+
+
+def both(oracle_lib, cuda_lib, nvar, w, **kw):
+    ho, hc = oracle_lib.create(**kw), cuda_lib.create(**kw)
+    ho.load(nvar, w); hc.load(nvar, w)
+    return ho, hc
+
+
+def test_backend_is_cuda(cuda_lib):
+    assert cuda_lib.backend == "cuda"
+
+
+def test_kat_rounds_identical(oracle_lib, cuda_lib):
+    nvar, w, pts = kat_problem()
+    ho, hc = both(oracle_lib, cuda_lib, nvar, w)
+    assert all(np.array_equal(a, b) for a, b in zip(ho.jac_structure(), hc.jac_structure()))
+    rows = np.arange(w.nrows, dtype=np.int64)
+    for p in pts:
+        assert_batches_identical(ho.separate(p), hc.separate(p), f"separate at {p}")
+        assert bits_equal(ho.eval_g(p), hc.eval_g(p))
+        assert_batches_identical(ho.gencut_rows(p, rows, False), hc.gencut_rows(p, rows, False), f"gencut at {p}")
+        assert_batches_identical(ho.gencut_rows(p, rows[::3], True), hc.gencut_rows(p, rows[::3], True), f"gencut+round at {p}")
+
+
+def test_golden_vectors_on_gpu(cuda_lib):
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "kat_values.json")))
+    nvar, w, pts = kat_problem()
+    h = cuda_lib.create(); h.load(nvar, w)
+    checked = 0
+    for pi, p in enumerate(pts):
+        g = h.eval_g(p)
+        for r in range(w.nrows):
+            ref = gold["rows"][r]["values"][pi]
+            if ref["g"] is None or not np.isfinite(g[r]):
+                continue
+            assert g[r] == pytest.approx(float(ref["g"]), rel=2e-14, abs=1e-300)
+            checked += 1
+    assert checked > 100
+
+
+@pytest.mark.parametrize("kind,nv,nr", [(0, 1000, 5000), (1, 5000, 20000), (2, 2000, 3000), (1, 100, 33), (0, 50, 1)])
+def test_synthetic_families_identical(oracle_lib, cuda_lib, kind, nv, nr):
+    w = cuda_lib.synth_rows(kind, 20260001 + kind, nv, 0, nr)
+    x0 = cuda_lib.synth_point(kind, 20260001 + kind, nv)
+    ho, hc = both(oracle_lib, cuda_lib, nv, w)
+    g = ho.eval_g(x0)
+    assert bits_equal(g, hc.eval_g(x0))
+    for v in (0.0, 0.01, 0.1, 1.0):
+        ub = np.full(nr, np.quantile(g, 1 - v) if v > 0 else g.max() + 1.0)
+        ho.set_bounds(w.lb, ub); hc.set_bounds(w.lb, ub)
+        for x in (x0, 0.5 * x0):
+            assert_batches_identical(ho.separate(x), hc.separate(x), f"kind {kind} v {v}")
+        assert ho.algorithmic_bytes() == hc.algorithmic_bytes()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_expression_trees(oracle_lib, cuda_lib, seed):
+    rng = np.random.default_rng(100 + seed)
+    nvar = 6
+    exprs = [random_tree(rng, nvar, int(rng.integers(1, 6))) for _ in range(400)]
+    exprs = [e if E.variables(e) else e + E.var(0) for e in exprs]
+    m = len(exprs)
+    w = E.to_wire(exprs, np.full(m, -np.inf), rng.uniform(-1, 1, m), [ROW_NL] * m)
+    ho, hc = both(oracle_lib, cuda_lib, nvar, w)
+    rows = np.arange(m, dtype=np.int64)
+    for _ in range(3):
+        x = np.round(rng.uniform(-2, 2, nvar), 2)
+        assert bits_equal(ho.eval_g(x), hc.eval_g(x))
+        for r0 in range(0, m, 100):
+            sub = rows[r0:r0 + 100]
+            while len(sub):
+                bo, bc = ho.gencut_rows(x, sub, True), hc.gencut_rows(x, sub, True)
+                assert_batches_identical(bo, bc, f"seed {seed} rows {sub[0]}..")
+                if bo.status == 0:
+                    break
+                sub = sub[sub > bo.err_row]
+        assert_batches_identical(ho.separate(x), hc.separate(x), f"seed {seed} separate")
+
+
+def test_error_row_truncation(oracle_lib, cuda_lib):
+    """First non-finite row stops the round; cuts before it are delivered (src/model.jl:69-73,278)."""
+    x, y, z = E.var(0), E.var(1), E.var(2)
+    exprs = [x**2 + y**2 - 1.0] * 40 + [E.sqrt(x**2 + y**2) - (z - 0.25)] + [x**2 + y**2 - 1.0] * 40
+    m = len(exprs)
+    w = E.to_wire(exprs, np.full(m, -np.inf), np.full(m, -2.0), [ROW_NL] * m)
+    ho, hc = both(oracle_lib, cuda_lib, 3, w)
+    bo, bc = ho.separate(np.zeros(3)), hc.separate(np.zeros(3))
+    assert bo.status == KTN_NUMERIC_NONFINITE and bo.err_row == 40 and bo.n_cuts == 40
+    assert_batches_identical(bo, bc)
+    assert_batches_identical(ho.separate(np.ones(3)), hc.separate(np.ones(3)))    # and the state re-arms for the next round
+
+
+def test_big_shapes_dense_rows_and_reload(oracle_lib, cuda_lib):
+    rng = np.random.default_rng(5)
+    nvar = 300
+    # 200-term rows exceed the shared-memory lane budget -> global-scratch kernel; last row is a dense epigraph row
+    exprs = [E.sum_([E.exp(E.const(float(rng.uniform(-1, 1))) * E.var(int(j)) + float(rng.uniform(-1, 1))) for j in rng.choice(nvar, 200, replace=False)]) for _ in range(70)]
+    exprs += [x for x in [E.var(0)**2 + E.var(1)] * 5]
+    exprs.append(E.sum_([(E.var(j) - 0.5)**2 for j in range(0, nvar - 1, 2)]) - E.var(nvar - 1))
+    m = len(exprs)
+    w = E.to_wire(exprs, np.full(m, -np.inf), np.full(m, 100.0), [ROW_NL] * (m - 1) + [ROW_NL | ROW_DENSE])
+    ho, hc = both(oracle_lib, cuda_lib, nvar, w)
+    for _ in range(3):
+        xx = rng.uniform(-1, 2, nvar)
+        bo = ho.separate(xx)
+        assert bo.n_cuts > 0
+        assert_batches_identical(bo, hc.separate(xx))
+    nv2, w2, pts = kat_problem()                       # initialize! again on the same handle (test/runtests.jl:24)
+    ho.load(nv2, w2); hc.load(nv2, w2)
+    assert_batches_identical(ho.separate(pts[1]), hc.separate(pts[1]))
+
+
+@pytest.mark.parametrize("kind,name", [(1, "lse"), (0, "qcqp")])
+def test_baseline_size_round(oracle_lib, cuda_lib, kind, name):
+    """BASELINE.json size: 10^6 rows, 10^5 variables.  Full comparison with the oracle plus properties."""
+    nv, nr = 100000, 1000000
+    w = cuda_lib.synth_rows(kind, 20260001 + kind, nv, 0, nr)
+    x0 = cuda_lib.synth_point(kind, 20260001 + kind, nv)
+    hc = cuda_lib.create(); hc.load(nv, w)
+    g = hc.eval_g(x0)
+    ub = np.full(nr, np.quantile(g, 0.9))
+    hc.set_bounds(w.lb, ub)
+    b1 = hc.separate(x0)
+    b2 = hc.separate(x0)
+    for f in BATCH_FIELDS:                              # idempotence: a round is a pure function of x*
+        assert bits_equal(getattr(b1, f), getattr(b2, f)), f
+    assert np.all(np.diff(b1.row_id) > 0)              # ascending row order = the reference's loop order
+    assert b1.row_ptr[0] == 0 and np.all(np.diff(b1.row_ptr) > 0) and b1.row_ptr[-1] == len(b1.col) == len(b1.val)
+    assert abs(b1.n_cuts - 0.1 * nr) < 0.001 * nr
+    assert np.all(b1.g > ub[0] + 1e-6) and np.all(b1.viol == b1.g - ub[0])
+    sel = np.zeros(nr, bool); sel[b1.row_id] = True
+    assert np.all(g[~sel] <= ub[0] + 1e-6)             # nothing violated was missed
+    # first-order identity: sum_k J_k x*_k + b == g up to rounding of the accumulation
+    lin = np.add.reduceat(b1.val * x0[b1.col], b1.row_ptr[:-1]) + b1.bconst
+    assert np.allclose(lin, b1.g, rtol=1e-12, atol=1e-12)
+    assert np.array_equal(b1.hi, ub[0] - b1.bconst)
+    # and the whole round against the oracle
+    ho = oracle_lib.create(); ho.load(nv, w); ho.set_bounds(w.lb, ub)
+    assert_batches_identical(ho.separate(x0), b1, name)
+
+
+def test_device_resident_round_and_counters(cuda_lib):
+    import torch
+    nv, nr = 2000, 50000
+    w = cuda_lib.synth_rows(1, 3, nv, 0, nr); x0 = cuda_lib.synth_point(1, 3, nv)
+    h = cuda_lib.create(); h.load(nv, w)
+    g = h.eval_g(x0); h.set_bounds(w.lb, np.full(nr, np.quantile(g, 0.9)))
+    ref = h.separate(x0)
+    dx = torch.from_numpy(x0).cuda()
+    h.set_stream(torch.cuda.current_stream().cuda_stream)
+    l0 = h.timings()["launches"]
+    h.separate_device_async(dx.data_ptr())
+    got = h.fetch_last()
+    assert h.timings()["launches"] - l0 == 2            # K1 + K2
+    assert_batches_identical(ref, got)
+    h.set_stream(0)
+
+
+def test_ecp_end_to_end_on_gpu(cuda_lib):
+    import katana_jl_b200 as K
+    from reference_problems import PROBLEMS
+    for name, cite, build, obj, sol in PROBLEMS:
+        if name.startswith("501") and not name.endswith(("n2", "n5")):
+            continue
+        m = K.Model(K.KatanaSolver(separator=K.KatanaGPUSeparator(), log_level=0))
+        vars_ = build(m)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            status = m.solve()
+        assert status == "Optimal", (name, cite)
+        assert np.isclose(m.getobjectivevalue(), obj, rtol=1e-6, atol=1e-6), (name, cite)
+        if sol is not None:
+            assert np.allclose([m.getvalue(v) for v in vars_], sol, rtol=1e-3, atol=1e-3), (name, cite)
