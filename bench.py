@@ -191,7 +191,8 @@ def main():
             idt.copy_(torch.frombuffer(bytearray(comm_unique_id(lib)), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         h.comm_init(world, rank, bytes(idt.cpu().numpy().tobytes()))
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()           # a real (non-default) stream: handle 0 would mean "the library's own stream"
+    torch.cuda.set_stream(stream)
     h.set_stream(stream.cuda_stream)
     dx = torch.from_numpy(x0).cuda()
 

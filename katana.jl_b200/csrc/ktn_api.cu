@@ -123,12 +123,6 @@ extern "C" int ktn_load_end(ktn_handle* h) {
         std::vector<KtnIns> pr;
         for (KtnShapeDesc& s : sh) if (!(s.flags & KTN_SH_BIG)) { const uint32_t off = (uint32_t)pr.size(); pr.insert(pr.end(), P.prog.begin() + s.prog_off, P.prog.begin() + s.prog_off + s.n_ins); s.prog_off = off; }
         const size_t sb = (sh.size() * sizeof(KtnShapeDesc) + 15) & ~(size_t)15;
-        if (sb + pr.size() * sizeof(KtnIns) > 32768 && P.n_regular_chunks > 0) {
-            for (KtnShapeDesc& s : P.shapes) s.flags |= KTN_SH_BIG;
-            rc = P.finalize(sigma, 0);
-            if (rc != KTN_OK) { h->err = P.err; return rc; }
-            sh = P.shapes; pr.clear();
-        }
         table.assign(sb + pr.size() * sizeof(KtnIns) + 16, 0);
         memcpy(table.data(), sh.data(), sh.size() * sizeof(KtnShapeDesc));
         if (!pr.empty()) memcpy(table.data() + sb, pr.data(), pr.size() * sizeof(KtnIns));
@@ -228,6 +222,7 @@ static int enqueue_round(ktn_handle* h, const double* d_x, int mode, int do_roun
     h->epoch = (h->epoch % 0x3ffffff0u) + 1u;
     KtnRoundParams p = ktn_make_params(h, d_x, mode, do_round);
     cudaError_t e = cudaSuccess;
+    (void)cudaGetLastError();   // a stale non-sticky error must not be blamed on this round's launches
     if (h->ring_head - h->ring_tail >= ktn_handle::RING) drain_ring(h, false);
     if (h->ring_head - h->ring_tail >= ktn_handle::RING) { CK(h, cudaEventSynchronize(h->ring[h->ring_tail % ktn_handle::RING][2])); drain_ring(h, false); }
     cudaEvent_t* ev = h->ring[h->ring_head % ktn_handle::RING];
@@ -259,6 +254,7 @@ static int upload_x(ktn_handle* h, const double* x) {
     memcpy(h->h_x, x, 8 * (size_t)h->prob.num_var);
     CK(h, cudaEventRecord(h->ev0, h->stream));
     CK(h, cudaMemcpyAsync(h->x.p, h->h_x, 8 * (size_t)h->prob.num_var, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaEventRecord(h->ev1, h->stream));
     return KTN_OK;
 }
 

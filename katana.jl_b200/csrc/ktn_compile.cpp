@@ -464,7 +464,7 @@ void KtnProblem::repack_bounds() {
     for (size_t i = 0; i < chunk_rows.size(); ++i) if (chunk_rows[i] >= 0) { chunk_lb[i] = lb[chunk_rows[i]]; chunk_ub[i] = ub[chunk_rows[i]]; }
 }
 
-int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit) {
+int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit) {
     if (rows_loaded != num_constr) { err = "not all rows were loaded"; return KTN_ERR_USAGE; }
     if (sigma < 32) sigma = 32;
     lane_limit_hint = lane_limit;
@@ -472,8 +472,15 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit) {
     max_lane_bytes = 0;
     for (auto& s : shapes) {
         if (ktn_shape_lane_bytes(s) > lane_limit) s.flags |= KTN_SH_BIG;
-        if (!(s.flags & KTN_SH_BIG)) max_lane_bytes = std::max(max_lane_bytes, ktn_shape_lane_bytes(s));
     }
+    // the regular kernel keeps every shape descriptor and the regular shapes' programs in shared memory; if that
+    // table would not fit, every shape takes the global-memory kernel instead (correct, slower)
+    {
+        size_t tb = (shapes.size() * sizeof(KtnShapeDesc) + 15) & ~(size_t)15;
+        for (auto& s : shapes) if (!(s.flags & KTN_SH_BIG)) tb += (size_t)s.n_ins * sizeof(KtnIns);
+        if (tb > table_limit) for (auto& s : shapes) s.flags |= KTN_SH_BIG;
+    }
+    for (auto& s : shapes) if (!(s.flags & KTN_SH_BIG)) max_lane_bytes = std::max(max_lane_bytes, ktn_shape_lane_bytes(s));
     chunks.clear(); blob.clear(); chunk_rows.clear(); big_scratch_doubles = 0;
     std::vector<KtnChunkDesc> big;
     std::vector<std::vector<int32_t>> big_rows;

@@ -44,7 +44,7 @@ struct KtnProblem {
     int add_rows(int64_t first_row, int64_t nrows, const int64_t* eptr, const int32_t* op, const int32_t* arg,
                  const double* val, const double* lb, const double* ub, const uint8_t* flags);
     // sigma: rows per sorting window; lane_limit: max per-lane shared-memory bytes of a regular shape
-    int finalize(int64_t sigma, uint32_t lane_limit);
+    int finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit = 32768);
     void repack_bounds();                   // chunk_lb / chunk_ub from lb / ub
 };
 

@@ -164,7 +164,8 @@ def test_device_resident_round_and_counters(cuda_lib):
     g = h.eval_g(x0); h.set_bounds(w.lb, np.full(nr, np.quantile(g, 0.9)))
     ref = h.separate(x0)
     dx = torch.from_numpy(x0).cuda()
-    h.set_stream(torch.cuda.current_stream().cuda_stream)
+    s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    h.set_stream(s.cuda_stream)
     l0 = h.timings()["launches"]
     h.separate_device_async(dx.data_ptr())
     got = h.fetch_last()
