@@ -437,6 +437,23 @@ int KtnProblem::add_rows(int64_t first_row, int64_t nrows, const int64_t* eptr, 
                 const int cs = ShapeCompiler::term_cstride(code[found].kind & 0xf);
                 sd.j_in_blob = 1; sd.j_base = code[found].idx + cs - 1; sd.j_stride = cs;
             }
+            // family detection: exact match of the program against the canonical fused forms
+            {
+                auto is = [&](size_t q, uint8_t op, uint8_t kind, uint32_t n, uint32_t idx, uint32_t a) {
+                    return q < code.size() && code[q].op == op && code[q].kind == kind && code[q].n == n && code[q].idx == idx && code[q].a == a; };
+                sd.family = KTN_FAM_GENERIC;
+                if (sd.j_in_blob && nu >= 1 && nu < 60000 && sd.n_const == 2 * nu) {
+                    const uint8_t EA = KTN_T_EXP_AFF | KTN_TF_SAVEBLOB;
+                    if (code.size() == 8 && sd.j_base == 1 && sd.j_stride == 2 && is(0, KF_TERMS, EA | KTN_TF_FIRST, nu, 0, 0) && code[1].op == KF_STORE && code[1].kind == KTN_K_S &&
+                        code[2].op == KF_LOG && code[3].op == KR_ONE && code[4].op == KR_MULRCP && code[4].kind == KTN_K_S && code[4].idx == code[1].idx &&
+                        code[5].op == KF_STORE && code[5].kind == KTN_K_R1 && is(6, KR_TERMS, EA, nu, 0, 0) && code[7].op == K_END)
+                        sd.family = KTN_FAM_LSE;
+                    if (code.size() == 7 && sd.j_base == 0 && sd.j_stride == 1 && is(0, KF_TERMS, KTN_T_MULC_SQ | KTN_TF_FIRST, nu, 0, 0) && is(1, KF_TERMS, KTN_T_MULC_X, nu, nu, 0) &&
+                        code[2].op == KR_ONE && code[3].op == KF_STORE && code[3].kind == KTN_K_R1 && is(4, KR_TERMS, KTN_T_MULC_SQ, nu, 0, 0) &&
+                        is(5, KR_TERMS, KTN_T_MULC_X | KTN_TF_JACC, nu, nu, 0) && code[6].op == K_END)
+                        sd.family = KTN_FAM_QUAD;
+                }
+            }
             sd.prog_off = (uint32_t)prog.size();
             prog.insert(prog.end(), code.begin(), code.end());
             sid = (uint32_t)shapes.size();
@@ -545,6 +562,23 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
             }
             i = j;
         }
+    }
+    // regular chunks grouped by family (stable: window order is kept inside a family); one K1 launch per family present
+    {
+        std::vector<uint32_t> order(chunks.size());
+        for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return shapes[chunks[a].shape].family < shapes[chunks[b].shape].family; });
+        std::vector<KtnChunkDesc> sorted(chunks.size());
+        std::vector<int32_t> rows_sorted(chunk_rows.size());
+        for (uint32_t i = 0; i < order.size(); ++i) {
+            sorted[i] = chunks[order[i]];
+            sorted[i].row_slot = i * 32;
+            for (int q = 0; q < 32; ++q) rows_sorted[i * 32 + q] = chunk_rows[chunks[order[i]].row_slot + q];
+        }
+        chunks.swap(sorted); chunk_rows.swap(rows_sorted);
+        for (int f = 0; f <= KTN_FAM__COUNT; ++f) fam_begin[f] = (uint32_t)chunks.size();
+        for (uint32_t i = (uint32_t)chunks.size(); i-- > 0;) fam_begin[shapes[chunks[i].shape].family] = i;
+        for (int f = KTN_FAM__COUNT - 1; f >= 0; --f) if (fam_begin[f] > fam_begin[f + 1]) fam_begin[f] = fam_begin[f + 1];
     }
     n_regular_chunks = (uint32_t)chunks.size();
     for (size_t c = 0; c < big.size(); ++c) {

@@ -66,22 +66,48 @@ KTN_HD double ktn_pow2i(int k) { return ktn_bits2d((uint64_t)(k + 1023) << 52); 
 // exp(x).  k = round(x/ln2); r = x - k ln2 (two fma steps); exp(r) = 1 + r + r^2 q(r),
 // q = sum_{j=0..11} r^j/(j+2)!  split into even/odd halves for ILP; result scaled by 2^k.
 // Full-range path: NaN, +-inf, overflow, gradual underflow.
+// Coefficient tables.  On the device they live in constant memory so every DFMA reads its coefficient as a
+// constant-bank operand instead of materialising a 64-bit immediate with two moves.
+#define KTN_EXP_COEFFS { \
+    2.08767569878680989792e-09 /* 1/12! */, 2.75573192239858906526e-07 /* 1/10! */, 2.48015873015873015873e-05 /* 1/8! */, \
+    1.38888888888888888889e-03 /* 1/6!  */, 4.16666666666666666667e-02 /* 1/4!  */, 5.00000000000000000000e-01 /* 1/2! */, \
+    1.60590438368216145994e-10 /* 1/13! */, 2.50521083854417187751e-08 /* 1/11! */, 2.75573192239858906526e-06 /* 1/9! */, \
+    1.98412698412698412698e-04 /* 1/7!  */, 8.33333333333333333333e-03 /* 1/5!  */, 1.66666666666666666667e-01 /* 1/3! */ }
+#define KTN_LOG_COEFFS { \
+    8.69565217391304347826e-02 /* 2/23 */, 1.05263157894736842105e-01 /* 2/19 */, 1.33333333333333333333e-01 /* 2/15 */, \
+    1.81818181818181818182e-01 /* 2/11 */, 2.85714285714285714286e-01 /* 2/7  */, 6.66666666666666666667e-01 /* 2/3  */, \
+    9.52380952380952380952e-02 /* 2/21 */, 1.17647058823529411765e-01 /* 2/17 */, 1.53846153846153846154e-01 /* 2/13 */, \
+    2.22222222222222222222e-01 /* 2/9  */, 4.00000000000000000000e-01 /* 2/5  */, 0.0 }
+static const double KTN_EXPC_HOST[12] = KTN_EXP_COEFFS;
+static const double KTN_LOGC_HOST[12] = KTN_LOG_COEFFS;
+#if defined(__CUDACC__)
+static __constant__ double KTN_EXPC_DEV[12] = KTN_EXP_COEFFS;
+static __constant__ double KTN_LOGC_DEV[12] = KTN_LOG_COEFFS;
+#endif
+#if defined(__CUDA_ARCH__)
+#define KTN_EXPC(i) KTN_EXPC_DEV[i]
+#define KTN_LOGC(i) KTN_LOGC_DEV[i]
+#else
+#define KTN_EXPC(i) KTN_EXPC_HOST[i]
+#define KTN_LOGC(i) KTN_LOGC_HOST[i]
+#endif
+
 KTN_HD double ktn_exp_poly(double r) {
     double z = r * r;
-    // even part A(z): 1/2!, 1/4!, 1/6!, 1/8!, 1/10!, 1/12!
-    double a = 2.08767569878680989792e-09;              /* 1/12! */
-    a = ktn_fma(a, z, 2.75573192239858906526e-07);      /* 1/10! */
-    a = ktn_fma(a, z, 2.48015873015873015873e-05);      /* 1/8!  */
-    a = ktn_fma(a, z, 1.38888888888888888889e-03);      /* 1/6!  */
-    a = ktn_fma(a, z, 4.16666666666666666667e-02);      /* 1/4!  */
-    a = ktn_fma(a, z, 5.00000000000000000000e-01);      /* 1/2!  */
-    // odd part B(z): 1/3!, 1/5!, 1/7!, 1/9!, 1/11!, 1/13!
-    double b = 1.60590438368216145994e-10;              /* 1/13! */
-    b = ktn_fma(b, z, 2.50521083854417187751e-08);      /* 1/11! */
-    b = ktn_fma(b, z, 2.75573192239858906526e-06);      /* 1/9!  */
-    b = ktn_fma(b, z, 1.98412698412698412698e-04);      /* 1/7!  */
-    b = ktn_fma(b, z, 8.33333333333333333333e-03);      /* 1/5!  */
-    b = ktn_fma(b, z, 1.66666666666666666667e-01);      /* 1/3!  */
+    // even part A(z): 1/12!, 1/10!, 1/8!, 1/6!, 1/4!, 1/2!
+    double a = KTN_EXPC(0);
+    a = ktn_fma(a, z, KTN_EXPC(1));
+    a = ktn_fma(a, z, KTN_EXPC(2));
+    a = ktn_fma(a, z, KTN_EXPC(3));
+    a = ktn_fma(a, z, KTN_EXPC(4));
+    a = ktn_fma(a, z, KTN_EXPC(5));
+    // odd part B(z): 1/13!, 1/11!, 1/9!, 1/7!, 1/5!, 1/3!
+    double b = KTN_EXPC(6);
+    b = ktn_fma(b, z, KTN_EXPC(7));
+    b = ktn_fma(b, z, KTN_EXPC(8));
+    b = ktn_fma(b, z, KTN_EXPC(9));
+    b = ktn_fma(b, z, KTN_EXPC(10));
+    b = ktn_fma(b, z, KTN_EXPC(11));
     double q = ktn_fma(b, r, a);
     double s = ktn_fma(z, q, r);
     return 1.0 + s;
@@ -123,19 +149,19 @@ KTN_HD double ktn_exp(double x) {
 // Taylor tail of 2*atanh(s) = 2s + s*z*P(z), z = s^2, P(z) = sum_{n>=1} 2/(2n+1) z^(n-1), n = 1..11
 KTN_HD double ktn_log_tail_poly(double z) {
     double w = z * z;
-    // even-index coefficients (n = 1,3,5,7,9,11): 2/3, 2/7, 2/11, 2/15, 2/19, 2/23
-    double a = 8.69565217391304347826e-02;              /* 2/23 */
-    a = ktn_fma(a, w, 1.05263157894736842105e-01);      /* 2/19 */
-    a = ktn_fma(a, w, 1.33333333333333333333e-01);      /* 2/15 */
-    a = ktn_fma(a, w, 1.81818181818181818182e-01);      /* 2/11 */
-    a = ktn_fma(a, w, 2.85714285714285714286e-01);      /* 2/7  */
-    a = ktn_fma(a, w, 6.66666666666666666667e-01);      /* 2/3  */
-    // odd-index coefficients (n = 2,4,6,8,10): 2/5, 2/9, 2/13, 2/17, 2/21
-    double b = 9.52380952380952380952e-02;              /* 2/21 */
-    b = ktn_fma(b, w, 1.17647058823529411765e-01);      /* 2/17 */
-    b = ktn_fma(b, w, 1.53846153846153846154e-01);      /* 2/13 */
-    b = ktn_fma(b, w, 2.22222222222222222222e-01);      /* 2/9  */
-    b = ktn_fma(b, w, 4.00000000000000000000e-01);      /* 2/5  */
+    // odd n = 11,9,..,1: 2/23, 2/19, 2/15, 2/11, 2/7, 2/3
+    double a = KTN_LOGC(0);
+    a = ktn_fma(a, w, KTN_LOGC(1));
+    a = ktn_fma(a, w, KTN_LOGC(2));
+    a = ktn_fma(a, w, KTN_LOGC(3));
+    a = ktn_fma(a, w, KTN_LOGC(4));
+    a = ktn_fma(a, w, KTN_LOGC(5));
+    // even n = 10,8,..,2: 2/21, 2/17, 2/13, 2/9, 2/5
+    double b = KTN_LOGC(6);
+    b = ktn_fma(b, w, KTN_LOGC(7));
+    b = ktn_fma(b, w, KTN_LOGC(8));
+    b = ktn_fma(b, w, KTN_LOGC(9));
+    b = ktn_fma(b, w, KTN_LOGC(10));
     return ktn_fma(b, z, a);
 }
 

@@ -83,6 +83,16 @@ enum {
 };
 enum { KTN_TF_FIRST = 0x10, KTN_TF_JACC = 0x20, KTN_TF_SAVEBLOB = 0x40 };   // SAVEBLOB: exp values are kept in the term's dead `d` constant slot
 
+// shape families: program patterns with a hand-written, interpreter-free fast path in ktn_kernels.cu.
+// The fast path performs the same arithmetic as the shape's program (which stays the definition and is what
+// the host emulator runs); everything else takes the generic interpreter.
+enum {
+    KTN_FAM_GENERIC = 0,
+    KTN_FAM_LSE,        // log(sum_u exp(c_u x_u + d_u))                     (BASELINE.json configs[2])
+    KTN_FAM_QUAD,       // sum_u a_u x_u^2 + sum_u b_u x_u                  (BASELINE.json configs[1])
+    KTN_FAM__COUNT
+};
+
 // shape flags
 enum { KTN_SH_NL = 1, KTN_SH_DENSE = 2, KTN_SH_BIG = 4 };
 
@@ -98,7 +108,7 @@ struct KtnShapeDesc {
     // Jacobian accumulator of unique variable u lives at slot j_base + u * j_stride of the scratch
     // area, or -- when j_in_blob -- of the chunk's constant area (a constant that is dead by then).
     uint32_t j_base, j_stride, j_in_blob;
-    uint32_t pad;
+    uint32_t family;       // KTN_FAM_*: which hand-specialised instantiation of the round kernel runs this shape
     // blob sections of one chunk (lane stride L rows):
     //   consts: n_const * L doubles | cols: n_uniq * L int32 | order: n_uniq * L * order_bytes
 };
