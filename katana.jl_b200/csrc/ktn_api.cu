@@ -18,7 +18,7 @@ extern "C" const char* ktn_last_error(ktn_handle* h) { return h ? h->err.c_str()
 static void free_problem(ktn_handle* h) {
     DevBuf* all[] = {&h->chunks, &h->shapes, &h->prog, &h->blob, &h->chunk_rows, &h->chunk_lb, &h->chunk_ub, &h->jac_ptr, &h->jac_col,
                      &h->row_lb, &h->row_ub, &h->x, &h->force, &h->g_row, &h->b_row, &h->sel, &h->stage_val, &h->big_scratch,
-                     &h->st_flag, &h->st_cnt, &h->st_nnz, &h->table, &h->out_row, &h->out_ptr, &h->out_col, &h->out_val, &h->out_lo, &h->out_hi, &h->out_g, &h->out_viol, &h->out_b};
+                     &h->blk_cnt, &h->table, &h->out_row, &h->out_ptr, &h->out_col, &h->out_val, &h->out_lo, &h->out_hi, &h->out_g, &h->out_viol, &h->out_b};
     for (DevBuf* b : all) b->release();
     if (h->h_x) { cudaFreeHost(h->h_x); h->h_x = nullptr; }
     h->prob = KtnProblem();
@@ -50,8 +50,8 @@ extern "C" int ktn_create(const ktn_options* o, ktn_handle** out) {
     cudaEventCreate(&h->evx0); cudaEventCreate(&h->evx1);
     for (int i = 0; i < ktn_handle::RING; ++i) for (int j = 0; j < 3; ++j) cudaEventCreate(&h->ring[i][j]);
     if (cudaMallocHost(&h->h_counts, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
-    if (h->ticket.alloc(16) != cudaSuccess || h->counts.alloc(8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
-    cudaMemset(h->ticket.p, 0, 16);
+    if (h->ticket.alloc(4 * KTN_TICKETS) != cudaSuccess || h->counts.alloc(8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
+    cudaMemset(h->ticket.p, 0, 4 * KTN_TICKETS);
     { unsigned long long init[8] = {0, 0, ~0ull, ~0ull, 0, 0, ~0ull, 0}; cudaMemcpy(h->counts.p, init, 64, cudaMemcpyHostToDevice); }
     if (ktn_kernels_configure(h->max_smem) != cudaSuccess) { fprintf(stderr, "libktn: kernel configuration failed (is this an sm_100a device?)\n"); delete h; return KTN_ERR_CUDA; }
     *out = h;
@@ -147,9 +147,9 @@ extern "C" int ktn_load_end(ktn_handle* h) {
     CK(h, h->g_row.alloc(8 * (m + 1))); CK(h, h->b_row.alloc(8 * (m + 1))); CK(h, h->sel.alloc(4 * (m + 1)));
     CK(h, cudaMemset(h->sel.p, 0, 4 * (m + 1))); CK(h, cudaMemset(h->g_row.p, 0, 8 * (m + 1)));
     CK(h, h->stage_val.alloc(8 * (N + 1))); CK(h, h->big_scratch.alloc(8 * (P.big_scratch_doubles + 1)));
-    const size_t nblk = (m + 1023) / 1024 + 1;
-    CK(h, h->st_flag.alloc(4 * nblk)); CK(h, h->st_cnt.alloc(8 * nblk)); CK(h, h->st_nnz.alloc(16 * nblk));
-    CK(h, cudaMemset(h->st_flag.p, 0, 4 * nblk));
+    h->blk_stride = (uint32_t)((m + KTN_CROWS - 1) / KTN_CROWS + 1);
+    CK(h, h->blk_cnt.alloc(16 * (size_t)h->blk_stride));
+    CK(h, cudaMemset(h->blk_cnt.p, 0, 16 * (size_t)h->blk_stride));
     CK(h, upload(h->table, table));
     CK(h, h->out_row.alloc(4 * (m + 1))); CK(h, h->out_ptr.alloc(8 * (m + 2))); CK(h, h->out_col.alloc(4 * (N + 1))); CK(h, h->out_val.alloc(8 * (N + 1)));
     CK(h, h->out_lo.alloc(8 * (m + 1))); CK(h, h->out_hi.alloc(8 * (m + 1))); CK(h, h->out_g.alloc(8 * (m + 1))); CK(h, h->out_viol.alloc(8 * (m + 1))); CK(h, h->out_b.alloc(8 * (m + 1)));
@@ -183,6 +183,14 @@ extern "C" int ktn_jac_structure(ktn_handle* h, int64_t* row_ptr, int32_t* cols)
     return KTN_OK;
 }
 
+static KtnLaunchPlan make_plan(const ktn_handle* h) {
+    KtnLaunchPlan pl;
+    for (int f = 0; f <= KTN_FAM__COUNT; ++f) pl.fam_begin[f] = h->prob.fam_begin[f];
+    memcpy(pl.cls_begin, h->prob.cls_begin, sizeof pl.cls_begin);
+    pl.n_regular = h->prob.n_regular_chunks; pl.n_total = (uint32_t)h->prob.chunks.size();
+    return pl;
+}
+
 KtnRoundParams ktn_make_params(ktn_handle* h, const double* d_x, int mode, int do_round) {
     KtnRoundParams p; memset(&p, 0, sizeof p);
     p.chunks = h->chunks.as<KtnChunkDesc>(); p.shapes = h->shapes.as<KtnShapeDesc>(); p.prog = h->prog.as<KtnIns>();
@@ -196,7 +204,7 @@ KtnRoundParams ktn_make_params(ktn_handle* h, const double* d_x, int mode, int d
     p.warp_bytes = h->warp_bytes; p.blob_cap = h->blob_cap;
     p.g_row = h->g_row.as<double>(); p.b_row = h->b_row.as<double>(); p.sel = h->sel.as<uint32_t>();
     p.stage_val = h->stage_val.as<double>(); p.big_scratch = h->big_scratch.as<double>(); p.ticket = h->ticket.as<unsigned int>();
-    p.st_flag = h->st_flag.as<uint32_t>(); p.st_cnt = h->st_cnt.as<uint32_t>(); p.st_nnz = h->st_nnz.as<unsigned long long>();
+    p.blk_cnt = h->blk_cnt.as<unsigned long long>(); p.blk_stride = h->blk_stride;
     p.counts = h->counts.as<unsigned long long>();
     p.row_offset = h->row_offset;
     p.table = h->table.as<unsigned char>(); p.table_bytes = h->table_bytes; p.table_prog_off = h->table_prog_off; p.epoch = h->epoch;
@@ -227,7 +235,7 @@ static int enqueue_round(ktn_handle* h, const double* d_x, int mode, int do_roun
     if (h->ring_head - h->ring_tail >= ktn_handle::RING) { CK(h, cudaEventSynchronize(h->ring[h->ring_tail % ktn_handle::RING][2])); drain_ring(h, false); }
     cudaEvent_t* ev = h->ring[h->ring_head % ktn_handle::RING];
     CK(h, cudaEventRecord(ev[0], h->stream));
-    int n = ktn_launch_round(p, h->prob.n_regular_chunks, (uint32_t)h->prob.chunks.size(), h->num_sms, h->max_smem, h->epoch, h->stream, ev[1], &e);
+    int n = ktn_launch_round(p, make_plan(h), h->num_sms, h->max_smem, h->epoch, h->stream, ev[1], &e);
     h->tm.launches += n;
     if (e != cudaSuccess) return fail(h, KTN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     CK(h, cudaEventRecord(ev[2], h->stream));
@@ -327,7 +335,7 @@ extern "C" int ktn_eval_g(ktn_handle* h, const double* x, double* g_out) {
     int rc = upload_x(h, x); if (rc) return rc;
     KtnRoundParams p = ktn_make_params(h, h->x.as<double>(), KTN_MODE_SEPARATE, 0);
     cudaError_t e = cudaSuccess;
-    h->tm.launches += ktn_launch_eval(p, h->prob.n_regular_chunks, (uint32_t)h->prob.chunks.size(), h->num_sms, h->max_smem, h->stream, &e);
+    h->tm.launches += ktn_launch_eval(p, make_plan(h), h->num_sms, h->max_smem, h->stream, &e);
     if (e != cudaSuccess) return fail(h, KTN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     CK(h, cudaMemcpyAsync(g_out, h->g_row.p, 8 * (size_t)h->prob.num_constr, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 #include "../../include/ktn.h"
 
 namespace {
@@ -442,7 +443,8 @@ int KtnProblem::add_rows(int64_t first_row, int64_t nrows, const int64_t* eptr, 
                 auto is = [&](size_t q, uint8_t op, uint8_t kind, uint32_t n, uint32_t idx, uint32_t a) {
                     return q < code.size() && code[q].op == op && code[q].kind == kind && code[q].n == n && code[q].idx == idx && code[q].a == a; };
                 sd.family = KTN_FAM_GENERIC;
-                if (sd.j_in_blob && nu >= 1 && nu < 60000 && sd.n_const == 2 * nu) {
+                const bool no_family = getenv("KTN_NO_FAMILY") != nullptr;      // A/B switch: every shape takes the interpreter
+                if (!no_family && sd.j_in_blob && (sd.flags & KTN_SH_NL) && nu >= 1 && nu <= 256 && sd.n_const == 2 * nu) {
                     const uint8_t EA = KTN_T_EXP_AFF | KTN_TF_SAVEBLOB;
                     if (code.size() == 8 && sd.j_base == 1 && sd.j_stride == 2 && is(0, KF_TERMS, EA | KTN_TF_FIRST, nu, 0, 0) && code[1].op == KF_STORE && code[1].kind == KTN_K_S &&
                         code[2].op == KF_LOG && code[3].op == KR_ONE && code[4].op == KR_MULRCP && code[4].kind == KTN_K_S && code[4].idx == code[1].idx &&
@@ -510,7 +512,7 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
         const KtnShapeDesc& s = shapes[sid];
         KtnChunkDesc cd; memset(&cd, 0, sizeof cd);
         const uint32_t L = (isbig && nr == 1) ? 1u : 32u;
-        cd.shape = sid; cd.nrows = (uint16_t)nr; cd.stride = (uint16_t)L;
+        cd.shape = sid; cd.nrows = (uint16_t)nr; cd.stride = (uint16_t)L; cd.aux = s.n_uniq;
         uint64_t off = align_up(blob.size(), 128);
         uint64_t sec_c = 0, sec_col = align_up(sec_c + 8ull * s.n_const * L, 16), sec_ord = align_up(sec_col + 4ull * s.n_uniq * L, 16);
         uint64_t bytes = align_up(sec_ord + (uint64_t)s.order_bytes * s.n_uniq * L, 16);
@@ -527,6 +529,8 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
             int32_t* dcol = (int32_t*)(base + sec_col);
             for (uint32_t u = 0; u < s.n_uniq; ++u) dcol[(uint64_t)u * L + lane] = rcol[u];
             uint8_t* dord = base + sec_ord;
+            // family chunks (ktn_family.h) carry the inverse permutation: rank[u] = Jacobian entry index of unique variable u
+            if (s.family != KTN_FAM_GENERIC) { for (uint32_t p = 0; p < s.n_uniq; ++p) dord[(uint64_t)rord[p] * L + lane] = (uint8_t)p; continue; }
             for (uint32_t p = 0; p < s.n_uniq; ++p) {
                 uint64_t e = (uint64_t)p * L + lane;
                 if (s.order_bytes == 1) dord[e] = (uint8_t)rord[p];
@@ -563,29 +567,36 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
             i = j;
         }
     }
-    // regular chunks grouped by family (stable: window order is kept inside a family); one K1 launch per family present
+    // regular chunks grouped by (family, class) (stable: window order is kept inside a class); one K1 launch per family present
     {
+        auto key = [&](uint32_t c) { const KtnShapeDesc& s = shapes[chunks[c].shape]; return s.family * (uint32_t)KTN_FAM_NCLS + (s.family != KTN_FAM_GENERIC ? ktn_family_class(s.n_uniq) : 0u); };
         std::vector<uint32_t> order(chunks.size());
         for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return shapes[chunks[a].shape].family < shapes[chunks[b].shape].family; });
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key(a) < key(b); });
         std::vector<KtnChunkDesc> sorted(chunks.size());
         std::vector<int32_t> rows_sorted(chunk_rows.size());
+        std::vector<uint32_t> count((size_t)KTN_FAM__COUNT * KTN_FAM_NCLS + 1, 0u);
         for (uint32_t i = 0; i < order.size(); ++i) {
+            count[key(order[i])]++;
             sorted[i] = chunks[order[i]];
             sorted[i].row_slot = i * 32;
             for (int q = 0; q < 32; ++q) rows_sorted[i * 32 + q] = chunk_rows[chunks[order[i]].row_slot + q];
         }
         chunks.swap(sorted); chunk_rows.swap(rows_sorted);
-        for (int f = 0; f <= KTN_FAM__COUNT; ++f) fam_begin[f] = (uint32_t)chunks.size();
-        for (uint32_t i = (uint32_t)chunks.size(); i-- > 0;) fam_begin[shapes[chunks[i].shape].family] = i;
-        for (int f = KTN_FAM__COUNT - 1; f >= 0; --f) if (fam_begin[f] > fam_begin[f + 1]) fam_begin[f] = fam_begin[f + 1];
+        uint32_t at = 0;
+        for (int f = 0; f < KTN_FAM__COUNT; ++f) {
+            fam_begin[f] = at;
+            for (int k = 0; k < KTN_FAM_NCLS; ++k) { cls_begin[f][k] = at; at += count[(size_t)f * KTN_FAM_NCLS + k]; }
+            cls_begin[f][KTN_FAM_NCLS] = at;
+        }
+        fam_begin[KTN_FAM__COUNT] = at;
     }
     n_regular_chunks = (uint32_t)chunks.size();
     for (size_t c = 0; c < big.size(); ++c) {
         KtnChunkDesc cd = big[c];
         cd.row_slot = (uint32_t)chunk_rows.size();
         for (int q = 0; q < 32; ++q) chunk_rows.push_back(q < cd.nrows ? big_rows[c][q] : -1);
-        cd.scratch_off = big_scratch_doubles;
+        cd.aux = big_scratch_doubles;
         big_scratch_doubles += (uint64_t)shapes[cd.shape].n_scratch * cd.stride;
         chunks.push_back(cd);
     }

@@ -32,6 +32,7 @@ struct KtnProblem {
     std::vector<KtnChunkDesc> chunks;       // regular chunks first, then BIG chunks
     uint32_t n_regular_chunks = 0;
     uint32_t fam_begin[KTN_FAM__COUNT + 1] = {0};   // regular chunks of family f: [fam_begin[f], fam_begin[f+1])
+    uint32_t cls_begin[KTN_FAM__COUNT][KTN_FAM_NCLS + 1] = {{0}};   // ... of class k inside family f: [cls_begin[f][k], cls_begin[f][k+1])
     std::vector<uint8_t> blob;
     std::vector<int32_t> chunk_rows;        // chunk * 32 + lane -> row or -1
     std::vector<double> chunk_lb, chunk_ub; // same indexing

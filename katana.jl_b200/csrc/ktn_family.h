@@ -1,0 +1,177 @@
+// ktn_family.h -- row evaluators of the shape FAMILIES (KTN_FAM_* in ktn_program.h).
+//
+// A family is a program pattern the tape compiler recognises exactly (ktn_compile.cpp, "family detection").
+// For those shapes the round kernel does not interpret the program: it runs the functions below, which perform
+// the SAME fp64 operations in the SAME order as the shape's program (the program stays the definition; the
+// CPU suite runs both through tests/emu and checks them against the oracle bit for bit).
+// Reference: these replace forward_eval / reverse_eval of the per-constraint tape behind eval_g / eval_jac_g
+// (called at src/separators.jl:112-113), plus linear_oa_cut (src/algorithms.jl:3-18), round_coefs
+// (src/model.jl:200-207) and _addcut's finiteness test (src/model.jl:69) for the selected rows.
+//
+// Data of one family row (chunk blob, lane stride L):
+//   constants   two per unique variable u (LSE: c_u = slot 2u, d_u = slot 2u+1;  QUAD: a_u = slot u, b_u = slot nu+u)
+//   cols        column of unique variable u (first-occurrence order = the order of the terms)
+//   rank        position of unique variable u among the row's ascending columns = its Jacobian entry index
+//
+// Fast path (nu <= KTN_FAM_REGS, one instantiation per nu): the whole row lives in registers.  ktn_family_forward loads every constant
+// and column at once (one memory round trip), gathers x*, evaluates g.  ktn_family_cut builds the cut from the
+// same registers: no value is read twice.  Rows with more unique variables take the streaming fallbacks.
+#ifndef KTN_FAMILY_H
+#define KTN_FAMILY_H
+#include "ktn_interp.h"
+
+#define KTN_FAM_DMAX 1.7976931348623157e308
+
+template <int N> struct KtnFamRegs { double p0[N], p1[N], x[N]; };   // LSE: c, exp value;  QUAD: a, b
+
+template <int FAM> struct KtnFamily;
+
+// log(sum_u exp(c_u * x_u + d_u))
+// Program: KF_TERMS(EXP_AFF, FIRST); STORE S; LOG | KR_ONE; MULRCP S; STORE R1; KR_TERMS(EXP_AFF); END
+template <> struct KtnFamily<KTN_FAM_LSE> {
+    static KTN_HDM uint32_t slot0(uint32_t u, uint32_t) { return 2 * u; }
+    static KTN_HDM uint32_t slot1(uint32_t u, uint32_t) { return 2 * u + 1; }
+    static KTN_HDM double arg(double c, double d, double x) { return (0.0 + c * x) + d; }      // LOAD c; MUL x; ADDZ; ADD d
+    // forward over the N register-resident terms
+    template <int N> static KTN_HDM double forward(KtnFamRegs<N>& r, double& aux) {
+        double a[N];
+        bool slow = false;
+#pragma unroll
+        for (int u = 0; u < N; ++u) a[u] = arg(r.p0[u], r.p1[u], r.x[u]);
+#pragma unroll
+        for (int u = 0; u < N; ++u) r.p1[u] = ktn_exp_fast(a[u]);      // branch-free: N independent chains
+#pragma unroll
+        for (int u = 0; u < N; ++u) slow = slow || !ktn_exp_is_fast(a[u]);
+        if (slow) {
+#pragma unroll
+            for (int u = 0; u < N; ++u) if (!ktn_exp_is_fast(a[u])) r.p1[u] = ktn_exp_slow(a[u]);
+        }
+        double acc = 0.0;        // n-ary sum starts from zero(T): first step is 0.0 + e_0
+#pragma unroll
+        for (int u = 0; u < N; ++u) acc = acc + r.p1[u];
+        aux = acc;
+        return ktn_log(acc);
+    }
+    static KTN_HDM double adjoint(double aux) { return revmul(1.0, 1.0 / aux); }                  // KR_ONE; KR_MULRCP S
+    static KTN_HDM double jac(double adj, double c, double e, double) { return 0.0 + revmul(revmul(adj, e), c); }
+    // streaming fallback (any nu)
+    template <class R> static KTN_HDM double forward_stream(const R& r, double& aux) {
+        double acc = 0.0;
+        for (uint32_t u = 0; u < r.nu; ++u) acc = acc + ktn_exp(arg(r.cst(2 * u), r.cst(2 * u + 1), r.x(u)));
+        aux = acc;
+        return ktn_log(acc);
+    }
+    template <class R> static KTN_HDM double jac_stream(const R& r, uint32_t u, double adj) {
+        const double c = r.cst(2 * u);
+        return jac(adj, c, ktn_exp(arg(c, r.cst(2 * u + 1), r.x(u))), 0.0);
+    }
+};
+
+// sum_u a_u * x_u^2 + sum_u b_u * x_u
+// Program: KF_TERMS(MULC_SQ, FIRST); KF_TERMS(MULC_X) | KR_ONE; STORE R1; KR_TERMS(MULC_SQ); KR_TERMS(MULC_X, JACC); END
+template <> struct KtnFamily<KTN_FAM_QUAD> {
+    static KTN_HDM uint32_t slot0(uint32_t u, uint32_t) { return u; }
+    static KTN_HDM uint32_t slot1(uint32_t u, uint32_t nu) { return nu + u; }
+    template <int N> static KTN_HDM double forward(KtnFamRegs<N>& r, double& aux) {
+        double acc = 0.0;
+#pragma unroll
+        for (int u = 0; u < N; ++u) acc = acc + (r.x[u] * r.x[u]) * r.p0[u];
+#pragma unroll
+        for (int u = 0; u < N; ++u) acc = acc + r.p1[u] * r.x[u];
+        aux = 0.0;
+        return acc;
+    }
+    static KTN_HDM double adjoint(double) { return 1.0; }                                         // KR_ONE
+    static KTN_HDM double jac(double adj, double a, double b, double x) { return (0.0 + revmul(revmul(adj, a), 2.0 * x)) + revmul(adj, b); }
+    template <class R> static KTN_HDM double forward_stream(const R& r, double& aux) {
+        double acc = 0.0;
+        for (uint32_t u = 0; u < r.nu; ++u) { const double x = r.x(u); acc = acc + (x * x) * r.cst(u); }
+        for (uint32_t u = 0; u < r.nu; ++u) acc = acc + r.cst(r.nu + u) * r.x(u);
+        aux = 0.0;
+        return acc;
+    }
+    template <class R> static KTN_HDM double jac_stream(const R& r, uint32_t u, double adj) { return jac(adj, r.cst(u), r.cst(r.nu + u), r.x(u)); }
+};
+
+// ---- register-resident rows -------------------------------------------------------------------------------
+// Row context R: nu, cst(i), col(u), xat(col), rank(u).  All loads of the row are issued before the first use.
+template <int FAM, int N, class R>
+KTN_HDM double ktn_family_forward(const R& r, KtnFamRegs<N>& v, double& aux) {
+    typedef KtnFamily<FAM> F;
+    int32_t col[N];
+#pragma unroll
+    for (int u = 0; u < N; ++u) { v.p0[u] = r.cst(F::slot0(u, N)); v.p1[u] = r.cst(F::slot1(u, N)); col[u] = r.col(u); }
+#pragma unroll
+    for (int u = 0; u < N; ++u) v.x[u] = r.xat(col[u]);
+    return F::template forward<N>(v, aux);
+}
+
+// Cut row from the registers ktn_family_forward left behind.  Sink S: t(q) scratch cells (one per Jacobian entry) and the
+// coefficient row out[0..nu).  Coefficients and the products -x_u * J_u are computed in term order and scattered to
+// their Jacobian entry index; the constant is then accumulated sequentially in entry order, as the reference does
+// (b = g; b += -xstar[col] * partial).  Returns true when a coefficient is not finite.
+template <int FAM, int N, class R, class S>
+KTN_HDM bool ktn_family_cut(const R& r, const KtnFamRegs<N>& v, S& s, double g, double aux, bool do_round, double rng, double& b_out) {
+    typedef KtnFamily<FAM> F;
+    const uint32_t nu = N;
+    const double adj = F::adjoint(aux);
+    double mx = -ktn_inf(), mn = ktn_inf();
+    bool anynan = false;
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        const double jv = F::jac(adj, v.p0[u], v.p1[u], v.x[u]);
+        const uint32_t q = r.rank(u);
+        s.put_t(q, (-v.x[u]) * jv);
+        s.put_j(q, jv);
+        mx = jv > mx ? jv : mx; mn = jv < mn ? jv : mn; anynan = anynan || (jv != jv);
+    }
+    double b = g;
+#pragma unroll
+    for (int q = 0; q < N; ++q) b = b + s.get_t(q);
+    b_out = b;
+    // round_coefs zeroes jv when jv + rng < maximum(coefs).  jv + rng is monotone in jv, so when the smallest coefficient
+    // passes (and everything is finite) all pass: the exact second sweep only runs for rows that need it.
+    bool bad = false;
+    if (anynan || !(ktn_fabs(mn) <= KTN_FAM_DMAX) || !(ktn_fabs(mx) <= KTN_FAM_DMAX) || (do_round && (mn + rng < mx))) {
+        if (anynan) mx = ktn_nan();     // Julia's maximum() propagates NaN
+        for (uint32_t q = 0; q < nu; ++q) {
+            double jv = s.get_j(q);
+            if (do_round && (jv + rng < mx)) jv = 0.0;
+            bad = bad || !(ktn_fabs(jv) <= KTN_FAM_DMAX);
+            s.put_j(q, jv);
+        }
+    }
+    return bad;
+}
+
+// ---- streaming fallback for rows with more than KTN_FAM_REGS unique variables -----------------------------
+// Sink S here: put_j / get_j on the coefficient row, and xsorted(q) = x* of the q-th ascending column.
+template <int FAM, class R, class S>
+KTN_HDM bool ktn_family_cut_stream(const R& r, S& s, double g, double aux, bool do_round, double rng, double& b_out) {
+    typedef KtnFamily<FAM> F;
+    const uint32_t nu = r.nu;
+    const double adj = F::adjoint(aux);
+    double mx = -ktn_inf(), mn = ktn_inf();
+    bool anynan = false;
+    for (uint32_t u = 0; u < nu; ++u) {
+        const double jv = F::jac_stream(r, u, adj);
+        s.put_j(r.rank(u), jv);
+        mx = jv > mx ? jv : mx; mn = jv < mn ? jv : mn; anynan = anynan || (jv != jv);
+    }
+    double b = g;
+    for (uint32_t q = 0; q < nu; ++q) b = b + (-s.xsorted(q)) * s.get_j(q);
+    b_out = b;
+    bool bad = false;
+    if (anynan || !(ktn_fabs(mn) <= KTN_FAM_DMAX) || !(ktn_fabs(mx) <= KTN_FAM_DMAX) || (do_round && (mn + rng < mx))) {
+        if (anynan) mx = ktn_nan();
+        for (uint32_t q = 0; q < nu; ++q) {
+            double jv = s.get_j(q);
+            if (do_round && (jv + rng < mx)) jv = 0.0;
+            bad = bad || !(ktn_fabs(jv) <= KTN_FAM_DMAX);
+            s.put_j(q, jv);
+        }
+    }
+    return bad;
+}
+
+#endif

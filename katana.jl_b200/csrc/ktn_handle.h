@@ -32,12 +32,12 @@ struct ktn_handle {
     KtnProblem prob;
     bool loading = false, loaded = false, round_pending = false, have_round = false;
     DevBuf chunks, shapes, prog, blob, chunk_rows, chunk_lb, chunk_ub, jac_ptr, jac_col, row_lb, row_ub;
-    DevBuf x, force, g_row, b_row, sel, stage_val, big_scratch, ticket, st_flag, st_cnt, st_nnz, counts, table;
+    DevBuf x, force, g_row, b_row, sel, stage_val, big_scratch, ticket, blk_cnt, counts, table;
     DevBuf out_row, out_ptr, out_col, out_val, out_lo, out_hi, out_g, out_viol, out_b;
     double* h_x = nullptr;                 // pinned
     unsigned long long* h_counts = nullptr;  // pinned [8]
     int64_t n_cuts = 0, nnz_cuts = 0, err_row = -1;
-    uint32_t warp_bytes = 0, blob_cap = 0, table_bytes = 0, table_prog_off = 0, epoch = 0;
+    uint32_t warp_bytes = 0, blob_cap = 0, table_bytes = 0, table_prog_off = 0, epoch = 0, blk_stride = 0;
     ktn_timings tm;
     std::string err;
     // sharding (ktn_comm.cu): NCCL communicator, packed send buffer, gathered buffer

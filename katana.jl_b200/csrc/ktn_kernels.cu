@@ -5,8 +5,14 @@
 // constraint (src/separators.jl:111-116), then tests each NL row (src/separators.jl:120) and
 // builds a cut per violated row (src/algorithms.jl:3-18, src/model.jl:200-207, :68-79).
 //
-// Here a round is two launches:
-//   K1 ktn_round_kernel   one WARP runs 32 rows of the same shape in lock step.  Per chunk:
+// Here a round is two launches (three when a problem mixes family and generic shapes):
+//   K1f ktn_family_kernel  shapes of a recognised FAMILY (log-sum-exp, separable quadratic; ktn_family.h):
+//        no interpreter.  Phase A: one thread per row streams the row's constants / column ids with coalesced
+//        loads straight from the chunk blob (lane stride 32), gathers x* through L1/L2, evaluates g and tests it.
+//        Selected rows are pushed on a block-wide shared-memory list; phase B drains the list 256 rows at a
+//        time, one thread per SELECTED row (dense lanes whatever the violated fraction): Jacobian row in
+//        Jacobian-entry order, cut constant, round_coefs, finiteness, coefficients to the staging CSR.
+//   K1 ktn_round_kernel   every other shape: one WARP interprets 32 rows of the same shape in lock step.  Per chunk:
 //        1. an elected lane issues a TMA bulk copy (cp.async.bulk + mbarrier) of the chunk's SoA
 //           blob (constants, column ids, sort order) into the warp's shared memory; the next
 //           chunk's ticket and descriptor are fetched while the current chunk computes;
@@ -16,15 +22,17 @@
 //           (accumulators aliased into dead constant slots of the blob where the compiler could);
 //        5. violated lanes build the cut row (constant b, round_coefs, finiteness) and store the
 //           coefficients at the row's slot of the static Jacobian CSR layout.
-//   K2 ktn_compact_kernel single-pass (decoupled look-back) ordered stream compaction of the
-//        selected rows into the CSR the host LP consumes, ascending row order, coalesced copies.
+//   K2 ktn_compact_kernel ordered stream compaction of the selected rows into the CSR the host LP consumes,
+//        ascending row order, coalesced copies.  K1 leaves per-block cut counts (one 64-bit atomic per warp and
+//        block of 4096 rows), so every K2 block finds its output offset with one short sum: no look-back chain.
 // BIG shapes (long tapes, the dense epigraph row) take ktn_big_kernel with global scratch.
 // All arithmetic is fp64, unfused, in the oracle's order.
 #include "ktn_kernels.cuh"
 #include "ktn_math.h"
 #include "ktn_interp.h"
+#include "ktn_family.h"
 
-#define KTN_CBLOCK 1024   // rows per compaction block
+#define KTN_CBLOCK 1024   // threads per compaction block
 
 namespace {
 
@@ -46,6 +54,159 @@ __device__ __forceinline__ bool row_selected(const KtnRoundParams& p, double g, 
     if (p.mode == KTN_MODE_FORCE) return p.force[row] != 0;
     const bool sat = (g >= lb - p.f_tol) && (g <= ub + p.f_tol);   // src/separators.jl:120 (NaN -> not satisfied)
     return !sat;
+}
+
+// Adds the selected rows of the calling lanes to the per-block cut counts K2 turns into output offsets.
+// Called by all lanes of `act` (the lanes that hold a selected row); lanes whose rows fall into the same
+// compaction block share one 64-bit atomic.
+__device__ __forceinline__ void count_selected(const KtnRoundParams& p, unsigned act, int32_t row, uint32_t nnz) {
+    const uint32_t blk = (uint32_t)row >> KTN_CROWS_LOG2;
+    const unsigned grp = __match_any_sync(act, blk);
+    const uint32_t nz = __reduce_add_sync(grp, nnz);
+    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(grp) - 1))
+        atomicAdd(p.blk_cnt + (size_t)(p.epoch & 1u) * p.blk_stride + blk, ((unsigned long long)__popc(grp) << KTN_BLK_SHIFT) + nz);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1f: family shapes (ktn_family.h).  One warp per chunk, one thread per row, dynamic chunk tickets; warps are independent.
+// The whole row is register resident: every constant and column id of the row is requested at once with coalesced loads
+// straight from the chunk blob (lane stride 32; streamed past L1 so that L1 keeps x*), x* is gathered through L1/L2, g is
+// evaluated and tested, and the selected lanes build their cut row from the same registers -- nothing is read twice.
+// ---------------------------------------------------------------------------------------------
+#define KTN_FW_WARPS 4
+#define KTN_FW_PASS 8         // selected lanes that build their cut at the same time (scratch cells per Jacobian entry)
+
+__device__ __forceinline__ double ldg_stream(const double* p) {
+    double v; asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ int32_t ldg_stream(const int32_t* p) {
+    int32_t v; asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ uint32_t ldg_stream(const uint8_t* p) {
+    uint32_t v; asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+}
+
+struct FamRow {     // row context of ktn_family.h: SoA sections of one chunk, lane offset applied
+    const double* C; const int32_t* cols; const uint8_t* rk; const double* X; uint32_t nu;
+    __device__ __forceinline__ double cst(uint32_t i) const { return ldg_stream(C + i * 32u); }
+    __device__ __forceinline__ int32_t col(uint32_t u) const { return ldg_stream(cols + u * 32u); }
+    __device__ __forceinline__ double xat(int32_t c) const { return __ldg(X + c); }
+    __device__ __forceinline__ double x(uint32_t u) const { return xat(col(u)); }
+    __device__ __forceinline__ uint32_t rank(uint32_t u) const { return ldg_stream(rk + u * 32u); }
+};
+struct FamSink {    // cut-row sink: products in the warp's shared-memory scratch, coefficients in the staging CSR
+    double* t; double* out;
+    __device__ __forceinline__ void put_t(uint32_t q, double v) { t[q * KTN_FW_PASS] = v; }
+    __device__ __forceinline__ double get_t(uint32_t q) const { return t[q * KTN_FW_PASS]; }
+    __device__ __forceinline__ void put_j(uint32_t q, double v) { out[q] = v; }
+    __device__ __forceinline__ double get_j(uint32_t q) const { return out[q]; }
+};
+struct FamStreamSink {
+    double* out; const int32_t* scol; const double* X;
+    __device__ __forceinline__ void put_j(uint32_t q, double v) { out[q] = v; }
+    __device__ __forceinline__ double get_j(uint32_t q) const { return out[q]; }
+    __device__ __forceinline__ double xsorted(uint32_t q) const { return __ldg(X + __ldg(scol + q)); }
+};
+
+__device__ __forceinline__ void family_finish_row(const KtnRoundParams& p, unsigned grp, int32_t row, uint32_t nu, double b, bool bad) {
+    p.b_row[row] = b;
+    p.sel[row] = nu | (bad ? KTN_SEL_ERRBIT : 0u);
+    if (bad) atomicMin(&p.counts[2 + (p.epoch & 1u)], (unsigned long long)row + 1ull);
+    count_selected(p, grp, row, nu);
+}
+
+// N = 1..16: register-resident rows of exactly N unique variables; N = 0: streaming fallback (any count)
+template <int FAM, int N>
+__device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c, uint32_t lane, double* scratch) {
+    typedef KtnFamily<FAM> F;
+    const KtnChunkDesc cd = p.chunks[c];
+    const uint32_t nu = N > 0 ? (uint32_t)N : (uint32_t)cd.aux, slot = c * 32u + lane;
+    const unsigned char* blob = p.blob + cd.blob_off;
+    const FamRow r{reinterpret_cast<const double*>(blob) + lane, reinterpret_cast<const int32_t*>(blob + 512u * nu) + lane, blob + 640u * nu + lane, p.x, nu};
+    const int32_t row = ldg_stream(p.chunk_rows + slot);
+    double lb = 0.0, ub = 0.0;
+    if (p.mode != KTN_MODE_EVAL) { lb = ldg_stream(p.chunk_lb + slot); ub = ldg_stream(p.chunk_ub + slot); }
+    constexpr int NR = N > 0 ? N : 1;
+    KtnFamRegs<NR> v;
+    double aux, g;
+    if constexpr (N > 0) g = ktn_family_forward<FAM, NR>(r, v, aux);
+    else g = F::forward_stream(r, aux);
+    if (row >= 0) p.g_row[row] = g;
+    if (p.mode == KTN_MODE_EVAL) return;
+    const bool selected = row >= 0 && row_selected(p, g, lb, ub, row);
+    if (row >= 0 && !selected) p.sel[row] = 0u;
+    unsigned selm = __ballot_sync(0xffffffffu, selected);
+    if constexpr (N > 0) {
+        while (selm) {      // KTN_FW_PASS selected lanes at a time share the warp's scratch
+            const uint32_t cut = __fns(selm, 0, KTN_FW_PASS + 1);
+            const unsigned grp = cut == 0xffffffffu ? selm : (selm & ((1u << cut) - 1u));
+            if ((grp >> lane) & 1u) {
+                FamSink s{scratch + __popc(grp & ((1u << lane) - 1u)), p.stage_val + p.jac_ptr[row]};
+                double b;
+                const bool bad = ktn_family_cut<FAM, NR>(r, v, s, g, aux, p.do_round != 0, p.rng, b);
+                family_finish_row(p, grp, row, nu, b, bad);
+            }
+            __syncwarp();
+            selm &= ~grp;
+        }
+    } else if (selected) {
+        const int64_t base = p.jac_ptr[row];
+        FamStreamSink s{p.stage_val + base, p.jac_col + base, p.x};
+        double b;
+        const bool bad = ktn_family_cut_stream<FAM>(r, s, g, aux, p.do_round != 0, p.rng, b);
+        family_finish_row(p, selm, row, nu, b, bad);
+    }
+}
+
+template <int FAM>
+__device__ __forceinline__ void family_dispatch(const KtnRoundParams& p, uint32_t cls, uint32_t c, uint32_t lane, double* scratch) {
+    switch (cls) {
+#define KTN_CASE(n) case n: family_chunk<FAM, n>(p, c, lane, scratch); break;
+        KTN_CASE(1) KTN_CASE(2) KTN_CASE(3) KTN_CASE(4) KTN_CASE(5) KTN_CASE(6) KTN_CASE(7) KTN_CASE(8)
+        KTN_CASE(9) KTN_CASE(10) KTN_CASE(11) KTN_CASE(12) KTN_CASE(13) KTN_CASE(14) KTN_CASE(15) KTN_CASE(16)
+#undef KTN_CASE
+        default: family_chunk<FAM, 0>(p, c, lane, scratch); break;
+    }
+}
+
+// Every class has its own ticket counter.  The warps of one SM start in the same class (classes are spread over the SMs in
+// proportion to their work) and move to the next class when theirs runs dry, so an SM executes ONE specialised code path at
+// a time: the instruction working set stays one class, not the whole kernel.
+template <int FAM>
+__global__ void __launch_bounds__(KTN_FW_WARPS * 32, 16 / KTN_FW_WARPS) ktn_family_kernel(const KtnRoundParams p) {
+    __shared__ double sh_scratch[KTN_FW_WARPS][KTN_FAM_REGS * KTN_FW_PASS];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    unsigned int* tickets = p.ticket + p.ticket_idx;
+    uint32_t cls = 0;
+    {
+        uint32_t smid, nsm;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+        unsigned long long total = 0, acc = 0;
+        for (uint32_t k = 0; k < KTN_FAM_NCLS; ++k) total += (unsigned long long)(p.cls_begin[k + 1] - p.cls_begin[k]) * ((k ? k : 32u) + 3u);
+        const unsigned long long target = (total * (2ull * smid + 1ull)) / (2ull * nsm);
+        for (uint32_t k = 0; k < KTN_FAM_NCLS; ++k) {
+            acc += (unsigned long long)(p.cls_begin[k + 1] - p.cls_begin[k]) * ((k ? k : 32u) + 3u);
+            if (acc > target) { cls = k; break; }
+        }
+    }
+    auto take = [&](uint32_t k) -> uint32_t {      // next chunk ticket of class k (an empty class costs no atomic)
+        uint32_t t = 0;
+        if (lane == 0 && p.cls_begin[k + 1] > p.cls_begin[k]) t = atomicAdd(&tickets[k], 1u);
+        return t;
+    };
+    uint32_t cur = __shfl_sync(0xffffffffu, take(cls), 0), fails = 0;
+    for (;;) {
+        while (p.cls_begin[cls] + cur >= p.cls_begin[cls + 1]) {
+            if (++fails == KTN_FAM_NCLS) return;
+            cls = cls + 1 == KTN_FAM_NCLS ? 0u : cls + 1;
+            cur = __shfl_sync(0xffffffffu, take(cls), 0);
+        }
+        fails = 0;
+        const uint32_t nxt = take(cls);            // travels while this chunk computes
+        family_dispatch<FAM>(p, cls, p.cls_begin[cls] + cur, lane, sh_scratch[warp]);
+        cur = __shfl_sync(0xffffffffu, nxt, 0);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -70,7 +231,7 @@ __global__ void __launch_bounds__(512, 1) ktn_round_kernel(const KtnRoundParams 
     uint32_t parity = 0;
 
     uint32_t c_cur = 0, c_nxt = 0;
-    if (lane == 0) { c_cur = atomicAdd(&p.ticket[0], 1u); c_nxt = atomicAdd(&p.ticket[0], 1u); }
+    if (lane == 0) { c_cur = atomicAdd(&p.ticket[p.ticket_idx], 1u); c_nxt = atomicAdd(&p.ticket[p.ticket_idx], 1u); }
     c_cur = p.chunk_begin + __shfl_sync(0xffffffffu, c_cur, 0);
     c_nxt = p.chunk_begin + __shfl_sync(0xffffffffu, c_nxt, 0);
     KtnChunkDesc cd, cdn;
@@ -83,7 +244,7 @@ __global__ void __launch_bounds__(512, 1) ktn_round_kernel(const KtnRoundParams 
     while (have) {
         // next-next ticket and next descriptor travel while this chunk computes
         uint32_t c_n2 = 0;
-        if (lane == 0) c_n2 = atomicAdd(&p.ticket[0], 1u);
+        if (lane == 0) c_n2 = atomicAdd(&p.ticket[p.ticket_idx], 1u);
         const bool have_nxt = c_nxt < p.chunk_end;
         if (have_nxt) cdn = p.chunks[c_nxt];
         const int32_t row = p.chunk_rows[cd.row_slot + lane];
@@ -115,7 +276,8 @@ __global__ void __launch_bounds__(512, 1) ktn_round_kernel(const KtnRoundParams 
             if (!EVAL_ONLY) {
                 const bool selected = row >= 0 && row_selected(p, g, lb, ub, row);
                 uint32_t selv = 0u;
-                if (__any_sync(0xffffffffu, selected)) {
+                const unsigned selm = __ballot_sync(0xffffffffu, selected);
+                if (selm) {
                     run_program(prog, sd.n_fwd, sd.n_ins, m, 0xffffffffu);
                     if (selected) {
                         // linear_oa_cut (src/algorithms.jl:8-16): b = g; b += -xstar[col]*partial in Jacobian-entry order.
@@ -157,6 +319,7 @@ __global__ void __launch_bounds__(512, 1) ktn_round_kernel(const KtnRoundParams 
                         selv = nu | (bad ? KTN_SEL_ERRBIT : 0u);
                         p.b_row[row] = b;
                         if (bad) atomicMin(&p.counts[2 + (p.epoch & 1u)], (unsigned long long)row + 1ull);
+                        count_selected(p, selm, row, nu);
                     }
                 }
                 if (row >= 0) p.sel[row] = selv;
@@ -190,7 +353,7 @@ __global__ void __launch_bounds__(128) ktn_big_kernel(const KtnRoundParams p) {
         const size_t sec_ord = (sec_col + (size_t)4 * nu * L + 15) & ~(size_t)15;
         const int32_t* cols = reinterpret_cast<const int32_t*>(blob + sec_col);
         const uint8_t* ord = blob + sec_ord;
-        double* S = p.big_scratch + cd.scratch_off;
+        double* S = p.big_scratch + cd.aux;
         double* J = S + (size_t)sd.j_base * L;     // BIG shapes keep their accumulators in scratch (j_in_blob == 0)
         const size_t jmul = (size_t)L * sd.j_stride;
         double g = 0.0; bool selected = false;
@@ -210,6 +373,7 @@ __global__ void __launch_bounds__(128) ktn_big_kernel(const KtnRoundParams p) {
         }
         if (EVAL_ONLY) continue;
         if (!(sd.flags & KTN_SH_DENSE)) {
+            const unsigned selm = __ballot_sync(0xffffffffu, selected);
             if (selected) {
                 double b = g, mx = 0.0;
                 for (uint32_t q = 0; q < nu; ++q) {
@@ -230,6 +394,7 @@ __global__ void __launch_bounds__(128) ktn_big_kernel(const KtnRoundParams p) {
                 p.b_row[row] = b;
                 p.sel[row] = nu | (bad ? KTN_SEL_ERRBIT : 0u);
                 if (bad) atomicMin(&p.counts[2 + (p.epoch & 1u)], (unsigned long long)row + 1ull);
+                count_selected(p, selm, row, nu);
             } else if (row >= 0) p.sel[row] = 0u;
         } else {
             // dense row: every column 0..num_var-1 is an entry (src/nlpeval.jl:49-54); columns the
@@ -274,6 +439,7 @@ __global__ void __launch_bounds__(128) ktn_big_kernel(const KtnRoundParams p) {
                 if (lane == 0) {
                     p.b_row[rrow] = b; p.sel[rrow] = (uint32_t)n | (bad ? KTN_SEL_ERRBIT : 0u);
                     if (bad) atomicMin(&p.counts[2 + (p.epoch & 1u)], (unsigned long long)rrow + 1ull);
+                    atomicAdd(p.blk_cnt + (size_t)(p.epoch & 1u) * p.blk_stride + ((uint32_t)rrow >> KTN_CROWS_LOG2), (1ull << KTN_BLK_SHIFT) + (unsigned long long)n);
                 }
                 __syncwarp();
             }
@@ -282,7 +448,7 @@ __global__ void __launch_bounds__(128) ktn_big_kernel(const KtnRoundParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: ordered stream compaction, single pass with decoupled look-back.
+// K2: ordered stream compaction; block offsets come from the per-block cut counts K1 left in blk_cnt.
 // Selected rows -> CSR in ascending row order (the loop order of src/model.jl:272).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void block_scan2(uint32_t& a, unsigned long long& b, uint32_t& ta, unsigned long long& tb) {
@@ -315,60 +481,45 @@ __device__ __forceinline__ void block_scan2(uint32_t& a, unsigned long long& b, 
     __syncthreads();
 }
 
-// look-back state of block k: st_flag[k] = (epoch << 2) | {1: aggregate ready, 2: inclusive prefix ready};
-// aggregates live in st_cnt / st_nnz [k], inclusive prefixes in [nblocks + k].
-// One block = KTN_CBLOCK threads x KTN_CRPT consecutive rows per thread.
-#define KTN_CRPT 4
-#define KTN_CROWS (KTN_CBLOCK * KTN_CRPT)
+// One block = KTN_CBLOCK threads x KTN_CRPT consecutive rows per thread = KTN_CROWS rows.
+#define KTN_CRPT (KTN_CROWS / KTN_CBLOCK)
 __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRoundParams p, uint32_t nblocks, uint32_t epoch) {
-    __shared__ uint32_t s_bid, s_cnt_base; __shared__ unsigned long long s_nnz_base;
+    __shared__ uint32_t s_cnt_base; __shared__ unsigned long long s_nnz_base;
+    __shared__ unsigned long long s_red[2][32];
     __shared__ uint32_t s_off[KTN_CROWS + 1];        // exclusive nnz offsets of the block's selected rows (compact list)
     __shared__ uint16_t s_rowl[KTN_CROWS];           // block-local row index of each selected row
-    if (threadIdx.x == 0) s_bid = atomicAdd(&p.ticket[2], 1u);
-    __syncthreads();
-    const uint32_t bid = s_bid;
+    const uint32_t bid = blockIdx.x;
     const int64_t row0 = (int64_t)bid * KTN_CROWS, i0 = row0 + (int64_t)threadIdx.x * KTN_CRPT;
+    // output offset of this block = cuts / nnz of all blocks before it, from K1's per-block counts
+    unsigned long long* bc = p.blk_cnt + (size_t)(epoch & 1u) * p.blk_stride;
+    {
+        unsigned long long cb = 0, nb = 0;
+        for (uint32_t j = threadIdx.x; j < bid; j += KTN_CBLOCK) { const unsigned long long v = bc[j]; cb += v >> KTN_BLK_SHIFT; nb += v & KTN_BLK_NNZ_MASK; }
+        for (int o = 16; o > 0; o >>= 1) { cb += __shfl_xor_sync(0xffffffffu, cb, o); nb += __shfl_xor_sync(0xffffffffu, nb, o); }
+        if ((threadIdx.x & 31u) == 0) { s_red[0][threadIdx.x >> 5] = cb; s_red[1][threadIdx.x >> 5] = nb; }
+    }
     uint32_t sv[KTN_CRPT];
     if (i0 + KTN_CRPT <= p.num_rows) { const uint4 q = *reinterpret_cast<const uint4*>(p.sel + i0); sv[0] = q.x; sv[1] = q.y; sv[2] = q.z; sv[3] = q.w; }
     else for (int r = 0; r < KTN_CRPT; ++r) sv[r] = (i0 + r < p.num_rows) ? p.sel[i0 + r] : 0u;
     uint32_t a = 0; unsigned long long b = 0;
     for (int r = 0; r < KTN_CRPT; ++r) { a += sv[r] ? 1u : 0u; b += sv[r] & ~KTN_SEL_ERRBIT; }
     uint32_t ta; unsigned long long tb;
-    block_scan2(a, b, ta, tb);
-    if (threadIdx.x < 32) {   // warp 0: publish the aggregate, then look back 32 predecessors per probe
-        volatile uint32_t* flag = p.st_flag; volatile uint32_t* scnt = p.st_cnt; volatile unsigned long long* snnz = p.st_nnz;
-        const uint32_t lane = threadIdx.x;
-        uint32_t cb = 0; unsigned long long nb = 0;
-        if (bid > 0) {
-            if (lane == 0) { scnt[bid] = ta; snnz[bid] = tb; __threadfence(); flag[bid] = (epoch << 2) | 1u; }
-            int64_t wnd = (int64_t)bid - 1;      // lane l inspects block wnd - l
-            for (;;) {
-                const int64_t k = wnd - lane;
-                uint32_t f = 2u;                  // blocks before the first count as an (empty) inclusive prefix
-                if (k >= 0) { while (((f = flag[k]) >> 2) != epoch) __nanosleep(20); f &= 3u; }
-                __threadfence();
-                const unsigned pm = __ballot_sync(0xffffffffu, f == 2u);
-                const int first = pm ? __ffs(pm) - 1 : 32;          // nearest predecessor holding an inclusive prefix
-                uint32_t vc = 0; unsigned long long vn = 0;
-                if (k >= 0 && (int)lane <= first) { const size_t src = (size_t)k + (f == 2u ? nblocks : 0u); vc = scnt[src]; vn = snnz[src]; }
-                for (int o = 16; o > 0; o >>= 1) { vc += __shfl_xor_sync(0xffffffffu, vc, o); vn += __shfl_xor_sync(0xffffffffu, vn, o); }
-                cb += vc; nb += vn;
-                if (pm) break;
-                wnd -= 32;
-            }
-        }
-        if (lane == 0) {
-            scnt[nblocks + bid] = cb + ta; snnz[nblocks + bid] = nb + tb; __threadfence(); flag[bid] = (epoch << 2) | 2u;
-            s_cnt_base = cb; s_nnz_base = nb;
+    block_scan2(a, b, ta, tb);      // contains the barriers that publish s_red
+    if (threadIdx.x < 32) {
+        unsigned long long cb = s_red[0][threadIdx.x], nb = s_red[1][threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) { cb += __shfl_xor_sync(0xffffffffu, cb, o); nb += __shfl_xor_sync(0xffffffffu, nb, o); }
+        if (threadIdx.x == 0) {
+            s_cnt_base = (uint32_t)cb; s_nnz_base = nb;
+            p.blk_cnt[(size_t)((epoch & 1u) ^ 1u) * p.blk_stride + bid] = 0ull;     // re-arm the slot the NEXT round's K1 adds into
             if (bid == nblocks - 1) {   // totals, and re-arm the per-round device state
                 const unsigned long long err = p.counts[2 + (epoch & 1u)];   // written by this round's K1 only
                 p.counts[4] = cb + ta; p.counts[5] = nb + tb; p.counts[6] = err;
                 p.counts[2 + ((epoch & 1u) ^ 1u)] = ~0ull;                    // re-arm the slot the NEXT round's K1 uses
                 if (err == ~0ull) { p.counts[0] = cb + ta; p.counts[1] = nb + tb; }
                 p.out_ptr[cb + ta] = (int64_t)(nb + tb);
-                p.ticket[0] = 0u; p.ticket[1] = 0u; p.ticket[2] = 0u;
             }
         }
+        if (bid == nblocks - 1) for (uint32_t i = threadIdx.x; i < KTN_TICKETS; i += 32) p.ticket[i] = 0u;     // K1 is over: re-arm its work tickets
     }
     __syncthreads();
     const uint32_t cbase = s_cnt_base; const unsigned long long nbase = s_nnz_base;
@@ -457,24 +608,41 @@ void ktn_plan_occupancy(uint32_t table_bytes, uint32_t warp_bytes, int max_smem_
     *wpb_out = best_w; *bps_out = best_b;
 }
 
+template <int FAM>
+static void launch_family(KtnRoundParams p, const KtnLaunchPlan& plan, uint32_t ticket_idx, int num_sms, cudaStream_t stream) {
+    const uint32_t begin = plan.fam_begin[FAM], end = plan.fam_begin[FAM + 1];
+    static int bps = 0;     // resident blocks per SM of this instantiation
+    if (!bps) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, ktn_family_kernel<FAM>, KTN_FW_WARPS * 32, 0) != cudaSuccess || bps < 1) bps = 1; }
+    p.chunk_begin = begin; p.chunk_end = end; p.ticket_idx = ticket_idx;
+    for (int k = 0; k <= KTN_FAM_NCLS; ++k) p.cls_begin[k] = plan.cls_begin[FAM][k];
+    uint32_t blocks = (uint32_t)(num_sms * bps);
+    const uint32_t need = (end - begin + KTN_FW_WARPS - 1) / KTN_FW_WARPS;
+    if (blocks > need) blocks = need;
+    ktn_family_kernel<FAM><<<blocks, KTN_FW_WARPS * 32, 0, stream>>>(p);
+}
+
 template <bool EVAL>
-static int launch_eval_part(const KtnRoundParams& p0, uint32_t n_regular, uint32_t n_total, int num_sms, int max_smem_optin,
+static int launch_eval_part(const KtnRoundParams& p0, const KtnLaunchPlan& plan, int num_sms, int max_smem_optin,
                             cudaStream_t stream, cudaError_t* err) {
     int launches = 0;
     KtnRoundParams p = p0;
-    if (n_regular > 0) {
+    if (EVAL) p.mode = KTN_MODE_EVAL;
+    const uint32_t g_begin = plan.fam_begin[KTN_FAM_GENERIC], g_end = plan.fam_begin[KTN_FAM_GENERIC + 1];
+    if (g_end > g_begin) {
         int wpb, bps; ktn_plan_occupancy(p.table_bytes, p.warp_bytes, max_smem_optin, &wpb, &bps);
         const size_t smem = ((p.table_bytes + 127u) & ~127u) + (size_t)wpb * p.warp_bytes;
         uint32_t blocks = (uint32_t)(num_sms * bps);
-        const uint32_t need = (n_regular + wpb - 1) / wpb;
+        const uint32_t need = (g_end - g_begin + wpb - 1) / wpb;
         if (blocks > need) blocks = need;
-        p.chunk_begin = 0; p.chunk_end = n_regular;
+        p.chunk_begin = g_begin; p.chunk_end = g_end; p.ticket_idx = 0;
         ktn_round_kernel<EVAL><<<blocks, wpb * 32, smem, stream>>>(p);
         ++launches;
     }
-    if (n_total > n_regular) {
-        p.chunk_begin = n_regular; p.chunk_end = n_total;
-        uint32_t blocks = (n_total - n_regular + 3) / 4;
+    if (plan.fam_begin[KTN_FAM_LSE + 1] > plan.fam_begin[KTN_FAM_LSE]) { launch_family<KTN_FAM_LSE>(p, plan, KTN_TICKET_LSE, num_sms, stream); ++launches; }
+    if (plan.fam_begin[KTN_FAM_QUAD + 1] > plan.fam_begin[KTN_FAM_QUAD]) { launch_family<KTN_FAM_QUAD>(p, plan, KTN_TICKET_QUAD, num_sms, stream); ++launches; }
+    if (plan.n_total > plan.n_regular) {
+        p.chunk_begin = plan.n_regular; p.chunk_end = plan.n_total;
+        uint32_t blocks = (plan.n_total - plan.n_regular + 3) / 4;
         if (blocks > (uint32_t)num_sms * 8u) blocks = (uint32_t)num_sms * 8u;
         ktn_big_kernel<EVAL><<<blocks, 128, 0, stream>>>(p);
         ++launches;
@@ -483,9 +651,9 @@ static int launch_eval_part(const KtnRoundParams& p0, uint32_t n_regular, uint32
     return launches;
 }
 
-int ktn_launch_round(const KtnRoundParams& p, uint32_t n_regular, uint32_t n_total, int num_sms, int max_smem_optin,
+int ktn_launch_round(const KtnRoundParams& p, const KtnLaunchPlan& plan, int num_sms, int max_smem_optin,
                      uint32_t epoch, cudaStream_t stream, cudaEvent_t after_eval, cudaError_t* err) {
-    int launches = launch_eval_part<false>(p, n_regular, n_total, num_sms, max_smem_optin, stream, err);
+    int launches = launch_eval_part<false>(p, plan, num_sms, max_smem_optin, stream, err);
     if (*err != cudaSuccess) return launches;
     if (after_eval) cudaEventRecord(after_eval, stream);
     const uint32_t nblocks = (uint32_t)((p.num_rows + KTN_CROWS - 1) / KTN_CROWS);
@@ -497,9 +665,9 @@ int ktn_launch_round(const KtnRoundParams& p, uint32_t n_regular, uint32_t n_tot
     return launches;
 }
 
-int ktn_launch_eval(const KtnRoundParams& p, uint32_t n_regular, uint32_t n_total, int num_sms, int max_smem_optin,
+int ktn_launch_eval(const KtnRoundParams& p, const KtnLaunchPlan& plan, int num_sms, int max_smem_optin,
                     cudaStream_t stream, cudaError_t* err) {
-    int launches = launch_eval_part<true>(p, n_regular, n_total, num_sms, max_smem_optin, stream, err);
-    if (*err == cudaSuccess) *err = cudaMemsetAsync(p.ticket, 0, 16, stream);   // the eval path has no K2 to re-arm the tickets
+    int launches = launch_eval_part<true>(p, plan, num_sms, max_smem_optin, stream, err);
+    if (*err == cudaSuccess) *err = cudaMemsetAsync(p.ticket, 0, 4 * KTN_TICKETS, stream);   // the eval path has no K2 to re-arm the tickets
     return launches;
 }

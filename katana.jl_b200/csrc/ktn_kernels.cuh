@@ -5,7 +5,7 @@
 #include <stdint.h>
 #include "ktn_program.h"
 
-enum { KTN_MODE_SEPARATE = 0, KTN_MODE_FORCE = 1 };
+enum { KTN_MODE_SEPARATE = 0, KTN_MODE_FORCE = 1, KTN_MODE_EVAL = 2 };   // EVAL: g only (set by ktn_launch_eval)
 
 struct KtnRoundParams {
     // compiled problem (device)
@@ -35,12 +35,15 @@ struct KtnRoundParams {
     uint32_t* sel;             // 0 = not selected, else nnz | KTN_SEL_ERRBIT
     double* stage_val;         // cut coefficients in the static CSR layout
     double* big_scratch;
-    unsigned int* ticket;      // [0] K1 chunk scheduler, [2] K2 block order
+    unsigned int* ticket;      // KTN_TICKETS dynamic work tickets (interpreter K1: one; family K1: one per class); re-armed by K2
+    uint32_t ticket_idx;       // first ticket this launch draws from
+    uint32_t cls_begin[KTN_FAM_NCLS + 1];   // family launches: chunk range of every class
     // block-shared table of the regular kernel: shape descriptors, then the programs of the regular shapes
     const unsigned char* table; uint32_t table_bytes, table_prog_off;
     uint32_t epoch;                    // round counter (>= 1): look-back flags and error slots are epoch-stamped
-    // compaction (decoupled look-back state per 1024-row block; no per-round reset)
-    uint32_t* st_flag; uint32_t* st_cnt; unsigned long long* st_nnz;
+    // compaction: per block of KTN_CROWS rows, cuts << KTN_BLK_SHIFT | nnz of the selected rows, added by K1 and summed
+    // by K2.  Two copies indexed by epoch parity; K2 zeroes the copy the next round adds into.
+    unsigned long long* blk_cnt; uint32_t blk_stride;
     // [0] n_cuts [1] nnz (both truncated at the first non-finite row) [2],[3] first-error row + 1 of even / odd epochs
     // (~0 = none) [4] n_cuts_total [5] nnz_total [6] first-error row + 1 of the last round
     unsigned long long* counts;
@@ -48,12 +51,16 @@ struct KtnRoundParams {
     double* out_lo; double* out_hi; double* out_g; double* out_viol; double* out_b;
 };
 
+// Chunk ranges of one problem: regular chunks sorted by (family, class), then the BIG chunks.
+struct KtnLaunchPlan { uint32_t fam_begin[KTN_FAM__COUNT + 1]; uint32_t cls_begin[KTN_FAM__COUNT][KTN_FAM_NCLS + 1]; uint32_t n_regular, n_total; };
+enum { KTN_TICKET_GENERIC = 0, KTN_TICKET_LSE = 8, KTN_TICKET_QUAD = 32, KTN_TICKETS = 64 };
+
 // Launches the kernels of one round on `stream`; returns the number of kernels launched.
-int ktn_launch_round(const KtnRoundParams& p, uint32_t n_regular, uint32_t n_total_chunks, int num_sms,
+int ktn_launch_round(const KtnRoundParams& p, const KtnLaunchPlan& plan, int num_sms,
                      int max_smem_optin, uint32_t epoch, cudaStream_t stream, cudaEvent_t after_eval, cudaError_t* err);
 void ktn_plan_occupancy(uint32_t table_bytes, uint32_t warp_bytes, int max_smem_optin, int* warps_per_block, int* blocks_per_sm);
 // forward evaluation only (ktn_eval_g): writes g_row for every row
-int ktn_launch_eval(const KtnRoundParams& p, uint32_t n_regular, uint32_t n_total_chunks, int num_sms,
+int ktn_launch_eval(const KtnRoundParams& p, const KtnLaunchPlan& plan, int num_sms,
                     int max_smem_optin, cudaStream_t stream, cudaError_t* err);
 cudaError_t ktn_kernels_configure(int max_smem_optin);
 

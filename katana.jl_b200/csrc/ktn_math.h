@@ -134,8 +134,11 @@ double ktn_exp_slow(double x) {
 }
 // Fast path for |x| <= 708 (result is a normal number): identical arithmetic, k is read from the low
 // word of (t + SHIFT) and added to the exponent field, which equals the multiplication by 2^k bit for bit.
-KTN_HD double ktn_exp(double x) {
-    if (!(ktn_fabs(x) <= 708.0)) return ktn_exp_slow(x);
+// ktn_exp_fast is branch-free and may be evaluated on ANY input (the result is only meaningful when
+// ktn_exp_is_fast(x)); callers that evaluate several exponentials at once run it unconditionally and
+// patch the rare out-of-range lanes with ktn_exp_slow afterwards: the same value ktn_exp returns.
+KTN_HD int ktn_exp_is_fast(double x) { return ktn_fabs(x) <= 708.0; }
+KTN_HD double ktn_exp_fast(double x) {
     const double SHIFT = 6755399441055744.0;
     double ts = x * KTN_INV_LN2 + SHIFT;
     double kd = ts - SHIFT;
@@ -144,6 +147,10 @@ KTN_HD double ktn_exp(double x) {
     double y = ktn_exp_poly(r);
     int64_t k = (int64_t)(int32_t)(uint32_t)ktn_d2bits(ts);
     return ktn_bits2d(ktn_d2bits(y) + ((uint64_t)k << 52));
+}
+KTN_HD double ktn_exp(double x) {
+    if (!ktn_exp_is_fast(x)) return ktn_exp_slow(x);
+    return ktn_exp_fast(x);
 }
 
 // Taylor tail of 2*atanh(s) = 2s + s*z*P(z), z = s^2, P(z) = sum_{n>=1} 2/(2n+1) z^(n-1), n = 1..11

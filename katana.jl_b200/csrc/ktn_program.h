@@ -93,6 +93,13 @@ enum {
     KTN_FAM__COUNT
 };
 
+// Family chunks are further split into CLASSES by unique-variable count: class k (1 <= k <= KTN_FAM_REGS) = rows of exactly
+// k unique variables, which run a code path specialised for k with the whole row in registers; class 0 = more than that
+// (streaming fallback).  Chunks are sorted by (family, class) so that every class is one contiguous chunk range.
+#define KTN_FAM_REGS 16
+#define KTN_FAM_NCLS (KTN_FAM_REGS + 1)
+static inline uint32_t ktn_family_class(uint32_t n_uniq) { return n_uniq <= KTN_FAM_REGS ? n_uniq : 0u; }
+
 // shape flags
 enum { KTN_SH_NL = 1, KTN_SH_DENSE = 2, KTN_SH_BIG = 4 };
 
@@ -115,15 +122,22 @@ struct KtnShapeDesc {
 
 struct KtnChunkDesc {
     uint64_t blob_off;     // byte offset of the chunk's blob (16-byte aligned)
-    uint64_t scratch_off;  // BIG chunks: offset in doubles into the global scratch arena
+    uint64_t aux;          // BIG chunks: offset in doubles into the global scratch arena; regular chunks: n_uniq of the shape
     uint32_t shape;
     uint32_t blob_bytes;   // multiple of 16
     uint16_t nrows;        // valid lanes
     uint16_t stride;       // lane stride L of the SoA sections (32 for regular chunks)
-    uint32_t row_slot;     // index of the chunk's first lane in chunk_rows[] (= chunk * 32)
+    uint32_t row_slot;     // index of the chunk's first lane in chunk_rows[]; always chunk index * 32
 };
 
 // per-row result flags written by the round kernel
 #define KTN_SEL_ERRBIT 0x40000000u
+
+// Compaction blocks: K1 counts the selected rows of every block of KTN_CROWS consecutive rows
+// (cuts << KTN_BLK_SHIFT | nnz, one 64-bit atomic per warp and block), K2 turns the counts into offsets.
+#define KTN_CROWS_LOG2 12
+#define KTN_CROWS (1 << KTN_CROWS_LOG2)
+#define KTN_BLK_SHIFT 48
+#define KTN_BLK_NNZ_MASK ((1ull << KTN_BLK_SHIFT) - 1ull)
 
 #endif

@@ -10,6 +10,7 @@
 #include "../../include/ktn.h"
 #include "../../katana.jl_b200/csrc/ktn_compile.h"
 #include "../../katana.jl_b200/csrc/ktn_interp.h"
+#include "../../katana.jl_b200/csrc/ktn_family.h"
 
 struct ktn_handle {
     ktn_options opt; KtnProblem prob; bool loaded = false, have_round = false;
@@ -42,6 +43,52 @@ int ktn_jac_structure(ktn_handle* h, int64_t* rp, int32_t* cols) {
     if (cols) memcpy(cols, h->prob.jac_col.data(), 4 * h->prob.jac_col.size()); return 0; }
 }
 
+// family shapes (ktn_family.h): the same row functions the sm_100a family kernel runs, on the same packed chunk
+struct EmuFamRow {
+    const double* C; const int32_t* cols; const uint8_t* rk; const double* X; uint32_t nu, L, lane;
+    double cst(uint32_t i) const { return C[(size_t)i * L + lane]; }
+    int32_t col(uint32_t u) const { return cols[(size_t)u * L + lane]; }
+    double xat(int32_t c) const { return X[c]; }
+    double x(uint32_t u) const { return X[col(u)]; }
+    uint32_t rank(uint32_t u) const { return rk[(size_t)u * L + lane]; }
+};
+struct EmuFamSink {
+    double t[KTN_FAM_REGS]; double* out; const int32_t* scol; const double* X;
+    void put_t(uint32_t q, double v) { t[q] = v; } double get_t(uint32_t q) const { return t[q]; }
+    void put_j(uint32_t q, double v) { out[q] = v; } double get_j(uint32_t q) const { return out[q]; }
+    double xsorted(uint32_t q) const { return X[scol[q]]; }
+};
+template <int FAM, int N>
+static void run_family_row(ktn_handle* h, const KtnChunkDesc& cd, uint32_t lane, int32_t row, const double* x, int mode, bool forced, double lb, double ub, int do_round) {
+    KtnProblem& P = h->prob;
+    const uint32_t L = cd.stride, nu = (uint32_t)cd.aux;
+    const uint8_t* blob = P.blob.data() + cd.blob_off;
+    const EmuFamRow r{(const double*)blob, (const int32_t*)(blob + (size_t)512 * nu), blob + (size_t)640 * nu, x, nu, L, lane};
+    constexpr int NR = N > 0 ? N : 1;
+    KtnFamRegs<NR> v;
+    double aux, g;
+    if constexpr (N > 0) g = ktn_family_forward<FAM, NR>(r, v, aux); else g = KtnFamily<FAM>::forward_stream(r, aux);
+    h->g_row[row] = g;
+    if (mode == 2) return;
+    const bool selected = mode == 1 ? forced : !((g >= lb - h->opt.f_tol) && (g <= ub + h->opt.f_tol));
+    if (!selected) { h->sel[row] = 0; return; }
+    const int64_t base = P.jac_ptr[row];
+    EmuFamSink s{{0}, h->stage_val.data() + base, P.jac_col.data() + base, x};
+    double b; bool bad;
+    if constexpr (N > 0) bad = ktn_family_cut<FAM, NR>(r, v, s, g, aux, do_round != 0, h->opt.cut_coef_rng, b);
+    else bad = ktn_family_cut_stream<FAM>(r, s, g, aux, do_round != 0, h->opt.cut_coef_rng, b);
+    h->b_row[row] = b; h->sel[row] = nu | (bad ? KTN_SEL_ERRBIT : 0u);
+}
+template <int FAM, class... A> static void run_family_dispatch(uint32_t nu, A... a) {
+    switch (ktn_family_class(nu)) {
+#define KTN_CASE(n) case n: run_family_row<FAM, n>(a...); break;
+        KTN_CASE(1) KTN_CASE(2) KTN_CASE(3) KTN_CASE(4) KTN_CASE(5) KTN_CASE(6) KTN_CASE(7) KTN_CASE(8)
+        KTN_CASE(9) KTN_CASE(10) KTN_CASE(11) KTN_CASE(12) KTN_CASE(13) KTN_CASE(14) KTN_CASE(15) KTN_CASE(16)
+#undef KTN_CASE
+        default: run_family_row<FAM, 0>(a...); break;
+    }
+}
+
 static uint32_t ord_at(const uint8_t* ord, uint32_t ob, size_t e) { return ob == 1 ? ord[e] : ob == 2 ? ((const uint16_t*)ord)[e] : ((const uint32_t*)ord)[e]; }
 
 // mode 0 = separate, 1 = force(mask), 2 = eval only
@@ -58,6 +105,14 @@ static void run_chunks(ktn_handle* h, const double* x, int mode, const std::vect
         for (uint32_t lane = 0; lane < cd.nrows; ++lane) {
             const int32_t row = P.chunk_rows[cd.row_slot + lane];
             if (mode == 0 && !(sd.flags & KTN_SH_NL)) { h->sel[row] = 0; continue; }
+            if (sd.family != KTN_FAM_GENERIC) {   // family chunks never take the interpreter (their blob carries rank, not order)
+                const double flb = P.chunk_lb[cd.row_slot + lane], fub = P.chunk_ub[cd.row_slot + lane];
+                if (cd.row_slot != c * 32 || L != 32 || cd.aux != nu) { fprintf(stderr, "emu: family chunk layout violated\n"); abort(); }
+                const bool forced = mode == 1 && force[row] != 0;
+                if (sd.family == KTN_FAM_LSE) run_family_dispatch<KTN_FAM_LSE>(nu, h, cd, lane, row, x, mode, forced, flb, fub, do_round);
+                else run_family_dispatch<KTN_FAM_QUAD>(nu, h, cd, lane, row, x, mode, forced, flb, fub, do_round);
+                continue;
+            }
             for (uint32_t u = 0; u < nu; ++u) S[(size_t)u * L + lane] = x[cols[(size_t)u * L + lane]];
             // aliased shapes write into their constants: work on a private copy of the chunk blob, as the kernel's
             // shared-memory staging does
@@ -146,6 +201,7 @@ int64_t ktn_algorithmic_bytes(ktn_handle* h) { return h->prob.alg_bytes_static +
 // number of shapes / chunks, for tests of the packing
 int64_t ktn_emu_num_shapes(ktn_handle* h) { return (int64_t)h->prob.shapes.size(); }
 int64_t ktn_emu_num_chunks(ktn_handle* h) { return (int64_t)h->prob.chunks.size(); }
+int64_t ktn_emu_num_family_chunks(ktn_handle* h, int32_t fam) { return fam < 0 || fam >= KTN_FAM__COUNT ? -1 : (int64_t)h->prob.fam_begin[fam + 1] - (int64_t)h->prob.fam_begin[fam]; }
 int64_t ktn_emu_num_big_chunks(ktn_handle* h) { return (int64_t)h->prob.chunks.size() - h->prob.n_regular_chunks; }
 int ktn_set_stream(ktn_handle*, void*) { return KTN_ERR_UNSUPPORTED; }
 int ktn_separate_device_async(ktn_handle*, const double*) { return KTN_ERR_UNSUPPORTED; }

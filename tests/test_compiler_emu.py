@@ -51,6 +51,60 @@ def test_synthetic_families_identical(oracle_lib, emu_lib, synth_lib, kind, nv, 
         assert ho.algorithmic_bytes() == he.algorithmic_bytes()
 
 
+def test_family_detection(emu_lib, synth_lib):
+    """The two benchmark forms are recognised as families (interpreter-free kernels); SOC rows stay generic."""
+    import ctypes as C
+    emu_lib.dll.ktn_emu_num_family_chunks.restype = C.c_int64
+    for kind, fam in ((0, 2), (1, 1), (2, 0)):
+        w = synth_lib.synth_rows(kind, 7, 1000, 0, 700)
+        h = emu_lib.create(); h.load(1000, w)
+        nch = emu_lib.dll.ktn_emu_num_chunks(h.h)
+        assert emu_lib.dll.ktn_emu_num_family_chunks(h.h, C.c_int32(fam)) == nch
+    # a row that is not in nlconstr_ixs never takes a family kernel; a 300-term row exceeds the family's 1-byte sort order
+    x = [E.var(j) for j in range(4)]
+    quad = E.sum_([E.const(1.5) * x[j]**2 for j in range(4)] + [E.const(0.5) * x[j] for j in range(4)])
+    w = E.to_wire([quad, quad], [-np.inf] * 2, [1.0] * 2, [ROW_NL, 0])
+    h = emu_lib.create(); h.load(4, w)
+    assert emu_lib.dll.ktn_emu_num_family_chunks(h.h, C.c_int32(2)) == 1 and emu_lib.dll.ktn_emu_num_family_chunks(h.h, C.c_int32(0)) == 1
+
+
+@pytest.mark.parametrize("family", ["lse", "quad"])
+def test_family_rows_edge_values(oracle_lib, emu_lib, family, monkeypatch):
+    """Family fast path == interpreter == oracle on overflow, underflow, NaN / inf points, repeated coefficients,
+    coefficient ranges that make round_coefs zero entries, ragged chunks and every unique-variable count 1..20."""
+    rng = np.random.default_rng(11)
+    nvar = 80
+    exprs = []
+    for nu in list(range(1, 21)) * 3 + [40, 70]:
+        cols = rng.choice(nvar, nu, replace=False)
+        scale = 10.0 ** rng.integers(-12, 12, nu)
+        if family == "lse":
+            exprs.append(E.log(E.sum_([E.exp(E.const(float(rng.uniform(-1, 1) * scale[k])) * E.var(int(cols[k])) + float(rng.uniform(-1, 1))) for k in range(nu)])))
+        else:
+            exprs.append(E.sum_([E.const(float(rng.uniform(0.5, 1.5) * scale[k])) * E.var(int(cols[k]))**2 for k in range(nu)] +
+                                [E.const(float(rng.uniform(-1, 1))) * E.var(int(cols[k])) for k in range(nu)]))
+    m = len(exprs)
+    w = E.to_wire(exprs, np.full(m, -np.inf), np.full(m, -1e300), [ROW_NL] * m)
+    pts = [rng.uniform(-2, 2, nvar), np.zeros(nvar), np.full(nvar, 1e3), np.full(nvar, -1e3), np.full(nvar, 1e200), rng.uniform(-1e-9, 1e-9, nvar)]
+    p = rng.uniform(-2, 2, nvar); p[3] = np.nan; pts.append(p)
+    p = rng.uniform(-2, 2, nvar); p[5] = np.inf; p[7] = -np.inf; pts.append(p)
+    results = []
+    for no_family in ("", "1"):
+        if no_family:
+            monkeypatch.setenv("KTN_NO_FAMILY", "1")
+        ho, he = both(oracle_lib, emu_lib, nvar, w)
+        for rng_coef in (1e9, 10.0):
+            ho.set_params(1e-6, rng_coef, 0); he.set_params(1e-6, rng_coef, 0)
+            for x in pts:
+                assert bits_equal(ho.eval_g(x), he.eval_g(x))
+                bo, be = ho.separate(x), he.separate(x)
+                assert_batches_identical(bo, be, f"{family} no_family={no_family!r} rng={rng_coef}")
+                results.append(bo.n_cuts)
+                sub = np.arange(1, m, 3, dtype=np.int64)                      # forced cuts (loadproblem! / boundroutine path)
+                assert_batches_identical(ho.gencut_rows(x, sub, False), he.gencut_rows(x, sub, False), f"{family} gencut")
+    assert max(results) > 0
+
+
 def test_fused_shapes_use_few_instructions(emu_lib, synth_lib):
     """The benchmark families compile to fused term runs (a handful of instructions per shape)."""
     import ctypes as C
