@@ -187,6 +187,7 @@ static KtnLaunchPlan make_plan(const ktn_handle* h) {
     KtnLaunchPlan pl;
     for (int f = 0; f <= KTN_FAM__COUNT; ++f) pl.fam_begin[f] = h->prob.fam_begin[f];
     memcpy(pl.cls_begin, h->prob.cls_begin, sizeof pl.cls_begin);
+    memcpy(pl.cls_blob_off, h->prob.cls_blob_off, sizeof pl.cls_blob_off); memcpy(pl.cls_blob_stride, h->prob.cls_blob_stride, sizeof pl.cls_blob_stride);
     pl.n_regular = h->prob.n_regular_chunks; pl.n_total = (uint32_t)h->prob.chunks.size();
     return pl;
 }

@@ -501,8 +501,6 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
     }
     for (auto& s : shapes) if (!(s.flags & KTN_SH_BIG)) max_lane_bytes = std::max(max_lane_bytes, ktn_shape_lane_bytes(s));
     chunks.clear(); blob.clear(); chunk_rows.clear(); big_scratch_doubles = 0;
-    std::vector<KtnChunkDesc> big;
-    std::vector<std::vector<int32_t>> big_rows;
     std::vector<std::pair<uint32_t, int32_t>> win;  // (shape, row)
     alg_bytes_static = 8 * num_var;
     for (int64_t i = 0; i < num_constr; ++i) if (flags[i] & KTN_ROW_NL)
@@ -515,7 +513,8 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
         cd.shape = sid; cd.nrows = (uint16_t)nr; cd.stride = (uint16_t)L; cd.aux = s.n_uniq;
         uint64_t off = align_up(blob.size(), 128);
         uint64_t sec_c = 0, sec_col = align_up(sec_c + 8ull * s.n_const * L, 16), sec_ord = align_up(sec_col + 4ull * s.n_uniq * L, 16);
-        uint64_t bytes = align_up(sec_ord + (uint64_t)s.order_bytes * s.n_uniq * L, 16);
+        const bool rankword = s.family != KTN_FAM_GENERIC && s.n_uniq <= KTN_FAM_REGS;      // family rows of <= 16 unique variables: one packed word per row
+        uint64_t bytes = align_up(sec_ord + (rankword ? 8ull * L : (uint64_t)s.order_bytes * s.n_uniq * L), 16);
         cd.blob_off = off; cd.blob_bytes = (uint32_t)bytes;
         blob.resize(off + bytes, 0);
         uint8_t* base = blob.data() + off;
@@ -530,6 +529,7 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
             for (uint32_t u = 0; u < s.n_uniq; ++u) dcol[(uint64_t)u * L + lane] = rcol[u];
             uint8_t* dord = base + sec_ord;
             // family chunks (ktn_family.h) carry the inverse permutation: rank[u] = Jacobian entry index of unique variable u
+            if (rankword) { uint64_t w = 0; for (uint32_t p = 0; p < s.n_uniq; ++p) w |= (uint64_t)p << (4 * rord[p]); ((uint64_t*)dord)[lane] = w; continue; }
             if (s.family != KTN_FAM_GENERIC) { for (uint32_t p = 0; p < s.n_uniq; ++p) dord[(uint64_t)rord[p] * L + lane] = (uint8_t)p; continue; }
             for (uint32_t p = 0; p < s.n_uniq; ++p) {
                 uint64_t e = (uint64_t)p * L + lane;
@@ -541,7 +541,9 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
         return cd;
     };
 
-    std::vector<int32_t> rowbuf;
+    // 1. form the chunks: inside every window of sigma consecutive rows, rows of one shape go together, 32 per chunk
+    struct Pending { uint32_t sid; int32_t nr; uint32_t orig; int32_t rows[32]; };
+    std::vector<Pending> reg, bigp;
     for (int64_t w0 = 0; w0 < num_constr; w0 += sigma) {
         int64_t w1 = std::min(num_constr, w0 + sigma);
         win.clear();
@@ -551,38 +553,43 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
         while (i < win.size()) {
             uint32_t sid = win[i].first; size_t j = i;
             while (j < win.size() && win[j].first == sid) ++j;
-            bool isbig = shapes[sid].flags & KTN_SH_BIG;
+            const bool isbig = shapes[sid].flags & KTN_SH_BIG;
             for (size_t c0 = i; c0 < j; c0 += 32) {
-                int nr = (int)std::min<size_t>(32, j - c0);
-                rowbuf.clear();
-                for (int q = 0; q < nr; ++q) rowbuf.push_back(win[c0 + q].second);
-                KtnChunkDesc cd = pack_chunk(sid, rowbuf.data(), nr, isbig);
-                if (isbig) { big.push_back(cd); big_rows.push_back(rowbuf); }
-                else {
-                    cd.row_slot = (uint32_t)chunk_rows.size();
-                    for (int q = 0; q < 32; ++q) chunk_rows.push_back(q < nr ? rowbuf[q] : -1);
-                    chunks.push_back(cd);
-                }
+                Pending pc; pc.sid = sid; pc.nr = (int32_t)std::min<size_t>(32, j - c0); pc.orig = (uint32_t)(reg.size() + bigp.size());
+                for (int q = 0; q < 32; ++q) pc.rows[q] = q < pc.nr ? win[c0 + q].second : -1;
+                (isbig ? bigp : reg).push_back(pc);
             }
             i = j;
         }
     }
-    // regular chunks grouped by (family, class) (stable: window order is kept inside a class); one K1 launch per family present
+    // 2. regular chunks are ordered by (family, class), window order kept inside a class, and packed in that order: the blobs
+    //    of one family class are contiguous and equally sized, so the family kernel finds a chunk without a descriptor
     {
-        auto key = [&](uint32_t c) { const KtnShapeDesc& s = shapes[chunks[c].shape]; return s.family * (uint32_t)KTN_FAM_NCLS + (s.family != KTN_FAM_GENERIC ? ktn_family_class(s.n_uniq) : 0u); };
-        std::vector<uint32_t> order(chunks.size());
-        for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key(a) < key(b); });
-        std::vector<KtnChunkDesc> sorted(chunks.size());
-        std::vector<int32_t> rows_sorted(chunk_rows.size());
+        auto key = [&](const Pending& pc) { const KtnShapeDesc& s = shapes[pc.sid]; return s.family * (uint32_t)KTN_FAM_NCLS + (s.family != KTN_FAM_GENERIC ? ktn_family_class(s.n_uniq) : 0u); };
+        std::stable_sort(reg.begin(), reg.end(), [&](const Pending& a, const Pending& b) { return key(a) < key(b); });
         std::vector<uint32_t> count((size_t)KTN_FAM__COUNT * KTN_FAM_NCLS + 1, 0u);
-        for (uint32_t i = 0; i < order.size(); ++i) {
-            count[key(order[i])]++;
-            sorted[i] = chunks[order[i]];
-            sorted[i].row_slot = i * 32;
-            for (int q = 0; q < 32; ++q) rows_sorted[i * 32 + q] = chunk_rows[chunks[order[i]].row_slot + q];
+        memset(cls_blob_off, 0, sizeof cls_blob_off); memset(cls_blob_stride, 0, sizeof cls_blob_stride);
+        // KTN_PACK=window (experiment): blobs stay in window order; the family kernel then finds them through the descriptors
+        const bool window_pack = getenv("KTN_PACK") && !strcmp(getenv("KTN_PACK"), "window");
+        std::vector<KtnChunkDesc> packed;
+        if (window_pack) {
+            std::vector<size_t> byorig(reg.size());
+            for (size_t i = 0; i < reg.size(); ++i) byorig[i] = i;
+            std::stable_sort(byorig.begin(), byorig.end(), [&](size_t a, size_t b) { return reg[a].orig < reg[b].orig; });
+            packed.resize(reg.size());
+            for (size_t i : byorig) packed[i] = pack_chunk(reg[i].sid, reg[i].rows, reg[i].nr, false);
         }
-        chunks.swap(sorted); chunk_rows.swap(rows_sorted);
+        for (size_t i = 0; i < reg.size(); ++i) {
+            const Pending& pc = reg[i];
+            KtnChunkDesc cd = window_pack ? packed[i] : pack_chunk(pc.sid, pc.rows, pc.nr, false);
+            cd.row_slot = (uint32_t)chunk_rows.size();
+            for (int q = 0; q < 32; ++q) chunk_rows.push_back(pc.rows[q]);
+            const uint32_t k = key(pc);
+            if (count[k]++ == 0) cls_blob_off[k / KTN_FAM_NCLS][k % KTN_FAM_NCLS] = cd.blob_off;
+            else if (count[k] == 2) cls_blob_stride[k / KTN_FAM_NCLS][k % KTN_FAM_NCLS] = (uint32_t)(cd.blob_off - chunks.back().blob_off);
+            if (window_pack) cls_blob_stride[k / KTN_FAM_NCLS][k % KTN_FAM_NCLS] = 0xffffffffu;
+            chunks.push_back(cd);
+        }
         uint32_t at = 0;
         for (int f = 0; f < KTN_FAM__COUNT; ++f) {
             fam_begin[f] = at;
@@ -592,10 +599,11 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
         fam_begin[KTN_FAM__COUNT] = at;
     }
     n_regular_chunks = (uint32_t)chunks.size();
-    for (size_t c = 0; c < big.size(); ++c) {
-        KtnChunkDesc cd = big[c];
+    for (size_t c = 0; c < bigp.size(); ++c) {
+        const Pending& pc = bigp[c];
+        KtnChunkDesc cd = pack_chunk(pc.sid, pc.rows, pc.nr, true);
         cd.row_slot = (uint32_t)chunk_rows.size();
-        for (int q = 0; q < 32; ++q) chunk_rows.push_back(q < cd.nrows ? big_rows[c][q] : -1);
+        for (int q = 0; q < 32; ++q) chunk_rows.push_back(pc.rows[q]);
         cd.aux = big_scratch_doubles;
         big_scratch_doubles += (uint64_t)shapes[cd.shape].n_scratch * cd.stride;
         chunks.push_back(cd);

@@ -33,6 +33,8 @@ struct KtnProblem {
     uint32_t n_regular_chunks = 0;
     uint32_t fam_begin[KTN_FAM__COUNT + 1] = {0};   // regular chunks of family f: [fam_begin[f], fam_begin[f+1])
     uint32_t cls_begin[KTN_FAM__COUNT][KTN_FAM_NCLS + 1] = {{0}};   // ... of class k inside family f: [cls_begin[f][k], cls_begin[f][k+1])
+    uint64_t cls_blob_off[KTN_FAM__COUNT][KTN_FAM_NCLS] = {{0}};    // blob offset of the first chunk of the class
+    uint32_t cls_blob_stride[KTN_FAM__COUNT][KTN_FAM_NCLS] = {{0}}; // bytes between consecutive chunk blobs of the class (classes >= 1)
     std::vector<uint8_t> blob;
     std::vector<int32_t> chunk_rows;        // chunk * 32 + lane -> row or -1
     std::vector<double> chunk_lb, chunk_ub; // same indexing

@@ -11,7 +11,8 @@
 // Data of one family row (chunk blob, lane stride L):
 //   constants   two per unique variable u (LSE: c_u = slot 2u, d_u = slot 2u+1;  QUAD: a_u = slot u, b_u = slot nu+u)
 //   cols        column of unique variable u (first-occurrence order = the order of the terms)
-//   rank        position of unique variable u among the row's ascending columns = its Jacobian entry index
+//   rank        position of unique variable u among the row's ascending columns = its Jacobian entry index;
+//               nu <= 16: ONE 64-bit word per row, 4 bits per u;  nu > 16: one byte per u
 //
 // Fast path (nu <= KTN_FAM_REGS, one instantiation per nu): the whole row lives in registers.  ktn_family_forward loads every constant
 // and column at once (one memory round trip), gathers x*, evaluates g.  ktn_family_cut builds the cut from the
@@ -29,6 +30,7 @@ template <int FAM> struct KtnFamily;
 // log(sum_u exp(c_u * x_u + d_u))
 // Program: KF_TERMS(EXP_AFF, FIRST); STORE S; LOG | KR_ONE; MULRCP S; STORE R1; KR_TERMS(EXP_AFF); END
 template <> struct KtnFamily<KTN_FAM_LSE> {
+    static const bool KEEP_P1 = true;     // p1 holds exp(c x + d) after the forward pass: kept for the cut
     static KTN_HDM uint32_t slot0(uint32_t u, uint32_t) { return 2 * u; }
     static KTN_HDM uint32_t slot1(uint32_t u, uint32_t) { return 2 * u + 1; }
     static KTN_HDM double arg(double c, double d, double x) { return (0.0 + c * x) + d; }      // LOAD c; MUL x; ADDZ; ADD d
@@ -54,6 +56,7 @@ template <> struct KtnFamily<KTN_FAM_LSE> {
     }
     static KTN_HDM double adjoint(double aux) { return revmul(1.0, 1.0 / aux); }                  // KR_ONE; KR_MULRCP S
     static KTN_HDM double jac(double adj, double c, double e, double) { return 0.0 + revmul(revmul(adj, e), c); }
+    static KTN_HDM double jac_plain(double adj, double c, double e, double) { return 0.0 + (adj * e) * c; }
     // streaming fallback (any nu)
     template <class R> static KTN_HDM double forward_stream(const R& r, double& aux) {
         double acc = 0.0;
@@ -70,6 +73,7 @@ template <> struct KtnFamily<KTN_FAM_LSE> {
 // sum_u a_u * x_u^2 + sum_u b_u * x_u
 // Program: KF_TERMS(MULC_SQ, FIRST); KF_TERMS(MULC_X) | KR_ONE; STORE R1; KR_TERMS(MULC_SQ); KR_TERMS(MULC_X, JACC); END
 template <> struct KtnFamily<KTN_FAM_QUAD> {
+    static const bool KEEP_P1 = false;
     static KTN_HDM uint32_t slot0(uint32_t u, uint32_t) { return u; }
     static KTN_HDM uint32_t slot1(uint32_t u, uint32_t nu) { return nu + u; }
     template <int N> static KTN_HDM double forward(KtnFamRegs<N>& r, double& aux) {
@@ -83,6 +87,7 @@ template <> struct KtnFamily<KTN_FAM_QUAD> {
     }
     static KTN_HDM double adjoint(double) { return 1.0; }                                         // KR_ONE
     static KTN_HDM double jac(double adj, double a, double b, double x) { return (0.0 + revmul(revmul(adj, a), 2.0 * x)) + revmul(adj, b); }
+    static KTN_HDM double jac_plain(double adj, double a, double b, double x) { return (0.0 + (adj * a) * (2.0 * x)) + adj * b; }
     template <class R> static KTN_HDM double forward_stream(const R& r, double& aux) {
         double acc = 0.0;
         for (uint32_t u = 0; u < r.nu; ++u) { const double x = r.x(u); acc = acc + (x * x) * r.cst(u); }
@@ -94,51 +99,88 @@ template <> struct KtnFamily<KTN_FAM_QUAD> {
 };
 
 // ---- register-resident rows -------------------------------------------------------------------------------
-// Row context R: nu, cst(i), col(u), xat(col), rank(u).  All loads of the row are issued before the first use.
+// Row context R: cst(i), col(u), xat(col), rankword() (register-resident rows) / rank(u) (streaming rows).
+// ktn_family_load requests every constant and column id of the row at once (the kernel reads them from the shared-memory
+// slot a bulk copy filled, and gives the slot back right after); ktn_family_eval gathers x* and evaluates g.
 template <int FAM, int N, class R>
-KTN_HDM double ktn_family_forward(const R& r, KtnFamRegs<N>& v, double& aux) {
+KTN_HDM void ktn_family_load(const R& r, KtnFamRegs<N>& v, int32_t (&col)[N]) {
     typedef KtnFamily<FAM> F;
-    int32_t col[N];
 #pragma unroll
     for (int u = 0; u < N; ++u) { v.p0[u] = r.cst(F::slot0(u, N)); v.p1[u] = r.cst(F::slot1(u, N)); col[u] = r.col(u); }
+}
+template <int FAM, int N, class R>
+KTN_HDM double ktn_family_eval(const R& r, KtnFamRegs<N>& v, const int32_t (&col)[N], double& aux) {
 #pragma unroll
     for (int u = 0; u < N; ++u) v.x[u] = r.xat(col[u]);
-    return F::template forward<N>(v, aux);
+    return KtnFamily<FAM>::template forward<N>(v, aux);
 }
 
-// Cut row from the registers ktn_family_forward left behind.  Sink S: t(q) scratch cells (one per Jacobian entry) and the
+KTN_HDM double ktn_dmax(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return fmax(a, b);
+#else
+    return a > b ? a : (b != b ? a : b);
+#endif
+}
+KTN_HDM double ktn_dmin(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return fmin(a, b);
+#else
+    return a < b ? a : (b != b ? a : b);
+#endif
+}
+
+// Cut row from the registers ktn_family_eval left behind.  Sink S: t(q) scratch cells (one per Jacobian entry) and the
 // coefficient row out[0..nu).  Coefficients and the products -x_u * J_u are computed in term order and scattered to
 // their Jacobian entry index; the constant is then accumulated sequentially in entry order, as the reference does
 // (b = g; b += -xstar[col] * partial).  Returns true when a coefficient is not finite.
+//
+// reverse_eval's product rule revmul(a, p) equals a * p whenever a * p is not NaN, and NaN operands stay NaN through the
+// later products, so the coefficients are first formed with plain multiplications (`plain`); only a row in which one of
+// them came out NaN repeats the sweep with the exact rule.  min / max skip NaN (tracked separately).
 template <int FAM, int N, class R, class S>
 KTN_HDM bool ktn_family_cut(const R& r, const KtnFamRegs<N>& v, S& s, double g, double aux, bool do_round, double rng, double& b_out) {
     typedef KtnFamily<FAM> F;
-    const uint32_t nu = N;
     const double adj = F::adjoint(aux);
+    const uint64_t rw = r.rankword();                       // 4 bits per unique variable: its Jacobian entry index
+    double p0[N], p1[N];
+#pragma unroll
+    for (int u = 0; u < N; ++u) { p0[u] = r.cst(F::slot0(u, N)); p1[u] = F::KEEP_P1 ? v.p1[u] : r.cst(F::slot1(u, N)); }   // constants are re-read, not kept
     double mx = -ktn_inf(), mn = ktn_inf();
     bool anynan = false;
 #pragma unroll
     for (int u = 0; u < N; ++u) {
-        const double jv = F::jac(adj, v.p0[u], v.p1[u], v.x[u]);
-        const uint32_t q = r.rank(u);
+        const double jv = F::jac_plain(adj, p0[u], p1[u], v.x[u]);
+        const uint32_t q = (uint32_t)(rw >> (4 * u)) & 15u;
         s.put_t(q, (-v.x[u]) * jv);
         s.put_j(q, jv);
-        mx = jv > mx ? jv : mx; mn = jv < mn ? jv : mn; anynan = anynan || (jv != jv);
+        mx = ktn_dmax(mx, jv); mn = ktn_dmin(mn, jv); anynan = anynan || (jv != jv);
+    }
+    if (anynan) {                                           // rare: repeat the sweep with reverse_eval's exact product rule
+        anynan = false; mx = -ktn_inf(); mn = ktn_inf();
+#pragma unroll
+        for (int u = 0; u < N; ++u) {
+            const double jv = F::jac(adj, p0[u], p1[u], v.x[u]);
+            const uint32_t q = (uint32_t)(rw >> (4 * u)) & 15u;
+            s.put_t(q, (-v.x[u]) * jv);
+            s.put_j(q, jv);
+            mx = ktn_dmax(mx, jv); mn = ktn_dmin(mn, jv); anynan = anynan || (jv != jv);
+        }
     }
     double b = g;
 #pragma unroll
-    for (int q = 0; q < N; ++q) b = b + s.get_t(q);
+    for (int k = 0; k < N; ++k) b = b + s.get_t(k);
     b_out = b;
     // round_coefs zeroes jv when jv + rng < maximum(coefs).  jv + rng is monotone in jv, so when the smallest coefficient
     // passes (and everything is finite) all pass: the exact second sweep only runs for rows that need it.
     bool bad = false;
     if (anynan || !(ktn_fabs(mn) <= KTN_FAM_DMAX) || !(ktn_fabs(mx) <= KTN_FAM_DMAX) || (do_round && (mn + rng < mx))) {
         if (anynan) mx = ktn_nan();     // Julia's maximum() propagates NaN
-        for (uint32_t q = 0; q < nu; ++q) {
-            double jv = s.get_j(q);
-            if (do_round && (jv + rng < mx)) jv = 0.0;
-            bad = bad || !(ktn_fabs(jv) <= KTN_FAM_DMAX);
-            s.put_j(q, jv);
+        for (uint32_t k = 0; k < (uint32_t)N; ++k) {
+            double c = s.get_j(k);
+            if (do_round && (c + rng < mx)) c = 0.0;
+            bad = bad || !(ktn_fabs(c) <= KTN_FAM_DMAX);
+            s.put_j(k, c);
         }
     }
     return bad;

@@ -29,10 +29,19 @@ KTN_HD KtnInsWord ktn_fetch_ins(const KtnIns* p) {
 }
 
 // reverse_eval's product rule: a * p, except a zero adjoint stays zero under a non-finite partial.
-// a * p is NaN in exactly those cases (and when a NaN is genuinely propagated), so only NaN results re-check.
+// a * p is NaN in exactly those cases (and when a NaN is genuinely propagated), so only NaN results re-check; the re-check is
+// an out-of-line call so that the common path is one multiply, one compare and a branch that is never taken.
+KTN_HD_NOINLINE double revmul_nan(double a, double p, double r) { return (a == 0.0 && !ktn_isfinite(p)) ? a : r; }
+#ifndef KTN_OPT_REVMUL_CALL
+#define KTN_OPT_REVMUL_CALL 1
+#endif
 KTN_HD double revmul(double a, double p) {
     double r = a * p;
+#if KTN_OPT_REVMUL_CALL
+    if (r != r) r = revmul_nan(a, p, r);
+#else
     if (r != r) r = (a == 0.0 && !ktn_isfinite(p)) ? a : r;
+#endif
     return r;
 }
 

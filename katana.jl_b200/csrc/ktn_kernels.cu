@@ -68,31 +68,66 @@ __device__ __forceinline__ void count_selected(const KtnRoundParams& p, unsigned
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1f: family shapes (ktn_family.h).  One warp per chunk, one thread per row, dynamic chunk tickets; warps are independent.
-// The whole row is register resident: every constant and column id of the row is requested at once with coalesced loads
-// straight from the chunk blob (lane stride 32; streamed past L1 so that L1 keeps x*), x* is gathered through L1/L2, g is
-// evaluated and tested, and the selected lanes build their cut row from the same registers -- nothing is read twice.
+// K1f: family shapes (ktn_family.h).  Persistent: ONE block of 16 warps per SM; one warp per chunk, one thread per row.
+//   * the block first copies the head of x* (as much as fits beside the scratch, ~25k doubles) into shared memory: the gather
+//     of x* is what saturates an SM's memory port (one 32-byte sector per clock), and L1 cannot help -- its tags cover 128-byte
+//     lines, so random 8-byte gathers fill one sector per line -- while shared memory serves those columns without a request;
+//   * a row is register resident: every constant and column id of the row is requested at once with coalesced loads straight
+//     from the chunk blob (lane stride 32, streamed past L1), x* is gathered, g is evaluated and tested, and the selected lanes
+//     build their cut row from the same registers;
+//   * every class (rows of exactly k unique variables) has its own ticket counter, its own contiguous range of equally sized
+//     blobs (no descriptor to fetch) and its own specialised, fully unrolled code path; the warps of an SM start in the same
+//     class (classes are spread over the SMs in proportion to their work) and move on together, so the instruction working
+//     set is one class, not the whole kernel.
+// (A TMA producer/consumer ring was measured and dropped: bulk-copy traffic in flight delays the dependent x* gathers more
+//  than it hides DRAM latency -- profiles/microbench/mb2.cu.)
 // ---------------------------------------------------------------------------------------------
-#define KTN_FW_WARPS 4
-#define KTN_FW_PASS 8         // selected lanes that build their cut at the same time (scratch cells per Jacobian entry)
+// tuning knobs (scripts/build_variants.sh builds A/B variants of the library with -D overrides)
+#ifndef KTN_OPT_PASS
+#define KTN_OPT_PASS 8
+#endif
+#ifndef KTN_OPT_WARPS
+#define KTN_OPT_WARPS 16
+#endif
+#ifndef KTN_OPT_XCACHE
+#define KTN_OPT_XCACHE 0
+#endif
+#define KTN_FP_WARPS KTN_OPT_WARPS
+#define KTN_FW_PASS KTN_OPT_PASS                          // selected lanes that build their cut at the same time (scratch cells per entry)
+#define KTN_FP_SCRATCH_BYTES (128 + KTN_FP_WARPS * KTN_FAM_REGS * KTN_FW_PASS * 8)   // [0,128): barrier of the x* fill
 
+#ifdef KTN_OPT_TIMING
+// debug build only (scripts/build_variants.sh ... "-DKTN_OPT_TIMING"): per-phase warp cycles, summed over all warps
+__device__ unsigned long long ktn_dbg_cycles[16];
+#define KTN_T(var) const long long var = clock64()
+#define KTN_TADD(i, a, b) do { if ((threadIdx.x & 31u) == 0) atomicAdd(&ktn_dbg_cycles[i], (unsigned long long)((b) - (a))); } while (0)
+#else
+#define KTN_T(var)
+#define KTN_TADD(i, a, b)
+#endif
+
+// read-only streaming loads that do not allocate in L1 (plain asm, not volatile: the compiler may batch and hoist them)
 __device__ __forceinline__ double ldg_stream(const double* p) {
-    double v; asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
+    double v; asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
 }
 __device__ __forceinline__ int32_t ldg_stream(const int32_t* p) {
-    int32_t v; asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+    int32_t v; asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ uint64_t ldg_stream(const uint64_t* p) {
+    uint64_t v; asm("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v;
 }
 __device__ __forceinline__ uint32_t ldg_stream(const uint8_t* p) {
-    uint32_t v; asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+    uint32_t v; asm("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v;
 }
 
-struct FamRow {     // row context of ktn_family.h: SoA sections of one chunk, lane offset applied
-    const double* C; const int32_t* cols; const uint8_t* rk; const double* X; uint32_t nu;
+struct FamRow {     // row context of ktn_family.h: the chunk's SoA sections in global memory, lane offset applied
+    const double* C; const int32_t* cols; const uint8_t* rk; const double* X; const double* sx; int32_t xs; uint32_t nu;
     __device__ __forceinline__ double cst(uint32_t i) const { return ldg_stream(C + i * 32u); }
     __device__ __forceinline__ int32_t col(uint32_t u) const { return ldg_stream(cols + u * 32u); }
-    __device__ __forceinline__ double xat(int32_t c) const { return __ldg(X + c); }
+    __device__ __forceinline__ double xat(int32_t c) const { return (KTN_OPT_XCACHE && c < xs) ? sx[c] : __ldg(X + c); }     // head of x*: shared memory
     __device__ __forceinline__ double x(uint32_t u) const { return xat(col(u)); }
-    __device__ __forceinline__ uint32_t rank(uint32_t u) const { return ldg_stream(rk + u * 32u); }
+    __device__ __forceinline__ uint32_t rank(uint32_t u) const { return ldg_stream(rk + u * 32u); }     // streaming rows: one byte per u
+    __device__ __forceinline__ uint64_t rankword() const { return ldg_stream(reinterpret_cast<const uint64_t*>(rk)); }
 };
 struct FamSink {    // cut-row sink: products in the warp's shared-memory scratch, coefficients in the staging CSR
     double* t; double* out;
@@ -115,27 +150,46 @@ __device__ __forceinline__ void family_finish_row(const KtnRoundParams& p, unsig
     count_selected(p, grp, row, nu);
 }
 
-// N = 1..16: register-resident rows of exactly N unique variables; N = 0: streaming fallback (any count)
+__device__ __forceinline__ const unsigned char* family_blob(const KtnRoundParams& p, uint32_t cls, uint32_t c) {
+    return p.blob + p.cls_blob_off[cls] + (size_t)(c - p.cls_begin[cls]) * p.cls_blob_stride[cls];
+}
+
+// One chunk.  N = 1..16: register-resident rows of exactly N unique variables (class blobs are contiguous and equally sized:
+// no descriptor); N = 0: streaming fallback (any count) through the chunk descriptor.
 template <int FAM, int N>
-__device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c, uint32_t lane, double* scratch) {
+__device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c, uint32_t lane, const double* sx, int32_t xs, double* scratch) {
     typedef KtnFamily<FAM> F;
-    const KtnChunkDesc cd = p.chunks[c];
-    const uint32_t nu = N > 0 ? (uint32_t)N : (uint32_t)cd.aux, slot = c * 32u + lane;
-    const unsigned char* blob = p.blob + cd.blob_off;
-    const FamRow r{reinterpret_cast<const double*>(blob) + lane, reinterpret_cast<const int32_t*>(blob + 512u * nu) + lane, blob + 640u * nu + lane, p.x, nu};
-    const int32_t row = ldg_stream(p.chunk_rows + slot);
-    double lb = 0.0, ub = 0.0;
-    if (p.mode != KTN_MODE_EVAL) { lb = ldg_stream(p.chunk_lb + slot); ub = ldg_stream(p.chunk_ub + slot); }
+    const uint32_t slotid = c * 32u + lane;
+    uint32_t nu = (uint32_t)N;
+    const unsigned char* blob;
+    if (N > 0 && p.cls_blob_stride[N > 0 ? N : 0] != 0xffffffffu) blob = family_blob(p, (uint32_t)N, c);
+    else { const KtnChunkDesc cd = p.chunks[c]; nu = (uint32_t)cd.aux; blob = p.blob + cd.blob_off; }
+    const FamRow r{reinterpret_cast<const double*>(blob) + lane, reinterpret_cast<const int32_t*>(blob + 512u * nu) + lane,
+                   blob + 640u * nu + (N > 0 ? lane * 8u : lane), p.x, sx, xs, nu};
     constexpr int NR = N > 0 ? N : 1;
     KtnFamRegs<NR> v;
     double aux, g;
-    if constexpr (N > 0) g = ktn_family_forward<FAM, NR>(r, v, aux);
-    else g = F::forward_stream(r, aux);
+    KTN_T(t0);
+    if constexpr (N > 0) {
+        int32_t col[NR];
+        ktn_family_load<FAM, NR>(r, v, col);
+        g = ktn_family_eval<FAM, NR>(r, v, col, aux);
+    } else g = F::forward_stream(r, aux);
+    const int32_t row = ldg_stream(p.chunk_rows + slotid);
+    double lb = 0.0, ub = 0.0;
+    if (p.mode != KTN_MODE_EVAL) { lb = ldg_stream(p.chunk_lb + slotid); ub = ldg_stream(p.chunk_ub + slotid); }
+#ifdef KTN_OPT_TIMING
+    asm volatile("" ::"d"(g));
+#endif
+    KTN_T(t1);
     if (row >= 0) p.g_row[row] = g;
     if (p.mode == KTN_MODE_EVAL) return;
     const bool selected = row >= 0 && row_selected(p, g, lb, ub, row);
     if (row >= 0 && !selected) p.sel[row] = 0u;
     unsigned selm = __ballot_sync(0xffffffffu, selected);
+    KTN_T(t2);
+    KTN_TADD(0, t0, t1); KTN_TADD(1, t1, t2);
+    KTN_TADD(4, 0, 1); KTN_TADD(5, 0, __popc(selm)); KTN_TADD(6, 0, (__popc(selm) + KTN_FW_PASS - 1) / KTN_FW_PASS);
     if constexpr (N > 0) {
         while (selm) {      // KTN_FW_PASS selected lanes at a time share the warp's scratch
             const uint32_t cut = __fns(selm, 0, KTN_FW_PASS + 1);
@@ -149,6 +203,8 @@ __device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c
             __syncwarp();
             selm &= ~grp;
         }
+        KTN_T(t3);
+        KTN_TADD(2, t2, t3);
     } else if (selected) {
         const int64_t base = p.jac_ptr[row];
         FamStreamSink s{p.stage_val + base, p.jac_col + base, p.x};
@@ -159,24 +215,40 @@ __device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c
 }
 
 template <int FAM>
-__device__ __forceinline__ void family_dispatch(const KtnRoundParams& p, uint32_t cls, uint32_t c, uint32_t lane, double* scratch) {
+__device__ __forceinline__ void family_dispatch(const KtnRoundParams& p, uint32_t cls, uint32_t c, uint32_t lane, const double* sx, int32_t xs, double* scratch) {
     switch (cls) {
-#define KTN_CASE(n) case n: family_chunk<FAM, n>(p, c, lane, scratch); break;
+#define KTN_CASE(n) case n: family_chunk<FAM, n>(p, c, lane, sx, xs, scratch); break;
         KTN_CASE(1) KTN_CASE(2) KTN_CASE(3) KTN_CASE(4) KTN_CASE(5) KTN_CASE(6) KTN_CASE(7) KTN_CASE(8)
         KTN_CASE(9) KTN_CASE(10) KTN_CASE(11) KTN_CASE(12) KTN_CASE(13) KTN_CASE(14) KTN_CASE(15) KTN_CASE(16)
 #undef KTN_CASE
-        default: family_chunk<FAM, 0>(p, c, lane, scratch); break;
+        default: family_chunk<FAM, 0>(p, c, lane, sx, xs, scratch); break;
     }
 }
 
-// Every class has its own ticket counter.  The warps of one SM start in the same class (classes are spread over the SMs in
-// proportion to their work) and move to the next class when theirs runs dry, so an SM executes ONE specialised code path at
-// a time: the instruction working set stays one class, not the whole kernel.
 template <int FAM>
-__global__ void __launch_bounds__(KTN_FW_WARPS * 32, 16 / KTN_FW_WARPS) ktn_family_kernel(const KtnRoundParams p) {
-    __shared__ double sh_scratch[KTN_FW_WARPS][KTN_FAM_REGS * KTN_FW_PASS];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+__global__ void __launch_bounds__(KTN_FP_WARPS * 32, 1) ktn_family_kernel(const KtnRoundParams p, int32_t xs) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    double* scratch = reinterpret_cast<double*>(smem + 128) + (size_t)(threadIdx.x >> 5) * (KTN_FAM_REGS * KTN_FW_PASS);
+    double* sx = reinterpret_cast<double*>(smem + KTN_FP_SCRATCH_BYTES);
+    const uint32_t lane = threadIdx.x & 31u;
+    if (KTN_OPT_XCACHE && xs > 0) {
+        // head of x* -> shared memory: a handful of TMA bulk copies, one wait
+        uint64_t& xbar = *reinterpret_cast<uint64_t*>(smem);
+        if (threadIdx.x == 0) { mbar_init(&xbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t total = (uint32_t)xs * 8u;
+            mbar_expect(&xbar, total);
+            for (uint32_t off = 0; off < total; off += 32768u) bulk_g2s(reinterpret_cast<unsigned char*>(sx) + off, reinterpret_cast<const unsigned char*>(p.x) + off, total - off < 32768u ? total - off : 32768u, &xbar);
+        }
+        uint32_t done = 0;
+        for (uint32_t spin = 0; !done; ++spin) {
+            asm volatile("{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\nselp.u32 %0, 1, 0, q;\n}" : "=r"(done) : "r"(smem_u32(&xbar)), "r"(0u) : "memory");
+            if (spin > (1u << 24)) __trap();
+        }
+    }
     unsigned int* tickets = p.ticket + p.ticket_idx;
+    const uint32_t my_n = lane < KTN_FAM_NCLS ? p.cls_begin[lane + 1] - p.cls_begin[lane] : 0u;     // lane k: chunks of class k
     uint32_t cls = 0;
     {
         uint32_t smid, nsm;
@@ -190,22 +262,28 @@ __global__ void __launch_bounds__(KTN_FW_WARPS * 32, 16 / KTN_FW_WARPS) ktn_fami
             if (acc > target) { cls = k; break; }
         }
     }
-    auto take = [&](uint32_t k) -> uint32_t {      // next chunk ticket of class k (an empty class costs no atomic)
-        uint32_t t = 0;
-        if (lane == 0 && p.cls_begin[k + 1] > p.cls_begin[k]) t = atomicAdd(&tickets[k], 1u);
-        return t;
-    };
-    uint32_t cur = __shfl_sync(0xffffffffu, take(cls), 0), fails = 0;
+    auto take = [&](uint32_t k) -> uint32_t { uint32_t t = 0; if (lane == 0) t = atomicAdd(&tickets[k], 1u); return t; };
+    auto bcast = [&](uint32_t t) -> uint32_t { return __shfl_sync(0xffffffffu, t, 0); };
+    uint32_t n_cls = p.cls_begin[cls + 1] - p.cls_begin[cls];
+    uint32_t cur = n_cls ? bcast(take(cls)) : 0u;
     for (;;) {
-        while (p.cls_begin[cls] + cur >= p.cls_begin[cls + 1]) {
-            if (++fails == KTN_FAM_NCLS) return;
-            cls = cls + 1 == KTN_FAM_NCLS ? 0u : cls + 1;
-            cur = __shfl_sync(0xffffffffu, take(cls), 0);
+        if (cur >= n_cls) {
+            // this class is dry: one look at every class counter picks the next live class
+            const bool live = lane < KTN_FAM_NCLS && my_n > 0 && __ldcg(&tickets[lane]) < my_n;
+            const unsigned livem = __ballot_sync(0xffffffffu, live);
+            if (!livem) return;
+            const unsigned ahead = livem & ~((2u << cls) - 1u);        // first live class after cls, cyclically
+            cls = (uint32_t)__ffs(ahead ? ahead : livem) - 1u;
+            n_cls = p.cls_begin[cls + 1] - p.cls_begin[cls];
+            cur = bcast(take(cls));
+            continue;
         }
-        fails = 0;
-        const uint32_t nxt = take(cls);            // travels while this chunk computes
-        family_dispatch<FAM>(p, cls, p.cls_begin[cls] + cur, lane, sh_scratch[warp]);
-        cur = __shfl_sync(0xffffffffu, nxt, 0);
+        const uint32_t nxt = take(cls);             // the next ticket travels while this chunk computes
+        family_dispatch<FAM>(p, cls, p.cls_begin[cls] + cur, lane, sx, xs, scratch);
+        KTN_T(tb);
+        cur = bcast(nxt);
+        KTN_T(tc);
+        KTN_TADD(3, tb, tc);
     }
 }
 
@@ -583,6 +661,10 @@ void ktn_launch_pack(const KtnRoundParams& p, unsigned char* sendbuf, int num_sm
 cudaError_t ktn_kernels_configure(int max_smem_optin) {
     cudaError_t e = cudaFuncSetAttribute(ktn_round_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(ktn_round_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
 }
 
@@ -608,17 +690,32 @@ void ktn_plan_occupancy(uint32_t table_bytes, uint32_t warp_bytes, int max_smem_
     *wpb_out = best_w; *bps_out = best_b;
 }
 
+#ifdef KTN_OPT_TIMING
+extern "C" int ktn_debug_cycles(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    if (out16 && cudaMemcpyFromSymbol(out16, ktn_dbg_cycles, sizeof ktn_dbg_cycles) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[16] = {0}; if (cudaMemcpyToSymbol(ktn_dbg_cycles, z, sizeof z) != cudaSuccess) return -1; }
+    return 0;
+}
+#endif
+
 template <int FAM>
-static void launch_family(KtnRoundParams p, const KtnLaunchPlan& plan, uint32_t ticket_idx, int num_sms, cudaStream_t stream) {
+static void launch_family(KtnRoundParams p, const KtnLaunchPlan& plan, uint32_t ticket_idx, int num_sms, int max_smem_optin, cudaStream_t stream) {
     const uint32_t begin = plan.fam_begin[FAM], end = plan.fam_begin[FAM + 1];
-    static int bps = 0;     // resident blocks per SM of this instantiation
-    if (!bps) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, ktn_family_kernel<FAM>, KTN_FW_WARPS * 32, 0) != cudaSuccess || bps < 1) bps = 1; }
     p.chunk_begin = begin; p.chunk_end = end; p.ticket_idx = ticket_idx;
     for (int k = 0; k <= KTN_FAM_NCLS; ++k) p.cls_begin[k] = plan.cls_begin[FAM][k];
-    uint32_t blocks = (uint32_t)(num_sms * bps);
-    const uint32_t need = (end - begin + KTN_FW_WARPS - 1) / KTN_FW_WARPS;
+    for (int k = 0; k < KTN_FAM_NCLS; ++k) { p.cls_blob_off[k] = plan.cls_blob_off[FAM][k]; p.cls_blob_stride[k] = plan.cls_blob_stride[FAM][k]; }
+    uint32_t blocks = (uint32_t)num_sms;                       // persistent: one block per SM
+    const uint32_t need = (end - begin + KTN_FP_WARPS - 1) / KTN_FP_WARPS;
     if (blocks > need) blocks = need;
-    ktn_family_kernel<FAM><<<blocks, KTN_FW_WARPS * 32, 0, stream>>>(p);
+    // shared memory: the warps' scratch, then as much of the head of x* as fits
+    int64_t xs = ((int64_t)max_smem_optin - KTN_FP_SCRATCH_BYTES) / 8;
+    if (!KTN_OPT_XCACHE || xs < 0) xs = 0;
+    if (xs > p.num_var) xs = p.num_var;
+    xs &= ~(int64_t)1;                                         // bulk copies move multiples of 16 bytes
+    if (blocks < (uint32_t)num_sms / 4u) xs = 0;               // tiny launches: filling the cache would cost more than it saves
+    const size_t smem = (size_t)KTN_FP_SCRATCH_BYTES + 8 * (size_t)xs;
+    ktn_family_kernel<FAM><<<blocks, KTN_FP_WARPS * 32, smem, stream>>>(p, (int32_t)xs);
 }
 
 template <bool EVAL>
@@ -638,8 +735,8 @@ static int launch_eval_part(const KtnRoundParams& p0, const KtnLaunchPlan& plan,
         ktn_round_kernel<EVAL><<<blocks, wpb * 32, smem, stream>>>(p);
         ++launches;
     }
-    if (plan.fam_begin[KTN_FAM_LSE + 1] > plan.fam_begin[KTN_FAM_LSE]) { launch_family<KTN_FAM_LSE>(p, plan, KTN_TICKET_LSE, num_sms, stream); ++launches; }
-    if (plan.fam_begin[KTN_FAM_QUAD + 1] > plan.fam_begin[KTN_FAM_QUAD]) { launch_family<KTN_FAM_QUAD>(p, plan, KTN_TICKET_QUAD, num_sms, stream); ++launches; }
+    if (plan.fam_begin[KTN_FAM_LSE + 1] > plan.fam_begin[KTN_FAM_LSE]) { launch_family<KTN_FAM_LSE>(p, plan, KTN_TICKET_LSE, num_sms, max_smem_optin, stream); ++launches; }
+    if (plan.fam_begin[KTN_FAM_QUAD + 1] > plan.fam_begin[KTN_FAM_QUAD]) { launch_family<KTN_FAM_QUAD>(p, plan, KTN_TICKET_QUAD, num_sms, max_smem_optin, stream); ++launches; }
     if (plan.n_total > plan.n_regular) {
         p.chunk_begin = plan.n_regular; p.chunk_end = plan.n_total;
         uint32_t blocks = (plan.n_total - plan.n_regular + 3) / 4;

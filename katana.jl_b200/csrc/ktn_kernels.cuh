@@ -37,7 +37,9 @@ struct KtnRoundParams {
     double* big_scratch;
     unsigned int* ticket;      // KTN_TICKETS dynamic work tickets (interpreter K1: one; family K1: one per class); re-armed by K2
     uint32_t ticket_idx;       // first ticket this launch draws from
-    uint32_t cls_begin[KTN_FAM_NCLS + 1];   // family launches: chunk range of every class
+    uint32_t cls_begin[KTN_FAM_NCLS + 1];   // family launches: chunk range of every class,
+    uint32_t cls_blob_stride[KTN_FAM_NCLS]; // bytes between consecutive chunk blobs of the class,
+    uint64_t cls_blob_off[KTN_FAM_NCLS];    // blob offset of the class's first chunk
     // block-shared table of the regular kernel: shape descriptors, then the programs of the regular shapes
     const unsigned char* table; uint32_t table_bytes, table_prog_off;
     uint32_t epoch;                    // round counter (>= 1): look-back flags and error slots are epoch-stamped
@@ -52,7 +54,11 @@ struct KtnRoundParams {
 };
 
 // Chunk ranges of one problem: regular chunks sorted by (family, class), then the BIG chunks.
-struct KtnLaunchPlan { uint32_t fam_begin[KTN_FAM__COUNT + 1]; uint32_t cls_begin[KTN_FAM__COUNT][KTN_FAM_NCLS + 1]; uint32_t n_regular, n_total; };
+struct KtnLaunchPlan {
+    uint32_t fam_begin[KTN_FAM__COUNT + 1]; uint32_t cls_begin[KTN_FAM__COUNT][KTN_FAM_NCLS + 1];
+    uint64_t cls_blob_off[KTN_FAM__COUNT][KTN_FAM_NCLS]; uint32_t cls_blob_stride[KTN_FAM__COUNT][KTN_FAM_NCLS];
+    uint32_t n_regular, n_total;
+};
 enum { KTN_TICKET_GENERIC = 0, KTN_TICKET_LSE = 8, KTN_TICKET_QUAD = 32, KTN_TICKETS = 64 };
 
 // Launches the kernels of one round on `stream`; returns the number of kernels launched.

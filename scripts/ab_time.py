@@ -1,0 +1,34 @@
+"""A/B timing of library variants: K1 / K2 device times of one separation round per workload.  Run under gpurun:
+python scripts/ab_time.py build/variants/libktn_a.so build/variants/libktn_b.so ..."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from katana_jl_b200.binding import KtnLibrary
+cases = [(1, 100000, 1000000, 0.1, "lse1e6"), (0, 100000, 1000000, 0.1, "qcqp1e6")]
+if os.environ.get("AB_CASES") == "all":
+    cases += [(1, 100000, 1000000, 1.0, "lse1e6"), (1, 100000, 1000000, 0.01, "lse1e6"), (0, 10000, 100000, 0.1, "qcqp1e5"), (2, 100000, 1000000, 0.1, "soc1e6")]
+data = {}
+for path in sys.argv[1:]:
+    P = KtnLibrary(path)
+    out = [os.path.basename(path)]
+    for kind, nv, nr, v, name in cases:
+        if (kind, nv, nr) not in data:
+            data[(kind, nv, nr)] = (P.synth_rows(kind, 20260001 + kind, nv, 0, nr), P.synth_point(kind, 20260001 + kind, nv))
+        w, x0 = data[(kind, nv, nr)]
+        h = P.create(); h.load(nv, w)
+        g = h.eval_g(x0)
+        h.set_bounds(w.lb, np.full(nr, np.quantile(g, 1 - v)))
+        k1, k2 = [], []
+        dbg = getattr(P.dll, "ktn_debug_cycles", None) if hasattr(P.dll, "ktn_debug_cycles") else None
+        import ctypes
+        if dbg: dbg(None, 1)
+        for it in range(12):
+            st, nc, nz, er = h.separate(x0, fetch=False)
+            tm = h.timings(); k1.append(tm["eval_ms"]); k2.append(tm["compact_ms"])
+        out.append(f"{name} v={v}: K1 {1e3 * np.median(k1[2:]):.1f} us (min {1e3 * min(k1):.1f}) K2 {1e3 * np.median(k2[2:]):.1f} us cuts {nc}")
+        if dbg:
+            arr = (ctypes.c_ulonglong * 16)(); dbg(arr, 1); a = [x / 12.0 for x in arr]
+            nch = max(a[4], 1)
+            out.append(f"[per chunk-warp cycles: fwd {a[0]/nch:.0f} sel {a[1]/nch:.0f} cut {a[2]/nch:.0f} ticket(per batch) {a[3]/nch:.0f}; chunks {nch:.0f} selected lanes/chunk {a[5]/nch:.2f} passes/chunk {a[6]/nch:.2f}]")
+        h.close()
+    print(" | ".join(out), flush=True)

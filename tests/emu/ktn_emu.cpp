@@ -51,6 +51,7 @@ struct EmuFamRow {
     double xat(int32_t c) const { return X[c]; }
     double x(uint32_t u) const { return X[col(u)]; }
     uint32_t rank(uint32_t u) const { return rk[(size_t)u * L + lane]; }
+    uint64_t rankword() const { return ((const uint64_t*)rk)[lane]; }
 };
 struct EmuFamSink {
     double t[KTN_FAM_REGS]; double* out; const int32_t* scol; const double* X;
@@ -67,7 +68,7 @@ static void run_family_row(ktn_handle* h, const KtnChunkDesc& cd, uint32_t lane,
     constexpr int NR = N > 0 ? N : 1;
     KtnFamRegs<NR> v;
     double aux, g;
-    if constexpr (N > 0) g = ktn_family_forward<FAM, NR>(r, v, aux); else g = KtnFamily<FAM>::forward_stream(r, aux);
+    if constexpr (N > 0) { int32_t col[NR]; ktn_family_load<FAM, NR>(r, v, col); g = ktn_family_eval<FAM, NR>(r, v, col, aux); } else g = KtnFamily<FAM>::forward_stream(r, aux);
     h->g_row[row] = g;
     if (mode == 2) return;
     const bool selected = mode == 1 ? forced : !((g >= lb - h->opt.f_tol) && (g <= ub + h->opt.f_tol));
