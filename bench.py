@@ -272,12 +272,12 @@ def main():
                    "rows_per_gpu": rows, "num_var": nv, "violated_fraction": args.v, "cuts_per_round_per_gpu": n_cuts, "cut_nnz_per_round_per_gpu": nnz,
                    "l2": f"no flush needed: one round streams {alg_round / 1e6:.0f} MB of inputs > 126 MB L2",
                    "exchange": "none" if world == 1 else "NCCL: sizes allgather + one grouped broadcast per rank of the packed cut blob"},
-        "roofline": {"bound": "hbm", "kernel": "ktn_round_kernel (K1: evaluate, test, reverse sweep, cut rows)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "ktn_family_kernel (K1: evaluate g, test, Jacobian row, cut row; one launch per round)" if args.workload in ("lse", "qcqp") else "ktn_round_kernel (K1, tape interpreter)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_k1, "ms_per_launch": k1_ms,
                      "round": {"algorithmic_bytes": alg_round, "ms": k1_ms + k2_ms, "frac": alg_round / ((k1_ms + k2_ms) * 1e-3) / 1e9 / peak,
                                "k2_compact_ms": k2_ms}},
         "e2e": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": 1e3 * e2e_dt / e2e_steps, "steps": e2e_steps, "call": "KatanaGPUSeparator.separate(xstar) -> CutBatch (ktn_separate + ktn_fetch_cuts)"},
+                "ms_per_step": 1e3 * e2e_dt / e2e_steps, "steps": e2e_steps, "call": "KatanaGPUSeparator.separate(xstar) -> CutBatch (ktn_separate + ktn_fetch_cuts_view: x* from host memory, cuts into the library's pinned buffer)"},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
     }

@@ -151,6 +151,18 @@ int ktn_gencut_rows(ktn_handle* h, const double* x, const int64_t* rows, int64_t
 int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val,
                    double* lo, double* hi, double* g, double* viol, double* bconst);
 
+/* Zero-copy variant of ktn_fetch_cuts: the same nine arrays, delivered as pointers into LIBRARY-OWNED pinned host memory
+ * (one device->host transfer per array, no host-side copy).  Two buffers alternate: a view stays valid until the SECOND
+ * later call of ktn_fetch_cuts_view on the handle, ktn_load_begin or ktn_destroy.  This is the call the batched
+ * addconstr! hand-off of optimize! uses: the cut rows go to the LP solver straight from the view. */
+typedef struct ktn_cut_view {
+    int64_t n_cuts, nnz;
+    const int64_t* row_id; const int64_t* row_ptr;   /* n_cuts, n_cuts + 1 */
+    const int32_t* col; const double* val;           /* nnz */
+    const double* lo; const double* hi; const double* g; const double* viol; const double* bconst;   /* n_cuts */
+} ktn_cut_view;
+int ktn_fetch_cuts_view(ktn_handle* h, ktn_cut_view* out);
+
 /* All constraint values of the last round (sep.g, src/separators.jl:113) -- backs the
  * per-row isconstrsat(sep, i, lb, ub, f_tol) compatibility hook (src/separators.jl:120). */
 int ktn_get_g(ktn_handle* h, double* g_out);

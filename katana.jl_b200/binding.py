@@ -35,6 +35,11 @@ class ktn_timings(C.Structure):
                 ("eval_ms_sum", C.c_double), ("compact_ms_sum", C.c_double), ("rounds_timed", C.c_int64)]
 
 
+class ktn_cut_view(C.Structure):
+    _fields_ = [("n_cuts", C.c_int64), ("nnz", C.c_int64), ("row_id", C.c_void_p), ("row_ptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p),
+                ("lo", C.c_void_p), ("hi", C.c_void_p), ("g", C.c_void_p), ("viol", C.c_void_p), ("bconst", C.c_void_p)]
+
+
 _P = C.c_void_p
 _SIGS = {
     "ktn_create": (C.c_int, [C.POINTER(ktn_options), C.POINTER(_P)]),
@@ -52,6 +57,7 @@ _SIGS = {
     "ktn_separate": (C.c_int, [_P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ktn_gencut_rows": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ktn_fetch_cuts": (C.c_int, [_P] + [_P] * 9),
+    "ktn_fetch_cuts_view": (C.c_int, [_P, C.POINTER(ktn_cut_view)]),
     "ktn_get_g": (C.c_int, [_P, _P]),
     "ktn_eval_g": (C.c_int, [_P, _P, _P]),
     "ktn_timings_get": (C.c_int, [_P, C.POINTER(ktn_timings)]),
@@ -236,13 +242,34 @@ class Handle:
                  "ktn_fetch_cuts")
         return b
 
-    def separate(self, xstar, fetch=True):
+    def _fetch_view(self, status, err):
+        """Zero-copy CutBatch: numpy views of the library's pinned buffer (ktn_fetch_cuts_view).  Valid until the second
+        later view fetch on this handle; copy what must live longer."""
+        v = ktn_cut_view()
+        self._ck(self.dll.ktn_fetch_cuts_view(self.h, C.byref(v)), "ktn_fetch_cuts_view")
+        nc, nz = v.n_cuts, v.nnz
+
+        def arr(ptr, n, ctype, dtype):
+            if n == 0 or not ptr:
+                return np.empty(0, dtype)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,))
+
+        return CutBatch(status, err, arr(v.row_id, nc, C.c_int64, np.int64), arr(v.row_ptr, nc + 1, C.c_int64, np.int64),
+                        arr(v.col, nz, C.c_int32, np.int32), arr(v.val, nz, C.c_double, np.float64), arr(v.lo, nc, C.c_double, np.float64),
+                        arr(v.hi, nc, C.c_double, np.float64), arr(v.g, nc, C.c_double, np.float64), arr(v.viol, nc, C.c_double, np.float64),
+                        arr(v.bconst, nc, C.c_double, np.float64))
+
+    def separate(self, xstar, fetch=True, view=False):
+        """One round at x*.  view=True returns zero-copy views of the library's pinned buffer (the hot path of optimize!);
+        the default copies into fresh arrays."""
         x = np.ascontiguousarray(xstar, np.float64)
         assert len(x) == self.num_var
         nc, nz, er = C.c_int64(), C.c_int64(), C.c_int64()
         st = self._ck(self.dll.ktn_separate(self.h, _ptr(x), C.byref(nc), C.byref(nz), C.byref(er)), "ktn_separate", numeric_ok=True)
         if not fetch:
             return st, nc.value, nz.value, er.value
+        if view:
+            return self._fetch_view(st, er.value)
         return self._fetch(st, nc.value, nz.value, er.value)
 
     def gencut_rows(self, x, rows, round_coefs=False):

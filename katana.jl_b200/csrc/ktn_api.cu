@@ -65,6 +65,7 @@ extern "C" void ktn_destroy(ktn_handle* h) {
     free_problem(h);
     h->ticket.release(); h->counts.release();
     if (h->h_counts) cudaFreeHost(h->h_counts);
+    for (int i = 0; i < 2; ++i) if (h->h_view[i]) cudaFreeHost(h->h_view[i]);
     ktn_comm_release(h);
     if (h->ev0) {
         cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
@@ -138,6 +139,7 @@ extern "C" int ktn_load_end(ktn_handle* h) {
     blob_cap = (blob_cap + 127u) & ~127u;
     h->blob_cap = blob_cap; h->warp_bytes = 128u + blob_cap + ((scratch_cap + 127u) & ~127u);
     const size_t m = (size_t)P.num_constr, N = (size_t)P.jac_ptr[m];
+    if (N > 0xfffffff0ull) return fail(h, KTN_ERR_UNSUPPORTED, "more than 2^32 Jacobian entries on one device: shard the rows over more GPUs");
     CK(h, upload(h->chunks, P.chunks)); CK(h, upload(h->shapes, P.shapes)); CK(h, upload(h->prog, P.prog));
     CK(h, upload(h->blob, P.blob)); CK(h, upload(h->chunk_rows, P.chunk_rows));
     CK(h, upload(h->chunk_lb, P.chunk_lb)); CK(h, upload(h->chunk_ub, P.chunk_ub));
@@ -151,7 +153,7 @@ extern "C" int ktn_load_end(ktn_handle* h) {
     CK(h, h->blk_cnt.alloc(16 * (size_t)h->blk_stride));
     CK(h, cudaMemset(h->blk_cnt.p, 0, 16 * (size_t)h->blk_stride));
     CK(h, upload(h->table, table));
-    CK(h, h->out_row.alloc(4 * (m + 1))); CK(h, h->out_ptr.alloc(8 * (m + 2))); CK(h, h->out_col.alloc(4 * (N + 1))); CK(h, h->out_val.alloc(8 * (N + 1)));
+    CK(h, h->out_row.alloc(8 * (m + 1))); CK(h, h->out_ptr.alloc(8 * (m + 2))); CK(h, h->out_col.alloc(4 * (N + 1))); CK(h, h->out_val.alloc(8 * (N + 1)));
     CK(h, h->out_lo.alloc(8 * (m + 1))); CK(h, h->out_hi.alloc(8 * (m + 1))); CK(h, h->out_g.alloc(8 * (m + 1))); CK(h, h->out_viol.alloc(8 * (m + 1))); CK(h, h->out_b.alloc(8 * (m + 1)));
     CK(h, cudaMallocHost(&h->h_x, 8 * ((size_t)P.num_var + 1)));
     // the packed blob lives on the device now
@@ -209,7 +211,7 @@ KtnRoundParams ktn_make_params(ktn_handle* h, const double* d_x, int mode, int d
     p.counts = h->counts.as<unsigned long long>();
     p.row_offset = h->row_offset;
     p.table = h->table.as<unsigned char>(); p.table_bytes = h->table_bytes; p.table_prog_off = h->table_prog_off; p.epoch = h->epoch;
-    p.out_row = h->out_row.as<int32_t>(); p.out_ptr = h->out_ptr.as<int64_t>(); p.out_col = h->out_col.as<int32_t>(); p.out_val = h->out_val.as<double>();
+    p.out_row = h->out_row.as<int64_t>(); p.out_ptr = h->out_ptr.as<int64_t>(); p.out_col = h->out_col.as<int32_t>(); p.out_val = h->out_val.as<double>();
     p.out_lo = h->out_lo.as<double>(); p.out_hi = h->out_hi.as<double>(); p.out_g = h->out_g.as<double>(); p.out_viol = h->out_viol.as<double>(); p.out_b = h->out_b.as<double>();
     return p;
 }
@@ -301,12 +303,7 @@ extern "C" int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, 
     cudaSetDevice(h->device);
     const size_t nc = (size_t)h->n_cuts, nz = (size_t)h->nnz_cuts;
     CK(h, cudaEventRecord(h->ev2, h->stream));
-    if (row_id && nc) {
-        std::vector<int32_t> tmp(nc);
-        CK(h, cudaMemcpyAsync(tmp.data(), h->out_row.p, 4 * nc, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaStreamSynchronize(h->stream));
-        for (size_t i = 0; i < nc; ++i) row_id[i] = tmp[i] + h->row_offset;
-    }
+    if (row_id && nc) CK(h, cudaMemcpyAsync(row_id, h->out_row.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
     if (row_ptr) { if (nc) CK(h, cudaMemcpyAsync(row_ptr, h->out_ptr.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream)); }
     if (col && nz) CK(h, cudaMemcpyAsync(col, h->out_col.p, 4 * nz, cudaMemcpyDeviceToHost, h->stream));
     if (val && nz) CK(h, cudaMemcpyAsync(val, h->out_val.p, 8 * nz, cudaMemcpyDeviceToHost, h->stream));
@@ -319,6 +316,50 @@ extern "C" int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, 
     CK(h, cudaStreamSynchronize(h->stream));
     if (row_ptr) row_ptr[nc] = (int64_t)nz;   // the device array ends at the untruncated total
     float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev2, h->ev3) == cudaSuccess) h->tm.d2h_ms = ms;
+    return KTN_OK;
+}
+
+// Zero-copy download: nine device->pinned copies into ONE library-owned buffer (two buffers alternate, so a view stays
+// valid until the round after the next one), one synchronisation, no host-side copy.
+extern "C" int ktn_fetch_cuts_view(ktn_handle* h, ktn_cut_view* out) {
+    if (!h || !h->loaded || !out) return fail(h, KTN_ERR_USAGE, "no problem loaded");
+    if (h->round_pending) { int rc = finish_round(h, nullptr, nullptr, nullptr); if (rc < 0) return rc; }
+    cudaSetDevice(h->device);
+    const size_t nc = (size_t)h->n_cuts, nz = (size_t)h->nnz_cuts;
+    const KtnPackLayout L = ktn_pack_layout(nc, nz);
+    h->view_cur ^= 1;
+    unsigned char*& buf = h->h_view[h->view_cur]; size_t& cap = h->h_view_cap[h->view_cur];
+    if (cap < L.total) {
+        if (buf) cudaFreeHost(buf);
+        buf = nullptr; cap = 0;
+        const size_t want = L.total + L.total / 4 + 4096;
+        CK(h, cudaMallocHost(&buf, want));
+        cap = want;
+    }
+    CK(h, cudaEventRecord(h->ev2, h->stream));
+    if (nc) {
+        CK(h, cudaMemcpyAsync(buf + L.row_id, h->out_row.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(buf + L.row_ptr, h->out_ptr.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(buf + L.lo, h->out_lo.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(buf + L.hi, h->out_hi.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(buf + L.g, h->out_g.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(buf + L.viol, h->out_viol.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(buf + L.b, h->out_b.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (nz) {
+        CK(h, cudaMemcpyAsync(buf + L.col, h->out_col.p, 4 * nz, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(buf + L.val, h->out_val.p, 8 * nz, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(h, cudaEventRecord(h->ev3, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    reinterpret_cast<int64_t*>(buf + L.row_ptr)[nc] = (int64_t)nz;   // the device array ends at the untruncated total
+    float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev2, h->ev3) == cudaSuccess) h->tm.d2h_ms = ms;
+    out->n_cuts = (int64_t)nc; out->nnz = (int64_t)nz;
+    out->row_id = reinterpret_cast<const int64_t*>(buf + L.row_id); out->row_ptr = reinterpret_cast<const int64_t*>(buf + L.row_ptr);
+    out->col = reinterpret_cast<const int32_t*>(buf + L.col); out->val = reinterpret_cast<const double*>(buf + L.val);
+    out->lo = reinterpret_cast<const double*>(buf + L.lo); out->hi = reinterpret_cast<const double*>(buf + L.hi);
+    out->g = reinterpret_cast<const double*>(buf + L.g); out->viol = reinterpret_cast<const double*>(buf + L.viol);
+    out->bconst = reinterpret_cast<const double*>(buf + L.b);
     return KTN_OK;
 }
 

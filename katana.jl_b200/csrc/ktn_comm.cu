@@ -140,9 +140,9 @@ extern "C" int ktn_fetch_gathered(ktn_handle* h, int64_t* row_id, int64_t* row_p
     for (int r = 0; r < h->nranks; ++r) {
         const unsigned char* b = host.data() + h->g_off[r];
         const unsigned long long* hd = reinterpret_cast<const unsigned long long*>(b);
-        const int64_t n = (int64_t)hd[0], nz = (int64_t)hd[1], base = (int64_t)hd[4];
+        const int64_t n = (int64_t)hd[0], nz = (int64_t)hd[1];
         const KtnPackLayout L = ktn_pack_layout(n, nz);
-        if (row_id) { const int32_t* s = reinterpret_cast<const int32_t*>(b + L.row_id); for (int64_t i = 0; i < n; ++i) row_id[co + i] = s[i] + base; }
+        if (row_id) memcpy(row_id + co, b + L.row_id, 8 * (size_t)n);     // global ids: K2 applied the rank's row offset
         if (row_ptr) { const int64_t* s = reinterpret_cast<const int64_t*>(b + L.row_ptr); for (int64_t i = 0; i < n; ++i) row_ptr[co + i + 1] = s[i + 1] + zo; }
         if (lo) memcpy(lo + co, b + L.lo, 8 * (size_t)n);
         if (hi) memcpy(hi + co, b + L.hi, 8 * (size_t)n);

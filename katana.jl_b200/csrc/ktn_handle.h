@@ -37,6 +37,7 @@ struct ktn_handle {
     double* h_x = nullptr;                 // pinned
     unsigned long long* h_counts = nullptr;  // pinned [8]
     int64_t n_cuts = 0, nnz_cuts = 0, err_row = -1;
+    unsigned char* h_view[2] = {nullptr, nullptr}; size_t h_view_cap[2] = {0, 0}; int view_cur = 0;   // pinned buffers behind ktn_fetch_cuts_view
     uint32_t warp_bytes = 0, blob_cap = 0, table_bytes = 0, table_prog_off = 0, epoch = 0, blk_stride = 0;
     ktn_timings tm;
     std::string err;

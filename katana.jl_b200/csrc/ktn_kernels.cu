@@ -565,10 +565,15 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
     __shared__ uint32_t s_cnt_base; __shared__ unsigned long long s_nnz_base;
     __shared__ unsigned long long s_red[2][32];
     __shared__ uint32_t s_off[KTN_CROWS + 1];        // exclusive nnz offsets of the block's selected rows (compact list)
+    __shared__ uint32_t s_src[KTN_CROWS];            // first staging entry of each selected row (jac_ptr; the library caps nnz(J) at 2^32 - 1)
     __shared__ uint16_t s_rowl[KTN_CROWS];           // block-local row index of each selected row
     const uint32_t bid = blockIdx.x;
     const int64_t row0 = (int64_t)bid * KTN_CROWS, i0 = row0 + (int64_t)threadIdx.x * KTN_CRPT;
-    // output offset of this block = cuts / nnz of all blocks before it, from K1's per-block counts
+    // every independent load of the block is requested up front: the row flags, then K1's per-block counts
+    uint32_t sv[KTN_CRPT];
+    if (i0 + KTN_CRPT <= p.num_rows) { const uint4 q = *reinterpret_cast<const uint4*>(p.sel + i0); sv[0] = q.x; sv[1] = q.y; sv[2] = q.z; sv[3] = q.w; }
+    else for (int r = 0; r < KTN_CRPT; ++r) sv[r] = (i0 + r < p.num_rows) ? p.sel[i0 + r] : 0u;
+    // output offset of this block = cuts / nnz of all blocks before it
     unsigned long long* bc = p.blk_cnt + (size_t)(epoch & 1u) * p.blk_stride;
     {
         unsigned long long cb = 0, nb = 0;
@@ -576,10 +581,8 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
         for (int o = 16; o > 0; o >>= 1) { cb += __shfl_xor_sync(0xffffffffu, cb, o); nb += __shfl_xor_sync(0xffffffffu, nb, o); }
         if ((threadIdx.x & 31u) == 0) { s_red[0][threadIdx.x >> 5] = cb; s_red[1][threadIdx.x >> 5] = nb; }
     }
-    uint32_t sv[KTN_CRPT];
-    if (i0 + KTN_CRPT <= p.num_rows) { const uint4 q = *reinterpret_cast<const uint4*>(p.sel + i0); sv[0] = q.x; sv[1] = q.y; sv[2] = q.z; sv[3] = q.w; }
-    else for (int r = 0; r < KTN_CRPT; ++r) sv[r] = (i0 + r < p.num_rows) ? p.sel[i0 + r] : 0u;
     uint32_t a = 0; unsigned long long b = 0;
+#pragma unroll
     for (int r = 0; r < KTN_CRPT; ++r) { a += sv[r] ? 1u : 0u; b += sv[r] & ~KTN_SEL_ERRBIT; }
     uint32_t ta; unsigned long long tb;
     block_scan2(a, b, ta, tb);      // contains the barriers that publish s_red
@@ -601,31 +604,48 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
     }
     __syncthreads();
     const uint32_t cbase = s_cnt_base; const unsigned long long nbase = s_nnz_base;
+    // compact list of the block's selected rows: local row index (bit 15: non-finite flag) and nnz offset
+#pragma unroll
     for (int r = 0; r < KTN_CRPT; ++r) {
         const uint32_t s = sv[r];
         if (!s) continue;
-        const int64_t i = i0 + r;
-        const int64_t cidx = (int64_t)cbase + a, o = (int64_t)(nbase + b);
-        s_off[a] = (uint32_t)b; s_rowl[a] = (uint16_t)(threadIdx.x * KTN_CRPT + r);
-        const double g = p.g_row[i], bc = p.b_row[i], lb = p.row_lb[i], ub = p.row_ub[i];
-        p.out_row[cidx] = (int32_t)i; p.out_ptr[cidx] = o;
-        p.out_lo[cidx] = lb - bc; p.out_hi[cidx] = ub - bc;     // src/model.jl:74-75
-        p.out_g[cidx] = g; p.out_b[cidx] = bc;
-        const double v1 = lb - g, v2 = g - ub;
-        p.out_viol[cidx] = (g == g) ? (v1 > v2 ? v1 : v2) : g;
-        // the reference stops at the first non-finite cut (src/model.jl:278): cuts before it stand
-        if ((s & KTN_SEL_ERRBIT) && (unsigned long long)i + 1ull == p.counts[2 + (epoch & 1u)]) { p.counts[0] = (unsigned long long)cidx; p.counts[1] = (unsigned long long)o; }
+        s_off[a] = (uint32_t)b; s_rowl[a] = (uint16_t)((threadIdx.x * KTN_CRPT + r) | ((s & KTN_SEL_ERRBIT) ? 0x8000u : 0u));
         a += 1u; b += s & ~KTN_SEL_ERRBIT;
     }
     if (threadIdx.x == 0) s_off[ta] = (uint32_t)tb;
     __syncthreads();
-    // expand: one thread per output entry, coalesced writes; the owning row is found by binary search
-    for (unsigned long long e = threadIdx.x; e < tb; e += KTN_CBLOCK) {
-        uint32_t lo = 0, hi = ta;   // largest k with s_off[k] <= e
-        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= e) lo = mid; else hi = mid; }
-        const int64_t src = p.jac_ptr[row0 + s_rowl[lo]] + (int64_t)(e - s_off[lo]);
-        p.out_col[nbase + e] = p.jac_col[src];
-        p.out_val[nbase + e] = p.stage_val[src];
+    // one thread per SELECTED row: its five scalars are independent loads, its outputs are coalesced
+    for (uint32_t k = threadIdx.x; k < ta; k += KTN_CBLOCK) {
+        const uint32_t rl = s_rowl[k];
+        const int64_t i = row0 + (rl & 0x7fffu);
+        const double g = p.g_row[i], bcst = p.b_row[i], lb = p.row_lb[i], ub = p.row_ub[i];
+        s_src[k] = (uint32_t)p.jac_ptr[i];
+        const int64_t cidx = (int64_t)cbase + k, o = (int64_t)(nbase + s_off[k]);
+        p.out_row[cidx] = i + p.row_offset; p.out_ptr[cidx] = o;
+        p.out_lo[cidx] = lb - bcst; p.out_hi[cidx] = ub - bcst;     // src/model.jl:74-75
+        p.out_g[cidx] = g; p.out_b[cidx] = bcst;
+        const double v1 = lb - g, v2 = g - ub;
+        p.out_viol[cidx] = (g == g) ? (v1 > v2 ? v1 : v2) : g;
+        // the reference stops at the first non-finite cut (src/model.jl:278): cuts before it stand
+        if ((rl & 0x8000u) && (unsigned long long)i + 1ull == p.counts[2 + (epoch & 1u)]) { p.counts[0] = (unsigned long long)cidx; p.counts[1] = (unsigned long long)o; }
+    }
+    __syncthreads();
+    // expand: one thread per output entry, coalesced writes; the owning row is found by binary search in shared memory.
+    // Four entries per thread and step: all eight loads are in flight before the first store.
+    const uint32_t nent = (uint32_t)tb;
+    for (uint32_t e0 = threadIdx.x; e0 < nent; e0 += 4u * KTN_CBLOCK) {
+        uint32_t src[4]; int32_t cv[4]; double vv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t e = e0 + (uint32_t)k * KTN_CBLOCK;
+            uint32_t lo = 0, hi = ta;   // largest k with s_off[k] <= e
+            if (e < nent) { while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= e) lo = mid; else hi = mid; } }
+            src[k] = e < nent ? s_src[lo] + (e - s_off[lo]) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { cv[k] = src[k] != 0xffffffffu ? p.jac_col[src[k]] : 0; vv[k] = src[k] != 0xffffffffu ? p.stage_val[src[k]] : 0.0; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (src[k] != 0xffffffffu) { const unsigned long long e = nbase + e0 + (uint32_t)k * KTN_CBLOCK; p.out_col[e] = cv[k]; p.out_val[e] = vv[k]; }
     }
 }
 

@@ -49,7 +49,7 @@ struct KtnRoundParams {
     // [0] n_cuts [1] nnz (both truncated at the first non-finite row) [2],[3] first-error row + 1 of even / odd epochs
     // (~0 = none) [4] n_cuts_total [5] nnz_total [6] first-error row + 1 of the last round
     unsigned long long* counts;
-    int32_t* out_row; int64_t* out_ptr; int32_t* out_col; double* out_val;
+    int64_t* out_row; int64_t* out_ptr; int32_t* out_col; double* out_val;     // out_row: GLOBAL row ids (row_offset applied)
     double* out_lo; double* out_hi; double* out_g; double* out_viol; double* out_b;
 };
 
@@ -77,7 +77,7 @@ __host__ __device__
 #endif
 inline KtnPackLayout ktn_pack_layout(unsigned long long n, unsigned long long nz) {
     KtnPackLayout L; unsigned long long o = 64;
-    L.row_id = o; o = (o + 4 * n + 15) & ~15ull;
+    L.row_id = o; o = (o + 8 * n + 15) & ~15ull;
     L.row_ptr = o; o = (o + 8 * (n + 1) + 15) & ~15ull;
     L.lo = o; o = (o + 8 * n + 15) & ~15ull;
     L.hi = o; o = (o + 8 * n + 15) & ~15ull;

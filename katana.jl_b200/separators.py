@@ -78,7 +78,8 @@ class KatanaGPUSeparator(AbstractKatanaSeparator):
     # precompute!(sep, xstar) -- src/separators.jl:111-116
     def precompute(self, xstar):
         self.xstar = np.asarray(xstar, np.float64)
-        self.last = self.handle.separate(self.xstar)
+        # zero-copy views of the library's pinned cut buffer: optimize! hands the rows to the LP before the next round
+        self.last = self.handle.separate(self.xstar, view=True)
         self.g = None
 
     def separate(self, xstar):

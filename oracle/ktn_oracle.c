@@ -422,6 +422,13 @@ int ktn_gencut_rows(ktn_handle* h, const double* x, const int64_t* rows, int64_t
     return status;
 }
 
+int ktn_fetch_cuts_view(ktn_handle* h, ktn_cut_view* out) {
+    if (!h || !out) return KTN_ERR_USAGE;
+    out->n_cuts = h->n_cuts; out->nnz = h->nnz_cuts;
+    out->row_id = h->c_row; out->row_ptr = h->c_ptr; out->col = h->c_col; out->val = h->c_val;
+    out->lo = h->c_lo; out->hi = h->c_hi; out->g = h->c_g; out->viol = h->c_viol; out->bconst = h->c_b;
+    return KTN_OK;
+}
 int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val,
                    double* lo, double* hi, double* g, double* viol, double* bconst) {
     if (!h) return KTN_ERR_USAGE;

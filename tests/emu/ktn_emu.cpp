@@ -195,6 +195,9 @@ int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* co
     if (viol && nc) memcpy(viol, h->c_viol.data(), 8 * nc);
     if (bconst && nc) memcpy(bconst, h->c_b.data(), 8 * nc);
     return 0; }
+int ktn_fetch_cuts_view(ktn_handle* h, ktn_cut_view* v) {
+    v->n_cuts = (int64_t)h->c_row.size(); v->nnz = (int64_t)h->c_col.size(); v->row_id = h->c_row.data(); v->row_ptr = h->c_ptr.data(); v->col = h->c_col.data(); v->val = h->c_val.data();
+    v->lo = h->c_lo.data(); v->hi = h->c_hi.data(); v->g = h->c_g.data(); v->viol = h->c_viol.data(); v->bconst = h->c_b.data(); return 0; }
 int ktn_get_g(ktn_handle* h, double* g) { memcpy(g, h->g_row.data(), 8 * h->g_row.size()); return 0; }
 int ktn_eval_g(ktn_handle* h, const double* x, double* g) { run_chunks(h, x, 2, {}, 0); memcpy(g, h->g_row.data(), 8 * h->g_row.size()); return 0; }
 int ktn_timings_get(ktn_handle*, ktn_timings* t) { memset(t, 0, sizeof *t); return 0; }

@@ -156,6 +156,23 @@ def test_baseline_size_round(oracle_lib, cuda_lib, kind, name):
     assert_batches_identical(ho.separate(x0), b1, name)
 
 
+def test_zero_copy_view_matches_copy(oracle_lib, cuda_lib):
+    """ktn_fetch_cuts_view (pinned, library-owned, double-buffered) delivers the same arrays as ktn_fetch_cuts."""
+    nv, nr = 3000, 40000
+    w = cuda_lib.synth_rows(1, 9, nv, 0, nr); x0 = cuda_lib.synth_point(1, 9, nv)
+    ho, hc = both(oracle_lib, cuda_lib, nv, w)
+    g = ho.eval_g(x0)
+    ub = np.full(nr, np.quantile(g, 0.8)); ho.set_bounds(w.lb, ub); hc.set_bounds(w.lb, ub)
+    ref = ho.separate(x0)
+    v1 = hc.separate(x0, view=True)
+    assert_batches_identical(ref, v1, "view")
+    v2 = hc.separate(0.5 * x0, view=True)              # the previous view survives one more fetch (two buffers alternate)
+    assert_batches_identical(ref, v1, "view after the next round")
+    assert_batches_identical(ho.separate(0.5 * x0), v2, "second view")
+    ub0 = np.full(nr, g.max() + 1.0); hc.set_bounds(w.lb, ub0)
+    assert hc.separate(x0, view=True).n_cuts == 0      # empty batch
+
+
 def test_device_resident_round_and_counters(cuda_lib):
     import torch
     nv, nr = 2000, 50000
