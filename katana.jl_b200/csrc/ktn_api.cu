@@ -11,6 +11,7 @@
 #include "ktn_handle.h"
 
 void ktn_comm_release(ktn_handle* h);
+int ktn_comm_launch_pending(ktn_handle* h);
 
 extern "C" const char* ktn_backend(void) { return "cuda"; }
 extern "C" const char* ktn_last_error(ktn_handle* h) { return h ? h->err.c_str() : "null handle"; }
@@ -230,6 +231,7 @@ static void drain_ring(ktn_handle* h, bool all) {
 }
 
 static int enqueue_round(ktn_handle* h, const double* d_x, int mode, int do_round) {
+    { int rc = ktn_comm_launch_pending(h); if (rc) return rc; }       // sharded runs: the previous round's cut payload travels beside this round
     h->epoch = (h->epoch % 0x3ffffff0u) + 1u;
     KtnRoundParams p = ktn_make_params(h, d_x, mode, do_round);
     cudaError_t e = cudaSuccess;

@@ -42,10 +42,16 @@ bool load_nccl(std::string* why) {
 #define NK(h, call) do { ncclResult_t r__ = (call); if (r__ != 0) return fail(h, KTN_ERR_NCCL, "%s failed: %s", #call, N.GetErrorString(r__)); } while (0)
 
 void ktn_comm_release(ktn_handle* h) {
+    if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
     if (h->comm && N.ok) N.CommDestroy((ncclComm_t)h->comm);
     h->comm = nullptr;
-    h->sendbuf.release(); h->gathered.release(); h->all_counts.release();
-    if (h->h_all_counts) { cudaFreeHost(h->h_all_counts); h->h_all_counts = nullptr; }
+    for (auto& x : h->xch) {
+        x.sendbuf.release(); x.gathered.release(); x.all_counts.release();
+        if (x.h_all_counts) { cudaFreeHost(x.h_all_counts); x.h_all_counts = nullptr; }
+        if (x.packed) { cudaEventDestroy(x.packed); cudaEventDestroy(x.sizes); cudaEventDestroy(x.done); x.packed = x.sizes = x.done = nullptr; }
+        x.state = 0;
+    }
+    if (h->comm_stream) { cudaStreamDestroy(h->comm_stream); h->comm_stream = nullptr; }
 }
 
 extern "C" int ktn_comm_unique_id(void* id128) {
@@ -66,9 +72,15 @@ extern "C" int ktn_comm_init(ktn_handle* h, int32_t nranks, int32_t rank, const 
     ncclComm_t c = nullptr;
     NK(h, N.CommInitRank(&c, nranks, id, rank));
     h->comm = c; h->nranks = nranks; h->rank = rank;
-    CK(h, h->all_counts.alloc(16 * (size_t)nranks + 64));
-    CK(h, cudaMallocHost(&h->h_all_counts, 16 * (size_t)nranks + 64));
-    h->g_cuts.assign(nranks, 0); h->g_nnz.assign(nranks, 0); h->g_off.assign(nranks + 1, 0);
+    CK(h, cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    for (auto& x : h->xch) {
+        CK(h, x.all_counts.alloc(16 * (size_t)nranks + 64));
+        CK(h, cudaMallocHost(&x.h_all_counts, 16 * (size_t)nranks + 64));
+        x.g_cuts.assign(nranks, 0); x.g_nnz.assign(nranks, 0); x.g_off.assign(nranks + 1, 0);
+        CK(h, cudaEventCreateWithFlags(&x.packed, cudaEventDisableTiming)); CK(h, cudaEventCreateWithFlags(&x.sizes, cudaEventDisableTiming));
+        CK(h, cudaEventCreateWithFlags(&x.done, cudaEventDisableTiming));
+        x.state = 0;
+    }
     return KTN_OK;
 }
 
@@ -78,67 +90,99 @@ extern "C" int ktn_set_row_offset(ktn_handle* h, int64_t first_global_row) {
     return KTN_OK;
 }
 
-// Enqueue pack + exchange after the last round.  The sizes travel first (16 bytes per rank); the host reads them
-// to place every rank's blob, then one grouped broadcast per rank moves the payload over NVLink.
+// Second half of an exchange: the sizes of every rank are on the host (their copy was enqueued a round ago, so the wait is
+// short); place every rank's blob and move the payloads with one grouped broadcast per rank over NVLink.
+static int launch_payload(ktn_handle* h, ktn_handle::Exchange& x) {
+    if (x.state != 1) return KTN_OK;
+    ncclComm_t comm = (ncclComm_t)h->comm;
+    CK(h, cudaEventSynchronize(x.sizes));
+    size_t off = 0;
+    for (int r = 0; r < h->nranks; ++r) {
+        x.g_cuts[r] = (int64_t)x.h_all_counts[2 * r]; x.g_nnz[r] = (int64_t)x.h_all_counts[2 * r + 1];
+        x.g_off[r] = (int64_t)off;
+        off += ktn_pack_layout(x.g_cuts[r], x.g_nnz[r]).total;
+    }
+    x.g_off[h->nranks] = (int64_t)off; x.gathered_bytes = (int64_t)off;
+    if (x.gathered.bytes < off) { CK(h, cudaStreamSynchronize(h->comm_stream)); CK(h, x.gathered.alloc(off + off / 4)); }
+    NK(h, N.GroupStart());
+    for (int r = 0; r < h->nranks; ++r) {
+        const size_t bytes = (size_t)(x.g_off[r + 1] - x.g_off[r]);
+        NK(h, N.Broadcast(x.sendbuf.p, x.gathered.as<unsigned char>() + x.g_off[r], bytes, ncclUint8, r, comm, h->comm_stream));
+    }
+    NK(h, N.GroupEnd());
+    CK(h, cudaEventRecord(x.done, h->comm_stream));
+    x.state = 2;
+    return KTN_OK;
+}
+
+// Enqueue the exchange of the last round.  First half now: pack this rank's cuts into one blob (on the round's stream) and
+// all-gather the sizes (16 bytes per rank, on the exchange stream), nothing is waited for.  Payloads go out two calls later
+// (ktn_comm_launch_pending, from the round launcher), when their sizes have long reached the host, and overlap the kernels
+// of later rounds; ktn_sync_gathered launches what is still outstanding.  Every rank makes the same sequence of NCCL calls.
 extern "C" int ktn_allgather_cuts_async(ktn_handle* h) {
     if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
     if (!h->comm) return fail(h, KTN_ERR_USAGE, "ktn_comm_init has not been called");
     cudaSetDevice(h->device);
     ncclComm_t comm = (ncclComm_t)h->comm;
+    h->xch_cur = (h->xch_cur + 1) % 3;
+    ktn_handle::Exchange& x = h->xch[h->xch_cur];
+    // the slot reused here was last used three exchanges ago; its payload (and the one after it) goes out before anything of
+    // this exchange is enqueued on the exchange stream, in the same order on every rank
+    int rc = launch_payload(h, x); if (rc) return rc;
+    rc = launch_payload(h, h->xch[(h->xch_cur + 1) % 3]); if (rc) return rc;
     const size_t m = (size_t)h->prob.num_constr, NZ = (size_t)h->prob.jac_ptr[m];
     const size_t cap = ktn_pack_layout(m, NZ).total;
-    if (h->sendbuf.bytes < cap) CK(h, h->sendbuf.alloc(cap));
+    if (x.sendbuf.bytes < cap) { CK(h, cudaStreamSynchronize(h->comm_stream)); CK(h, x.sendbuf.alloc(cap)); }
+    if (x.state == 2) CK(h, cudaStreamWaitEvent(h->stream, x.done, 0));
     CK(h, cudaEventRecord(h->evx0, h->stream));
     KtnRoundParams p = ktn_make_params(h, nullptr, 0, 0);
-    ktn_launch_pack(p, h->sendbuf.as<unsigned char>(), h->num_sms, h->stream);
+    ktn_launch_pack(p, x.sendbuf.as<unsigned char>(), h->num_sms, h->stream);
     h->tm.launches += 1;
-    NK(h, N.AllGather(h->counts.p, h->all_counts.p, 2, ncclUint64, comm, h->stream));
-    CK(h, cudaMemcpyAsync(h->h_all_counts, h->all_counts.p, 16 * (size_t)h->nranks, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));
-    size_t off = 0;
-    for (int r = 0; r < h->nranks; ++r) {
-        h->g_cuts[r] = (int64_t)h->h_all_counts[2 * r]; h->g_nnz[r] = (int64_t)h->h_all_counts[2 * r + 1];
-        h->g_off[r] = (int64_t)off;
-        off += ktn_pack_layout(h->g_cuts[r], h->g_nnz[r]).total;
-    }
-    h->g_off[h->nranks] = (int64_t)off; h->gathered_bytes = (int64_t)off;
-    if (h->gathered.bytes < off) CK(h, h->gathered.alloc(off + off / 4));
-    NK(h, N.GroupStart());
-    for (int r = 0; r < h->nranks; ++r) {
-        const size_t bytes = (size_t)(h->g_off[r + 1] - h->g_off[r]);
-        NK(h, N.Broadcast(h->sendbuf.p, h->gathered.as<unsigned char>() + h->g_off[r], bytes, ncclUint8, r, comm, h->stream));
-    }
-    NK(h, N.GroupEnd());
-    CK(h, cudaEventRecord(h->evx1, h->stream));
-    h->gather_pending = true;
+    CK(h, cudaEventRecord(x.packed, h->stream));
+    CK(h, cudaStreamWaitEvent(h->comm_stream, x.packed, 0));
+    // the pack kernel wrote {n_cuts, nnz} at the head of the blob: all-gather those 16 bytes
+    NK(h, N.AllGather(x.sendbuf.p, x.all_counts.p, 2, ncclUint64, comm, h->comm_stream));
+    CK(h, cudaMemcpyAsync(x.h_all_counts, x.all_counts.p, 16 * (size_t)h->nranks, cudaMemcpyDeviceToHost, h->comm_stream));
+    CK(h, cudaEventRecord(x.sizes, h->comm_stream));
+    x.state = 1;
+    // the next round must not overwrite the compacted outputs before the pack has read them: same stream, nothing to do.
     return KTN_OK;
+}
+
+// Called by the round launcher before it enqueues the kernels of a new round: the payload of the exchange enqueued TWO calls ago
+// goes out now (its sizes reached the host long ago, so the host does not stall), and runs beside the new round.
+int ktn_comm_launch_pending(ktn_handle* h) {
+    if (!h->comm) return KTN_OK;
+    return launch_payload(h, h->xch[(h->xch_cur + 2) % 3]);       // the slot used before the previous one
 }
 
 extern "C" int ktn_sync_gathered(ktn_handle* h, int64_t* total_cuts, int64_t* total_nnz) {
     if (!h || !h->comm) return fail(h, KTN_ERR_USAGE, "no communicator");
     cudaSetDevice(h->device);
-    if (h->gather_pending) {
-        CK(h, cudaStreamSynchronize(h->stream));
-        h->gather_pending = false;
-        float ms = 0.f; if (cudaEventElapsedTime(&ms, h->evx0, h->evx1) == cudaSuccess) h->tm.exchange_ms = ms;
-    }
+    ktn_handle::Exchange& x = h->xch[h->xch_cur];
+    int rc = launch_payload(h, h->xch[(h->xch_cur + 1) % 3]); if (rc) return rc;      // oldest first: the same order on every rank
+    rc = launch_payload(h, h->xch[(h->xch_cur + 2) % 3]); if (rc) return rc;
+    rc = launch_payload(h, x); if (rc) return rc;
+    if (x.state != 2) return fail(h, KTN_ERR_USAGE, "no exchange has been enqueued");
+    CK(h, cudaStreamSynchronize(h->comm_stream));
     int64_t c = 0, z = 0;
-    for (int r = 0; r < h->nranks; ++r) { c += h->g_cuts[r]; z += h->g_nnz[r]; }
+    for (int r = 0; r < h->nranks; ++r) { c += x.g_cuts[r]; z += x.g_nnz[r]; }
     if (total_cuts) *total_cuts = c;
     if (total_nnz) *total_nnz = z;
     return KTN_OK;
 }
 
-// Unpacks the gathered blobs into one CSR; row ids carry each rank's global row offset (exchanged in the header).
+// Unpacks the gathered blobs of the LAST exchange into one CSR; row ids are global (K2 applied each rank's row offset).
 extern "C" int ktn_fetch_gathered(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val,
                                   double* lo, double* hi, double* g, double* viol, double* bconst) {
     int rc = ktn_sync_gathered(h, nullptr, nullptr); if (rc) return rc;
-    std::vector<unsigned char> host((size_t)h->gathered_bytes + 16);
-    CK(h, cudaMemcpy(host.data(), h->gathered.p, (size_t)h->gathered_bytes, cudaMemcpyDeviceToHost));
+    ktn_handle::Exchange& x = h->xch[h->xch_cur];
+    std::vector<unsigned char> host((size_t)x.gathered_bytes + 16);
+    CK(h, cudaMemcpy(host.data(), x.gathered.p, (size_t)x.gathered_bytes, cudaMemcpyDeviceToHost));
     int64_t co = 0, zo = 0;
     if (row_ptr) row_ptr[0] = 0;
     for (int r = 0; r < h->nranks; ++r) {
-        const unsigned char* b = host.data() + h->g_off[r];
+        const unsigned char* b = host.data() + x.g_off[r];
         const unsigned long long* hd = reinterpret_cast<const unsigned long long*>(b);
         const int64_t n = (int64_t)hd[0], nz = (int64_t)hd[1];
         const KtnPackLayout L = ktn_pack_layout(n, nz);

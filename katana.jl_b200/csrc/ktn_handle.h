@@ -41,12 +41,20 @@ struct ktn_handle {
     uint32_t warp_bytes = 0, blob_cap = 0, table_bytes = 0, table_prog_off = 0, epoch = 0, blk_stride = 0;
     ktn_timings tm;
     std::string err;
-    // sharding (ktn_comm.cu): NCCL communicator, packed send buffer, gathered buffer
+    // sharding (ktn_comm.cu): NCCL communicator on its own stream; three exchange slots rotate so that the payload of round i
+    // travels while later rounds compute and the host never waits for sizes that are not there yet
     void* comm = nullptr; int nranks = 1, rank = 0;
-    DevBuf sendbuf, gathered, all_counts;
-    unsigned long long* h_all_counts = nullptr;   // pinned [2 * nranks]
-    std::vector<int64_t> g_cuts, g_nnz, g_off;    // per rank, after ktn_sync_gathered
-    bool gather_pending = false; int64_t gathered_bytes = 0, row_offset = 0;
+    cudaStream_t comm_stream = nullptr;
+    struct Exchange {
+        DevBuf sendbuf, gathered, all_counts;
+        unsigned long long* h_all_counts = nullptr;     // pinned [2 * nranks]
+        std::vector<int64_t> g_cuts, g_nnz, g_off;      // per rank, once the sizes are on the host
+        cudaEvent_t packed = nullptr, sizes = nullptr, done = nullptr;
+        int state = 0;                                  // 0 idle, 1 sizes in flight (payload not launched), 2 payload in flight / complete
+        int64_t gathered_bytes = 0;
+    } xch[3];                                           // the payload of exchange k is launched when exchange k+2 is enqueued
+    int xch_cur = 0;                                    // slot of the last ktn_allgather_cuts_async
+    int64_t row_offset = 0;
     cudaEvent_t evx0 = nullptr, evx1 = nullptr;
 };
 
