@@ -273,7 +273,7 @@ def main():
         "config": {"workload": f"{args.workload}: {desc}; m={rows} rows/GPU, n={nv} vars, violated fraction {args.v}, f_tol 1e-6",
                    "rows_per_gpu": rows, "num_var": nv, "violated_fraction": args.v, "cuts_per_round_per_gpu": n_cuts, "cut_nnz_per_round_per_gpu": nnz,
                    "l2": f"no flush needed: one round streams {alg_round / 1e6:.0f} MB of inputs > 126 MB L2",
-                   "exchange": "none" if world == 1 else "NCCL on its own stream, pipelined one round deep: sizes allgather, then one grouped broadcast per rank of the packed cut blob"},
+                   "exchange": "none" if world == 1 else "NCCL on its own stream, pipelined one round deep: sizes allgather, then ONE ncclAllGather of the packed cut blobs (slots of the largest blob)"},
         "roofline": {"bound": "hbm", "kernel": "ktn_family_kernel (K1: evaluate g, test, Jacobian row, cut row; one launch per round)" if args.workload in ("lse", "qcqp") else "ktn_round_kernel (K1, tape interpreter)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_k1, "ms_per_launch": k1_ms,
                      "round": {"algorithmic_bytes": alg_round, "ms": k1_ms + k2_ms, "frac": alg_round / ((k1_ms + k2_ms) * 1e-3) / 1e9 / peak,

@@ -91,25 +91,26 @@ extern "C" int ktn_set_row_offset(ktn_handle* h, int64_t first_global_row) {
 }
 
 // Second half of an exchange: the sizes of every rank are on the host (their copy was enqueued a round ago, so the wait is
-// short); place every rank's blob and move the payloads with one grouped broadcast per rank over NVLink.
+// short); size the common slot and move the payloads with one all-gather over NVLink / NVSwitch.
 static int launch_payload(ktn_handle* h, ktn_handle::Exchange& x) {
     if (x.state != 1) return KTN_OK;
     ncclComm_t comm = (ncclComm_t)h->comm;
     CK(h, cudaEventSynchronize(x.sizes));
-    size_t off = 0;
+    // every rank's blob travels in a slot of the size of the largest one: ONE ncclAllGather (NVSwitch-friendly) instead of a
+    // broadcast per rank; with balanced shards the padding is negligible
+    size_t slot = 0;
     for (int r = 0; r < h->nranks; ++r) {
         x.g_cuts[r] = (int64_t)x.h_all_counts[2 * r]; x.g_nnz[r] = (int64_t)x.h_all_counts[2 * r + 1];
-        x.g_off[r] = (int64_t)off;
-        off += ktn_pack_layout(x.g_cuts[r], x.g_nnz[r]).total;
+        const size_t t = ktn_pack_layout(x.g_cuts[r], x.g_nnz[r]).total;
+        if (t > slot) slot = t;
     }
-    x.g_off[h->nranks] = (int64_t)off; x.gathered_bytes = (int64_t)off;
+    slot = (slot + 127) & ~(size_t)127;
+    for (int r = 0; r <= h->nranks; ++r) x.g_off[r] = (int64_t)(slot * (size_t)r);
+    const size_t off = slot * (size_t)h->nranks;
+    x.gathered_bytes = (int64_t)off;
     if (x.gathered.bytes < off) { CK(h, cudaStreamSynchronize(h->comm_stream)); CK(h, x.gathered.alloc(off + off / 4)); }
-    NK(h, N.GroupStart());
-    for (int r = 0; r < h->nranks; ++r) {
-        const size_t bytes = (size_t)(x.g_off[r + 1] - x.g_off[r]);
-        NK(h, N.Broadcast(x.sendbuf.p, x.gathered.as<unsigned char>() + x.g_off[r], bytes, ncclUint8, r, comm, h->comm_stream));
-    }
-    NK(h, N.GroupEnd());
+    if (x.sendbuf.bytes < slot) return fail(h, KTN_ERR_NCCL, "exchange slot larger than the send buffer");   // cannot happen: the buffer holds every row
+    NK(h, N.AllGather(x.sendbuf.p, x.gathered.p, slot, ncclUint8, comm, h->comm_stream));
     CK(h, cudaEventRecord(x.done, h->comm_stream));
     x.state = 2;
     return KTN_OK;
@@ -131,7 +132,7 @@ extern "C" int ktn_allgather_cuts_async(ktn_handle* h) {
     int rc = launch_payload(h, x); if (rc) return rc;
     rc = launch_payload(h, h->xch[(h->xch_cur + 1) % 3]); if (rc) return rc;
     const size_t m = (size_t)h->prob.num_constr, NZ = (size_t)h->prob.jac_ptr[m];
-    const size_t cap = ktn_pack_layout(m, NZ).total;
+    const size_t cap = ((ktn_pack_layout(m, NZ).total + 127) & ~(size_t)127) + 128;
     if (x.sendbuf.bytes < cap) { CK(h, cudaStreamSynchronize(h->comm_stream)); CK(h, x.sendbuf.alloc(cap)); }
     if (x.state == 2) CK(h, cudaStreamWaitEvent(h->stream, x.done, 0));
     CK(h, cudaEventRecord(h->evx0, h->stream));
