@@ -173,6 +173,26 @@ def test_zero_copy_view_matches_copy(oracle_lib, cuda_lib):
     assert hc.separate(x0, view=True).n_cuts == 0      # empty batch
 
 
+def test_many_rounds_keep_state_clean(oracle_lib, cuda_lib):
+    """600 rounds with changing cut sets on one handle: per-round device state (selection flags, per-block counters by round
+    parity, error slots, tickets) is re-armed by the kernels themselves; nothing from an earlier round may resurface."""
+    nv, nr = 500, 3000
+    w = cuda_lib.synth_rows(0, 5, nv, 0, nr); x0 = cuda_lib.synth_point(0, 5, nv)
+    ho, hc = both(oracle_lib, cuda_lib, nv, w)
+    g = ho.eval_g(x0)
+    ub = np.full(nr, np.quantile(g, 0.7)); ho.set_bounds(w.lb, ub); hc.set_bounds(w.lb, ub)
+    scales = [1.0, 0.2, 0.6, 1.3]
+    refs = [ho.separate(s * x0) for s in scales]
+    assert len({r.n_cuts for r in refs}) > 2
+    for it in range(600):
+        k = it % len(scales)
+        if it % 97 == 0 or it in (254, 255, 256, 257, 509, 510, 511, 512):
+            assert_batches_identical(refs[k], hc.separate(scales[k] * x0), f"round {it}")
+            assert bits_equal(hc.get_g(), ho.eval_g(scales[k] * x0))
+        else:
+            hc.separate(scales[k] * x0, fetch=False)
+
+
 def test_device_resident_round_and_counters(cuda_lib):
     import torch
     nv, nr = 2000, 50000
