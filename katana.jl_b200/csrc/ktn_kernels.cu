@@ -157,7 +157,7 @@ __device__ __forceinline__ const unsigned char* family_blob(const KtnRoundParams
 // One chunk.  N = 1..16: register-resident rows of exactly N unique variables (class blobs are contiguous and equally sized:
 // no descriptor); N = 0: streaming fallback (any count) through the chunk descriptor.
 template <int FAM, int N>
-__device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c, uint32_t lane, const double* sx, int32_t xs, double* scratch) {
+__device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c, uint32_t lane, const double* sx, int32_t xs, double* scratch, unsigned int* ticket, uint32_t* next) {
     typedef KtnFamily<FAM> F;
     const uint32_t slotid = c * 32u + lane;
     uint32_t nu = (uint32_t)N;
@@ -173,8 +173,14 @@ __device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c
     if constexpr (N > 0) {
         int32_t col[NR];
         ktn_family_load<FAM, NR>(r, v, col);
+        // the warp's next ticket is drawn HERE, behind the row's loads, and parked in shared memory: its round trip overlaps
+        // theirs (drawn before the loads, the compiler spills the result at once and the chunk starts with a stall)
+        if (lane == 0) *next = atomicAdd(ticket, 1u);
         g = ktn_family_eval<FAM, NR>(r, v, col, aux);
-    } else g = F::forward_stream(r, aux);
+    } else {
+        if (lane == 0) *next = atomicAdd(ticket, 1u);
+        g = F::forward_stream(r, aux);
+    }
     const int32_t row = ldg_stream(p.chunk_rows + slotid);
     double lb = 0.0, ub = 0.0;
     if (p.mode != KTN_MODE_EVAL) { lb = ldg_stream(p.chunk_lb + slotid); ub = ldg_stream(p.chunk_ub + slotid); }
@@ -215,13 +221,13 @@ __device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c
 }
 
 template <int FAM>
-__device__ __forceinline__ void family_dispatch(const KtnRoundParams& p, uint32_t cls, uint32_t c, uint32_t lane, const double* sx, int32_t xs, double* scratch) {
+__device__ __forceinline__ void family_dispatch(const KtnRoundParams& p, uint32_t cls, uint32_t c, uint32_t lane, const double* sx, int32_t xs, double* scratch, unsigned int* ticket, uint32_t* next) {
     switch (cls) {
-#define KTN_CASE(n) case n: family_chunk<FAM, n>(p, c, lane, sx, xs, scratch); break;
+#define KTN_CASE(n) case n: family_chunk<FAM, n>(p, c, lane, sx, xs, scratch, ticket, next); break;
         KTN_CASE(1) KTN_CASE(2) KTN_CASE(3) KTN_CASE(4) KTN_CASE(5) KTN_CASE(6) KTN_CASE(7) KTN_CASE(8)
         KTN_CASE(9) KTN_CASE(10) KTN_CASE(11) KTN_CASE(12) KTN_CASE(13) KTN_CASE(14) KTN_CASE(15) KTN_CASE(16)
 #undef KTN_CASE
-        default: family_chunk<FAM, 0>(p, c, lane, sx, xs, scratch); break;
+        default: family_chunk<FAM, 0>(p, c, lane, sx, xs, scratch, ticket, next); break;
     }
 }
 
@@ -231,6 +237,7 @@ __global__ void __launch_bounds__(KTN_FP_WARPS * 32, 1) ktn_family_kernel(const 
     double* scratch = reinterpret_cast<double*>(smem + 128) + (size_t)(threadIdx.x >> 5) * (KTN_FAM_REGS * KTN_FW_PASS);
     double* sx = reinterpret_cast<double*>(smem + KTN_FP_SCRATCH_BYTES);
     const uint32_t lane = threadIdx.x & 31u;
+    uint32_t* next = reinterpret_cast<uint32_t*>(smem + 16) + (threadIdx.x >> 5);       // per-warp mailbox of the next ticket
     if (KTN_OPT_XCACHE && xs > 0) {
         // head of x* -> shared memory: a handful of TMA bulk copies, one wait
         uint64_t& xbar = *reinterpret_cast<uint64_t*>(smem);
@@ -278,10 +285,10 @@ __global__ void __launch_bounds__(KTN_FP_WARPS * 32, 1) ktn_family_kernel(const 
             cur = bcast(take(cls));
             continue;
         }
-        const uint32_t nxt = take(cls);             // the next ticket travels while this chunk computes
-        family_dispatch<FAM>(p, cls, p.cls_begin[cls] + cur, lane, sx, xs, scratch);
+        family_dispatch<FAM>(p, cls, p.cls_begin[cls] + cur, lane, sx, xs, scratch, &tickets[cls], next);   // draws the next ticket on the way
         KTN_T(tb);
-        cur = bcast(nxt);
+        __syncwarp();
+        cur = *reinterpret_cast<volatile uint32_t*>(next);
         KTN_T(tc);
         KTN_TADD(3, tb, tc);
     }
