@@ -84,7 +84,7 @@ __device__ __forceinline__ void count_selected(const KtnRoundParams& p, unsigned
 // ---------------------------------------------------------------------------------------------
 // tuning knobs (scripts/build_variants.sh builds A/B variants of the library with -D overrides)
 #ifndef KTN_OPT_PASS
-#define KTN_OPT_PASS 8
+#define KTN_OPT_PASS 16
 #endif
 #ifndef KTN_OPT_WARPS
 #define KTN_OPT_WARPS 16
