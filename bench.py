@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--v", type=float, default=0.1, help="violated fraction of the rows at x*")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--topk", type=int, default=0, help="build extension: keep only the k most violated rows per round (0 = reference behaviour: all)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -185,6 +186,8 @@ def main():
     g = h.eval_g(x0)
     ub = np.full(rows, np.quantile(g, 1 - args.v))
     h.set_bounds(w.lb, ub)
+    if args.topk > 0:
+        h.set_params(1e-6, 1e9, args.topk)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -271,7 +274,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}; m={rows} rows/GPU, n={nv} vars, violated fraction {args.v}, f_tol 1e-6",
-                   "rows_per_gpu": rows, "num_var": nv, "violated_fraction": args.v, "cuts_per_round_per_gpu": n_cuts, "cut_nnz_per_round_per_gpu": nnz,
+                   "rows_per_gpu": rows, "num_var": nv, "violated_fraction": args.v, "topk": args.topk, "cuts_per_round_per_gpu": n_cuts, "cut_nnz_per_round_per_gpu": nnz,
                    "l2": f"no flush needed: one round streams {alg_round / 1e6:.0f} MB of inputs > 126 MB L2",
                    "exchange": "none" if world == 1 else "NCCL on its own stream, pipelined one round deep: sizes allgather, then ONE ncclAllGather of the packed cut blobs (slots of the largest blob)"},
         "roofline": {"bound": "hbm", "kernel": "ktn_family_kernel (K1: evaluate g, test, Jacobian row, cut row; one launch per round)" if args.workload in ("lse", "qcqp") else "ktn_round_kernel (K1, tape interpreter)", "achieved": achieved, "peak": peak, "unit": "GB/s",

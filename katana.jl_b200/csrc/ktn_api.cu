@@ -19,7 +19,7 @@ extern "C" const char* ktn_last_error(ktn_handle* h) { return h ? h->err.c_str()
 static void free_problem(ktn_handle* h) {
     DevBuf* all[] = {&h->chunks, &h->shapes, &h->prog, &h->blob, &h->chunk_rows, &h->chunk_lb, &h->chunk_ub, &h->jac_ptr, &h->jac_col,
                      &h->row_lb, &h->row_ub, &h->x, &h->force, &h->g_row, &h->b_row, &h->sel, &h->stage_val, &h->big_scratch,
-                     &h->blk_cnt, &h->table, &h->out_row, &h->out_ptr, &h->out_col, &h->out_val, &h->out_lo, &h->out_hi, &h->out_g, &h->out_viol, &h->out_b};
+                     &h->blk_cnt, &h->topk_key, &h->topk_state, &h->topk_eqcnt, &h->table, &h->out_row, &h->out_ptr, &h->out_col, &h->out_val, &h->out_lo, &h->out_hi, &h->out_g, &h->out_viol, &h->out_b};
     for (DevBuf* b : all) b->release();
     if (h->h_x) { cudaFreeHost(h->h_x); h->h_x = nullptr; }
     h->prob = KtnProblem();
@@ -77,11 +77,20 @@ extern "C" void ktn_destroy(ktn_handle* h) {
     delete h;
 }
 
-extern "C" int ktn_set_params(ktn_handle* h, double f_tol, double rng, int64_t topk) {
-    if (!h) return KTN_ERR_USAGE;
-    if (topk != 0) return fail(h, KTN_ERR_UNSUPPORTED, "topk > 0 is not implemented in the CUDA backend yet");
-    h->opt.f_tol = f_tol; h->opt.cut_coef_rng = rng; h->opt.topk = topk;
+// device buffers of the top-k stage: one key per row, the select state, one tie count per compaction block
+static int ensure_topk(ktn_handle* h) {
+    if (h->opt.topk <= 0 || !h->loaded || h->topk_key.p) return KTN_OK;
+    const size_t m = (size_t)h->prob.num_constr;
+    CK(h, h->topk_key.alloc(8 * (m + 1))); CK(h, h->topk_state.alloc(sizeof(KtnTopkState))); CK(h, h->topk_eqcnt.alloc(4 * (size_t)h->blk_stride + 16));
     return KTN_OK;
+}
+
+extern "C" int ktn_set_params(ktn_handle* h, double f_tol, double rng, int64_t topk) {
+    if (!h || topk < 0) return fail(h, KTN_ERR_USAGE, "bad parameters");
+    if (topk > 0 && h->comm) return fail(h, KTN_ERR_UNSUPPORTED, "topk > 0 on a sharded handle: a global top-k needs a cross-rank selection, which is not built");
+    h->opt.f_tol = f_tol; h->opt.cut_coef_rng = rng; h->opt.topk = topk;
+    cudaSetDevice(h->device);
+    return ensure_topk(h);
 }
 
 extern "C" int ktn_load_begin(ktn_handle* h, int64_t num_var, int64_t num_constr) {
@@ -160,7 +169,7 @@ extern "C" int ktn_load_end(ktn_handle* h) {
     // the packed blob lives on the device now
     std::vector<uint8_t>().swap(P.blob);
     h->loading = false; h->loaded = true;
-    return KTN_OK;
+    return ensure_topk(h);
 }
 
 extern "C" int ktn_set_bounds(ktn_handle* h, const double* lb, const double* ub) {
@@ -204,6 +213,7 @@ KtnRoundParams ktn_make_params(ktn_handle* h, const double* d_x, int mode, int d
     p.row_lb = h->row_lb.as<double>(); p.row_ub = h->row_ub.as<double>();
     p.x = d_x; p.force = h->force.as<uint8_t>();
     p.f_tol = h->opt.f_tol; p.rng = h->opt.cut_coef_rng; p.mode = mode; p.do_round = do_round;
+    p.topk = h->comm ? 0 : h->opt.topk; p.topk_key = h->topk_key.as<unsigned long long>(); p.topk_state = h->topk_state.as<KtnTopkState>(); p.topk_eqcnt = h->topk_eqcnt.as<unsigned int>();
     p.num_var = h->prob.num_var; p.num_rows = h->prob.num_constr;
     p.warp_bytes = h->warp_bytes; p.blob_cap = h->blob_cap;
     p.g_row = h->g_row.as<double>(); p.b_row = h->b_row.as<double>(); p.sel = h->sel.as<uint32_t>();

@@ -32,6 +32,7 @@ struct ktn_handle {
     KtnProblem prob;
     bool loading = false, loaded = false, round_pending = false, have_round = false;
     DevBuf chunks, shapes, prog, blob, chunk_rows, chunk_lb, chunk_ub, jac_ptr, jac_col, row_lb, row_ub;
+    DevBuf topk_key, topk_state, topk_eqcnt;      // top-k selection (allocated when ktn_options.topk > 0)
     DevBuf x, force, g_row, b_row, sel, stage_val, big_scratch, ticket, blk_cnt, counts, table;
     DevBuf out_row, out_ptr, out_col, out_val, out_lo, out_hi, out_g, out_viol, out_b;
     double* h_x = nullptr;                 // pinned

@@ -657,6 +657,131 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
 }
 
 // ---------------------------------------------------------------------------------------------
+// Top-k selection (ktn_options.topk > 0; a build extension, the reference emits every violated row -- src/model.jl:272-283).
+// Between K1 and K2: of the violated rows keep the k ranked first by (NaN first, violation max(lb - g, g - ub) descending,
+// row index ascending); the survivors are emitted in ascending row order by the unchanged K2.
+//   T1 keys      one 64-bit order-preserving key per row (0 = not violated)
+//   T2 select    8 passes of an 8-bit radix select, most significant digit first: block-local shared-memory histograms of the
+//                keys that still match the prefix, merged with global atomics; the LAST block to finish picks the digit that
+//                holds the k-th key (no block ever waits for another)  ->  threshold key T and how many keys == T to keep
+//   T3 ties      per 4096-row block: number of keys == T (ties at the threshold are taken in row order)
+//   T4 demote    rows below the threshold (or beyond the tie quota) are deselected; per-block cut counts and the first
+//                non-finite row are rewritten for the survivors; K2 then runs as always
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long topk_key(double g, double lb, double ub) {
+    if (g != g) return ~0ull;                                       // NaN ranks first
+    const double v1 = lb - g, v2 = g - ub, v = v1 > v2 ? v1 : v2;
+    unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);               // order-preserving map of fp64 onto unsigned integers
+    return u == ~0ull ? u - 1ull : (u == 0ull ? 1ull : u);          // keep clear of the two reserved values
+}
+
+__global__ void __launch_bounds__(256) ktn_topk_key_kernel(const KtnRoundParams p, unsigned long long* key, KtnTopkState* st, unsigned long long k) {
+    if (blockIdx.x == 0 && threadIdx.x < 256) {
+        st->hist[threadIdx.x] = 0u;
+        if (threadIdx.x == 0) { st->prefix = 0ull; st->mask = 0ull; st->remaining = k; st->done = 0u; st->all = 0u; st->eq_total = 0ull; }
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.num_rows; i += (int64_t)gridDim.x * blockDim.x)
+        key[i] = p.sel[i] ? topk_key(p.g_row[i], p.row_lb[i], p.row_ub[i]) : 0ull;
+}
+
+__global__ void __launch_bounds__(256) ktn_topk_select_kernel(const KtnRoundParams p, const unsigned long long* key, KtnTopkState* st, int pass) {
+    __shared__ unsigned int sh[256];
+    __shared__ unsigned int s_last;
+    sh[threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned long long prefix = st->prefix, mask = st->mask;      // written by the last block of the previous pass (a previous launch)
+    const int shift = 56 - 8 * pass;
+    if (!st->all) {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.num_rows; i += (int64_t)gridDim.x * blockDim.x) {
+            const unsigned long long kk = key[i];
+            if (kk != 0ull && (kk & mask) == prefix) atomicAdd(&sh[(unsigned)(kk >> shift) & 255u], 1u);
+        }
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], sh[threadIdx.x]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->done, 1u) == gridDim.x - 1u) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last block: digit of the k-th key among the keys matching the prefix (bins scanned from the top)
+    if (threadIdx.x == 0) {
+        volatile unsigned int* hist = st->hist;
+        unsigned long long rem = st->remaining, total = 0;
+        for (int d = 0; d < 256; ++d) total += hist[d];
+        if (pass == 0 && total <= rem) st->all = 1u;                    // fewer violated rows than k: everything survives
+        else if (!st->all) {
+            unsigned long long above = 0; int d = 255;
+            for (; d > 0; --d) { if (above + hist[d] >= rem) break; above += hist[d]; }
+            st->prefix = prefix | ((unsigned long long)d << shift); st->mask = mask | (255ull << shift);
+            st->remaining = rem - above;                                // keys in higher bins all survive
+            st->eq_total = hist[d];                                     // after the last pass: number of keys equal to the threshold
+        }
+        for (int d = 0; d < 256; ++d) hist[d] = 0u;
+        st->done = 0u;
+        if (pass == 7) p.counts[2 + (p.epoch & 1u)] = ~0ull;            // the first non-finite row is recomputed over the survivors (T4)
+    }
+}
+
+__global__ void __launch_bounds__(KTN_CBLOCK) ktn_topk_ties_kernel(const KtnRoundParams p, const unsigned long long* key, const KtnTopkState* st, unsigned int* eqcnt) {
+    __shared__ unsigned int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0u;
+    __syncthreads();
+    const unsigned long long T = st->prefix;
+    const int64_t i0 = (int64_t)blockIdx.x * KTN_CROWS + (int64_t)threadIdx.x * KTN_CRPT;
+    unsigned int c = 0;
+    if (!st->all) for (int r = 0; r < KTN_CRPT; ++r) if (i0 + r < p.num_rows && key[i0 + r] == T) ++c;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31u) == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) eqcnt[blockIdx.x] = s_cnt;
+}
+
+__global__ void __launch_bounds__(KTN_CBLOCK) ktn_topk_demote_kernel(const KtnRoundParams p, const unsigned long long* key, const KtnTopkState* st, const unsigned int* eqcnt) {
+    __shared__ unsigned int s_w[32];
+    __shared__ unsigned long long s_eq_before, s_cnt, s_nnz;
+    const uint32_t bid = blockIdx.x, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_cnt = 0ull; s_nnz = 0ull; }
+    const bool all = st->all != 0u;
+    const unsigned long long T = st->prefix, quota = st->remaining;     // keys == T that survive, in row order
+    // keys == T in the blocks before this one
+    unsigned long long before = 0;
+    if (!all) for (uint32_t j = threadIdx.x; j < bid; j += KTN_CBLOCK) before += eqcnt[j];
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (threadIdx.x == 0) s_eq_before = 0ull;
+    __syncthreads();
+    if (lane == 0 && before) atomicAdd(&s_eq_before, before);
+    // ordered rank of this thread's keys == T inside the block
+    const int64_t i0 = (int64_t)bid * KTN_CROWS + (int64_t)threadIdx.x * KTN_CRPT;
+    unsigned long long kk[KTN_CRPT]; unsigned int mine = 0;
+    for (int r = 0; r < KTN_CRPT; ++r) { kk[r] = i0 + r < p.num_rows ? key[i0 + r] : 0ull; if (!all && kk[r] == T) ++mine; }
+    unsigned int incl = mine;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += n; }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) { unsigned int v = s_w[lane]; for (int o = 1; o < 32; o <<= 1) { const unsigned int n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v += n; } s_w[lane] = v; }
+    __syncthreads();
+    unsigned long long rank = s_eq_before + (warp ? s_w[warp - 1] : 0u) + (incl - mine);
+    unsigned long long cnt = 0, nnz = 0;
+    for (int r = 0; r < KTN_CRPT; ++r) {
+        if (kk[r] == 0ull) continue;
+        const int64_t i = i0 + r;
+        bool keep = all || kk[r] > T;
+        if (!all && kk[r] == T) { keep = rank < quota; ++rank; }
+        if (!keep) { p.sel[i] = 0u; continue; }
+        const uint32_t s = p.sel[i];
+        ++cnt; nnz += s & ~KTN_SEL_ERRBIT;
+        if (s & KTN_SEL_ERRBIT) atomicMin(&p.counts[2 + (p.epoch & 1u)], (unsigned long long)i + 1ull);
+    }
+    for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); nnz += __shfl_xor_sync(0xffffffffu, nnz, o); }
+    if (lane == 0 && cnt) { atomicAdd(&s_cnt, cnt); atomicAdd(&s_nnz, nnz); }
+    __syncthreads();
+    if (threadIdx.x == 0) p.blk_cnt[(size_t)(p.epoch & 1u) * p.blk_stride + bid] = (s_cnt << KTN_BLK_SHIFT) | s_nnz;     // replaces K1's count of ALL violated rows
+}
+
+// ---------------------------------------------------------------------------------------------
 // K3 (sharded runs only): pack the compacted cuts of this rank into ONE contiguous blob so the exchange over
 // NVLink is a single message per rank.  Layout (ktn_pack_layout): 64-byte header {n_cuts, nnz, first-error row + 1},
 // then row_id | row_ptr | lo | hi | g | viol | b | col | val, each section 16-byte aligned.
@@ -781,6 +906,14 @@ int ktn_launch_round(const KtnRoundParams& p, const KtnLaunchPlan& plan, int num
     if (*err != cudaSuccess) return launches;
     if (after_eval) cudaEventRecord(after_eval, stream);
     const uint32_t nblocks = (uint32_t)((p.num_rows + KTN_CROWS - 1) / KTN_CROWS);
+    if (nblocks > 0 && p.topk > 0 && p.mode == KTN_MODE_SEPARATE) {      // keep the k most violated rows
+        const uint32_t grid = (uint32_t)num_sms * 4u;
+        ktn_topk_key_kernel<<<grid, 256, 0, stream>>>(p, p.topk_key, p.topk_state, (unsigned long long)p.topk);
+        for (int pass = 0; pass < 8; ++pass) ktn_topk_select_kernel<<<grid, 256, 0, stream>>>(p, p.topk_key, p.topk_state, pass);
+        ktn_topk_ties_kernel<<<nblocks, KTN_CBLOCK, 0, stream>>>(p, p.topk_key, p.topk_state, p.topk_eqcnt);
+        ktn_topk_demote_kernel<<<nblocks, KTN_CBLOCK, 0, stream>>>(p, p.topk_key, p.topk_state, p.topk_eqcnt);
+        launches += 11;
+    }
     if (nblocks > 0) {
         ktn_compact_kernel<<<nblocks, KTN_CBLOCK, 0, stream>>>(p, nblocks, epoch);
         ++launches;

@@ -5,6 +5,9 @@
 #include <stdint.h>
 #include "ktn_program.h"
 
+// device state of the top-k radix select (ktn_kernels.cu, "Top-k selection")
+struct KtnTopkState { unsigned long long prefix, mask, remaining, eq_total; unsigned int hist[256]; unsigned int done, all; };
+
 enum { KTN_MODE_SEPARATE = 0, KTN_MODE_FORCE = 1, KTN_MODE_EVAL = 2 };   // EVAL: g only (set by ktn_launch_eval)
 
 struct KtnRoundParams {
@@ -24,6 +27,8 @@ struct KtnRoundParams {
     const double* x;
     const uint8_t* force;      // KTN_MODE_FORCE: per-row mask
     double f_tol, rng;
+    int64_t topk;              // > 0: keep only the k most violated rows (build extension)
+    unsigned long long* topk_key; KtnTopkState* topk_state; unsigned int* topk_eqcnt;
     int32_t mode, do_round;
     int64_t num_var, num_rows, row_offset;
     uint32_t chunk_begin, chunk_end;   // chunk range this launch covers

@@ -193,6 +193,44 @@ def test_many_rounds_keep_state_clean(oracle_lib, cuda_lib):
             hc.separate(scales[k] * x0, fetch=False)
 
 
+@pytest.mark.parametrize("kind,nv,nr", [(1, 3000, 30000), (0, 400, 9000)])
+def test_topk_matches_oracle(oracle_lib, cuda_lib, kind, nv, nr):
+    """topk > 0: of the violated rows the k ranked first by (NaN first, violation descending, row ascending) become cuts,
+    emitted in ascending row order -- radix select + tie handling on the device against the oracle's sort."""
+    w = cuda_lib.synth_rows(kind, 31 + kind, nv, 0, nr); x0 = cuda_lib.synth_point(kind, 31 + kind, nv)
+    ho, hc = both(oracle_lib, cuda_lib, nv, w)
+    g = ho.eval_g(x0)
+    ub = np.full(nr, np.quantile(g, 0.7)); ho.set_bounds(w.lb, ub); hc.set_bounds(w.lb, ub)
+    nviol = ho.separate(x0).n_cuts
+    for k in (1, 2, 17, 1000, nviol - 1, nviol, nviol + 5, 10 * nr):
+        ho.set_params(1e-6, 1e9, k); hc.set_params(1e-6, 1e9, k)
+        for x in (x0, 0.7 * x0):
+            bo, bc = ho.separate(x), hc.separate(x)
+            assert_batches_identical(bo, bc, f"kind {kind} topk {k}")
+    ho.set_params(1e-6, 1e9, 0); hc.set_params(1e-6, 1e9, 0)
+    assert_batches_identical(ho.separate(x0), hc.separate(x0), "back to all violated rows")
+
+
+def test_topk_ties_nan_and_errors(oracle_lib, cuda_lib):
+    """Ties at the threshold are broken by row index, NaN violations rank first, and the first non-finite row among the
+    SELECTED rows ends the batch."""
+    x, y, z = E.var(0), E.var(1), E.var(2)
+    disk = x**2 + y**2 - 1.0
+    exprs = []
+    for i in range(6000):                               # many identical rows -> identical violations (ties), a few distinct
+        exprs.append(disk if i % 7 else disk + float(i % 5))
+    exprs[100] = E.log(z)                               # NaN at z < 0: ranks first, and its cut row is non-finite
+    exprs[4000] = E.sqrt(x**2 + y**2) - z               # finite g, non-finite gradient at the origin
+    m = len(exprs)
+    w = E.to_wire(exprs, np.full(m, -np.inf), np.full(m, -5.0), [ROW_NL] * m)
+    ho, hc = both(oracle_lib, cuda_lib, 3, w)
+    for k in (1, 3, 50, 857, 858, 859, 5999, 6000, 7000):
+        ho.set_params(1e-6, 1e9, k); hc.set_params(1e-6, 1e9, k)
+        for pt in ([2.0, 2.0, 1.0], [2.0, 2.0, -1.0], [0.0, 0.0, 3.0], [0.0, 0.0, -1.0]):
+            bo, bc = ho.separate(np.array(pt)), hc.separate(np.array(pt))
+            assert_batches_identical(bo, bc, f"topk {k} at {pt}")
+
+
 def test_device_resident_round_and_counters(cuda_lib):
     import torch
     nv, nr = 2000, 50000
