@@ -706,20 +706,29 @@ __global__ void __launch_bounds__(256) ktn_topk_select_kernel(const KtnRoundPara
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // last block: digit of the k-th key among the keys matching the prefix (bins scanned from the top)
+    // last block: digit of the k-th key among the keys matching the prefix.  One bin per thread, suffix sums over the bins
+    // (so that "above" = keys in higher bins), and exactly one thread finds above < k' <= above + hist[d].
+    __shared__ unsigned long long suf[256];
+    const unsigned int mybin = *reinterpret_cast<volatile unsigned int*>(&st->hist[threadIdx.x]);
+    suf[threadIdx.x] = mybin;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        const unsigned long long add = threadIdx.x + o < 256 ? suf[threadIdx.x + o] : 0ull;
+        __syncthreads();
+        suf[threadIdx.x] += add;
+        __syncthreads();
+    }
+    const unsigned long long rem = st->remaining, total = suf[0], above = suf[threadIdx.x] - mybin;
+    const bool was_all = st->all != 0u;
+    __syncthreads();
+    if (pass == 0 && total <= rem) { if (threadIdx.x == 0) st->all = 1u; }              // fewer violated rows than k: everything survives
+    else if (!was_all && mybin > 0u && above < rem && rem <= above + mybin) {
+        st->prefix = prefix | ((unsigned long long)threadIdx.x << shift); st->mask = mask | (255ull << shift);
+        st->remaining = rem - above;                                    // keys in higher bins all survive
+        st->eq_total = mybin;                                           // after the last pass: number of keys equal to the threshold
+    }
+    st->hist[threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
-        volatile unsigned int* hist = st->hist;
-        unsigned long long rem = st->remaining, total = 0;
-        for (int d = 0; d < 256; ++d) total += hist[d];
-        if (pass == 0 && total <= rem) st->all = 1u;                    // fewer violated rows than k: everything survives
-        else if (!st->all) {
-            unsigned long long above = 0; int d = 255;
-            for (; d > 0; --d) { if (above + hist[d] >= rem) break; above += hist[d]; }
-            st->prefix = prefix | ((unsigned long long)d << shift); st->mask = mask | (255ull << shift);
-            st->remaining = rem - above;                                // keys in higher bins all survive
-            st->eq_total = hist[d];                                     // after the last pass: number of keys equal to the threshold
-        }
-        for (int d = 0; d < 256; ++d) hist[d] = 0u;
         st->done = 0u;
         if (pass == 7) p.counts[2 + (p.epoch & 1u)] = ~0ull;            // the first non-finite row is recomputed over the survivors (T4)
     }
