@@ -69,32 +69,25 @@ __device__ __forceinline__ void count_selected(const KtnRoundParams& p, unsigned
 
 // ---------------------------------------------------------------------------------------------
 // K1f: family shapes (ktn_family.h).  Persistent: ONE block of 16 warps per SM; one warp per chunk, one thread per row.
-//   * the block first copies the head of x* (as much as fits beside the scratch, ~25k doubles) into shared memory: the gather
-//     of x* is what saturates an SM's memory port (one 32-byte sector per clock), and L1 cannot help -- its tags cover 128-byte
-//     lines, so random 8-byte gathers fill one sector per line -- while shared memory serves those columns without a request;
 //   * a row is register resident: every constant and column id of the row is requested at once with coalesced loads straight
-//     from the chunk blob (lane stride 32, streamed past L1), x* is gathered, g is evaluated and tested, and the selected lanes
-//     build their cut row from the same registers;
+//     from the chunk blob (lane stride 32, streamed past L1), x* is gathered through L1 / L2, g is evaluated and tested, and
+//     the selected lanes build their cut row from the same registers;
 //   * every class (rows of exactly k unique variables) has its own ticket counter, its own contiguous range of equally sized
 //     blobs (no descriptor to fetch) and its own specialised, fully unrolled code path; the warps of an SM start in the same
 //     class (classes are spread over the SMs in proportion to their work) and move on together, so the instruction working
 //     set is one class, not the whole kernel.
-// (A TMA producer/consumer ring was measured and dropped: bulk-copy traffic in flight delays the dependent x* gathers more
-//  than it hides DRAM latency -- profiles/microbench/mb2.cu.)
+// Measured and dropped (profiles/microbench/mb2.cu): a TMA producer/consumer ring, a shared-memory cache
+// of x*, block-pooled lane-dense cuts, L2 bulk prefetch of the next chunk, cp.async prefetch of the next chunk's column ids,
+// more warps at fewer registers.  What bounds the kernel is the x* gather: an SM's L1 -> crossbar port takes about one
+// 32-byte sector per clock, and shrinking L1 (by using shared memory) shrinks the SM's outstanding-miss capacity.
 // ---------------------------------------------------------------------------------------------
-// tuning knobs (scripts/build_variants.sh builds A/B variants of the library with -D overrides)
+// tuning knob (scripts/build_variants.sh builds A/B variants of the library with -D overrides)
 #ifndef KTN_OPT_PASS
 #define KTN_OPT_PASS 16
 #endif
-#ifndef KTN_OPT_WARPS
-#define KTN_OPT_WARPS 16
-#endif
-#ifndef KTN_OPT_XCACHE
-#define KTN_OPT_XCACHE 0
-#endif
-#define KTN_FP_WARPS KTN_OPT_WARPS
+#define KTN_FP_WARPS 16
 #define KTN_FW_PASS KTN_OPT_PASS                          // selected lanes that build their cut at the same time (scratch cells per entry)
-#define KTN_FP_SCRATCH_BYTES (128 + KTN_FP_WARPS * KTN_FAM_REGS * KTN_FW_PASS * 8)   // [0,128): barrier of the x* fill
+#define KTN_FP_SMEM (128 + KTN_FP_WARPS * KTN_FAM_REGS * KTN_FW_PASS * 8)   // [0,128): per-warp ticket mailboxes; then the warps' cut scratch
 
 #ifdef KTN_OPT_TIMING
 // debug build only (scripts/build_variants.sh ... "-DKTN_OPT_TIMING"): per-phase warp cycles, summed over all warps
@@ -121,10 +114,10 @@ __device__ __forceinline__ uint32_t ldg_stream(const uint8_t* p) {
 }
 
 struct FamRow {     // row context of ktn_family.h: the chunk's SoA sections in global memory, lane offset applied
-    const double* C; const int32_t* cols; const uint8_t* rk; const double* X; const double* sx; int32_t xs; uint32_t nu;
+    const double* C; const int32_t* cols; const uint8_t* rk; const double* X; uint32_t nu;
     __device__ __forceinline__ double cst(uint32_t i) const { return ldg_stream(C + i * 32u); }
     __device__ __forceinline__ int32_t col(uint32_t u) const { return ldg_stream(cols + u * 32u); }
-    __device__ __forceinline__ double xat(int32_t c) const { return (KTN_OPT_XCACHE && c < xs) ? sx[c] : __ldg(X + c); }     // head of x*: shared memory
+    __device__ __forceinline__ double xat(int32_t c) const { return __ldg(X + c); }
     __device__ __forceinline__ double x(uint32_t u) const { return xat(col(u)); }
     __device__ __forceinline__ uint32_t rank(uint32_t u) const { return ldg_stream(rk + u * 32u); }     // streaming rows: one byte per u
     __device__ __forceinline__ uint64_t rankword() const { return ldg_stream(reinterpret_cast<const uint64_t*>(rk)); }
@@ -157,7 +150,7 @@ __device__ __forceinline__ const unsigned char* family_blob(const KtnRoundParams
 // One chunk.  N = 1..16: register-resident rows of exactly N unique variables (class blobs are contiguous and equally sized:
 // no descriptor); N = 0: streaming fallback (any count) through the chunk descriptor.
 template <int FAM, int N>
-__device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c, uint32_t lane, const double* sx, int32_t xs, double* scratch, unsigned int* ticket, uint32_t* next) {
+__device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c, uint32_t lane, double* scratch, unsigned int* ticket, uint32_t* next) {
     typedef KtnFamily<FAM> F;
     const uint32_t slotid = c * 32u + lane;
     uint32_t nu = (uint32_t)N;
@@ -165,7 +158,7 @@ __device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c
     if (N > 0 && p.cls_blob_stride[N > 0 ? N : 0] != 0xffffffffu) blob = family_blob(p, (uint32_t)N, c);
     else { const KtnChunkDesc cd = p.chunks[c]; nu = (uint32_t)cd.aux; blob = p.blob + cd.blob_off; }
     const FamRow r{reinterpret_cast<const double*>(blob) + lane, reinterpret_cast<const int32_t*>(blob + 512u * nu) + lane,
-                   blob + 640u * nu + (N > 0 ? lane * 8u : lane), p.x, sx, xs, nu};
+                   blob + 640u * nu + (N > 0 ? lane * 8u : lane), p.x, nu};
     constexpr int NR = N > 0 ? N : 1;
     KtnFamRegs<NR> v;
     double aux, g;
@@ -221,39 +214,22 @@ __device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c
 }
 
 template <int FAM>
-__device__ __forceinline__ void family_dispatch(const KtnRoundParams& p, uint32_t cls, uint32_t c, uint32_t lane, const double* sx, int32_t xs, double* scratch, unsigned int* ticket, uint32_t* next) {
+__device__ __forceinline__ void family_dispatch(const KtnRoundParams& p, uint32_t cls, uint32_t c, uint32_t lane, double* scratch, unsigned int* ticket, uint32_t* next) {
     switch (cls) {
-#define KTN_CASE(n) case n: family_chunk<FAM, n>(p, c, lane, sx, xs, scratch, ticket, next); break;
+#define KTN_CASE(n) case n: family_chunk<FAM, n>(p, c, lane, scratch, ticket, next); break;
         KTN_CASE(1) KTN_CASE(2) KTN_CASE(3) KTN_CASE(4) KTN_CASE(5) KTN_CASE(6) KTN_CASE(7) KTN_CASE(8)
         KTN_CASE(9) KTN_CASE(10) KTN_CASE(11) KTN_CASE(12) KTN_CASE(13) KTN_CASE(14) KTN_CASE(15) KTN_CASE(16)
 #undef KTN_CASE
-        default: family_chunk<FAM, 0>(p, c, lane, sx, xs, scratch, ticket, next); break;
+        default: family_chunk<FAM, 0>(p, c, lane, scratch, ticket, next); break;
     }
 }
 
 template <int FAM>
-__global__ void __launch_bounds__(KTN_FP_WARPS * 32, 1) ktn_family_kernel(const KtnRoundParams p, int32_t xs) {
+__global__ void __launch_bounds__(KTN_FP_WARPS * 32, 1) ktn_family_kernel(const KtnRoundParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     double* scratch = reinterpret_cast<double*>(smem + 128) + (size_t)(threadIdx.x >> 5) * (KTN_FAM_REGS * KTN_FW_PASS);
-    double* sx = reinterpret_cast<double*>(smem + KTN_FP_SCRATCH_BYTES);
     const uint32_t lane = threadIdx.x & 31u;
-    uint32_t* next = reinterpret_cast<uint32_t*>(smem + 16) + (threadIdx.x >> 5);       // per-warp mailbox of the next ticket
-    if (KTN_OPT_XCACHE && xs > 0) {
-        // head of x* -> shared memory: a handful of TMA bulk copies, one wait
-        uint64_t& xbar = *reinterpret_cast<uint64_t*>(smem);
-        if (threadIdx.x == 0) { mbar_init(&xbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const uint32_t total = (uint32_t)xs * 8u;
-            mbar_expect(&xbar, total);
-            for (uint32_t off = 0; off < total; off += 32768u) bulk_g2s(reinterpret_cast<unsigned char*>(sx) + off, reinterpret_cast<const unsigned char*>(p.x) + off, total - off < 32768u ? total - off : 32768u, &xbar);
-        }
-        uint32_t done = 0;
-        for (uint32_t spin = 0; !done; ++spin) {
-            asm volatile("{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\nselp.u32 %0, 1, 0, q;\n}" : "=r"(done) : "r"(smem_u32(&xbar)), "r"(0u) : "memory");
-            if (spin > (1u << 24)) __trap();
-        }
-    }
+    uint32_t* next = reinterpret_cast<uint32_t*>(smem) + (threadIdx.x >> 5);       // per-warp mailbox of the next ticket
     unsigned int* tickets = p.ticket + p.ticket_idx;
     const uint32_t my_n = lane < KTN_FAM_NCLS ? p.cls_begin[lane + 1] - p.cls_begin[lane] : 0u;     // lane k: chunks of class k
     uint32_t cls = 0;
@@ -285,7 +261,7 @@ __global__ void __launch_bounds__(KTN_FP_WARPS * 32, 1) ktn_family_kernel(const 
             cur = bcast(take(cls));
             continue;
         }
-        family_dispatch<FAM>(p, cls, p.cls_begin[cls] + cur, lane, sx, xs, scratch, &tickets[cls], next);   // draws the next ticket on the way
+        family_dispatch<FAM>(p, cls, p.cls_begin[cls] + cur, lane, scratch, &tickets[cls], next);   // draws the next ticket on the way
         KTN_T(tb);
         __syncwarp();
         cur = *reinterpret_cast<volatile uint32_t*>(next);
@@ -822,9 +798,9 @@ void ktn_launch_pack(const KtnRoundParams& p, unsigned char* sendbuf, int num_sm
 cudaError_t ktn_kernels_configure(int max_smem_optin) {
     cudaError_t e = cudaFuncSetAttribute(ktn_round_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, KTN_FP_SMEM);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, KTN_FP_SMEM);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(ktn_round_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
 }
@@ -861,7 +837,7 @@ extern "C" int ktn_debug_cycles(unsigned long long* out16, int reset) {
 #endif
 
 template <int FAM>
-static void launch_family(KtnRoundParams p, const KtnLaunchPlan& plan, uint32_t ticket_idx, int num_sms, int max_smem_optin, cudaStream_t stream) {
+static void launch_family(KtnRoundParams p, const KtnLaunchPlan& plan, uint32_t ticket_idx, int num_sms, cudaStream_t stream) {
     const uint32_t begin = plan.fam_begin[FAM], end = plan.fam_begin[FAM + 1];
     p.chunk_begin = begin; p.chunk_end = end; p.ticket_idx = ticket_idx;
     for (int k = 0; k <= KTN_FAM_NCLS; ++k) p.cls_begin[k] = plan.cls_begin[FAM][k];
@@ -869,14 +845,7 @@ static void launch_family(KtnRoundParams p, const KtnLaunchPlan& plan, uint32_t 
     uint32_t blocks = (uint32_t)num_sms;                       // persistent: one block per SM
     const uint32_t need = (end - begin + KTN_FP_WARPS - 1) / KTN_FP_WARPS;
     if (blocks > need) blocks = need;
-    // shared memory: the warps' scratch, then as much of the head of x* as fits
-    int64_t xs = ((int64_t)max_smem_optin - KTN_FP_SCRATCH_BYTES) / 8;
-    if (!KTN_OPT_XCACHE || xs < 0) xs = 0;
-    if (xs > p.num_var) xs = p.num_var;
-    xs &= ~(int64_t)1;                                         // bulk copies move multiples of 16 bytes
-    if (blocks < (uint32_t)num_sms / 4u) xs = 0;               // tiny launches: filling the cache would cost more than it saves
-    const size_t smem = (size_t)KTN_FP_SCRATCH_BYTES + 8 * (size_t)xs;
-    ktn_family_kernel<FAM><<<blocks, KTN_FP_WARPS * 32, smem, stream>>>(p, (int32_t)xs);
+    ktn_family_kernel<FAM><<<blocks, KTN_FP_WARPS * 32, KTN_FP_SMEM, stream>>>(p);
 }
 
 template <bool EVAL>
@@ -896,8 +865,8 @@ static int launch_eval_part(const KtnRoundParams& p0, const KtnLaunchPlan& plan,
         ktn_round_kernel<EVAL><<<blocks, wpb * 32, smem, stream>>>(p);
         ++launches;
     }
-    if (plan.fam_begin[KTN_FAM_LSE + 1] > plan.fam_begin[KTN_FAM_LSE]) { launch_family<KTN_FAM_LSE>(p, plan, KTN_TICKET_LSE, num_sms, max_smem_optin, stream); ++launches; }
-    if (plan.fam_begin[KTN_FAM_QUAD + 1] > plan.fam_begin[KTN_FAM_QUAD]) { launch_family<KTN_FAM_QUAD>(p, plan, KTN_TICKET_QUAD, num_sms, max_smem_optin, stream); ++launches; }
+    if (plan.fam_begin[KTN_FAM_LSE + 1] > plan.fam_begin[KTN_FAM_LSE]) { launch_family<KTN_FAM_LSE>(p, plan, KTN_TICKET_LSE, num_sms, stream); ++launches; }
+    if (plan.fam_begin[KTN_FAM_QUAD + 1] > plan.fam_begin[KTN_FAM_QUAD]) { launch_family<KTN_FAM_QUAD>(p, plan, KTN_TICKET_QUAD, num_sms, stream); ++launches; }
     if (plan.n_total > plan.n_regular) {
         p.chunk_begin = plan.n_regular; p.chunk_end = plan.n_total;
         uint32_t blocks = (plan.n_total - plan.n_regular + 3) / 4;
