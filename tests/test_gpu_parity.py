@@ -171,6 +171,13 @@ def test_zero_copy_view_matches_copy(oracle_lib, cuda_lib):
     assert_batches_identical(ho.separate(0.5 * x0), v2, "second view")
     ub0 = np.full(nr, g.max() + 1.0); hc.set_bounds(w.lb, ub0)
     assert hc.separate(x0, view=True).n_cuts == 0      # empty batch
+    # lean views (what KatanaGPUSeparator asks for): the LP's arrays are there, the diagnostics are not downloaded
+    from katana_jl_b200.binding import FLAG_LEAN_VIEW
+    hl = cuda_lib.create(flags=FLAG_LEAN_VIEW); hl.load(nv, w); hl.set_bounds(w.lb, ub)
+    vl = hl.separate(x0, view=True)
+    for f in ("row_id", "row_ptr", "col", "val", "lo", "hi"):
+        assert bits_equal(getattr(vl, f), getattr(ref, f)), f
+    assert len(vl.g) == len(vl.viol) == len(vl.bconst) == 0
 
 
 def test_many_rounds_keep_state_clean(oracle_lib, cuda_lib):
