@@ -157,7 +157,7 @@ def main():
     ap.add_argument("--workload", default="lse", choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=int, default=1000000, help="nonlinear rows per GPU (weak scaling)")
     ap.add_argument("--vars", type=int, default=100000)
-    ap.add_argument("--v", type=float, default=0.1, help="violated fraction of the rows at x*")
+    ap.add_argument("--violated", dest="v", type=float, default=0.1, help="violated fraction of the rows at x* (not --v: torchrun's own parser claims that prefix)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--topk", type=int, default=0, help="build extension: keep only the k most violated rows per round (0 = reference behaviour: all)")
