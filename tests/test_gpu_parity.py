@@ -238,6 +238,24 @@ def test_topk_ties_nan_and_errors(oracle_lib, cuda_lib):
             assert_batches_identical(bo, bc, f"topk {k} at {pt}")
 
 
+def test_empty_and_linear_only_problems(oracle_lib, cuda_lib):
+    """Edge cases of initialize! / the loop body: no constraints at all, and a model whose rows are all linear
+    (nlconstr_ixs empty, src/model.jl:115-122): a round is a no-op that reports zero cuts."""
+    x0, x1 = E.var(0), E.var(1)
+    empty = E.to_wire([], np.zeros(0), np.zeros(0), [])
+    ho, hc = both(oracle_lib, cuda_lib, 2, empty)
+    assert_batches_identical(ho.separate(np.array([1.0, 2.0])), hc.separate(np.array([1.0, 2.0])), "no rows")
+    assert hc.separate(np.array([1.0, 2.0]), view=True).n_cuts == 0
+    lin = E.to_wire([x0 + x1, E.const(2.0) * x0 - x1], [-np.inf, -np.inf], [-5.0, -5.0], [0, 0])
+    ho, hc = both(oracle_lib, cuda_lib, 2, lin)
+    pt = np.array([3.0, 4.0])
+    assert_batches_identical(ho.separate(pt), hc.separate(pt), "linear rows only")
+    assert hc.separate(pt).n_cuts == 0
+    rows = np.array([0, 1], np.int64)                       # ... but their rows can still be asked for (loadproblem!, src/model.jl:115-118)
+    assert_batches_identical(ho.gencut_rows(pt, rows, False), hc.gencut_rows(pt, rows, False), "gencut of linear rows")
+    assert bits_equal(ho.eval_g(pt), hc.eval_g(pt))
+
+
 def test_device_resident_round_and_counters(cuda_lib):
     import torch
     nv, nr = 2000, 50000
