@@ -255,13 +255,13 @@ static int enqueue_round(ktn_handle* h, const double* d_x, int mode, int do_roun
     if (e != cudaSuccess) return fail(h, KTN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     CK(h, cudaEventRecord(ev[2], h->stream));
     h->ring_head++;
-    CK(h, cudaMemcpyAsync(h->h_counts, h->counts.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-    h->round_pending = true; h->tm.rounds++;
+    h->round_pending = true; h->tm.rounds++;      // the counts are read back when somebody asks for them (finish_round): no copy between back-to-back rounds
     return KTN_OK;
 }
 
 static int finish_round(ktn_handle* h, int64_t* n_cuts, int64_t* nnz, int64_t* err_row) {
     if (!h->round_pending) return fail(h, KTN_ERR_USAGE, "no round is pending");
+    CK(h, cudaMemcpyAsync(h->h_counts, h->counts.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     h->round_pending = false; h->have_round = true;
     drain_ring(h, true);
