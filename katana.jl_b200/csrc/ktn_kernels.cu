@@ -613,22 +613,27 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
         if ((rl & 0x8000u) && (unsigned long long)i + 1ull == p.counts[2 + (epoch & 1u)]) { p.counts[0] = (unsigned long long)cidx; p.counts[1] = (unsigned long long)o; }
     }
     __syncthreads();
-    // expand: one thread per output entry, coalesced writes; the owning row is found by binary search in shared memory.
-    // Four entries per thread and step: all eight loads are in flight before the first store.
-    const uint32_t nent = (uint32_t)tb;
-    for (uint32_t e0 = threadIdx.x; e0 < nent; e0 += 4u * KTN_CBLOCK) {
-        uint32_t src[4]; int32_t cv[4]; double vv[4];
+    // expand: one thread per output entry, coalesced writes.  Every warp owns a contiguous range of the block's entries: one
+    // binary search (shared memory) finds the row of the range's first entry, after that each lane walks forward through the
+    // row offsets (a few steps per 32 entries).  Four steps are unrolled: all eight loads are in flight before the first store.
+    const uint32_t nent = (uint32_t)tb, lane = threadIdx.x & 31u;
+    const uint32_t per = ((nent + KTN_CBLOCK - 1) / KTN_CBLOCK) * 32u;         // entries per warp, a multiple of 32
+    const uint32_t wbeg = (threadIdx.x >> 5) * per, wend = wbeg + per < nent ? wbeg + per : nent;
+    if (wbeg < wend) {
+        uint32_t lo = 0, hi = ta;   // largest k with s_off[k] <= wbeg
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= wbeg) lo = mid; else hi = mid; }
+        for (uint32_t e0 = wbeg + lane; e0 - lane < wend; e0 += 128u) {
+            uint32_t src[4]; int32_t cv[4]; double vv[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t e = e0 + (uint32_t)k * KTN_CBLOCK;
-            uint32_t lo = 0, hi = ta;   // largest k with s_off[k] <= e
-            if (e < nent) { while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= e) lo = mid; else hi = mid; } }
-            src[k] = e < nent ? s_src[lo] + (e - s_off[lo]) : 0xffffffffu;
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t e = e0 + 32u * (uint32_t)k;
+                if (e < wend) { while (s_off[lo + 1] <= e) ++lo; src[k] = s_src[lo] + (e - s_off[lo]); } else src[k] = 0xffffffffu;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { cv[k] = src[k] != 0xffffffffu ? p.jac_col[src[k]] : 0; vv[k] = src[k] != 0xffffffffu ? p.stage_val[src[k]] : 0.0; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (src[k] != 0xffffffffu) { const unsigned long long e = nbase + e0 + 32u * (uint32_t)k; p.out_col[e] = cv[k]; p.out_val[e] = vv[k]; }
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { cv[k] = src[k] != 0xffffffffu ? p.jac_col[src[k]] : 0; vv[k] = src[k] != 0xffffffffu ? p.stage_val[src[k]] : 0.0; }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (src[k] != 0xffffffffu) { const unsigned long long e = nbase + e0 + (uint32_t)k * KTN_CBLOCK; p.out_col[e] = cv[k]; p.out_val[e] = vv[k]; }
     }
 }
 
