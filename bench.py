@@ -68,10 +68,16 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.004)
 
     def __enter__(self):
         if self.nv:
+            try:                            # first NVML queries are slow (lazy paths): take them before the timed region starts
+                nv = self.nv
+                nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM)
+                (nv.nvmlDeviceGetCurrentClocksEventReasons if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons)(self.dev)
+            except Exception:
+                pass
             self.t.start()
         return self
 
@@ -215,6 +221,10 @@ def main():
     for _ in range(args.warmup):
         step()
     st, n_cuts, nnz, err = h.sync_counts()
+    if world > 1:
+        h.sync_gathered()                  # warm-up covers the exchange's completion path too
+    import gc
+    gc.collect(); gc.disable()             # no collector pauses inside the timed loops
     t_before = h.timings()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -228,6 +238,10 @@ def main():
         barrier()
     ms_total = e0.elapsed_time(e1)
     t_after = h.timings()
+    exchange_desc = {"peer-push": "peer push: ktn_push_kernel stores every rank's packed cut blob into all ranks' receive arenas (CUDA IPC) over NVLink, "
+                                  "on its own stream beside the next round; NCCL bootstraps only",
+                     "nccl": "NCCL on its own stream, pipelined: sizes allgather, then ONE ncclAllGather of the packed cut blobs (slots of the largest blob)",
+                     "none": "none"}[h.exchange_transport() if world > 1 else "none"]
     if world > 1:
         t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -277,7 +291,7 @@ def main():
         "config": {"workload": f"{args.workload}: {desc}; m={rows} rows/GPU, n={nv} vars, violated fraction {args.v}, f_tol 1e-6",
                    "rows_per_gpu": rows, "num_var": nv, "violated_fraction": args.v, "topk": args.topk, "cuts_per_round_per_gpu": n_cuts, "cut_nnz_per_round_per_gpu": nnz,
                    "l2": f"no flush needed: one round streams {alg_round / 1e6:.0f} MB of inputs > 126 MB L2",
-                   "exchange": "none" if world == 1 else "NCCL on its own stream, pipelined one round deep: sizes allgather, then ONE ncclAllGather of the packed cut blobs (slots of the largest blob)"},
+                   "exchange": "none" if world == 1 else exchange_desc},
         "roofline": {"bound": "hbm", "kernel": "ktn_family_kernel (K1: evaluate g, test, Jacobian row, cut row; one launch per round)" if args.workload in ("lse", "qcqp") else "ktn_round_kernel (K1, tape interpreter)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_k1, "ms_per_launch": k1_ms,
                      "round": {"algorithmic_bytes": alg_round, "ms": k1_ms + k2_ms, "frac": alg_round / ((k1_ms + k2_ms) * 1e-3) / 1e9 / peak,

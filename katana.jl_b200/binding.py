@@ -71,6 +71,7 @@ _SIGS = {
     "ktn_set_row_offset": (C.c_int, [_P, C.c_int64]),
     "ktn_allgather_cuts_async": (C.c_int, [_P]),
     "ktn_sync_gathered": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ktn_exchange_transport": (C.c_int, [_P]),
     "ktn_fetch_gathered": (C.c_int, [_P] + [_P] * 9),
 }
 # exported by the CUDA library only (test / bench support, include/ktn.h bottom)
@@ -329,6 +330,9 @@ class Handle:
         nc, nz = C.c_int64(), C.c_int64()
         self._ck(self.dll.ktn_sync_gathered(self.h, C.byref(nc), C.byref(nz)), "ktn_sync_gathered")
         return nc.value, nz.value
+
+    def exchange_transport(self):
+        return {0: "none", 1: "nccl", 2: "peer-push"}[int(self.dll.ktn_exchange_transport(self.h))]
 
     def fetch_gathered(self):
         nc, nz = self.sync_gathered()

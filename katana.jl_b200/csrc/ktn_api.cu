@@ -12,6 +12,7 @@
 
 void ktn_comm_release(ktn_handle* h);
 int ktn_comm_launch_pending(ktn_handle* h);
+int ktn_comm_release_blob(ktn_handle* h, int idx);
 
 extern "C" const char* ktn_backend(void) { return "cuda"; }
 extern "C" const char* ktn_last_error(ktn_handle* h) { return h ? h->err.c_str() : "null handle"; }
@@ -19,7 +20,7 @@ extern "C" const char* ktn_last_error(ktn_handle* h) { return h ? h->err.c_str()
 static void free_problem(ktn_handle* h) {
     DevBuf* all[] = {&h->chunks, &h->shapes, &h->prog, &h->blob, &h->chunk_rows, &h->chunk_lb, &h->chunk_ub, &h->jac_ptr, &h->jac_col,
                      &h->row_lb, &h->row_ub, &h->x, &h->force, &h->g_row, &h->b_row, &h->sel, &h->stage_val, &h->big_scratch,
-                     &h->blk_cnt, &h->topk_key, &h->topk_state, &h->topk_eqcnt, &h->table, &h->out_row, &h->out_ptr, &h->out_col, &h->out_val, &h->out_lo, &h->out_hi, &h->out_g, &h->out_viol, &h->out_b};
+                     &h->blk_cnt, &h->topk_key, &h->topk_state, &h->topk_eqcnt, &h->table, &h->out_blob[0], &h->out_blob[1], &h->out_blob[2]};
     for (DevBuf* b : all) b->release();
     if (h->h_x) { cudaFreeHost(h->h_x); h->h_x = nullptr; }
     h->prob = KtnProblem();
@@ -163,8 +164,9 @@ extern "C" int ktn_load_end(ktn_handle* h) {
     CK(h, h->blk_cnt.alloc(16 * (size_t)h->blk_stride));
     CK(h, cudaMemset(h->blk_cnt.p, 0, 16 * (size_t)h->blk_stride));
     CK(h, upload(h->table, table));
-    CK(h, h->out_row.alloc(8 * (m + 1))); CK(h, h->out_ptr.alloc(8 * (m + 2))); CK(h, h->out_col.alloc(4 * (N + 1))); CK(h, h->out_val.alloc(8 * (N + 1)));
-    CK(h, h->out_lo.alloc(8 * (m + 1))); CK(h, h->out_hi.alloc(8 * (m + 1))); CK(h, h->out_g.alloc(8 * (m + 1))); CK(h, h->out_viol.alloc(8 * (m + 1))); CK(h, h->out_b.alloc(8 * (m + 1)));
+    h->out_cap = ((size_t)ktn_pack_layout(m, N).total + 127) / 128 * 128 + 128;      // every row selected
+    h->out_cur = 0; for (bool& b : h->blob_busy) b = false;
+    CK(h, h->out_blob[0].alloc(h->out_cap)); h->out_blob[1].release(); h->out_blob[2].release();     // [1], [2]: sharded handles, on first use
     CK(h, cudaMallocHost(&h->h_x, 8 * ((size_t)P.num_var + 1)));
     // the packed blob lives on the device now
     std::vector<uint8_t>().swap(P.blob);
@@ -222,8 +224,7 @@ KtnRoundParams ktn_make_params(ktn_handle* h, const double* d_x, int mode, int d
     p.counts = h->counts.as<unsigned long long>();
     p.row_offset = h->row_offset;
     p.table = h->table.as<unsigned char>(); p.table_bytes = h->table_bytes; p.table_prog_off = h->table_prog_off; p.epoch = h->epoch;
-    p.out_row = h->out_row.as<int64_t>(); p.out_ptr = h->out_ptr.as<int64_t>(); p.out_col = h->out_col.as<int32_t>(); p.out_val = h->out_val.as<double>();
-    p.out_lo = h->out_lo.as<double>(); p.out_hi = h->out_hi.as<double>(); p.out_g = h->out_g.as<double>(); p.out_viol = h->out_viol.as<double>(); p.out_b = h->out_b.as<double>();
+    p.out_blob = h->out_blob[h->out_cur].as<unsigned char>();
     return p;
 }
 
@@ -242,6 +243,11 @@ static void drain_ring(ktn_handle* h, bool all) {
 
 static int enqueue_round(ktn_handle* h, const double* d_x, int mode, int do_round) {
     { int rc = ktn_comm_launch_pending(h); if (rc) return rc; }       // sharded runs: the previous round's cut payload travels beside this round
+    if (h->comm) {      // the next of three cut blobs; the exchange that last read it (three rounds ago) must have finished
+        h->out_cur = (h->out_cur + 1) % 3;
+        if (!h->out_blob[h->out_cur].p) CK(h, h->out_blob[h->out_cur].alloc(h->out_cap));
+        { int rc = ktn_comm_release_blob(h, h->out_cur); if (rc) return rc; }
+    }
     h->epoch = (h->epoch % 0x3ffffff0u) + 1u;
     KtnRoundParams p = ktn_make_params(h, d_x, mode, do_round);
     cudaError_t e = cudaSuccess;
@@ -250,7 +256,11 @@ static int enqueue_round(ktn_handle* h, const double* d_x, int mode, int do_roun
     if (h->ring_head - h->ring_tail >= ktn_handle::RING) { CK(h, cudaEventSynchronize(h->ring[h->ring_tail % ktn_handle::RING][2])); drain_ring(h, false); }
     cudaEvent_t* ev = h->ring[h->ring_head % ktn_handle::RING];
     CK(h, cudaEventRecord(ev[0], h->stream));
-    int n = ktn_launch_round(p, make_plan(h), h->num_sms, h->max_smem, h->epoch, h->stream, ev[1], &e);
+    // peer-push exchange: the persistent K1 leaves the push kernel's SMs free, so that the push of the previous round starts at once
+    // beside this round instead of queueing behind K1's resident blocks (K1 owns every register of the SMs it runs on)
+    int sms = h->num_sms;
+    if (h->comm && h->px.on && h->px.reserve && sms > 2 * h->px.blocks) sms -= h->px.blocks;
+    int n = ktn_launch_round(p, make_plan(h), sms, h->max_smem, h->epoch, h->stream, ev[1], &e);
     h->tm.launches += n;
     if (e != cudaSuccess) return fail(h, KTN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     CK(h, cudaEventRecord(ev[2], h->stream));
@@ -266,6 +276,7 @@ static int finish_round(ktn_handle* h, int64_t* n_cuts, int64_t* nnz, int64_t* e
     h->round_pending = false; h->have_round = true;
     drain_ring(h, true);
     h->n_cuts = (int64_t)h->h_counts[0]; h->nnz_cuts = (int64_t)h->h_counts[1];
+    h->lay_cuts = (int64_t)h->h_counts[4]; h->lay_nnz = (int64_t)h->h_counts[5];
     h->err_row = h->h_counts[6] == ~0ull ? -1 : (int64_t)h->h_counts[6] - 1;
     if (n_cuts) *n_cuts = h->n_cuts;
     if (nnz) *nnz = h->nnz_cuts;
@@ -314,16 +325,18 @@ extern "C" int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, 
     if (h->round_pending) { int rc = finish_round(h, nullptr, nullptr, nullptr); if (rc < 0) return rc; }
     cudaSetDevice(h->device);
     const size_t nc = (size_t)h->n_cuts, nz = (size_t)h->nnz_cuts;
+    const KtnPackLayout S = ktn_pack_layout((unsigned long long)h->lay_cuts, (unsigned long long)h->lay_nnz);      // where K2 put the sections
+    const unsigned char* src = h->out_blob[h->out_cur].as<unsigned char>();
     CK(h, cudaEventRecord(h->ev2, h->stream));
-    if (row_id && nc) CK(h, cudaMemcpyAsync(row_id, h->out_row.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
-    if (row_ptr) { if (nc) CK(h, cudaMemcpyAsync(row_ptr, h->out_ptr.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream)); }
-    if (col && nz) CK(h, cudaMemcpyAsync(col, h->out_col.p, 4 * nz, cudaMemcpyDeviceToHost, h->stream));
-    if (val && nz) CK(h, cudaMemcpyAsync(val, h->out_val.p, 8 * nz, cudaMemcpyDeviceToHost, h->stream));
-    if (lo && nc) CK(h, cudaMemcpyAsync(lo, h->out_lo.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
-    if (hi && nc) CK(h, cudaMemcpyAsync(hi, h->out_hi.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
-    if (g && nc) CK(h, cudaMemcpyAsync(g, h->out_g.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
-    if (viol && nc) CK(h, cudaMemcpyAsync(viol, h->out_viol.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
-    if (bconst && nc) CK(h, cudaMemcpyAsync(bconst, h->out_b.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+    if (row_id && nc) CK(h, cudaMemcpyAsync(row_id, src + S.row_id, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+    if (row_ptr) { if (nc) CK(h, cudaMemcpyAsync(row_ptr, src + S.row_ptr, 8 * nc, cudaMemcpyDeviceToHost, h->stream)); }
+    if (col && nz) CK(h, cudaMemcpyAsync(col, src + S.col, 4 * nz, cudaMemcpyDeviceToHost, h->stream));
+    if (val && nz) CK(h, cudaMemcpyAsync(val, src + S.val, 8 * nz, cudaMemcpyDeviceToHost, h->stream));
+    if (lo && nc) CK(h, cudaMemcpyAsync(lo, src + S.lo, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+    if (hi && nc) CK(h, cudaMemcpyAsync(hi, src + S.hi, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+    if (g && nc) CK(h, cudaMemcpyAsync(g, src + S.g, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+    if (viol && nc) CK(h, cudaMemcpyAsync(viol, src + S.viol, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+    if (bconst && nc) CK(h, cudaMemcpyAsync(bconst, src + S.b, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaEventRecord(h->ev3, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     if (row_ptr) row_ptr[nc] = (int64_t)nz;   // the device array ends at the untruncated total
@@ -331,8 +344,9 @@ extern "C" int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, 
     return KTN_OK;
 }
 
-// Zero-copy download: nine device->pinned copies into ONE library-owned buffer (two buffers alternate, so a view stays
-// valid until the round after the next one), one synchronisation, no host-side copy.
+// Zero-copy download into ONE library-owned pinned buffer (two buffers alternate, so a view stays valid until the round
+// after the next one): the device blob already has the view's layout, so it comes down in one copy (lean view: two, around
+// the g | viol | b sections); one synchronisation, no host-side copy.
 extern "C" int ktn_fetch_cuts_view(ktn_handle* h, ktn_cut_view* out) {
     if (!h || !h->loaded || !out) return fail(h, KTN_ERR_USAGE, "no problem loaded");
     if (h->round_pending) { int rc = finish_round(h, nullptr, nullptr, nullptr); if (rc < 0) return rc; }
@@ -349,21 +363,31 @@ extern "C" int ktn_fetch_cuts_view(ktn_handle* h, ktn_cut_view* out) {
         CK(h, cudaMallocHost(&buf, want));
         cap = want;
     }
+    const KtnPackLayout S = ktn_pack_layout((unsigned long long)h->lay_cuts, (unsigned long long)h->lay_nnz);      // where K2 put the sections
+    const unsigned char* src = h->out_blob[h->out_cur].as<unsigned char>();
     CK(h, cudaEventRecord(h->ev2, h->stream));
-    if (nc) {
-        CK(h, cudaMemcpyAsync(buf + L.row_id, h->out_row.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaMemcpyAsync(buf + L.row_ptr, h->out_ptr.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaMemcpyAsync(buf + L.lo, h->out_lo.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaMemcpyAsync(buf + L.hi, h->out_hi.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
-        if (!lean) {
-            CK(h, cudaMemcpyAsync(buf + L.g, h->out_g.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
-            CK(h, cudaMemcpyAsync(buf + L.viol, h->out_viol.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
-            CK(h, cudaMemcpyAsync(buf + L.b, h->out_b.p, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+    if ((size_t)h->lay_cuts == nc && (size_t)h->lay_nnz == nz) {      // no truncation: source and view layouts coincide
+        if (!lean) { if (nc) CK(h, cudaMemcpyAsync(buf + L.row_id, src + S.row_id, L.total - L.row_id, cudaMemcpyDeviceToHost, h->stream)); }
+        else if (nc) {
+            CK(h, cudaMemcpyAsync(buf + L.row_id, src + S.row_id, L.g - L.row_id, cudaMemcpyDeviceToHost, h->stream));
+            if (nz) CK(h, cudaMemcpyAsync(buf + L.col, src + S.col, L.total - L.col, cudaMemcpyDeviceToHost, h->stream));
         }
-    }
-    if (nz) {
-        CK(h, cudaMemcpyAsync(buf + L.col, h->out_col.p, 4 * nz, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaMemcpyAsync(buf + L.val, h->out_val.p, 8 * nz, cudaMemcpyDeviceToHost, h->stream));
+    } else {                                                          // a non-finite cut truncated the round: section by section
+        if (nc) {
+            CK(h, cudaMemcpyAsync(buf + L.row_id, src + S.row_id, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+            CK(h, cudaMemcpyAsync(buf + L.row_ptr, src + S.row_ptr, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+            CK(h, cudaMemcpyAsync(buf + L.lo, src + S.lo, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+            CK(h, cudaMemcpyAsync(buf + L.hi, src + S.hi, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+            if (!lean) {
+                CK(h, cudaMemcpyAsync(buf + L.g, src + S.g, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+                CK(h, cudaMemcpyAsync(buf + L.viol, src + S.viol, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+                CK(h, cudaMemcpyAsync(buf + L.b, src + S.b, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+            }
+        }
+        if (nz) {
+            CK(h, cudaMemcpyAsync(buf + L.col, src + S.col, 4 * nz, cudaMemcpyDeviceToHost, h->stream));
+            CK(h, cudaMemcpyAsync(buf + L.val, src + S.val, 8 * nz, cudaMemcpyDeviceToHost, h->stream));
+        }
     }
     CK(h, cudaEventRecord(h->ev3, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));

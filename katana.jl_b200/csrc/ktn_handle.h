@@ -10,6 +10,9 @@
 #include "ktn_compile.h"
 #include "ktn_kernels.cuh"
 
+#define KTN_PX_MAX_RANKS 16
+#define KTN_PX_SLOTS 3
+#define KTN_PX_CTRL 4096u   // control page at the head of a receive arena: ack[rank] words
 #define KTN_LANE_LIMIT 1536u   // max per-lane shared-memory bytes of a regular (shared-memory staged) shape
 
 struct DevBuf {
@@ -34,7 +37,11 @@ struct ktn_handle {
     DevBuf chunks, shapes, prog, blob, chunk_rows, chunk_lb, chunk_ub, jac_ptr, jac_col, row_lb, row_ub;
     DevBuf topk_key, topk_state, topk_eqcnt;      // top-k selection (allocated when ktn_options.topk > 0)
     DevBuf x, force, g_row, b_row, sel, stage_val, big_scratch, ticket, blk_cnt, counts, table;
-    DevBuf out_row, out_ptr, out_col, out_val, out_lo, out_hi, out_g, out_viol, out_b;
+    // the round's cuts: one blob written by K2 (ktn_pack_layout).  Sharded handles rotate three blobs, so that the exchange of
+    // round i reads its blob while rounds i+1, i+2 write theirs; blob_ev = the exchange that last read a blob has finished
+    DevBuf out_blob[3]; int out_cur = 0; size_t out_cap = 0;
+    cudaEvent_t blob_ev[3] = {nullptr, nullptr, nullptr}; bool blob_busy[3] = {false, false, false};
+    int64_t lay_cuts = 0, lay_nnz = 0;      // untruncated totals of the last synced round: the arguments of the blob's layout
     double* h_x = nullptr;                 // pinned
     unsigned long long* h_counts = nullptr;  // pinned [8]
     int64_t n_cuts = 0, nnz_cuts = 0, err_row = -1;
@@ -47,14 +54,29 @@ struct ktn_handle {
     void* comm = nullptr; int nranks = 1, rank = 0;
     cudaStream_t comm_stream = nullptr;
     struct Exchange {
-        DevBuf sendbuf, gathered, all_counts;
-        unsigned long long* h_all_counts = nullptr;     // pinned [2 * nranks]
-        std::vector<int64_t> g_cuts, g_nnz, g_off;      // per rank, once the sizes are on the host
+        DevBuf gathered, all_counts;
+        unsigned long long* h_all_counts = nullptr;     // pinned [8 * nranks]: the blob headers of all ranks
+        std::vector<int64_t> g_cuts, g_nnz, g_off;      // per rank, once the headers are on the host
+        std::vector<int64_t> g_lay_cuts, g_lay_nnz, g_bytes;   // layout arguments and size of every rank's blob
+        int src_idx = 0;                                // which of the handle's cut blobs this exchange ships
         cudaEvent_t packed = nullptr, sizes = nullptr, done = nullptr;
         int state = 0;                                  // 0 idle, 1 sizes in flight (payload not launched), 2 payload in flight / complete
         int64_t gathered_bytes = 0;
     } xch[3];                                           // the payload of exchange k is launched when exchange k+2 is enqueued
     int xch_cur = 0;                                    // slot of the last ktn_allgather_cuts_async
+    // peer-push exchange (default when every rank can map every other rank's receive arena): the pack kernel's blob is stored
+    // straight into the peers' HBM over NVLink by ktn_push_kernel; NCCL only bootstraps it (and stays the fallback transport)
+    struct PeerExchange {
+        bool tried = false, on = false;
+        size_t slot_cap = 0;                            // bytes per (exchange slot, source rank)
+        DevBuf arena;                                   // control page + [KTN_PX_SLOTS][nranks][slot_cap], exported over CUDA IPC
+        DevBuf boot, hdr, ctr;                          // bootstrap buffer, gathered headers (+ error word), block counter + error word
+        unsigned char* peer[KTN_PX_MAX_RANKS] = {};     // every rank's arena as mapped here (own arena at [rank])
+        unsigned long long* h_boot = nullptr;           // pinned
+        unsigned long long seq = 0;                     // exchanges enqueued so far (1-based sequence number of the last one)
+        int blocks = 16;                                // grid of the push kernel (KTN_PUSH_BLOCKS)
+        bool reserve = true;                            // K1 leaves that many SMs free (KTN_PUSH_RESERVE=0 turns it off)
+    } px;
     int64_t row_offset = 0;
     cudaEvent_t evx0 = nullptr, evx1 = nullptr;
 };

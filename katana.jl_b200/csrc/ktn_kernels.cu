@@ -545,8 +545,8 @@ __device__ __forceinline__ void block_scan2(uint32_t& a, unsigned long long& b, 
 // One block = KTN_CBLOCK threads x KTN_CRPT consecutive rows per thread = KTN_CROWS rows.
 #define KTN_CRPT (KTN_CROWS / KTN_CBLOCK)
 __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRoundParams p, uint32_t nblocks, uint32_t epoch) {
-    __shared__ uint32_t s_cnt_base; __shared__ unsigned long long s_nnz_base;
-    __shared__ unsigned long long s_red[2][32];
+    __shared__ uint32_t s_cnt_base; __shared__ unsigned long long s_nnz_base, s_tot_n, s_tot_nz;
+    __shared__ unsigned long long s_red[4][32];
     __shared__ uint32_t s_off[KTN_CROWS + 1];        // exclusive nnz offsets of the block's selected rows (compact list)
     __shared__ uint32_t s_src[KTN_CROWS];            // first staging entry of each selected row (jac_ptr; the library caps nnz(J) at 2^32 - 1)
     __shared__ uint16_t s_rowl[KTN_CROWS];           // block-local row index of each selected row
@@ -556,37 +556,58 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
     uint32_t sv[KTN_CRPT];
     if (i0 + KTN_CRPT <= p.num_rows) { const uint4 q = *reinterpret_cast<const uint4*>(p.sel + i0); sv[0] = q.x; sv[1] = q.y; sv[2] = q.z; sv[3] = q.w; }
     else for (int r = 0; r < KTN_CRPT; ++r) sv[r] = (i0 + r < p.num_rows) ? p.sel[i0 + r] : 0u;
-    // output offset of this block = cuts / nnz of all blocks before it
+    // output offset of this block = cuts / nnz of all blocks before it; the totals of ALL blocks fix the blob's layout
     unsigned long long* bc = p.blk_cnt + (size_t)(epoch & 1u) * p.blk_stride;
     {
-        unsigned long long cb = 0, nb = 0;
-        for (uint32_t j = threadIdx.x; j < bid; j += KTN_CBLOCK) { const unsigned long long v = bc[j]; cb += v >> KTN_BLK_SHIFT; nb += v & KTN_BLK_NNZ_MASK; }
-        for (int o = 16; o > 0; o >>= 1) { cb += __shfl_xor_sync(0xffffffffu, cb, o); nb += __shfl_xor_sync(0xffffffffu, nb, o); }
-        if ((threadIdx.x & 31u) == 0) { s_red[0][threadIdx.x >> 5] = cb; s_red[1][threadIdx.x >> 5] = nb; }
+        unsigned long long cb = 0, nb = 0, ca = 0, na = 0;
+        for (uint32_t j = threadIdx.x; j < nblocks; j += KTN_CBLOCK) {
+            const unsigned long long v = bc[j], c = v >> KTN_BLK_SHIFT, n = v & KTN_BLK_NNZ_MASK;
+            ca += c; na += n;
+            if (j < bid) { cb += c; nb += n; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            cb += __shfl_xor_sync(0xffffffffu, cb, o); nb += __shfl_xor_sync(0xffffffffu, nb, o);
+            ca += __shfl_xor_sync(0xffffffffu, ca, o); na += __shfl_xor_sync(0xffffffffu, na, o);
+        }
+        if ((threadIdx.x & 31u) == 0) { const uint32_t w = threadIdx.x >> 5; s_red[0][w] = cb; s_red[1][w] = nb; s_red[2][w] = ca; s_red[3][w] = na; }
     }
     uint32_t a = 0; unsigned long long b = 0;
 #pragma unroll
     for (int r = 0; r < KTN_CRPT; ++r) { a += sv[r] ? 1u : 0u; b += sv[r] & ~KTN_SEL_ERRBIT; }
     uint32_t ta; unsigned long long tb;
     block_scan2(a, b, ta, tb);      // contains the barriers that publish s_red
+    unsigned long long* const hdr = reinterpret_cast<unsigned long long*>(p.out_blob);
     if (threadIdx.x < 32) {
-        unsigned long long cb = s_red[0][threadIdx.x], nb = s_red[1][threadIdx.x];
-        for (int o = 16; o > 0; o >>= 1) { cb += __shfl_xor_sync(0xffffffffu, cb, o); nb += __shfl_xor_sync(0xffffffffu, nb, o); }
+        const bool live = threadIdx.x < KTN_CBLOCK / 32;
+        unsigned long long cb = live ? s_red[0][threadIdx.x] : 0ull, nb = live ? s_red[1][threadIdx.x] : 0ull;
+        unsigned long long ca = live ? s_red[2][threadIdx.x] : 0ull, na = live ? s_red[3][threadIdx.x] : 0ull;
+        for (int o = 16; o > 0; o >>= 1) {
+            cb += __shfl_xor_sync(0xffffffffu, cb, o); nb += __shfl_xor_sync(0xffffffffu, nb, o);
+            ca += __shfl_xor_sync(0xffffffffu, ca, o); na += __shfl_xor_sync(0xffffffffu, na, o);
+        }
         if (threadIdx.x == 0) {
-            s_cnt_base = (uint32_t)cb; s_nnz_base = nb;
+            s_cnt_base = (uint32_t)cb; s_nnz_base = nb; s_tot_n = ca; s_tot_nz = na;
             p.blk_cnt[(size_t)((epoch & 1u) ^ 1u) * p.blk_stride + bid] = 0ull;     // re-arm the slot the NEXT round's K1 adds into
             if (bid == nblocks - 1) {   // totals, and re-arm the per-round device state
                 const unsigned long long err = p.counts[2 + (epoch & 1u)];   // written by this round's K1 only
                 p.counts[4] = cb + ta; p.counts[5] = nb + tb; p.counts[6] = err;
                 p.counts[2 + ((epoch & 1u) ^ 1u)] = ~0ull;                    // re-arm the slot the NEXT round's K1 uses
-                if (err == ~0ull) { p.counts[0] = cb + ta; p.counts[1] = nb + tb; }
-                p.out_ptr[cb + ta] = (int64_t)(nb + tb);
+                if (err == ~0ull) { p.counts[0] = cb + ta; p.counts[1] = nb + tb; hdr[0] = cb + ta; hdr[1] = nb + tb; }
+                const KtnPackLayout La = ktn_pack_layout(ca, na);
+                hdr[2] = err; hdr[3] = La.total; hdr[4] = (unsigned long long)p.row_offset; hdr[5] = ca; hdr[6] = na; hdr[7] = 0ull;
+                reinterpret_cast<int64_t*>(p.out_blob + La.row_ptr)[ca] = (int64_t)na;
             }
         }
         if (bid == nblocks - 1) for (uint32_t i = threadIdx.x; i < KTN_TICKETS; i += 32) p.ticket[i] = 0u;     // K1 is over: re-arm its work tickets
     }
     __syncthreads();
     const uint32_t cbase = s_cnt_base; const unsigned long long nbase = s_nnz_base;
+    const KtnPackLayout L = ktn_pack_layout(s_tot_n, s_tot_nz);
+    int64_t* const out_row = reinterpret_cast<int64_t*>(p.out_blob + L.row_id); int64_t* const out_ptr = reinterpret_cast<int64_t*>(p.out_blob + L.row_ptr);
+    double* const out_lo = reinterpret_cast<double*>(p.out_blob + L.lo); double* const out_hi = reinterpret_cast<double*>(p.out_blob + L.hi);
+    double* const out_g = reinterpret_cast<double*>(p.out_blob + L.g); double* const out_viol = reinterpret_cast<double*>(p.out_blob + L.viol);
+    double* const out_b = reinterpret_cast<double*>(p.out_blob + L.b);
+    int32_t* const out_col = reinterpret_cast<int32_t*>(p.out_blob + L.col); double* const out_val = reinterpret_cast<double*>(p.out_blob + L.val);
     // compact list of the block's selected rows: local row index (bit 15: non-finite flag) and nnz offset
 #pragma unroll
     for (int r = 0; r < KTN_CRPT; ++r) {
@@ -604,13 +625,13 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
         const double g = p.g_row[i], bcst = p.b_row[i], lb = p.row_lb[i], ub = p.row_ub[i];
         s_src[k] = (uint32_t)p.jac_ptr[i];
         const int64_t cidx = (int64_t)cbase + k, o = (int64_t)(nbase + s_off[k]);
-        p.out_row[cidx] = i + p.row_offset; p.out_ptr[cidx] = o;
-        p.out_lo[cidx] = lb - bcst; p.out_hi[cidx] = ub - bcst;     // src/model.jl:74-75
-        p.out_g[cidx] = g; p.out_b[cidx] = bcst;
+        out_row[cidx] = i + p.row_offset; out_ptr[cidx] = o;
+        out_lo[cidx] = lb - bcst; out_hi[cidx] = ub - bcst;     // src/model.jl:74-75
+        out_g[cidx] = g; out_b[cidx] = bcst;
         const double v1 = lb - g, v2 = g - ub;
-        p.out_viol[cidx] = (g == g) ? (v1 > v2 ? v1 : v2) : g;
+        out_viol[cidx] = (g == g) ? (v1 > v2 ? v1 : v2) : g;
         // the reference stops at the first non-finite cut (src/model.jl:278): cuts before it stand
-        if ((rl & 0x8000u) && (unsigned long long)i + 1ull == p.counts[2 + (epoch & 1u)]) { p.counts[0] = (unsigned long long)cidx; p.counts[1] = (unsigned long long)o; }
+        if ((rl & 0x8000u) && (unsigned long long)i + 1ull == p.counts[2 + (epoch & 1u)]) { p.counts[0] = (unsigned long long)cidx; p.counts[1] = (unsigned long long)o; hdr[0] = (unsigned long long)cidx; hdr[1] = (unsigned long long)o; }
     }
     __syncthreads();
     // expand: one thread per output entry, coalesced writes.  Every warp owns a contiguous range of the block's entries: one
@@ -632,7 +653,7 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
 #pragma unroll
             for (int k = 0; k < 4; ++k) { cv[k] = src[k] != 0xffffffffu ? p.jac_col[src[k]] : 0; vv[k] = src[k] != 0xffffffffu ? p.stage_val[src[k]] : 0.0; }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) if (src[k] != 0xffffffffu) { const unsigned long long e = nbase + e0 + 32u * (uint32_t)k; p.out_col[e] = cv[k]; p.out_val[e] = vv[k]; }
+            for (int k = 0; k < 4; ++k) if (src[k] != 0xffffffffu) { const unsigned long long e = nbase + e0 + 32u * (uint32_t)k; out_col[e] = cv[k]; out_val[e] = vv[k]; }
         }
     }
 }
@@ -771,34 +792,7 @@ __global__ void __launch_bounds__(KTN_CBLOCK) ktn_topk_demote_kernel(const KtnRo
     if (threadIdx.x == 0) p.blk_cnt[(size_t)(p.epoch & 1u) * p.blk_stride + bid] = (s_cnt << KTN_BLK_SHIFT) | s_nnz;     // replaces K1's count of ALL violated rows
 }
 
-// ---------------------------------------------------------------------------------------------
-// K3 (sharded runs only): pack the compacted cuts of this rank into ONE contiguous blob so the exchange over
-// NVLink is a single message per rank.  Layout (ktn_pack_layout): 64-byte header {n_cuts, nnz, first-error row + 1},
-// then row_id | row_ptr | lo | hi | g | viol | b | col | val, each section 16-byte aligned.
-// ---------------------------------------------------------------------------------------------
-template <class T> __device__ __forceinline__ void pack_copy(unsigned char* dst, const T* src, unsigned long long n) {
-    T* d = reinterpret_cast<T*>(dst);
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) d[i] = src[i];
-}
-__global__ void __launch_bounds__(256) ktn_pack_kernel(const KtnRoundParams p, unsigned char* out) {
-    const unsigned long long n = p.counts[0], nz = p.counts[1];
-    KtnPackLayout L = ktn_pack_layout(n, nz);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        unsigned long long* h = reinterpret_cast<unsigned long long*>(out);
-        h[0] = n; h[1] = nz; h[2] = p.counts[6]; h[3] = L.total; h[4] = (unsigned long long)p.row_offset;
-    }
-    pack_copy(out + L.row_id, p.out_row, n);
-    pack_copy(out + L.row_ptr, p.out_ptr, n + 1);
-    pack_copy(out + L.lo, p.out_lo, n); pack_copy(out + L.hi, p.out_hi, n);
-    pack_copy(out + L.g, p.out_g, n); pack_copy(out + L.viol, p.out_viol, n); pack_copy(out + L.b, p.out_b, n);
-    pack_copy(out + L.col, p.out_col, nz); pack_copy(out + L.val, p.out_val, nz);
-}
-
 }  // namespace
-
-void ktn_launch_pack(const KtnRoundParams& p, unsigned char* sendbuf, int num_sms, cudaStream_t stream) {
-    ktn_pack_kernel<<<num_sms * 4, 256, 0, stream>>>(p, sendbuf);
-}
 
 cudaError_t ktn_kernels_configure(int max_smem_optin) {
     cudaError_t e = cudaFuncSetAttribute(ktn_round_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);

@@ -54,8 +54,11 @@ struct KtnRoundParams {
     // [0] n_cuts [1] nnz (both truncated at the first non-finite row) [2],[3] first-error row + 1 of even / odd epochs
     // (~0 = none) [4] n_cuts_total [5] nnz_total [6] first-error row + 1 of the last round
     unsigned long long* counts;
-    int64_t* out_row; int64_t* out_ptr; int32_t* out_col; double* out_val;     // out_row: GLOBAL row ids (row_offset applied)
-    double* out_lo; double* out_hi; double* out_g; double* out_viol; double* out_b;
+    // K2 writes the round's cuts as ONE blob (ktn_pack_layout of the round's total counts): 64-byte header
+    // {n_cuts, nnz (both truncated at the first non-finite row), first-error row + 1 (~0 = none), blob bytes, row offset,
+    //  n_cuts_total, nnz_total (the layout's arguments), reserved}, then row_id (GLOBAL ids) | row_ptr | lo | hi | g | viol | b |
+    // col | val.  The host downloads it, and the sharded exchange ships it, as it lies.
+    unsigned char* out_blob;
 };
 
 // Chunk ranges of one problem: regular chunks sorted by (family, class), then the BIG chunks.
@@ -75,7 +78,7 @@ int ktn_launch_eval(const KtnRoundParams& p, const KtnLaunchPlan& plan, int num_
                     int max_smem_optin, cudaStream_t stream, cudaError_t* err);
 cudaError_t ktn_kernels_configure(int max_smem_optin);
 
-// packed per-rank cut blob exchanged between GPUs (byte offsets of the sections)
+// the cut blob K2 writes (byte offsets of the sections)
 struct KtnPackLayout { unsigned long long row_id, row_ptr, lo, hi, g, viol, b, col, val, total; };
 #if defined(__CUDACC__)
 __host__ __device__
@@ -94,5 +97,4 @@ inline KtnPackLayout ktn_pack_layout(unsigned long long n, unsigned long long nz
     L.total = o;
     return L;
 }
-void ktn_launch_pack(const KtnRoundParams& p, unsigned char* sendbuf, int num_sms, cudaStream_t stream);
 #endif

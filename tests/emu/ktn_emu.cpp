@@ -214,6 +214,7 @@ int ktn_comm_unique_id(void*) { return KTN_ERR_UNSUPPORTED; }
 int ktn_comm_init(ktn_handle*, int32_t, int32_t, const void*) { return KTN_ERR_UNSUPPORTED; }
 int ktn_set_row_offset(ktn_handle*, int64_t) { return KTN_ERR_UNSUPPORTED; }
 int ktn_allgather_cuts_async(ktn_handle*) { return KTN_ERR_UNSUPPORTED; }
+int ktn_exchange_transport(ktn_handle*) { return 0; }
 int ktn_sync_gathered(ktn_handle*, int64_t*, int64_t*) { return KTN_ERR_UNSUPPORTED; }
 int ktn_fetch_gathered(ktn_handle*, int64_t*, int64_t*, int32_t*, double*, double*, double*, double*, double*, double*) { return KTN_ERR_UNSUPPORTED; }
 }
