@@ -209,7 +209,7 @@ def main():
     def step():
         h.separate_device_async(dx.data_ptr())
         if world > 1:
-            h.allgather_cuts_async()       # pack + sizes now, payload (grouped broadcasts over NVLink) overlapped with the next round
+            h.allgather_cuts_async()       # the push kernel (or NCCL) ships the round's cut blob beside the next round
 
     def barrier():
         torch.cuda.synchronize()

@@ -200,7 +200,7 @@ int ktn_set_row_offset(ktn_handle* h, int64_t first_global_row);
 int ktn_allgather_cuts_async(ktn_handle* h);
 int ktn_sync_gathered(ktn_handle* h, int64_t* total_cuts, int64_t* total_nnz);
 /* Transport the exchange runs on, decided collectively at the first ktn_allgather_cuts_async: 0 = not sharded / not decided yet,
- * 1 = NCCL all-gather, 2 = peer push (the pack kernel's blob is stored into every rank's receive arena over NVLink by a CUDA
+ * 1 = NCCL all-gather, 2 = peer push (the round's cut blob is stored into every rank's receive arena over NVLink by a CUDA
  * kernel; arenas are shared through CUDA IPC).  KTN_EXCHANGE=nccl in the environment of any rank forces 1 on all ranks. */
 int ktn_exchange_transport(ktn_handle* h);
 int ktn_fetch_gathered(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val,
