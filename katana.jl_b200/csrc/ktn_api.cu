@@ -416,10 +416,13 @@ extern "C" int ktn_eval_g(ktn_handle* h, const double* x, double* g_out) {
     int rc = upload_x(h, x); if (rc) return rc;
     KtnRoundParams p = ktn_make_params(h, h->x.as<double>(), KTN_MODE_SEPARATE, 0);
     cudaError_t e = cudaSuccess;
+    CK(h, cudaEventRecord(h->ev2, h->stream));
     h->tm.launches += ktn_launch_eval(p, make_plan(h), h->num_sms, h->max_smem, h->stream, &e);
     if (e != cudaSuccess) return fail(h, KTN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    CK(h, cudaEventRecord(h->ev3, h->stream));
     CK(h, cudaMemcpyAsync(g_out, h->g_row.p, 8 * (size_t)h->prob.num_constr, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev2, h->ev3) == cudaSuccess) h->tm.eval_ms = ms;      // the evaluation kernels alone
     return KTN_OK;
 }
 

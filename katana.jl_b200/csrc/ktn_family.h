@@ -22,6 +22,9 @@
 #include "ktn_interp.h"
 
 #define KTN_FAM_DMAX 1.7976931348623157e308
+#ifndef KTN_FWD_GROUP
+#define KTN_FWD_GROUP 8            // terms in flight per row in the evaluation-only forward pass
+#endif
 
 template <int N> struct KtnFamRegs { double p0[N], p1[N], x[N]; };   // LSE: c, exp value;  QUAD: a, b
 
@@ -54,6 +57,36 @@ template <> struct KtnFamily<KTN_FAM_LSE> {
         aux = acc;
         return ktn_log(acc);
     }
+    // evaluation only (ktn_eval_g): the same operations in the same order as forward<N>, but the terms are loaded and
+    // consumed in groups of KTN_FWD_GROUP, so a row never holds more than one group in registers.  `hook` runs once, behind
+    // the first group's loads (the kernel draws its next work ticket there).
+    template <int N, class R, class H> static KTN_HDM double forward_only(const R& r, H hook) {
+        double acc = 0.0;
+#pragma unroll
+        for (int u0 = 0; u0 < N; u0 += KTN_FWD_GROUP) {
+            double a[KTN_FWD_GROUP], e[KTN_FWD_GROUP];
+            {
+                double c[KTN_FWD_GROUP], d[KTN_FWD_GROUP]; int32_t col[KTN_FWD_GROUP];
+#pragma unroll
+                for (int k = 0; k < KTN_FWD_GROUP; ++k) if (u0 + k < N) { c[k] = r.cst(2 * (u0 + k)); d[k] = r.cst(2 * (u0 + k) + 1); col[k] = r.col(u0 + k); }
+                if (u0 == 0) hook();
+#pragma unroll
+                for (int k = 0; k < KTN_FWD_GROUP; ++k) if (u0 + k < N) a[k] = arg(c[k], d[k], r.xat(col[k]));
+            }
+            bool slow = false;
+#pragma unroll
+            for (int k = 0; k < KTN_FWD_GROUP; ++k) if (u0 + k < N) e[k] = ktn_exp_fast(a[k]);
+#pragma unroll
+            for (int k = 0; k < KTN_FWD_GROUP; ++k) if (u0 + k < N) slow = slow || !ktn_exp_is_fast(a[k]);
+            if (slow) {
+#pragma unroll
+                for (int k = 0; k < KTN_FWD_GROUP; ++k) if (u0 + k < N) if (!ktn_exp_is_fast(a[k])) e[k] = ktn_exp_slow(a[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < KTN_FWD_GROUP; ++k) if (u0 + k < N) acc = acc + e[k];
+        }
+        return ktn_log(acc);
+    }
     static KTN_HDM double adjoint(double aux) { return revmul(1.0, 1.0 / aux); }                  // KR_ONE; KR_MULRCP S
     static KTN_HDM double jac(double adj, double c, double e, double) { return 0.0 + revmul(revmul(adj, e), c); }
     static KTN_HDM double jac_plain(double adj, double c, double e, double) { return 0.0 + (adj * e) * c; }
@@ -83,6 +116,29 @@ template <> struct KtnFamily<KTN_FAM_QUAD> {
 #pragma unroll
         for (int u = 0; u < N; ++u) acc = acc + r.p1[u] * r.x[u];
         aux = 0.0;
+        return acc;
+    }
+    template <int N, class R, class H> static KTN_HDM double forward_only(const R& r, H hook) {      // see KtnFamily<KTN_FAM_LSE>
+        double x[N], acc = 0.0;
+#pragma unroll
+        for (int u0 = 0; u0 < N; u0 += KTN_FWD_GROUP) {
+            double a[KTN_FWD_GROUP]; int32_t col[KTN_FWD_GROUP];
+#pragma unroll
+            for (int k = 0; k < KTN_FWD_GROUP; ++k) if (u0 + k < N) { a[k] = r.cst(u0 + k); col[k] = r.col(u0 + k); }
+            if (u0 == 0) hook();
+#pragma unroll
+            for (int k = 0; k < KTN_FWD_GROUP; ++k) if (u0 + k < N) x[u0 + k] = r.xat(col[k]);
+#pragma unroll
+            for (int k = 0; k < KTN_FWD_GROUP; ++k) if (u0 + k < N) acc = acc + (x[u0 + k] * x[u0 + k]) * a[k];
+        }
+#pragma unroll
+        for (int u0 = 0; u0 < N; u0 += KTN_FWD_GROUP) {
+            double b[KTN_FWD_GROUP];
+#pragma unroll
+            for (int k = 0; k < KTN_FWD_GROUP; ++k) if (u0 + k < N) b[k] = r.cst(N + u0 + k);
+#pragma unroll
+            for (int k = 0; k < KTN_FWD_GROUP; ++k) if (u0 + k < N) acc = acc + b[k] * x[u0 + k];
+        }
         return acc;
     }
     static KTN_HDM double adjoint(double) { return 1.0; }                                         // KR_ONE

@@ -86,6 +86,9 @@ __device__ __forceinline__ void count_selected(const KtnRoundParams& p, unsigned
 #define KTN_OPT_PASS 16
 #endif
 #define KTN_FP_WARPS 16
+#ifndef KTN_FWD_BLOCKS
+#define KTN_FWD_BLOCKS 2                                    // blocks per SM of the evaluation-only instantiation
+#endif
 #define KTN_FW_PASS KTN_OPT_PASS                          // selected lanes that build their cut at the same time (scratch cells per entry)
 #define KTN_FP_SMEM (128 + KTN_FP_WARPS * KTN_FAM_REGS * KTN_FW_PASS * 8)   // [0,128): per-warp ticket mailboxes; then the warps' cut scratch
 
@@ -149,7 +152,9 @@ __device__ __forceinline__ const unsigned char* family_blob(const KtnRoundParams
 
 // One chunk.  N = 1..16: register-resident rows of exactly N unique variables (class blobs are contiguous and equally sized:
 // no descriptor); N = 0: streaming fallback (any count) through the chunk descriptor.
-template <int FAM, int N>
+// FWD: evaluation only (ktn_eval_g), compiled without the cut path: the row's registers die as they are used, the kernel needs
+// half the registers and runs two blocks per SM.
+template <int FAM, int N, bool FWD>
 __device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c, uint32_t lane, double* scratch, unsigned int* ticket, uint32_t* next) {
     typedef KtnFamily<FAM> F;
     const uint32_t slotid = c * 32u + lane;
@@ -163,7 +168,10 @@ __device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c
     KtnFamRegs<NR> v;
     double aux, g;
     KTN_T(t0);
-    if constexpr (N > 0) {
+    if constexpr (N > 0 && FWD) {
+        g = F::template forward_only<NR>(r, [&]() { if (lane == 0) *next = atomicAdd(ticket, 1u); });
+        aux = 0.0;
+    } else if constexpr (N > 0) {
         int32_t col[NR];
         ktn_family_load<FAM, NR>(r, v, col);
         // the warp's next ticket is drawn HERE, behind the row's loads, and parked in shared memory: its round trip overlaps
@@ -175,6 +183,7 @@ __device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c
         g = F::forward_stream(r, aux);
     }
     const int32_t row = ldg_stream(p.chunk_rows + slotid);
+    if constexpr (FWD) { if (row >= 0) p.g_row[row] = g; return; }
     double lb = 0.0, ub = 0.0;
     if (p.mode != KTN_MODE_EVAL) { lb = ldg_stream(p.chunk_lb + slotid); ub = ldg_stream(p.chunk_ub + slotid); }
 #ifdef KTN_OPT_TIMING
@@ -213,19 +222,19 @@ __device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c
     }
 }
 
-template <int FAM>
+template <int FAM, bool FWD>
 __device__ __forceinline__ void family_dispatch(const KtnRoundParams& p, uint32_t cls, uint32_t c, uint32_t lane, double* scratch, unsigned int* ticket, uint32_t* next) {
     switch (cls) {
-#define KTN_CASE(n) case n: family_chunk<FAM, n>(p, c, lane, scratch, ticket, next); break;
+#define KTN_CASE(n) case n: family_chunk<FAM, n, FWD>(p, c, lane, scratch, ticket, next); break;
         KTN_CASE(1) KTN_CASE(2) KTN_CASE(3) KTN_CASE(4) KTN_CASE(5) KTN_CASE(6) KTN_CASE(7) KTN_CASE(8)
         KTN_CASE(9) KTN_CASE(10) KTN_CASE(11) KTN_CASE(12) KTN_CASE(13) KTN_CASE(14) KTN_CASE(15) KTN_CASE(16)
 #undef KTN_CASE
-        default: family_chunk<FAM, 0>(p, c, lane, scratch, ticket, next); break;
+        default: family_chunk<FAM, 0, FWD>(p, c, lane, scratch, ticket, next); break;
     }
 }
 
-template <int FAM>
-__global__ void __launch_bounds__(KTN_FP_WARPS * 32, 1) ktn_family_kernel(const KtnRoundParams p) {
+template <int FAM, bool FWD>
+__global__ void __launch_bounds__(KTN_FP_WARPS * 32, FWD ? KTN_FWD_BLOCKS : 1) ktn_family_kernel(const KtnRoundParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     double* scratch = reinterpret_cast<double*>(smem + 128) + (size_t)(threadIdx.x >> 5) * (KTN_FAM_REGS * KTN_FW_PASS);
     const uint32_t lane = threadIdx.x & 31u;
@@ -261,7 +270,7 @@ __global__ void __launch_bounds__(KTN_FP_WARPS * 32, 1) ktn_family_kernel(const 
             cur = bcast(take(cls));
             continue;
         }
-        family_dispatch<FAM>(p, cls, p.cls_begin[cls] + cur, lane, scratch, &tickets[cls], next);   // draws the next ticket on the way
+        family_dispatch<FAM, FWD>(p, cls, p.cls_begin[cls] + cur, lane, scratch, &tickets[cls], next);   // draws the next ticket on the way
         KTN_T(tb);
         __syncwarp();
         cur = *reinterpret_cast<volatile uint32_t*>(next);
@@ -797,9 +806,9 @@ __global__ void __launch_bounds__(KTN_CBLOCK) ktn_topk_demote_kernel(const KtnRo
 cudaError_t ktn_kernels_configure(int max_smem_optin) {
     cudaError_t e = cudaFuncSetAttribute(ktn_round_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, KTN_FP_SMEM);
+    e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_LSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KTN_FP_SMEM);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, KTN_FP_SMEM);
+    e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_QUAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KTN_FP_SMEM);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(ktn_round_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
 }
@@ -835,16 +844,16 @@ extern "C" int ktn_debug_cycles(unsigned long long* out16, int reset) {
 }
 #endif
 
-template <int FAM>
+template <int FAM, bool FWD>
 static void launch_family(KtnRoundParams p, const KtnLaunchPlan& plan, uint32_t ticket_idx, int num_sms, cudaStream_t stream) {
     const uint32_t begin = plan.fam_begin[FAM], end = plan.fam_begin[FAM + 1];
     p.chunk_begin = begin; p.chunk_end = end; p.ticket_idx = ticket_idx;
     for (int k = 0; k <= KTN_FAM_NCLS; ++k) p.cls_begin[k] = plan.cls_begin[FAM][k];
     for (int k = 0; k < KTN_FAM_NCLS; ++k) { p.cls_blob_off[k] = plan.cls_blob_off[FAM][k]; p.cls_blob_stride[k] = plan.cls_blob_stride[FAM][k]; }
-    uint32_t blocks = (uint32_t)num_sms;                       // persistent: one block per SM
+    uint32_t blocks = (uint32_t)num_sms * (FWD ? KTN_FWD_BLOCKS : 1);      // persistent: one block per SM (evaluation only: two)
     const uint32_t need = (end - begin + KTN_FP_WARPS - 1) / KTN_FP_WARPS;
     if (blocks > need) blocks = need;
-    ktn_family_kernel<FAM><<<blocks, KTN_FP_WARPS * 32, KTN_FP_SMEM, stream>>>(p);
+    ktn_family_kernel<FAM, FWD><<<blocks, KTN_FP_WARPS * 32, FWD ? 128 : KTN_FP_SMEM, stream>>>(p);
 }
 
 template <bool EVAL>
@@ -864,8 +873,8 @@ static int launch_eval_part(const KtnRoundParams& p0, const KtnLaunchPlan& plan,
         ktn_round_kernel<EVAL><<<blocks, wpb * 32, smem, stream>>>(p);
         ++launches;
     }
-    if (plan.fam_begin[KTN_FAM_LSE + 1] > plan.fam_begin[KTN_FAM_LSE]) { launch_family<KTN_FAM_LSE>(p, plan, KTN_TICKET_LSE, num_sms, stream); ++launches; }
-    if (plan.fam_begin[KTN_FAM_QUAD + 1] > plan.fam_begin[KTN_FAM_QUAD]) { launch_family<KTN_FAM_QUAD>(p, plan, KTN_TICKET_QUAD, num_sms, stream); ++launches; }
+    if (plan.fam_begin[KTN_FAM_LSE + 1] > plan.fam_begin[KTN_FAM_LSE]) { launch_family<KTN_FAM_LSE, EVAL>(p, plan, KTN_TICKET_LSE, num_sms, stream); ++launches; }
+    if (plan.fam_begin[KTN_FAM_QUAD + 1] > plan.fam_begin[KTN_FAM_QUAD]) { launch_family<KTN_FAM_QUAD, EVAL>(p, plan, KTN_TICKET_QUAD, num_sms, stream); ++launches; }
     if (plan.n_total > plan.n_regular) {
         p.chunk_begin = plan.n_regular; p.chunk_end = plan.n_total;
         uint32_t blocks = (plan.n_total - plan.n_regular + 3) / 4;

@@ -68,7 +68,10 @@ static void run_family_row(ktn_handle* h, const KtnChunkDesc& cd, uint32_t lane,
     constexpr int NR = N > 0 ? N : 1;
     KtnFamRegs<NR> v;
     double aux, g;
-    if constexpr (N > 0) { int32_t col[NR]; ktn_family_load<FAM, NR>(r, v, col); g = ktn_family_eval<FAM, NR>(r, v, col, aux); } else g = KtnFamily<FAM>::forward_stream(r, aux);
+    if constexpr (N > 0) {
+        if (mode == 2) { g = KtnFamily<FAM>::template forward_only<NR>(r, []() {}); aux = 0.0; }       // the evaluation-only instantiation of the kernel
+        else { int32_t col[NR]; ktn_family_load<FAM, NR>(r, v, col); g = ktn_family_eval<FAM, NR>(r, v, col, aux); }
+    } else g = KtnFamily<FAM>::forward_stream(r, aux);
     h->g_row[row] = g;
     if (mode == 2) return;
     const bool selected = mode == 1 ? forced : !((g >= lb - h->opt.f_tol) && (g <= ub + h->opt.f_tol));
