@@ -104,6 +104,8 @@ def test_error_row_truncation(oracle_lib, cuda_lib):
     bo, bc = ho.separate(np.zeros(3)), hc.separate(np.zeros(3))
     assert bo.status == KTN_NUMERIC_NONFINITE and bo.err_row == 40 and bo.n_cuts == 40
     assert_batches_identical(bo, bc)
+    # the same truncated round through the zero-copy view: K2 laid the blob out for ALL selected rows, the view holds the first 40
+    assert_batches_identical(bo, hc.separate(np.zeros(3), view=True), "view of a truncated round")
     assert_batches_identical(ho.separate(np.ones(3)), hc.separate(np.ones(3)))    # and the state re-arms for the next round
 
 
