@@ -1,6 +1,6 @@
 """A/B timing of library variants: K1 / K2 device times of one separation round per workload.  Run under gpurun:
 python scripts/ab_time.py build/variants/libktn_a.so build/variants/libktn_b.so ..."""
-import os, sys
+import hashlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from katana_jl_b200.binding import KtnLibrary
@@ -17,7 +17,12 @@ for path in sys.argv[1:]:
         w, x0 = data[(kind, nv, nr)]
         h = P.create(); h.load(nv, w)
         g = h.eval_g(x0)
+        ev = []
+        for _ in range(6):
+            h.eval_g(x0); ev.append(h.timings()["eval_ms"])
         h.set_bounds(w.lb, np.full(nr, np.quantile(g, 1 - v)))
+        b = h.separate(x0)        # results must not depend on the variant: compare the digests across the lines
+        digest = hashlib.sha1(g.tobytes() + b.row_id.tobytes() + b.col.tobytes() + b.val.tobytes() + b.lo.tobytes() + b.hi.tobytes()).hexdigest()[:10]
         k1, k2 = [], []
         dbg = getattr(P.dll, "ktn_debug_cycles", None) if hasattr(P.dll, "ktn_debug_cycles") else None
         import ctypes
@@ -25,7 +30,7 @@ for path in sys.argv[1:]:
         for it in range(12):
             st, nc, nz, er = h.separate(x0, fetch=False)
             tm = h.timings(); k1.append(tm["eval_ms"]); k2.append(tm["compact_ms"])
-        out.append(f"{name} v={v}: K1 {1e3 * np.median(k1[2:]):.1f} us (min {1e3 * min(k1):.1f}) K2 {1e3 * np.median(k2[2:]):.1f} us cuts {nc}")
+        out.append(f"{name} v={v}: K1 {1e3 * np.median(k1[2:]):.1f} us (min {1e3 * min(k1):.1f}) K2 {1e3 * np.median(k2[2:]):.1f} us cuts {nc} eval-only {1e3 * np.median(ev[2:]):.1f} us sha {digest}")
         if dbg:
             arr = (ctypes.c_ulonglong * 16)(); dbg(arr, 1); a = [x / 12.0 for x in arr]
             nch = max(a[4], 1)
