@@ -13,6 +13,7 @@
 void ktn_comm_release(ktn_handle* h);
 int ktn_comm_launch_pending(ktn_handle* h);
 int ktn_comm_release_blob(ktn_handle* h, int idx);
+void ktn_comm_plan_blocks(ktn_handle* h);
 
 extern "C" const char* ktn_backend(void) { return "cuda"; }
 extern "C" const char* ktn_last_error(ktn_handle* h) { return h ? h->err.c_str() : "null handle"; }
@@ -258,6 +259,7 @@ static int enqueue_round(ktn_handle* h, const double* d_x, int mode, int do_roun
     CK(h, cudaEventRecord(ev[0], h->stream));
     // peer-push exchange: the persistent K1 leaves the push kernel's SMs free, so that the push of the previous round starts at once
     // beside this round instead of queueing behind K1's resident blocks (K1 owns every register of the SMs it runs on)
+    ktn_comm_plan_blocks(h);
     int sms = h->num_sms;
     if (h->comm && h->px.on && h->px.reserve && sms > 2 * h->px.blocks) sms -= h->px.blocks;
     int n = ktn_launch_round(p, make_plan(h), sms, h->max_smem, h->epoch, h->stream, ev[1], &e);

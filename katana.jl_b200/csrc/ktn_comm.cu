@@ -238,7 +238,7 @@ static int peer_setup(ktn_handle* h, size_t my_cap) {
     const int R = h->nranks;
     const char* ex = getenv("KTN_EXCHANGE");
     const char* pb = getenv("KTN_PUSH_BLOCKS");
-    if (pb && atoi(pb) > 0) px.blocks = atoi(pb);
+    if (pb && atoi(pb) > 0) { px.blocks = atoi(pb); px.blocks_fixed = true; }
     { const char* rs = getenv("KTN_PUSH_RESERVE"); if (rs) px.reserve = atoi(rs) != 0; }
     CK(h, px.boot.alloc(128 + 128 * (size_t)R)); CK(h, cudaMallocHost(&px.h_boot, 128 * (size_t)R));
     std::vector<unsigned char> all(128 * (size_t)R);
@@ -401,6 +401,22 @@ extern "C" int ktn_allgather_cuts_async(ktn_handle* h) {
 int ktn_comm_launch_pending(ktn_handle* h) {
     if (!h->comm || h->px.on) return KTN_OK;
     return launch_payload(h, h->xch[(h->xch_cur + 2) % 3]);       // the slot used before the previous one
+}
+
+// Called by the round launcher (peer-push transport) before it sizes K1's grid: how many SMs the push kernel gets.  A push block
+// moves about 3 MB in the time of one K1 (measured: 16 blocks hide 44 MB at 2 GPUs, and 176 MB take 350 us at 8 GPUs =
+// ~30 GB/s per SM), so the grid follows the volume the last synced round produced: enough blocks to finish within a round,
+// few enough not to starve K1 when there is little to send.
+void ktn_comm_plan_blocks(ktn_handle* h) {
+    ktn_handle::PeerExchange& px = h->px;
+    if (!h->comm || !px.on || px.blocks_fixed || !h->have_round) return;
+    const double out = (double)ktn_pack_layout((unsigned long long)h->lay_cuts, (unsigned long long)h->lay_nnz).total * (double)h->nranks;
+    int b = (int)(out / 3.0e6) + 1;
+    const int hi = h->num_sms / 3 < 48 ? h->num_sms / 3 : 48;
+    if (b < 8) b = 8;
+    if (b > hi) b = hi;
+    if (b < 1) b = 1;
+    px.blocks = b;
 }
 
 // Called by the round launcher before K2 may overwrite cut blob `idx`: whatever exchange still has to read it goes first.

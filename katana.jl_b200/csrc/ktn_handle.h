@@ -74,7 +74,8 @@ struct ktn_handle {
         unsigned char* peer[KTN_PX_MAX_RANKS] = {};     // every rank's arena as mapped here (own arena at [rank])
         unsigned long long* h_boot = nullptr;           // pinned
         unsigned long long seq = 0;                     // exchanges enqueued so far (1-based sequence number of the last one)
-        int blocks = 16;                                // grid of the push kernel (KTN_PUSH_BLOCKS)
+        int blocks = 16;                                // grid of the push kernel: KTN_PUSH_BLOCKS, else sized per round (ktn_comm_plan_blocks)
+        bool blocks_fixed = false;
         bool reserve = true;                            // K1 leaves that many SMs free (KTN_PUSH_RESERVE=0 turns it off)
     } px;
     int64_t row_offset = 0;
