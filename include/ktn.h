@@ -72,7 +72,9 @@ typedef struct ktn_handle ktn_handle;
  * src/solver.jl:34-43): f_tol (src/model.jl:273) and cut_coef_rng (src/model.jl:276).
  * topk is a build extension: 0 = every violated row becomes a cut (reference behaviour); k > 0 = of the violated rows only
  * the k ranked first by (NaN first, violation max(lb - g, g - ub) descending, row index ascending) become cuts, still emitted
- * in ascending row order; the first non-finite row among THOSE ends the batch.  Not available on sharded handles. */
+ * in ascending row order; the first non-finite row among THOSE ends the batch.  On a sharded handle the selection is LOCAL to the rank's rows: the
+ * union of the ranks' selections contains the global top-k, which is one deterministic merge of the gathered batch away
+ * (katana.jl_b200/sharding.py merge_topk). */
 typedef struct ktn_options {
     int32_t struct_size;   /* sizeof(ktn_options), for versioning */
     int32_t device;        /* CUDA device ordinal; -1 = current device */

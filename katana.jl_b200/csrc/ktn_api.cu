@@ -89,7 +89,6 @@ static int ensure_topk(ktn_handle* h) {
 
 extern "C" int ktn_set_params(ktn_handle* h, double f_tol, double rng, int64_t topk) {
     if (!h || topk < 0) return fail(h, KTN_ERR_USAGE, "bad parameters");
-    if (topk > 0 && h->comm) return fail(h, KTN_ERR_UNSUPPORTED, "topk > 0 on a sharded handle: a global top-k needs a cross-rank selection, which is not built");
     h->opt.f_tol = f_tol; h->opt.cut_coef_rng = rng; h->opt.topk = topk;
     cudaSetDevice(h->device);
     return ensure_topk(h);
@@ -216,7 +215,8 @@ KtnRoundParams ktn_make_params(ktn_handle* h, const double* d_x, int mode, int d
     p.row_lb = h->row_lb.as<double>(); p.row_ub = h->row_ub.as<double>();
     p.x = d_x; p.force = h->force.as<uint8_t>();
     p.f_tol = h->opt.f_tol; p.rng = h->opt.cut_coef_rng; p.mode = mode; p.do_round = do_round;
-    p.topk = h->comm ? 0 : h->opt.topk; p.topk_key = h->topk_key.as<unsigned long long>(); p.topk_state = h->topk_state.as<KtnTopkState>(); p.topk_eqcnt = h->topk_eqcnt.as<unsigned int>();
+    p.topk = h->opt.topk;      // sharded handles: a LOCAL top-k of this rank's rows; the global one is the merge of the union (sharding.py merge_topk)
+    p.topk_key = h->topk_key.as<unsigned long long>(); p.topk_state = h->topk_state.as<KtnTopkState>(); p.topk_eqcnt = h->topk_eqcnt.as<unsigned int>();
     p.num_var = h->prob.num_var; p.num_rows = h->prob.num_constr;
     p.warp_bytes = h->warp_bytes; p.blob_cap = h->blob_cap;
     p.g_row = h->g_row.as<double>(); p.b_row = h->b_row.as<double>(); p.sel = h->sel.as<uint32_t>();

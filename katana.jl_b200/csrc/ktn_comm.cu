@@ -189,7 +189,6 @@ extern "C" int ktn_comm_unique_id(void* id128) {
 
 extern "C" int ktn_comm_init(ktn_handle* h, int32_t nranks, int32_t rank, const void* id128) {
     if (!h || nranks < 1 || rank < 0 || rank >= nranks || !id128) return fail(h, KTN_ERR_USAGE, "bad communicator arguments");
-    if (h->opt.topk > 0) return fail(h, KTN_ERR_UNSUPPORTED, "topk > 0 on a sharded handle: a global top-k needs a cross-rank selection, which is not built");
     std::string why;
     if (!load_nccl(&why)) return fail(h, KTN_ERR_NCCL, "%s", why.c_str());
     cudaSetDevice(h->device);

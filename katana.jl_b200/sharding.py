@@ -32,3 +32,23 @@ def combine_rank_major(parts):
     cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dt)
     return CutBatch(status, err_row, cat(row_id, np.int64), np.concatenate(ptr), cat(col, np.int32), cat(val, np.float64),
                     cat(lo, np.float64), cat(hi, np.float64), cat(g, np.float64), cat(viol, np.float64), cat(bc, np.float64))
+
+
+def merge_topk(batch, k):
+    """Global top-k of a combined batch ("top-k extension").  Every rank keeps its own k most violated
+    rows (ktn_options.topk on a sharded handle is a LOCAL selection); the union of those, combined rank-major, contains the
+    global top-k, and this is the identical deterministic merge every rank (or the host) runs on it: rank the cuts by
+    (NaN first, violation descending, row ascending) -- the oracle's order -- keep k, emit them in ascending row order.
+    Rounds that stopped at a non-finite cut are returned as they are (the reference abandons such a solve, src/model.jl:278)."""
+    n = len(batch.row_id)
+    if k <= 0 or n <= k or batch.status != 0:
+        return batch
+    v = batch.viol
+    nan = np.isnan(v)
+    order = np.lexsort((batch.row_id, -np.where(nan, 0.0, v), ~nan))      # last key first: NaN rows, then violation, then row
+    keep = np.sort(order[:k])                                                # positions in the batch = ascending rows
+    lens = np.diff(batch.row_ptr)[keep]
+    ptr = np.concatenate([np.zeros(1, np.int64), np.cumsum(lens)]).astype(np.int64)
+    src = np.repeat(batch.row_ptr[keep] - ptr[:-1], lens) + np.arange(int(ptr[-1]), dtype=np.int64)
+    return CutBatch(batch.status, batch.err_row, batch.row_id[keep], ptr, batch.col[src], batch.val[src], batch.lo[keep], batch.hi[keep],
+                    batch.g[keep], batch.viol[keep], batch.bconst[keep])

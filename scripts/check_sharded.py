@@ -43,6 +43,17 @@ for kind, nv, rows in ((1, 5000, 40000), (0, 2000, 30000)):
             if not same:
                 ok = False
                 print(f"rank {rank} kind {kind} rounds {upto}: MISMATCH in {f} {a.shape} {b.shape}", flush=True)
+    # top-k extension: local top-k per rank, exchange, identical merge on every rank == the single handle's top-k
+    from katana_jl_b200.sharding import merge_topk
+    for k in (1, 500, 10**7):
+        h.set_params(1e-6, 1e9, k); hf.set_params(1e-6, 1e9, k)
+        h.separate_device_async(dx[0].data_ptr()); h.allgather_cuts_async()
+        got = merge_topk(h.fetch_gathered(), k); ref = hf.separate(x0)
+        for f in ("row_id", "row_ptr", "col", "val", "lo", "hi", "g", "viol", "bconst"):
+            a, b = getattr(got, f), getattr(ref, f)
+            if not (a.shape == b.shape and a.tobytes() == b.tobytes()):
+                ok = False
+                print(f"rank {rank} kind {kind} top-{k}: MISMATCH in {f} {a.shape} {b.shape}", flush=True)
     h.close(); hf.close()
 t = torch.tensor([1 if ok else 0], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -21,7 +21,7 @@ def _worker(rank, world, port, out_dir):
     import torch.distributed as dist
     import katana_jl_b200  # noqa: F401
     from katana_jl_b200.binding import CUDA_LIB_PATH, KtnLibrary
-    from katana_jl_b200.sharding import combine_rank_major, shard_range
+    from katana_jl_b200.sharding import combine_rank_major, merge_topk, shard_range
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     synth = KtnLibrary(CUDA_LIB_PATH)                       # generators only, no device call
@@ -46,6 +46,17 @@ def _worker(rank, world, port, out_dir):
         full = hf.separate(x0)
         ok = all(np.array_equal(getattr(full, f), getattr(combined, f)) for f in ("row_id", "row_ptr", "col", "val", "lo", "hi", "g", "viol", "bconst"))
         open(os.path.join(out_dir, "result"), "w").write(f"{int(ok)} {full.n_cuts} {combined.n_cuts}")
+    # top-k extension: every rank keeps its k most violated rows, the merge of the union is the whole instance's top-k
+    for k in (1, 37, 200, 10**6):
+        h.set_params(1e-6, 1e9, k)
+        parts_k = [None] * world
+        dist.all_gather_object(parts_k, (r0, h.separate(x0)))
+        merged = merge_topk(combine_rank_major(parts_k), k)
+        if rank == 0:
+            hf.set_params(1e-6, 1e9, k)
+            full_k = hf.separate(x0)
+            ok_k = all(np.array_equal(getattr(full_k, f), getattr(merged, f)) for f in ("row_id", "row_ptr", "col", "val", "lo", "hi", "g", "viol", "bconst"))
+            open(os.path.join(out_dir, "result"), "a").write(f" {int(ok_k)}:{full_k.n_cuts}")
     dist.barrier()
     dist.destroy_process_group()
 
@@ -53,8 +64,10 @@ def _worker(rank, world, port, out_dir):
 def test_two_rank_shards_equal_whole(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    ok, n_full, n_comb = open(tmp_path / "result").read().split()
+    ok, n_full, n_comb, *topk = open(tmp_path / "result").read().split()
     assert ok == "1" and n_full == n_comb and int(n_full) > 100
+    assert len(topk) == 4 and all(t.startswith("1:") for t in topk), topk          # sharded top-k == whole-instance top-k
+    assert [int(t.split(":")[1]) for t in topk[:3]] == [1, 37, 200]
 
 
 def test_shard_ranges_cover_and_balance():
