@@ -38,11 +38,11 @@ __device__ __forceinline__ double ld_dsmem(const double* base, unsigned index, u
 }
 
 // MODE 0: gathers through L1/L2;  1: gathers from cluster shared memory;  2: DSMEM gathers only;  3: streams only
-template <int MODE>
+template <int MODE, unsigned CL>          // CL compile-time: col / CL and col % CL must not cost a runtime division
 __global__ void __launch_bounds__(WARPS * 32, 1) k_pattern(const unsigned char* blob, const double* x, int n, double* out, unsigned* ticket, unsigned nchunks) {
     extern __shared__ __align__(16) double xs[];                 // this CTA's share of x*: x[col] with col % CL == rank, at col / CL
     cg::cluster_group cluster = cg::this_cluster();
-    const unsigned CL = cluster.num_blocks(), rank = cluster.block_rank();
+    const unsigned rank = cluster.block_rank();
     if (MODE == 1 || MODE == 2) {
         for (int j = threadIdx.x; (unsigned)j * CL + rank < (unsigned)n; j += blockDim.x) xs[j] = x[(unsigned)j * CL + rank];
         cluster.sync();
@@ -79,10 +79,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pattern(const unsigned char* 
     if (MODE == 1 || MODE == 2) cluster.sync();                  // nobody leaves while a peer may still read its shared memory
 }
 
-template <int MODE>
-static float run(int CL, int blocks, size_t smem, const unsigned char* blob, const double* x, int n, double* out, unsigned* ticket, unsigned nchunks, int reps) {
-    CK(cudaFuncSetAttribute(k_pattern<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (CL > 8) CK(cudaFuncSetAttribute(k_pattern<MODE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+template <int MODE, unsigned CL>
+static float run(int blocks, size_t smem, const unsigned char* blob, const double* x, int n, double* out, unsigned* ticket, unsigned nchunks, int reps) {
+    CK(cudaFuncSetAttribute(k_pattern<MODE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (CL > 8) CK(cudaFuncSetAttribute(k_pattern<MODE, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(WARPS * 32); cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
@@ -93,7 +93,7 @@ static float run(int CL, int blocks, size_t smem, const unsigned char* blob, con
     for (int r = 0; r < reps + 2; ++r) {
         CK(cudaMemsetAsync(ticket, 0, 4));
         CK(cudaEventRecord(e0));
-        CK(cudaLaunchKernelEx(&cfg, k_pattern<MODE>, blob, x, n, out, ticket, nchunks));
+        CK(cudaLaunchKernelEx(&cfg, k_pattern<MODE, CL>, blob, x, n, out, ticket, nchunks));
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -102,8 +102,13 @@ static float run(int CL, int blocks, size_t smem, const unsigned char* blob, con
     return best * 1e3f;
 }
 
+template <unsigned CL> static int bench();
 int main(int argc, char** argv) {
-    const int CL = argc > 1 ? atoi(argv[1]) : 8;
+    const int cl = argc > 1 ? atoi(argv[1]) : 8;
+    switch (cl) { case 2: return bench<2>(); case 4: return bench<4>(); case 6: return bench<6>(); case 8: return bench<8>(); case 16: return bench<16>(); }
+    printf("cluster size must be 2, 4, 6, 8 or 16\n"); return 2;
+}
+template <unsigned CL> static int bench() {
     const int n = 100000; const unsigned nchunks = 31250;
     int dev = 0, sms = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     std::vector<unsigned char> hb((size_t)nchunks * 672 * K);
@@ -123,19 +128,19 @@ int main(int argc, char** argv) {
 
     // how many CTAs of this shape can be resident as clusters of CL
     {
-        CK(cudaFuncSetAttribute(k_pattern<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
-        if (CL > 8) CK(cudaFuncSetAttribute(k_pattern<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        cudaLaunchConfig_t cfg = {}; cfg.gridDim = dim3(sms / CL * CL); cfg.blockDim = dim3(WARPS * 32); cfg.dynamicSmemBytes = smem_x;
+        CK(cudaFuncSetAttribute(k_pattern<1, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
+        if (CL > 8) CK(cudaFuncSetAttribute(k_pattern<1, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg = {}; cfg.gridDim = dim3(sms / (int)CL * (int)CL); cfg.blockDim = dim3(WARPS * 32); cfg.dynamicSmemBytes = smem_x;
         cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        int ncl = 0; CK(cudaOccupancyMaxActiveClusters(&ncl, k_pattern<1>, &cfg));
-        printf("cluster size %d, %zu B of x* per CTA: %d clusters resident = %d of %d SMs\n", CL, smem_x, ncl, ncl * CL, sms);
-        const int blocks = ncl * CL;
+        int ncl = 0; CK(cudaOccupancyMaxActiveClusters(&ncl, k_pattern<1, CL>, &cfg));
+        printf("cluster size %u, %zu B of x* per CTA: %d clusters resident = %d of %d SMs\n", CL, smem_x, ncl, ncl * (int)CL, sms);
+        const int blocks = ncl * (int)CL;
         const double gathers = (double)nchunks * 32 * K;
-        const float tA = run<0>(1, sms, 0, blob, x, n, out, ticket, nchunks, 10);
-        const float tD = run<3>(1, sms, 0, blob, x, n, out, ticket, nchunks, 10);
-        const float tB = run<1>(CL, blocks, smem_x, blob, x, n, out, ticket, nchunks, 10);
-        const float tC = run<2>(CL, blocks, smem_x, blob, x, n, out, ticket, nchunks, 10);
+        const float tA = run<0, 1>(sms, 0, blob, x, n, out, ticket, nchunks, 10);
+        const float tD = run<3, 1>(sms, 0, blob, x, n, out, ticket, nchunks, 10);
+        const float tB = run<1, CL>(blocks, smem_x, blob, x, n, out, ticket, nchunks, 10);
+        const float tC = run<2, CL>(blocks, smem_x, blob, x, n, out, ticket, nchunks, 10);
         printf("A streams + gathers through L1/L2 (%d SMs)      %7.1f us\n", sms, tA);
         printf("D streams only (%d SMs)                         %7.1f us\n", sms, tD);
         printf("B streams through L2, gathers from DSMEM (%d SMs) %7.1f us   (includes staging x* and two cluster syncs)\n", blocks, tB);

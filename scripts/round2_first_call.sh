@@ -13,7 +13,7 @@ build)
   ;;
 run)
   mkdir -p gpurun_out
-  for cl in 8 16 4; do timeout 120 build/variants/mb3 $cl 2>&1 | tee -a gpurun_out/mb3.log; done
+  for cl in 8 16 6 4; do timeout 120 build/variants/mb3 $cl 2>&1 | tee -a gpurun_out/mb3.log; done
   # one process per variant (the binding loads the library RTLD_GLOBAL); equal digests = equal results
   for v in base xdsmem8 xdsmem16 fwd3g4 fwd1; do KTN_DEBUG=1 timeout 200 python scripts/ab_time.py build/variants/libktn_$v.so 2>&1 | tee -a gpurun_out/ab_round2.log; done
   ;;
