@@ -94,7 +94,8 @@ enum {
 typedef struct ktn_timings {
     double h2d_ms;        /* x* upload */
     double kernel_ms;     /* separation kernels, CUDA events on the library stream */
-    double exchange_ms;   /* NCCL allgather of compacted cuts (0 when not sharded) */
+    double exchange_ms;   /* reserved, 0: the exchange of a sharded round overlaps the following rounds on its own stream; its cost shows
+                             in the round rate (bench.py) and in the wait of ktn_sync_gathered, not as a span of its own */
     double d2h_ms;        /* cut download in ktn_fetch_cuts */
     int64_t launches;     /* kernels launched by this library since creation */
     int64_t rounds;       /* separation rounds run since creation */
