@@ -167,6 +167,7 @@ extern "C" int ktn_load_end(ktn_handle* h) {
     h->out_cap = ((size_t)ktn_pack_layout(m, N).total + 127) / 128 * 128 + 128;      // every row selected
     h->out_cur = 0; for (bool& b : h->blob_busy) b = false;
     CK(h, h->out_blob[0].alloc(h->out_cap)); h->out_blob[1].release(); h->out_blob[2].release();     // [1], [2]: sharded handles, on first use
+    CK(h, cudaMemset(h->out_blob[0].p, 0, 128));       // a shard without rows never runs K2: its blob header must read "nothing"
     CK(h, cudaMallocHost(&h->h_x, 8 * ((size_t)P.num_var + 1)));
     // the packed blob lives on the device now
     std::vector<uint8_t>().swap(P.blob);
@@ -246,7 +247,7 @@ static int enqueue_round(ktn_handle* h, const double* d_x, int mode, int do_roun
     { int rc = ktn_comm_launch_pending(h); if (rc) return rc; }       // sharded runs: the previous round's cut payload travels beside this round
     if (h->comm) {      // the next of three cut blobs; the exchange that last read it (three rounds ago) must have finished
         h->out_cur = (h->out_cur + 1) % 3;
-        if (!h->out_blob[h->out_cur].p) CK(h, h->out_blob[h->out_cur].alloc(h->out_cap));
+        if (!h->out_blob[h->out_cur].p) { CK(h, h->out_blob[h->out_cur].alloc(h->out_cap)); CK(h, cudaMemsetAsync(h->out_blob[h->out_cur].p, 0, 128, h->stream)); }
         { int rc = ktn_comm_release_blob(h, h->out_cur); if (rc) return rc; }
     }
     h->epoch = (h->epoch % 0x3ffffff0u) + 1u;
