@@ -120,8 +120,9 @@ __device__ __forceinline__ uint32_t ldg_stream(const uint8_t* p) {
 
 #ifdef KTN_OPT_XDSMEM
 // EXPERIMENT (round 2, not part of the default build; profiles/microbench/mb3_dsmem.cu has the reasoning): x* staged in the shared
-// memory of a cluster of KTN_OPT_XDSMEM CTAs -- x[c] lives in CTA c % CL at index c / CL -- and gathered from there with
-// 8-byte distributed-shared-memory loads instead of 32-byte sectors through L1 / L2.
+// memory of a cluster of KTN_OPT_XDSMEM CTAs -- 128-byte lines of x* are dealt round-robin: x[c] lives in CTA (c / 16) % CL at
+// index ((c / 16) / CL) * 16 + c % 16, so staging reads whole lines -- and gathered from there with 8-byte
+// distributed-shared-memory loads instead of 32-byte sectors through L1 / L2.
 extern __shared__ __align__(128) unsigned char ktn_dyn_smem[];
 __device__ __forceinline__ double ld_dsmem(const double* base, unsigned index, unsigned rank) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(base) + index * 8u;
@@ -142,7 +143,8 @@ struct FamRow {     // row context of ktn_family.h: the chunk's SoA sections in 
     __device__ __forceinline__ int32_t col(uint32_t u) const { return ldg_stream(cols + u * 32u); }
 #ifdef KTN_OPT_XDSMEM
     __device__ __forceinline__ double xat(int32_t c) const {
-        return xs ? ld_dsmem(xs, (uint32_t)c / KTN_OPT_XDSMEM, (uint32_t)c % KTN_OPT_XDSMEM) : __ldg(X + c);
+        const uint32_t line = (uint32_t)c >> 4;
+        return xs ? ld_dsmem(xs, (line / KTN_OPT_XDSMEM) * 16u + ((uint32_t)c & 15u), line % KTN_OPT_XDSMEM) : __ldg(X + c);
     }
 #else
     __device__ __forceinline__ double xat(int32_t c) const { return __ldg(X + c); }
@@ -273,10 +275,14 @@ __global__ void __launch_bounds__(KTN_FP_WARPS * 32, FWD ? KTN_FWD_BLOCKS : 1) k
     uint32_t* next = reinterpret_cast<uint32_t*>(smem) + (threadIdx.x >> 5);       // per-warp mailbox of the next ticket
     unsigned int* tickets = p.ticket + p.ticket_idx;
 #ifdef KTN_OPT_XDSMEM
-    if (p.x_cluster) {      // stage this CTA's share of x* (x[c] with c % CL == rank, at c / CL), then meet the cluster
+    if (p.x_cluster) {      // stage this CTA's share of x* (every CL-th 128-byte line, starting at line `rank`), then meet the cluster
         uint32_t rank; asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
         double* xs = reinterpret_cast<double*>(smem + (FWD ? 128 : KTN_FP_SMEM));
-        for (uint32_t j = threadIdx.x; j * KTN_OPT_XDSMEM + rank < (uint32_t)p.num_var; j += blockDim.x) xs[j] = __ldg(p.x + j * KTN_OPT_XDSMEM + rank);
+        for (uint32_t j = threadIdx.x;; j += blockDim.x) {
+            const uint32_t c = (((j >> 4) * KTN_OPT_XDSMEM + rank) << 4) | (j & 15u);
+            if ((j >> 4) * KTN_OPT_XDSMEM * 16u >= (uint32_t)p.num_var) break;           // past the last line of every rank
+            if (c < (uint32_t)p.num_var) xs[j] = __ldg(p.x + c);
+        }
         cluster_sync_all();
     }
 #endif
@@ -916,7 +922,8 @@ static void launch_family(KtnRoundParams p, const KtnLaunchPlan& plan, uint32_t 
 #ifdef KTN_OPT_XDSMEM
     {
         const size_t base = FWD ? 128 : KTN_FP_SMEM;
-        const size_t smem = base + 8 * (((size_t)p.num_var + KTN_OPT_XDSMEM - 1) / KTN_OPT_XDSMEM) + 64;
+        const size_t lines = ((size_t)p.num_var + 15) / 16;
+        const size_t smem = base + 128 * ((lines + KTN_OPT_XDSMEM - 1) / KTN_OPT_XDSMEM) + 64;      // this CTA's lines of x*
         cudaLaunchConfig_t cfg = {};
         cfg.blockDim = dim3(KTN_FP_WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
         cudaLaunchAttribute at[1];

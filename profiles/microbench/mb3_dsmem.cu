@@ -10,7 +10,7 @@
 //
 // What this measures (one persistent block of 16 warps per SM, the family kernel's shape: K = 10 terms per row, 31250 chunks):
 //   A  baseline   streams + gathers through L1/L2                              (mb2's k_once, 16 warps/SM)
-//   B  dsmem      streams through L1/L2, gathers from the cluster's shared memory (x[col] lives in CTA col % CL at col / CL)
+//   B  dsmem      streams through L1/L2, gathers from the cluster's shared memory (128-byte lines of x* dealt round-robin over the CTAs)
 //   C  dsmem only the gathers alone: words per clock per SM that DSMEM sustains for random addresses
 //   D  streams only (no gathers): the floor of the L2 path for the 200 MB
 // and how many SMs a cluster launch of that shape can use (cudaOccupancyMaxActiveClusters).
@@ -40,11 +40,14 @@ __device__ __forceinline__ double ld_dsmem(const double* base, unsigned index, u
 // MODE 0: gathers through L1/L2;  1: gathers from cluster shared memory;  2: DSMEM gathers only;  3: streams only
 template <int MODE, unsigned CL>          // CL compile-time: col / CL and col % CL must not cost a runtime division
 __global__ void __launch_bounds__(WARPS * 32, 1) k_pattern(const unsigned char* blob, const double* x, int n, double* out, unsigned* ticket, unsigned nchunks) {
-    extern __shared__ __align__(16) double xs[];                 // this CTA's share of x*: x[col] with col % CL == rank, at col / CL
+    extern __shared__ __align__(16) double xs[];                 // this CTA's share of x*: every CL-th 128-byte line, x[c] in CTA (c/16) % CL at ((c/16)/CL)*16 + c%16
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
     if (MODE == 1 || MODE == 2) {
-        for (int j = threadIdx.x; (unsigned)j * CL + rank < (unsigned)n; j += blockDim.x) xs[j] = x[(unsigned)j * CL + rank];
+        for (unsigned j = threadIdx.x; (j >> 4) * CL * 16u < (unsigned)n; j += blockDim.x) {
+            const unsigned c = (((j >> 4) * CL + rank) << 4) | (j & 15u);
+            if (c < (unsigned)n) xs[j] = x[c];
+        }
         cluster.sync();
     }
     const unsigned lane = threadIdx.x & 31;
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pattern(const unsigned char* 
         for (int u = 0; u < K; ++u) {
             if (MODE == 0) xv[u] = __ldg(x + cl[u]);
             else if (MODE == 3) xv[u] = (double)cl[u];
-            else xv[u] = ld_dsmem(xs, (unsigned)cl[u] / CL, (unsigned)cl[u] % CL);
+            else { const unsigned line = (unsigned)cl[u] >> 4; xv[u] = ld_dsmem(xs, (line / CL) * 16u + ((unsigned)cl[u] & 15u), line % CL); }
         }
 #pragma unroll
         for (int u = 0; u < K; ++u) acc += cc[u] * xv[u] + dd[u];
@@ -124,7 +127,7 @@ template <unsigned CL> static int bench() {
     unsigned char* blob; double *x, *out; unsigned* ticket;
     CK(cudaMalloc(&blob, hb.size())); CK(cudaMalloc(&x, 8 * (size_t)n)); CK(cudaMalloc(&out, 64)); CK(cudaMalloc(&ticket, 64));
     CK(cudaMemcpy(blob, hb.data(), hb.size(), cudaMemcpyHostToDevice)); CK(cudaMemcpy(x, hx.data(), 8 * (size_t)n, cudaMemcpyHostToDevice));
-    const size_t smem_x = 8 * (size_t)((n + CL - 1) / CL) + 64;
+    const size_t smem_x = 128 * (size_t)(((n + 15) / 16 + CL - 1) / CL) + 64;
 
     // how many CTAs of this shape can be resident as clusters of CL
     {
