@@ -17,6 +17,31 @@ def shard_range(num_rows, world_size, rank):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def shard_ranges_by_weight(weights, world_size):
+    """Contiguous [begin, end) per rank with (nearly) equal total weight: SURVEY.md section 8e splits on tape bytes, not on
+    row counts (a rank of long tapes would otherwise finish last).  `weights[i]` >= 0 is row i's cost -- use the tape length
+    `np.diff(wire.expr_ptr)` (dense epigraph rows: their n + 1 Jacobian entries).  Order is preserved, so the last row (the
+    epigraph row, src/model.jl:148) stays on the last non-empty rank.  Cuts are made where the prefix sum crosses k/world of the
+    total; ranks may be empty when there are fewer rows than ranks."""
+    w = np.asarray(weights, dtype=np.float64)
+    m = len(w)
+    if m == 0:
+        return [(0, 0)] * world_size
+    prefix = np.concatenate([[0.0], np.cumsum(np.maximum(w, 0.0))])
+    total = prefix[-1]
+    if total <= 0.0:
+        return [shard_range(m, world_size, r) for r in range(world_size)]
+    cuts = [0]
+    for k in range(1, world_size):
+        target = total * k / world_size
+        i = int(np.searchsorted(prefix, target, side="left"))          # first prefix >= target
+        if i > 0 and target - prefix[i - 1] < prefix[i] - target:        # the nearer boundary
+            i -= 1
+        cuts.append(min(max(i, cuts[-1]), m))
+    cuts.append(m)
+    return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
+
+
 def combine_rank_major(parts):
     """parts: list over ranks of (row_begin, CutBatch with shard-local row ids).  Returns one CutBatch
     with global row ids; stops at the first rank that reported a non-finite row (src/model.jl:278)."""

@@ -79,3 +79,23 @@ def test_shard_ranges_cover_and_balance():
             assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in rs]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_weighted_shards_balance_tape_bytes():
+    """split on tape bytes.  Contiguous, covering, and no rank heavier than the ideal share by more than one row."""
+    from katana_jl_b200.sharding import shard_ranges_by_weight
+    rng = np.random.default_rng(7)
+    for m in (0, 1, 5, 1000, 20011):
+        for world in (1, 2, 3, 8):
+            w = rng.integers(18, 67, size=m).astype(float)            # LSE tape lengths 4K + 2, K in 4..16
+            if m > 10:
+                w[-1] = 5000.0                                         # a dense epigraph row at the end
+            rs = shard_ranges_by_weight(w, world)
+            assert len(rs) == world and rs[0][0] == 0 and rs[-1][1] == m
+            assert all(rs[i][1] == rs[i + 1][0] and rs[i][0] <= rs[i][1] for i in range(world - 1))
+            if m >= 1000:
+                share = w.sum() / world
+                assert max(w[a:b].sum() for a, b in rs) <= share + w.max()
+    # equal weights degenerate to (almost) equal counts
+    rs = shard_ranges_by_weight(np.ones(1000), 8)
+    assert max(b - a for a, b in rs) - min(b - a for a, b in rs) <= 1
