@@ -50,7 +50,6 @@ extern "C" int ktn_create(const ktn_options* o, ktn_handle** out) {
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
     h->stream = h->own_stream;
     cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
-    cudaEventCreate(&h->evx0); cudaEventCreate(&h->evx1);
     for (int i = 0; i < ktn_handle::RING; ++i) for (int j = 0; j < 3; ++j) cudaEventCreate(&h->ring[i][j]);
     if (cudaMallocHost(&h->h_counts, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
     if (h->ticket.alloc(4 * KTN_TICKETS) != cudaSuccess || h->counts.alloc(8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
@@ -72,7 +71,6 @@ extern "C" void ktn_destroy(ktn_handle* h) {
     ktn_comm_release(h);
     if (h->ev0) {
         cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
-        cudaEventDestroy(h->evx0); cudaEventDestroy(h->evx1);
         for (int i = 0; i < ktn_handle::RING; ++i) for (int j = 0; j < 3; ++j) cudaEventDestroy(h->ring[i][j]);
     }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);

@@ -250,7 +250,7 @@ void ktn_comm_release(ktn_handle* h) {
     for (auto& x : h->xch) {
         x.gathered.release(); x.all_counts.release();
         if (x.h_all_counts) { cudaFreeHost(x.h_all_counts); x.h_all_counts = nullptr; }
-        if (x.packed) { cudaEventDestroy(x.packed); cudaEventDestroy(x.sizes); cudaEventDestroy(x.done); x.packed = x.sizes = x.done = nullptr; }
+        if (x.packed) { cudaEventDestroy(x.packed); cudaEventDestroy(x.sizes); x.packed = x.sizes = nullptr; }
         x.state = 0;
     }
     for (int k = 0; k < 3; ++k) { if (h->blob_ev[k]) { cudaEventDestroy(h->blob_ev[k]); h->blob_ev[k] = nullptr; } h->blob_busy[k] = false; }
@@ -283,7 +283,6 @@ extern "C" int ktn_comm_init(ktn_handle* h, int32_t nranks, int32_t rank, const 
         x.g_cuts.assign(nranks, 0); x.g_nnz.assign(nranks, 0); x.g_off.assign(nranks + 1, 0);
         x.g_lay_cuts.assign(nranks, 0); x.g_lay_nnz.assign(nranks, 0); x.g_bytes.assign(nranks, 0);
         CK(h, cudaEventCreateWithFlags(&x.packed, cudaEventDisableTiming)); CK(h, cudaEventCreateWithFlags(&x.sizes, cudaEventDisableTiming));
-        CK(h, cudaEventCreateWithFlags(&x.done, cudaEventDisableTiming));
         x.state = 0;
     }
     for (int k = 0; k < 3; ++k) { CK(h, cudaEventCreateWithFlags(&h->blob_ev[k], cudaEventDisableTiming)); h->blob_busy[k] = false; }

@@ -59,7 +59,7 @@ struct ktn_handle {
         std::vector<int64_t> g_cuts, g_nnz, g_off;      // per rank, once the headers are on the host
         std::vector<int64_t> g_lay_cuts, g_lay_nnz, g_bytes;   // layout arguments and size of every rank's blob
         int src_idx = 0;                                // which of the handle's cut blobs this exchange ships
-        cudaEvent_t packed = nullptr, sizes = nullptr, done = nullptr;
+        cudaEvent_t packed = nullptr, sizes = nullptr;    // the round's K2 has finished; the headers of all ranks are on the host
         int state = 0;                                  // 0 idle, 1 sizes in flight (payload not launched), 2 payload in flight / complete
         int64_t gathered_bytes = 0;
     } xch[3];                                           // the payload of exchange k is launched when exchange k+2 is enqueued
@@ -79,7 +79,6 @@ struct ktn_handle {
         bool reserve = true;                            // K1 leaves that many SMs free (KTN_PUSH_RESERVE=0 turns it off)
     } px;
     int64_t row_offset = 0;
-    cudaEvent_t evx0 = nullptr, evx1 = nullptr;
 };
 
 static inline int fail(ktn_handle* h, int code, const char* fmt, ...) {
