@@ -27,8 +27,6 @@
 //        block of 4096 rows), so every K2 block finds its output offset with one short sum: no look-back chain.
 // BIG shapes (long tapes, the dense epigraph row) take ktn_big_kernel with global scratch.
 // All arithmetic is fp64, unfused, in the oracle's order.
-#include <cstdio>
-#include <cstdlib>
 #include "ktn_kernels.cuh"
 #include "ktn_math.h"
 #include "ktn_interp.h"
@@ -118,37 +116,11 @@ __device__ __forceinline__ uint32_t ldg_stream(const uint8_t* p) {
     uint32_t v; asm("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v;
 }
 
-#ifdef KTN_OPT_XDSMEM
-// EXPERIMENT (round 2, not part of the default build; profiles/microbench/mb3_dsmem.cu has the reasoning): x* staged in the shared
-// memory of a cluster of KTN_OPT_XDSMEM CTAs -- 128-byte lines of x* are dealt round-robin: x[c] lives in CTA (c / 16) % CL at
-// index ((c / 16) / CL) * 16 + c % 16, so staging reads whole lines -- and gathered from there with 8-byte
-// distributed-shared-memory loads instead of 32-byte sectors through L1 / L2.
-extern __shared__ __align__(128) unsigned char ktn_dyn_smem[];
-__device__ __forceinline__ double ld_dsmem(const double* base, unsigned index, unsigned rank) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(base) + index * 8u;
-    unsigned ra; asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
-    double v; asm("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra)); return v;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-#endif
-
 struct FamRow {     // row context of ktn_family.h: the chunk's SoA sections in global memory, lane offset applied
     const double* C; const int32_t* cols; const uint8_t* rk; const double* X; uint32_t nu;
-#ifdef KTN_OPT_XDSMEM
-    const double* xs;                                                   // null: x* is not in the cluster (does not fit)
-#endif
     __device__ __forceinline__ double cst(uint32_t i) const { return ldg_stream(C + i * 32u); }
     __device__ __forceinline__ int32_t col(uint32_t u) const { return ldg_stream(cols + u * 32u); }
-#ifdef KTN_OPT_XDSMEM
-    __device__ __forceinline__ double xat(int32_t c) const {
-        const uint32_t line = (uint32_t)c >> 4;
-        return xs ? ld_dsmem(xs, (line / KTN_OPT_XDSMEM) * 16u + ((uint32_t)c & 15u), line % KTN_OPT_XDSMEM) : __ldg(X + c);
-    }
-#else
     __device__ __forceinline__ double xat(int32_t c) const { return __ldg(X + c); }
-#endif
     __device__ __forceinline__ double x(uint32_t u) const { return xat(col(u)); }
     __device__ __forceinline__ uint32_t rank(uint32_t u) const { return ldg_stream(rk + u * 32u); }     // streaming rows: one byte per u
     __device__ __forceinline__ uint64_t rankword() const { return ldg_stream(reinterpret_cast<const uint64_t*>(rk)); }
@@ -190,14 +162,8 @@ __device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c
     const unsigned char* blob;
     if (N > 0 && p.cls_blob_stride[N > 0 ? N : 0] != 0xffffffffu) blob = family_blob(p, (uint32_t)N, c);
     else { const KtnChunkDesc cd = p.chunks[c]; nu = (uint32_t)cd.aux; blob = p.blob + cd.blob_off; }
-#ifdef KTN_OPT_XDSMEM
-    const FamRow r{reinterpret_cast<const double*>(blob) + lane, reinterpret_cast<const int32_t*>(blob + 512u * nu) + lane,
-                   blob + 640u * nu + (N > 0 ? lane * 8u : lane), p.x, nu,
-                   p.x_cluster ? reinterpret_cast<const double*>(ktn_dyn_smem + (FWD ? 128 : KTN_FP_SMEM)) : nullptr};
-#else
     const FamRow r{reinterpret_cast<const double*>(blob) + lane, reinterpret_cast<const int32_t*>(blob + 512u * nu) + lane,
                    blob + 640u * nu + (N > 0 ? lane * 8u : lane), p.x, nu};
-#endif
     constexpr int NR = N > 0 ? N : 1;
     KtnFamRegs<NR> v;
     double aux, g;
@@ -274,18 +240,6 @@ __global__ void __launch_bounds__(KTN_FP_WARPS * 32, FWD ? KTN_FWD_BLOCKS : 1) k
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t* next = reinterpret_cast<uint32_t*>(smem) + (threadIdx.x >> 5);       // per-warp mailbox of the next ticket
     unsigned int* tickets = p.ticket + p.ticket_idx;
-#ifdef KTN_OPT_XDSMEM
-    if (p.x_cluster) {      // stage this CTA's share of x* (every CL-th 128-byte line, starting at line `rank`), then meet the cluster
-        uint32_t rank; asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-        double* xs = reinterpret_cast<double*>(smem + (FWD ? 128 : KTN_FP_SMEM));
-        for (uint32_t j = threadIdx.x;; j += blockDim.x) {
-            const uint32_t c = (((j >> 4) * KTN_OPT_XDSMEM + rank) << 4) | (j & 15u);
-            if ((j >> 4) * KTN_OPT_XDSMEM * 16u >= (uint32_t)p.num_var) break;           // past the last line of every rank
-            if (c < (uint32_t)p.num_var) xs[j] = __ldg(p.x + c);
-        }
-        cluster_sync_all();
-    }
-#endif
     const uint32_t my_n = lane < KTN_FAM_NCLS ? p.cls_begin[lane + 1] - p.cls_begin[lane] : 0u;     // lane k: chunks of class k
     uint32_t cls = 0;
     {
@@ -309,11 +263,7 @@ __global__ void __launch_bounds__(KTN_FP_WARPS * 32, FWD ? KTN_FWD_BLOCKS : 1) k
             // this class is dry: one look at every class counter picks the next live class
             const bool live = lane < KTN_FAM_NCLS && my_n > 0 && __ldcg(&tickets[lane]) < my_n;
             const unsigned livem = __ballot_sync(0xffffffffu, live);
-#ifdef KTN_OPT_XDSMEM
-            if (!livem) break;
-#else
             if (!livem) return;
-#endif
             const unsigned ahead = livem & ~((2u << cls) - 1u);        // first live class after cls, cyclically
             cls = (uint32_t)__ffs(ahead ? ahead : livem) - 1u;
             n_cls = p.cls_begin[cls + 1] - p.cls_begin[cls];
@@ -327,9 +277,6 @@ __global__ void __launch_bounds__(KTN_FP_WARPS * 32, FWD ? KTN_FWD_BLOCKS : 1) k
         KTN_T(tc);
         KTN_TADD(3, tb, tc);
     }
-#ifdef KTN_OPT_XDSMEM
-    if (p.x_cluster) cluster_sync_all();      // nobody leaves while a peer may still read its share of x*
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -859,22 +806,9 @@ __global__ void __launch_bounds__(KTN_CBLOCK) ktn_topk_demote_kernel(const KtnRo
 cudaError_t ktn_kernels_configure(int max_smem_optin) {
     cudaError_t e = cudaFuncSetAttribute(ktn_round_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return e;
-#ifdef KTN_OPT_XDSMEM
-    const int fam_smem = max_smem_optin;         // the experiment adds the CTA's share of x* behind the scratch
-#if KTN_OPT_XDSMEM > 8
-    cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_LSE, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_QUAD, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_LSE, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_QUAD, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-#endif
-    if ((e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_LSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fam_smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_QUAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fam_smem)) != cudaSuccess) return e;
-#else
-    const int fam_smem = KTN_FP_SMEM;
-#endif
-    e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_LSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fam_smem);
+    e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_LSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KTN_FP_SMEM);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_QUAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fam_smem);
+    e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_QUAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KTN_FP_SMEM);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(ktn_round_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
 }
@@ -919,37 +853,6 @@ static void launch_family(KtnRoundParams p, const KtnLaunchPlan& plan, uint32_t 
     uint32_t blocks = (uint32_t)num_sms * (FWD ? KTN_FWD_BLOCKS : 1);      // persistent: one block per SM (evaluation only: two)
     const uint32_t need = (end - begin + KTN_FP_WARPS - 1) / KTN_FP_WARPS;
     if (blocks > need) blocks = need;
-#ifdef KTN_OPT_XDSMEM
-    {
-        const size_t base = FWD ? 128 : KTN_FP_SMEM;
-        const size_t lines = ((size_t)p.num_var + 15) / 16;
-        const size_t smem = base + 128 * ((lines + KTN_OPT_XDSMEM - 1) / KTN_OPT_XDSMEM) + 64;      // this CTA's lines of x*
-        cudaLaunchConfig_t cfg = {};
-        cfg.blockDim = dim3(KTN_FP_WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = KTN_OPT_XDSMEM; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        static int resident[2][2] = {{-1, -1}, {-1, -1}}; static size_t resident_smem[2][2] = {{0, 0}, {0, 0}};
-        int& ncl = resident[FAM == KTN_FAM_LSE][FWD];
-        if (smem <= 220 * 1024 && blocks >= KTN_OPT_XDSMEM) {
-            if (ncl < 0 || resident_smem[FAM == KTN_FAM_LSE][FWD] != smem) {
-                cfg.gridDim = dim3((unsigned)num_sms / KTN_OPT_XDSMEM * KTN_OPT_XDSMEM);
-                if (cudaOccupancyMaxActiveClusters(&ncl, ktn_family_kernel<FAM, FWD>, &cfg) != cudaSuccess) { ncl = 0; (void)cudaGetLastError(); }
-                resident_smem[FAM == KTN_FAM_LSE][FWD] = smem;
-                if (getenv("KTN_DEBUG")) fprintf(stderr, "libktn: x* in cluster shared memory: %d clusters of %d resident, %zu B per CTA\n", ncl, KTN_OPT_XDSMEM, smem);
-            }
-            if (ncl > 0) {
-                uint32_t g = (uint32_t)ncl * KTN_OPT_XDSMEM;
-                if (g > blocks) g = blocks / KTN_OPT_XDSMEM * KTN_OPT_XDSMEM;
-                cfg.gridDim = dim3(g);
-                p.x_cluster = 1u;
-                cudaLaunchKernelEx(&cfg, ktn_family_kernel<FAM, FWD>, p);
-                return;
-            }
-        }
-        p.x_cluster = 0u;
-    }
-#endif
     ktn_family_kernel<FAM, FWD><<<blocks, KTN_FP_WARPS * 32, FWD ? 128 : KTN_FP_SMEM, stream>>>(p);
 }
 

@@ -59,7 +59,6 @@ struct KtnRoundParams {
     //  n_cuts_total, nnz_total (the layout's arguments), reserved}, then row_id (GLOBAL ids) | row_ptr | lo | hi | g | viol | b |
     // col | val.  The host downloads it, and the sharded exchange ships it, as it lies.
     unsigned char* out_blob;
-    uint32_t x_cluster;                // experiment builds only (-DKTN_OPT_XDSMEM, ktn_kernels.cu): x* is staged in the cluster's shared memory
 };
 
 // Chunk ranges of one problem: regular chunks sorted by (family, class), then the BIG chunks.

@@ -1,4 +1,7 @@
-// mb3_dsmem.cu -- should x* live in the shared memory of a thread-block cluster?  (round-2 experiment, sm_100a; NOT run yet)
+// mb3_dsmem.cu -- should x* live in the shared memory of a thread-block cluster?  Measured on a B200 (mb3_b200.log): NO.
+// Random 8-byte ld.shared::cluster gathers sustain 0.34 words/clk/SM (C: 129 us for the gathers alone), B = 131 us against
+// A = 60 us through L1/L2, and only 15 clusters of 8 are resident (120 of 148 SMs).  Note that all variants draw tickets from
+// ONE counter: D (43 us) is the same-address atomic cap (~0.7 G/s), not a streaming floor.
 //
 // Why: the family kernel's forward pass moves 200 MB of coalesced streams plus 10^7 random 8-byte gathers of x* per round.
 // Through L1/L2 every gather costs a 32-byte sector: 320 MB of sector traffic on top of the 200 MB of streams, and the L2

@@ -7,15 +7,13 @@ set -e
 cd "$(dirname "$0")/.."
 case "$1" in
 build)
-  bash scripts/build_variants.sh base "" xdsmem8 "-DKTN_OPT_XDSMEM=8 -DKTN_FWD_BLOCKS=1" xdsmem16 "-DKTN_OPT_XDSMEM=16" xdsmem6 "-DKTN_OPT_XDSMEM=6 -DKTN_FWD_BLOCKS=1" \
-       fwd3g4 "-DKTN_FWD_BLOCKS=3 -DKTN_FWD_GROUP=4" fwd1 "-DKTN_FWD_BLOCKS=1" pushtma "-DKTN_OPT_PUSH_TMA"
-  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/variants/mb3 profiles/microbench/mb3_dsmem.cu
+  bash scripts/build_variants.sh base "" \
+       fwd3g4 "-DKTN_FWD_BLOCKS=3 -DKTN_FWD_GROUP=4" fwd1 "-DKTN_FWD_BLOCKS=1" timing "-DKTN_OPT_TIMING" pushtma "-DKTN_OPT_PUSH_TMA"
   ;;
 run)
   mkdir -p gpurun_out
-  for cl in 8 16 6 4; do timeout 120 build/variants/mb3 $cl 2>&1 | tee -a gpurun_out/mb3.log; done
   # one process per variant (the binding loads the library RTLD_GLOBAL); equal digests = equal results
-  for v in base xdsmem8 xdsmem6 xdsmem16 fwd3g4 fwd1; do KTN_DEBUG=1 timeout 200 python scripts/ab_time.py build/variants/libktn_$v.so 2>&1 | tee -a gpurun_out/ab_round2.log; done
+  for v in base fwd3g4 fwd1 timing; do KTN_DEBUG=1 timeout 200 python scripts/ab_time.py build/variants/libktn_$v.so 2>&1 | tee -a gpurun_out/ab_round2.log; done
   ;;
 run2)
   mkdir -p gpurun_out
