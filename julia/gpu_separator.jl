@@ -1,53 +1,9 @@
-# INTEGRATION — plugging `libktn.so` into Katana.jl
-
-What a Katana.jl maintainer adds so that the ECP separation round
-(`src/model.jl:265-283`) runs on a B200 behind the existing plugin interface
-`AbstractKatanaSeparator` (`src/separators.jl:8`). The Julia host stays in Julia and
-reaches CUDA only through `ccall` into the C-ABI library of `include/ktn.h`; there are no
-CUDA.jl kernels and no CPU fallback in the library.
-
-This image has no `julia` binary, so the shim below is delivered as source that has not
-been executed here; every behaviour in it is mirrored one-to-one by the Python host mirror
-(`katana.jl_b200/separators.py`, `nlpeval.py`, `model.py`), which IS exercised by the test
-suite against the same library through `ctypes` (the second binding, `binding.py`).
-
-## 1. Build / load
-
-```
-make -C katana.jl_b200/csrc          # nvcc -gencode arch=compute_100a,code=sm_100a -> katana.jl_b200/libktn.so
-```
-
-```julia
-const libktn = "/path/to/katana.jl_b200/libktn.so"
-```
-
-## 2. Which reference interface each entry point replaces
-
-| C ABI (`include/ktn.h`) | replaces (reference file:line) |
-|---|---|
-| `ktn_create`, `ktn_destroy` | constructing `KatanaFirstOrderSeparator()` `src/separators.jl:58-77` |
-| `ktn_set_params` | `KatanaModelParams.f_tol / cut_coef_rng` read at `src/model.jl:273,276`; `topk` (extension, 0 = reference behaviour): keep only the k most violated rows per round |
-| `ktn_load_begin`, `ktn_add_rows`, `ktn_load_end` | `initialize!` `src/separators.jl:81-107` (`MathProgBase.initialize`, `jac_structure`, per-row bucketing); input is `MathProgBase.constr_expr` flattened |
-| `ktn_jac_structure` | `sep.sp_cols` built at `src/separators.jl:92-100` |
-| `ktn_set_bounds` | `m.l_constr / m.u_constr` passed per call at `src/model.jl:273-277` |
-| `ktn_separate` | one pass of the loop body `src/model.jl:268-283`: `precompute!` (`src/separators.jl:111-116`), `isconstrsat` (`:120`), `gencut` → `linear_oa_cut` (`src/algorithms.jl:3-18`), `round_coefs` (`src/model.jl:200-207`), the finiteness test and bound shift of `_addcut` (`src/model.jl:68-75`) |
-| `ktn_fetch_cuts`, `ktn_fetch_cuts_view` | the `AffExpr` / `LinearConstraint` objects `_addcut` builds (`src/model.jl:74-75`), delivered as one CSR batch |
-| `ktn_gencut_rows` | the unconditional `gencut` calls of `loadproblem!` and `boundroutine` (`src/model.jl:115-118,129,160-163,181-196`) |
-| `ktn_get_g` | `sep.g` behind `isconstrsat(sep, i, …)` (`src/separators.jl:120`) |
-| `ktn_comm_*`, `ktn_allgather_cuts_async`, `ktn_fetch_gathered` | new: constraint rows sharded over the GPUs of a box |
-
-Status codes: `0` OK; `1` = a selected row had a non-finite coefficient (the reference
-sets `m.status = :Error` and warns, `src/model.jl:69-73`; cuts of the rows before it are
-still delivered, as the reference adds them before returning); `< 0` usage / CUDA / NCCL
-error with `ktn_last_error(h)`.
-
-## 3. The Julia shim (`src/gpu_separator.jl`, Julia ≥ 1.0 syntax)
-
-The code of this section and the next ships as `julia/gpu_separator.jl` in this repository (`tests/test_abi.py` keeps file and
-guide identical and checks every `ccall` name and argument count against `include/ktn.h` and the built library; it cannot be
-executed here, the image has no `julia`).
-
-```julia
+# gpu_separator.jl -- the reference-side binding of the B200 separation library (libktn.so, include/ktn.h).
+#
+# A Katana.jl maintainer adds this file to src/ and `include`s it from src/Katana.jl after separators.jl.  It is the code of
+# INTEGRATION.md sections 3-4 verbatim (tests/test_abi.py keeps the two in step and checks every ccall name against the
+# exported symbols).  NOT executed in this repository: the build image has no julia binary.
+#
 mutable struct KatanaGPUSeparator <: AbstractKatanaSeparator
     handle :: Ptr{Cvoid}
     num_var :: Int
@@ -148,15 +104,7 @@ function gencut(sep::KatanaGPUSeparator, xstar, bounds, i)                      
     cols = unsafe_wrap(Array, v[].col, v[].nnz) .+ 1; vals = unsafe_wrap(Array, v[].val, v[].nnz)
     AffExpr([Variable(sep.linear_model, j) for j in cols], copy(vals), unsafe_load(v[].bconst))
 end
-```
 
-## 4. The change in `optimize!` (`src/model.jl:265-283`): cut batching
-
-Replace the per-row `isconstrsat` / `gencut` / `round_coefs` / `_addcut` loop by one round
-and one batched row insertion (§8f item 1 of SURVEY.md). `set_bounds!` is called once after
-`loadproblem!` fills `m.l_constr / m.u_constr` (`src/model.jl:110-167`).
-
-```julia
 xstar = MathProgBase.getsolution(mpb_lp)
 st, v = separate!(m.params.separator, xstar)             # precompute! + test + cuts, ascending row order
 colv = unsafe_wrap(Array, v.col, v.nnz); valv = unsafe_wrap(Array, v.val, v.nnz)
@@ -171,35 +119,3 @@ if st == 1                                                # non-finite coefficie
     Base.warn("Nonlinear constraint or objective likely undefined within domain"); return m.status = :Error
 end
 allsat = v.n_cuts == 0
-```
-
-The view stays valid until the second later `ktn_fetch_cuts_view` on the handle, so the
-rows are consumed before the next `separate!`.
-
-## 5. `nlpeval.jl` (epigraph row)
-
-`EpigraphNLPEvaluator` (`src/nlpeval.jl:6-63`) keeps lifting a nonlinear objective to the
-row `f(x[1:n]) − x[n+1]`; with this library it only has to expose that row through
-`constr_expr` (`:(f(x) - x[n+1] <= 0)`) and mark it `KTN_ROW_NL | KTN_ROW_DENSE`, so that
-its Jacobian row lists every column (`src/nlpeval.jl:49-54`) exactly as the reference does.
-
-## 6. Sharded use (8 GPUs of one box)
-
-One Julia process (or task) per GPU: `ktn_create(device = r)`, load only rows
-`[begin_r, end_r)` (contiguous, balanced by tape bytes — `shard_ranges_by_weight` in `katana.jl_b200/sharding.py` shows
-the split), `ktn_set_row_offset(h, begin_r)`, `ktn_comm_unique_id` on rank 0 → broadcast by
-the host's own means → `ktn_comm_init(h, nranks, r, id)`. Per round:
-`ktn_separate_device_async` / `ktn_separate`, `ktn_allgather_cuts_async`,
-`ktn_sync_gathered`, `ktn_fetch_gathered` — every rank then holds all cuts in ascending
-global row order (rank-major), identical to the single-GPU result. All ranks must enqueue the
-same sequence of exchanges (a rank runs at most two exchanges ahead of the slowest one); the
-transport (`ktn_exchange_transport`: peer push over CUDA IPC + NVLink, or NCCL) is agreed
-collectively at the first exchange. The peer transport needs the ranks to be separate processes
-on one NVLink-connected box; otherwise all ranks use NCCL.
-
-## 7. The `ctypes` binding (what the tests use)
-
-`katana.jl_b200/binding.py` declares every symbol of `include/ktn.h`
-(`tests/test_abi.py` checks header ↔ binding ↔ exported symbols of both `libktn.so` and
-the oracle). `KatanaGPUSeparator` in `separators.py` is the Python twin of the shim above;
-`model.py:optimize` is the twin of §4.

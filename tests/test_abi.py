@@ -49,3 +49,26 @@ def test_product_has_no_cpu_fallback():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "libktn_oracle" not in src and "libktn_emu" not in src and "oracle/" not in src.replace("oracle/ktn_oracle.c", ""), f
+
+
+def test_julia_shim_binds_exported_symbols_and_matches_the_guide():
+    """julia/gpu_separator.jl (the reference-side ccall binding; it cannot run here, there is no julia) names only symbols the
+    library exports, passes as many arguments as the header declares, and is the code INTEGRATION.md prints."""
+    shim = open(os.path.join(ROOT, "julia", "gpu_separator.jl")).read()
+    names = sorted(set(re.findall(r"ccall\(\(:(\w+)", shim)))
+    assert len(names) >= 8
+    dll = ctypes.CDLL(os.path.join(ROOT, "katana.jl_b200", "libktn.so"))
+    assert all(n in declared_symbols() and hasattr(dll, n) for n in names), names
+    # argument counts: the ccall's type tuple against the C prototype
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ktn.h")).read(), flags=re.S)
+    for m in re.finditer(r"ccall\(\(:(\w+),\s*libktn\),\s*\w+,\s*\(([^)]*)\)", shim):
+        name, types = m.group(1), [t for t in m.group(2).split(",") if t.strip()]
+        proto = re.search(r"\b%s\s*\(([^)]*)\)" % name, hdr)
+        assert proto, name
+        nargs = 0 if proto.group(1).strip() in ("", "void") else len(proto.group(1).split(","))
+        assert len(types) == nargs, (name, types, proto.group(1))
+    guide = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```julia\n(.*?)```", guide, flags=re.S)
+    for b in blocks:
+        if b.count("\n") > 5:
+            assert b.strip() in shim
