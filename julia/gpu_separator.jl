@@ -1,7 +1,7 @@
 # gpu_separator.jl -- the reference-side binding of the B200 separation library (libktn.so, include/ktn.h).
 #
 # A Katana.jl maintainer adds this file to src/ and `include`s it from src/Katana.jl after separators.jl.  It is the code of
-# INTEGRATION.md sections 3-4 verbatim (tests/test_abi.py keeps the two in step and checks every ccall name against the
+# INTEGRATION.md sections 3, 4 and 6 verbatim (tests/test_abi.py keeps the two in step and checks every ccall name against the
 # exported symbols).  NOT executed in this repository: the build image has no julia binary.
 #
 mutable struct KatanaGPUSeparator <: AbstractKatanaSeparator
@@ -119,3 +119,33 @@ if st == 1                                                # non-finite coefficie
     Base.warn("Nonlinear constraint or objective likely undefined within domain"); return m.status = :Error
 end
 allsat = v.n_cuts == 0
+
+# Sharded rounds: one process per GPU (e.g. Distributed.jl workers), rank r of nranks owns rows [row_begin, row_end).
+# `id` is the 128-byte communicator id made on rank 0 (ktn_comm_unique_id) and sent to the others by the host's own means.
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    rc = ccall((:ktn_comm_unique_id, libktn), Cint, (Ptr{UInt8},), id)
+    rc < 0 && error("ktn_comm_unique_id failed ($rc)")
+    return id
+end
+
+function join_shards!(sep::KatanaGPUSeparator, nranks::Integer, rank::Integer, id::Vector{UInt8}, row_begin::Integer)
+    check(sep, ccall((:ktn_set_row_offset, libktn), Cint, (Ptr{Cvoid}, Int64), sep.handle, row_begin), "ktn_set_row_offset")
+    check(sep, ccall((:ktn_comm_init, libktn), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), sep.handle, nranks, rank, id), "ktn_comm_init")
+end
+
+# One sharded round: separate this rank's rows at x*, exchange, and return ALL ranks' cuts (global row ids, ascending) as CSR.
+function separate_sharded(sep::KatanaGPUSeparator, xstar::Vector{Float64})
+    nc = Ref{Int64}(0); nz = Ref{Int64}(0); er = Ref{Int64}(-1)
+    st = ccall((:ktn_separate, libktn), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Int64}, Ref{Int64}, Ref{Int64}), sep.handle, xstar, nc, nz, er)
+    check(sep, st, "ktn_separate")
+    check(sep, ccall((:ktn_allgather_cuts_async, libktn), Cint, (Ptr{Cvoid},), sep.handle), "ktn_allgather_cuts_async")
+    check(sep, ccall((:ktn_sync_gathered, libktn), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), sep.handle, nc, nz), "ktn_sync_gathered")
+    n, z = nc[], nz[]
+    row = Vector{Int64}(undef, n); ptr = Vector{Int64}(undef, n + 1); col = Vector{Int32}(undef, z); val = Vector{Float64}(undef, z)
+    lo = Vector{Float64}(undef, n); hi = Vector{Float64}(undef, n)
+    check(sep, ccall((:ktn_fetch_gathered, libktn), Cint,
+                     (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                     sep.handle, row, ptr, col, val, lo, hi, C_NULL, C_NULL, C_NULL), "ktn_fetch_gathered")
+    return st, row .+ 1, ptr .+ 1, col .+ Int32(1), val, lo, hi          # 1-based for Julia; st == 1: a rank met a non-finite cut (:Error)
+end
