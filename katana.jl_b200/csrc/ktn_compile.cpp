@@ -528,8 +528,9 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
             int32_t* dcol = (int32_t*)(base + sec_col);
             for (uint32_t u = 0; u < s.n_uniq; ++u) dcol[(uint64_t)u * L + lane] = rcol[u];
             uint8_t* dord = base + sec_ord;
-            // family chunks (ktn_family.h) carry the inverse permutation: rank[u] = Jacobian entry index of unique variable u
-            if (rankword) { uint64_t w = 0; for (uint32_t p = 0; p < s.n_uniq; ++p) w |= (uint64_t)p << (4 * rord[p]); ((uint64_t*)dord)[lane] = w; continue; }
+            // family chunks (ktn_family.h), rows of <= 16 unique variables: ONE order word, 4 bits per Jacobian entry p = its unique variable;
+            // longer rows carry the inverse permutation: rank[u] = Jacobian entry index of unique variable u
+            if (rankword) { uint64_t w = 0; for (uint32_t p = 0; p < s.n_uniq; ++p) w |= (uint64_t)rord[p] << (4 * p); ((uint64_t*)dord)[lane] = w; continue; }
             if (s.family != KTN_FAM_GENERIC) { for (uint32_t p = 0; p < s.n_uniq; ++p) dord[(uint64_t)rord[p] * L + lane] = (uint8_t)p; continue; }
             for (uint32_t p = 0; p < s.n_uniq; ++p) {
                 uint64_t e = (uint64_t)p * L + lane;
@@ -569,25 +570,14 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
         std::stable_sort(reg.begin(), reg.end(), [&](const Pending& a, const Pending& b) { return key(a) < key(b); });
         std::vector<uint32_t> count((size_t)KTN_FAM__COUNT * KTN_FAM_NCLS + 1, 0u);
         memset(cls_blob_off, 0, sizeof cls_blob_off); memset(cls_blob_stride, 0, sizeof cls_blob_stride);
-        // KTN_PACK=window (experiment): blobs stay in window order; the family kernel then finds them through the descriptors
-        const bool window_pack = getenv("KTN_PACK") && !strcmp(getenv("KTN_PACK"), "window");
-        std::vector<KtnChunkDesc> packed;
-        if (window_pack) {
-            std::vector<size_t> byorig(reg.size());
-            for (size_t i = 0; i < reg.size(); ++i) byorig[i] = i;
-            std::stable_sort(byorig.begin(), byorig.end(), [&](size_t a, size_t b) { return reg[a].orig < reg[b].orig; });
-            packed.resize(reg.size());
-            for (size_t i : byorig) packed[i] = pack_chunk(reg[i].sid, reg[i].rows, reg[i].nr, false);
-        }
         for (size_t i = 0; i < reg.size(); ++i) {
             const Pending& pc = reg[i];
-            KtnChunkDesc cd = window_pack ? packed[i] : pack_chunk(pc.sid, pc.rows, pc.nr, false);
+            KtnChunkDesc cd = pack_chunk(pc.sid, pc.rows, pc.nr, false);
             cd.row_slot = (uint32_t)chunk_rows.size();
             for (int q = 0; q < 32; ++q) chunk_rows.push_back(pc.rows[q]);
             const uint32_t k = key(pc);
             if (count[k]++ == 0) cls_blob_off[k / KTN_FAM_NCLS][k % KTN_FAM_NCLS] = cd.blob_off;
             else if (count[k] == 2) cls_blob_stride[k / KTN_FAM_NCLS][k % KTN_FAM_NCLS] = (uint32_t)(cd.blob_off - chunks.back().blob_off);
-            if (window_pack) cls_blob_stride[k / KTN_FAM_NCLS][k % KTN_FAM_NCLS] = 0xffffffffu;
             chunks.push_back(cd);
         }
         uint32_t at = 0;
@@ -599,6 +589,8 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
         fam_begin[KTN_FAM__COUNT] = at;
     }
     n_regular_chunks = (uint32_t)chunks.size();
+    for (int f = 1; f < KTN_FAM__COUNT; ++f) for (uint32_t k = 1; k < KTN_FAM_NCLS; ++k)      // the family kernels compute a class's blob addresses
+        if (cls_begin[f][k + 1] - cls_begin[f][k] >= 2 && cls_blob_stride[f][k] != KTN_FAM_BLOB_BYTES(k)) { err = "family blob stride"; return KTN_ERR_USAGE; }
     for (size_t c = 0; c < bigp.size(); ++c) {
         const Pending& pc = bigp[c];
         KtnChunkDesc cd = pack_chunk(pc.sid, pc.rows, pc.nr, true);
@@ -609,6 +601,8 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
         chunks.push_back(cd);
     }
     blob.resize(align_up(blob.size(), 128) + 128, 0);
+    row_slot.assign((size_t)num_constr, -1);
+    for (size_t i = 0; i < chunk_rows.size(); ++i) if (chunk_rows[i] >= 0) row_slot[chunk_rows[i]] = (int32_t)i;
     repack_bounds();
     // the ragged per-row staging is no longer needed
     std::vector<double>().swap(rd_const); std::vector<int32_t>().swap(rd_col); std::vector<uint32_t>().swap(rd_order);

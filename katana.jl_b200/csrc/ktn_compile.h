@@ -37,6 +37,7 @@ struct KtnProblem {
     uint32_t cls_blob_stride[KTN_FAM__COUNT][KTN_FAM_NCLS] = {{0}}; // bytes between consecutive chunk blobs of the class (classes >= 1)
     std::vector<uint8_t> blob;
     std::vector<int32_t> chunk_rows;        // chunk * 32 + lane -> row or -1
+    std::vector<int32_t> row_slot;          // row -> chunk * 32 + lane (the inverse of chunk_rows)
     std::vector<double> chunk_lb, chunk_ub; // same indexing
     uint64_t big_scratch_doubles = 0;       // global scratch arena for BIG chunks
     uint32_t max_lane_bytes = 0;            // per-lane shared-memory need of the largest regular shape

@@ -32,7 +32,7 @@
 #include "ktn_interp.h"
 #include "ktn_family.h"
 
-#define KTN_CBLOCK 1024   // threads per compaction block
+#define KTN_CBLOCK 512    // threads per compaction block
 
 namespace {
 
@@ -68,69 +68,35 @@ __device__ __forceinline__ void count_selected(const KtnRoundParams& p, unsigned
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1f: family shapes (ktn_family.h).  Persistent: ONE block of 16 warps per SM; one warp per chunk, one thread per row.
+// K1f: family shapes (ktn_family.h).  Persistent: ONE block of 16 warps per SM; one thread per row.
 //   * a row is register resident: every constant and column id of the row is requested at once with coalesced loads straight
-//     from the chunk blob (lane stride 32, streamed past L1), x* is gathered through L1 / L2, g is evaluated and tested, and
-//     the selected lanes build their cut row from the same registers;
+//     from the chunk blob (lane stride 32), x* is gathered through L1 / L2, g is evaluated and tested.  NOTHING of the row is
+//     kept for the cut: a selected row leaves one 32-byte record {g, aux, lb, ub} and the compaction kernel builds its cut
+//     (one thread per selected row, lane-dense whatever the violated fraction).  Building the cut here, in lanes that are 90 %
+//     idle, costs 22-45 us of the round whichever way its operands are kept or re-read (profiles/microbench/mb5-mb7).
 //   * every class (rows of exactly k unique variables) has its own ticket counter, its own contiguous range of equally sized
-//     blobs (no descriptor to fetch) and its own specialised, fully unrolled code path; the warps of an SM start in the same
-//     class (classes are spread over the SMs in proportion to their work) and move on together, so the instruction working
-//     set is one class, not the whole kernel.
-// Measured and dropped (profiles/microbench/mb2.cu): a TMA producer/consumer ring, a shared-memory cache
-// of x*, block-pooled lane-dense cuts, L2 bulk prefetch of the next chunk, cp.async prefetch of the next chunk's column ids,
-// more warps at fewer registers.  What bounds the kernel is the x* gather: an SM's L1 -> crossbar port takes about one
-// 32-byte sector per clock, and shrinking L1 (by using shared memory) shrinks the SM's outstanding-miss capacity.
+//     blobs (no descriptor to fetch) and its own fully unrolled code path; the warps of an SM start in the same class (classes
+//     are spread over the SMs in proportion to their work) and move on together, so the instruction working set is one class.
+//   * short rows run R = 16 / k chunks per warp iteration (R rows per thread): the loads in flight per warp, not the warps,
+//     are what hides the two dependent round trips (constants, then the x* gather); measured 2.8 -> 3.3 TB/s for k = 4.
+// Measured and dropped (profiles/microbench/mb2.cu, mb4.cu): TMA / cp.async pipelines through shared
+// memory and a shared-memory cache of x* (every shared-memory byte is taken from L1, whose lines are the SM's outstanding-miss
+// capacity: 200 KB of idle shared memory alone slow the kernel down 2.2x), L2 prefetch, more warps at fewer registers.
 // ---------------------------------------------------------------------------------------------
-// tuning knob (scripts/build_variants.sh builds A/B variants of the library with -D overrides)
-#ifndef KTN_OPT_PASS
-#define KTN_OPT_PASS 16
-#endif
 #define KTN_FP_WARPS 16
-#ifndef KTN_FWD_BLOCKS
-#define KTN_FWD_BLOCKS 2                                    // blocks per SM of the evaluation-only instantiation
-#endif
-#define KTN_FW_PASS KTN_OPT_PASS                          // selected lanes that build their cut at the same time (scratch cells per entry)
-#define KTN_FP_SMEM (128 + KTN_FP_WARPS * KTN_FAM_REGS * KTN_FW_PASS * 8)   // [0,128): per-warp ticket mailboxes; then the warps' cut scratch
+#define KTN_FP_SMEM 0
 
 #ifdef KTN_OPT_TIMING
-// debug build only (scripts/build_variants.sh ... "-DKTN_OPT_TIMING"): per-phase warp cycles, summed over all warps
 __device__ unsigned long long ktn_dbg_cycles[16];
-#define KTN_T(var) const long long var = clock64()
-#define KTN_TADD(i, a, b) do { if ((threadIdx.x & 31u) == 0) atomicAdd(&ktn_dbg_cycles[i], (unsigned long long)((b) - (a))); } while (0)
-#else
-#define KTN_T(var)
-#define KTN_TADD(i, a, b)
 #endif
 
-// read-only streaming loads that do not allocate in L1 (plain asm, not volatile: the compiler may batch and hoist them)
-__device__ __forceinline__ double ldg_stream(const double* p) {
-    double v; asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
-}
-__device__ __forceinline__ int32_t ldg_stream(const int32_t* p) {
-    int32_t v; asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
-}
-__device__ __forceinline__ uint64_t ldg_stream(const uint64_t* p) {
-    uint64_t v; asm("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v;
-}
-__device__ __forceinline__ uint32_t ldg_stream(const uint8_t* p) {
-    uint32_t v; asm("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v;
-}
-
-struct FamRow {     // row context of ktn_family.h: the chunk's SoA sections in global memory, lane offset applied
+struct FamRow {     // streaming row context of ktn_family.h (class 0): the chunk's SoA sections in global memory, lane offset applied
     const double* C; const int32_t* cols; const uint8_t* rk; const double* X; uint32_t nu;
-    __device__ __forceinline__ double cst(uint32_t i) const { return ldg_stream(C + i * 32u); }
-    __device__ __forceinline__ int32_t col(uint32_t u) const { return ldg_stream(cols + u * 32u); }
+    __device__ __forceinline__ double cst(uint32_t i) const { return __ldg(C + i * 32u); }
+    __device__ __forceinline__ int32_t col(uint32_t u) const { return __ldg(cols + u * 32u); }
     __device__ __forceinline__ double xat(int32_t c) const { return __ldg(X + c); }
     __device__ __forceinline__ double x(uint32_t u) const { return xat(col(u)); }
-    __device__ __forceinline__ uint32_t rank(uint32_t u) const { return ldg_stream(rk + u * 32u); }     // streaming rows: one byte per u
-    __device__ __forceinline__ uint64_t rankword() const { return ldg_stream(reinterpret_cast<const uint64_t*>(rk)); }
-};
-struct FamSink {    // cut-row sink: products in the warp's shared-memory scratch, coefficients in the staging CSR
-    double* t; double* out;
-    __device__ __forceinline__ void put_t(uint32_t q, double v) { t[q * KTN_FW_PASS] = v; }
-    __device__ __forceinline__ double get_t(uint32_t q) const { return t[q * KTN_FW_PASS]; }
-    __device__ __forceinline__ void put_j(uint32_t q, double v) { out[q] = v; }
-    __device__ __forceinline__ double get_j(uint32_t q) const { return out[q]; }
+    __device__ __forceinline__ uint32_t rank(uint32_t u) const { return __ldg(rk + u * 32u); }
 };
 struct FamStreamSink {
     double* out; const int32_t* scol; const double* X;
@@ -139,143 +105,125 @@ struct FamStreamSink {
     __device__ __forceinline__ double xsorted(uint32_t q) const { return __ldg(X + __ldg(scol + q)); }
 };
 
-__device__ __forceinline__ void family_finish_row(const KtnRoundParams& p, unsigned grp, int32_t row, uint32_t nu, double b, bool bad) {
-    p.b_row[row] = b;
-    p.sel[row] = nu | (bad ? KTN_SEL_ERRBIT : 0u);
-    if (bad) atomicMin(&p.counts[2 + (p.epoch & 1u)], (unsigned long long)row + 1ull);
-    count_selected(p, grp, row, nu);
-}
-
-__device__ __forceinline__ const unsigned char* family_blob(const KtnRoundParams& p, uint32_t cls, uint32_t c) {
-    return p.blob + p.cls_blob_off[cls] + (size_t)(c - p.cls_begin[cls]) * p.cls_blob_stride[cls];
-}
-
-// One chunk.  N = 1..16: register-resident rows of exactly N unique variables (class blobs are contiguous and equally sized:
-// no descriptor); N = 0: streaming fallback (any count) through the chunk descriptor.
-// FWD: evaluation only (ktn_eval_g), compiled without the cut path: the row's registers die as they are used, the kernel needs
-// half the registers and runs two blocks per SM.
-template <int FAM, int N, bool FWD>
-__device__ __forceinline__ void family_chunk(const KtnRoundParams& p, uint32_t c, uint32_t lane, double* scratch, unsigned int* ticket, uint32_t* next) {
+// class 0: rows of more than KTN_FAM_REGS unique variables, one chunk per ticket, cut built here (streaming fallbacks)
+template <int FAM>
+__device__ __forceinline__ void family_stream_class(const KtnRoundParams& p, uint32_t lane, unsigned int* tk) {
     typedef KtnFamily<FAM> F;
-    const uint32_t slotid = c * 32u + lane;
-    uint32_t nu = (uint32_t)N;
-    const unsigned char* blob;
-    if (N > 0 && p.cls_blob_stride[N > 0 ? N : 0] != 0xffffffffu) blob = family_blob(p, (uint32_t)N, c);
-    else { const KtnChunkDesc cd = p.chunks[c]; nu = (uint32_t)cd.aux; blob = p.blob + cd.blob_off; }
-    const FamRow r{reinterpret_cast<const double*>(blob) + lane, reinterpret_cast<const int32_t*>(blob + 512u * nu) + lane,
-                   blob + 640u * nu + (N > 0 ? lane * 8u : lane), p.x, nu};
-    constexpr int NR = N > 0 ? N : 1;
-    KtnFamRegs<NR> v;
-    double aux, g;
-    KTN_T(t0);
-    if constexpr (N > 0 && FWD) {
-        g = F::template forward_only<NR>(r, [&]() { if (lane == 0) *next = atomicAdd(ticket, 1u); });
-        aux = 0.0;
-    } else if constexpr (N > 0) {
-        int32_t col[NR];
-        ktn_family_load<FAM, NR>(r, v, col);
-        // the warp's next ticket is drawn HERE, behind the row's loads, and parked in shared memory: its round trip overlaps
-        // theirs (drawn before the loads, the compiler spills the result at once and the chunk starts with a stall)
-        if (lane == 0) *next = atomicAdd(ticket, 1u);
-        g = ktn_family_eval<FAM, NR>(r, v, col, aux);
-    } else {
-        if (lane == 0) *next = atomicAdd(ticket, 1u);
-        g = F::forward_stream(r, aux);
-    }
-    const int32_t row = ldg_stream(p.chunk_rows + slotid);
-    if constexpr (FWD) { if (row >= 0) p.g_row[row] = g; return; }
-    double lb = 0.0, ub = 0.0;
-    if (p.mode != KTN_MODE_EVAL) { lb = ldg_stream(p.chunk_lb + slotid); ub = ldg_stream(p.chunk_ub + slotid); }
-#ifdef KTN_OPT_TIMING
-    asm volatile("" ::"d"(g));
-#endif
-    KTN_T(t1);
-    if (row >= 0) p.g_row[row] = g;
-    if (p.mode == KTN_MODE_EVAL) return;
-    const bool selected = row >= 0 && row_selected(p, g, lb, ub, row);
-    if (row >= 0 && !selected) p.sel[row] = 0u;
-    unsigned selm = __ballot_sync(0xffffffffu, selected);
-    KTN_T(t2);
-    KTN_TADD(0, t0, t1); KTN_TADD(1, t1, t2);
-    KTN_TADD(4, 0, 1); KTN_TADD(5, 0, __popc(selm)); KTN_TADD(6, 0, (__popc(selm) + KTN_FW_PASS - 1) / KTN_FW_PASS);
-    if constexpr (N > 0) {
-        while (selm) {      // KTN_FW_PASS selected lanes at a time share the warp's scratch
-            const uint32_t cut = __fns(selm, 0, KTN_FW_PASS + 1);
-            const unsigned grp = cut == 0xffffffffu ? selm : (selm & ((1u << cut) - 1u));
-            if ((grp >> lane) & 1u) {
-                FamSink s{scratch + __popc(grp & ((1u << lane) - 1u)), p.stage_val + p.jac_ptr[row]};
-                double b;
-                const bool bad = ktn_family_cut<FAM, NR>(r, v, s, g, aux, p.do_round != 0, p.rng, b);
-                family_finish_row(p, grp, row, nu, b, bad);
-            }
-            __syncwarp();
-            selm &= ~grp;
+    const uint32_t base = p.cls_begin[FAM][0], n = p.cls_begin[FAM][1] - base;
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(tk, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n) return;
+        const uint32_t c = base + t, slotid = c * 32u + lane;
+        const KtnChunkDesc cd = p.chunks[c];
+        const uint32_t nu = (uint32_t)cd.aux;
+        const unsigned char* blob = p.blob + cd.blob_off;
+        const FamRow r{reinterpret_cast<const double*>(blob) + lane, reinterpret_cast<const int32_t*>(blob + 512u * nu) + lane, blob + 640u * nu + lane, p.x, nu};
+        double aux;
+        const double g = F::forward_stream(r, aux);
+        const int32_t row = __ldg(p.chunk_rows + slotid);
+        if (row >= 0) p.g_row[row] = g;
+        if (p.mode == KTN_MODE_EVAL) continue;
+        const bool selected = row >= 0 && row_selected(p, g, __ldg(p.chunk_lb + slotid), __ldg(p.chunk_ub + slotid), row);
+        if (row >= 0 && !selected) p.sel[row] = 0u;
+        const unsigned selm = __ballot_sync(0xffffffffu, selected);
+        if (selected) {
+            const int64_t jb = p.jac_ptr[row];
+            FamStreamSink s{p.stage_val + jb, p.jac_col + jb, p.x};
+            double b;
+            const bool bad = ktn_family_cut_stream<FAM>(r, s, g, aux, p.do_round != 0, p.rng, b);
+            p.b_row[row] = b;
+            p.sel[row] = nu | (bad ? KTN_SEL_ERRBIT : 0u);
+            if (bad) atomicMin(&p.counts[2 + (p.epoch & 1u)], (unsigned long long)row + 1ull);
+            count_selected(p, selm, row, nu);
         }
-        KTN_T(t3);
-        KTN_TADD(2, t2, t3);
-    } else if (selected) {
-        const int64_t base = p.jac_ptr[row];
-        FamStreamSink s{p.stage_val + base, p.jac_col + base, p.x};
-        double b;
-        const bool bad = ktn_family_cut_stream<FAM>(r, s, g, aux, p.do_round != 0, p.rng, b);
-        family_finish_row(p, selm, row, nu, b, bad);
     }
 }
 
-template <int FAM, bool FWD>
-__device__ __forceinline__ void family_dispatch(const KtnRoundParams& p, uint32_t cls, uint32_t c, uint32_t lane, double* scratch, unsigned int* ticket, uint32_t* next) {
-    switch (cls) {
-#define KTN_CASE(n) case n: family_chunk<FAM, n, FWD>(p, c, lane, scratch, ticket, next); break;
-        KTN_CASE(1) KTN_CASE(2) KTN_CASE(3) KTN_CASE(4) KTN_CASE(5) KTN_CASE(6) KTN_CASE(7) KTN_CASE(8)
-        KTN_CASE(9) KTN_CASE(10) KTN_CASE(11) KTN_CASE(12) KTN_CASE(13) KTN_CASE(14) KTN_CASE(15) KTN_CASE(16)
-#undef KTN_CASE
-        default: family_chunk<FAM, 0, FWD>(p, c, lane, scratch, ticket, next); break;
+// class N = 1..16: R chunks per warp iteration, the R rows of a thread in registers
+template <int FAM, int N, int R>
+__device__ __forceinline__ void family_class(const KtnRoundParams& p, uint32_t lane, unsigned int* tk) {
+    typedef KtnFamily<FAM> F;
+    const uint32_t base = p.cls_begin[FAM][N], n = p.cls_begin[FAM][N + 1] - base;
+    const unsigned char* const blob0 = p.blob + p.cls_blob_off[FAM][N];
+    uint32_t t0 = 0;
+    if (lane == 0) t0 = atomicAdd(tk, (unsigned)R);
+    uint32_t cur = __shfl_sync(0xffffffffu, t0, 0);
+    while (cur < n) {
+        KtnFamRegs<N> v[R]; int32_t col[R][N]; int32_t row[R]; double lb[R], ub[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t ch = cur + r < n ? cur + r : n - 1;      // past the end: the last chunk again, results dropped
+            const unsigned char* blob = blob0 + (size_t)ch * KTN_FAM_BLOB_BYTES(N);
+            const double* C = reinterpret_cast<const double*>(blob) + lane;
+            const int32_t* cols = reinterpret_cast<const int32_t*>(blob + 512u * N) + lane;
+            const uint32_t slotid = (base + ch) * 32u + lane;
+#pragma unroll
+            for (int u = 0; u < N; ++u) { v[r].p0[u] = __ldg(C + F::slot0(u, N) * 32u); v[r].p1[u] = __ldg(C + F::slot1(u, N) * 32u); col[r][u] = __ldg(cols + u * 32u); }
+            row[r] = __ldg(p.chunk_rows + slotid);
+            if (cur + r >= n) row[r] = -1;
+            lb[r] = __ldg(p.chunk_lb + slotid); ub[r] = __ldg(p.chunk_ub + slotid);
+        }
+        // the warp's next ticket is drawn HERE, behind the rows' loads: its round trip overlaps theirs
+        uint32_t tn = 0;
+        if (lane == 0) tn = atomicAdd(tk, (unsigned)R);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int u = 0; u < N; ++u) v[r].x[u] = __ldg(p.x + col[r][u]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double aux;
+            const double g = F::template forward<N>(v[r], aux);
+            if (row[r] >= 0) p.g_row[row[r]] = g;
+            if (p.mode == KTN_MODE_EVAL) continue;
+            const bool selected = row[r] >= 0 && row_selected(p, g, lb[r], ub[r], row[r]);
+            if (row[r] >= 0 && !selected) p.sel[row[r]] = 0u;
+            const unsigned selm = __ballot_sync(0xffffffffu, selected);
+            if (selected) {
+                p.rec[row[r]] = make_double4(g, aux, lb[r], ub[r]);
+                p.sel[row[r]] = (uint32_t)N | KTN_SEL_DEFER;
+                count_selected(p, selm, row[r], (uint32_t)N);
+            }
+        }
+        cur = __shfl_sync(0xffffffffu, tn, 0);
     }
 }
 
-template <int FAM, bool FWD>
-__global__ void __launch_bounds__(KTN_FP_WARPS * 32, FWD ? KTN_FWD_BLOCKS : 1) ktn_family_kernel(const KtnRoundParams p) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    double* scratch = reinterpret_cast<double*>(smem + 128) + (size_t)(threadIdx.x >> 5) * (KTN_FAM_REGS * KTN_FW_PASS);
+template <int FAM>
+__global__ void __launch_bounds__(KTN_FP_WARPS * 32, 1) ktn_family_kernel(const KtnRoundParams p) {
     const uint32_t lane = threadIdx.x & 31u;
-    uint32_t* next = reinterpret_cast<uint32_t*>(smem) + (threadIdx.x >> 5);       // per-warp mailbox of the next ticket
     unsigned int* tickets = p.ticket + p.ticket_idx;
-    const uint32_t my_n = lane < KTN_FAM_NCLS ? p.cls_begin[lane + 1] - p.cls_begin[lane] : 0u;     // lane k: chunks of class k
+    const uint32_t my_n = lane < KTN_FAM_NCLS ? p.cls_begin[FAM][lane + 1] - p.cls_begin[FAM][lane] : 0u;     // lane k: chunks of class k
     uint32_t cls = 0;
     {
         uint32_t smid, nsm;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
         asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
         unsigned long long total = 0, acc = 0;
-        for (uint32_t k = 0; k < KTN_FAM_NCLS; ++k) total += (unsigned long long)(p.cls_begin[k + 1] - p.cls_begin[k]) * ((k ? k : 32u) + 3u);
+        for (uint32_t k = 0; k < KTN_FAM_NCLS; ++k) total += (unsigned long long)(p.cls_begin[FAM][k + 1] - p.cls_begin[FAM][k]) * ((k ? k : 32u) + 3u);
         const unsigned long long target = (total * (2ull * smid + 1ull)) / (2ull * nsm);
         for (uint32_t k = 0; k < KTN_FAM_NCLS; ++k) {
-            acc += (unsigned long long)(p.cls_begin[k + 1] - p.cls_begin[k]) * ((k ? k : 32u) + 3u);
+            acc += (unsigned long long)(p.cls_begin[FAM][k + 1] - p.cls_begin[FAM][k]) * ((k ? k : 32u) + 3u);
             if (acc > target) { cls = k; break; }
         }
     }
-    auto take = [&](uint32_t k) -> uint32_t { uint32_t t = 0; if (lane == 0) t = atomicAdd(&tickets[k], 1u); return t; };
-    auto bcast = [&](uint32_t t) -> uint32_t { return __shfl_sync(0xffffffffu, t, 0); };
-    uint32_t n_cls = p.cls_begin[cls + 1] - p.cls_begin[cls];
-    uint32_t cur = n_cls ? bcast(take(cls)) : 0u;
     for (;;) {
-        if (cur >= n_cls) {
-            // this class is dry: one look at every class counter picks the next live class
-            const bool live = lane < KTN_FAM_NCLS && my_n > 0 && __ldcg(&tickets[lane]) < my_n;
-            const unsigned livem = __ballot_sync(0xffffffffu, live);
-            if (!livem) return;
-            const unsigned ahead = livem & ~((2u << cls) - 1u);        // first live class after cls, cyclically
-            cls = (uint32_t)__ffs(ahead ? ahead : livem) - 1u;
-            n_cls = p.cls_begin[cls + 1] - p.cls_begin[cls];
-            cur = bcast(take(cls));
-            continue;
+        // rows per thread: 16 / k, at most 4
+        switch (cls) {
+#define KTN_CASE(n, r) case n: family_class<FAM, n, r>(p, lane, &tickets[n]); break;
+            KTN_CASE(1, 4) KTN_CASE(2, 4) KTN_CASE(3, 4) KTN_CASE(4, 4) KTN_CASE(5, 3) KTN_CASE(6, 2) KTN_CASE(7, 2) KTN_CASE(8, 2)
+            KTN_CASE(9, 1) KTN_CASE(10, 1) KTN_CASE(11, 1) KTN_CASE(12, 1) KTN_CASE(13, 1) KTN_CASE(14, 1) KTN_CASE(15, 1) KTN_CASE(16, 1)
+#undef KTN_CASE
+            default: family_stream_class<FAM>(p, lane, &tickets[0]); break;
         }
-        family_dispatch<FAM, FWD>(p, cls, p.cls_begin[cls] + cur, lane, scratch, &tickets[cls], next);   // draws the next ticket on the way
-        KTN_T(tb);
-        __syncwarp();
-        cur = *reinterpret_cast<volatile uint32_t*>(next);
-        KTN_T(tc);
-        KTN_TADD(3, tb, tc);
+        // this class is dry: one look at every class counter picks the next live class
+        const bool live = lane < KTN_FAM_NCLS && my_n > 0 && __ldcg(&tickets[lane]) < my_n;
+        const unsigned livem = __ballot_sync(0xffffffffu, live);
+        if (!livem) return;
+        const unsigned ahead = livem & ~((2u << cls) - 1u);        // first live class after cls, cyclically
+        cls = (uint32_t)__ffs(ahead ? ahead : livem) - 1u;
     }
 }
 
@@ -518,11 +466,18 @@ __global__ void __launch_bounds__(128) ktn_big_kernel(const KtnRoundParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: ordered stream compaction; block offsets come from the per-block cut counts K1 left in blk_cnt.
-// Selected rows -> CSR in ascending row order (the loop order of src/model.jl:272).
+// K2: ordered stream compaction + the cuts of the family rows.  Selected rows -> CSR in ascending row order (the loop order of
+// src/model.jl:272); block offsets come from the per-block cut counts K1 left in blk_cnt (no look-back chain).
+//   A  flags of the block's KTN_CROWS rows, block scan -> compact list of the selected rows with their entry offsets
+//   B  one thread per SELECTED row: bounds shift, violation, and -- for a family row (KTN_SEL_DEFER) -- the row's cut
+//      (ktn_family_cut_entries: coefficients and columns written straight to their final place, constant b in entry order)
+//   C  rows whose cut K1 built (interpreter shapes, long rows, the dense epigraph row): coalesced copy from the staging CSR
+//   D  the LAST block to finish settles the first non-finite row (src/model.jl:69-73, :278), writes totals and blob header and
+//      re-arms the per-round state
 // ---------------------------------------------------------------------------------------------
+#define KTN_CWARPS (KTN_CBLOCK / 32)
 __device__ __forceinline__ void block_scan2(uint32_t& a, unsigned long long& b, uint32_t& ta, unsigned long long& tb) {
-    // exclusive scan of (a, b) over a 1024-thread block; totals in (ta, tb)
+    // exclusive scan of (a, b) over the block; totals in (ta, tb)
     __shared__ uint32_t wa[32];
     __shared__ unsigned long long wb[32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -535,7 +490,7 @@ __device__ __forceinline__ void block_scan2(uint32_t& a, unsigned long long& b, 
     if (lane == 31) { wa[warp] = ia; wb[warp] = ib; }
     __syncthreads();
     if (warp == 0) {
-        uint32_t va = wa[lane]; unsigned long long vb = wb[lane];
+        uint32_t va = lane < KTN_CWARPS ? wa[lane] : 0u; unsigned long long vb = lane < KTN_CWARPS ? wb[lane] : 0ull;
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t na = __shfl_up_sync(0xffffffffu, va, o);
             const unsigned long long nb = __shfl_up_sync(0xffffffffu, vb, o);
@@ -551,20 +506,39 @@ __device__ __forceinline__ void block_scan2(uint32_t& a, unsigned long long& b, 
     __syncthreads();
 }
 
+struct CutRow {     // row context of ktn_family_cut_entries: the chunk's SoA sections in global memory, lane offset applied
+    const double* C; const int32_t* cols; const double* X;
+    __device__ __forceinline__ double cst(uint32_t i) const { return __ldg(C + i * 32u); }
+    __device__ __forceinline__ int32_t col(uint32_t u) const { return __ldg(cols + u * 32u); }
+    __device__ __forceinline__ double xat(int32_t c) const { return __ldg(X + c); }
+};
+struct CutSink {    // the row's slice of the round's CSR
+    double* val; int32_t* col;
+    __device__ __forceinline__ void put(uint32_t q, double v, int32_t c) { val[q] = v; col[q] = c; }
+    __device__ __forceinline__ double get(uint32_t q) const { return val[q]; }
+    __device__ __forceinline__ void set(uint32_t q, double v) { val[q] = v; }
+};
+
 // One block = KTN_CBLOCK threads x KTN_CRPT consecutive rows per thread = KTN_CROWS rows.
 #define KTN_CRPT (KTN_CROWS / KTN_CBLOCK)
 __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRoundParams p, uint32_t nblocks, uint32_t epoch) {
-    __shared__ uint32_t s_cnt_base; __shared__ unsigned long long s_nnz_base, s_tot_n, s_tot_nz;
+    __shared__ uint32_t s_cnt_base, s_first_bad, s_copy, s_last; __shared__ unsigned long long s_nnz_base, s_tot_n, s_tot_nz;
     __shared__ unsigned long long s_red[4][32];
     __shared__ uint32_t s_off[KTN_CROWS + 1];        // exclusive nnz offsets of the block's selected rows (compact list)
-    __shared__ uint32_t s_src[KTN_CROWS];            // first staging entry of each selected row (jac_ptr; the library caps nnz(J) at 2^32 - 1)
-    __shared__ uint16_t s_rowl[KTN_CROWS];           // block-local row index of each selected row
+    __shared__ uint32_t s_src[KTN_CROWS];            // first staging entry of each selected row whose cut K1 built (jac_ptr; the library caps nnz(J) at 2^32 - 1)
+    __shared__ uint16_t s_rowl[KTN_CROWS];           // block-local row index of each selected row | 0x8000 non-finite (K1) | 0x4000 deferred
     const uint32_t bid = blockIdx.x;
     const int64_t row0 = (int64_t)bid * KTN_CROWS, i0 = row0 + (int64_t)threadIdx.x * KTN_CRPT;
+    if (threadIdx.x == 0) { s_first_bad = 0xffffffffu; s_copy = 0u; }
     // every independent load of the block is requested up front: the row flags, then K1's per-block counts
     uint32_t sv[KTN_CRPT];
-    if (i0 + KTN_CRPT <= p.num_rows) { const uint4 q = *reinterpret_cast<const uint4*>(p.sel + i0); sv[0] = q.x; sv[1] = q.y; sv[2] = q.z; sv[3] = q.w; }
-    else for (int r = 0; r < KTN_CRPT; ++r) sv[r] = (i0 + r < p.num_rows) ? p.sel[i0 + r] : 0u;
+    if (i0 + KTN_CRPT <= p.num_rows) {
+#pragma unroll
+        for (int r = 0; r < KTN_CRPT; r += 4) { const uint4 q = *reinterpret_cast<const uint4*>(p.sel + i0 + r); sv[r] = q.x; sv[r + 1] = q.y; sv[r + 2] = q.z; sv[r + 3] = q.w; }
+    } else {
+#pragma unroll
+        for (int r = 0; r < KTN_CRPT; ++r) sv[r] = (i0 + r < p.num_rows) ? p.sel[i0 + r] : 0u;
+    }
     // output offset of this block = cuts / nnz of all blocks before it; the totals of ALL blocks fix the blob's layout
     unsigned long long* bc = p.blk_cnt + (size_t)(epoch & 1u) * p.blk_stride;
     {
@@ -582,12 +556,12 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
     }
     uint32_t a = 0; unsigned long long b = 0;
 #pragma unroll
-    for (int r = 0; r < KTN_CRPT; ++r) { a += sv[r] ? 1u : 0u; b += sv[r] & ~KTN_SEL_ERRBIT; }
+    for (int r = 0; r < KTN_CRPT; ++r) { a += sv[r] ? 1u : 0u; b += KTN_SEL_NNZ(sv[r]); }
     uint32_t ta; unsigned long long tb;
     block_scan2(a, b, ta, tb);      // contains the barriers that publish s_red
     unsigned long long* const hdr = reinterpret_cast<unsigned long long*>(p.out_blob);
     if (threadIdx.x < 32) {
-        const bool live = threadIdx.x < KTN_CBLOCK / 32;
+        const bool live = threadIdx.x < KTN_CWARPS;
         unsigned long long cb = live ? s_red[0][threadIdx.x] : 0ull, nb = live ? s_red[1][threadIdx.x] : 0ull;
         unsigned long long ca = live ? s_red[2][threadIdx.x] : 0ull, na = live ? s_red[3][threadIdx.x] : 0ull;
         for (int o = 16; o > 0; o >>= 1) {
@@ -597,17 +571,7 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
         if (threadIdx.x == 0) {
             s_cnt_base = (uint32_t)cb; s_nnz_base = nb; s_tot_n = ca; s_tot_nz = na;
             p.blk_cnt[(size_t)((epoch & 1u) ^ 1u) * p.blk_stride + bid] = 0ull;     // re-arm the slot the NEXT round's K1 adds into
-            if (bid == nblocks - 1) {   // totals, and re-arm the per-round device state
-                const unsigned long long err = p.counts[2 + (epoch & 1u)];   // written by this round's K1 only
-                p.counts[4] = cb + ta; p.counts[5] = nb + tb; p.counts[6] = err;
-                p.counts[2 + ((epoch & 1u) ^ 1u)] = ~0ull;                    // re-arm the slot the NEXT round's K1 uses
-                if (err == ~0ull) { p.counts[0] = cb + ta; p.counts[1] = nb + tb; hdr[0] = cb + ta; hdr[1] = nb + tb; }
-                const KtnPackLayout La = ktn_pack_layout(ca, na);
-                hdr[2] = err; hdr[3] = La.total; hdr[4] = (unsigned long long)p.row_offset; hdr[5] = ca; hdr[6] = na; hdr[7] = 0ull;
-                reinterpret_cast<int64_t*>(p.out_blob + La.row_ptr)[ca] = (int64_t)na;
-            }
         }
-        if (bid == nblocks - 1) for (uint32_t i = threadIdx.x; i < KTN_TICKETS; i += 32) p.ticket[i] = 0u;     // K1 is over: re-arm its work tickets
     }
     __syncthreads();
     const uint32_t cbase = s_cnt_base; const unsigned long long nbase = s_nnz_base;
@@ -617,54 +581,97 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
     double* const out_g = reinterpret_cast<double*>(p.out_blob + L.g); double* const out_viol = reinterpret_cast<double*>(p.out_blob + L.viol);
     double* const out_b = reinterpret_cast<double*>(p.out_blob + L.b);
     int32_t* const out_col = reinterpret_cast<int32_t*>(p.out_blob + L.col); double* const out_val = reinterpret_cast<double*>(p.out_blob + L.val);
-    // compact list of the block's selected rows: local row index (bit 15: non-finite flag) and nnz offset
+    // A: compact list of the block's selected rows: local row index (+ flags) and nnz offset
 #pragma unroll
     for (int r = 0; r < KTN_CRPT; ++r) {
         const uint32_t s = sv[r];
         if (!s) continue;
-        s_off[a] = (uint32_t)b; s_rowl[a] = (uint16_t)((threadIdx.x * KTN_CRPT + r) | ((s & KTN_SEL_ERRBIT) ? 0x8000u : 0u));
-        a += 1u; b += s & ~KTN_SEL_ERRBIT;
+        s_off[a] = (uint32_t)b;
+        s_rowl[a] = (uint16_t)((threadIdx.x * KTN_CRPT + r) | ((s & KTN_SEL_ERRBIT) ? 0x8000u : 0u) | ((s & KTN_SEL_DEFER) ? 0x4000u : 0u));
+        a += 1u; b += KTN_SEL_NNZ(s);
     }
     if (threadIdx.x == 0) s_off[ta] = (uint32_t)tb;
     __syncthreads();
-    // one thread per SELECTED row: its five scalars are independent loads, its outputs are coalesced
+    // B: one thread per SELECTED row
     for (uint32_t k = threadIdx.x; k < ta; k += KTN_CBLOCK) {
         const uint32_t rl = s_rowl[k];
-        const int64_t i = row0 + (rl & 0x7fffu);
-        const double g = p.g_row[i], bcst = p.b_row[i], lb = p.row_lb[i], ub = p.row_ub[i];
-        s_src[k] = (uint32_t)p.jac_ptr[i];
+        const int64_t i = row0 + (rl & 0x3fffu);
         const int64_t cidx = (int64_t)cbase + k, o = (int64_t)(nbase + s_off[k]);
+        double g, bcst, lb, ub; bool bad;
+        if (rl & 0x4000u) {
+            const double4 rc = p.rec[i];
+            const uint32_t slot = (uint32_t)__ldg(p.row_slot + i), c = slot >> 5, lane = slot & 31u, nu = s_off[k + 1] - s_off[k];
+            g = rc.x; lb = rc.z; ub = rc.w;
+            const int fam = c >= p.fam_begin[KTN_FAM_QUAD] ? KTN_FAM_QUAD : KTN_FAM_LSE;
+            const unsigned char* blob = p.blob + p.cls_blob_off[fam][nu] + (size_t)(c - p.cls_begin[fam][nu]) * KTN_FAM_BLOB_BYTES(nu);
+            const uint64_t ow = __ldg(reinterpret_cast<const unsigned long long*>(blob + 640u * nu) + lane);
+            const CutRow r{reinterpret_cast<const double*>(blob) + lane, reinterpret_cast<const int32_t*>(blob + 512u * nu) + lane, p.x};
+            CutSink s{out_val + o, out_col + o};
+            if (fam == KTN_FAM_LSE) bad = ktn_family_cut_entries<KTN_FAM_LSE>(r, nu, ow, s, g, rc.y, p.do_round != 0, p.rng, bcst);
+            else bad = ktn_family_cut_entries<KTN_FAM_QUAD>(r, nu, ow, s, g, rc.y, p.do_round != 0, p.rng, bcst);
+        } else {
+            g = p.g_row[i]; bcst = p.b_row[i]; lb = p.row_lb[i]; ub = p.row_ub[i];
+            s_src[k] = (uint32_t)p.jac_ptr[i];
+            bad = (rl & 0x8000u) != 0u;
+            s_copy = 1u;
+        }
         out_row[cidx] = i + p.row_offset; out_ptr[cidx] = o;
         out_lo[cidx] = lb - bcst; out_hi[cidx] = ub - bcst;     // src/model.jl:74-75
         out_g[cidx] = g; out_b[cidx] = bcst;
         const double v1 = lb - g, v2 = g - ub;
         out_viol[cidx] = (g == g) ? (v1 > v2 ? v1 : v2) : g;
-        // the reference stops at the first non-finite cut (src/model.jl:278): cuts before it stand
-        if ((rl & 0x8000u) && (unsigned long long)i + 1ull == p.counts[2 + (epoch & 1u)]) { p.counts[0] = (unsigned long long)cidx; p.counts[1] = (unsigned long long)o; hdr[0] = (unsigned long long)cidx; hdr[1] = (unsigned long long)o; }
+        if (bad) atomicMin(&s_first_bad, k);
     }
     __syncthreads();
-    // expand: one thread per output entry, coalesced writes.  Every warp owns a contiguous range of the block's entries: one
-    // binary search (shared memory) finds the row of the range's first entry, after that each lane walks forward through the
-    // row offsets (a few steps per 32 entries).  Four steps are unrolled: all eight loads are in flight before the first store.
+    // the reference stops at the first non-finite cut (src/model.jl:278): cuts before it stand
+    if (threadIdx.x == 0 && s_first_bad != 0xffffffffu) {
+        const uint32_t k = s_first_bad;
+        p.errpos[2 * bid] = (unsigned long long)cbase + k; p.errpos[2 * bid + 1] = nbase + s_off[k];
+        atomicMin(&p.counts[2 + (epoch & 1u)], (unsigned long long)(row0 + (s_rowl[k] & 0x3fffu)) + 1ull);
+    }
+    // C: expand the rows K1 built: one thread per output entry, coalesced writes.  Every warp owns a contiguous range of the
+    // block's entries: one binary search (shared memory) finds the row of the range's first entry, after that each lane walks
+    // forward through the row offsets (a few steps per 32 entries).  Four steps are unrolled: all loads are in flight before the first store.
     const uint32_t nent = (uint32_t)tb, lane = threadIdx.x & 31u;
-    const uint32_t per = ((nent + KTN_CBLOCK - 1) / KTN_CBLOCK) * 32u;         // entries per warp, a multiple of 32
-    const uint32_t wbeg = (threadIdx.x >> 5) * per, wend = wbeg + per < nent ? wbeg + per : nent;
-    if (wbeg < wend) {
-        uint32_t lo = 0, hi = ta;   // largest k with s_off[k] <= wbeg
-        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= wbeg) lo = mid; else hi = mid; }
-        for (uint32_t e0 = wbeg + lane; e0 - lane < wend; e0 += 128u) {
-            uint32_t src[4]; int32_t cv[4]; double vv[4];
+    if (s_copy) {
+        const uint32_t per = ((nent + KTN_CBLOCK - 1) / KTN_CBLOCK) * 32u;         // entries per warp, a multiple of 32
+        const uint32_t wbeg = (threadIdx.x >> 5) * per, wend = wbeg + per < nent ? wbeg + per : nent;
+        if (wbeg < wend) {
+            uint32_t lo = 0, hi = ta;   // largest k with s_off[k] <= wbeg
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= wbeg) lo = mid; else hi = mid; }
+            for (uint32_t e0 = wbeg + lane; e0 - lane < wend; e0 += 128u) {
+                uint32_t src[4]; int32_t cv[4]; double vv[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t e = e0 + 32u * (uint32_t)k;
-                if (e < wend) { while (s_off[lo + 1] <= e) ++lo; src[k] = s_src[lo] + (e - s_off[lo]); } else src[k] = 0xffffffffu;
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t e = e0 + 32u * (uint32_t)k;
+                    src[k] = 0xffffffffu;
+                    if (e < wend) { while (s_off[lo + 1] <= e) ++lo; if (!(s_rowl[lo] & 0x4000u)) src[k] = s_src[lo] + (e - s_off[lo]); }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { cv[k] = src[k] != 0xffffffffu ? p.jac_col[src[k]] : 0; vv[k] = src[k] != 0xffffffffu ? p.stage_val[src[k]] : 0.0; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (src[k] != 0xffffffffu) { const unsigned long long e = nbase + e0 + 32u * (uint32_t)k; out_col[e] = cv[k]; out_val[e] = vv[k]; }
             }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { cv[k] = src[k] != 0xffffffffu ? p.jac_col[src[k]] : 0; vv[k] = src[k] != 0xffffffffu ? p.stage_val[src[k]] : 0.0; }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (src[k] != 0xffffffffu) { const unsigned long long e = nbase + e0 + 32u * (uint32_t)k; out_col[e] = cv[k]; out_val[e] = vv[k]; }
         }
     }
+    // D: the last block to finish settles the round
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(&p.counts[7], 1ull) == (unsigned long long)nblocks - 1ull ? 1u : 0u; }
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long ca = s_tot_n, na = s_tot_nz;
+        const unsigned long long err = __ldcg(&p.counts[2 + (epoch & 1u)]);
+        unsigned long long n = ca, nz = na;
+        if (err != ~0ull) { const unsigned long long eb = (err - 1ull) >> KTN_CROWS_LOG2; n = __ldcg(&p.errpos[2 * eb]); nz = __ldcg(&p.errpos[2 * eb + 1]); }
+        p.counts[0] = n; p.counts[1] = nz; p.counts[4] = ca; p.counts[5] = na; p.counts[6] = err;
+        p.counts[2 + ((epoch & 1u) ^ 1u)] = ~0ull;                    // re-arm the slot the NEXT round's K1 uses
+        p.counts[7] = 0ull;
+        hdr[0] = n; hdr[1] = nz; hdr[2] = err; hdr[3] = L.total; hdr[4] = (unsigned long long)p.row_offset; hdr[5] = ca; hdr[6] = na; hdr[7] = 0ull;
+        out_ptr[ca] = (int64_t)na;
+    }
+    for (uint32_t i = threadIdx.x; i < KTN_TICKETS; i += KTN_CBLOCK) p.ticket[i] = 0u;     // K1 is over: re-arm its work tickets
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -781,7 +788,7 @@ __global__ void __launch_bounds__(KTN_CBLOCK) ktn_topk_demote_kernel(const KtnRo
     for (int o = 1; o < 32; o <<= 1) { const unsigned int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += n; }
     if (lane == 31) s_w[warp] = incl;
     __syncthreads();
-    if (warp == 0) { unsigned int v = s_w[lane]; for (int o = 1; o < 32; o <<= 1) { const unsigned int n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v += n; } s_w[lane] = v; }
+    if (warp == 0) { unsigned int v = lane < KTN_CWARPS ? s_w[lane] : 0u; for (int o = 1; o < 32; o <<= 1) { const unsigned int n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v += n; } s_w[lane] = v; }
     __syncthreads();
     unsigned long long rank = s_eq_before + (warp ? s_w[warp - 1] : 0u) + (incl - mine);
     unsigned long long cnt = 0, nnz = 0;
@@ -792,7 +799,7 @@ __global__ void __launch_bounds__(KTN_CBLOCK) ktn_topk_demote_kernel(const KtnRo
         if (!all && kk[r] == T) { keep = rank < quota; ++rank; }
         if (!keep) { p.sel[i] = 0u; continue; }
         const uint32_t s = p.sel[i];
-        ++cnt; nnz += s & ~KTN_SEL_ERRBIT;
+        ++cnt; nnz += KTN_SEL_NNZ(s);
         if (s & KTN_SEL_ERRBIT) atomicMin(&p.counts[2 + (p.epoch & 1u)], (unsigned long long)i + 1ull);
     }
     for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); nnz += __shfl_xor_sync(0xffffffffu, nnz, o); }
@@ -805,10 +812,6 @@ __global__ void __launch_bounds__(KTN_CBLOCK) ktn_topk_demote_kernel(const KtnRo
 
 cudaError_t ktn_kernels_configure(int max_smem_optin) {
     cudaError_t e = cudaFuncSetAttribute(ktn_round_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_LSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KTN_FP_SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(ktn_family_kernel<KTN_FAM_QUAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KTN_FP_SMEM);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(ktn_round_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
 }
@@ -844,16 +847,14 @@ extern "C" int ktn_debug_cycles(unsigned long long* out16, int reset) {
 }
 #endif
 
-template <int FAM, bool FWD>
+template <int FAM>
 static void launch_family(KtnRoundParams p, const KtnLaunchPlan& plan, uint32_t ticket_idx, int num_sms, cudaStream_t stream) {
     const uint32_t begin = plan.fam_begin[FAM], end = plan.fam_begin[FAM + 1];
     p.chunk_begin = begin; p.chunk_end = end; p.ticket_idx = ticket_idx;
-    for (int k = 0; k <= KTN_FAM_NCLS; ++k) p.cls_begin[k] = plan.cls_begin[FAM][k];
-    for (int k = 0; k < KTN_FAM_NCLS; ++k) { p.cls_blob_off[k] = plan.cls_blob_off[FAM][k]; p.cls_blob_stride[k] = plan.cls_blob_stride[FAM][k]; }
-    uint32_t blocks = (uint32_t)num_sms * (FWD ? KTN_FWD_BLOCKS : 1);      // persistent: one block per SM (evaluation only: two)
+    uint32_t blocks = (uint32_t)num_sms;      // persistent: one block per SM
     const uint32_t need = (end - begin + KTN_FP_WARPS - 1) / KTN_FP_WARPS;
     if (blocks > need) blocks = need;
-    ktn_family_kernel<FAM, FWD><<<blocks, KTN_FP_WARPS * 32, FWD ? 128 : KTN_FP_SMEM, stream>>>(p);
+    ktn_family_kernel<FAM><<<blocks, KTN_FP_WARPS * 32, KTN_FP_SMEM, stream>>>(p);
 }
 
 template <bool EVAL>
@@ -873,8 +874,8 @@ static int launch_eval_part(const KtnRoundParams& p0, const KtnLaunchPlan& plan,
         ktn_round_kernel<EVAL><<<blocks, wpb * 32, smem, stream>>>(p);
         ++launches;
     }
-    if (plan.fam_begin[KTN_FAM_LSE + 1] > plan.fam_begin[KTN_FAM_LSE]) { launch_family<KTN_FAM_LSE, EVAL>(p, plan, KTN_TICKET_LSE, num_sms, stream); ++launches; }
-    if (plan.fam_begin[KTN_FAM_QUAD + 1] > plan.fam_begin[KTN_FAM_QUAD]) { launch_family<KTN_FAM_QUAD, EVAL>(p, plan, KTN_TICKET_QUAD, num_sms, stream); ++launches; }
+    if (plan.fam_begin[KTN_FAM_LSE + 1] > plan.fam_begin[KTN_FAM_LSE]) { launch_family<KTN_FAM_LSE>(p, plan, KTN_TICKET_LSE, num_sms, stream); ++launches; }
+    if (plan.fam_begin[KTN_FAM_QUAD + 1] > plan.fam_begin[KTN_FAM_QUAD]) { launch_family<KTN_FAM_QUAD>(p, plan, KTN_TICKET_QUAD, num_sms, stream); ++launches; }
     if (plan.n_total > plan.n_regular) {
         p.chunk_begin = plan.n_regular; p.chunk_end = plan.n_total;
         uint32_t blocks = (plan.n_total - plan.n_regular + 3) / 4;

@@ -23,6 +23,7 @@ struct KtnRoundParams {
     const int32_t* jac_col;
     const double* row_lb;
     const double* row_ub;
+    const int32_t* row_slot;   // row -> chunk * 32 + lane
     // round inputs
     const double* x;
     const uint8_t* force;      // KTN_MODE_FORCE: per-row mask
@@ -37,22 +38,25 @@ struct KtnRoundParams {
     // round outputs
     double* g_row;             // g_i(x*) for every evaluated row (sep.g)
     double* b_row;             // cut constant of selected rows
-    uint32_t* sel;             // 0 = not selected, else nnz | KTN_SEL_ERRBIT
+    uint32_t* sel;             // 0 = not selected, else nnz | KTN_SEL_ERRBIT | KTN_SEL_DEFER
+    double4* rec;              // family rows K1 selected: {g, aux, lb, ub}, one 32-byte sector per row, read by K2's cut
     double* stage_val;         // cut coefficients in the static CSR layout
     double* big_scratch;
     unsigned int* ticket;      // KTN_TICKETS dynamic work tickets (interpreter K1: one; family K1: one per class); re-armed by K2
     uint32_t ticket_idx;       // first ticket this launch draws from
-    uint32_t cls_begin[KTN_FAM_NCLS + 1];   // family launches: chunk range of every class,
-    uint32_t cls_blob_stride[KTN_FAM_NCLS]; // bytes between consecutive chunk blobs of the class,
-    uint64_t cls_blob_off[KTN_FAM_NCLS];    // blob offset of the class's first chunk
+    uint32_t fam_begin[KTN_FAM__COUNT + 1];                 // chunk range of every family,
+    uint32_t cls_begin[KTN_FAM__COUNT][KTN_FAM_NCLS + 1];   // of every class of a family,
+    uint64_t cls_blob_off[KTN_FAM__COUNT][KTN_FAM_NCLS];    // blob offset of the class's first chunk (blobs of a class >= 1 are KTN_FAM_BLOB_BYTES apart)
     // block-shared table of the regular kernel: shape descriptors, then the programs of the regular shapes
     const unsigned char* table; uint32_t table_bytes, table_prog_off;
     uint32_t epoch;                    // round counter (>= 1): look-back flags and error slots are epoch-stamped
     // compaction: per block of KTN_CROWS rows, cuts << KTN_BLK_SHIFT | nnz of the selected rows, added by K1 and summed
     // by K2.  Two copies indexed by epoch parity; K2 zeroes the copy the next round adds into.
     unsigned long long* blk_cnt; uint32_t blk_stride;
+    unsigned long long* errpos;        // per compaction block: (cut index, entry offset) of the block's first non-finite row (K2)
     // [0] n_cuts [1] nnz (both truncated at the first non-finite row) [2],[3] first-error row + 1 of even / odd epochs
-    // (~0 = none) [4] n_cuts_total [5] nnz_total [6] first-error row + 1 of the last round
+    // (~0 = none) [4] n_cuts_total [5] nnz_total [6] first-error row + 1 of the last round [7] K2 blocks finished (the last one
+    // to finish writes the totals and the blob header and re-arms the per-round state)
     unsigned long long* counts;
     // K2 writes the round's cuts as ONE blob (ktn_pack_layout of the round's total counts): 64-byte header
     // {n_cuts, nnz (both truncated at the first non-finite row), first-error row + 1 (~0 = none), blob bytes, row offset,
@@ -64,7 +68,7 @@ struct KtnRoundParams {
 // Chunk ranges of one problem: regular chunks sorted by (family, class), then the BIG chunks.
 struct KtnLaunchPlan {
     uint32_t fam_begin[KTN_FAM__COUNT + 1]; uint32_t cls_begin[KTN_FAM__COUNT][KTN_FAM_NCLS + 1];
-    uint64_t cls_blob_off[KTN_FAM__COUNT][KTN_FAM_NCLS]; uint32_t cls_blob_stride[KTN_FAM__COUNT][KTN_FAM_NCLS];
+    uint64_t cls_blob_off[KTN_FAM__COUNT][KTN_FAM_NCLS];
     uint32_t n_regular, n_total;
 };
 enum { KTN_TICKET_GENERIC = 0, KTN_TICKET_LSE = 8, KTN_TICKET_QUAD = 32, KTN_TICKETS = 64 };

@@ -95,10 +95,12 @@ enum {
 
 // Family chunks are further split into CLASSES by unique-variable count: class k (1 <= k <= KTN_FAM_REGS) = rows of exactly
 // k unique variables, which run a code path specialised for k with the whole row in registers; class 0 = more than that
-// (streaming fallback).  Chunks are sorted by (family, class) so that every class is one contiguous chunk range.
+// (streaming fallback).  Chunks are sorted by (family, class) so that every class is one contiguous chunk range, and the
+// blobs of a class k >= 1 are contiguous and KTN_FAM_BLOB_BYTES(k) apart (constants | columns | one order word per row).
 #define KTN_FAM_REGS 16
 #define KTN_FAM_NCLS (KTN_FAM_REGS + 1)
 static inline uint32_t ktn_family_class(uint32_t n_uniq) { return n_uniq <= KTN_FAM_REGS ? n_uniq : 0u; }
+#define KTN_FAM_BLOB_BYTES(k) (640u * (k) + 256u)
 
 // shape flags
 enum { KTN_SH_NL = 1, KTN_SH_DENSE = 2, KTN_SH_BIG = 4 };
@@ -130,8 +132,10 @@ struct KtnChunkDesc {
     uint32_t row_slot;     // index of the chunk's first lane in chunk_rows[]; always chunk index * 32
 };
 
-// per-row result flags written by the round kernel
-#define KTN_SEL_ERRBIT 0x40000000u
+// per-row result word `sel` written by the round kernels: 0 = not selected, else nnz | flags
+#define KTN_SEL_ERRBIT 0x40000000u      // a coefficient of the row's cut is not finite (set by the kernel that built the cut)
+#define KTN_SEL_DEFER  0x20000000u      // family row: K1 only evaluated and tested it; the compaction kernel builds the cut (ktn_family_cut_entries)
+#define KTN_SEL_NNZ(s) ((s) & 0x1fffffffu)
 
 // Compaction blocks: K1 counts the selected rows of every block of KTN_CROWS consecutive rows
 // (cuts << KTN_BLK_SHIFT | nnz, one 64-bit atomic per warp and block), K2 turns the counts into offsets.

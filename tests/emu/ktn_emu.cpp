@@ -14,7 +14,7 @@
 
 struct ktn_handle {
     ktn_options opt; KtnProblem prob; bool loaded = false, have_round = false;
-    std::vector<double> g_row, b_row, stage_val; std::vector<uint32_t> sel;
+    std::vector<double> g_row, b_row, aux_row, stage_val, x_last; std::vector<uint32_t> sel; int do_round = 1;
     std::vector<int64_t> c_row, c_ptr; std::vector<int32_t> c_col; std::vector<double> c_val, c_lo, c_hi, c_g, c_viol, c_b;
     int64_t err_row = -1; std::string err;
 };
@@ -33,7 +33,7 @@ int ktn_load_end(ktn_handle* h) {
     uint32_t limit = 1536; if (const char* s = getenv("KTN_EMU_LANE_LIMIT")) limit = (uint32_t)atoi(s);
     int rc = h->prob.finalize(sigma, limit); if (rc) { h->err = h->prob.err; return rc; }
     size_t m = (size_t)h->prob.num_constr;
-    h->g_row.assign(m, 0.0); h->b_row.assign(m, 0.0); h->sel.assign(m, 0u); h->stage_val.assign((size_t)h->prob.jac_ptr[m], 0.0);
+    h->g_row.assign(m, 0.0); h->b_row.assign(m, 0.0); h->aux_row.assign(m, 0.0); h->sel.assign(m, 0u); h->stage_val.assign((size_t)h->prob.jac_ptr[m], 0.0);
     h->loaded = true; return 0; }
 int ktn_set_bounds(ktn_handle* h, const double* lb, const double* ub) { h->prob.lb.assign(lb, lb + h->prob.num_constr); h->prob.ub.assign(ub, ub + h->prob.num_constr); h->prob.repack_bounds(); return 0; }
 int64_t ktn_num_rows(ktn_handle* h) { return h->prob.rows_loaded; }
@@ -43,7 +43,7 @@ int ktn_jac_structure(ktn_handle* h, int64_t* rp, int32_t* cols) {
     if (cols) memcpy(cols, h->prob.jac_col.data(), 4 * h->prob.jac_col.size()); return 0; }
 }
 
-// family shapes (ktn_family.h): the same row functions the sm_100a family kernel runs, on the same packed chunk
+// family shapes (ktn_family.h): the same row functions the sm_100a kernels run, on the same packed chunk
 struct EmuFamRow {
     const double* C; const int32_t* cols; const uint8_t* rk; const double* X; uint32_t nu, L, lane;
     double cst(uint32_t i) const { return C[(size_t)i * L + lane]; }
@@ -51,37 +51,50 @@ struct EmuFamRow {
     double xat(int32_t c) const { return X[c]; }
     double x(uint32_t u) const { return X[col(u)]; }
     uint32_t rank(uint32_t u) const { return rk[(size_t)u * L + lane]; }
-    uint64_t rankword() const { return ((const uint64_t*)rk)[lane]; }
+    uint64_t orderword() const { return ((const uint64_t*)rk)[lane]; }
 };
 struct EmuFamSink {
-    double t[KTN_FAM_REGS]; double* out; const int32_t* scol; const double* X;
-    void put_t(uint32_t q, double v) { t[q] = v; } double get_t(uint32_t q) const { return t[q]; }
+    double* out; const int32_t* scol; const double* X;
     void put_j(uint32_t q, double v) { out[q] = v; } double get_j(uint32_t q) const { return out[q]; }
     double xsorted(uint32_t q) const { return X[scol[q]]; }
 };
+struct EmuCutSink {     // K2's sink: coefficient and column of entry q; the column must be the static Jacobian structure's
+    double* val; const int32_t* scol; bool* colmismatch;
+    void put(uint32_t q, double v, int32_t c) { val[q] = v; if (scol[q] != c) *colmismatch = true; }
+    double get(uint32_t q) const { return val[q]; }
+    void set(uint32_t q, double v) { val[q] = v; }
+};
+static EmuFamRow emu_row(const KtnProblem& P, const KtnChunkDesc& cd, uint32_t lane, const double* x) {
+    const uint32_t nu = (uint32_t)cd.aux;
+    const uint8_t* blob = P.blob.data() + cd.blob_off;
+    return EmuFamRow{(const double*)blob, (const int32_t*)(blob + (size_t)512 * nu), blob + (size_t)640 * nu, x, nu, cd.stride, lane};
+}
+// K1: forward, test, record {g, aux}; rows of more than KTN_FAM_REGS variables build their cut here (streaming fallback)
 template <int FAM, int N>
 static void run_family_row(ktn_handle* h, const KtnChunkDesc& cd, uint32_t lane, int32_t row, const double* x, int mode, bool forced, double lb, double ub, int do_round) {
     KtnProblem& P = h->prob;
-    const uint32_t L = cd.stride, nu = (uint32_t)cd.aux;
-    const uint8_t* blob = P.blob.data() + cd.blob_off;
-    const EmuFamRow r{(const double*)blob, (const int32_t*)(blob + (size_t)512 * nu), blob + (size_t)640 * nu, x, nu, L, lane};
+    const EmuFamRow r = emu_row(P, cd, lane, x);
+    const uint32_t nu = r.nu;
     constexpr int NR = N > 0 ? N : 1;
-    KtnFamRegs<NR> v;
     double aux, g;
     if constexpr (N > 0) {
-        if (mode == 2) { g = KtnFamily<FAM>::template forward_only<NR>(r, []() {}); aux = 0.0; }       // the evaluation-only instantiation of the kernel
-        else { int32_t col[NR]; ktn_family_load<FAM, NR>(r, v, col); g = ktn_family_eval<FAM, NR>(r, v, col, aux); }
+        typedef KtnFamily<FAM> F;
+        KtnFamRegs<NR> v;
+        for (int u = 0; u < N; ++u) { v.p0[u] = r.cst(F::slot0(u, N)); v.p1[u] = r.cst(F::slot1(u, N)); v.x[u] = r.x(u); }
+        g = F::template forward<NR>(v, aux);
     } else g = KtnFamily<FAM>::forward_stream(r, aux);
     h->g_row[row] = g;
     if (mode == 2) return;
     const bool selected = mode == 1 ? forced : !((g >= lb - h->opt.f_tol) && (g <= ub + h->opt.f_tol));
     if (!selected) { h->sel[row] = 0; return; }
-    const int64_t base = P.jac_ptr[row];
-    EmuFamSink s{{0}, h->stage_val.data() + base, P.jac_col.data() + base, x};
-    double b; bool bad;
-    if constexpr (N > 0) bad = ktn_family_cut<FAM, NR>(r, v, s, g, aux, do_round != 0, h->opt.cut_coef_rng, b);
-    else bad = ktn_family_cut_stream<FAM>(r, s, g, aux, do_round != 0, h->opt.cut_coef_rng, b);
-    h->b_row[row] = b; h->sel[row] = nu | (bad ? KTN_SEL_ERRBIT : 0u);
+    if constexpr (N > 0) { h->aux_row[row] = aux; h->sel[row] = nu | KTN_SEL_DEFER; }
+    else {
+        const int64_t base = P.jac_ptr[row];
+        EmuFamSink s{h->stage_val.data() + base, P.jac_col.data() + base, x};
+        double b;
+        const bool bad = ktn_family_cut_stream<FAM>(r, s, g, aux, do_round != 0, h->opt.cut_coef_rng, b);
+        h->b_row[row] = b; h->sel[row] = nu | (bad ? KTN_SEL_ERRBIT : 0u);
+    }
 }
 template <int FAM, class... A> static void run_family_dispatch(uint32_t nu, A... a) {
     switch (ktn_family_class(nu)) {
@@ -92,6 +105,23 @@ template <int FAM, class... A> static void run_family_dispatch(uint32_t nu, A...
         default: run_family_row<FAM, 0>(a...); break;
     }
 }
+// K2: the cut of a deferred family row, into the staging row (the kernel writes the round's CSR directly)
+static bool run_family_cut(ktn_handle* h, int64_t row, double& b) {
+    KtnProblem& P = h->prob;
+    const uint32_t slot = (uint32_t)P.row_slot[row], c = slot >> 5, lane = slot & 31u;
+    const KtnChunkDesc& cd = P.chunks[c];
+    const int fam = (int)P.shapes[cd.shape].family;
+    if (c < P.fam_begin[fam] || c >= P.fam_begin[fam + 1] || cd.blob_off != P.cls_blob_off[fam][cd.aux] + (uint64_t)(c - P.cls_begin[fam][cd.aux]) * KTN_FAM_BLOB_BYTES(cd.aux)) {
+        fprintf(stderr, "emu: family blob addressing violated\n"); abort(); }
+    const EmuFamRow r = emu_row(P, cd, lane, h->x_last.data());
+    const int64_t base = P.jac_ptr[row];
+    bool mismatch = false;
+    EmuCutSink s{h->stage_val.data() + base, P.jac_col.data() + base, &mismatch};
+    const bool bad = fam == KTN_FAM_LSE ? ktn_family_cut_entries<KTN_FAM_LSE>(r, r.nu, r.orderword(), s, h->g_row[row], h->aux_row[row], h->do_round != 0, h->opt.cut_coef_rng, b)
+                                        : ktn_family_cut_entries<KTN_FAM_QUAD>(r, r.nu, r.orderword(), s, h->g_row[row], h->aux_row[row], h->do_round != 0, h->opt.cut_coef_rng, b);
+    if (mismatch) { fprintf(stderr, "emu: order word does not reproduce the Jacobian structure\n"); abort(); }
+    return bad;
+}
 
 static uint32_t ord_at(const uint8_t* ord, uint32_t ob, size_t e) { return ob == 1 ? ord[e] : ob == 2 ? ((const uint16_t*)ord)[e] : ((const uint32_t*)ord)[e]; }
 
@@ -99,6 +129,7 @@ static uint32_t ord_at(const uint8_t* ord, uint32_t ob, size_t e) { return ob ==
 static void run_chunks(ktn_handle* h, const double* x, int mode, const std::vector<uint8_t>& force, int do_round) {
     KtnProblem& P = h->prob;
     std::vector<double> S;
+    h->x_last.assign(x, x + P.num_var); h->do_round = do_round;
     for (size_t c = 0; c < P.chunks.size(); ++c) {
         const KtnChunkDesc& cd = P.chunks[c]; const KtnShapeDesc& sd = P.shapes[cd.shape];
         const uint32_t L = cd.stride, nu = sd.n_uniq;
@@ -166,6 +197,7 @@ static int compact(ktn_handle* h, int64_t* n_cuts, int64_t* nnz, int64_t* err_ro
     h->err_row = -1;
     for (int64_t i = 0; i < P.num_constr; ++i) {
         uint32_t s = h->sel[i]; if (!s) continue;
+        if (s & KTN_SEL_DEFER) { double b; const bool bad = run_family_cut(h, i, b); h->b_row[i] = b; s = KTN_SEL_NNZ(s) | (bad ? KTN_SEL_ERRBIT : 0u); }
         if (s & KTN_SEL_ERRBIT) { h->err_row = i; break; }
         const int64_t base = P.jac_ptr[i];
         for (uint32_t q = 0; q < s; ++q) { h->c_col.push_back(P.jac_col[base + q]); h->c_val.push_back(h->stage_val[base + q]); }
