@@ -11,6 +11,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+SYNTH_LIB_PATH = os.path.join(_HERE, "libktn_synth.so")
 CUDA_LIB_PATH = os.environ.get("KTN_LIB") or os.path.join(_HERE, "libktn.so")      # KTN_LIB: an A/B variant build of the CUDA library (scripts/build_variants.sh)
 
 # wire-format constants (include/ktn.h)
@@ -86,26 +87,13 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(_P)
 
 
-class KtnLibrary:
-    """A loaded shared library exporting include/ktn.h."""
+class _SynthMixin:
+    """ktn_synth_rows / ktn_synth_point of a loaded library (self.dll)."""
 
-    def __init__(self, path):
-        if not os.path.exists(path):
-            raise KtnError(f"shared library not found: {path} (run `python -c 'import __graft_entry__ as g; g.build()'`)")
-        self.path = path
-        self.dll = C.CDLL(path, mode=C.RTLD_GLOBAL)
-        for name, (res, args) in _SIGS.items():
+    def _bind_synth(self):
+        for name, (res, args) in _SYNTH_SIGS.items():
             fn = getattr(self.dll, name)
             fn.restype, fn.argtypes = res, args
-        self.has_synth = hasattr(self.dll, "ktn_synth_rows")
-        if self.has_synth:
-            for name, (res, args) in _SYNTH_SIGS.items():
-                fn = getattr(self.dll, name)
-                fn.restype, fn.argtypes = res, args
-        self.backend = self.dll.ktn_backend().decode()
-
-    def create(self, f_tol=1e-6, cut_coef_rng=1e9, topk=0, device=-1, flags=0):
-        return Handle(self, f_tol, cut_coef_rng, topk, device, flags)
 
     # ---- synthetic instances (SURVEY.md section 8d) ----
     def synth_rows(self, kind, seed, num_var, row_begin, nrows):
@@ -129,6 +117,39 @@ class KtnLibrary:
         if rc != 0:
             raise KtnError(f"ktn_synth_point failed: {rc}")
         return x
+
+
+class SynthLibrary(_SynthMixin):
+    """libktn_synth.so: the deterministic instance generators alone (no CUDA, no separator).  Tests, the CPU baseline and
+    `bench.py --impl reference` take their inputs from here, so that they never map the product library."""
+
+    def __init__(self, path=None):
+        path = path or SYNTH_LIB_PATH
+        if not os.path.exists(path):
+            raise KtnError(f"shared library not found: {path} (run `python -c 'import __graft_entry__ as g; g.build()'`)")
+        self.path = path
+        self.dll = C.CDLL(path)
+        self._bind_synth()
+
+
+class KtnLibrary(_SynthMixin):
+    """A loaded shared library exporting include/ktn.h."""
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise KtnError(f"shared library not found: {path} (run `python -c 'import __graft_entry__ as g; g.build()'`)")
+        self.path = path
+        self.dll = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(self.dll, name)
+            fn.restype, fn.argtypes = res, args
+        self.has_synth = hasattr(self.dll, "ktn_synth_rows")
+        if self.has_synth:
+            self._bind_synth()
+        self.backend = self.dll.ktn_backend().decode()
+
+    def create(self, f_tol=1e-6, cut_coef_rng=1e9, topk=0, device=-1, flags=0):
+        return Handle(self, f_tol, cut_coef_rng, topk, device, flags)
 
 
 @dataclass

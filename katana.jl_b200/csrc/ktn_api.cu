@@ -20,7 +20,7 @@ extern "C" const char* ktn_last_error(ktn_handle* h) { return h ? h->err.c_str()
 
 static void free_problem(ktn_handle* h) {
     DevBuf* all[] = {&h->chunks, &h->shapes, &h->prog, &h->blob, &h->chunk_rows, &h->chunk_lb, &h->chunk_ub, &h->jac_ptr, &h->jac_col,
-                     &h->row_lb, &h->row_ub, &h->row_slot, &h->rec, &h->errpos, &h->x, &h->force, &h->g_row, &h->b_row, &h->sel, &h->stage_val, &h->big_scratch,
+                     &h->row_lb, &h->row_ub, &h->row_slot, &h->rec, &h->worklist, &h->errpos, &h->blk_off, &h->chunk_jp, &h->dump, &h->x, &h->force, &h->g_row, &h->b_row, &h->sel, &h->stage_val, &h->big_scratch,
                      &h->blk_cnt, &h->topk_key, &h->topk_state, &h->topk_eqcnt, &h->table, &h->out_blob[0], &h->out_blob[1], &h->out_blob[2]};
     for (DevBuf* b : all) b->release();
     if (h->h_x) { cudaFreeHost(h->h_x); h->h_x = nullptr; }
@@ -154,7 +154,8 @@ extern "C" int ktn_load_end(ktn_handle* h) {
     CK(h, upload(h->chunk_lb, P.chunk_lb)); CK(h, upload(h->chunk_ub, P.chunk_ub));
     CK(h, upload(h->jac_ptr, P.jac_ptr)); CK(h, upload(h->jac_col, P.jac_col));
     CK(h, upload(h->row_lb, P.lb)); CK(h, upload(h->row_ub, P.ub)); CK(h, upload(h->row_slot, P.row_slot));
-    CK(h, h->rec.alloc(32 * (m + 1)));
+    CK(h, h->rec.alloc(32 * (m + 1))); CK(h, h->worklist.alloc(8 * (m + 1)));
+    CK(h, upload(h->chunk_jp, P.chunk_jp)); CK(h, h->dump.alloc(24 * (N + 1)));
     CK(h, h->x.alloc(8 * ((size_t)P.num_var + 1))); CK(h, h->force.alloc(m + 16));
     CK(h, h->g_row.alloc(8 * (m + 1))); CK(h, h->b_row.alloc(8 * (m + 1))); CK(h, h->sel.alloc(4 * (m + 1)));
     CK(h, cudaMemset(h->sel.p, 0, 4 * (m + 1))); CK(h, cudaMemset(h->g_row.p, 0, 8 * (m + 1)));
@@ -162,7 +163,7 @@ extern "C" int ktn_load_end(ktn_handle* h) {
     h->blk_stride = (uint32_t)((m + KTN_CROWS - 1) / KTN_CROWS + 1);
     CK(h, h->blk_cnt.alloc(16 * (size_t)h->blk_stride));
     CK(h, cudaMemset(h->blk_cnt.p, 0, 16 * (size_t)h->blk_stride));
-    CK(h, h->errpos.alloc(16 * (size_t)h->blk_stride));
+    CK(h, h->errpos.alloc(16 * (size_t)h->blk_stride)); CK(h, h->blk_off.alloc(16 * ((size_t)h->blk_stride + 1)));
     CK(h, upload(h->table, table));
     h->out_cap = ((size_t)ktn_pack_layout(m, N).total + 127) / 128 * 128 + 128;      // every row selected
     h->out_cur = 0; for (bool& b : h->blob_busy) b = false;
@@ -214,7 +215,8 @@ KtnRoundParams ktn_make_params(ktn_handle* h, const double* d_x, int mode, int d
     p.chunk_lb = h->chunk_lb.as<double>(); p.chunk_ub = h->chunk_ub.as<double>();
     p.jac_ptr = h->jac_ptr.as<int64_t>(); p.jac_col = h->jac_col.as<int32_t>();
     p.row_lb = h->row_lb.as<double>(); p.row_ub = h->row_ub.as<double>(); p.row_slot = h->row_slot.as<int32_t>();
-    p.rec = h->rec.as<double4>(); p.errpos = h->errpos.as<unsigned long long>();
+    p.chunk_jp = h->chunk_jp.as<uint32_t>(); p.dump = h->dump.as<double>(); p.dump_nnz = (uint64_t)h->prob.jac_ptr[h->prob.num_constr];
+    p.rec = h->rec.as<double4>(); p.worklist = h->worklist.as<unsigned long long>(); p.errpos = h->errpos.as<unsigned long long>(); p.blk_off = h->blk_off.as<unsigned long long>();
     for (int f = 0; f <= KTN_FAM__COUNT; ++f) p.fam_begin[f] = h->prob.fam_begin[f];
     memcpy(p.cls_begin, h->prob.cls_begin, sizeof p.cls_begin); memcpy(p.cls_blob_off, h->prob.cls_blob_off, sizeof p.cls_blob_off);
     p.x = d_x; p.force = h->force.as<uint8_t>();

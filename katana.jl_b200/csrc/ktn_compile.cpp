@@ -515,6 +515,7 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
         uint64_t sec_c = 0, sec_col = align_up(sec_c + 8ull * s.n_const * L, 16), sec_ord = align_up(sec_col + 4ull * s.n_uniq * L, 16);
         const bool rankword = s.family != KTN_FAM_GENERIC && s.n_uniq <= KTN_FAM_REGS;      // family rows of <= 16 unique variables: one packed word per row
         uint64_t bytes = align_up(sec_ord + (rankword ? 8ull * L : (uint64_t)s.order_bytes * s.n_uniq * L), 16);
+        if (rankword) bytes = KTN_FAM_BLOB_BYTES(s.n_uniq);      // grouped layout of the family classes (ktn_program.h)
         cd.blob_off = off; cd.blob_bytes = (uint32_t)bytes;
         blob.resize(off + bytes, 0);
         uint8_t* base = blob.data() + off;
@@ -523,14 +524,22 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
             const double* rc = rd_const.data() + row_const_off[row];
             const int32_t* rcol = rd_col.data() + row_col_off[row];
             const uint32_t* rord = rd_order.data() + row_col_off[row];
+            if (rankword) {      // family rows of <= 16 unique variables
+                for (uint32_t u = 0; u < s.n_uniq; ++u) {
+                    double* pr = (double*)(base + KTN_FAM_PAIR_AT(u, lane));
+                    pr[0] = rc[ktn_family_slot(s.family, 0, u, s.n_uniq)]; pr[1] = rc[ktn_family_slot(s.family, 1, u, s.n_uniq)];
+                    *(int32_t*)(base + KTN_FAM_COL_AT(s.n_uniq, u, lane)) = rcol[u];
+                }
+                uint64_t w = 0; for (uint32_t p = 0; p < s.n_uniq; ++p) w |= (uint64_t)p << (4 * rord[p]);      // rank word: 4 bits per unique variable = its Jacobian entry index
+                ((uint64_t*)(base + KTN_FAM_ORD_OFF(s.n_uniq)))[lane] = w;
+                continue;
+            }
             double* dc = (double*)(base + sec_c);
             for (uint32_t c = 0; c < s.n_const; ++c) dc[(uint64_t)c * L + lane] = rc[c];
             int32_t* dcol = (int32_t*)(base + sec_col);
             for (uint32_t u = 0; u < s.n_uniq; ++u) dcol[(uint64_t)u * L + lane] = rcol[u];
             uint8_t* dord = base + sec_ord;
-            // family chunks (ktn_family.h), rows of <= 16 unique variables: ONE order word, 4 bits per Jacobian entry p = its unique variable;
-            // longer rows carry the inverse permutation: rank[u] = Jacobian entry index of unique variable u
-            if (rankword) { uint64_t w = 0; for (uint32_t p = 0; p < s.n_uniq; ++p) w |= (uint64_t)rord[p] << (4 * p); ((uint64_t*)dord)[lane] = w; continue; }
+            // long family rows carry the inverse permutation: rank[u] = Jacobian entry index of unique variable u
             if (s.family != KTN_FAM_GENERIC) { for (uint32_t p = 0; p < s.n_uniq; ++p) dord[(uint64_t)rord[p] * L + lane] = (uint8_t)p; continue; }
             for (uint32_t p = 0; p < s.n_uniq; ++p) {
                 uint64_t e = (uint64_t)p * L + lane;
@@ -602,6 +611,8 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
     }
     blob.resize(align_up(blob.size(), 128) + 128, 0);
     row_slot.assign((size_t)num_constr, -1);
+    chunk_jp.assign(chunk_rows.size(), 0u);
+    for (size_t i = 0; i < chunk_rows.size(); ++i) if (chunk_rows[i] >= 0) chunk_jp[i] = (uint32_t)jac_ptr[chunk_rows[i]];
     for (size_t i = 0; i < chunk_rows.size(); ++i) if (chunk_rows[i] >= 0) row_slot[chunk_rows[i]] = (int32_t)i;
     repack_bounds();
     // the ragged per-row staging is no longer needed

@@ -38,6 +38,7 @@ struct KtnProblem {
     std::vector<uint8_t> blob;
     std::vector<int32_t> chunk_rows;        // chunk * 32 + lane -> row or -1
     std::vector<int32_t> row_slot;          // row -> chunk * 32 + lane (the inverse of chunk_rows)
+    std::vector<uint32_t> chunk_jp;         // chunk * 32 + lane -> jac_ptr[row]
     std::vector<double> chunk_lb, chunk_ub; // same indexing
     uint64_t big_scratch_doubles = 0;       // global scratch arena for BIG chunks
     uint32_t max_lane_bytes = 0;            // per-lane shared-memory need of the largest regular shape

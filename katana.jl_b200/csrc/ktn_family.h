@@ -9,18 +9,18 @@
 // (src/model.jl:200-207) and _addcut's finiteness test (src/model.jl:69) for the selected rows.
 //
 // Data of one family row (chunk blob, lane stride L):
-//   constants   two per unique variable u (LSE: c_u = slot 2u, d_u = slot 2u+1;  QUAD: a_u = slot u, b_u = slot nu+u;
-//               SOC: sigma_u = slot u for the nu - 1 squared terms, no constant for the linear variable)
+//   constants   two per unique variable u (LSE: c_u = slot 2u, d_u = slot 2u+1;  QUAD: a_u = slot u, b_u = slot nu+u); rows of
+//               <= 16 unique variables store them as PAIRS (p0_u, p1_u), 16 bytes per row and variable (ktn_program.h)
 //   cols        column of unique variable u (first-occurrence order = the order of the terms)
-//   order       nu <= 16: ONE 64-bit word per row, 4 bits per Jacobian entry q (ascending column) = the unique variable u
-//               it belongs to;  nu > 16: one byte per u holding its entry index (rank)
+//   rank        position of unique variable u among the row's ascending columns = its Jacobian entry index;
+//               nu <= 16: ONE 64-bit word per row, 4 bits per u;  nu > 16: one byte per u
 //
 // The work is split between the two kernels of a round (ktn_kernels.cu):
-//   K1  forward<N>: the whole row in registers, every constant and column requested at once; g, the violation test, and for
-//       a selected row one 32-byte record {g, aux, lb, ub}.  Nothing of the row is kept for the cut.
-//   K2  ktn_family_cut_entries: one thread per SELECTED row walks the row's Jacobian entries in entry order (ascending
-//       column, through the order word), recomputes the entry's term from the blob and x*, and writes coefficient and column
-//       straight into the round's CSR; the constant b = g + sum -x_q J_q accumulates in that same order, as the reference does.
+//   K1  forward<N>: the whole row in registers, every constant and column requested at once; g, the violation test.  Nothing
+//       of the row is kept for the cut: a selected row leaves one 32-byte record {g, aux, lb, ub}.
+//   K2  ktn_family_cut_terms (the cut kernel): one thread per SELECTED row recomputes the row's terms from the blob and x*,
+//       scatters coefficient and product to their Jacobian entry (rank word), and accumulates the constant b = g + sum -x_q J_q
+//       in entry order, as the reference does.
 // Rows with more than 16 unique variables take the streaming fallbacks (cut built in K1).
 #ifndef KTN_FAMILY_H
 #define KTN_FAMILY_H
@@ -35,8 +35,6 @@ template <int FAM> struct KtnFamily;
 // log(sum_u exp(c_u * x_u + d_u))
 // Program: KF_TERMS(EXP_AFF, FIRST); STORE S; LOG | KR_ONE; MULRCP S; STORE R1; KR_TERMS(EXP_AFF); END
 template <> struct KtnFamily<KTN_FAM_LSE> {
-    static KTN_HDM uint32_t slot0(uint32_t u, uint32_t) { return 2 * u; }
-    static KTN_HDM uint32_t slot1(uint32_t u, uint32_t) { return 2 * u + 1; }
     static KTN_HDM double arg(double c, double d, double x) { return (0.0 + c * x) + d; }      // LOAD c; MUL x; ADDZ; ADD d
     // forward over the N register-resident terms; aux = the sum (the cut's adjoint is its reciprocal)
     template <int N> static KTN_HDM double forward(KtnFamRegs<N>& r, double& aux) {
@@ -82,8 +80,6 @@ template <> struct KtnFamily<KTN_FAM_LSE> {
 // sum_u a_u * x_u^2 + sum_u b_u * x_u
 // Program: KF_TERMS(MULC_SQ, FIRST); KF_TERMS(MULC_X) | KR_ONE; STORE R1; KR_TERMS(MULC_SQ); KR_TERMS(MULC_X, JACC); END
 template <> struct KtnFamily<KTN_FAM_QUAD> {
-    static KTN_HDM uint32_t slot0(uint32_t u, uint32_t) { return u; }
-    static KTN_HDM uint32_t slot1(uint32_t u, uint32_t nu) { return nu + u; }
     template <int N> static KTN_HDM double forward(KtnFamRegs<N>& r, double& aux) {
         double acc = 0.0;
 #pragma unroll
@@ -111,44 +107,52 @@ template <> struct KtnFamily<KTN_FAM_QUAD> {
 KTN_HDM double ktn_dmax(double a, double b) { return a > b ? a : (b != b ? a : b); }
 KTN_HDM double ktn_dmin(double a, double b) { return a < b ? a : (b != b ? a : b); }
 
-// ---- the cut of a selected row, in Jacobian-entry order (K2; tests/emu) --------------------------------------------------
-// Row context R: cst(i), col(u), xat(col).  `ow`: 4 bits per entry q = the unique variable it belongs to.
-// Sink S: put(q, coefficient, column), get(q), set(q, coefficient) on the row's slice of the round's CSR.
-// b = g; b += -x*_q J_q in entry order (src/algorithms.jl:8-16); round_coefs (src/model.jl:200-207); returns true when a
-// coefficient is not finite (src/model.jl:69).
+// ---- the cut of a selected row (the cut kernel; tests/emu) --------------------------------------------------------------
+// Row context R: pairs2(g, a0, a1, b0, b1) = the constants of unique variables 2g (a) and 2g + 1 (b); cols8(g, c[8]) = the
+// columns of unique variables 8g .. 8g + 7; xat(col).  `rw`: 4 bits per unique variable u = its Jacobian entry index (rank).
+// Sink S: put(q, J) / get(q) / set(q, J): coefficient of entry q;  put_t(q, t) / get_t(q): the product -x* J of entry q.
+// The terms are walked in TERM order, eight at a time (their loads are in flight together: one 256-bit load per two terms'
+// constants, one per eight columns, then the eight x* gathers); coefficients and products are scattered to their entry index,
+// and the constant b = g; b += -x*_q J_q then accumulates in ENTRY order, as the reference does (src/algorithms.jl:8-16).
+// round_coefs (src/model.jl:200-207); returns true when a coefficient is not finite (src/model.jl:69).
 //
 // reverse_eval's product rule revmul(a, p) equals a * p whenever a * p is not NaN, and NaN operands stay NaN through the
 // later products, so the coefficients are first formed with plain multiplications; only a row in which one of them came out
 // NaN repeats the sweep with the exact rule.  round_coefs zeroes J when J + rng < maximum(J): J + rng is monotone in J, so when
 // the smallest coefficient passes (and everything is finite) all pass, and the second sweep only runs for rows that need it.
 template <int FAM, class R, class S>
-KTN_HDM bool ktn_family_cut_entries(const R& r, uint32_t nu, uint64_t ow, S& s, double g, double aux, bool do_round, double rng, double& b_out) {
+KTN_HDM bool ktn_family_cut_terms(const R& r, uint32_t nu, uint64_t rw, S& s, double g, double aux, bool do_round, double rng, double& b_out) {
     typedef KtnFamily<FAM> F;
     const double adj = F::adjoint(aux);
-    double mx = -ktn_inf(), mn = ktn_inf(), b = g;
-    bool anynan = false;
-#pragma unroll 4
-    for (uint32_t q = 0; q < nu; ++q) {
-        const uint32_t u = (uint32_t)(ow >> (4 * q)) & 15u;
-        const int32_t c = r.col(u);
-        const double x = r.xat(c);
-        const double jv = F::entry(adj, r.cst(F::slot0(u, nu)), r.cst(F::slot1(u, nu)), x, false);
-        b = b + (-x) * jv;
-        s.put(q, jv, c);
-        mx = ktn_dmax(mx, jv); mn = ktn_dmin(mn, jv); anynan = anynan || (jv != jv);
-    }
-    if (anynan) {                                           // rare: repeat the sweep with reverse_eval's exact product rule
-        anynan = false; mx = -ktn_inf(); mn = ktn_inf(); b = g;
-        for (uint32_t q = 0; q < nu; ++q) {
-            const uint32_t u = (uint32_t)(ow >> (4 * q)) & 15u;
-            const int32_t c = r.col(u);
-            const double x = r.xat(c);
-            const double jv = F::entry(adj, r.cst(F::slot0(u, nu)), r.cst(F::slot1(u, nu)), x, true);
-            b = b + (-x) * jv;
-            s.put(q, jv, c);
-            mx = ktn_dmax(mx, jv); mn = ktn_dmin(mn, jv); anynan = anynan || (jv != jv);
+    double mx, mn;
+    bool anynan, exact = false;
+    for (;;) {
+        mx = -ktn_inf(); mn = ktn_inf(); anynan = false;
+        for (uint32_t u0 = 0; u0 < nu; u0 += 8) {
+            int32_t c[8]; double p0[8], p1[8], x[8];
+            r.cols8(u0 >> 3, c);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (u0 + 2 * k < nu) r.pairs2((u0 >> 1) + k, p0[2 * k], p1[2 * k], p0[2 * k + 1], p1[2 * k + 1]);
+                else { p0[2 * k] = p1[2 * k] = p0[2 * k + 1] = p1[2 * k + 1] = 0.0; }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = r.xat(c[k]);          // columns past the row's end are padded with 0: a valid index
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (u0 + k < nu) {
+                    const double jv = F::entry(adj, p0[k], p1[k], x[k], exact);
+                    const uint32_t q = (uint32_t)(rw >> (4 * (u0 + k))) & 15u;
+                    s.put(q, jv); s.put_t(q, (-x[k]) * jv);
+                    mx = ktn_dmax(mx, jv); mn = ktn_dmin(mn, jv); anynan = anynan || (jv != jv);
+                }
+            }
         }
+        if (!anynan || exact) break;
+        exact = true;                                       // rare: repeat the sweep with reverse_eval's exact product rule
     }
+    double b = g;
+    for (uint32_t q = 0; q < nu; ++q) b = b + s.get_t(q);
     b_out = b;
     bool bad = false;
     if (anynan || !(ktn_fabs(mn) <= KTN_FAM_DMAX) || !(ktn_fabs(mx) <= KTN_FAM_DMAX) || (do_round && (mn + rng < mx))) {

@@ -32,7 +32,12 @@
 #include "ktn_interp.h"
 #include "ktn_family.h"
 
-#define KTN_CBLOCK 512    // threads per compaction block
+#ifndef KTN_CBLOCK
+#define KTN_CBLOCK 256    // threads per compaction block
+#endif
+#ifndef KTN_CBPS
+#define KTN_CBPS 3        // compaction blocks per SM the register budget is set for
+#endif
 
 namespace {
 
@@ -84,11 +89,23 @@ __device__ __forceinline__ void count_selected(const KtnRoundParams& p, unsigned
 // capacity: 200 KB of idle shared memory alone slow the kernel down 2.2x), L2 prefetch, more warps at fewer registers.
 // ---------------------------------------------------------------------------------------------
 #define KTN_FP_WARPS 16
+#ifndef KTN_DUMP
+#define KTN_DUMP 0
+#endif
 #define KTN_FP_SMEM 0
 
 #ifdef KTN_OPT_TIMING
 __device__ unsigned long long ktn_dbg_cycles[16];
 #endif
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// 256-bit read-only loads (LDG.E.256): one per lane and group of the family blobs
+__device__ __forceinline__ void ldg256(const void* p, double& a, double& b, double& c, double& d) {
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void ldg256(const void* p, int32_t (&v)[8]) {
+    asm("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
 
 struct FamRow {     // streaming row context of ktn_family.h (class 0): the chunk's SoA sections in global memory, lane offset applied
     const double* C; const int32_t* cols; const uint8_t* rk; const double* X; uint32_t nu;
@@ -135,7 +152,6 @@ __device__ __forceinline__ void family_stream_class(const KtnRoundParams& p, uin
             const bool bad = ktn_family_cut_stream<FAM>(r, s, g, aux, p.do_round != 0, p.rng, b);
             p.b_row[row] = b;
             p.sel[row] = nu | (bad ? KTN_SEL_ERRBIT : 0u);
-            if (bad) atomicMin(&p.counts[2 + (p.epoch & 1u)], (unsigned long long)row + 1ull);
             count_selected(p, selm, row, nu);
         }
     }
@@ -152,18 +168,34 @@ __device__ __forceinline__ void family_class(const KtnRoundParams& p, uint32_t l
     uint32_t cur = __shfl_sync(0xffffffffu, t0, 0);
     while (cur < n) {
         KtnFamRegs<N> v[R]; int32_t col[R][N]; int32_t row[R]; double lb[R], ub[R];
+#if KTN_DUMP
+        uint32_t jp[R];
+#endif
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const uint32_t ch = cur + r < n ? cur + r : n - 1;      // past the end: the last chunk again, results dropped
             const unsigned char* blob = blob0 + (size_t)ch * KTN_FAM_BLOB_BYTES(N);
-            const double* C = reinterpret_cast<const double*>(blob) + lane;
-            const int32_t* cols = reinterpret_cast<const int32_t*>(blob + 512u * N) + lane;
             const uint32_t slotid = (base + ch) * 32u + lane;
 #pragma unroll
-            for (int u = 0; u < N; ++u) { v[r].p0[u] = __ldg(C + F::slot0(u, N) * 32u); v[r].p1[u] = __ldg(C + F::slot1(u, N) * 32u); col[r][u] = __ldg(cols + u * 32u); }
+            for (int gq = 0; gq < (N + 1) / 2; ++gq) {       // pair groups: unique variables 2 gq, 2 gq + 1
+                double a0, a1, b0, b1;
+                ldg256(blob + gq * 1024 + lane * 32u, a0, a1, b0, b1);
+                v[r].p0[2 * gq] = a0; v[r].p1[2 * gq] = a1;
+                if (2 * gq + 1 < N) { v[r].p0[2 * gq + 1] = b0; v[r].p1[2 * gq + 1] = b1; }
+            }
+#pragma unroll
+            for (int gq = 0; gq < (N + 7) / 8; ++gq) {       // column groups: unique variables 8 gq .. 8 gq + 7
+                int32_t c8[8];
+                ldg256(blob + KTN_FAM_COL_OFF(N) + gq * 1024 + lane * 32u, c8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (8 * gq + k < N) col[r][8 * gq + k] = c8[k];
+            }
             row[r] = __ldg(p.chunk_rows + slotid);
             if (cur + r >= n) row[r] = -1;
             lb[r] = __ldg(p.chunk_lb + slotid); ub[r] = __ldg(p.chunk_ub + slotid);
+#if KTN_DUMP
+            jp[r] = __ldg(p.chunk_jp + slotid);
+#endif
         }
         // the warp's next ticket is drawn HERE, behind the rows' loads: its round trip overlaps theirs
         uint32_t tn = 0;
@@ -185,6 +217,15 @@ __device__ __forceinline__ void family_class(const KtnRoundParams& p, uint32_t l
                 p.rec[row[r]] = make_double4(g, aux, lb[r], ub[r]);
                 p.sel[row[r]] = (uint32_t)N | KTN_SEL_DEFER;
                 count_selected(p, selm, row[r], (uint32_t)N);
+#if KTN_DUMP == 1
+                double2* d2 = reinterpret_cast<double2*>(p.dump) + jp[r];
+#pragma unroll
+                for (int u = 0; u < N; ++u) d2[u] = make_double2(v[r].p1[u], v[r].x[u]);
+#elif KTN_DUMP == 2
+                double2* d2 = reinterpret_cast<double2*>(p.dump) + jp[r]; double* d1 = p.dump + 2 * (size_t)p.dump_nnz + jp[r];
+#pragma unroll
+                for (int u = 0; u < N; ++u) { d2[u] = make_double2(v[r].p0[u], v[r].p1[u]); d1[u] = v[r].x[u]; }
+#endif
             }
         }
         cur = __shfl_sync(0xffffffffu, tn, 0);
@@ -336,8 +377,7 @@ __global__ void __launch_bounds__(512, 1) ktn_round_kernel(const KtnRoundParams 
                         }
                         selv = nu | (bad ? KTN_SEL_ERRBIT : 0u);
                         p.b_row[row] = b;
-                        if (bad) atomicMin(&p.counts[2 + (p.epoch & 1u)], (unsigned long long)row + 1ull);
-                        count_selected(p, selm, row, nu);
+                                    count_selected(p, selm, row, nu);
                     }
                 }
                 if (row >= 0) p.sel[row] = selv;
@@ -411,8 +451,7 @@ __global__ void __launch_bounds__(128) ktn_big_kernel(const KtnRoundParams p) {
                 }
                 p.b_row[row] = b;
                 p.sel[row] = nu | (bad ? KTN_SEL_ERRBIT : 0u);
-                if (bad) atomicMin(&p.counts[2 + (p.epoch & 1u)], (unsigned long long)row + 1ull);
-                count_selected(p, selm, row, nu);
+                    count_selected(p, selm, row, nu);
             } else if (row >= 0) p.sel[row] = 0u;
         } else {
             // dense row: every column 0..num_var-1 is an entry (src/nlpeval.jl:49-54); columns the
@@ -456,7 +495,6 @@ __global__ void __launch_bounds__(128) ktn_big_kernel(const KtnRoundParams p) {
                 bad = __any_sync(0xffffffffu, bad);
                 if (lane == 0) {
                     p.b_row[rrow] = b; p.sel[rrow] = (uint32_t)n | (bad ? KTN_SEL_ERRBIT : 0u);
-                    if (bad) atomicMin(&p.counts[2 + (p.epoch & 1u)], (unsigned long long)rrow + 1ull);
                     atomicAdd(p.blk_cnt + (size_t)(p.epoch & 1u) * p.blk_stride + ((uint32_t)rrow >> KTN_CROWS_LOG2), (1ull << KTN_BLK_SHIFT) + (unsigned long long)n);
                 }
                 __syncwarp();
@@ -506,30 +544,37 @@ __device__ __forceinline__ void block_scan2(uint32_t& a, unsigned long long& b, 
     __syncthreads();
 }
 
-struct CutRow {     // row context of ktn_family_cut_entries: the chunk's SoA sections in global memory, lane offset applied
-    const double* C; const int32_t* cols; const double* X;
-    __device__ __forceinline__ double cst(uint32_t i) const { return __ldg(C + i * 32u); }
-    __device__ __forceinline__ int32_t col(uint32_t u) const { return __ldg(cols + u * 32u); }
-    __device__ __forceinline__ double xat(int32_t c) const { return __ldg(X + c); }
-};
-struct CutSink {    // the row's slice of the round's CSR
-    double* val; int32_t* col;
-    __device__ __forceinline__ void put(uint32_t q, double v, int32_t c) { val[q] = v; col[q] = c; }
-    __device__ __forceinline__ double get(uint32_t q) const { return val[q]; }
-    __device__ __forceinline__ void set(uint32_t q, double v) { val[q] = v; }
-};
+// Large problems: exclusive scan of K1's per-block counts by one block, so that the compaction blocks read their offsets instead
+// of each summing all counts (quadratic in the number of blocks).  off[2 j] = cuts, off[2 j + 1] = nnz before block j; totals at j = nblocks.
+__global__ void __launch_bounds__(1024) ktn_blkscan_kernel(const KtnRoundParams p, uint32_t nblocks, uint32_t epoch) {
+    __shared__ unsigned long long s_c[1024], s_n[1024];
+    const unsigned long long* bc = p.blk_cnt + (size_t)(epoch & 1u) * p.blk_stride;
+    const uint32_t per = (nblocks + 1023u) / 1024u, j0 = threadIdx.x * per, j1 = j0 + per < nblocks ? j0 + per : nblocks;
+    unsigned long long c = 0, n = 0;
+    for (uint32_t j = j0; j < j1; ++j) { const unsigned long long v = bc[j]; c += v >> KTN_BLK_SHIFT; n += v & KTN_BLK_NNZ_MASK; }
+    s_c[threadIdx.x] = c; s_n[threadIdx.x] = n;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned long long ac = threadIdx.x >= (unsigned)o ? s_c[threadIdx.x - o] : 0ull, an = threadIdx.x >= (unsigned)o ? s_n[threadIdx.x - o] : 0ull;
+        __syncthreads();
+        s_c[threadIdx.x] += ac; s_n[threadIdx.x] += an;
+        __syncthreads();
+    }
+    c = s_c[threadIdx.x] - c; n = s_n[threadIdx.x] - n;      // exclusive
+    for (uint32_t j = j0; j < j1; ++j) { const unsigned long long v = bc[j]; p.blk_off[2 * j] = c; p.blk_off[2 * j + 1] = n; c += v >> KTN_BLK_SHIFT; n += v & KTN_BLK_NNZ_MASK; }
+    if (threadIdx.x == 1023) { p.blk_off[2 * (size_t)nblocks] = s_c[1023]; p.blk_off[2 * (size_t)nblocks + 1] = s_n[1023]; }
+}
 
 // One block = KTN_CBLOCK threads x KTN_CRPT consecutive rows per thread = KTN_CROWS rows.
 #define KTN_CRPT (KTN_CROWS / KTN_CBLOCK)
-__global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRoundParams p, uint32_t nblocks, uint32_t epoch) {
-    __shared__ uint32_t s_cnt_base, s_first_bad, s_copy, s_last; __shared__ unsigned long long s_nnz_base, s_tot_n, s_tot_nz;
+__global__ void __launch_bounds__(KTN_CBLOCK, KTN_CBPS) ktn_compact_kernel(const KtnRoundParams p, uint32_t nblocks, uint32_t epoch, int scanned) {
+    __shared__ uint32_t s_cnt_base; __shared__ unsigned long long s_nnz_base, s_tot_n, s_tot_nz;
     __shared__ unsigned long long s_red[4][32];
     __shared__ uint32_t s_off[KTN_CROWS + 1];        // exclusive nnz offsets of the block's selected rows (compact list)
-    __shared__ uint32_t s_src[KTN_CROWS];            // first staging entry of each selected row whose cut K1 built (jac_ptr; the library caps nnz(J) at 2^32 - 1)
+    __shared__ uint32_t s_src[KTN_CROWS];            // first entry of each selected row in the static Jacobian CSR (jac_ptr; the library caps nnz(J) at 2^32 - 1)
     __shared__ uint16_t s_rowl[KTN_CROWS];           // block-local row index of each selected row | 0x8000 non-finite (K1) | 0x4000 deferred
     const uint32_t bid = blockIdx.x;
     const int64_t row0 = (int64_t)bid * KTN_CROWS, i0 = row0 + (int64_t)threadIdx.x * KTN_CRPT;
-    if (threadIdx.x == 0) { s_first_bad = 0xffffffffu; s_copy = 0u; }
     // every independent load of the block is requested up front: the row flags, then K1's per-block counts
     uint32_t sv[KTN_CRPT];
     if (i0 + KTN_CRPT <= p.num_rows) {
@@ -541,7 +586,7 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
     }
     // output offset of this block = cuts / nnz of all blocks before it; the totals of ALL blocks fix the blob's layout
     unsigned long long* bc = p.blk_cnt + (size_t)(epoch & 1u) * p.blk_stride;
-    {
+    if (!scanned) {
         unsigned long long cb = 0, nb = 0, ca = 0, na = 0;
         for (uint32_t j = threadIdx.x; j < nblocks; j += KTN_CBLOCK) {
             const unsigned long long v = bc[j], c = v >> KTN_BLK_SHIFT, n = v & KTN_BLK_NNZ_MASK;
@@ -559,18 +604,22 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
     for (int r = 0; r < KTN_CRPT; ++r) { a += sv[r] ? 1u : 0u; b += KTN_SEL_NNZ(sv[r]); }
     uint32_t ta; unsigned long long tb;
     block_scan2(a, b, ta, tb);      // contains the barriers that publish s_red
-    unsigned long long* const hdr = reinterpret_cast<unsigned long long*>(p.out_blob);
     if (threadIdx.x < 32) {
-        const bool live = threadIdx.x < KTN_CWARPS;
-        unsigned long long cb = live ? s_red[0][threadIdx.x] : 0ull, nb = live ? s_red[1][threadIdx.x] : 0ull;
-        unsigned long long ca = live ? s_red[2][threadIdx.x] : 0ull, na = live ? s_red[3][threadIdx.x] : 0ull;
-        for (int o = 16; o > 0; o >>= 1) {
-            cb += __shfl_xor_sync(0xffffffffu, cb, o); nb += __shfl_xor_sync(0xffffffffu, nb, o);
-            ca += __shfl_xor_sync(0xffffffffu, ca, o); na += __shfl_xor_sync(0xffffffffu, na, o);
+        unsigned long long cb, nb, ca, na;
+        if (scanned) { cb = p.blk_off[2 * (size_t)bid]; nb = p.blk_off[2 * (size_t)bid + 1]; ca = p.blk_off[2 * (size_t)nblocks]; na = p.blk_off[2 * (size_t)nblocks + 1]; }
+        else {
+            const bool live = threadIdx.x < KTN_CWARPS;
+            cb = live ? s_red[0][threadIdx.x] : 0ull; nb = live ? s_red[1][threadIdx.x] : 0ull;
+            ca = live ? s_red[2][threadIdx.x] : 0ull; na = live ? s_red[3][threadIdx.x] : 0ull;
+            for (int o = 16; o > 0; o >>= 1) {
+                cb += __shfl_xor_sync(0xffffffffu, cb, o); nb += __shfl_xor_sync(0xffffffffu, nb, o);
+                ca += __shfl_xor_sync(0xffffffffu, ca, o); na += __shfl_xor_sync(0xffffffffu, na, o);
+            }
         }
         if (threadIdx.x == 0) {
             s_cnt_base = (uint32_t)cb; s_nnz_base = nb; s_tot_n = ca; s_tot_nz = na;
             p.blk_cnt[(size_t)((epoch & 1u) ^ 1u) * p.blk_stride + bid] = 0ull;     // re-arm the slot the NEXT round's K1 adds into
+            if (bid == 0) { p.counts[4] = ca; p.counts[5] = na; }                   // the cut kernel's work list ends here
         }
     }
     __syncthreads();
@@ -581,7 +630,9 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
     double* const out_g = reinterpret_cast<double*>(p.out_blob + L.g); double* const out_viol = reinterpret_cast<double*>(p.out_blob + L.viol);
     double* const out_b = reinterpret_cast<double*>(p.out_blob + L.b);
     int32_t* const out_col = reinterpret_cast<int32_t*>(p.out_blob + L.col); double* const out_val = reinterpret_cast<double*>(p.out_blob + L.val);
-    // A: compact list of the block's selected rows: local row index (+ flags) and nnz offset
+    if (bid == nblocks - 1 && threadIdx.x == 0) out_ptr[s_tot_n] = (int64_t)s_tot_nz;
+    // compact list of the block's selected rows: local row index (+ flags) and nnz offset
+    bool copy = false;
 #pragma unroll
     for (int r = 0; r < KTN_CRPT; ++r) {
         const uint32_t s = sv[r];
@@ -589,89 +640,147 @@ __global__ void __launch_bounds__(KTN_CBLOCK, 2) ktn_compact_kernel(const KtnRou
         s_off[a] = (uint32_t)b;
         s_rowl[a] = (uint16_t)((threadIdx.x * KTN_CRPT + r) | ((s & KTN_SEL_ERRBIT) ? 0x8000u : 0u) | ((s & KTN_SEL_DEFER) ? 0x4000u : 0u));
         a += 1u; b += KTN_SEL_NNZ(s);
+        copy = copy || !(s & KTN_SEL_DEFER);
     }
     if (threadIdx.x == 0) s_off[ta] = (uint32_t)tb;
-    __syncthreads();
-    // B: one thread per SELECTED row
+    const int any_copy = __syncthreads_or(copy ? 1 : 0);
+    // one thread per SELECTED row: where it goes.  Rows whose cut K1 built get their scalars here; a family row gets an entry of
+    // the cut kernel's work list (slot, nnz) with its record {g, aux, lb, ub} parked in the cut's own scalar arrays (so that the
+    // cut kernel starts from coalesced loads), and the sectors of the chunk blob that hold the row are requested into L2.
+    unsigned long long* const wl = p.worklist;
     for (uint32_t k = threadIdx.x; k < ta; k += KTN_CBLOCK) {
         const uint32_t rl = s_rowl[k];
         const int64_t i = row0 + (rl & 0x3fffu);
         const int64_t cidx = (int64_t)cbase + k, o = (int64_t)(nbase + s_off[k]);
-        double g, bcst, lb, ub; bool bad;
-        if (rl & 0x4000u) {
+        s_src[k] = (uint32_t)p.jac_ptr[i];
+        out_row[cidx] = i + p.row_offset; out_ptr[cidx] = o;
+        if (!(rl & 0x4000u)) {
+            const double g = p.g_row[i], bcst = p.b_row[i], lb = p.row_lb[i], ub = p.row_ub[i];
+            out_lo[cidx] = lb - bcst; out_hi[cidx] = ub - bcst;     // src/model.jl:74-75
+            out_g[cidx] = g; out_b[cidx] = bcst;
+            const double v1 = lb - g, v2 = g - ub;
+            out_viol[cidx] = (g == g) ? (v1 > v2 ? v1 : v2) : g;
+            wl[cidx] = 0ull;
+            if (rl & 0x8000u) atomicMin(&p.counts[2 + (epoch & 1u)], (unsigned long long)cidx);      // first non-finite cut of the round
+        } else {
             const double4 rc = p.rec[i];
-            const uint32_t slot = (uint32_t)__ldg(p.row_slot + i), c = slot >> 5, lane = slot & 31u, nu = s_off[k + 1] - s_off[k];
-            g = rc.x; lb = rc.z; ub = rc.w;
+            const uint32_t slot = (uint32_t)__ldg(p.row_slot + i), c = slot >> 5, ln = slot & 31u, nu = s_off[k + 1] - s_off[k];
             const int fam = c >= p.fam_begin[KTN_FAM_QUAD] ? KTN_FAM_QUAD : KTN_FAM_LSE;
             const unsigned char* blob = p.blob + p.cls_blob_off[fam][nu] + (size_t)(c - p.cls_begin[fam][nu]) * KTN_FAM_BLOB_BYTES(nu);
-            const uint64_t ow = __ldg(reinterpret_cast<const unsigned long long*>(blob + 640u * nu) + lane);
-            const CutRow r{reinterpret_cast<const double*>(blob) + lane, reinterpret_cast<const int32_t*>(blob + 512u * nu) + lane, p.x};
-            CutSink s{out_val + o, out_col + o};
-            if (fam == KTN_FAM_LSE) bad = ktn_family_cut_entries<KTN_FAM_LSE>(r, nu, ow, s, g, rc.y, p.do_round != 0, p.rng, bcst);
-            else bad = ktn_family_cut_entries<KTN_FAM_QUAD>(r, nu, ow, s, g, rc.y, p.do_round != 0, p.rng, bcst);
-        } else {
-            g = p.g_row[i]; bcst = p.b_row[i]; lb = p.row_lb[i]; ub = p.row_ub[i];
-            s_src[k] = (uint32_t)p.jac_ptr[i];
-            bad = (rl & 0x8000u) != 0u;
-            s_copy = 1u;
+            for (uint32_t gq = 0; gq < KTN_FAM_PGROUPS(nu) + KTN_FAM_CGROUPS(nu); ++gq) prefetch_l2(blob + gq * 1024u + ln * 32u);
+            prefetch_l2(blob + KTN_FAM_ORD_OFF(nu) + ln * 8u);
+            out_g[cidx] = rc.x; out_b[cidx] = rc.y; out_lo[cidx] = rc.z; out_hi[cidx] = rc.w;
+            wl[cidx] = ((unsigned long long)(nu | ((uint32_t)fam << 8) | 0x10000u) << 32) | slot;
         }
-        out_row[cidx] = i + p.row_offset; out_ptr[cidx] = o;
-        out_lo[cidx] = lb - bcst; out_hi[cidx] = ub - bcst;     // src/model.jl:74-75
-        out_g[cidx] = g; out_b[cidx] = bcst;
-        const double v1 = lb - g, v2 = g - ub;
-        out_viol[cidx] = (g == g) ? (v1 > v2 ? v1 : v2) : g;
-        if (bad) atomicMin(&s_first_bad, k);
     }
     __syncthreads();
-    // the reference stops at the first non-finite cut (src/model.jl:278): cuts before it stand
-    if (threadIdx.x == 0 && s_first_bad != 0xffffffffu) {
-        const uint32_t k = s_first_bad;
-        p.errpos[2 * bid] = (unsigned long long)cbase + k; p.errpos[2 * bid + 1] = nbase + s_off[k];
-        atomicMin(&p.counts[2 + (epoch & 1u)], (unsigned long long)(row0 + (s_rowl[k] & 0x3fffu)) + 1ull);
-    }
-    // C: expand the rows K1 built: one thread per output entry, coalesced writes.  Every warp owns a contiguous range of the
-    // block's entries: one binary search (shared memory) finds the row of the range's first entry, after that each lane walks
-    // forward through the row offsets (a few steps per 32 entries).  Four steps are unrolled: all loads are in flight before the first store.
+    // expand: one thread per output entry, coalesced writes: the columns of every entry (the static Jacobian structure IS the
+    // entry order) and the coefficients K1 staged.  Every warp owns a contiguous range of the block's entries: one binary search
+    // (shared memory) finds the row of the range's first entry, after that each lane walks forward through the row offsets
+    // (a few steps per 32 entries).  Four steps are unrolled: all loads are in flight before the first store.
     const uint32_t nent = (uint32_t)tb, lane = threadIdx.x & 31u;
-    if (s_copy) {
-        const uint32_t per = ((nent + KTN_CBLOCK - 1) / KTN_CBLOCK) * 32u;         // entries per warp, a multiple of 32
-        const uint32_t wbeg = (threadIdx.x >> 5) * per, wend = wbeg + per < nent ? wbeg + per : nent;
-        if (wbeg < wend) {
-            uint32_t lo = 0, hi = ta;   // largest k with s_off[k] <= wbeg
-            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= wbeg) lo = mid; else hi = mid; }
-            for (uint32_t e0 = wbeg + lane; e0 - lane < wend; e0 += 128u) {
-                uint32_t src[4]; int32_t cv[4]; double vv[4];
+    const uint32_t per = ((nent + KTN_CBLOCK - 1) / KTN_CBLOCK) * 32u;         // entries per warp, a multiple of 32
+    const uint32_t wbeg = (threadIdx.x >> 5) * per, wend = wbeg + per < nent ? wbeg + per : nent;
+    if (wbeg < wend) {
+        uint32_t lo = 0, hi = ta;   // largest k with s_off[k] <= wbeg
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= wbeg) lo = mid; else hi = mid; }
+        for (uint32_t e0 = wbeg + lane; e0 - lane < wend; e0 += 128u) {
+            uint32_t src[4]; int32_t cv[4]; double vv[4]; bool built[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t e = e0 + 32u * (uint32_t)k;
-                    src[k] = 0xffffffffu;
-                    if (e < wend) { while (s_off[lo + 1] <= e) ++lo; if (!(s_rowl[lo] & 0x4000u)) src[k] = s_src[lo] + (e - s_off[lo]); }
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { cv[k] = src[k] != 0xffffffffu ? p.jac_col[src[k]] : 0; vv[k] = src[k] != 0xffffffffu ? p.stage_val[src[k]] : 0.0; }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) if (src[k] != 0xffffffffu) { const unsigned long long e = nbase + e0 + 32u * (uint32_t)k; out_col[e] = cv[k]; out_val[e] = vv[k]; }
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t e = e0 + 32u * (uint32_t)k;
+                src[k] = 0xffffffffu; built[k] = false;
+                if (e < wend) { while (s_off[lo + 1] <= e) ++lo; src[k] = s_src[lo] + (e - s_off[lo]); built[k] = !(s_rowl[lo] & 0x4000u); }
             }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { cv[k] = src[k] != 0xffffffffu ? __ldg(p.jac_col + src[k]) : 0; vv[k] = (any_copy && built[k]) ? p.stage_val[src[k]] : 0.0; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (src[k] != 0xffffffffu) { const unsigned long long e = nbase + e0 + 32u * (uint32_t)k; out_col[e] = cv[k]; if (built[k]) out_val[e] = vv[k]; }
         }
     }
-    // D: the last block to finish settles the round
-    __syncthreads();
-    if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(&p.counts[7], 1ull) == (unsigned long long)nblocks - 1ull ? 1u : 0u; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: the cuts of the family rows (KTN_SEL_DEFER).  One thread per cut of the compacted list, KTN_XBLOCK consecutive cuts per
+// block: consecutive cuts own consecutive slices of the round's CSR, so the block stages its coefficients in shared memory and
+// writes them out coalesced.  Per row: record {g, aux, lb, ub}, slot -> the row's groups in the chunk blob (256-bit loads),
+// x* gathers, ktn_family_cut_terms.  Every load of a row is independent of the row's arithmetic: eight terms are in flight at once.
+// The LAST block to finish settles the first non-finite row (src/model.jl:69-73, :278), writes totals and blob header and
+// re-arms the per-round state.
+// ---------------------------------------------------------------------------------------------
+#define KTN_XBLOCK 128
+struct CutRow {     // row context of ktn_family_cut_terms: the row's groups in the chunk blob (ktn_program.h)
+    const unsigned char* blob; const double* X; uint32_t nu, lane;
+    __device__ __forceinline__ void pairs2(uint32_t g, double& a0, double& a1, double& b0, double& b1) const { ldg256(blob + g * 1024u + lane * 32u, a0, a1, b0, b1); }
+    __device__ __forceinline__ void cols8(uint32_t g, int32_t (&c)[8]) const { ldg256(blob + KTN_FAM_COL_OFF(nu) + g * 1024u + lane * 32u, c); }
+    __device__ __forceinline__ double xat(int32_t c) const { return __ldg(X + c); }
+};
+struct CutSink {    // coefficients: the row's slice of the block's staging (or of the round's CSR); products: a column of the block's scratch
+    double* val; double* t;
+    __device__ __forceinline__ void put(uint32_t q, double v) { val[q] = v; }
+    __device__ __forceinline__ double get(uint32_t q) const { return val[q]; }
+    __device__ __forceinline__ void set(uint32_t q, double v) { val[q] = v; }
+    __device__ __forceinline__ void put_t(uint32_t q, double v) { t[q * KTN_XBLOCK] = v; }
+    __device__ __forceinline__ double get_t(uint32_t q) const { return t[q * KTN_XBLOCK]; }
+};
+
+__global__ void __launch_bounds__(KTN_XBLOCK, 4) ktn_cut_kernel(const KtnRoundParams p, uint32_t epoch) {
+    __shared__ double s_val[KTN_XBLOCK * KTN_FAM_REGS];      // coefficients of the block's cuts, in CSR order
+    __shared__ double s_t[KTN_FAM_REGS * KTN_XBLOCK];        // products -x* J: [entry][thread]
+    __shared__ unsigned long long s_e0, s_e1; __shared__ uint32_t s_last;
+    const unsigned long long ca = __ldcg(&p.counts[4]), na = __ldcg(&p.counts[5]);
+    const KtnPackLayout L = ktn_pack_layout(ca, na);
+    const int64_t* const out_row = reinterpret_cast<const int64_t*>(p.out_blob + L.row_id); const int64_t* const out_ptr = reinterpret_cast<const int64_t*>(p.out_blob + L.row_ptr);
+    double* const out_lo = reinterpret_cast<double*>(p.out_blob + L.lo); double* const out_hi = reinterpret_cast<double*>(p.out_blob + L.hi);
+    double* const out_g = reinterpret_cast<double*>(p.out_blob + L.g); double* const out_viol = reinterpret_cast<double*>(p.out_blob + L.viol);
+    double* const out_b = reinterpret_cast<double*>(p.out_blob + L.b); double* const out_val = reinterpret_cast<double*>(p.out_blob + L.val);
+    for (unsigned long long c0 = (unsigned long long)blockIdx.x * KTN_XBLOCK; c0 < ca; c0 += (unsigned long long)gridDim.x * KTN_XBLOCK) {
+        const unsigned long long cidx = c0 + threadIdx.x;
+        const bool active = cidx < ca;
+        int64_t o = 0; unsigned long long w = 0ull;
+        if (active) { w = __ldcg(p.worklist + cidx); o = __ldcg(out_ptr + cidx); }
+        if (threadIdx.x == 0) { s_e0 = (unsigned long long)o; const unsigned long long cend = c0 + KTN_XBLOCK < ca ? c0 + KTN_XBLOCK : ca; s_e1 = (unsigned long long)__ldcg(out_ptr + cend); }
+        const bool mine = active && w != 0ull;
+        // the block's slice of the CSR is staged when every cut of the block is a family cut (else: straight to the CSR)
+        const int staged = __syncthreads_and((mine || !active) ? 1 : 0);
+        const unsigned long long e0 = s_e0, e1 = s_e1;
+        if (mine) {
+            const double g = __ldcg(out_g + cidx), aux = __ldcg(out_b + cidx), lb = __ldcg(out_lo + cidx), ub = __ldcg(out_hi + cidx);      // parked by the compaction kernel
+            const uint32_t slot = (uint32_t)w, c = slot >> 5, ln = slot & 31u, nu = (uint32_t)(w >> 32) & 0xffu;
+            const int fam = (int)((w >> 40) & 0xffu);
+            const unsigned char* blob = p.blob + p.cls_blob_off[fam][nu] + (size_t)(c - p.cls_begin[fam][nu]) * KTN_FAM_BLOB_BYTES(nu);
+            const uint64_t rw = __ldg(reinterpret_cast<const unsigned long long*>(blob + KTN_FAM_ORD_OFF(nu)) + ln);
+            const CutRow r{blob, p.x, nu, ln};
+            CutSink s{staged ? s_val + ((unsigned long long)o - e0) : out_val + o, s_t + threadIdx.x};
+            double bcst; bool bad;
+            if (fam == KTN_FAM_LSE) bad = ktn_family_cut_terms<KTN_FAM_LSE>(r, nu, rw, s, g, aux, p.do_round != 0, p.rng, bcst);
+            else bad = ktn_family_cut_terms<KTN_FAM_QUAD>(r, nu, rw, s, g, aux, p.do_round != 0, p.rng, bcst);
+            out_lo[cidx] = lb - bcst; out_hi[cidx] = ub - bcst;     // src/model.jl:74-75
+            out_b[cidx] = bcst;
+            const double v1 = lb - g, v2 = g - ub;
+            out_viol[cidx] = (g == g) ? (v1 > v2 ? v1 : v2) : g;
+            if (bad) atomicMin(&p.counts[2 + (epoch & 1u)], cidx);      // first non-finite cut of the round
+        }
+        __syncthreads();
+        if (staged) for (unsigned long long e = e0 + threadIdx.x; e < e1; e += KTN_XBLOCK) out_val[e] = s_val[e - e0];
+        __syncthreads();
+    }
+    // the last block to finish settles the round
+    if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(&p.counts[7], 1ull) == (unsigned long long)gridDim.x - 1ull ? 1u : 0u; }
     __syncthreads();
     if (!s_last) return;
     if (threadIdx.x == 0) {
         __threadfence();
-        const unsigned long long ca = s_tot_n, na = s_tot_nz;
-        const unsigned long long err = __ldcg(&p.counts[2 + (epoch & 1u)]);
-        unsigned long long n = ca, nz = na;
-        if (err != ~0ull) { const unsigned long long eb = (err - 1ull) >> KTN_CROWS_LOG2; n = __ldcg(&p.errpos[2 * eb]); nz = __ldcg(&p.errpos[2 * eb + 1]); }
-        p.counts[0] = n; p.counts[1] = nz; p.counts[4] = ca; p.counts[5] = na; p.counts[6] = err;
-        p.counts[2 + ((epoch & 1u) ^ 1u)] = ~0ull;                    // re-arm the slot the NEXT round's K1 uses
+        unsigned long long* const hdr = reinterpret_cast<unsigned long long*>(p.out_blob);
+        const unsigned long long errc = __ldcg(&p.counts[2 + (epoch & 1u)]);      // the reference stops at the first non-finite cut (src/model.jl:278): cuts before it stand
+        unsigned long long n = ca, nz = na, err = ~0ull;
+        if (errc != ~0ull) { n = errc; nz = (unsigned long long)__ldcg(out_ptr + errc); err = (unsigned long long)(__ldcg(out_row + errc) - p.row_offset) + 1ull; }
+        p.counts[0] = n; p.counts[1] = nz; p.counts[6] = err;
+        p.counts[2 + ((epoch & 1u) ^ 1u)] = ~0ull;                    // re-arm the slot the NEXT round uses
         p.counts[7] = 0ull;
         hdr[0] = n; hdr[1] = nz; hdr[2] = err; hdr[3] = L.total; hdr[4] = (unsigned long long)p.row_offset; hdr[5] = ca; hdr[6] = na; hdr[7] = 0ull;
-        out_ptr[ca] = (int64_t)na;
     }
-    for (uint32_t i = threadIdx.x; i < KTN_TICKETS; i += KTN_CBLOCK) p.ticket[i] = 0u;     // K1 is over: re-arm its work tickets
+    for (uint32_t i = threadIdx.x; i < KTN_TICKETS; i += KTN_XBLOCK) p.ticket[i] = 0u;     // K1 is over: re-arm its work tickets
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -748,7 +857,6 @@ __global__ void __launch_bounds__(256) ktn_topk_select_kernel(const KtnRoundPara
     st->hist[threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
         st->done = 0u;
-        if (pass == 7) p.counts[2 + (p.epoch & 1u)] = ~0ull;            // the first non-finite row is recomputed over the survivors (T4)
     }
 }
 
@@ -800,7 +908,6 @@ __global__ void __launch_bounds__(KTN_CBLOCK) ktn_topk_demote_kernel(const KtnRo
         if (!keep) { p.sel[i] = 0u; continue; }
         const uint32_t s = p.sel[i];
         ++cnt; nnz += KTN_SEL_NNZ(s);
-        if (s & KTN_SEL_ERRBIT) atomicMin(&p.counts[2 + (p.epoch & 1u)], (unsigned long long)i + 1ull);
     }
     for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); nnz += __shfl_xor_sync(0xffffffffu, nnz, o); }
     if (lane == 0 && cnt) { atomicAdd(&s_cnt, cnt); atomicAdd(&s_nnz, nnz); }
@@ -902,8 +1009,13 @@ int ktn_launch_round(const KtnRoundParams& p, const KtnLaunchPlan& plan, int num
         launches += 11;
     }
     if (nblocks > 0) {
-        ktn_compact_kernel<<<nblocks, KTN_CBLOCK, 0, stream>>>(p, nblocks, epoch);
-        ++launches;
+        const int scanned = nblocks > 1024u ? 1 : 0;
+        if (scanned) { ktn_blkscan_kernel<<<1, 1024, 0, stream>>>(p, nblocks, epoch); ++launches; }
+        ktn_compact_kernel<<<nblocks, KTN_CBLOCK, 0, stream>>>(p, nblocks, epoch, scanned);
+        uint32_t xblocks = (uint32_t)((p.num_rows + KTN_XBLOCK - 1) / KTN_XBLOCK);
+        if (xblocks > (uint32_t)num_sms * 4u) xblocks = (uint32_t)num_sms * 4u;      // resident blocks: every block loops over its share of the cuts
+        ktn_cut_kernel<<<xblocks, KTN_XBLOCK, 0, stream>>>(p, epoch);
+        launches += 2;
     }
     *err = cudaGetLastError();
     return launches;

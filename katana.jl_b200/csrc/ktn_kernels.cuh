@@ -24,6 +24,8 @@ struct KtnRoundParams {
     const double* row_lb;
     const double* row_ub;
     const int32_t* row_slot;   // row -> chunk * 32 + lane
+    const uint32_t* chunk_jp;  // chunk * 32 + lane -> first Jacobian entry of the row (jac_ptr)
+    double* dump; uint64_t dump_nnz;
     // round inputs
     const double* x;
     const uint8_t* force;      // KTN_MODE_FORCE: per-row mask
@@ -53,6 +55,8 @@ struct KtnRoundParams {
     // compaction: per block of KTN_CROWS rows, cuts << KTN_BLK_SHIFT | nnz of the selected rows, added by K1 and summed
     // by K2.  Two copies indexed by epoch parity; K2 zeroes the copy the next round adds into.
     unsigned long long* blk_cnt; uint32_t blk_stride;
+    unsigned long long* blk_off;       // large problems: exclusive scan of blk_cnt (ktn_blkscan_kernel), 2 words per block + totals
+    unsigned long long* worklist;      // per cut of the compacted list: 0 = cut built by K1, else (nnz | family << 8 | 1 << 16) << 32 | chunk slot (cut kernel)
     unsigned long long* errpos;        // per compaction block: (cut index, entry offset) of the block's first non-finite row (K2)
     // [0] n_cuts [1] nnz (both truncated at the first non-finite row) [2],[3] first-error row + 1 of even / odd epochs
     // (~0 = none) [4] n_cuts_total [5] nnz_total [6] first-error row + 1 of the last round [7] K2 blocks finished (the last one

@@ -100,7 +100,22 @@ enum {
 #define KTN_FAM_REGS 16
 #define KTN_FAM_NCLS (KTN_FAM_REGS + 1)
 static inline uint32_t ktn_family_class(uint32_t n_uniq) { return n_uniq <= KTN_FAM_REGS ? n_uniq : 0u; }
-#define KTN_FAM_BLOB_BYTES(k) (640u * (k) + 256u)
+// Blob of a class k >= 1 chunk (lane stride 32 bytes: one 256-bit load per lane and group, and a SELECTED row's data sits in few
+// 32-byte sectors -- the compaction kernel reads it back sector by sector from DRAM, where every sector is a row activation):
+//   pair groups  [(k + 1) / 2][32 lanes] x 32 bytes: (p0, p1) of unique variables 2g and 2g + 1 (ktn_family_slot; zero padding)
+//   col groups   [(k + 7) / 8][32 lanes] x 32 bytes: columns of unique variables 8g .. 8g + 7 (zero padding)
+//   rank         [32 lanes] x 8 bytes: 4 bits per unique variable = its Jacobian entry index
+#define KTN_FAM_PGROUPS(k) (((k) + 1u) / 2u)
+#define KTN_FAM_CGROUPS(k) (((k) + 7u) / 8u)
+#define KTN_FAM_COL_OFF(k) (1024u * KTN_FAM_PGROUPS(k))
+#define KTN_FAM_ORD_OFF(k) (1024u * (KTN_FAM_PGROUPS(k) + KTN_FAM_CGROUPS(k)))
+#define KTN_FAM_BLOB_BYTES(k) (KTN_FAM_ORD_OFF(k) + 256u)
+// byte offset (inside the chunk blob) of the pair / the column of unique variable u of the row in `lane`
+#define KTN_FAM_PAIR_AT(u, lane) (((u) >> 1) * 1024u + (lane) * 32u + ((u) & 1u) * 16u)
+#define KTN_FAM_COL_AT(k, u, lane) (KTN_FAM_COL_OFF(k) + ((u) >> 3) * 1024u + (lane) * 32u + ((u) & 7u) * 4u)
+static inline uint32_t ktn_family_slot(uint32_t family, uint32_t which, uint32_t u, uint32_t nu) {
+    return family == 1u /* KTN_FAM_LSE */ ? 2u * u + which : (which ? nu + u : u);      // QUAD: a_u = slot u, b_u = slot nu + u
+}
 
 // shape flags
 enum { KTN_SH_NL = 1, KTN_SH_DENSE = 2, KTN_SH_BIG = 4 };
@@ -139,7 +154,7 @@ struct KtnChunkDesc {
 
 // Compaction blocks: K1 counts the selected rows of every block of KTN_CROWS consecutive rows
 // (cuts << KTN_BLK_SHIFT | nnz, one 64-bit atomic per warp and block), K2 turns the counts into offsets.
-#define KTN_CROWS_LOG2 12
+#define KTN_CROWS_LOG2 11
 #define KTN_CROWS (1 << KTN_CROWS_LOG2)
 #define KTN_BLK_SHIFT 48
 #define KTN_BLK_NNZ_MASK ((1ull << KTN_BLK_SHIFT) - 1ull)

@@ -8,6 +8,11 @@ cases = [(1, 100000, 1000000, 0.1, "lse1e6"), (0, 100000, 1000000, 0.1, "qcqp1e6
 if os.environ.get("AB_CASES") == "all":
     cases += [(1, 100000, 1000000, 1.0, "lse1e6"), (1, 100000, 1000000, 0.01, "lse1e6"), (0, 10000, 100000, 0.1, "qcqp1e5"), (2, 100000, 1000000, 0.1, "soc1e6")]
 data = {}
+if len(sys.argv) > 2:      # one process per variant: the libraries export the same symbols, and the first one loaded would serve the internal calls of all
+    import subprocess
+    for path in sys.argv[1:]:
+        subprocess.run([sys.executable, os.path.abspath(__file__), path], check=False)
+    sys.exit(0)
 for path in sys.argv[1:]:
     P = KtnLibrary(path)
     out = [os.path.basename(path)]

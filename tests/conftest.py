@@ -43,6 +43,7 @@ def cuda_lib():
 
 @pytest.fixture(scope="session")
 def synth_lib():
-    """libktn.so loaded only for its synthetic generators (no device call)."""
-    from katana_jl_b200.binding import CUDA_LIB_PATH, KtnLibrary
-    return KtnLibrary(CUDA_LIB_PATH)
+    """libktn_synth.so: the synthetic generators alone (no device call, not the product library)."""
+    from katana_jl_b200.binding import SynthLibrary
+    _make("katana.jl_b200/csrc", "../libktn_synth.so")
+    return SynthLibrary()

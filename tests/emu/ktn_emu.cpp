@@ -51,18 +51,22 @@ struct EmuFamRow {
     double xat(int32_t c) const { return X[c]; }
     double x(uint32_t u) const { return X[col(u)]; }
     uint32_t rank(uint32_t u) const { return rk[(size_t)u * L + lane]; }
-    uint64_t orderword() const { return ((const uint64_t*)rk)[lane]; }
+    // class >= 1 blobs (grouped layout, ktn_program.h): C = the blob
+    uint64_t rankword() const { return ((const uint64_t*)((const uint8_t*)C + KTN_FAM_ORD_OFF(nu)))[lane]; }
+    void pairs2(uint32_t g, double& a0, double& a1, double& b0, double& b1) const { const double* q = (const double*)((const uint8_t*)C + g * 1024u + lane * 32u); a0 = q[0]; a1 = q[1]; b0 = q[2]; b1 = q[3]; }
+    void cols8(uint32_t g, int32_t (&c)[8]) const { memcpy(c, (const uint8_t*)C + KTN_FAM_COL_OFF(nu) + g * 1024u + lane * 32u, 32); }
+    void pair(uint32_t u, double& p0, double& p1) const { const double* q = (const double*)((const uint8_t*)C + KTN_FAM_PAIR_AT(u, lane)); p0 = q[0]; p1 = q[1]; }
+    int32_t gcol(uint32_t u) const { return *(const int32_t*)((const uint8_t*)C + KTN_FAM_COL_AT(nu, u, lane)); }
 };
 struct EmuFamSink {
     double* out; const int32_t* scol; const double* X;
     void put_j(uint32_t q, double v) { out[q] = v; } double get_j(uint32_t q) const { return out[q]; }
     double xsorted(uint32_t q) const { return X[scol[q]]; }
 };
-struct EmuCutSink {     // K2's sink: coefficient and column of entry q; the column must be the static Jacobian structure's
-    double* val; const int32_t* scol; bool* colmismatch;
-    void put(uint32_t q, double v, int32_t c) { val[q] = v; if (scol[q] != c) *colmismatch = true; }
-    double get(uint32_t q) const { return val[q]; }
-    void set(uint32_t q, double v) { val[q] = v; }
+struct EmuCutSink {     // the cut kernel's sink: coefficients of the row (entry order) and the products -x* J
+    double* val; double t[KTN_FAM_REGS];
+    void put(uint32_t q, double v) { val[q] = v; } double get(uint32_t q) const { return val[q]; } void set(uint32_t q, double v) { val[q] = v; }
+    void put_t(uint32_t q, double v) { t[q] = v; } double get_t(uint32_t q) const { return t[q]; }
 };
 static EmuFamRow emu_row(const KtnProblem& P, const KtnChunkDesc& cd, uint32_t lane, const double* x) {
     const uint32_t nu = (uint32_t)cd.aux;
@@ -80,7 +84,7 @@ static void run_family_row(ktn_handle* h, const KtnChunkDesc& cd, uint32_t lane,
     if constexpr (N > 0) {
         typedef KtnFamily<FAM> F;
         KtnFamRegs<NR> v;
-        for (int u = 0; u < N; ++u) { v.p0[u] = r.cst(F::slot0(u, N)); v.p1[u] = r.cst(F::slot1(u, N)); v.x[u] = r.x(u); }
+        for (int u = 0; u < N; ++u) { r.pair(u, v.p0[u], v.p1[u]); v.x[u] = x[r.gcol(u)]; }
         g = F::template forward<NR>(v, aux);
     } else g = KtnFamily<FAM>::forward_stream(r, aux);
     h->g_row[row] = g;
@@ -115,11 +119,11 @@ static bool run_family_cut(ktn_handle* h, int64_t row, double& b) {
         fprintf(stderr, "emu: family blob addressing violated\n"); abort(); }
     const EmuFamRow r = emu_row(P, cd, lane, h->x_last.data());
     const int64_t base = P.jac_ptr[row];
-    bool mismatch = false;
-    EmuCutSink s{h->stage_val.data() + base, P.jac_col.data() + base, &mismatch};
-    const bool bad = fam == KTN_FAM_LSE ? ktn_family_cut_entries<KTN_FAM_LSE>(r, r.nu, r.orderword(), s, h->g_row[row], h->aux_row[row], h->do_round != 0, h->opt.cut_coef_rng, b)
-                                        : ktn_family_cut_entries<KTN_FAM_QUAD>(r, r.nu, r.orderword(), s, h->g_row[row], h->aux_row[row], h->do_round != 0, h->opt.cut_coef_rng, b);
-    if (mismatch) { fprintf(stderr, "emu: order word does not reproduce the Jacobian structure\n"); abort(); }
+    const uint64_t rw = r.rankword();
+    for (uint32_t u = 0; u < r.nu; ++u) if (P.jac_col[base + ((rw >> (4 * u)) & 15u)] != r.gcol(u)) { fprintf(stderr, "emu: rank word does not reproduce the Jacobian structure\n"); abort(); }
+    EmuCutSink s{h->stage_val.data() + base, {0}};
+    const bool bad = fam == KTN_FAM_LSE ? ktn_family_cut_terms<KTN_FAM_LSE>(r, r.nu, rw, s, h->g_row[row], h->aux_row[row], h->do_round != 0, h->opt.cut_coef_rng, b)
+                                        : ktn_family_cut_terms<KTN_FAM_QUAD>(r, r.nu, rw, s, h->g_row[row], h->aux_row[row], h->do_round != 0, h->opt.cut_coef_rng, b);
     return bad;
 }
 

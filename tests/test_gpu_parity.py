@@ -271,7 +271,7 @@ def test_device_resident_round_and_counters(cuda_lib):
     l0 = h.timings()["launches"]
     h.separate_device_async(dx.data_ptr())
     got = h.fetch_last()
-    assert h.timings()["launches"] - l0 == 2            # K1 + K2
+    assert h.timings()["launches"] - l0 == 3            # K1 (evaluate, test) + K2 (compact) + K3 (cuts of the family rows)
     assert_batches_identical(ref, got)
     h.set_stream(0)
 
