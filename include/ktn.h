@@ -87,8 +87,10 @@ typedef struct ktn_options {
 
 /* ktn_options.flags */
 enum {
-    KTN_FLAG_LEAN_VIEW = 1  /* ktn_fetch_cuts_view downloads only what the LP needs (row_id, row_ptr, col, val, lo, hi);
+    KTN_FLAG_LEAN_VIEW = 1, /* ktn_fetch_cuts_view downloads only what the LP needs (row_id, row_ptr, col, val, lo, hi);
                                g, viol and bconst come back NULL: 11 % less PCIe traffic per round */
+    KTN_FLAG_TIME_KERNELS = 2 /* ktn_timings.compact_ms / cut_ms are timed separately (one more CUDA event per round, between the
+                               compaction and the cut kernel); otherwise compact_ms covers both and cut_ms is 0 */
 };
 
 typedef struct ktn_timings {
@@ -100,10 +102,12 @@ typedef struct ktn_timings {
     int64_t launches;     /* kernels launched by this library since creation */
     int64_t rounds;       /* separation rounds run since creation */
     double eval_ms;       /* last round: evaluation kernel(s) (K1) */
-    double compact_ms;    /* last round: compaction kernel (K2) */
+    double compact_ms;    /* last round: compaction kernel (K2); without KTN_FLAG_TIME_KERNELS: K2 + K3 */
     double eval_ms_sum;   /* sums over every round timed since creation (CUDA events on the round's stream) */
     double compact_ms_sum;
     int64_t rounds_timed;
+    double cut_ms;        /* last round: cut kernel (K3: cuts of the family rows) */
+    double cut_ms_sum;
 } ktn_timings;
 
 /* lifetime -- replaces constructing KatanaFirstOrderSeparator() (src/separators.jl:58-77). */

@@ -18,7 +18,8 @@ CUDA_LIB_PATH = os.environ.get("KTN_LIB") or os.path.join(_HERE, "libktn.so")   
 OP_CONST, OP_VAR, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_NEG, OP_EXP, OP_LOG, OP_SQRT, OP_ABS = range(12)
 ROW_NL, ROW_DENSE = 1, 2
 KTN_OK, KTN_NUMERIC_NONFINITE = 0, 1
-FLAG_LEAN_VIEW = 1          # ktn_options.flags: cut views carry only what the LP needs
+FLAG_LEAN_VIEW = 1
+FLAG_TIME_KERNELS = 2          # ktn_options.flags: cut views carry only what the LP needs
 SYNTH_QCQP, SYNTH_LSE, SYNTH_SOC = 0, 1, 2
 
 
@@ -34,7 +35,7 @@ class ktn_options(C.Structure):
 class ktn_timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("exchange_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("launches", C.c_int64), ("rounds", C.c_int64), ("eval_ms", C.c_double), ("compact_ms", C.c_double),
-                ("eval_ms_sum", C.c_double), ("compact_ms_sum", C.c_double), ("rounds_timed", C.c_int64)]
+                ("eval_ms_sum", C.c_double), ("compact_ms_sum", C.c_double), ("rounds_timed", C.c_int64), ("cut_ms", C.c_double), ("cut_ms_sum", C.c_double)]
 
 
 class ktn_cut_view(C.Structure):

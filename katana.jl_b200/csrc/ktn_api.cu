@@ -50,7 +50,7 @@ extern "C" int ktn_create(const ktn_options* o, ktn_handle** out) {
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
     h->stream = h->own_stream;
     cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
-    for (int i = 0; i < ktn_handle::RING; ++i) for (int j = 0; j < 3; ++j) cudaEventCreate(&h->ring[i][j]);
+    for (int i = 0; i < ktn_handle::RING; ++i) for (int j = 0; j < 4; ++j) cudaEventCreate(&h->ring[i][j]);
     if (cudaMallocHost(&h->h_counts, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
     if (h->ticket.alloc(4 * KTN_TICKETS) != cudaSuccess || h->counts.alloc(8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return KTN_ERR_CUDA; }
     cudaMemset(h->ticket.p, 0, 4 * KTN_TICKETS);
@@ -71,7 +71,7 @@ extern "C" void ktn_destroy(ktn_handle* h) {
     ktn_comm_release(h);
     if (h->ev0) {
         cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
-        for (int i = 0; i < ktn_handle::RING; ++i) for (int j = 0; j < 3; ++j) cudaEventDestroy(h->ring[i][j]);
+        for (int i = 0; i < ktn_handle::RING; ++i) for (int j = 0; j < 4; ++j) cudaEventDestroy(h->ring[i][j]);
     }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -239,10 +239,12 @@ static void drain_ring(ktn_handle* h, bool all) {
     while (h->ring_tail != h->ring_head) {
         cudaEvent_t* e = h->ring[h->ring_tail % ktn_handle::RING];
         if (!all && cudaEventQuery(e[2]) != cudaSuccess) break;
-        float a = 0.f, b = 0.f;
-        if (cudaEventElapsedTime(&a, e[0], e[1]) == cudaSuccess && cudaEventElapsedTime(&b, e[1], e[2]) == cudaSuccess) {
-            h->eval_ms_sum += a; h->compact_ms_sum += b; h->rounds_timed++;
-            h->tm.kernel_ms = a + b; h->tm.eval_ms = a; h->tm.compact_ms = b;
+        float a = 0.f, b = 0.f, c = 0.f;      // K1 | K2 + K3 | K2 alone (KTN_FLAG_TIME_KERNELS: an event is recorded between K2 and K3, which costs the round a few microseconds)
+        const bool detail = (h->opt.flags & KTN_FLAG_TIME_KERNELS) != 0;
+        if (cudaEventElapsedTime(&a, e[0], e[1]) == cudaSuccess && cudaEventElapsedTime(&b, e[1], e[2]) == cudaSuccess && (!detail || cudaEventElapsedTime(&c, e[1], e[3]) == cudaSuccess)) {
+            if (!detail) c = b;
+            h->eval_ms_sum += a; h->compact_ms_sum += c; h->cut_ms_sum += b - c; h->rounds_timed++;
+            h->tm.kernel_ms = a + b; h->tm.eval_ms = a; h->tm.compact_ms = c; h->tm.cut_ms = b - c;
         }
         h->ring_tail++;
     }
@@ -268,7 +270,7 @@ static int enqueue_round(ktn_handle* h, const double* d_x, int mode, int do_roun
     ktn_comm_plan_blocks(h);
     int sms = h->num_sms;
     if (h->comm && h->px.on && h->px.reserve && sms > 2 * h->px.blocks) sms -= h->px.blocks;
-    int n = ktn_launch_round(p, make_plan(h), sms, h->max_smem, h->epoch, h->stream, ev[1], &e);
+    int n = ktn_launch_round(p, make_plan(h), sms, h->max_smem, h->epoch, h->stream, ev[1], (h->opt.flags & KTN_FLAG_TIME_KERNELS) ? ev[3] : nullptr, &e);
     h->tm.launches += n;
     if (e != cudaSuccess) return fail(h, KTN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     CK(h, cudaEventRecord(ev[2], h->stream));
@@ -438,7 +440,7 @@ extern "C" int ktn_timings_get(ktn_handle* h, ktn_timings* out) {
     if (!h || !out) return KTN_ERR_USAGE;
     cudaSetDevice(h->device);
     drain_ring(h, false);
-    h->tm.eval_ms_sum = h->eval_ms_sum; h->tm.compact_ms_sum = h->compact_ms_sum; h->tm.rounds_timed = h->rounds_timed;
+    h->tm.eval_ms_sum = h->eval_ms_sum; h->tm.compact_ms_sum = h->compact_ms_sum; h->tm.cut_ms_sum = h->cut_ms_sum; h->tm.rounds_timed = h->rounds_timed;
     *out = h->tm;
     return KTN_OK;
 }

@@ -59,11 +59,22 @@ template <> struct KtnFamily<KTN_FAM_LSE> {
     static KTN_HDM double adjoint(double aux) { return revmul(1.0, 1.0 / aux); }                  // KR_ONE; KR_MULRCP S
     static KTN_HDM double jac(double adj, double c, double e, double) { return 0.0 + revmul(revmul(adj, e), c); }
     static KTN_HDM double jac_plain(double adj, double c, double e, double) { return 0.0 + (adj * e) * c; }
-    // Jacobian entry of the term (c, d) at x: the exponential is evaluated again, with the forward pass's operations
-    static KTN_HDM double entry(double adj, double c, double d, double x, bool exact) {
-        const double e = ktn_exp(arg(c, d, x));
-        return exact ? jac(adj, c, e, x) : jac_plain(adj, c, e, x);
+    // the cut evaluates the exponentials again, with the forward pass's operations: eight at a time, branch-free (p1: d -> exp)
+    static KTN_HDM void pre8(const double (&p0)[8], double (&p1)[8], const double (&x)[8]) {
+        double a[8];
+        bool slow = false;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = arg(p0[k], p1[k], x[k]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) p1[k] = ktn_exp_fast(a[k]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) slow = slow || !ktn_exp_is_fast(a[k]);
+        if (slow) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (!ktn_exp_is_fast(a[k])) p1[k] = ktn_exp_slow(a[k]);
+        }
     }
+    static KTN_HDM double entry(double adj, double c, double e, double x, bool exact) { return exact ? jac(adj, c, e, x) : jac_plain(adj, c, e, x); }
     // streaming fallback (any nu)
     template <class R> static KTN_HDM double forward_stream(const R& r, double& aux) {
         double acc = 0.0;
@@ -92,6 +103,7 @@ template <> struct KtnFamily<KTN_FAM_QUAD> {
     static KTN_HDM double adjoint(double) { return 1.0; }                                         // KR_ONE
     static KTN_HDM double jac(double adj, double a, double b, double x) { return (0.0 + revmul(revmul(adj, a), 2.0 * x)) + revmul(adj, b); }
     static KTN_HDM double jac_plain(double adj, double a, double b, double x) { return (0.0 + (adj * a) * (2.0 * x)) + adj * b; }
+    static KTN_HDM void pre8(const double (&)[8], double (&)[8], const double (&)[8]) {}
     static KTN_HDM double entry(double adj, double a, double b, double x, bool exact) { return exact ? jac(adj, a, b, x) : jac_plain(adj, a, b, x); }
     template <class R> static KTN_HDM double forward_stream(const R& r, double& aux) {
         double acc = 0.0;
@@ -110,7 +122,7 @@ KTN_HDM double ktn_dmin(double a, double b) { return a < b ? a : (b != b ? a : b
 // ---- the cut of a selected row (the cut kernel; tests/emu) --------------------------------------------------------------
 // Row context R: pairs2(g, a0, a1, b0, b1) = the constants of unique variables 2g (a) and 2g + 1 (b); cols8(g, c[8]) = the
 // columns of unique variables 8g .. 8g + 7; xat(col).  `rw`: 4 bits per unique variable u = its Jacobian entry index (rank).
-// Sink S: put(q, J) / get(q) / set(q, J): coefficient of entry q;  put_t(q, t) / get_t(q): the product -x* J of entry q.
+// Sink S: put(q, J, col): coefficient and column of entry q, get(q) / set(q, J);  put_t(q, t) / get_t(q): the product -x* J of entry q.
 // The terms are walked in TERM order, eight at a time (their loads are in flight together: one 256-bit load per two terms'
 // constants, one per eight columns, then the eight x* gathers); coefficients and products are scattered to their entry index,
 // and the constant b = g; b += -x*_q J_q then accumulates in ENTRY order, as the reference does (src/algorithms.jl:8-16).
@@ -138,12 +150,13 @@ KTN_HDM bool ktn_family_cut_terms(const R& r, uint32_t nu, uint64_t rw, S& s, do
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) x[k] = r.xat(c[k]);          // columns past the row's end are padded with 0: a valid index
+            F::pre8(p0, p1, x);                                      // (padding: exp(0 * x + 0) = 1, never used)
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 if (u0 + k < nu) {
                     const double jv = F::entry(adj, p0[k], p1[k], x[k], exact);
                     const uint32_t q = (uint32_t)(rw >> (4 * (u0 + k))) & 15u;
-                    s.put(q, jv); s.put_t(q, (-x[k]) * jv);
+                    s.put(q, jv, c[k]); s.put_t(q, (-x[k]) * jv);
                     mx = ktn_dmax(mx, jv); mn = ktn_dmin(mn, jv); anynan = anynan || (jv != jv);
                 }
             }

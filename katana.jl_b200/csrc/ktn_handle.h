@@ -27,11 +27,11 @@ struct ktn_handle {
     int device = 0, num_sms = 0, max_smem = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
-    // per-round kernel timing: ring of (start, after K1, after K2) events, drained by ktn_timings_get
+    // per-round kernel timing: ring of (start, after K1, after K3, after K2) events, drained by ktn_timings_get
     static const int RING = 128;
-    cudaEvent_t ring[RING][3];
+    cudaEvent_t ring[RING][4];
     int ring_head = 0, ring_tail = 0;      // [tail, head) not yet drained
-    double eval_ms_sum = 0, compact_ms_sum = 0; int64_t rounds_timed = 0;
+    double eval_ms_sum = 0, compact_ms_sum = 0, cut_ms_sum = 0; int64_t rounds_timed = 0;
     KtnProblem prob;
     bool loading = false, loaded = false, round_pending = false, have_round = false;
     DevBuf chunks, shapes, prog, blob, chunk_rows, chunk_lb, chunk_ub, jac_ptr, jac_col, row_lb, row_ub, row_slot, rec, worklist, errpos, blk_off, chunk_jp, dump;

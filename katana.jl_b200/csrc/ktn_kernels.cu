@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(KTN_CBLOCK, KTN_CBPS) ktn_compact_kernel(const
     __shared__ uint32_t s_off[KTN_CROWS + 1];        // exclusive nnz offsets of the block's selected rows (compact list)
     __shared__ uint32_t s_src[KTN_CROWS];            // first entry of each selected row in the static Jacobian CSR (jac_ptr; the library caps nnz(J) at 2^32 - 1)
     __shared__ uint16_t s_rowl[KTN_CROWS];           // block-local row index of each selected row | 0x8000 non-finite (K1) | 0x4000 deferred
-    const uint32_t bid = blockIdx.x;
+    const uint32_t bid = nblocks - 1u - blockIdx.x;      // the rows K1 read last first: what the L2 still holds of their chunk blobs need not come from DRAM
     const int64_t row0 = (int64_t)bid * KTN_CROWS, i0 = row0 + (int64_t)threadIdx.x * KTN_CRPT;
     // every independent load of the block is requested up front: the row flags, then K1's per-block counts
     uint32_t sv[KTN_CRPT];
@@ -652,9 +652,9 @@ __global__ void __launch_bounds__(KTN_CBLOCK, KTN_CBPS) ktn_compact_kernel(const
         const uint32_t rl = s_rowl[k];
         const int64_t i = row0 + (rl & 0x3fffu);
         const int64_t cidx = (int64_t)cbase + k, o = (int64_t)(nbase + s_off[k]);
-        s_src[k] = (uint32_t)p.jac_ptr[i];
         out_row[cidx] = i + p.row_offset; out_ptr[cidx] = o;
         if (!(rl & 0x4000u)) {
+            s_src[k] = (uint32_t)p.jac_ptr[i];
             const double g = p.g_row[i], bcst = p.b_row[i], lb = p.row_lb[i], ub = p.row_ub[i];
             out_lo[cidx] = lb - bcst; out_hi[cidx] = ub - bcst;     // src/model.jl:74-75
             out_g[cidx] = g; out_b[cidx] = bcst;
@@ -674,10 +674,11 @@ __global__ void __launch_bounds__(KTN_CBLOCK, KTN_CBPS) ktn_compact_kernel(const
         }
     }
     __syncthreads();
-    // expand: one thread per output entry, coalesced writes: the columns of every entry (the static Jacobian structure IS the
-    // entry order) and the coefficients K1 staged.  Every warp owns a contiguous range of the block's entries: one binary search
-    // (shared memory) finds the row of the range's first entry, after that each lane walks forward through the row offsets
-    // (a few steps per 32 entries).  Four steps are unrolled: all loads are in flight before the first store.
+    // expand the rows whose cut K1 built: one thread per output entry, coalesced writes of columns and coefficients from the
+    // static / staging CSR.  Every warp owns a contiguous range of the block's entries: one binary search (shared memory) finds
+    // the row of the range's first entry, after that each lane walks forward through the row offsets (a few steps per 32
+    // entries).  Four steps are unrolled: all loads are in flight before the first store.  (Family rows: the cut kernel.)
+    if (!any_copy) return;
     const uint32_t nent = (uint32_t)tb, lane = threadIdx.x & 31u;
     const uint32_t per = ((nent + KTN_CBLOCK - 1) / KTN_CBLOCK) * 32u;         // entries per warp, a multiple of 32
     const uint32_t wbeg = (threadIdx.x >> 5) * per, wend = wbeg + per < nent ? wbeg + per : nent;
@@ -685,17 +686,17 @@ __global__ void __launch_bounds__(KTN_CBLOCK, KTN_CBPS) ktn_compact_kernel(const
         uint32_t lo = 0, hi = ta;   // largest k with s_off[k] <= wbeg
         while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= wbeg) lo = mid; else hi = mid; }
         for (uint32_t e0 = wbeg + lane; e0 - lane < wend; e0 += 128u) {
-            uint32_t src[4]; int32_t cv[4]; double vv[4]; bool built[4];
+            uint32_t src[4]; int32_t cv[4]; double vv[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t e = e0 + 32u * (uint32_t)k;
-                src[k] = 0xffffffffu; built[k] = false;
-                if (e < wend) { while (s_off[lo + 1] <= e) ++lo; src[k] = s_src[lo] + (e - s_off[lo]); built[k] = !(s_rowl[lo] & 0x4000u); }
+                src[k] = 0xffffffffu;
+                if (e < wend) { while (s_off[lo + 1] <= e) ++lo; if (!(s_rowl[lo] & 0x4000u)) src[k] = s_src[lo] + (e - s_off[lo]); }
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { cv[k] = src[k] != 0xffffffffu ? __ldg(p.jac_col + src[k]) : 0; vv[k] = (any_copy && built[k]) ? p.stage_val[src[k]] : 0.0; }
+            for (int k = 0; k < 4; ++k) { cv[k] = src[k] != 0xffffffffu ? __ldg(p.jac_col + src[k]) : 0; vv[k] = src[k] != 0xffffffffu ? p.stage_val[src[k]] : 0.0; }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) if (src[k] != 0xffffffffu) { const unsigned long long e = nbase + e0 + 32u * (uint32_t)k; out_col[e] = cv[k]; if (built[k]) out_val[e] = vv[k]; }
+            for (int k = 0; k < 4; ++k) if (src[k] != 0xffffffffu) { const unsigned long long e = nbase + e0 + 32u * (uint32_t)k; out_col[e] = cv[k]; out_val[e] = vv[k]; }
         }
     }
 }
@@ -708,25 +709,31 @@ __global__ void __launch_bounds__(KTN_CBLOCK, KTN_CBPS) ktn_compact_kernel(const
 // The LAST block to finish settles the first non-finite row (src/model.jl:69-73, :278), writes totals and blob header and
 // re-arms the per-round state.
 // ---------------------------------------------------------------------------------------------
+#ifndef KTN_XBLOCK
 #define KTN_XBLOCK 128
+#endif
+#ifndef KTN_XBPS
+#define KTN_XBPS 4
+#endif
 struct CutRow {     // row context of ktn_family_cut_terms: the row's groups in the chunk blob (ktn_program.h)
     const unsigned char* blob; const double* X; uint32_t nu, lane;
     __device__ __forceinline__ void pairs2(uint32_t g, double& a0, double& a1, double& b0, double& b1) const { ldg256(blob + g * 1024u + lane * 32u, a0, a1, b0, b1); }
     __device__ __forceinline__ void cols8(uint32_t g, int32_t (&c)[8]) const { ldg256(blob + KTN_FAM_COL_OFF(nu) + g * 1024u + lane * 32u, c); }
     __device__ __forceinline__ double xat(int32_t c) const { return __ldg(X + c); }
 };
-struct CutSink {    // coefficients: the row's slice of the block's staging (or of the round's CSR); products: a column of the block's scratch
-    double* val; double* t;
-    __device__ __forceinline__ void put(uint32_t q, double v) { val[q] = v; }
+struct CutSink {    // coefficients and columns: the row's slice of the block's staging (or of the round's CSR); products: a column of the block's scratch
+    double* val; int32_t* col; double* t;
+    __device__ __forceinline__ void put(uint32_t q, double v, int32_t c) { val[q] = v; col[q] = c; }
     __device__ __forceinline__ double get(uint32_t q) const { return val[q]; }
     __device__ __forceinline__ void set(uint32_t q, double v) { val[q] = v; }
     __device__ __forceinline__ void put_t(uint32_t q, double v) { t[q * KTN_XBLOCK] = v; }
     __device__ __forceinline__ double get_t(uint32_t q) const { return t[q * KTN_XBLOCK]; }
 };
 
-__global__ void __launch_bounds__(KTN_XBLOCK, 4) ktn_cut_kernel(const KtnRoundParams p, uint32_t epoch) {
+__global__ void __launch_bounds__(KTN_XBLOCK, KTN_XBPS) ktn_cut_kernel(const KtnRoundParams p, uint32_t epoch) {
     __shared__ double s_val[KTN_XBLOCK * KTN_FAM_REGS];      // coefficients of the block's cuts, in CSR order
     __shared__ double s_t[KTN_FAM_REGS * KTN_XBLOCK];        // products -x* J: [entry][thread]
+    __shared__ int32_t s_col[KTN_XBLOCK * KTN_FAM_REGS];     // columns of the block's cuts, in CSR order
     __shared__ unsigned long long s_e0, s_e1; __shared__ uint32_t s_last;
     const unsigned long long ca = __ldcg(&p.counts[4]), na = __ldcg(&p.counts[5]);
     const KtnPackLayout L = ktn_pack_layout(ca, na);
@@ -734,6 +741,7 @@ __global__ void __launch_bounds__(KTN_XBLOCK, 4) ktn_cut_kernel(const KtnRoundPa
     double* const out_lo = reinterpret_cast<double*>(p.out_blob + L.lo); double* const out_hi = reinterpret_cast<double*>(p.out_blob + L.hi);
     double* const out_g = reinterpret_cast<double*>(p.out_blob + L.g); double* const out_viol = reinterpret_cast<double*>(p.out_blob + L.viol);
     double* const out_b = reinterpret_cast<double*>(p.out_blob + L.b); double* const out_val = reinterpret_cast<double*>(p.out_blob + L.val);
+    int32_t* const out_col = reinterpret_cast<int32_t*>(p.out_blob + L.col);
     for (unsigned long long c0 = (unsigned long long)blockIdx.x * KTN_XBLOCK; c0 < ca; c0 += (unsigned long long)gridDim.x * KTN_XBLOCK) {
         const unsigned long long cidx = c0 + threadIdx.x;
         const bool active = cidx < ca;
@@ -751,7 +759,7 @@ __global__ void __launch_bounds__(KTN_XBLOCK, 4) ktn_cut_kernel(const KtnRoundPa
             const unsigned char* blob = p.blob + p.cls_blob_off[fam][nu] + (size_t)(c - p.cls_begin[fam][nu]) * KTN_FAM_BLOB_BYTES(nu);
             const uint64_t rw = __ldg(reinterpret_cast<const unsigned long long*>(blob + KTN_FAM_ORD_OFF(nu)) + ln);
             const CutRow r{blob, p.x, nu, ln};
-            CutSink s{staged ? s_val + ((unsigned long long)o - e0) : out_val + o, s_t + threadIdx.x};
+            CutSink s{staged ? s_val + ((unsigned long long)o - e0) : out_val + o, staged ? s_col + ((unsigned long long)o - e0) : out_col + o, s_t + threadIdx.x};
             double bcst; bool bad;
             if (fam == KTN_FAM_LSE) bad = ktn_family_cut_terms<KTN_FAM_LSE>(r, nu, rw, s, g, aux, p.do_round != 0, p.rng, bcst);
             else bad = ktn_family_cut_terms<KTN_FAM_QUAD>(r, nu, rw, s, g, aux, p.do_round != 0, p.rng, bcst);
@@ -762,7 +770,7 @@ __global__ void __launch_bounds__(KTN_XBLOCK, 4) ktn_cut_kernel(const KtnRoundPa
             if (bad) atomicMin(&p.counts[2 + (epoch & 1u)], cidx);      // first non-finite cut of the round
         }
         __syncthreads();
-        if (staged) for (unsigned long long e = e0 + threadIdx.x; e < e1; e += KTN_XBLOCK) out_val[e] = s_val[e - e0];
+        if (staged) for (unsigned long long e = e0 + threadIdx.x; e < e1; e += KTN_XBLOCK) { out_val[e] = s_val[e - e0]; out_col[e] = s_col[e - e0]; }
         __syncthreads();
     }
     // the last block to finish settles the round
@@ -995,7 +1003,7 @@ static int launch_eval_part(const KtnRoundParams& p0, const KtnLaunchPlan& plan,
 }
 
 int ktn_launch_round(const KtnRoundParams& p, const KtnLaunchPlan& plan, int num_sms, int max_smem_optin,
-                     uint32_t epoch, cudaStream_t stream, cudaEvent_t after_eval, cudaError_t* err) {
+                     uint32_t epoch, cudaStream_t stream, cudaEvent_t after_eval, cudaEvent_t after_compact, cudaError_t* err) {
     int launches = launch_eval_part<false>(p, plan, num_sms, max_smem_optin, stream, err);
     if (*err != cudaSuccess) return launches;
     if (after_eval) cudaEventRecord(after_eval, stream);
@@ -1012,8 +1020,9 @@ int ktn_launch_round(const KtnRoundParams& p, const KtnLaunchPlan& plan, int num
         const int scanned = nblocks > 1024u ? 1 : 0;
         if (scanned) { ktn_blkscan_kernel<<<1, 1024, 0, stream>>>(p, nblocks, epoch); ++launches; }
         ktn_compact_kernel<<<nblocks, KTN_CBLOCK, 0, stream>>>(p, nblocks, epoch, scanned);
+        if (after_compact) cudaEventRecord(after_compact, stream);
         uint32_t xblocks = (uint32_t)((p.num_rows + KTN_XBLOCK - 1) / KTN_XBLOCK);
-        if (xblocks > (uint32_t)num_sms * 4u) xblocks = (uint32_t)num_sms * 4u;      // resident blocks: every block loops over its share of the cuts
+        if (xblocks > (uint32_t)num_sms * KTN_XBPS) xblocks = (uint32_t)num_sms * KTN_XBPS;      // resident blocks: every block loops over its share of the cuts
         ktn_cut_kernel<<<xblocks, KTN_XBLOCK, 0, stream>>>(p, epoch);
         launches += 2;
     }

@@ -79,7 +79,7 @@ enum { KTN_TICKET_GENERIC = 0, KTN_TICKET_LSE = 8, KTN_TICKET_QUAD = 32, KTN_TIC
 
 // Launches the kernels of one round on `stream`; returns the number of kernels launched.
 int ktn_launch_round(const KtnRoundParams& p, const KtnLaunchPlan& plan, int num_sms,
-                     int max_smem_optin, uint32_t epoch, cudaStream_t stream, cudaEvent_t after_eval, cudaError_t* err);
+                     int max_smem_optin, uint32_t epoch, cudaStream_t stream, cudaEvent_t after_eval, cudaEvent_t after_compact, cudaError_t* err);
 void ktn_plan_occupancy(uint32_t table_bytes, uint32_t warp_bytes, int max_smem_optin, int* warps_per_block, int* blocks_per_sm);
 // forward evaluation only (ktn_eval_g): writes g_row for every row
 int ktn_launch_eval(const KtnRoundParams& p, const KtnLaunchPlan& plan, int num_sms,

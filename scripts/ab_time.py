@@ -20,7 +20,7 @@ for path in sys.argv[1:]:
         if (kind, nv, nr) not in data:
             data[(kind, nv, nr)] = (P.synth_rows(kind, 20260001 + kind, nv, 0, nr), P.synth_point(kind, 20260001 + kind, nv))
         w, x0 = data[(kind, nv, nr)]
-        h = P.create(); h.load(nv, w)
+        h = P.create(flags=2 if os.environ.get('AB_DETAIL') else 0); h.load(nv, w)
         g = h.eval_g(x0)
         ev = []
         for _ in range(6):
@@ -28,14 +28,14 @@ for path in sys.argv[1:]:
         h.set_bounds(w.lb, np.full(nr, np.quantile(g, 1 - v)))
         b = h.separate(x0)        # results must not depend on the variant: compare the digests across the lines
         digest = hashlib.sha1(g.tobytes() + b.row_id.tobytes() + b.col.tobytes() + b.val.tobytes() + b.lo.tobytes() + b.hi.tobytes()).hexdigest()[:10]
-        k1, k2 = [], []
+        k1, k2, k3 = [], [], []
         dbg = getattr(P.dll, "ktn_debug_cycles", None) if hasattr(P.dll, "ktn_debug_cycles") else None
         import ctypes
         if dbg: dbg(None, 1)
         for it in range(12):
             st, nc, nz, er = h.separate(x0, fetch=False)
-            tm = h.timings(); k1.append(tm["eval_ms"]); k2.append(tm["compact_ms"])
-        out.append(f"{name} v={v}: K1 {1e3 * np.median(k1[2:]):.1f} us (min {1e3 * min(k1):.1f}) K2 {1e3 * np.median(k2[2:]):.1f} us cuts {nc} eval-only {1e3 * np.median(ev[2:]):.1f} us sha {digest}")
+            tm = h.timings(); k1.append(tm["eval_ms"]); k2.append(tm["compact_ms"]); k3.append(tm["cut_ms"])
+        out.append(f"{name} v={v}: K1 {1e3 * np.median(k1[2:]):.1f} us (min {1e3 * min(k1):.1f}) K2 {1e3 * np.median(k2[2:]):.1f} us K3 {1e3 * np.median(k3[2:]):.1f} us cuts {nc} eval-only {1e3 * np.median(ev[2:]):.1f} us sha {digest}")
         if dbg:
             arr = (ctypes.c_ulonglong * 16)(); dbg(arr, 1); a = [x / 12.0 for x in arr]
             nch = max(a[4], 1)

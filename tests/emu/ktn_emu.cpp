@@ -63,9 +63,9 @@ struct EmuFamSink {
     void put_j(uint32_t q, double v) { out[q] = v; } double get_j(uint32_t q) const { return out[q]; }
     double xsorted(uint32_t q) const { return X[scol[q]]; }
 };
-struct EmuCutSink {     // the cut kernel's sink: coefficients of the row (entry order) and the products -x* J
-    double* val; double t[KTN_FAM_REGS];
-    void put(uint32_t q, double v) { val[q] = v; } double get(uint32_t q) const { return val[q]; } void set(uint32_t q, double v) { val[q] = v; }
+struct EmuCutSink {     // the cut kernel's sink: coefficients and columns of the row (entry order) and the products -x* J
+    double* val; const int32_t* scol; bool* colmismatch; double t[KTN_FAM_REGS];
+    void put(uint32_t q, double v, int32_t c) { val[q] = v; if (scol[q] != c) *colmismatch = true; } double get(uint32_t q) const { return val[q]; } void set(uint32_t q, double v) { val[q] = v; }
     void put_t(uint32_t q, double v) { t[q] = v; } double get_t(uint32_t q) const { return t[q]; }
 };
 static EmuFamRow emu_row(const KtnProblem& P, const KtnChunkDesc& cd, uint32_t lane, const double* x) {
@@ -121,9 +121,11 @@ static bool run_family_cut(ktn_handle* h, int64_t row, double& b) {
     const int64_t base = P.jac_ptr[row];
     const uint64_t rw = r.rankword();
     for (uint32_t u = 0; u < r.nu; ++u) if (P.jac_col[base + ((rw >> (4 * u)) & 15u)] != r.gcol(u)) { fprintf(stderr, "emu: rank word does not reproduce the Jacobian structure\n"); abort(); }
-    EmuCutSink s{h->stage_val.data() + base, {0}};
+    bool mismatch = false;
+    EmuCutSink s{h->stage_val.data() + base, P.jac_col.data() + base, &mismatch, {0}};
     const bool bad = fam == KTN_FAM_LSE ? ktn_family_cut_terms<KTN_FAM_LSE>(r, r.nu, rw, s, h->g_row[row], h->aux_row[row], h->do_round != 0, h->opt.cut_coef_rng, b)
                                         : ktn_family_cut_terms<KTN_FAM_QUAD>(r, r.nu, rw, s, h->g_row[row], h->aux_row[row], h->do_round != 0, h->opt.cut_coef_rng, b);
+    if (mismatch) { fprintf(stderr, "emu: the cut's columns differ from the Jacobian structure\n"); abort(); }
     return bad;
 }
 
