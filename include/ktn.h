@@ -83,7 +83,17 @@ typedef struct ktn_options {
     int64_t topk;          /* 0 = all violated rows */
     int32_t flags;         /* KTN_FLAG_* */
     int32_t reserved;
+    /* Single-process sharded operation: ngpus > 1 makes ONE handle drive `ngpus` devices.  The rows are
+     * split into contiguous ranges, one per device (devices[s]; a negative entry means device s); every call of this header then
+     * acts on the whole problem: ktn_separate runs the round on all devices at once, ktn_fetch_cuts / ktn_fetch_cuts_view deliver
+     * ONE batch in ascending row order (rank-major concatenation; every device downloads its share over its own PCIe link), with
+     * the reference's error semantics (the batch ends at the first non-finite row, src/model.jl:69-73, :278).  The same device
+     * may be listed more than once (tests on one GPU).  Not available on such a handle: topk, ktn_set_stream and the
+     * device-resident / ktn_comm_* entry points (those serve the one-process-per-GPU mode). */
+    int32_t ngpus;         /* 0 or 1: one device (`device`) */
+    int32_t devices[16];
 } ktn_options;
+#define KTN_MAX_GPUS 16
 
 /* ktn_options.flags */
 enum {

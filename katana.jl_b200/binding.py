@@ -18,8 +18,8 @@ CUDA_LIB_PATH = os.environ.get("KTN_LIB") or os.path.join(_HERE, "libktn.so")   
 OP_CONST, OP_VAR, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_NEG, OP_EXP, OP_LOG, OP_SQRT, OP_ABS = range(12)
 ROW_NL, ROW_DENSE = 1, 2
 KTN_OK, KTN_NUMERIC_NONFINITE = 0, 1
-FLAG_LEAN_VIEW = 1
-FLAG_TIME_KERNELS = 2          # ktn_options.flags: cut views carry only what the LP needs
+FLAG_LEAN_VIEW = 1          # ktn_options.flags: cut views carry only what the LP needs
+FLAG_TIME_KERNELS = 2       # compaction and cut kernel timed separately (one more event per round)
 SYNTH_QCQP, SYNTH_LSE, SYNTH_SOC = 0, 1, 2
 
 
@@ -29,7 +29,8 @@ class KtnError(RuntimeError):
 
 class ktn_options(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("f_tol", C.c_double),
-                ("cut_coef_rng", C.c_double), ("topk", C.c_int64), ("flags", C.c_int32), ("reserved", C.c_int32)]
+                ("cut_coef_rng", C.c_double), ("topk", C.c_int64), ("flags", C.c_int32), ("reserved", C.c_int32),
+                ("ngpus", C.c_int32), ("devices", C.c_int32 * 16)]
 
 
 class ktn_timings(C.Structure):
@@ -140,7 +141,7 @@ class KtnLibrary(_SynthMixin):
         if not os.path.exists(path):
             raise KtnError(f"shared library not found: {path} (run `python -c 'import __graft_entry__ as g; g.build()'`)")
         self.path = path
-        self.dll = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        self.dll = C.CDLL(path)      # RTLD_LOCAL: the CUDA library, the oracle and the emulator export the same symbols
         for name, (res, args) in _SIGS.items():
             fn = getattr(self.dll, name)
             fn.restype, fn.argtypes = res, args
@@ -149,8 +150,9 @@ class KtnLibrary(_SynthMixin):
             self._bind_synth()
         self.backend = self.dll.ktn_backend().decode()
 
-    def create(self, f_tol=1e-6, cut_coef_rng=1e9, topk=0, device=-1, flags=0):
-        return Handle(self, f_tol, cut_coef_rng, topk, device, flags)
+    def create(self, f_tol=1e-6, cut_coef_rng=1e9, topk=0, device=-1, flags=0, ngpus=0, devices=None):
+        """ngpus > 1: ONE handle that shards the rows over `ngpus` devices (ktn_options.ngpus / devices, include/ktn.h)."""
+        return Handle(self, f_tol, cut_coef_rng, topk, device, flags, ngpus, devices)
 
 
 @dataclass
@@ -194,9 +196,12 @@ class CutBatch:
 
 
 class Handle:
-    def __init__(self, lib, f_tol, cut_coef_rng, topk, device, flags=0):
+    def __init__(self, lib, f_tol, cut_coef_rng, topk, device, flags=0, ngpus=0, devices=None):
         self.lib, self.dll = lib, lib.dll
-        o = ktn_options(C.sizeof(ktn_options), device, f_tol, cut_coef_rng, topk, flags, 0)
+        dev = (C.c_int32 * 16)(*([-1] * 16))
+        for s, d in enumerate(devices or []):
+            dev[s] = d
+        o = ktn_options(C.sizeof(ktn_options), device, f_tol, cut_coef_rng, topk, flags, 0, ngpus, dev)
         p = _P()
         rc = self.dll.ktn_create(C.byref(o), C.byref(p))
         if rc != 0 or not p:

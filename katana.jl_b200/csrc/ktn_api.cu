@@ -15,6 +15,17 @@ int ktn_comm_launch_pending(ktn_handle* h);
 int ktn_comm_release_blob(ktn_handle* h, int idx);
 void ktn_comm_plan_blocks(ktn_handle* h);
 
+// single-process sharded operation (ktn_options.ngpus > 1): defined at the end of this file
+static int group_create(ktn_handle* front, ktn_handle** out);
+static void group_destroy(ktn_handle* f);
+static int group_fail(ktn_handle* f, ktn_handle* s, int rc);
+static int group_load_begin(ktn_handle* f, int64_t num_var, int64_t num_constr);
+static int group_add_rows(ktn_handle* f, int64_t first_row, int64_t nrows, const int64_t* eptr, const int32_t* op, const int32_t* arg, const double* val,
+                          const double* lb, const double* ub, const uint8_t* flags);
+static int group_load_end(ktn_handle* f);
+static int group_round(ktn_handle* f, const double* x, const int64_t* rows, int64_t nrows, int do_round, int64_t* n_cuts, int64_t* nnz, int64_t* err_row);
+static int group_fetch(ktn_handle* f, ktn_cut_view* view, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val, double* lo, double* hi, double* g, double* viol, double* bconst);
+
 extern "C" const char* ktn_backend(void) { return "cuda"; }
 extern "C" const char* ktn_last_error(ktn_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
@@ -37,6 +48,7 @@ extern "C" int ktn_create(const ktn_options* o, ktn_handle** out) {
     memset(&h->opt, 0, sizeof h->opt); memset(&h->tm, 0, sizeof h->tm);
     h->opt.f_tol = 1e-6; h->opt.cut_coef_rng = 1e9; h->opt.device = -1;
     if (o) memcpy(&h->opt, o, (size_t)o->struct_size < sizeof(ktn_options) ? (size_t)o->struct_size : sizeof(ktn_options));
+    if (h->opt.ngpus > 1) return group_create(h, out);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {   // no CPU fallback: the product path fails loudly without a GPU
@@ -62,6 +74,7 @@ extern "C" int ktn_create(const ktn_options* o, ktn_handle** out) {
 
 extern "C" void ktn_destroy(ktn_handle* h) {
     if (!h) return;
+    if (!h->shards.empty()) { group_destroy(h); return; }
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     free_problem(h);
@@ -87,6 +100,12 @@ static int ensure_topk(ktn_handle* h) {
 
 extern "C" int ktn_set_params(ktn_handle* h, double f_tol, double rng, int64_t topk) {
     if (!h || topk < 0) return fail(h, KTN_ERR_USAGE, "bad parameters");
+    if (!h->shards.empty()) {
+        if (topk > 0) return fail(h, KTN_ERR_UNSUPPORTED, "topk is not available on a multi-device handle");
+        for (ktn_handle* s : h->shards) { int rc = ktn_set_params(s, f_tol, rng, 0); if (rc) return group_fail(h, s, rc); }
+        h->opt.f_tol = f_tol; h->opt.cut_coef_rng = rng;
+        return KTN_OK;
+    }
     h->opt.f_tol = f_tol; h->opt.cut_coef_rng = rng; h->opt.topk = topk;
     cudaSetDevice(h->device);
     return ensure_topk(h);
@@ -94,6 +113,7 @@ extern "C" int ktn_set_params(ktn_handle* h, double f_tol, double rng, int64_t t
 
 extern "C" int ktn_load_begin(ktn_handle* h, int64_t num_var, int64_t num_constr) {
     if (!h || num_var < 0 || num_constr < 0 || num_constr > 0x7fffff00ll || num_var > 0x7fffff00ll) return fail(h, KTN_ERR_USAGE, "bad problem sizes");
+    if (!h->shards.empty()) return group_load_begin(h, num_var, num_constr);
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     free_problem(h);
@@ -104,6 +124,7 @@ extern "C" int ktn_load_begin(ktn_handle* h, int64_t num_var, int64_t num_constr
 
 extern "C" int ktn_add_rows(ktn_handle* h, int64_t first_row, int64_t nrows, const int64_t* eptr, const int32_t* op,
                             const int32_t* arg, const double* val, const double* lb, const double* ub, const uint8_t* flags) {
+    if (h && !h->shards.empty()) return group_add_rows(h, first_row, nrows, eptr, op, arg, val, lb, ub, flags);
     if (!h || !h->loading) return fail(h, KTN_ERR_USAGE, "ktn_add_rows before ktn_load_begin");
     int rc = h->prob.add_rows(first_row, nrows, eptr, op, arg, val, lb, ub, flags);
     if (rc != KTN_OK) h->err = h->prob.err;
@@ -118,6 +139,7 @@ template <class T> static cudaError_t upload(DevBuf& b, const std::vector<T>& v,
 }
 
 extern "C" int ktn_load_end(ktn_handle* h) {
+    if (h && !h->shards.empty()) return group_load_end(h);
     if (!h || !h->loading) return fail(h, KTN_ERR_USAGE, "ktn_load_end before ktn_load_begin");
     cudaSetDevice(h->device);
     KtnProblem& P = h->prob;
@@ -177,6 +199,10 @@ extern "C" int ktn_load_end(ktn_handle* h) {
 }
 
 extern "C" int ktn_set_bounds(ktn_handle* h, const double* lb, const double* ub) {
+    if (h && !h->shards.empty()) {
+        for (size_t s = 0; s < h->shards.size(); ++s) { int rc = ktn_set_bounds(h->shards[s], lb + h->shard_begin[s], ub + h->shard_begin[s]); if (rc) return group_fail(h, h->shards[s], rc); }
+        return KTN_OK;
+    }
     if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
     cudaSetDevice(h->device);
     KtnProblem& P = h->prob;
@@ -190,9 +216,27 @@ extern "C" int ktn_set_bounds(ktn_handle* h, const double* lb, const double* ub)
     return KTN_OK;
 }
 
-extern "C" int64_t ktn_num_rows(ktn_handle* h) { return h ? h->prob.rows_loaded : 0; }
-extern "C" int64_t ktn_jac_nnz(ktn_handle* h) { return (h && !h->prob.jac_ptr.empty()) ? h->prob.jac_ptr.back() : 0; }
+extern "C" int64_t ktn_num_rows(ktn_handle* h) {
+    if (h && !h->shards.empty()) { int64_t n = 0; for (ktn_handle* s : h->shards) n += s->prob.rows_loaded; return n; }
+    return h ? h->prob.rows_loaded : 0;
+}
+extern "C" int64_t ktn_jac_nnz(ktn_handle* h) {
+    if (h && !h->shards.empty()) { int64_t n = 0; for (ktn_handle* s : h->shards) n += ktn_jac_nnz(s); return n; }
+    return (h && !h->prob.jac_ptr.empty()) ? h->prob.jac_ptr.back() : 0;
+}
 extern "C" int ktn_jac_structure(ktn_handle* h, int64_t* row_ptr, int32_t* cols) {
+    if (h && !h->shards.empty()) {      // concatenation of the shards' structures
+        int64_t rows = 0, nz = 0;
+        for (ktn_handle* s : h->shards) {
+            const KtnProblem& P = s->prob;
+            if (P.jac_ptr.empty()) return fail(h, KTN_ERR_USAGE, "no problem");
+            if (row_ptr) for (int64_t i = 0; i < P.num_constr; ++i) row_ptr[rows + i] = nz + P.jac_ptr[i];
+            if (cols && !P.jac_col.empty()) memcpy(cols + nz, P.jac_col.data(), 4 * P.jac_col.size());
+            rows += P.num_constr; nz += P.jac_ptr[P.num_constr];
+        }
+        if (row_ptr) row_ptr[rows] = nz;
+        return KTN_OK;
+    }
     if (!h || h->prob.jac_ptr.empty()) return fail(h, KTN_ERR_USAGE, "no problem");
     if (row_ptr) memcpy(row_ptr, h->prob.jac_ptr.data(), 8 * h->prob.jac_ptr.size());
     if (cols) memcpy(cols, h->prob.jac_col.data(), 4 * h->prob.jac_col.size());
@@ -303,6 +347,7 @@ static int upload_x(ktn_handle* h, const double* x) {
 }
 
 extern "C" int ktn_separate(ktn_handle* h, const double* xstar, int64_t* n_cuts, int64_t* nnz, int64_t* err_row) {
+    if (h && !h->shards.empty()) return group_round(h, xstar, nullptr, 0, 1, n_cuts, nnz, err_row);
     if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
     cudaSetDevice(h->device);
     int rc = upload_x(h, xstar); if (rc) return rc;
@@ -314,6 +359,11 @@ extern "C" int ktn_separate(ktn_handle* h, const double* xstar, int64_t* n_cuts,
 
 extern "C" int ktn_gencut_rows(ktn_handle* h, const double* x, const int64_t* rows, int64_t nrows, int do_round,
                                int64_t* n_cuts, int64_t* nnz, int64_t* err_row) {
+    if (h && !h->shards.empty()) {
+        if (nrows < 0 || (nrows > 0 && !rows)) return fail(h, KTN_ERR_USAGE, "bad row list");
+        for (int64_t j = 0; j < nrows; ++j) if (rows[j] < 0 || rows[j] >= h->g_num_constr || (j && rows[j] <= rows[j - 1])) return fail(h, KTN_ERR_USAGE, "rows must be ascending and in range");
+        return group_round(h, x, rows ? rows : (const int64_t*)&nrows, nrows, do_round ? 1 : 0, n_cuts, nnz, err_row);
+    }
     if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
     cudaSetDevice(h->device);
     const int64_t m = h->prob.num_constr;
@@ -331,6 +381,7 @@ extern "C" int ktn_gencut_rows(ktn_handle* h, const double* x, const int64_t* ro
 
 extern "C" int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val,
                               double* lo, double* hi, double* g, double* viol, double* bconst) {
+    if (h && !h->shards.empty()) return group_fetch(h, nullptr, row_id, row_ptr, col, val, lo, hi, g, viol, bconst);
     if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
     if (h->round_pending) { int rc = finish_round(h, nullptr, nullptr, nullptr); if (rc < 0) return rc; }
     cudaSetDevice(h->device);
@@ -358,6 +409,7 @@ extern "C" int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, 
 // after the next one): the device blob already has the view's layout, so it comes down in one copy (lean view: two, around
 // the g | viol | b sections); one synchronisation, no host-side copy.
 extern "C" int ktn_fetch_cuts_view(ktn_handle* h, ktn_cut_view* out) {
+    if (h && out && !h->shards.empty()) return group_fetch(h, out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     if (!h || !h->loaded || !out) return fail(h, KTN_ERR_USAGE, "no problem loaded");
     if (h->round_pending) { int rc = finish_round(h, nullptr, nullptr, nullptr); if (rc < 0) return rc; }
     cudaSetDevice(h->device);
@@ -413,6 +465,10 @@ extern "C" int ktn_fetch_cuts_view(ktn_handle* h, ktn_cut_view* out) {
 }
 
 extern "C" int ktn_get_g(ktn_handle* h, double* g_out) {
+    if (h && !h->shards.empty()) {
+        for (size_t s = 0; s < h->shards.size(); ++s) { int rc = ktn_get_g(h->shards[s], g_out + h->shard_begin[s]); if (rc) return group_fail(h, h->shards[s], rc); }
+        return KTN_OK;
+    }
     if (!h || !h->have_round) return fail(h, KTN_ERR_USAGE, "no round has run");
     cudaSetDevice(h->device);
     CK(h, cudaMemcpyAsync(g_out, h->g_row.p, 8 * (size_t)h->prob.num_constr, cudaMemcpyDeviceToHost, h->stream));
@@ -421,6 +477,10 @@ extern "C" int ktn_get_g(ktn_handle* h, double* g_out) {
 }
 
 extern "C" int ktn_eval_g(ktn_handle* h, const double* x, double* g_out) {
+    if (h && !h->shards.empty()) {
+        for (size_t s = 0; s < h->shards.size(); ++s) { int rc = ktn_eval_g(h->shards[s], x, g_out + h->shard_begin[s]); if (rc) return group_fail(h, h->shards[s], rc); }
+        return KTN_OK;
+    }
     if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
     cudaSetDevice(h->device);
     int rc = upload_x(h, x); if (rc) return rc;
@@ -438,6 +498,19 @@ extern "C" int ktn_eval_g(ktn_handle* h, const double* x, double* g_out) {
 
 extern "C" int ktn_timings_get(ktn_handle* h, ktn_timings* out) {
     if (!h || !out) return KTN_ERR_USAGE;
+    if (!h->shards.empty()) {      // the devices work side by side: times are the slowest device's, counts are sums
+        ktn_timings t; memset(&t, 0, sizeof t);
+        for (ktn_handle* s : h->shards) {
+            ktn_timings q; int rc = ktn_timings_get(s, &q); if (rc) return rc;
+            t.h2d_ms = q.h2d_ms > t.h2d_ms ? q.h2d_ms : t.h2d_ms; t.kernel_ms = q.kernel_ms > t.kernel_ms ? q.kernel_ms : t.kernel_ms;
+            t.d2h_ms = q.d2h_ms > t.d2h_ms ? q.d2h_ms : t.d2h_ms; t.eval_ms = q.eval_ms > t.eval_ms ? q.eval_ms : t.eval_ms;
+            t.compact_ms = q.compact_ms > t.compact_ms ? q.compact_ms : t.compact_ms; t.cut_ms = q.cut_ms > t.cut_ms ? q.cut_ms : t.cut_ms;
+            t.eval_ms_sum = q.eval_ms_sum > t.eval_ms_sum ? q.eval_ms_sum : t.eval_ms_sum; t.compact_ms_sum = q.compact_ms_sum > t.compact_ms_sum ? q.compact_ms_sum : t.compact_ms_sum;
+            t.cut_ms_sum = q.cut_ms_sum > t.cut_ms_sum ? q.cut_ms_sum : t.cut_ms_sum; t.rounds_timed = q.rounds_timed; t.rounds = q.rounds; t.launches += q.launches;
+        }
+        *out = t;
+        return KTN_OK;
+    }
     cudaSetDevice(h->device);
     drain_ring(h, false);
     h->tm.eval_ms_sum = h->eval_ms_sum; h->tm.compact_ms_sum = h->compact_ms_sum; h->tm.cut_ms_sum = h->cut_ms_sum; h->tm.rounds_timed = h->rounds_timed;
@@ -447,6 +520,7 @@ extern "C" int ktn_timings_get(ktn_handle* h, ktn_timings* out) {
 
 extern "C" int ktn_set_stream(ktn_handle* h, void* s) {
     if (!h) return KTN_ERR_USAGE;
+    if (!h->shards.empty()) return fail(h, KTN_ERR_UNSUPPORTED, "not available on a multi-device handle");
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     h->stream = s ? (cudaStream_t)s : h->own_stream;
@@ -454,19 +528,206 @@ extern "C" int ktn_set_stream(ktn_handle* h, void* s) {
 }
 
 extern "C" int ktn_separate_device_async(ktn_handle* h, const double* d_x) {
+    if (h && !h->shards.empty()) return fail(h, KTN_ERR_UNSUPPORTED, "not available on a multi-device handle");
     if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
     cudaSetDevice(h->device);
     return enqueue_round(h, d_x, KTN_MODE_SEPARATE, 1);
 }
 
 extern "C" int ktn_sync_counts(ktn_handle* h, int64_t* n_cuts, int64_t* nnz, int64_t* err_row) {
+    if (h && !h->shards.empty()) return fail(h, KTN_ERR_UNSUPPORTED, "not available on a multi-device handle");
     if (!h || !h->loaded) return fail(h, KTN_ERR_USAGE, "no problem loaded");
     cudaSetDevice(h->device);
     return finish_round(h, n_cuts, nnz, err_row);
 }
 
 extern "C" int64_t ktn_algorithmic_bytes(ktn_handle* h) {
+    if (h && !h->shards.empty()) { int64_t b = 0; for (size_t s = 0; s < h->shards.size(); ++s) b += h->shards[s]->prob.alg_bytes_static + 12 * h->sh_nnz[s] + 28 * h->sh_cuts[s] - (s ? 8 * h->g_num_var : 0); return b; }      // SURVEY 8d counts x* once
     if (!h || !h->loaded) return 0;
     return h->prob.alg_bytes_static + 12 * h->nnz_cuts + 28 * h->n_cuts;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-process sharded operation (ktn_options.ngpus > 1).  The reference owns ONE separator in ONE
+// process (src/Katana.jl:18, the loop src/model.jl:257-283): here one FRONT handle drives one handle per device.  Rows are split
+// into contiguous ranges; a round is enqueued on every device before any is waited for; the combined batch is the rank-major
+// concatenation (= ascending row order), cut at the first non-finite row as the reference does (src/model.jl:69-73, :278); every
+// device downloads its share over its own PCIe link straight into its place in ONE pinned buffer.
+// ---------------------------------------------------------------------------------------------
+#include <thread>
+void ktn_launch_shift(const int64_t* in, int64_t* out, int64_t n, int64_t add, cudaStream_t stream);
+
+static int group_fail(ktn_handle* f, ktn_handle* s, int rc) { if (f && s) f->err = s->err; return rc; }
+
+static int group_create(ktn_handle* f, ktn_handle** out) {
+    const int n = f->opt.ngpus;
+    if (n > KTN_MAX_GPUS) { delete f; return KTN_ERR_USAGE; }
+    if (f->opt.topk > 0) { fprintf(stderr, "libktn: topk is not available on a multi-device handle\n"); delete f; return KTN_ERR_UNSUPPORTED; }
+    for (int s = 0; s < n; ++s) {
+        ktn_options o = f->opt;
+        o.struct_size = (int32_t)sizeof(ktn_options); o.ngpus = 0; o.device = f->opt.devices[s] >= 0 ? f->opt.devices[s] : s;
+        ktn_handle* sh = nullptr;
+        const int rc = ktn_create(&o, &sh);
+        if (rc != KTN_OK) { for (ktn_handle* q : f->shards) ktn_destroy(q); f->shards.clear(); delete f; return rc; }
+        f->shards.push_back(sh);
+    }
+    f->shard_begin.assign((size_t)n + 1, 0); f->sh_cuts.assign((size_t)n, 0); f->sh_nnz.assign((size_t)n, 0);
+    f->device = f->shards[0]->device;
+    *out = f;
+    return KTN_OK;
+}
+
+static void group_destroy(ktn_handle* f) {
+    for (ktn_handle* s : f->shards) ktn_destroy(s);
+    f->shards.clear();
+    cudaSetDevice(f->device);
+    if (f->g_hx) cudaFreeHost(f->g_hx);
+    for (int i = 0; i < 2; ++i) if (f->h_view[i]) cudaFreeHost(f->h_view[i]);
+    delete f;
+}
+
+static int group_load_begin(ktn_handle* f, int64_t num_var, int64_t num_constr) {
+    const int64_t n = (int64_t)f->shards.size();
+    f->g_num_var = num_var; f->g_num_constr = num_constr; f->loaded = false; f->have_round = false;
+    for (int64_t s = 0; s <= n; ++s) f->shard_begin[s] = num_constr * s / n;      // contiguous, equal row counts
+    for (int64_t s = 0; s < n; ++s) {
+        int rc = ktn_load_begin(f->shards[s], num_var, f->shard_begin[s + 1] - f->shard_begin[s]); if (rc) return group_fail(f, f->shards[s], rc);
+        f->shards[s]->row_offset = f->shard_begin[s];
+    }
+    cudaSetDevice(f->device);
+    if (f->g_hx) { cudaFreeHost(f->g_hx); f->g_hx = nullptr; }
+    CK(f, cudaHostAlloc(&f->g_hx, 8 * ((size_t)num_var + 1), cudaHostAllocPortable));
+    f->loading = true;
+    return KTN_OK;
+}
+
+static int group_add_rows(ktn_handle* f, int64_t first_row, int64_t nrows, const int64_t* eptr, const int32_t* op, const int32_t* arg, const double* val,
+                          const double* lb, const double* ub, const uint8_t* flags) {
+    if (!f->loading) return fail(f, KTN_ERR_USAGE, "ktn_add_rows before ktn_load_begin");
+    std::vector<int64_t> ep;
+    for (size_t s = 0; s < f->shards.size(); ++s) {
+        const int64_t r0 = first_row > f->shard_begin[s] ? first_row : f->shard_begin[s];
+        const int64_t r1 = first_row + nrows < f->shard_begin[s + 1] ? first_row + nrows : f->shard_begin[s + 1];
+        if (r0 >= r1) continue;
+        const int64_t a = r0 - first_row, cnt = r1 - r0, base = eptr[a];
+        ep.resize((size_t)cnt + 1);
+        for (int64_t i = 0; i <= cnt; ++i) ep[i] = eptr[a + i] - base;
+        int rc = ktn_add_rows(f->shards[s], r0 - f->shard_begin[s], cnt, ep.data(), op + base, arg + base, val + base, lb + a, ub + a, flags + a);
+        if (rc) return group_fail(f, f->shards[s], rc);
+    }
+    return KTN_OK;
+}
+
+static int group_load_end(ktn_handle* f) {
+    if (!f->loading) return fail(f, KTN_ERR_USAGE, "ktn_load_end before ktn_load_begin");
+    const size_t n = f->shards.size();
+    std::vector<int> rc(n, KTN_OK);
+    std::vector<std::thread> th;
+    for (size_t s = 0; s < n; ++s) th.emplace_back([&, s] { rc[s] = ktn_load_end(f->shards[s]); });      // the tape compiler is host work: one thread per shard
+    for (std::thread& t : th) t.join();
+    for (size_t s = 0; s < n; ++s) if (rc[s]) return group_fail(f, f->shards[s], rc[s]);
+    f->loading = false; f->loaded = true;
+    return KTN_OK;
+}
+
+// One round on every device: rows == nullptr: separation (violated rows); else unconditional cuts of the listed rows.
+static int group_round(ktn_handle* f, const double* x, const int64_t* rows, int64_t nrows, int do_round, int64_t* n_cuts, int64_t* nnz, int64_t* err_row) {
+    if (!f->loaded) return fail(f, KTN_ERR_USAGE, "no problem loaded");
+    const size_t n = f->shards.size();
+    memcpy(f->g_hx, x, 8 * (size_t)f->g_num_var);
+    std::vector<uint8_t> mask;
+    for (size_t s = 0; s < n; ++s) {       // enqueue everywhere first: the devices run side by side
+        ktn_handle* h = f->shards[s];
+        cudaSetDevice(h->device);
+        if (rows) {
+            const int64_t m = h->prob.num_constr;
+            mask.assign((size_t)m + 1, 0);
+            for (int64_t j = 0; j < nrows; ++j) if (rows[j] >= f->shard_begin[s] && rows[j] < f->shard_begin[s + 1]) mask[rows[j] - f->shard_begin[s]] = 1;
+            CK(f, cudaStreamSynchronize(h->stream));
+            CK(f, cudaMemcpy(h->force.p, mask.data(), (size_t)m, cudaMemcpyHostToDevice));
+        }
+        CK(f, cudaEventRecord(h->ev0, h->stream));
+        CK(f, cudaMemcpyAsync(h->x.p, f->g_hx, 8 * (size_t)f->g_num_var, cudaMemcpyHostToDevice, h->stream));
+        CK(f, cudaEventRecord(h->ev1, h->stream));
+        int rc = enqueue_round(h, h->x.as<double>(), rows ? KTN_MODE_FORCE : KTN_MODE_SEPARATE, do_round); if (rc) return group_fail(f, h, rc);
+    }
+    int64_t tc = 0, tz = 0, er = -1; bool stopped = false;
+    for (size_t s = 0; s < n; ++s) {
+        ktn_handle* h = f->shards[s];
+        cudaSetDevice(h->device);
+        int64_t c = 0, z = 0, e = -1;
+        int rc = finish_round(h, &c, &z, &e); if (rc < 0) return group_fail(f, h, rc);
+        float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->tm.h2d_ms = ms;
+        if (stopped) { c = 0; z = 0; }                         // the reference never reaches the rows behind the first non-finite cut
+        f->sh_cuts[s] = c; f->sh_nnz[s] = z; tc += c; tz += z;
+        if (!stopped && e >= 0) { er = e + f->shard_begin[s]; stopped = true; }
+    }
+    f->n_cuts = tc; f->nnz_cuts = tz; f->err_row = er; f->have_round = true;
+    if (n_cuts) *n_cuts = tc;
+    if (nnz) *nnz = tz;
+    if (err_row) *err_row = er;
+    return er >= 0 ? KTN_NUMERIC_NONFINITE : KTN_OK;
+}
+
+// The combined batch of the last round, into a view (library-owned pinned memory) or into caller buffers.
+static int group_fetch(ktn_handle* f, ktn_cut_view* view, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val, double* lo, double* hi, double* g, double* viol, double* bconst) {
+    if (!f->have_round) return fail(f, KTN_ERR_USAGE, "no round has run");
+    const size_t nc = (size_t)f->n_cuts, nz = (size_t)f->nnz_cuts;
+    const bool lean = view && (f->opt.flags & KTN_FLAG_LEAN_VIEW) != 0;
+    if (view) {
+        const KtnPackLayout L = ktn_pack_layout(nc, nz);
+        f->view_cur ^= 1;
+        unsigned char*& buf = f->h_view[f->view_cur]; size_t& cap = f->h_view_cap[f->view_cur];
+        if (cap < L.total) {
+            cudaSetDevice(f->device);
+            if (buf) cudaFreeHost(buf);
+            buf = nullptr; cap = 0;
+            const size_t want = L.total + L.total / 4 + 4096;
+            CK(f, cudaHostAlloc(&buf, want, cudaHostAllocPortable));
+            cap = want;
+        }
+        row_id = reinterpret_cast<int64_t*>(buf + L.row_id); row_ptr = reinterpret_cast<int64_t*>(buf + L.row_ptr);
+        col = reinterpret_cast<int32_t*>(buf + L.col); val = reinterpret_cast<double*>(buf + L.val);
+        lo = reinterpret_cast<double*>(buf + L.lo); hi = reinterpret_cast<double*>(buf + L.hi);
+        g = lean ? nullptr : reinterpret_cast<double*>(buf + L.g); viol = lean ? nullptr : reinterpret_cast<double*>(buf + L.viol);
+        bconst = lean ? nullptr : reinterpret_cast<double*>(buf + L.b);
+    }
+    size_t cb = 0, zb = 0;
+    for (size_t s = 0; s < f->shards.size(); ++s) {       // every device copies its share to its place; all copies are in flight together
+        ktn_handle* h = f->shards[s];
+        const size_t c = (size_t)f->sh_cuts[s], z = (size_t)f->sh_nnz[s];
+        if (c == 0) continue;
+        cudaSetDevice(h->device);
+        const KtnPackLayout S = ktn_pack_layout((unsigned long long)h->lay_cuts, (unsigned long long)h->lay_nnz);
+        const unsigned char* src = h->out_blob[h->out_cur].as<unsigned char>();
+        CK(f, cudaEventRecord(h->ev2, h->stream));
+        if (row_id) CK(f, cudaMemcpyAsync(row_id + cb, src + S.row_id, 8 * c, cudaMemcpyDeviceToHost, h->stream));
+        if (row_ptr) {     // the shard's entry offsets start at 0: shifted on the device to the combined batch's
+            if (h->rp_shift.bytes < 8 * (c + 1)) CK(f, h->rp_shift.alloc(8 * (c + 1) + 8 * (c + 1) / 4));
+            ktn_launch_shift(reinterpret_cast<const int64_t*>(src + S.row_ptr), h->rp_shift.as<int64_t>(), (int64_t)c, (int64_t)zb, h->stream);
+            CK(f, cudaMemcpyAsync(row_ptr + cb, h->rp_shift.p, 8 * c, cudaMemcpyDeviceToHost, h->stream));
+        }
+        if (lo) CK(f, cudaMemcpyAsync(lo + cb, src + S.lo, 8 * c, cudaMemcpyDeviceToHost, h->stream));
+        if (hi) CK(f, cudaMemcpyAsync(hi + cb, src + S.hi, 8 * c, cudaMemcpyDeviceToHost, h->stream));
+        if (g) CK(f, cudaMemcpyAsync(g + cb, src + S.g, 8 * c, cudaMemcpyDeviceToHost, h->stream));
+        if (viol) CK(f, cudaMemcpyAsync(viol + cb, src + S.viol, 8 * c, cudaMemcpyDeviceToHost, h->stream));
+        if (bconst) CK(f, cudaMemcpyAsync(bconst + cb, src + S.b, 8 * c, cudaMemcpyDeviceToHost, h->stream));
+        if (col && z) CK(f, cudaMemcpyAsync(col + zb, src + S.col, 4 * z, cudaMemcpyDeviceToHost, h->stream));
+        if (val && z) CK(f, cudaMemcpyAsync(val + zb, src + S.val, 8 * z, cudaMemcpyDeviceToHost, h->stream));
+        CK(f, cudaEventRecord(h->ev3, h->stream));
+        cb += c; zb += z;
+    }
+    for (size_t s = 0; s < f->shards.size(); ++s) {
+        ktn_handle* h = f->shards[s];
+        if (f->sh_cuts[s] == 0) continue;
+        cudaSetDevice(h->device);
+        CK(f, cudaStreamSynchronize(h->stream));
+        float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev2, h->ev3) == cudaSuccess) h->tm.d2h_ms = ms;
+    }
+    if (row_ptr) row_ptr[nc] = (int64_t)nz;
+    if (view) {
+        view->n_cuts = (int64_t)nc; view->nnz = (int64_t)nz; view->row_id = row_id; view->row_ptr = row_ptr; view->col = col; view->val = val;
+        view->lo = lo; view->hi = hi; view->g = g; view->viol = viol; view->bconst = bconst;
+    }
+    return KTN_OK;
+}

@@ -488,13 +488,15 @@ int ktn_comm_launch_pending(ktn_handle* h) {
     return launch_payload(h, h->xch[(h->xch_cur + 2) % 3]);       // the slot used before the previous one
 }
 
-// Called by the round launcher (peer-push transport) before it sizes K1's grid: how many SMs the push kernel gets.  A push block
-// moves about 3 MB in the time of one K1 (measured: 16 blocks hide 44 MB at 2 GPUs, and 176 MB take 350 us at 8 GPUs =
-// ~30 GB/s per SM), so the grid follows the volume the last synced round produced: enough blocks to finish within a round,
-// few enough not to starve K1 when there is little to send.
+// Called by the round launcher (peer-push transport) before it sizes K1's grid: how many SMs the push kernel gets.
+// MEASURED default: 16 blocks (2 GPUs: 165 us per round, 8 GPUs: 355 us, v = 0.1).  A volume-driven
+// rule (about 3 MB per block, up to 48 blocks) shipped unmeasured in round 1 and cost the 4- and 8-GPU runs a factor 1.8
+// (the blocks are taken from K1); it is available as KTN_PUSH_PLAN=volume for experiments, KTN_PUSH_BLOCKS fixes the grid.
 void ktn_comm_plan_blocks(ktn_handle* h) {
     ktn_handle::PeerExchange& px = h->px;
     if (!h->comm || !px.on || px.blocks_fixed || !h->have_round) return;
+    static const bool by_volume = getenv("KTN_PUSH_PLAN") && !strcmp(getenv("KTN_PUSH_PLAN"), "volume");
+    if (!by_volume) { px.blocks = 16; return; }
     const double out = (double)ktn_pack_layout((unsigned long long)h->lay_cuts, (unsigned long long)h->lay_nnz).total * (double)h->nranks;
     int b = (int)(out / 3.0e6) + 1;
     const int hi = h->num_sms / 3 < 48 ? h->num_sms / 3 : 48;

@@ -79,6 +79,13 @@ struct ktn_handle {
         bool reserve = true;                            // K1 leaves that many SMs free (KTN_PUSH_RESERVE=0 turns it off)
     } px;
     int64_t row_offset = 0;
+    // single-process sharded operation (ktn_options.ngpus > 1): this handle is only the FRONT of one handle per device
+    std::vector<ktn_handle*> shards;
+    std::vector<int64_t> shard_begin;               // rows [shard_begin[s], shard_begin[s + 1]) live on shards[s]
+    std::vector<int64_t> sh_cuts, sh_nnz;           // last round: cuts / nnz every shard contributes to the combined batch
+    int64_t g_num_var = 0, g_num_constr = 0;
+    double* g_hx = nullptr;                         // pinned staging of x* (all devices upload from it)
+    DevBuf rp_shift;                                // shard: row_ptr of the last round shifted to the combined batch's entry offsets
 };
 
 static inline int fail(ktn_handle* h, int code, const char* fmt, ...) {

@@ -1030,6 +1030,16 @@ int ktn_launch_round(const KtnRoundParams& p, const KtnLaunchPlan& plan, int num
     return launches;
 }
 
+// row_ptr of a shard's batch shifted to the combined batch's entry offsets (single-process sharded handles, ktn_api.cu)
+namespace { __global__ void ktn_shift_kernel(const int64_t* in, int64_t* out, int64_t n, int64_t add) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i] + add;
+} }
+void ktn_launch_shift(const int64_t* in, int64_t* out, int64_t n, int64_t add, cudaStream_t stream) {
+    if (n <= 0) return;
+    const int64_t blocks = (n + 255) / 256;
+    ktn_shift_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, stream>>>(in, out, n, add);
+}
+
 int ktn_launch_eval(const KtnRoundParams& p, const KtnLaunchPlan& plan, int num_sms, int max_smem_optin,
                     cudaStream_t stream, cudaError_t* err) {
     int launches = launch_eval_part<true>(p, plan, num_sms, max_smem_optin, stream, err);

@@ -46,9 +46,12 @@ class KatanaGPUSeparator(AbstractKatanaSeparator):
     another implementation of the same C ABI as the checker).
     """
 
-    def __init__(self, library=None, topk=0):
+    def __init__(self, library=None, topk=0, ngpus=1, devices=None):
+        """ngpus > 1: the ONE separator of the model shards its rows over `ngpus` devices of this process (ktn_options.ngpus);
+        `separate` still returns one combined batch in ascending row order to the one LP master."""
         self._lib = library
         self.topk = topk
+        self.ngpus, self.devices = ngpus, devices
         self.handle = None
         self.last = None           # CutBatch of the last precompute!
         self.xstar = None
@@ -62,7 +65,8 @@ class KatanaGPUSeparator(AbstractKatanaSeparator):
         if self.handle is not None:                            # one separator is reused across models (test/runtests.jl:24)
             self.handle.close()
         # lean views: optimize! hands (row_ptr, col, val, lo, hi) to the LP; g / viol / bconst stay on the device
-        self.handle = lib.create(f_tol=f_tol, cut_coef_rng=cut_coef_rng, topk=self.topk, flags=FLAG_LEAN_VIEW)
+        self.handle = lib.create(f_tol=f_tol, cut_coef_rng=cut_coef_rng, topk=self.topk, flags=FLAG_LEAN_VIEW,
+                                 ngpus=self.ngpus if self.ngpus > 1 else 0, devices=self.devices)
         self.num_var, self.num_constr = num_var, num_constr
         lb = np.full(num_constr, -np.inf); ub = np.full(num_constr, np.inf)
         self.handle.load(num_var, rows_to_wire(oracle, num_constr, lb, ub))

@@ -9,6 +9,6 @@ while [ $# -gt 1 ]; do
   name=$1; flags=$2; shift 2
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -std=c++17 -Xcompiler -fPIC,-ffp-contract=off -ccbin g++ $flags -Xptxas -v -c -o ../../build/variants/k_$name.o ktn_kernels.cu 2> ../../build/variants/k_$name.ptxas.log
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -std=c++17 -Xcompiler -fPIC,-ffp-contract=off -ccbin g++ $flags -c -o ../../build/variants/c_$name.o ktn_comm.cu
-  /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../build/variants/libktn_$name.so ktn_api.o ../../build/variants/c_$name.o ../../build/variants/k_$name.o ktn_compile.o ktn_synth.o -lcudart -ldl
+  /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -Xlinker -Bsymbolic -o ../../build/variants/libktn_$name.so ktn_api.o ../../build/variants/c_$name.o ../../build/variants/k_$name.o ktn_compile.o ktn_synth.o -lcudart -ldl
   echo "$name: $flags :: $(grep -A2 'ktn_family_kernelILi1' ../../build/variants/k_$name.ptxas.log | grep -o 'Used [0-9]* registers' | head -1) $(grep -B1 'ktn_family_kernelILi1' ../../build/variants/k_$name.ptxas.log | grep -o '[0-9]* bytes spill stores' | head -1)"
 done

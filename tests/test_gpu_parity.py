@@ -291,3 +291,109 @@ def test_ecp_end_to_end_on_gpu(cuda_lib):
         assert np.isclose(m.getobjectivevalue(), obj, rtol=1e-6, atol=1e-6), (name, cite)
         if sol is not None:
             assert np.allclose([m.getvalue(v) for v in vars_], sol, rtol=1e-3, atol=1e-3), (name, cite)
+
+
+@pytest.mark.parametrize("family", ["lse", "quad"])
+def test_family_rows_edge_values_on_gpu(oracle_lib, cuda_lib, family):
+    """Device twin of test_compiler_emu.py::test_family_rows_edge_values: the family kernels (K1 forward, K3 cut incl. the exact
+    revmul resweep, the rounding sweep, ktn_exp_slow, rows of more than 16 unique variables = the streaming class) on overflow,
+    underflow, NaN / inf points, coefficient ranges that make round_coefs (src/model.jl:200-207) zero entries, ragged chunks
+    and every unique-variable count 1..20, 40, 70 -- with cut_coef_rng 1e9 and 10."""
+    rng = np.random.default_rng(11)
+    nvar = 80
+    exprs = []
+    for nu in list(range(1, 21)) * 3 + [40, 70]:
+        cols = rng.choice(nvar, nu, replace=False)
+        scale = 10.0 ** rng.integers(-12, 12, nu)
+        if family == "lse":
+            exprs.append(E.log(E.sum_([E.exp(E.const(float(rng.uniform(-1, 1) * scale[k])) * E.var(int(cols[k])) + float(rng.uniform(-1, 1))) for k in range(nu)])))
+        else:
+            exprs.append(E.sum_([E.const(float(rng.uniform(0.5, 1.5) * scale[k])) * E.var(int(cols[k]))**2 for k in range(nu)] +
+                                [E.const(float(rng.uniform(-1, 1))) * E.var(int(cols[k])) for k in range(nu)]))
+    m = len(exprs)
+    w = E.to_wire(exprs, np.full(m, -np.inf), np.full(m, -1e300), [ROW_NL] * m)
+    pts = [rng.uniform(-2, 2, nvar), np.zeros(nvar), np.full(nvar, 1e3), np.full(nvar, -1e3), np.full(nvar, 1e200), rng.uniform(-1e-9, 1e-9, nvar)]
+    p = rng.uniform(-2, 2, nvar); p[3] = np.nan; pts.append(p)
+    p = rng.uniform(-2, 2, nvar); p[5] = np.inf; p[7] = -np.inf; pts.append(p)
+    ho, hc = both(oracle_lib, cuda_lib, nvar, w)
+    ncuts = []
+    for rng_coef in (1e9, 10.0):
+        ho.set_params(1e-6, rng_coef, 0); hc.set_params(1e-6, rng_coef, 0)
+        for x in pts:
+            assert bits_equal(ho.eval_g(x), hc.eval_g(x))
+            bo, bc = ho.separate(x), hc.separate(x)
+            assert_batches_identical(bo, bc, f"{family} rng={rng_coef}")
+            ncuts.append(bo.n_cuts)
+            # row by row, so that the rows behind the first non-finite cut (which ends a batch, src/model.jl:278) are compared too
+            for r0 in range(0, m, 7):
+                sub = np.arange(r0, min(m, r0 + 7), dtype=np.int64)
+                assert_batches_identical(ho.gencut_rows(x, sub, True), hc.gencut_rows(x, sub, True), f"{family} gencut+round rows {r0}")
+    assert max(ncuts) > 0
+
+
+def test_round_coefs_on_generic_and_big_kernels(oracle_lib, cuda_lib):
+    """cut_coef_rng = 10 (round_coefs zeroes small coefficients, src/model.jl:200-207) on the interpreter kernel (generic
+    shapes), the global-scratch kernel (200-term rows) and the dense epigraph row (src/nlpeval.jl:49-54)."""
+    rng = np.random.default_rng(23)
+    nvar = 240
+    x = [E.var(j) for j in range(nvar)]
+    exprs = []
+    for _ in range(150):                                                         # generic shapes: products, divisions, sqrt, powers
+        c = rng.choice(nvar, 4, replace=False); s = 10.0 ** rng.integers(-6, 6, 4)
+        exprs.append(E.const(float(s[0])) * x[c[0]] * x[c[1]] + E.sqrt(E.const(float(s[1])) * x[c[2]]**2 + 1.0) + E.const(float(s[2])) * x[c[3]]**3 - x[c[0]] / (x[c[1]]**2 + 2.0))
+    for _ in range(40):                                                          # 200-term rows: BIG kernel
+        exprs.append(E.sum_([E.exp(E.const(float(rng.uniform(-1, 1) * 10.0 ** rng.integers(-4, 3))) * x[int(j)]) for j in rng.choice(nvar, 200, replace=False)]))
+    exprs.append(E.sum_([E.const(float(10.0 ** rng.integers(-5, 5))) * (x[j] - 0.5)**2 for j in range(0, nvar - 1, 3)]) - x[nvar - 1])
+    m = len(exprs)
+    w = E.to_wire(exprs, np.full(m, -np.inf), np.full(m, -1e300), [ROW_NL] * (m - 1) + [ROW_NL | ROW_DENSE])
+    ho, hc = both(oracle_lib, cuda_lib, nvar, w)
+    zeroed = 0
+    for rng_coef in (10.0, 1e3, 1e9):
+        ho.set_params(1e-6, rng_coef, 0); hc.set_params(1e-6, rng_coef, 0)
+        for _ in range(3):
+            xx = rng.uniform(-1.5, 1.5, nvar)
+            bo = ho.separate(xx)
+            assert_batches_identical(bo, hc.separate(xx), f"rng={rng_coef}")
+            zeroed += int(np.sum(bo.val == 0.0))
+    assert zeroed > 0                                                            # the rounding sweep did run
+
+
+def test_single_process_sharded_handle(oracle_lib, cuda_lib):
+    """ktn_options.ngpus: ONE handle, rows sharded over several devices (here the same device three times, so that the path runs
+    on a one-GPU box), ONE combined batch in ascending row order == the oracle over all rows, bit for bit: separate, views,
+    gencut_rows, eval_g / get_g, jac_structure, reload, and the reference's stop at the first non-finite row when that row is
+    on a shard that is NOT the last (src/model.jl:69-73, :278)."""
+    for kind, nv, nr in ((1, 4000, 9001), (0, 1000, 5000), (2, 2000, 3000)):
+        w = cuda_lib.synth_rows(kind, 77 + kind, nv, 0, nr); x0 = cuda_lib.synth_point(kind, 77 + kind, nv)
+        ho = oracle_lib.create(); ho.load(nv, w)
+        hs = cuda_lib.create(ngpus=3, devices=[0, 0, 0]); hs.load(nv, w)
+        assert all(np.array_equal(a, b) for a, b in zip(ho.jac_structure(), hs.jac_structure()))
+        g = ho.eval_g(x0)
+        assert bits_equal(g, hs.eval_g(x0))
+        for v in (0.0, 0.03, 0.5, 1.0):
+            ub = np.full(nr, np.quantile(g, 1 - v) if v > 0 else g.max() + 1.0)
+            ho.set_bounds(w.lb, ub); hs.set_bounds(w.lb, ub)
+            bo = ho.separate(x0)
+            assert_batches_identical(bo, hs.separate(x0), f"sharded kind {kind} v {v}")
+            assert_batches_identical(bo, hs.separate(x0, view=True), f"sharded view kind {kind} v {v}")
+            assert bits_equal(ho.get_g(), hs.get_g())
+            assert ho.algorithmic_bytes() == hs.algorithmic_bytes()
+        rows = np.unique(np.random.default_rng(kind).integers(0, nr, 300)).astype(np.int64)
+        assert_batches_identical(ho.gencut_rows(x0, rows, True), hs.gencut_rows(x0, rows, True), "sharded gencut")
+        hs.close(); ho.close()
+    # first non-finite row on the middle shard: the cuts of the later shards are dropped, the earlier ones stand
+    x, y, z = E.var(0), E.var(1), E.var(2)
+    exprs = [x**2 + y**2 - 1.0] * 50 + [E.sqrt(x**2 + y**2) - (z - 0.25)] + [x**2 + y**2 - 1.0] * 39
+    m = len(exprs)
+    w = E.to_wire(exprs, np.full(m, -np.inf), np.full(m, -2.0), [ROW_NL] * m)
+    ho = oracle_lib.create(); ho.load(3, w)
+    hs = cuda_lib.create(ngpus=3, devices=[0, 0, 0]); hs.load(3, w)
+    bo, bs = ho.separate(np.zeros(3)), hs.separate(np.zeros(3))
+    assert bo.status == KTN_NUMERIC_NONFINITE and bo.err_row == 50 and bo.n_cuts == 50
+    assert_batches_identical(bo, bs, "sharded, truncated on the middle shard")
+    assert_batches_identical(bo, hs.separate(np.zeros(3), view=True), "sharded view, truncated")
+    assert_batches_identical(ho.separate(np.ones(3)), hs.separate(np.ones(3)))
+    nv2, w2, pts = kat_problem()                                                 # reload on the same (sharded) handle
+    ho.load(nv2, w2); hs.load(nv2, w2)
+    for p in pts:
+        assert_batches_identical(ho.separate(p), hs.separate(p), "sharded KAT")
