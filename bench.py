@@ -115,19 +115,25 @@ def cpu_rounds(oracle, w, x0, nv, ub, threads, seconds_budget, min_rounds=2):
     return float(np.median(ts)), len(ts), nc
 
 
+def workload_string(args, desc):
+    """config.workload: the SAME string in both arms (the driver compares them)."""
+    return f"{args.workload}: {desc}; m={args.rows} rows per GPU, n={args.vars} vars, violated fraction {args.v}, f_tol 1e-6"
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm for the path.  The reference is Julia over un-vendored
-    packages and cannot be built or run here, so this arm times the oracle (its C restatement) with all host threads."""
+    packages and cannot be built or run here, so this arm times the oracle (its C restatement) with all host threads.
+    It loads the oracle and the synthetic generators only (libktn_synth.so), never the product library."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import katana_jl_b200  # noqa: F401
-    from katana_jl_b200.binding import CUDA_LIB_PATH, KtnLibrary
-    synth = KtnLibrary(CUDA_LIB_PATH)      # generators only
+    from katana_jl_b200.binding import KtnLibrary, SynthLibrary
+    synth = SynthLibrary()
     oracle = KtnLibrary(os.path.join(ROOT, "oracle", "libktn_oracle.so"))
     kind, seed, desc = WORKLOADS[args.workload]
     nv = args.vars
-    rows = args.rows                      # the CPU arm processes one GPU's share of the weak-scaling workload per step
+    rows = args.rows                      # a step is a bounded sample of the job: one GPU's share of the weak-scaling workload
     w, x0 = make_instance(synth, kind, seed, nv, 0, rows)
     h = oracle.create(); h.load(nv, w); g = h.eval_g(x0); h.close()
     ub = np.full(rows, np.quantile(g, 1 - args.v))
@@ -145,13 +151,27 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "constraints/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}; m={rows} rows, n={nv} vars, violated fraction {args.v}", "rows_per_step": rows},
+        "config": {"workload": workload_string(args, desc), "rows_per_step": rows,
+                   "note": "the CPU rate does not depend on the GPU count: every step separates one GPU's share of the workload"},
         "cpu_baseline": {"value": value, "unit": "constraints/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} full rounds over {rows} rows (C restatement of the Katana.jl separator, OpenMP over rows; not Julia)"},
         "e2e": {"value": value, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out), flush=True)
+
+
+def sub_batch(b, keep):
+    """The cuts of `b` whose row ids are in the sorted array `keep`, as (row_id, col, val, lo, hi) with per-cut entry slices concatenated."""
+    sel = np.nonzero(np.isin(b.row_id, keep))[0]
+    rp = np.asarray(b.row_ptr)
+    idx = np.concatenate([np.arange(rp[c], rp[c + 1]) for c in sel]) if len(sel) else np.empty(0, np.int64)
+    return (np.asarray(b.row_id)[sel].copy(), (rp[sel + 1] - rp[sel]).copy(), np.asarray(b.col)[idx].copy(), np.asarray(b.val)[idx].copy(),
+            np.asarray(b.lo)[sel].copy(), np.asarray(b.hi)[sel].copy())
+
+
+def same_cuts(a, b):
+    return all(x.shape == y.shape and x.tobytes() == y.tobytes() for x, y in zip(a, b))
 
 
 def main():
@@ -175,23 +195,25 @@ def main():
     import torch
     import torch.distributed as dist
     import katana_jl_b200  # noqa: F401
-    from katana_jl_b200.binding import KtnLibrary, comm_unique_id, load_cuda_library
+    from katana_jl_b200.binding import FLAG_LEAN_VIEW, KtnLibrary, comm_unique_id, load_cuda_library
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")     # host-side barriers: an NCCL barrier would keep the waiting ranks' GPUs busy
     lib = load_cuda_library()              # fails loudly if libktn.so is missing: there is no CPU fallback
     kind, seed, desc = WORKLOADS[args.workload]
     nv, rows = args.vars, args.rows
     row_begin = rank * rows               # weak scaling: every GPU owns `rows` rows of an instance with world*rows rows
     w, x0 = make_instance(lib, kind, seed, nv, row_begin, rows)
-    from katana_jl_b200.binding import FLAG_LEAN_VIEW
     h = lib.create(device=local, flags=FLAG_LEAN_VIEW)        # as KatanaGPUSeparator creates it: cut views carry what the LP needs
     h.load(nv, w)
     h.set_row_offset(row_begin)
     g = h.eval_g(x0)
-    ub = np.full(rows, np.quantile(g, 1 - args.v))
+    ub_scalar = float(np.quantile(g, 1 - args.v))
+    ub = np.full(rows, ub_scalar)
     h.set_bounds(w.lb, ub)
     if args.topk > 0:
         h.set_params(1e-6, 1e9, args.topk)
@@ -233,7 +255,7 @@ def main():
         for _ in range(args.steps):
             step()
         if world > 1:
-            h.sync_gathered()              # the exchange is pipelined one round deep: the last payload belongs to the timed region
+            tot_cuts, tot_nnz = h.sync_gathered()      # the exchange is pipelined one round deep: the last payload belongs to the timed region
         e1.record(stream)
         barrier()
     ms_total = e0.elapsed_time(e1)
@@ -251,61 +273,110 @@ def main():
     launches = t_after["launches"] - t_before["launches"]
     timed = max(1, t_after["rounds_timed"] - t_before["rounds_timed"])
     k1_ms = (t_after["eval_ms_sum"] - t_before["eval_ms_sum"]) / timed
-    k2_ms = (t_after["compact_ms_sum"] - t_before["compact_ms_sum"]) / timed
+    k2_ms = (t_after["compact_ms_sum"] - t_before["compact_ms_sum"]) / timed       # K2 + K3 (no event is recorded between them)
+    gc.enable()
+
+    # ---- sharded runs: the gathered batch of one more round against a single handle, outside the timed region ------
+    sharded = None
+    if world > 1:
+        xt = max(1, t_after["exchanges_timed"] - t_before["exchanges_timed"])
+        exchange_ms = (t_after["exchange_ms_sum"] - t_before["exchange_ms_sum"]) / xt
+        ubs = [None] * world
+        dist.all_gather_object(ubs, ub_scalar, group=cpu_group)
+        step()
+        gathered = h.fetch_gathered()      # every rank downloads the combined batch: ascending global rows
+        blob_bytes = 64 + 28 * n_cuts + 12 * nnz + 8
+        sharded = {"exchange_ms": exchange_ms, "inbound_bytes_per_gpu": (world - 1) * blob_bytes,
+                   "inbound_gbs_per_gpu": (world - 1) * blob_bytes / (exchange_ms * 1e-3) / 1e9 if exchange_ms > 0 else None,
+                   "gathered_cuts": int(gathered.n_cuts)}
+        piece = max(1, min(rows, 100000 // world))
+        keep = np.concatenate([np.arange(r * rows, r * rows + piece) for r in range(world)])
+        if rank == 0:
+            chk = lib.create(device=local, flags=0)
+            chk.load_begin(nv, world * piece)
+            for r in range(world):
+                chk.add_rows(r * piece, lib.synth_rows(kind, seed, nv, r * rows, piece))
+            chk.load_end()
+            chk.set_bounds(np.full(world * piece, -np.inf), np.repeat(np.array(ubs), piece))
+            ref = chk.separate(x0)
+            ref_rows = keep[ref.row_id]                 # the check handle numbers its rows 0 .. world * piece - 1
+            want = (ref_rows, np.diff(ref.row_ptr), ref.col, ref.val, ref.lo, ref.hi)
+            sharded["sharded_parity_exchange"] = bool(same_cuts(sub_batch(gathered, keep), want))
+            chk.close()
 
     # ---- e2e: the separator call a Katana user makes, host buffers in and out ------------------------------------
     h.set_stream(0)
-    from katana_jl_b200.separators import KatanaGPUSeparator
-    sep = KatanaGPUSeparator(); sep.handle = h; sep.num_var, sep.num_constr = nv, rows
-    x_host = x0.copy()
-    for _ in range(3):
-        batch = sep.separate(x_host)
-    barrier()
-    e2e_steps = max(3, min(args.steps, 20))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        batch = sep.separate(x_host)
     torch.cuda.synchronize()
-    e2e_dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t.item())
-    e2e_value = world * rows * e2e_steps / e2e_dt
-    h2d_bytes = 8 * nv
-    d2h_bytes = 64 + sum(int(getattr(batch, f).nbytes) for f in ("row_id", "row_ptr", "col", "val", "lo", "hi", "g", "viol", "bconst"))
-
-    if rank != 0:
+    from katana_jl_b200.separators import KatanaGPUSeparator
+    x_host = x0.copy()
+    e2e_steps = max(3, min(args.steps, 20))
+    if world == 1:
+        sep = KatanaGPUSeparator(); sep.handle = h; sep.num_var, sep.num_constr = nv, rows
+        e2e_call = "KatanaGPUSeparator.separate(xstar) -> CutBatch (ktn_separate + ktn_fetch_cuts_view: x* from host memory, cuts into the library's pinned buffer)"
+    elif rank == 0:
+        # ONE separator in ONE process over all world*rows rows, as the reference owns it (src/Katana.jl:18): ktn_options.ngpus
+        hg = lib.create(flags=FLAG_LEAN_VIEW, ngpus=world, devices=list(range(world)))
+        hg.load_begin(nv, world * rows)
+        for r in range(world):
+            hg.add_rows(r * rows, w if r == 0 else lib.synth_rows(kind, seed, nv, r * rows, rows))
+        hg.load_end()
+        hg.set_bounds(np.full(world * rows, -np.inf), np.repeat(np.array(ubs), rows))
+        sep = KatanaGPUSeparator(ngpus=world); sep.handle = hg; sep.num_var, sep.num_constr = nv, world * rows
+        e2e_call = (f"KatanaGPUSeparator(ngpus={world}).separate(xstar) -> ONE CutBatch of all {world} devices' cuts in host memory (single process: x* uploaded to every "
+                    "device, rounds side by side, every device downloads its cuts over its own PCIe link into one pinned buffer)")
+    e2e_dt, batch = None, None
+    if world == 1 or rank == 0:
+        for _ in range(3):
+            batch = sep.separate(x_host)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            batch = sep.separate(x_host)
+        e2e_dt = time.perf_counter() - t0
         if world > 1:
-            dist.barrier(); dist.destroy_process_group()
+            sharded["sharded_parity"] = bool(same_cuts(sub_batch(batch, keep), want)) and bool(sharded["sharded_parity_exchange"])
+            sharded["e2e_cuts"] = int(batch.n_cuts)
+    if world > 1:
+        dist.barrier(group=cpu_group)      # the other ranks wait here, GPUs idle, while rank 0 times the single-process separator
+    if rank != 0:
+        dist.destroy_process_group()
         return
+    e2e_value = world * rows * e2e_steps / e2e_dt
+    h2d_bytes = 8 * nv * world
+    d2h_bytes = 64 + sum(int(getattr(batch, f).nbytes) for f in ("row_id", "row_ptr", "col", "val", "lo", "hi", "g", "viol", "bconst"))
 
     # ---- roofline of the dominant kernel (K1) and of the whole round ---------------------------------------------
     peak, peak_src = load_peaks()
     alg_round = h.algorithmic_bytes()                      # sum_NL(4 nnz + 8 C + 16) + 8 n + sum_sel(12 nnz + 28)
-    alg_k1 = alg_round - 4 * nnz - 20 * n_cuts             # K1 reads the inputs and writes coefficient values + constant of the selected rows
+    alg_k1 = alg_round - 12 * nnz - 28 * n_cuts            # K1 reads every row's columns, constants and bounds and x*; the cuts' CSR is K2 / K3's share
     achieved = alg_k1 / (k1_ms * 1e-3) / 1e9
+    family = args.workload in ("lse", "qcqp")
     out = {
         "metric": METRIC, "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}; m={rows} rows/GPU, n={nv} vars, violated fraction {args.v}, f_tol 1e-6",
+        "config": {"workload": workload_string(args, desc),
                    "rows_per_gpu": rows, "num_var": nv, "violated_fraction": args.v, "topk": args.topk, "cuts_per_round_per_gpu": n_cuts, "cut_nnz_per_round_per_gpu": nnz,
                    "l2": f"no flush needed: one round streams {alg_round / 1e6:.0f} MB of inputs > 126 MB L2",
                    "exchange": "none" if world == 1 else exchange_desc},
-        "roofline": {"bound": "hbm", "kernel": "ktn_family_kernel (K1: evaluate g, test, Jacobian row, cut row; one launch per round)" if args.workload in ("lse", "qcqp") else "ktn_round_kernel (K1, tape interpreter)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "ktn_family_kernel (K1: evaluate g of every row, violation test; one launch per round)" if family else "ktn_round_kernel (K1, tape interpreter: evaluate, test, cut rows)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_k1, "ms_per_launch": k1_ms,
                      "round": {"algorithmic_bytes": alg_round, "ms": k1_ms + k2_ms, "frac": alg_round / ((k1_ms + k2_ms) * 1e-3) / 1e9 / peak,
-                               "k2_compact_ms": k2_ms}},
+                               "k2_k3_ms": k2_ms, "kernels": "K1 ktn_family_kernel, K2 ktn_compact_kernel (ordered compaction), K3 ktn_cut_kernel (cuts of the selected rows)"}},
         "e2e": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": 1e3 * e2e_dt / e2e_steps, "steps": e2e_steps, "call": "KatanaGPUSeparator.separate(xstar) -> CutBatch (ktn_separate + ktn_fetch_cuts_view: x* from host memory, cuts into the library's pinned buffer)"},
+                "ms_per_step": 1e3 * e2e_dt / e2e_steps, "steps": e2e_steps, "call": e2e_call},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
     }
+    if sharded is not None:
+        out["sharded"] = sharded
+        out["sharded_parity"] = sharded.get("sharded_parity")
     traffic_file = os.path.join(ROOT, "profiles", "k1_dram_traffic.json")
     if os.path.exists(traffic_file):
         tr = json.load(open(traffic_file)).get(args.workload)
         if tr and tr.get("rows") == rows and abs(tr.get("v", -1) - args.v) < 1e-9:
             out["roofline"]["traffic"] = tr["dram_bytes"]
+            out["roofline"]["traffic_source"] = tr.get("source")
 
     # ---- cpu_baseline: the reference algorithm on this box's host cores (N = 1 only) -----------------------------
     if world == 1 and not args.no_cpu:
@@ -321,7 +392,7 @@ def main():
                                "all_cores": {"value": sample_rows / medn, "cores": cores, "rounds": nn}}
     print(json.dumps(out), flush=True)
     if world > 1:
-        dist.barrier(); dist.destroy_process_group()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

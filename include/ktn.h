@@ -106,8 +106,8 @@ enum {
 typedef struct ktn_timings {
     double h2d_ms;        /* x* upload */
     double kernel_ms;     /* separation kernels, CUDA events on the library stream */
-    double exchange_ms;   /* reserved, 0: the exchange of a sharded round overlaps the following rounds on its own stream; its cost shows
-                             in the round rate (bench.py) and in the wait of ktn_sync_gathered, not as a span of its own */
+    double exchange_ms;   /* sharded handles: the last synced exchange's transfer on the exchange stream (the push kernel / the
+                             ncclAllGather, CUDA events; it runs beside the following rounds, so it is NOT part of kernel_ms) */
     double d2h_ms;        /* cut download in ktn_fetch_cuts */
     int64_t launches;     /* kernels launched by this library since creation */
     int64_t rounds;       /* separation rounds run since creation */
@@ -118,6 +118,8 @@ typedef struct ktn_timings {
     int64_t rounds_timed;
     double cut_ms;        /* last round: cut kernel (K3: cuts of the family rows) */
     double cut_ms_sum;
+    double exchange_ms_sum; /* sharded handles: sum of exchange_ms over the exchanges synced since creation */
+    int64_t exchanges_timed;
 } ktn_timings;
 
 /* lifetime -- replaces constructing KatanaFirstOrderSeparator() (src/separators.jl:58-77). */
@@ -222,6 +224,10 @@ int ktn_sync_gathered(ktn_handle* h, int64_t* total_cuts, int64_t* total_nnz);
 int ktn_exchange_transport(ktn_handle* h);
 int ktn_fetch_gathered(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val,
                        double* lo, double* hi, double* g, double* viol, double* bconst);
+/* ktn_sync_gathered / ktn_fetch_gathered return KTN_NUMERIC_NONFINITE on EVERY rank when a rank's round hit a non-finite cut: the
+ * gathered batch then ends at that row, as the reference's loop does (src/model.jl:69-73, :278), and this returns its global index
+ * (-1: none). */
+int ktn_gathered_error_row(ktn_handle* h, int64_t* err_row);
 
 /* ---- deterministic synthetic instances (test / bench support) ----
  * kind: 0 = sparse convex QCQP (config 2), 1 = log-sum-exp (config 3), 2 = SOC-like risk rows (config 4).

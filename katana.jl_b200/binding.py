@@ -36,7 +36,7 @@ class ktn_options(C.Structure):
 class ktn_timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("exchange_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("launches", C.c_int64), ("rounds", C.c_int64), ("eval_ms", C.c_double), ("compact_ms", C.c_double),
-                ("eval_ms_sum", C.c_double), ("compact_ms_sum", C.c_double), ("rounds_timed", C.c_int64), ("cut_ms", C.c_double), ("cut_ms_sum", C.c_double)]
+                ("eval_ms_sum", C.c_double), ("compact_ms_sum", C.c_double), ("rounds_timed", C.c_int64), ("cut_ms", C.c_double), ("cut_ms_sum", C.c_double), ("exchange_ms_sum", C.c_double), ("exchanges_timed", C.c_int64)]
 
 
 class ktn_cut_view(C.Structure):
@@ -76,6 +76,7 @@ _SIGS = {
     "ktn_sync_gathered": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ktn_exchange_transport": (C.c_int, [_P]),
     "ktn_fetch_gathered": (C.c_int, [_P] + [_P] * 9),
+    "ktn_gathered_error_row": (C.c_int, [_P, C.POINTER(C.c_int64)]),
 }
 # exported by the CUDA library only (test / bench support, include/ktn.h bottom)
 _SYNTH_SIGS = {
@@ -268,7 +269,7 @@ class Handle:
                      np.empty(nc, np.float64), np.empty(nc, np.float64), np.empty(nc, np.float64), np.empty(nc, np.float64), np.empty(nc, np.float64))
         fn = self.dll.ktn_fetch_gathered if gathered else self.dll.ktn_fetch_cuts
         self._ck(fn(self.h, _ptr(b.row_id), _ptr(b.row_ptr), _ptr(b.col), _ptr(b.val), _ptr(b.lo), _ptr(b.hi), _ptr(b.g), _ptr(b.viol), _ptr(b.bconst)),
-                 "ktn_fetch_cuts")
+                 "ktn_fetch_cuts", numeric_ok=True)
         return b
 
     def _fetch_view(self, status, err):
@@ -355,15 +356,20 @@ class Handle:
 
     def sync_gathered(self):
         nc, nz = C.c_int64(), C.c_int64()
-        self._ck(self.dll.ktn_sync_gathered(self.h, C.byref(nc), C.byref(nz)), "ktn_sync_gathered")
+        self.gathered_status = self._ck(self.dll.ktn_sync_gathered(self.h, C.byref(nc), C.byref(nz)), "ktn_sync_gathered", numeric_ok=True)
         return nc.value, nz.value
+
+    def gathered_error_row(self):
+        er = C.c_int64(-1)
+        self._ck(self.dll.ktn_gathered_error_row(self.h, C.byref(er)), "ktn_gathered_error_row")
+        return er.value
 
     def exchange_transport(self):
         return {0: "none", 1: "nccl", 2: "peer-push"}[int(self.dll.ktn_exchange_transport(self.h))]
 
     def fetch_gathered(self):
         nc, nz = self.sync_gathered()
-        return self._fetch(0, nc, nz, -1, gathered=True)
+        return self._fetch(self.gathered_status, nc, nz, self.gathered_error_row(), gathered=True)
 
 
 def comm_unique_id(lib):

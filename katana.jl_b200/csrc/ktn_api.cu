@@ -513,7 +513,8 @@ extern "C" int ktn_timings_get(ktn_handle* h, ktn_timings* out) {
     }
     cudaSetDevice(h->device);
     drain_ring(h, false);
-    h->tm.eval_ms_sum = h->eval_ms_sum; h->tm.compact_ms_sum = h->compact_ms_sum; h->tm.cut_ms_sum = h->cut_ms_sum; h->tm.rounds_timed = h->rounds_timed;
+    h->tm.eval_ms_sum = h->eval_ms_sum; h->tm.compact_ms_sum = h->compact_ms_sum; h->tm.cut_ms_sum = h->cut_ms_sum;
+    h->tm.exchange_ms_sum = h->exchange_ms_sum; h->tm.exchanges_timed = h->exchanges_timed; h->tm.rounds_timed = h->rounds_timed;
     *out = h->tm;
     return KTN_OK;
 }

@@ -250,7 +250,7 @@ void ktn_comm_release(ktn_handle* h) {
     for (auto& x : h->xch) {
         x.gathered.release(); x.all_counts.release();
         if (x.h_all_counts) { cudaFreeHost(x.h_all_counts); x.h_all_counts = nullptr; }
-        if (x.packed) { cudaEventDestroy(x.packed); cudaEventDestroy(x.sizes); x.packed = x.sizes = nullptr; }
+        if (x.packed) { cudaEventDestroy(x.packed); cudaEventDestroy(x.sizes); cudaEventDestroy(x.t0); cudaEventDestroy(x.t1); x.packed = x.sizes = x.t0 = x.t1 = nullptr; }
         x.state = 0;
     }
     for (int k = 0; k < 3; ++k) { if (h->blob_ev[k]) { cudaEventDestroy(h->blob_ev[k]); h->blob_ev[k] = nullptr; } h->blob_busy[k] = false; }
@@ -283,6 +283,7 @@ extern "C" int ktn_comm_init(ktn_handle* h, int32_t nranks, int32_t rank, const 
         x.g_cuts.assign(nranks, 0); x.g_nnz.assign(nranks, 0); x.g_off.assign(nranks + 1, 0);
         x.g_lay_cuts.assign(nranks, 0); x.g_lay_nnz.assign(nranks, 0); x.g_bytes.assign(nranks, 0);
         CK(h, cudaEventCreateWithFlags(&x.packed, cudaEventDisableTiming)); CK(h, cudaEventCreateWithFlags(&x.sizes, cudaEventDisableTiming));
+        CK(h, cudaEventCreate(&x.t0)); CK(h, cudaEventCreate(&x.t1));
         x.state = 0;
     }
     for (int k = 0; k < 3; ++k) { CK(h, cudaEventCreateWithFlags(&h->blob_ev[k], cudaEventDisableTiming)); h->blob_busy[k] = false; }
@@ -382,6 +383,7 @@ static int peer_exchange(ktn_handle* h, size_t my_cap) {
     }
     q.ack_local = px.arena.as<unsigned long long>(); q.src = h->out_blob[x.src_idx].as<unsigned char>(); q.seq = seq;
     q.ctr = px.ctr.as<unsigned int>(); q.nranks = h->nranks; q.rank = h->rank;
+    CK(h, cudaEventRecord(x.t0, h->comm_stream));
 #ifdef KTN_OPT_PUSH_TMA
     {
         static bool attr = false;
@@ -393,6 +395,7 @@ static int peer_exchange(ktn_handle* h, size_t my_cap) {
     ktn_push_kernel<<<px.blocks, 512, 0, h->comm_stream>>>(q);
 #endif
     CK(h, cudaGetLastError());
+    CK(h, cudaEventRecord(x.t1, h->comm_stream));
     h->tm.launches += 1;
     CK(h, cudaEventRecord(h->blob_ev[x.src_idx], h->comm_stream)); h->blob_busy[x.src_idx] = true;
     x.state = 2;
@@ -442,7 +445,9 @@ static int launch_payload(ktn_handle* h, ktn_handle::Exchange& x) {
     x.gathered_bytes = (int64_t)off;
     if (x.gathered.bytes < off) { CK(h, cudaStreamSynchronize(h->comm_stream)); CK(h, x.gathered.alloc(off + off / 4)); }
     if (h->out_cap < slot) return fail(h, KTN_ERR_NCCL, "exchange slot larger than this rank's cut blob (very unbalanced shards)");
+    CK(h, cudaEventRecord(x.t0, h->comm_stream));
     NK(h, N.AllGather(h->out_blob[x.src_idx].p, x.gathered.p, slot, ncclUint8, comm, h->comm_stream));
+    CK(h, cudaEventRecord(x.t1, h->comm_stream));
     CK(h, cudaEventRecord(h->blob_ev[x.src_idx], h->comm_stream)); h->blob_busy[x.src_idx] = true;
     x.state = 2;
     return KTN_OK;
@@ -531,17 +536,32 @@ extern "C" int ktn_sync_gathered(ktn_handle* h, int64_t* total_cuts, int64_t* to
         if (x.state != 2) return fail(h, KTN_ERR_USAGE, "no exchange has been enqueued");
         CK(h, cudaStreamSynchronize(h->comm_stream));
     }
-    int64_t c = 0, z = 0;
-    for (int r = 0; r < h->nranks; ++r) { c += x.g_cuts[r]; z += x.g_nnz[r]; }
+    { float ms = 0.f; if (cudaEventElapsedTime(&ms, x.t0, x.t1) == cudaSuccess) { h->tm.exchange_ms = ms; h->exchange_ms_sum += ms; h->exchanges_timed++; } }
+    // the reference stops at the first non-finite cut (src/model.jl:69-73, :278): the batch ends inside the first rank that saw
+    // one (its own cuts are already truncated there); the ranks behind it contribute nothing.  Every rank reads the same headers,
+    // so every rank returns the same status.
+    const unsigned long long* hd = h->px.on ? h->px.h_boot : x.h_all_counts;
+    int64_t c = 0, z = 0; x.g_err_row = -1;
+    for (int r = 0; r < h->nranks; ++r) {
+        if (x.g_err_row >= 0) { x.g_cuts[r] = 0; x.g_nnz[r] = 0; continue; }
+        c += x.g_cuts[r]; z += x.g_nnz[r];
+        if (hd[8 * r + 2] != ~0ull) x.g_err_row = (int64_t)(hd[8 * r + 2] - 1ull) + (int64_t)hd[8 * r + 4];
+    }
     if (total_cuts) *total_cuts = c;
     if (total_nnz) *total_nnz = z;
+    return x.g_err_row >= 0 ? KTN_NUMERIC_NONFINITE : KTN_OK;
+}
+
+extern "C" int ktn_gathered_error_row(ktn_handle* h, int64_t* err_row) {
+    if (!h || !h->comm || !err_row) return fail(h, KTN_ERR_USAGE, "no communicator");
+    *err_row = h->xch[h->xch_cur].g_err_row;
     return KTN_OK;
 }
 
 // Unpacks the gathered blobs of the LAST exchange into one CSR; row ids are global (K2 applied each rank's row offset).
 extern "C" int ktn_fetch_gathered(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val,
                                   double* lo, double* hi, double* g, double* viol, double* bconst) {
-    int rc = ktn_sync_gathered(h, nullptr, nullptr); if (rc) return rc;
+    const int status = ktn_sync_gathered(h, nullptr, nullptr); if (status < 0) return status;
     ktn_handle::Exchange& x = h->xch[h->xch_cur];
     // every rank's blob at its real size (the slots are larger: worst case, or the largest blob)
     const unsigned char* base = h->px.on ? h->px.arena.as<unsigned char>() + KTN_PX_CTRL + (size_t)h->xch_cur * h->nranks * h->px.slot_cap
@@ -569,5 +589,5 @@ extern "C" int ktn_fetch_gathered(ktn_handle* h, int64_t* row_id, int64_t* row_p
         if (val) memcpy(val + zo, b + L.val, 8 * (size_t)nz);
         co += n; zo += nz;
     }
-    return KTN_OK;
+    return status;
 }

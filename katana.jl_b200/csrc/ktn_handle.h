@@ -32,6 +32,7 @@ struct ktn_handle {
     cudaEvent_t ring[RING][4];
     int ring_head = 0, ring_tail = 0;      // [tail, head) not yet drained
     double eval_ms_sum = 0, compact_ms_sum = 0, cut_ms_sum = 0; int64_t rounds_timed = 0;
+    double exchange_ms_sum = 0; int64_t exchanges_timed = 0;
     KtnProblem prob;
     bool loading = false, loaded = false, round_pending = false, have_round = false;
     DevBuf chunks, shapes, prog, blob, chunk_rows, chunk_lb, chunk_ub, jac_ptr, jac_col, row_lb, row_ub, row_slot, rec, worklist, errpos, blk_off, chunk_jp, dump;
@@ -56,7 +57,9 @@ struct ktn_handle {
     struct Exchange {
         DevBuf gathered, all_counts;
         unsigned long long* h_all_counts = nullptr;     // pinned [8 * nranks]: the blob headers of all ranks
-        std::vector<int64_t> g_cuts, g_nnz, g_off;      // per rank, once the headers are on the host
+        std::vector<int64_t> g_cuts, g_nnz, g_off;      // per rank, once the headers are on the host (ranks behind the first non-finite cut: 0)
+        int64_t g_err_row = -1;                         // global index of the first non-finite row of the gathered batch (-1: none)
+        cudaEvent_t t0 = nullptr, t1 = nullptr;         // around the exchange's transfer on the exchange stream (exchange_ms)
         std::vector<int64_t> g_lay_cuts, g_lay_nnz, g_bytes;   // layout arguments and size of every rank's blob
         int src_idx = 0;                                // which of the handle's cut blobs this exchange ships
         cudaEvent_t packed = nullptr, sizes = nullptr;    // the round's K2 has finished; the headers of all ranks are on the host

@@ -504,5 +504,6 @@ int ktn_set_row_offset(ktn_handle* h, int64_t r) { (void)r; return fail(h, KTN_E
 int ktn_allgather_cuts_async(ktn_handle* h) { return fail(h, KTN_ERR_UNSUPPORTED, "oracle is single process"); }
 int ktn_exchange_transport(ktn_handle* h) { (void)h; return 0; }
 int ktn_sync_gathered(ktn_handle* h, int64_t* a, int64_t* b) { (void)a; (void)b; return fail(h, KTN_ERR_UNSUPPORTED, "oracle is single process"); }
+int ktn_gathered_error_row(ktn_handle* h, int64_t* e) { (void)e; return fail(h, KTN_ERR_UNSUPPORTED, "oracle is single process"); }
 int ktn_fetch_gathered(ktn_handle* h, int64_t* a, int64_t* b, int32_t* c, double* d, double* e, double* f, double* g, double* v, double* w) {
     (void)w; (void)a; (void)b; (void)c; (void)d; (void)e; (void)f; (void)g; (void)v; return fail(h, KTN_ERR_UNSUPPORTED, "oracle is single process"); }

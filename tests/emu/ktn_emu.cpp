@@ -257,6 +257,7 @@ int ktn_set_row_offset(ktn_handle*, int64_t) { return KTN_ERR_UNSUPPORTED; }
 int ktn_allgather_cuts_async(ktn_handle*) { return KTN_ERR_UNSUPPORTED; }
 int ktn_exchange_transport(ktn_handle*) { return 0; }
 int ktn_sync_gathered(ktn_handle*, int64_t*, int64_t*) { return KTN_ERR_UNSUPPORTED; }
+int ktn_gathered_error_row(ktn_handle*, int64_t*) { return KTN_ERR_UNSUPPORTED; }
 int ktn_fetch_gathered(ktn_handle*, int64_t*, int64_t*, int32_t*, double*, double*, double*, double*, double*, double*) { return KTN_ERR_UNSUPPORTED; }
 }
 extern "C" int ktn_emu_shape_info(ktn_handle* h, int64_t sid, uint32_t* out /* n_fwd, n_ins, n_uniq, n_const, n_scratch, flags */) {
