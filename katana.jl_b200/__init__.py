@@ -6,7 +6,7 @@ directory, whose name is not a valid Python identifier, under that module name).
 from . import binding, expr  # noqa: F401
 from .binding import CutBatch, KtnError, KtnLibrary, WireRows, load_cuda_library  # noqa: F401
 from .lp import HighsLP  # noqa: F401
-from .model import KatanaNonlinearModel, getKatanaCuts, getKatanaSols  # noqa: F401
+from .model import KatanaNonlinearModel  # noqa: F401
 from .nlpeval import EpigraphNLPEvaluator, ExprNLPEvaluator  # noqa: F401
 from .separators import AbstractKatanaSeparator, AffExpr, KatanaGPUSeparator, linear_oa_cut  # noqa: F401
 from .solver import KatanaSolver, LinearQuadraticModel, Model, NonlinearModel, getKatanaModel  # noqa: F401

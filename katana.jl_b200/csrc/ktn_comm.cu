@@ -124,83 +124,7 @@ __global__ void __launch_bounds__(512) ktn_push_kernel(const KtnPushParams q) {
     if (threadIdx.x == 0) *q.ctr = 0;
 }
 
-#ifdef KTN_OPT_PUSH_TMA
-// EXPERIMENT (round 2, not part of the default build): the same push with the copy engines of the SM instead of its load/store
-// units.  One warp per CTA; lane 0 streams the blob through a ring of KTN_PT_STAGES shared-memory tiles: a bulk copy
-// global -> shared per tile (mbarrier completion), then one bulk copy shared -> peer global per destination (bulk async-group).
-// A handful of CTAs should saturate NVLink, so K1 keeps (almost) all SMs.  Flow control and header publication are the
-// load/store kernel's.
-#define KTN_PT_TILE 32768u
-#define KTN_PT_STAGES 4u
-__device__ __forceinline__ uint32_t pt_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__global__ void __launch_bounds__(32) ktn_push_tma_kernel(const KtnPushParams q) {
-    extern __shared__ __align__(128) unsigned char pt_tiles[];                      // [KTN_PT_STAGES][KTN_PT_TILE], then the mbarriers
-    uint64_t* bar = reinterpret_cast<uint64_t*>(pt_tiles + KTN_PT_STAGES * KTN_PT_TILE);
-    const unsigned lane = threadIdx.x;
-    __shared__ int s_flag;
-    if (lane == 0) {
-        s_flag = 0;
-        for (unsigned s = 0; s < KTN_PT_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pt_smem(bar + s)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    if (lane < (unsigned)q.nranks) {
-        if (blockIdx.x == 0) st_sys(q.ack_dst[lane], q.seq);
-        if (q.seq > KTN_PX_SLOTS) {
-            const unsigned long long need = q.seq - KTN_PX_SLOTS + 1, t0 = now_ns();
-            while (ld_sys(q.ack_local + lane) < need) { if (now_ns() - t0 > KTN_PX_TIMEOUT_NS) { s_flag = 1; break; } __nanosleep(200); }
-        }
-    }
-    __syncwarp();
-    if (s_flag) { if (lane == 0) atomicOr(q.ctr + 1, 1u); return; }
-    const unsigned long long* hd = reinterpret_cast<const unsigned long long*>(q.src);
-    const unsigned long long total = hd[3];
-    if (lane == 0 && total > 64) {
-        const unsigned long long ntiles = (total - 64 + KTN_PT_TILE - 1) / KTN_PT_TILE;
-        const unsigned long long mine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;       // tiles blockIdx.x, + gridDim.x, ...
-        auto tile_off = [&](unsigned long long i) { return 64ull + (blockIdx.x + i * gridDim.x) * (unsigned long long)KTN_PT_TILE; };
-        auto tile_len = [&](unsigned long long i) { const unsigned long long o = tile_off(i); return (uint32_t)(total - o < KTN_PT_TILE ? total - o : KTN_PT_TILE); };
-        auto load = [&](unsigned long long i) {
-            const unsigned s = (unsigned)(i % KTN_PT_STAGES); const uint32_t n = tile_len(i);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pt_smem(bar + s)), "r"(n) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(pt_smem(pt_tiles + s * KTN_PT_TILE)), "l"(q.src + tile_off(i)), "r"(n), "r"(pt_smem(bar + s)) : "memory");
-        };
-        for (unsigned long long i = 0; i < mine && i < KTN_PT_STAGES - 1; ++i) load(i);
-        for (unsigned long long i = 0; i < mine; ++i) {
-            const unsigned s = (unsigned)(i % KTN_PT_STAGES); const uint32_t parity = (uint32_t)((i / KTN_PT_STAGES) & 1u), n = tile_len(i);
-            uint32_t done = 0;
-            while (!done) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(pt_smem(bar + s)), "r"(parity) : "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            for (int k = 0; k < q.nranks; ++k) {
-                int r = q.rank + 1 + k; if (r >= q.nranks) r -= q.nranks;
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(q.dst[r] + tile_off(i)), "r"(pt_smem(pt_tiles + s * KTN_PT_TILE)), "r"(n) : "memory");
-            }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            // the tile loaded next goes into the stage of tile i - 1: its stores (the group before this one) must have read it
-            if (i + KTN_PT_STAGES - 1 < mine) {
-                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                load(i + KTN_PT_STAGES - 1);
-            }
-        }
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");                    // all stores of this CTA are complete
-        asm volatile("fence.proxy.async;" ::: "memory");
-    }
-    __syncwarp();
-    __threadfence_system();
-    if (lane == 0) s_flag = (atomicAdd(q.ctr, 1u) == gridDim.x - 1) ? 2 : 0;
-    __syncwarp();
-    if (s_flag != 2) return;
-    __threadfence_system();
-    if (lane < (unsigned)q.nranks) {
-        unsigned long long* d = reinterpret_cast<unsigned long long*>(q.dst[lane]);
-        for (int k = 0; k < 7; ++k) st_sys(d + k, hd[k]);
-        __threadfence_system();
-        st_sys(d + 7, q.seq);
-    }
-    if (lane == 0) *q.ctr = 0;
-}
-#endif
+
 
 // Waits (on the exchange stream) until the headers of exchange `seq` from all ranks have landed in this rank's arena, and copies
 // them out: hdr[8 * r + k], then the error word.
@@ -384,16 +308,7 @@ static int peer_exchange(ktn_handle* h, size_t my_cap) {
     q.ack_local = px.arena.as<unsigned long long>(); q.src = h->out_blob[x.src_idx].as<unsigned char>(); q.seq = seq;
     q.ctr = px.ctr.as<unsigned int>(); q.nranks = h->nranks; q.rank = h->rank;
     CK(h, cudaEventRecord(x.t0, h->comm_stream));
-#ifdef KTN_OPT_PUSH_TMA
-    {
-        static bool attr = false;
-        const int smem = (int)(KTN_PT_STAGES * KTN_PT_TILE + 64);
-        if (!attr) { CK(h, cudaFuncSetAttribute(ktn_push_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-        ktn_push_tma_kernel<<<px.blocks, 32, smem, h->comm_stream>>>(q);
-    }
-#else
     ktn_push_kernel<<<px.blocks, 512, 0, h->comm_stream>>>(q);
-#endif
     CK(h, cudaGetLastError());
     CK(h, cudaEventRecord(x.t1, h->comm_stream));
     h->tm.launches += 1;

@@ -382,7 +382,10 @@ __global__ void __launch_bounds__(512, 1) ktn_round_kernel(const KtnRoundParams 
                 }
                 if (row >= 0) p.sel[row] = selv;
             }
-            __syncwarp();   // every lane is done with the blob before the next bulk copy overwrites it
+            // the reverse sweep wrote Jacobian accumulators into the blob through the generic proxy; the next bulk copy writes the same
+            // bytes through the async proxy: order the two (PTX: fence.proxy.async), then make sure every lane is done with the blob
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
         }
         c_cur = c_nxt; cd = cdn; have = have_nxt;
         c_nxt = p.chunk_begin + __shfl_sync(0xffffffffu, c_n2, 0);

@@ -203,7 +203,9 @@ class KatanaNonlinearModel:                                    # src/model.jl:9-
             max_viol = max(max_viol, cuts_viol)                # :284
             cuts_lastprnt += cuts_viol
             obj = lm.getobjval()                               # :287
-            obj_delta = abs((obj_prev - obj) / obj) if obj != 0 else (0.0 if obj_prev == obj else math.inf)
+            # IEEE division as in Julia: 0/0 = NaN (NaN <= obj_eps is false: the loop goes on), x/0 = Inf
+            with np.errstate(divide="ignore", invalid="ignore"):
+                obj_delta = float(np.abs((np.float64(obj_prev) - np.float64(obj)) / np.float64(obj)))
             obj_prev = obj
             if self.params.log_level > 0:                      # :291-303
                 r = self.iter % self.params.log_level
@@ -239,18 +241,3 @@ class KatanaNonlinearModel:                                    # src/model.jl:9-
     def getobjval(self): return self.linear_model.getobjval()
     def getsolution(self): return self.linear_model.getsolution()
     def getsolvetime(self): return self.soltime
-
-
-# src/util.jl:3-36
-def getKatanaCuts(m):
-    M, N = len(m.linear_cuts), m.num_var + 2
-    table = np.zeros((M, N))
-    for i, (cols, vals, lo, hi) in enumerate(m.linear_cuts):
-        np.add.at(table[i], cols, vals)
-        table[i, -2] = hi if np.isfinite(hi) else lo
-        table[i, -1] = -1 if np.isfinite(hi) else 1
-    return table
-
-
-def getKatanaSols(m):
-    return m.lp_sols

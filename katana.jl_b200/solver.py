@@ -85,8 +85,8 @@ class Model:
         m = self.internal = NonlinearModel(self.solver)
         m.loadproblem(len(self.lb), len(allc), np.array(self.lb), np.array(self.ub),
                       np.array([c[1] for c in allc], dtype=float), np.array([c[2] for c in allc], dtype=float), self.sense, d)
-        if m.status == "Error":
-            return m.status
+        # the reference proceeds into optimize! whatever loadproblem! left in m.status (src/solver.jl:34-43 -> src/model.jl:219):
+        # optimize! ends by overwriting it
         return m.optimize()
 
     def getobjectivevalue(self):
