@@ -1,21 +1,27 @@
 # gpu_separator.jl -- the reference-side binding of the B200 separation library (libktn.so, include/ktn.h).
 #
-# A Katana.jl maintainer adds this file to src/ and `include`s it from src/Katana.jl after separators.jl.  It is the code of
-# INTEGRATION.md sections 3, 4 and 6 verbatim (tests/test_abi.py keeps the two in step and checks every ccall name against the
-# exported symbols).  NOT executed in this repository: the build image has no julia binary.
+# A Katana.jl maintainer adds this file to src/ and `include`s it from src/Katana.jl after separators.jl and nlpeval.jl.  It is the
+# code of INTEGRATION.md sections 3, 4 and 6 verbatim (tests/test_abi.py keeps the two in step and checks every ccall name and
+# argument count against the header and the exported symbols; tests/test_julia_shim_rules.py runs the shim's flattening rules,
+# ported 1:1 to Python, through the C ABI on the reference's test problems).  NOT executed in this repository: the build image
+# has no julia binary.
 #
 mutable struct KatanaGPUSeparator <: AbstractKatanaSeparator
     handle :: Ptr{Cvoid}
     num_var :: Int
     num_constr :: Int
+    ngpus :: Int                    # > 1: the ONE separator shards its rows over that many devices of this process
+    linear_model                    # JuMP model the cuts' variables belong to (src/separators.jl:62,86)
+    cols :: Vector{Vector{Int}}     # per row: Jacobian columns, 1-based (the reference's sp_cols, src/separators.jl:92-100)
     xstar :: Vector{Float64}
     g :: Vector{Float64}            # filled lazily for the per-row isconstrsat hook
     have_g :: Bool
-    KatanaGPUSeparator() = new(C_NULL, 0, 0, Float64[], Float64[], false)
+    KatanaGPUSeparator(; ngpus = 1) = new(C_NULL, 0, 0, ngpus, nothing, Vector{Int}[], Float64[], Float64[], false)
 end
 
 struct KtnOptions            # include/ktn.h: ktn_options
     struct_size::Int32; device::Int32; f_tol::Float64; cut_coef_rng::Float64; topk::Int64; flags::Int32; reserved::Int32
+    ngpus::Int32; devices::NTuple{16, Int32}
 end
 
 struct KtnCutView            # include/ktn.h: ktn_cut_view
@@ -30,7 +36,7 @@ check(sep, rc, what) = rc < 0 && error("$what failed ($rc): " *
 # op codes of the wire format (include/ktn.h KTN_OP_*)
 const KTN_OPS = Dict(:+ => 2, :- => 3, :* => 4, :/ => 5, :^ => 6, :exp => 8, :log => 9, :sqrt => 10, :abs => 11)
 
-# Flatten one MathProgBase constraint expression `lhs <= / >= / == rhs` (an Expr tree over x[i]) into prefix arrays.
+# Flatten one expression tree over x[i] (MathProgBase constr_expr / obj_expr) into prefix arrays.
 function flatten!(op::Vector{Int32}, arg::Vector{Int32}, val::Vector{Float64}, ex)
     if ex isa Number
         push!(op, 0); push!(arg, 0); push!(val, Float64(ex))
@@ -49,27 +55,47 @@ function flatten!(op::Vector{Int32}, arg::Vector{Int32}, val::Vector{Float64}, e
     end
 end
 
+# The body g_i(x) of a MathProgBase constraint expression: `body <= rhs`, `body >= rhs`, `body == rhs` are :call nodes with the
+# body first; a two-sided row `lb <= body <= ub` is a :comparison node with the body in the middle.  Bounds travel separately.
+constr_body(c::Expr) = c.head == :comparison ? c.args[3] : c.args[2]
+
+# The epigraph wrapper hands out expression graphs too (src/nlpeval.jl:23 advertises [:Grad, :Jac] only): rows 1 .. num_constr - 1
+# are the wrapped evaluator's, the last row is f(x[1:n]) - x[n+1] (src/nlpeval.jl:35,42-45) and is never linear.
+MathProgBase.features_available(d::EpigraphNLPEvaluator) = [:Grad, :Jac, :ExprGraph]
+MathProgBase.constr_expr(d::EpigraphNLPEvaluator, i) = i < d.num_constr ? MathProgBase.constr_expr(d.nlpeval, i) :
+    Expr(:call, :<=, Expr(:call, :-, MathProgBase.obj_expr(d.nlpeval), Expr(:ref, :x, d.num_var)), 0.0)
+MathProgBase.isconstrlinear(d::EpigraphNLPEvaluator, i) = i < d.num_constr && MathProgBase.isconstrlinear(d.nlpeval, i)
+
 # initialize!(sep, linear_model, num_var, num_constr, oracle)           -- src/separators.jl:81-107
 function initialize!(sep::KatanaGPUSeparator, linear_model, num_var::Int, num_constr::Int, oracle)
     MathProgBase.initialize(oracle, [:ExprGraph])              # the separator initialises the oracle itself (:88)
     if sep.handle == C_NULL                                    # one separator is reused across models (test/runtests.jl:24)
-        o = Ref(KtnOptions(sizeof(KtnOptions), -1, 1e-6, 1e9, 0, 0, 0)); h = Ref{Ptr{Cvoid}}(C_NULL)
+        o = Ref(KtnOptions(sizeof(KtnOptions), -1, 1e-6, 1e9, 0, 1, 0, sep.ngpus > 1 ? sep.ngpus : 0, ntuple(_ -> Int32(-1), 16)))   # flags = 1: lean views
+        h = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:ktn_create, libktn), Cint, (Ref{KtnOptions}, Ref{Ptr{Cvoid}}), o, h)
         rc == 0 || error("ktn_create failed ($rc): no B200 / CUDA device?")
         sep.handle = h[]
     end
     check(sep, ccall((:ktn_load_begin, libktn), Cint, (Ptr{Cvoid}, Int64, Int64), sep.handle, num_var, num_constr), "ktn_load_begin")
     op, arg, val, eptr = Int32[], Int32[], Float64[], Int64[0]
+    flags = zeros(UInt8, num_constr)
+    dense_row = oracle isa EpigraphNLPEvaluator ? num_constr : 0          # its Jacobian row lists every column (src/nlpeval.jl:49-54)
     for i in 1:num_constr
-        c = MathProgBase.constr_expr(oracle, i)                # :(lhs <= rhs) etc.; only lhs is compiled, bounds travel separately
-        flatten!(op, arg, val, c.args[2]); push!(eptr, length(op))
+        flatten!(op, arg, val, constr_body(MathProgBase.constr_expr(oracle, i))); push!(eptr, length(op))
+        # KTN_ROW_NL = the rows optimize! tests every round: those loadproblem! keeps in nlconstr_ixs (src/model.jl:116-121, :148)
+        flags[i] = (MathProgBase.isconstrlinear(oracle, i) ? 0x00 : 0x01) | (i == dense_row ? 0x02 : 0x00)
     end
     lb, ub = fill(-Inf, num_constr), fill(Inf, num_constr)     # real bounds arrive through set_bounds!
-    flags = fill(UInt8(1), num_constr)                         # KTN_ROW_NL; the epigraph row (nlpeval.jl) adds KTN_ROW_DENSE = 2
     check(sep, ccall((:ktn_add_rows, libktn), Cint,
           (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}),
           sep.handle, 0, num_constr, eptr, op, arg, val, lb, ub, flags), "ktn_add_rows")
     check(sep, ccall((:ktn_load_end, libktn), Cint, (Ptr{Cvoid},), sep.handle), "ktn_load_end")
+    rp = Vector{Int64}(undef, num_constr + 1)
+    check(sep, ccall((:ktn_jac_structure, libktn), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int32}), sep.handle, rp, C_NULL), "ktn_jac_structure")
+    jc = Vector{Int32}(undef, rp[end])
+    check(sep, ccall((:ktn_jac_structure, libktn), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int32}), sep.handle, rp, jc), "ktn_jac_structure")
+    sep.cols = [Int.(jc[rp[i] + 1:rp[i + 1]]) .+ 1 for i in 1:num_constr]
+    sep.linear_model = linear_model
     sep.num_var, sep.num_constr = num_var, num_constr
     sep.g = zeros(num_constr); sep.have_g = false
 end
@@ -98,13 +124,24 @@ function isconstrsat(sep::KatanaGPUSeparator, i, lb, ub, f_tol)                 
 end
 function gencut(sep::KatanaGPUSeparator, xstar, bounds, i)                                        # src/separators.jl:118
     rows = Int64[i - 1]; nc, nz, er = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0)
-    check(sep, ccall((:ktn_gencut_rows, libktn), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int64, Cint, Ref{Int64}, Ref{Int64}, Ref{Int64}),
-          sep.handle, xstar, rows, 1, 0, nc, nz, er), "ktn_gencut_rows")
-    v = Ref{KtnCutView}(); ccall((:ktn_fetch_cuts_view, libktn), Cint, (Ptr{Cvoid}, Ref{KtnCutView}), sep.handle, v)
-    cols = unsafe_wrap(Array, v[].col, v[].nnz) .+ 1; vals = unsafe_wrap(Array, v[].val, v[].nnz)
-    AffExpr([Variable(sep.linear_model, j) for j in cols], copy(vals), unsafe_load(v[].bconst))
+    st = ccall((:ktn_gencut_rows, libktn), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int64, Cint, Ref{Int64}, Ref{Int64}, Ref{Int64}),
+               sep.handle, xstar, rows, 1, 0, nc, nz, er)
+    check(sep, st, "ktn_gencut_rows")
+    vars = [Variable(sep.linear_model, j) for j in sep.cols[i]]
+    # a non-finite coefficient (status 1: the row yields no cut): hand _addcut NaN coefficients, so that ITS finiteness test sets
+    # m.status = :Error and warns, exactly as with the reference separator (src/model.jl:69-73)
+    (st == 1 || nc[] != 1) && return AffExpr(vars, fill(NaN, length(vars)), NaN)
+    vals = Vector{Float64}(undef, nz[]); b = Vector{Float64}(undef, 1)     # a full (not lean) fetch: bconst is needed here
+    check(sep, ccall((:ktn_fetch_cuts, libktn), Cint,
+          (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+          sep.handle, C_NULL, C_NULL, C_NULL, vals, C_NULL, C_NULL, C_NULL, C_NULL, b), "ktn_fetch_cuts")
+    AffExpr(vars, vals, b[1])
 end
 
+# loadproblem! (src/model.jl:172), right after `initialize!(sep, m.linear_model, m.num_var, m.num_constr, d)`:
+set_bounds!(m.params.separator, m.l_constr, m.u_constr)   # bounds are model state (src/model.jl:273-277): handed over once
+
+# optimize! (src/model.jl:265-283), instead of the per-row isconstrsat / gencut / round_coefs / _addcut loop:
 xstar = MathProgBase.getsolution(mpb_lp)
 st, v = separate!(m.params.separator, xstar)             # precompute! + test + cuts, ascending row order
 colv = unsafe_wrap(Array, v.col, v.nnz); valv = unsafe_wrap(Array, v.val, v.nnz)
@@ -120,7 +157,8 @@ if st == 1                                                # non-finite coefficie
 end
 allsat = v.n_cuts == 0
 
-# Sharded rounds: one process per GPU (e.g. Distributed.jl workers), rank r of nranks owns rows [row_begin, row_end).
+# Sharded rounds, one process per GPU (e.g. Distributed.jl workers): rank r of nranks owns rows [row_begin, row_end).
+# (Inside ONE process, `KatanaGPUSeparator(ngpus = 8)` above needs none of this: ktn_options.ngpus.)
 # `id` is the 128-byte communicator id made on rank 0 (ktn_comm_unique_id) and sent to the others by the host's own means.
 function comm_unique_id()
     id = zeros(UInt8, 128)
@@ -135,17 +173,19 @@ function join_shards!(sep::KatanaGPUSeparator, nranks::Integer, rank::Integer, i
 end
 
 # One sharded round: separate this rank's rows at x*, exchange, and return ALL ranks' cuts (global row ids, ascending) as CSR.
+# The status is the same on every rank: 1 = some rank met a non-finite cut; the batch ends at that row (err_row, 1-based).
 function separate_sharded(sep::KatanaGPUSeparator, xstar::Vector{Float64})
     nc = Ref{Int64}(0); nz = Ref{Int64}(0); er = Ref{Int64}(-1)
-    st = ccall((:ktn_separate, libktn), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Int64}, Ref{Int64}, Ref{Int64}), sep.handle, xstar, nc, nz, er)
-    check(sep, st, "ktn_separate")
+    check(sep, ccall((:ktn_separate, libktn), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Int64}, Ref{Int64}, Ref{Int64}), sep.handle, xstar, nc, nz, er), "ktn_separate")
     check(sep, ccall((:ktn_allgather_cuts_async, libktn), Cint, (Ptr{Cvoid},), sep.handle), "ktn_allgather_cuts_async")
-    check(sep, ccall((:ktn_sync_gathered, libktn), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), sep.handle, nc, nz), "ktn_sync_gathered")
+    st = ccall((:ktn_sync_gathered, libktn), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), sep.handle, nc, nz)
+    check(sep, st, "ktn_sync_gathered")
+    check(sep, ccall((:ktn_gathered_error_row, libktn), Cint, (Ptr{Cvoid}, Ref{Int64}), sep.handle, er), "ktn_gathered_error_row")
     n, z = nc[], nz[]
     row = Vector{Int64}(undef, n); ptr = Vector{Int64}(undef, n + 1); col = Vector{Int32}(undef, z); val = Vector{Float64}(undef, z)
     lo = Vector{Float64}(undef, n); hi = Vector{Float64}(undef, n)
     check(sep, ccall((:ktn_fetch_gathered, libktn), Cint,
                      (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                      sep.handle, row, ptr, col, val, lo, hi, C_NULL, C_NULL, C_NULL), "ktn_fetch_gathered")
-    return st, row .+ 1, ptr .+ 1, col .+ Int32(1), val, lo, hi          # 1-based for Julia; st == 1: a rank met a non-finite cut (:Error)
+    return st, er[] + 1, row .+ 1, ptr .+ 1, col .+ Int32(1), val, lo, hi          # 1-based for Julia
 end
