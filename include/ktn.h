@@ -230,7 +230,8 @@ int ktn_fetch_gathered(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t
 int ktn_gathered_error_row(ktn_handle* h, int64_t* err_row);
 
 /* ---- deterministic synthetic instances (test / bench support) ----
- * kind: 0 = sparse convex QCQP (config 2), 1 = log-sum-exp (config 3), 2 = SOC-like risk rows (config 4).
+ * kind: 0 = sparse convex QCQP (config 2), 1 = log-sum-exp (config 3), 2 = SOC-like risk rows (config 4), 3 = portfolio (config 4 at
+ * size: nine sparse linear rows, not flagged KTN_ROW_NL, for every SOC-like row).
  * Two-call protocol: call with op = NULL to get *n_nodes, then with caller buffers
  * (expr_ptr: nrows+1, op/arg/val: n_nodes, lb/ub: nrows, flags: nrows, xstar: num_var).
  * Rows [row_begin, row_begin+nrows) of the instance (num_var, seed) are produced; a row's

@@ -455,6 +455,14 @@ int KtnProblem::add_rows(int64_t first_row, int64_t nrows, const int64_t* eptr, 
                         is(5, KR_TERMS, KTN_T_MULC_X | KTN_TF_JACC, nu, nu, 0) && code[6].op == K_END)
                         sd.family = KTN_FAM_QUAD;
                 }
+                // sqrt(sum_{u < nu-1} (s_u x_u)^2) - x_{nu-1}: the linear variable is the row's LAST unique variable and none of the squared ones
+                if (!no_family && !sd.j_in_blob && (sd.flags & KTN_SH_NL) && nu >= 2 && nu <= 256 && sd.n_const == nu - 1 && code.size() == 13 &&
+                    is(0, KF_TERMS, KTN_T_SQ_MULC | KTN_TF_FIRST, nu - 1, 0, 0) && code[1].op == KF_SQRT && code[2].op == KF_STORE && code[2].kind == KTN_K_S &&
+                    code[3].op == KF_SUB && code[3].kind == KTN_K_S && code[3].idx == nu - 1 && code[4].op == KR_ONE && code[5].op == KF_STORE && code[5].kind == KTN_K_R1 &&
+                    code[6].op == KR_MULHRCP && code[6].kind == KTN_K_S && code[6].idx == code[2].idx && code[7].op == KF_STORE && code[7].kind == KTN_K_R2 &&
+                    is(8, KR_TERMS, KTN_T_SQ_MULC, nu - 1, 0, 0) && code[9].op == KF_LOAD && code[9].kind == KTN_K_R1 && code[10].op == KR_NEG &&
+                    code[11].op == KR_JSET && code[11].idx == nu - 1 && code[12].op == K_END)
+                    sd.family = KTN_FAM_SOC;
             }
             sd.prog_off = (uint32_t)prog.size();
             prog.insert(prog.end(), code.begin(), code.end());
@@ -499,6 +507,8 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
         for (auto& s : shapes) if (!(s.flags & KTN_SH_BIG)) tb += (size_t)s.n_ins * sizeof(KtnIns);
         if (tb > table_limit) for (auto& s : shapes) s.flags |= KTN_SH_BIG;
     }
+    // a shape the global-scratch kernel runs is interpreted: it is no family shape (its chunks carry the interpreter's sort order)
+    for (auto& s : shapes) if (s.flags & KTN_SH_BIG) s.family = KTN_FAM_GENERIC;
     for (auto& s : shapes) if (!(s.flags & KTN_SH_BIG)) max_lane_bytes = std::max(max_lane_bytes, ktn_shape_lane_bytes(s));
     chunks.clear(); blob.clear(); chunk_rows.clear(); big_scratch_doubles = 0;
     std::vector<std::pair<uint32_t, int32_t>> win;  // (shape, row)
@@ -527,7 +537,8 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
             if (rankword) {      // family rows of <= 16 unique variables
                 for (uint32_t u = 0; u < s.n_uniq; ++u) {
                     double* pr = (double*)(base + KTN_FAM_PAIR_AT(u, lane));
-                    pr[0] = rc[ktn_family_slot(s.family, 0, u, s.n_uniq)]; pr[1] = rc[ktn_family_slot(s.family, 1, u, s.n_uniq)];
+                    const uint32_t s0 = ktn_family_slot(s.family, 0, u, s.n_uniq), s1 = ktn_family_slot(s.family, 1, u, s.n_uniq);
+                    pr[0] = s0 == KTN_FAM_NOSLOT ? 0.0 : rc[s0]; pr[1] = s1 == KTN_FAM_NOSLOT ? 0.0 : rc[s1];
                     *(int32_t*)(base + KTN_FAM_COL_AT(s.n_uniq, u, lane)) = rcol[u];
                 }
                 uint64_t w = 0; for (uint32_t p = 0; p < s.n_uniq; ++p) w |= (uint64_t)p << (4 * rord[p]);      // rank word: 4 bits per unique variable = its Jacobian entry index

@@ -9,7 +9,8 @@
 // (src/model.jl:200-207) and _addcut's finiteness test (src/model.jl:69) for the selected rows.
 //
 // Data of one family row (chunk blob, lane stride L):
-//   constants   two per unique variable u (LSE: c_u = slot 2u, d_u = slot 2u+1;  QUAD: a_u = slot u, b_u = slot nu+u); rows of
+//   constants   two per unique variable u (LSE: c_u = slot 2u, d_u = slot 2u+1;  QUAD: a_u = slot u, b_u = slot nu+u;  SOC: s_u = slot u,
+//               none for the linear variable); rows of
 //               <= 16 unique variables store them as PAIRS (p0_u, p1_u), 16 bytes per row and variable (ktn_program.h)
 //   cols        column of unique variable u (first-occurrence order = the order of the terms)
 //   rank        position of unique variable u among the row's ascending columns = its Jacobian entry index;
@@ -74,7 +75,7 @@ template <> struct KtnFamily<KTN_FAM_LSE> {
             for (int k = 0; k < 8; ++k) if (!ktn_exp_is_fast(a[k])) p1[k] = ktn_exp_slow(a[k]);
         }
     }
-    static KTN_HDM double entry(double adj, double c, double e, double x, bool exact) { return exact ? jac(adj, c, e, x) : jac_plain(adj, c, e, x); }
+    static KTN_HDM double entry(double adj, double c, double e, double x, bool exact, uint32_t, uint32_t) { return exact ? jac(adj, c, e, x) : jac_plain(adj, c, e, x); }
     // streaming fallback (any nu)
     template <class R> static KTN_HDM double forward_stream(const R& r, double& aux) {
         double acc = 0.0;
@@ -104,7 +105,7 @@ template <> struct KtnFamily<KTN_FAM_QUAD> {
     static KTN_HDM double jac(double adj, double a, double b, double x) { return (0.0 + revmul(revmul(adj, a), 2.0 * x)) + revmul(adj, b); }
     static KTN_HDM double jac_plain(double adj, double a, double b, double x) { return (0.0 + (adj * a) * (2.0 * x)) + adj * b; }
     static KTN_HDM void pre8(const double (&)[8], double (&)[8], const double (&)[8]) {}
-    static KTN_HDM double entry(double adj, double a, double b, double x, bool exact) { return exact ? jac(adj, a, b, x) : jac_plain(adj, a, b, x); }
+    static KTN_HDM double entry(double adj, double a, double b, double x, bool exact, uint32_t, uint32_t) { return exact ? jac(adj, a, b, x) : jac_plain(adj, a, b, x); }
     template <class R> static KTN_HDM double forward_stream(const R& r, double& aux) {
         double acc = 0.0;
         for (uint32_t u = 0; u < r.nu; ++u) { const double x = r.x(u); acc = acc + (x * x) * r.cst(u); }
@@ -113,6 +114,39 @@ template <> struct KtnFamily<KTN_FAM_QUAD> {
         return acc;
     }
     template <class R> static KTN_HDM double jac_stream(const R& r, uint32_t u, double adj) { return jac(adj, r.cst(u), r.cst(r.nu + u), r.x(u)); }
+};
+
+// sqrt(sum_{u < nu-1} (s_u * x_u)^2) - x_{nu-1}
+// Program: KF_TERMS(SQ_MULC, FIRST); SQRT; STORE S; SUB x_t | KR_ONE; STORE R1; MULHRCP S; STORE R2; KR_TERMS(SQ_MULC); LOAD R1; NEG; JSET t; END
+// At a point where every squared term vanishes the root is 0, its partial 0.5 / 0 is infinite and the coefficients are NaN: the
+// row ends the batch, as in the reference (src/model.jl:69-73; test/3d.jl:153-171 starts away from the apex for that reason).
+template <> struct KtnFamily<KTN_FAM_SOC> {
+    template <int N> static KTN_HDM double forward(KtnFamRegs<N>& r, double& aux) {
+        double acc = 0.0;
+#pragma unroll
+        for (int u = 0; u < N - 1; ++u) { const double q = r.p0[u] * r.x[u]; acc = acc + q * q; }
+        const double s = ktn_sqrt(acc);
+        aux = s;
+        return s - r.x[N - 1];
+    }
+    static KTN_HDM double adjoint(double aux) { return revmul(1.0, 0.5 / aux); }                  // KR_ONE; KR_MULHRCP S
+    static KTN_HDM void pre8(const double (&)[8], double (&)[8], const double (&)[8]) {}
+    static KTN_HDM double entry(double adj, double s, double, double x, bool exact, uint32_t u, uint32_t nu) {
+        if (u + 1 == nu) return 0.0 + (-1.0);                                                     // LOAD R1 (= 1); NEG; JSET
+        return exact ? 0.0 + revmul(revmul(adj, 2.0 * (s * x)), s) : 0.0 + (adj * (2.0 * (s * x))) * s;
+    }
+    template <class R> static KTN_HDM double forward_stream(const R& r, double& aux) {
+        double acc = 0.0;
+        for (uint32_t u = 0; u + 1 < r.nu; ++u) { const double q = r.cst(u) * r.x(u); acc = acc + q * q; }
+        const double s = ktn_sqrt(acc);
+        aux = s;
+        return s - r.x(r.nu - 1);
+    }
+    template <class R> static KTN_HDM double jac_stream(const R& r, uint32_t u, double adj) {
+        if (u + 1 == r.nu) return 0.0 + (-1.0);
+        const double s = r.cst(u);
+        return 0.0 + revmul(revmul(adj, 2.0 * (s * r.x(u))), s);
+    }
 };
 
 // NaN-skipping max / min (one body for host and device: the rounding decision below must not depend on the compiler's fmax)
@@ -154,7 +188,7 @@ KTN_HDM bool ktn_family_cut_terms(const R& r, uint32_t nu, uint64_t rw, S& s, do
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 if (u0 + k < nu) {
-                    const double jv = F::entry(adj, p0[k], p1[k], x[k], exact);
+                    const double jv = F::entry(adj, p0[k], p1[k], x[k], exact, u0 + k, nu);
                     const uint32_t q = (uint32_t)(rw >> (4 * (u0 + k))) & 15u;
                     s.put(q, jv, c[k]); s.put_t(q, (-x[k]) * jv);
                     mx = ktn_dmax(mx, jv); mn = ktn_dmin(mn, jv); anynan = anynan || (jv != jv);

@@ -136,7 +136,8 @@ __device__ __forceinline__ void family_stream_class(const KtnRoundParams& p, uin
         const KtnChunkDesc cd = p.chunks[c];
         const uint32_t nu = (uint32_t)cd.aux;
         const unsigned char* blob = p.blob + cd.blob_off;
-        const FamRow r{reinterpret_cast<const double*>(blob) + lane, reinterpret_cast<const int32_t*>(blob + 512u * nu) + lane, blob + 640u * nu + lane, p.x, nu};
+        const uint32_t sec_col = 256u * KTN_FAM_NCONST((uint32_t)FAM, nu), sec_rk = sec_col + 128u * nu;      // constants | columns | rank bytes
+        const FamRow r{reinterpret_cast<const double*>(blob) + lane, reinterpret_cast<const int32_t*>(blob + sec_col) + lane, blob + sec_rk + lane, p.x, nu};
         double aux;
         const double g = F::forward_stream(r, aux);
         const int32_t row = __ldg(p.chunk_rows + slotid);
@@ -668,7 +669,8 @@ __global__ void __launch_bounds__(KTN_CBLOCK, KTN_CBPS) ktn_compact_kernel(const
         } else {
             const double4 rc = p.rec[i];
             const uint32_t slot = (uint32_t)__ldg(p.row_slot + i), c = slot >> 5, ln = slot & 31u, nu = s_off[k + 1] - s_off[k];
-            const int fam = c >= p.fam_begin[KTN_FAM_QUAD] ? KTN_FAM_QUAD : KTN_FAM_LSE;
+            int fam = KTN_FAM_LSE;
+            while (fam + 1 < KTN_FAM__COUNT && c >= p.fam_begin[fam + 1]) ++fam;      // chunks are sorted by family
             const unsigned char* blob = p.blob + p.cls_blob_off[fam][nu] + (size_t)(c - p.cls_begin[fam][nu]) * KTN_FAM_BLOB_BYTES(nu);
             for (uint32_t gq = 0; gq < KTN_FAM_PGROUPS(nu) + KTN_FAM_CGROUPS(nu); ++gq) prefetch_l2(blob + gq * 1024u + ln * 32u);
             prefetch_l2(blob + KTN_FAM_ORD_OFF(nu) + ln * 8u);
@@ -765,7 +767,8 @@ __global__ void __launch_bounds__(KTN_XBLOCK, KTN_XBPS) ktn_cut_kernel(const Ktn
             CutSink s{staged ? s_val + ((unsigned long long)o - e0) : out_val + o, staged ? s_col + ((unsigned long long)o - e0) : out_col + o, s_t + threadIdx.x};
             double bcst; bool bad;
             if (fam == KTN_FAM_LSE) bad = ktn_family_cut_terms<KTN_FAM_LSE>(r, nu, rw, s, g, aux, p.do_round != 0, p.rng, bcst);
-            else bad = ktn_family_cut_terms<KTN_FAM_QUAD>(r, nu, rw, s, g, aux, p.do_round != 0, p.rng, bcst);
+            else if (fam == KTN_FAM_QUAD) bad = ktn_family_cut_terms<KTN_FAM_QUAD>(r, nu, rw, s, g, aux, p.do_round != 0, p.rng, bcst);
+            else bad = ktn_family_cut_terms<KTN_FAM_SOC>(r, nu, rw, s, g, aux, p.do_round != 0, p.rng, bcst);
             out_lo[cidx] = lb - bcst; out_hi[cidx] = ub - bcst;     // src/model.jl:74-75
             out_b[cidx] = bcst;
             const double v1 = lb - g, v2 = g - ub;
@@ -994,6 +997,7 @@ static int launch_eval_part(const KtnRoundParams& p0, const KtnLaunchPlan& plan,
     }
     if (plan.fam_begin[KTN_FAM_LSE + 1] > plan.fam_begin[KTN_FAM_LSE]) { launch_family<KTN_FAM_LSE>(p, plan, KTN_TICKET_LSE, num_sms, stream); ++launches; }
     if (plan.fam_begin[KTN_FAM_QUAD + 1] > plan.fam_begin[KTN_FAM_QUAD]) { launch_family<KTN_FAM_QUAD>(p, plan, KTN_TICKET_QUAD, num_sms, stream); ++launches; }
+    if (plan.fam_begin[KTN_FAM_SOC + 1] > plan.fam_begin[KTN_FAM_SOC]) { launch_family<KTN_FAM_SOC>(p, plan, KTN_TICKET_SOC, num_sms, stream); ++launches; }
     if (plan.n_total > plan.n_regular) {
         p.chunk_begin = plan.n_regular; p.chunk_end = plan.n_total;
         uint32_t blocks = (plan.n_total - plan.n_regular + 3) / 4;

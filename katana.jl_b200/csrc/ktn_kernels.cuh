@@ -75,7 +75,7 @@ struct KtnLaunchPlan {
     uint64_t cls_blob_off[KTN_FAM__COUNT][KTN_FAM_NCLS];
     uint32_t n_regular, n_total;
 };
-enum { KTN_TICKET_GENERIC = 0, KTN_TICKET_LSE = 8, KTN_TICKET_QUAD = 32, KTN_TICKETS = 64 };
+enum { KTN_TICKET_GENERIC = 0, KTN_TICKET_LSE = 8, KTN_TICKET_QUAD = 32, KTN_TICKET_SOC = 56, KTN_TICKETS = 80 };
 
 // Launches the kernels of one round on `stream`; returns the number of kernels launched.
 int ktn_launch_round(const KtnRoundParams& p, const KtnLaunchPlan& plan, int num_sms,

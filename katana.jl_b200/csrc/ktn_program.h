@@ -90,6 +90,7 @@ enum {
     KTN_FAM_GENERIC = 0,
     KTN_FAM_LSE,        // log(sum_u exp(c_u x_u + d_u))                     (BASELINE.json configs[2])
     KTN_FAM_QUAD,       // sum_u a_u x_u^2 + sum_u b_u x_u                  (BASELINE.json configs[1])
+    KTN_FAM_SOC,        // sqrt(sum_{u<nu-1} (s_u x_u)^2) - x_{nu-1}         (BASELINE.json configs[3], test/3d.jl:161)
     KTN_FAM__COUNT
 };
 
@@ -113,8 +114,13 @@ static inline uint32_t ktn_family_class(uint32_t n_uniq) { return n_uniq <= KTN_
 // byte offset (inside the chunk blob) of the pair / the column of unique variable u of the row in `lane`
 #define KTN_FAM_PAIR_AT(u, lane) (((u) >> 1) * 1024u + (lane) * 32u + ((u) & 1u) * 16u)
 #define KTN_FAM_COL_AT(k, u, lane) (KTN_FAM_COL_OFF(k) + ((u) >> 3) * 1024u + (lane) * 32u + ((u) & 7u) * 4u)
+// constants per row of a family shape (rows of more than KTN_FAM_REGS variables keep the generic section layout: constants | columns | rank bytes)
+#define KTN_FAM_NCONST(family, nu) ((family) == 3u /* KTN_FAM_SOC */ ? (nu) - 1u : 2u * (nu))
+#define KTN_FAM_NOSLOT 0xffffffffu      // the pair's half is not backed by a constant of the row: packed as 0.0
 static inline uint32_t ktn_family_slot(uint32_t family, uint32_t which, uint32_t u, uint32_t nu) {
-    return family == 1u /* KTN_FAM_LSE */ ? 2u * u + which : (which ? nu + u : u);      // QUAD: a_u = slot u, b_u = slot nu + u
+    if (family == 1u /* KTN_FAM_LSE */) return 2u * u + which;                           // c_u = slot 2u, d_u = slot 2u + 1
+    if (family == 2u /* KTN_FAM_QUAD */) return which ? nu + u : u;                      // a_u = slot u, b_u = slot nu + u
+    return (which == 0u && u + 1u < nu) ? u : KTN_FAM_NOSLOT;                            // SOC: s_u = slot u; the linear variable has none
 }
 
 // shape flags

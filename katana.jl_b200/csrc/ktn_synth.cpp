@@ -4,6 +4,8 @@
 //   kind 0  sparse convex QCQP   g_i = sum_k a_ik x_jk^2 + sum_k b_ik x_jk          8 distinct columns
 //   kind 1  log-sum-exp          g_i = log sum_{k<K_i} exp(a_ik x_jk + b_ik)        K_i in {4..16}
 //   kind 2  SOC-like risk row    g_i = sqrt(sum_{k<8} (s_ik x_jk)^2) - x_t           as test/3d.jl:161
+//   kind 3  portfolio            nine sparse LINEAR rows sum_{k<16} a_ik x_jk (not in nlconstr_ixs: never separated) for every
+//                                SOC-like row of kind 2 (rows with index = 9 mod 10)                       BASELINE.json configs[3]
 // Expressions are emitted the way JuMP's @NLconstraint parser builds them (n-ary +, binary *, ^).
 #include <cstdint>
 #include <cmath>
@@ -39,7 +41,7 @@ static int lse_terms(uint64_t seed, int64_t row) { Rng r = row_rng(seed ^ 0x5151
 extern "C" int ktn_synth_rows(int32_t kind, uint64_t seed, int64_t num_var, int64_t row_begin, int64_t nrows,
                               int64_t* n_nodes, int64_t* expr_ptr, int32_t* op, int32_t* arg, double* val,
                               double* lb, double* ub, uint8_t* flags) {
-    if (kind < 0 || kind > 2 || num_var < 17 || nrows < 0 || !n_nodes) return KTN_ERR_USAGE;
+    if (kind < 0 || kind > 3 || num_var < 17 || nrows < 0 || !n_nodes) return KTN_ERR_USAGE;
     Emit e{op, arg, val};
     int32_t cols[17];
     for (int64_t r = 0; r < nrows; ++r) {
@@ -62,6 +64,11 @@ extern "C" int ktn_synth_rows(int32_t kind, uint64_t seed, int64_t num_var, int6
                 const double a = g.uni(-1.0, 1.0), b = g.uni(-1.0, 1.0);
                 e.call(KTN_OP_EXP, 1); e.call(KTN_OP_ADD, 2); e.call(KTN_OP_MUL, 2); e.cst(a); e.var(cols[k]); e.cst(b);
             }
+        } else if (kind == 3 && row % 10 != 9) {
+            if (op) flags[r] = 0;                       // a linear row: copied into the LP at loadproblem! (src/model.jl:115-118), not tested per round
+            distinct_cols(g, num_var, 16, cols);
+            e.call(KTN_OP_ADD, 16);
+            for (int k = 0; k < 16; ++k) { e.call(KTN_OP_MUL, 2); e.cst(g.uni(-1.0, 1.0)); e.var(cols[k]); }
         } else {
             distinct_cols(g, num_var, 9, cols);
             e.call(KTN_OP_SUB, 2);
@@ -77,7 +84,7 @@ extern "C" int ktn_synth_rows(int32_t kind, uint64_t seed, int64_t num_var, int6
 }
 
 extern "C" int ktn_synth_point(int32_t kind, uint64_t seed, int64_t num_var, double* x) {
-    if (kind < 0 || kind > 2 || !x) return KTN_ERR_USAGE;
+    if (kind < 0 || kind > 3 || !x) return KTN_ERR_USAGE;
     const double lo = kind == 0 ? -1.0 : kind == 1 ? -2.0 : 0.05, hi = kind == 0 ? 1.0 : kind == 1 ? 2.0 : 1.0;
     for (int64_t j = 0; j < num_var; ++j) { Rng r = row_rng(seed ^ 0xA5A5A5A5ull, j); x[j] = r.uni(lo, hi); }
     return KTN_OK;

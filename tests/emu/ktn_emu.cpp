@@ -71,7 +71,8 @@ struct EmuCutSink {     // the cut kernel's sink: coefficients and columns of th
 static EmuFamRow emu_row(const KtnProblem& P, const KtnChunkDesc& cd, uint32_t lane, const double* x) {
     const uint32_t nu = (uint32_t)cd.aux;
     const uint8_t* blob = P.blob.data() + cd.blob_off;
-    return EmuFamRow{(const double*)blob, (const int32_t*)(blob + (size_t)512 * nu), blob + (size_t)640 * nu, x, nu, cd.stride, lane};
+    const size_t sec_col = (size_t)256 * KTN_FAM_NCONST(P.shapes[cd.shape].family, nu), sec_rk = sec_col + (size_t)128 * nu;   // long rows: constants | columns | rank bytes
+    return EmuFamRow{(const double*)blob, (const int32_t*)(blob + sec_col), blob + sec_rk, x, nu, cd.stride, lane};
 }
 // K1: forward, test, record {g, aux}; rows of more than KTN_FAM_REGS variables build their cut here (streaming fallback)
 template <int FAM, int N>
@@ -124,7 +125,8 @@ static bool run_family_cut(ktn_handle* h, int64_t row, double& b) {
     bool mismatch = false;
     EmuCutSink s{h->stage_val.data() + base, P.jac_col.data() + base, &mismatch, {0}};
     const bool bad = fam == KTN_FAM_LSE ? ktn_family_cut_terms<KTN_FAM_LSE>(r, r.nu, rw, s, h->g_row[row], h->aux_row[row], h->do_round != 0, h->opt.cut_coef_rng, b)
-                                        : ktn_family_cut_terms<KTN_FAM_QUAD>(r, r.nu, rw, s, h->g_row[row], h->aux_row[row], h->do_round != 0, h->opt.cut_coef_rng, b);
+                   : fam == KTN_FAM_QUAD ? ktn_family_cut_terms<KTN_FAM_QUAD>(r, r.nu, rw, s, h->g_row[row], h->aux_row[row], h->do_round != 0, h->opt.cut_coef_rng, b)
+                                         : ktn_family_cut_terms<KTN_FAM_SOC>(r, r.nu, rw, s, h->g_row[row], h->aux_row[row], h->do_round != 0, h->opt.cut_coef_rng, b);
     if (mismatch) { fprintf(stderr, "emu: the cut's columns differ from the Jacobian structure\n"); abort(); }
     return bad;
 }
@@ -151,7 +153,8 @@ static void run_chunks(ktn_handle* h, const double* x, int mode, const std::vect
                 if (cd.row_slot != c * 32 || L != 32 || cd.aux != nu) { fprintf(stderr, "emu: family chunk layout violated\n"); abort(); }
                 const bool forced = mode == 1 && force[row] != 0;
                 if (sd.family == KTN_FAM_LSE) run_family_dispatch<KTN_FAM_LSE>(nu, h, cd, lane, row, x, mode, forced, flb, fub, do_round);
-                else run_family_dispatch<KTN_FAM_QUAD>(nu, h, cd, lane, row, x, mode, forced, flb, fub, do_round);
+                else if (sd.family == KTN_FAM_QUAD) run_family_dispatch<KTN_FAM_QUAD>(nu, h, cd, lane, row, x, mode, forced, flb, fub, do_round);
+                else run_family_dispatch<KTN_FAM_SOC>(nu, h, cd, lane, row, x, mode, forced, flb, fub, do_round);
                 continue;
             }
             for (uint32_t u = 0; u < nu; ++u) S[(size_t)u * L + lane] = x[cols[(size_t)u * L + lane]];

@@ -52,10 +52,10 @@ def test_synthetic_families_identical(oracle_lib, emu_lib, synth_lib, kind, nv, 
 
 
 def test_family_detection(emu_lib, synth_lib):
-    """The two benchmark forms are recognised as families (interpreter-free kernels); SOC rows stay generic."""
+    """The three benchmark forms are recognised as families (interpreter-free kernels)."""
     import ctypes as C
     emu_lib.dll.ktn_emu_num_family_chunks.restype = C.c_int64
-    for kind, fam in ((0, 2), (1, 1), (2, 0)):
+    for kind, fam in ((0, 2), (1, 1), (2, 3)):
         w = synth_lib.synth_rows(kind, 7, 1000, 0, 700)
         h = emu_lib.create(); h.load(1000, w)
         nch = emu_lib.dll.ktn_emu_num_chunks(h.h)
@@ -68,7 +68,7 @@ def test_family_detection(emu_lib, synth_lib):
     assert emu_lib.dll.ktn_emu_num_family_chunks(h.h, C.c_int32(2)) == 1 and emu_lib.dll.ktn_emu_num_family_chunks(h.h, C.c_int32(0)) == 1
 
 
-@pytest.mark.parametrize("family", ["lse", "quad"])
+@pytest.mark.parametrize("family", ["lse", "quad", "soc"])
 def test_family_rows_edge_values(oracle_lib, emu_lib, family, monkeypatch):
     """Family fast path == interpreter == oracle on overflow, underflow, NaN / inf points, repeated coefficients,
     coefficient ranges that make round_coefs zero entries, ragged chunks and every unique-variable count 1..20."""
@@ -80,9 +80,11 @@ def test_family_rows_edge_values(oracle_lib, emu_lib, family, monkeypatch):
         scale = 10.0 ** rng.integers(-12, 12, nu)
         if family == "lse":
             exprs.append(E.log(E.sum_([E.exp(E.const(float(rng.uniform(-1, 1) * scale[k])) * E.var(int(cols[k])) + float(rng.uniform(-1, 1))) for k in range(nu)])))
-        else:
+        elif family == "quad":
             exprs.append(E.sum_([E.const(float(rng.uniform(0.5, 1.5) * scale[k])) * E.var(int(cols[k]))**2 for k in range(nu)] +
                                 [E.const(float(rng.uniform(-1, 1))) * E.var(int(cols[k])) for k in range(nu)]))
+        elif nu >= 2:                                                           # sqrt(sum (s x)^2) - t  (test/3d.jl:161)
+            exprs.append(E.sqrt(E.sum_([(E.const(float(rng.uniform(0.1, 0.5) * scale[k])) * E.var(int(cols[k])))**2 for k in range(nu - 1)])) - E.var(int(cols[nu - 1])))
     m = len(exprs)
     w = E.to_wire(exprs, np.full(m, -np.inf), np.full(m, -1e300), [ROW_NL] * m)
     pts = [rng.uniform(-2, 2, nvar), np.zeros(nvar), np.full(nvar, 1e3), np.full(nvar, -1e3), np.full(nvar, 1e200), rng.uniform(-1e-9, 1e-9, nvar)]
@@ -190,3 +192,23 @@ def test_reload_on_same_handle(oracle_lib, emu_lib):
     w2 = E.to_wire([x0**2], [-np.inf], [1.0], [ROW_NL])
     he.load(1, w2); ho.load(1, w2)
     assert_batches_identical(ho.separate(np.array([3.0])), he.separate(np.array([3.0])))
+
+
+def test_long_rows_of_family_form(oracle_lib, emu_lib):
+    """Log-sum-exp / quadratic / SOC rows too long for the shared-memory lane budget run as interpreted BIG shapes (their chunks
+    carry the interpreter's sort order, not the families' rank bytes)."""
+    rng = np.random.default_rng(3)
+    nvar = 400
+    exprs = []
+    for nu in (60, 91, 150, 256, 300):
+        cols = rng.choice(nvar, nu, replace=False)
+        exprs.append(E.log(E.sum_([E.exp(E.const(float(rng.uniform(-1, 1))) * E.var(int(c)) + float(rng.uniform(-1, 1))) for c in cols])))
+        exprs.append(E.sum_([E.const(float(rng.uniform(0.5, 1.5))) * E.var(int(c))**2 for c in cols] + [E.const(float(rng.uniform(-1, 1))) * E.var(int(c)) for c in cols]))
+        exprs.append(E.sqrt(E.sum_([(E.const(float(rng.uniform(0.1, 0.5))) * E.var(int(c)))**2 for c in cols[:-1]])) - E.var(int(cols[-1])))
+    m = len(exprs)
+    w = E.to_wire(exprs, np.full(m, -np.inf), np.full(m, -1e300), [ROW_NL] * m)
+    ho, he = both(oracle_lib, emu_lib, nvar, w)
+    for _ in range(3):
+        x = rng.uniform(-1, 1, nvar)
+        assert bits_equal(ho.eval_g(x), he.eval_g(x))
+        assert_batches_identical(ho.separate(x), he.separate(x), "long family-form rows")
