@@ -168,6 +168,15 @@ int ktn_separate(ktn_handle* h, const double* xstar, int64_t* n_cuts, int64_t* n
 int ktn_gencut_rows(ktn_handle* h, const double* x, const int64_t* rows, int64_t nrows, int round_coefs,
                     int64_t* n_cuts, int64_t* nnz_cuts, int64_t* err_row);
 
+/* boundroutine's ladder (src/model.jl:175-197): points x_n = 2^n * ray for n = n_first .. n_last (the reference: 2 .. 1023); every
+ * nonlinear row is tested at each point in turn, and at the FIRST point where a row is violated the violated rows are cut (as
+ * ktn_separate does) and the search stops.  The reference runs up to 1022 sequential precompute! rounds for this; here the points
+ * are evaluated in batches of 16 without a host round trip in between (forward evaluation + one violation flag per point), then
+ * ONE separation round runs at the point that was hit.  *n_hit receives that exponent (-1: no point violated any row: no cuts).
+ * The cuts are fetched as after ktn_separate.  Not available on a multi-device handle. */
+int ktn_separate_ladder(ktn_handle* h, const double* ray, int32_t n_first, int32_t n_last, int32_t* n_hit,
+                        int64_t* n_cuts, int64_t* nnz_cuts, int64_t* err_row);
+
 /* Download the cuts of the last ktn_separate / ktn_gencut_rows.  Cut c (ascending row order):
  *   row_id[c]                      0-based constraint index
  *   row_ptr[c] .. row_ptr[c+1]     its entries in col[] / val[]   (row_ptr has n_cuts+1 entries)

@@ -60,6 +60,7 @@ _SIGS = {
     "ktn_jac_nnz": (C.c_int64, [_P]),
     "ktn_separate": (C.c_int, [_P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ktn_gencut_rows": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ktn_separate_ladder": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ktn_fetch_cuts": (C.c_int, [_P] + [_P] * 9),
     "ktn_fetch_cuts_view": (C.c_int, [_P, C.POINTER(ktn_cut_view)]),
     "ktn_get_g": (C.c_int, [_P, _P]),
@@ -301,6 +302,15 @@ class Handle:
         if view:
             return self._fetch_view(st, er.value)
         return self._fetch(st, nc.value, nz.value, er.value)
+
+    def separate_ladder(self, ray, n_first=2, n_last=1023, view=False):
+        """boundroutine's search (src/model.jl:175-197): the cuts at the first point 2^n * ray that violates a row.  Returns (n_hit, CutBatch)."""
+        r = np.ascontiguousarray(ray, np.float64)
+        assert len(r) == self.num_var
+        hit, nc, nz, er = C.c_int32(-1), C.c_int64(), C.c_int64(), C.c_int64()
+        st = self._ck(self.dll.ktn_separate_ladder(self.h, _ptr(r), n_first, n_last, C.byref(hit), C.byref(nc), C.byref(nz), C.byref(er)),
+                      "ktn_separate_ladder", numeric_ok=True)
+        return hit.value, (self._fetch_view(st, er.value) if view else self._fetch(st, nc.value, nz.value, er.value))
 
     def gencut_rows(self, x, rows, round_coefs=False):
         x = np.ascontiguousarray(x, np.float64); rows = np.ascontiguousarray(rows, np.int64)

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -31,7 +32,7 @@ extern "C" const char* ktn_last_error(ktn_handle* h) { return h ? h->err.c_str()
 
 static void free_problem(ktn_handle* h) {
     DevBuf* all[] = {&h->chunks, &h->shapes, &h->prog, &h->blob, &h->chunk_rows, &h->chunk_lb, &h->chunk_ub, &h->jac_ptr, &h->jac_col,
-                     &h->row_lb, &h->row_ub, &h->row_slot, &h->rec, &h->worklist, &h->errpos, &h->blk_off, &h->chunk_jp, &h->dump, &h->x, &h->force, &h->g_row, &h->b_row, &h->sel, &h->stage_val, &h->big_scratch,
+                     &h->row_lb, &h->row_ub, &h->row_slot, &h->row_nl, &h->ladder, &h->rec, &h->worklist, &h->errpos, &h->blk_off, &h->chunk_jp, &h->dump, &h->x, &h->force, &h->g_row, &h->b_row, &h->sel, &h->stage_val, &h->big_scratch,
                      &h->blk_cnt, &h->topk_key, &h->topk_state, &h->topk_eqcnt, &h->table, &h->out_blob[0], &h->out_blob[1], &h->out_blob[2]};
     for (DevBuf* b : all) b->release();
     if (h->h_x) { cudaFreeHost(h->h_x); h->h_x = nullptr; }
@@ -176,6 +177,7 @@ extern "C" int ktn_load_end(ktn_handle* h) {
     CK(h, upload(h->chunk_lb, P.chunk_lb)); CK(h, upload(h->chunk_ub, P.chunk_ub));
     CK(h, upload(h->jac_ptr, P.jac_ptr)); CK(h, upload(h->jac_col, P.jac_col));
     CK(h, upload(h->row_lb, P.lb)); CK(h, upload(h->row_ub, P.ub)); CK(h, upload(h->row_slot, P.row_slot));
+    { std::vector<uint8_t> nl(P.flags.size()); for (size_t i = 0; i < nl.size(); ++i) nl[i] = (P.flags[i] & KTN_ROW_NL) ? 1 : 0; CK(h, upload(h->row_nl, nl)); }
     CK(h, h->rec.alloc(32 * (m + 1))); CK(h, h->worklist.alloc(8 * (m + 1)));
     CK(h, upload(h->chunk_jp, P.chunk_jp)); CK(h, h->dump.alloc(24 * (N + 1)));
     CK(h, h->x.alloc(8 * ((size_t)P.num_var + 1))); CK(h, h->force.alloc(m + 16));
@@ -377,6 +379,49 @@ extern "C" int ktn_gencut_rows(ktn_handle* h, const double* x, const int64_t* ro
     int rc = upload_x(h, x); if (rc) return rc;
     rc = enqueue_round(h, h->x.as<double>(), KTN_MODE_FORCE, do_round ? 1 : 0); if (rc) return rc;
     return finish_round(h, n_cuts, nnz, err_row);
+}
+
+// boundroutine's ladder, src/model.jl:175-197: see include/ktn.h
+void ktn_launch_scale(const double* ray, double* x, int64_t n, double scale, cudaStream_t stream);
+void ktn_launch_anyviol(const KtnRoundParams& p, const uint8_t* row_nl, unsigned int* flag, cudaStream_t stream);
+extern "C" int ktn_separate_ladder(ktn_handle* h, const double* ray, int32_t n_first, int32_t n_last, int32_t* n_hit,
+                                   int64_t* n_cuts, int64_t* nnz, int64_t* err_row) {
+    if (h && !h->shards.empty()) return fail(h, KTN_ERR_UNSUPPORTED, "not available on a multi-device handle");
+    if (!h || !h->loaded || !ray || n_first < 0 || n_last > 1023 || n_last < n_first) return fail(h, KTN_ERR_USAGE, "bad ladder");
+    cudaSetDevice(h->device);
+    const int64_t nv = h->prob.num_var;
+    const int B = 16;
+    // device copy of the ray behind x (x itself is rewritten per point), one violation flag per point of a batch
+    if (h->ladder.bytes < 8 * ((size_t)nv + 1) + 4 * B) CK(h, h->ladder.alloc(8 * ((size_t)nv + 1) + 4 * B));
+    double* d_ray = h->ladder.as<double>();
+    unsigned int* d_flag = reinterpret_cast<unsigned int*>(h->ladder.as<unsigned char>() + 8 * ((size_t)nv + 1));
+    memcpy(h->h_x, ray, 8 * (size_t)nv);
+    CK(h, cudaMemcpyAsync(d_ray, h->h_x, 8 * (size_t)nv, cudaMemcpyHostToDevice, h->stream));
+    int hit = -1;
+    unsigned int flags[B];
+    for (int n0 = n_first; n0 <= n_last && hit < 0; n0 += B) {
+        const int cnt = n_last - n0 + 1 < B ? n_last - n0 + 1 : B;
+        CK(h, cudaMemsetAsync(d_flag, 0, 4 * B, h->stream));
+        for (int k = 0; k < cnt; ++k) {       // no host round trip between the points of a batch
+            ktn_launch_scale(d_ray, h->x.as<double>(), nv, ldexp(1.0, n0 + k), h->stream);
+            KtnRoundParams p = ktn_make_params(h, h->x.as<double>(), KTN_MODE_SEPARATE, 0);
+            cudaError_t e = cudaSuccess;
+            h->tm.launches += 2 + ktn_launch_eval(p, make_plan(h), h->num_sms, h->max_smem, h->stream, &e);
+            if (e != cudaSuccess) return fail(h, KTN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+            ktn_launch_anyviol(p, h->row_nl.as<uint8_t>(), d_flag + k, h->stream);
+        }
+        CK(h, cudaMemcpyAsync(flags, d_flag, 4 * (size_t)cnt, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        for (int k = 0; k < cnt; ++k) if (flags[k]) { hit = n0 + k; break; }
+    }
+    if (n_hit) *n_hit = hit;
+    if (hit < 0) {       // every row satisfied along the whole ladder: an empty batch (a round at the last point, which selects nothing)
+        hit = n_last;
+    }
+    std::vector<double> x((size_t)nv);
+    const double sc = ldexp(1.0, hit);
+    for (int64_t j = 0; j < nv; ++j) x[j] = sc * ray[j];      // (2.0^n) * ray, src/model.jl:183
+    return ktn_separate(h, x.data(), n_cuts, nnz, err_row);
 }
 
 extern "C" int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, int32_t* col, double* val,

@@ -1047,6 +1047,27 @@ void ktn_launch_shift(const int64_t* in, int64_t* out, int64_t n, int64_t add, c
     ktn_shift_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, stream>>>(in, out, n, add);
 }
 
+// boundroutine's ladder (ktn_separate_ladder): x = scale * ray, and "is any nonlinear row violated at the point just evaluated?"
+namespace {
+__global__ void ktn_scale_kernel(const double* ray, double* x, int64_t n, double scale) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = scale * ray[i];
+}
+__global__ void ktn_anyviol_kernel(const double* g, const double* lb, const double* ub, const uint8_t* nl, int64_t m, double f_tol, unsigned int* flag) {
+    bool v = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+        if (nl[i]) { const double gi = g[i]; v = v || !((gi >= lb[i] - f_tol) && (gi <= ub[i] + f_tol)); }      // src/separators.jl:120 (NaN: not satisfied)
+    if (__any_sync(0xffffffffu, v) && (threadIdx.x & 31u) == 0) *flag = 1u;
+}
+}
+void ktn_launch_scale(const double* ray, double* x, int64_t n, double scale, cudaStream_t stream) {
+    const int64_t b = (n + 255) / 256;
+    ktn_scale_kernel<<<(unsigned)(b < 592 ? (b ? b : 1) : 592), 256, 0, stream>>>(ray, x, n, scale);
+}
+void ktn_launch_anyviol(const KtnRoundParams& p, const uint8_t* row_nl, unsigned int* flag, cudaStream_t stream) {
+    const int64_t b = (p.num_rows + 255) / 256;
+    ktn_anyviol_kernel<<<(unsigned)(b < 1184 ? (b ? b : 1) : 1184), 256, 0, stream>>>(p.g_row, p.row_lb, p.row_ub, row_nl, p.num_rows, p.f_tol, flag);
+}
+
 int ktn_launch_eval(const KtnRoundParams& p, const KtnLaunchPlan& plan, int num_sms, int max_smem_optin,
                     cudaStream_t stream, cudaError_t* err) {
     int launches = launch_eval_part<true>(p, plan, num_sms, max_smem_optin, stream, err);

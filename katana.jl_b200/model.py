@@ -157,6 +157,14 @@ class KatanaNonlinearModel:                                    # src/model.jl:9-
 
     # boundroutine(m, ray) -- src/model.jl:175-197
     def boundroutine(self, ray):
+        sep = self.params.separator
+        if hasattr(sep, "separate_ladder") and getattr(sep, "ngpus", 1) <= 1:
+            # the whole search in one library call: the points are evaluated on the device in batches, the cuts are made at the
+            # first point that violates a row -- what the loop below does with up to 1022 sequential rounds
+            n_hit, batch = sep.separate_ladder(np.asarray(ray, np.float64))
+            self._addbatch(batch)
+            self.round_log.append({"ladder_hit": n_hit, "cuts": batch.n_cuts})
+            return
         for n in range(2, 1024):
             x = (2.0 ** n) * ray
             allsat, _ = self._separate_round(x)

@@ -92,6 +92,13 @@ class KatanaGPUSeparator(AbstractKatanaSeparator):
         self.precompute(xstar)
         return self.last
 
+    def separate_ladder(self, ray, n_first=2, n_last=1023):
+        """boundroutine's search along an unbounded ray (src/model.jl:175-197) as ONE call: (exponent hit or -1, CutBatch)."""
+        n_hit, self.last = self.handle.separate_ladder(ray, n_first, n_last, view=True)
+        self.xstar = (2.0 ** (n_hit if n_hit >= 0 else n_last)) * np.asarray(ray, np.float64)
+        self.g = None
+        return n_hit, self.last
+
     # isconstrsat(sep, i, lb, ub, f_tol) -- src/separators.jl:120
     def isconstrsat(self, i, lb, ub, f_tol):
         if self.g is None:

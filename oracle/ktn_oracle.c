@@ -494,6 +494,28 @@ int64_t ktn_algorithmic_bytes(ktn_handle* h) {
     return by;
 }
 
+/* boundroutine, src/model.jl:175-197: the sequential ladder as the reference runs it: one full round per point, stop at the first
+ * point where a row was violated (cuts were made) or a cut was not finite */
+int ktn_separate_ladder(ktn_handle* h, const double* ray, int32_t n_first, int32_t n_last, int32_t* n_hit,
+                        int64_t* n_cuts, int64_t* nnz_cuts, int64_t* err_row) {
+    if (!h || !h->jac || !ray || n_first < 0 || n_last > 1023 || n_last < n_first) return fail(h, KTN_ERR_USAGE, "bad ladder");
+    double* x = (double*)malloc(sizeof(double) * (size_t)(h->num_var + 1));
+    int status = KTN_OK; int64_t nc = 0, nz = 0, er = -1;
+    if (n_hit) *n_hit = -1;
+    for (int32_t n = n_first; n <= n_last; ++n) {
+        const double sc = ldexp(1.0, n);
+        for (int64_t j = 0; j < h->num_var; ++j) x[j] = sc * ray[j];
+        status = ktn_separate(h, x, &nc, &nz, &er);
+        if (status < 0) break;
+        if (nc > 0 || status == KTN_NUMERIC_NONFINITE) { if (n_hit) *n_hit = n; break; }      /* !allsat: stop searching in this direction */
+    }
+    free(x);
+    if (n_cuts) *n_cuts = nc;
+    if (nnz_cuts) *nnz_cuts = nz;
+    if (err_row) *err_row = er;
+    return status;
+}
+
 /* device-resident and sharded entry points have no CPU meaning */
 int ktn_set_stream(ktn_handle* h, void* s) { (void)s; return fail(h, KTN_ERR_UNSUPPORTED, "oracle has no stream"); }
 int ktn_separate_device_async(ktn_handle* h, const double* d) { (void)d; return fail(h, KTN_ERR_UNSUPPORTED, "oracle has no device path"); }

@@ -251,6 +251,7 @@ int64_t ktn_emu_num_shapes(ktn_handle* h) { return (int64_t)h->prob.shapes.size(
 int64_t ktn_emu_num_chunks(ktn_handle* h) { return (int64_t)h->prob.chunks.size(); }
 int64_t ktn_emu_num_family_chunks(ktn_handle* h, int32_t fam) { return fam < 0 || fam >= KTN_FAM__COUNT ? -1 : (int64_t)h->prob.fam_begin[fam + 1] - (int64_t)h->prob.fam_begin[fam]; }
 int64_t ktn_emu_num_big_chunks(ktn_handle* h) { return (int64_t)h->prob.chunks.size() - h->prob.n_regular_chunks; }
+int ktn_separate_ladder(ktn_handle*, const double*, int32_t, int32_t, int32_t*, int64_t*, int64_t*, int64_t*) { return KTN_ERR_UNSUPPORTED; }
 int ktn_set_stream(ktn_handle*, void*) { return KTN_ERR_UNSUPPORTED; }
 int ktn_separate_device_async(ktn_handle*, const double*) { return KTN_ERR_UNSUPPORTED; }
 int ktn_sync_counts(ktn_handle*, int64_t*, int64_t*, int64_t*) { return KTN_ERR_UNSUPPORTED; }

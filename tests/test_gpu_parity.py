@@ -423,3 +423,36 @@ def test_long_rows_of_family_form_on_gpu(oracle_lib, cuda_lib):
             x = rng.uniform(-1, 1, nvar)
             assert bits_equal(ho.eval_g(x), hc.eval_g(x))
             assert_batches_identical(ho.separate(x), hc.separate(x), "long family-form rows")
+
+
+def test_ladder_matches_the_sequential_search(oracle_lib, cuda_lib):
+    """ktn_separate_ladder (boundroutine batching, src/model.jl:175-197): the device evaluates the points 2^n * ray in batches and
+    cuts at the first violating one; the oracle runs the reference's sequential loop.  Same exponent, same cuts, bit for bit --
+    on the KAT problem, on synthetic families (hit in the first batch, in a later batch, never), and with a non-finite cut."""
+    nvar, w, pts = kat_problem()
+    ho, hc = both(oracle_lib, cuda_lib, nvar, w)
+    rng = np.random.default_rng(9)
+    for _ in range(4):
+        ray = rng.normal(size=nvar)
+        (no, bo), (nc, bc) = ho.separate_ladder(ray), hc.separate_ladder(ray)
+        assert no == nc
+        assert_batches_identical(bo, bc, "ladder KAT")
+    for kind, nv, nr, scale in ((0, 1000, 4000, 1.0), (1, 3000, 6000, 1e-7), (2, 2000, 3000, 1e-12)):
+        ws = cuda_lib.synth_rows(kind, 5 + kind, nv, 0, nr); x0 = cuda_lib.synth_point(kind, 5 + kind, nv)
+        ho, hc = both(oracle_lib, cuda_lib, nv, ws)
+        ub = np.full(nr, 50.0); ho.set_bounds(ws.lb, ub); hc.set_bounds(ws.lb, ub)
+        ray = x0 * scale                                      # small rays: the first violation comes many doublings out
+        (no, bo), (nc, bc) = ho.separate_ladder(ray), hc.separate_ladder(ray)
+        assert no == nc and (no >= 2)
+        assert_batches_identical(bo, bc, f"ladder kind {kind}")
+        (no, bo), (nc, bc) = ho.separate_ladder(ray, 2, 4), hc.separate_ladder(ray, 2, 4)      # a ladder that may end before anything is violated
+        assert no == nc
+        assert_batches_identical(bo, bc, f"short ladder kind {kind}")
+        assert_batches_identical(ho.separate(x0), hc.separate(x0))                              # the handle is usable afterwards
+    x, y, z = E.var(0), E.var(1), E.var(2)                    # sqrt at the apex: the first violated row is not finite -> :Error
+    exprs = [E.sqrt(x**2 + y**2) - (z - 0.25), x**2 + y**2 - 1.0]
+    w = E.to_wire(exprs, np.full(2, -np.inf), np.full(2, -2.0), [ROW_NL] * 2)
+    ho, hc = both(oracle_lib, cuda_lib, 3, w)
+    (no, bo), (nc, bc) = ho.separate_ladder(np.zeros(3)), hc.separate_ladder(np.zeros(3))
+    assert no == nc == 2 and bo.status == KTN_NUMERIC_NONFINITE
+    assert_batches_identical(bo, bc, "ladder, non-finite")

@@ -99,3 +99,23 @@ def test_against_mpmath_golden_vectors(oracle_lib):
                 assert dense[j] == pytest.approx(float(ref["grad"][j]), rel=1e-13, abs=1e-300), (r, pi, j)
                 checked += 1
     assert checked > 200
+
+
+def test_ladder_is_the_sequential_search(oracle_lib):
+    """ktn_separate_ladder on the oracle IS boundroutine's loop (src/model.jl:175-197): rounds at 2^n * ray, n = 2, 3, ..., until a
+    row is violated; the cuts are those of that round."""
+    import numpy as np
+    from katana_jl_b200 import expr as E
+    from katana_jl_b200.binding import ROW_NL
+    x, y = E.var(0), E.var(1)
+    exprs = [x**2 + y**2, E.exp(x) - y, x + y]                       # disk of radius 100, exp(x) <= y + 5000, a linear row (never tested)
+    w = E.to_wire(exprs, [-np.inf] * 3, [1e4, 5e3, 1.0], [ROW_NL, ROW_NL, 0])
+    h = oracle_lib.create(); h.load(2, w)
+    ray = np.array([1.0, 0.25])
+    n_hit, b = h.separate_ladder(ray)
+    want_n = next(n for n in range(2, 1024) if h.separate(2.0**n * ray).n_cuts > 0)
+    assert n_hit == want_n == 4                                      # exp(2^4) - 4 > 5000 (2^3: exp(8) - 2 = 2979); the disk holds until 2^7
+    ref = h.separate(2.0**want_n * ray)
+    assert ref.n_cuts == b.n_cuts and np.array_equal(ref.val, b.val) and np.array_equal(ref.row_id, b.row_id)
+    n_hit, b = h.separate_ladder(np.array([-1.0, 1.0]), 2, 5)        # a direction that stays feasible for the points asked: no cuts
+    assert n_hit == -1 and b.n_cuts == 0
