@@ -37,7 +37,7 @@ static void free_problem(ktn_handle* h) {
     for (DevBuf* b : all) b->release();
     if (h->h_x) { cudaFreeHost(h->h_x); h->h_x = nullptr; }
     h->prob = KtnProblem();
-    h->loaded = h->loading = h->round_pending = h->have_round = false;
+    h->loaded = h->loading = h->round_pending = h->have_round = h->forced_last = false;
     h->n_cuts = h->nnz_cuts = 0; h->err_row = -1;
 }
 
@@ -305,6 +305,7 @@ static int enqueue_round(ktn_handle* h, const double* d_x, int mode, int do_roun
     }
     h->epoch = (h->epoch % 0x3ffffff0u) + 1u;
     KtnRoundParams p = ktn_make_params(h, d_x, mode, do_round);
+    p.clear_unselected = h->forced_last ? 1 : 0; h->forced_last = mode == KTN_MODE_FORCE;
     cudaError_t e = cudaSuccess;
     (void)cudaGetLastError();   // a stale non-sticky error must not be blamed on this round's launches
     if (h->ring_head - h->ring_tail >= ktn_handle::RING) drain_ring(h, false);

@@ -586,7 +586,7 @@ int KtnProblem::finalize(int64_t sigma, uint32_t lane_limit, size_t table_limit)
     // 2. regular chunks are ordered by (family, class), window order kept inside a class, and packed in that order: the blobs
     //    of one family class are contiguous and equally sized, so the family kernel finds a chunk without a descriptor
     {
-        auto key = [&](const Pending& pc) { const KtnShapeDesc& s = shapes[pc.sid]; return s.family * (uint32_t)KTN_FAM_NCLS + (s.family != KTN_FAM_GENERIC ? ktn_family_class(s.n_uniq) : 0u); };
+        auto key = [&](const Pending& pc) { const KtnShapeDesc& s = shapes[pc.sid]; return s.family * (uint32_t)KTN_FAM_NCLS + (s.family != KTN_FAM_GENERIC ? ktn_family_class(s.n_uniq) : ((s.flags & KTN_SH_NL) ? 0u : 1u)); };      // interpreted shapes: class 0 = rows of nlconstr_ixs, class 1 = the rest (never tested: a separation round skips them)
         std::stable_sort(reg.begin(), reg.end(), [&](const Pending& a, const Pending& b) { return key(a) < key(b); });
         std::vector<uint32_t> count((size_t)KTN_FAM__COUNT * KTN_FAM_NCLS + 1, 0u);
         memset(cls_blob_off, 0, sizeof cls_blob_off); memset(cls_blob_stride, 0, sizeof cls_blob_stride);

@@ -35,6 +35,7 @@ struct ktn_handle {
     double exchange_ms_sum = 0; int64_t exchanges_timed = 0;
     KtnProblem prob;
     bool loading = false, loaded = false, round_pending = false, have_round = false;
+    bool forced_last = false;              // the last round was unconditional (ktn_gencut_rows): rows outside nlconstr_ixs may carry selection flags
     DevBuf chunks, shapes, prog, blob, chunk_rows, chunk_lb, chunk_ub, jac_ptr, jac_col, row_lb, row_ub, row_slot, row_nl, ladder, rec, worklist, errpos, blk_off, chunk_jp, dump;
     DevBuf topk_key, topk_state, topk_eqcnt;      // top-k selection (allocated when ktn_options.topk > 0)
     DevBuf x, force, g_row, b_row, sel, stage_val, big_scratch, ticket, blk_cnt, counts, table;

@@ -984,7 +984,10 @@ static int launch_eval_part(const KtnRoundParams& p0, const KtnLaunchPlan& plan,
     int launches = 0;
     KtnRoundParams p = p0;
     if (EVAL) p.mode = KTN_MODE_EVAL;
-    const uint32_t g_begin = plan.fam_begin[KTN_FAM_GENERIC], g_end = plan.fam_begin[KTN_FAM_GENERIC + 1];
+    // interpreted shapes: the rows of nlconstr_ixs first.  A separation round never looks at the others (src/model.jl:272): their
+    // chunks are skipped unless an unconditional round (ktn_gencut_rows) selected some of them last time and their flags must be cleared
+    const uint32_t g_begin = plan.fam_begin[KTN_FAM_GENERIC];
+    const uint32_t g_end = (!EVAL && p.mode == KTN_MODE_SEPARATE && !p.clear_unselected) ? plan.cls_begin[KTN_FAM_GENERIC][1] : plan.fam_begin[KTN_FAM_GENERIC + 1];
     if (g_end > g_begin) {
         int wpb, bps; ktn_plan_occupancy(p.table_bytes, p.warp_bytes, max_smem_optin, &wpb, &bps);
         const size_t smem = ((p.table_bytes + 127u) & ~127u) + (size_t)wpb * p.warp_bytes;

@@ -33,6 +33,7 @@ struct KtnRoundParams {
     int64_t topk;              // > 0: keep only the k most violated rows (build extension)
     unsigned long long* topk_key; KtnTopkState* topk_state; unsigned int* topk_eqcnt;
     int32_t mode, do_round;
+    int32_t clear_unselected;  // separation round after an unconditional one: also visit the chunks of rows outside nlconstr_ixs (their flags are reset)
     int64_t num_var, num_rows, row_offset;
     uint32_t chunk_begin, chunk_end;   // chunk range this launch covers
     uint32_t warp_bytes;               // shared-memory bytes per warp (regular kernel)
