@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--violated", dest="v", type=float, default=0.1, help="violated fraction of the rows at x* (not --v: torchrun's own parser claims that prefix)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="exchange sweeps only: skip the end-to-end leg and the sharded parity check (the line then carries no e2e)")
     ap.add_argument("--topk", type=int, default=0, help="build extension: keep only the k most violated rows per round (0 = reference behaviour: all)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -283,7 +284,13 @@ def main():
 
     # ---- sharded runs: the gathered batch of one more round against a single handle, outside the timed region ------
     sharded = None
-    if world > 1:
+    if world > 1 and args.skip_e2e:
+        xt = max(1, t_after["exchanges_timed"] - t_before["exchanges_timed"])
+        exchange_ms = (t_after["exchange_ms_sum"] - t_before["exchange_ms_sum"]) / xt
+        blob_bytes = 64 + 28 * n_cuts + 12 * nnz + 8
+        sharded = {"exchange_ms": exchange_ms, "inbound_bytes_per_gpu": (world - 1) * blob_bytes,
+                   "inbound_gbs_per_gpu": (world - 1) * blob_bytes / (exchange_ms * 1e-3) / 1e9 if exchange_ms > 0 else None}
+    elif world > 1:
         xt = max(1, t_after["exchanges_timed"] - t_before["exchanges_timed"])
         exchange_ms = (t_after["exchange_ms_sum"] - t_before["exchange_ms_sum"]) / xt
         ubs = [None] * world
@@ -309,6 +316,13 @@ def main():
             sharded["sharded_parity_exchange"] = bool(same_cuts(sub_batch(gathered, keep), want))
             chk.close()
 
+    if args.skip_e2e:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "n_gpus": world, "ms_per_step": ms_per_step, "k1_ms": k1_ms, "k2_k3_ms": k2_ms, "sharded": sharded,
+                              "push_blocks": os.environ.get("KTN_PUSH_BLOCKS"), "exchange": os.environ.get("KTN_EXCHANGE"), "e2e": None}), flush=True)
+        if world > 1:
+            dist.barrier(group=cpu_group); dist.destroy_process_group()
+        return
     # ---- e2e: the separator call a Katana user makes, host buffers in and out ------------------------------------
     h.set_stream(0)
     torch.cuda.synchronize()
