@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(KTN_CBLOCK, KTN_CBPS) ktn_compact_kernel(const
 #define KTN_XBLOCK 128
 #endif
 #ifndef KTN_XBPS
-#define KTN_XBPS 4
+#define KTN_XBPS 3       // measured: 3 blocks of 128 threads per SM (166 registers) 30.8 us, 4 (128 registers) 37.4, 2: 34.8 (profiles/r02_ab_ab11.log)
 #endif
 struct CutRow {     // row context of ktn_family_cut_terms: the row's groups in the chunk blob (ktn_program.h)
     const unsigned char* blob; const double* X; uint32_t nu, lane;
@@ -736,9 +736,17 @@ struct CutSink {    // coefficients and columns: the row's slice of the block's 
 };
 
 __global__ void __launch_bounds__(KTN_XBLOCK, KTN_XBPS) ktn_cut_kernel(const KtnRoundParams p, uint32_t epoch) {
+#ifndef KTN_X_NOSTAGE
     __shared__ double s_val[KTN_XBLOCK * KTN_FAM_REGS];      // coefficients of the block's cuts, in CSR order
+#else
+    double* const s_val = nullptr;
+#endif
     __shared__ double s_t[KTN_FAM_REGS * KTN_XBLOCK];        // products -x* J: [entry][thread]
+#ifndef KTN_X_NOSTAGE
     __shared__ int32_t s_col[KTN_XBLOCK * KTN_FAM_REGS];     // columns of the block's cuts, in CSR order
+#else
+    int32_t* const s_col = nullptr;
+#endif
     __shared__ unsigned long long s_e0, s_e1; __shared__ uint32_t s_last;
     const unsigned long long ca = __ldcg(&p.counts[4]), na = __ldcg(&p.counts[5]);
     const KtnPackLayout L = ktn_pack_layout(ca, na);
@@ -750,15 +758,21 @@ __global__ void __launch_bounds__(KTN_XBLOCK, KTN_XBPS) ktn_cut_kernel(const Ktn
     for (unsigned long long c0 = (unsigned long long)blockIdx.x * KTN_XBLOCK; c0 < ca; c0 += (unsigned long long)gridDim.x * KTN_XBLOCK) {
         const unsigned long long cidx = c0 + threadIdx.x;
         const bool active = cidx < ca;
-        int64_t o = 0; unsigned long long w = 0ull;
-        if (active) { w = __ldcg(p.worklist + cidx); o = __ldcg(out_ptr + cidx); }
+        int64_t o = 0; unsigned long long w = 0ull; double g = 0.0, aux = 0.0, lb = 0.0, ub = 0.0;
+        if (active) {      // one round trip: the work-list entry and the row's record, parked by the compaction kernel in the cut's own scalar arrays
+            w = __ldcg(p.worklist + cidx); o = __ldcg(out_ptr + cidx);
+            g = __ldcg(out_g + cidx); aux = __ldcg(out_b + cidx); lb = __ldcg(out_lo + cidx); ub = __ldcg(out_hi + cidx);
+        }
         if (threadIdx.x == 0) { s_e0 = (unsigned long long)o; const unsigned long long cend = c0 + KTN_XBLOCK < ca ? c0 + KTN_XBLOCK : ca; s_e1 = (unsigned long long)__ldcg(out_ptr + cend); }
         const bool mine = active && w != 0ull;
         // the block's slice of the CSR is staged when every cut of the block is a family cut (else: straight to the CSR)
+#ifndef KTN_X_NOSTAGE
         const int staged = __syncthreads_and((mine || !active) ? 1 : 0);
+#else
+        const int staged = 0; __syncthreads();
+#endif
         const unsigned long long e0 = s_e0, e1 = s_e1;
         if (mine) {
-            const double g = __ldcg(out_g + cidx), aux = __ldcg(out_b + cidx), lb = __ldcg(out_lo + cidx), ub = __ldcg(out_hi + cidx);      // parked by the compaction kernel
             const uint32_t slot = (uint32_t)w, c = slot >> 5, ln = slot & 31u, nu = (uint32_t)(w >> 32) & 0xffu;
             const int fam = (int)((w >> 40) & 0xffu);
             const unsigned char* blob = p.blob + p.cls_blob_off[fam][nu] + (size_t)(c - p.cls_begin[fam][nu]) * KTN_FAM_BLOB_BYTES(nu);
