@@ -456,3 +456,46 @@ def test_ladder_matches_the_sequential_search(oracle_lib, cuda_lib):
     (no, bo), (nc, bc) = ho.separate_ladder(np.zeros(3)), hc.separate_ladder(np.zeros(3))
     assert no == nc == 2 and bo.status == KTN_NUMERIC_NONFINITE
     assert_batches_identical(bo, bc, "ladder, non-finite")
+
+
+def test_ten_million_rows(oracle_lib, cuda_lib):
+    """BASELINE.json configs[4], largest size: 10^7 log-sum-exp rows, 10^6 variables, on ONE handle (loaded in ten batches).  Rows are
+    independent given x*, so the round's cuts restricted to rows [k 10^6, (k+1) 10^6) must equal, bit for bit, the round of an
+    oracle that holds only those rows (same bounds); three such slices are compared in full (first, middle, last), the rest
+    through size-independent properties."""
+    nv, piece, pieces = 1000000, 1000000, 10
+    nr = piece * pieces
+    x0 = cuda_lib.synth_point(1, 20260002, nv)
+    hc = cuda_lib.create()
+    hc.load_begin(nv, nr)
+    for k in range(pieces):
+        hc.add_rows(k * piece, cuda_lib.synth_rows(1, 20260002, nv, k * piece, piece))
+    hc.load_end()
+    g = hc.eval_g(x0)
+    ubv = float(np.quantile(g, 0.9))
+    hc.set_bounds(np.full(nr, -np.inf), np.full(nr, ubv))
+    b = hc.separate(x0)
+    assert abs(b.n_cuts - 0.1 * nr) < 0.001 * nr and np.all(np.diff(b.row_id) > 0)
+    assert b.row_ptr[0] == 0 and np.all(np.diff(b.row_ptr) > 0) and b.row_ptr[-1] == len(b.col) == len(b.val)
+    assert np.all(b.g > ubv + 1e-6) and np.array_equal(b.g, g[b.row_id]) and np.array_equal(b.hi, ubv - b.bconst)
+    sel = np.zeros(nr, bool); sel[b.row_id] = True
+    assert np.all(g[~sel] <= ubv + 1e-6)
+    lin = np.add.reduceat(b.val * x0[b.col], b.row_ptr[:-1]) + b.bconst
+    assert np.allclose(lin, b.g, rtol=1e-12, atol=1e-12)
+    os.environ["KTN_ORACLE_THREADS"] = str(os.cpu_count() or 1)
+    try:
+        for k in (0, 4, 9):
+            w = cuda_lib.synth_rows(1, 20260002, nv, k * piece, piece)
+            ho = oracle_lib.create(); ho.load(nv, w); ho.set_bounds(w.lb, np.full(piece, ubv))
+            bo = ho.separate(x0)
+            c0, c1 = np.searchsorted(b.row_id, [k * piece, (k + 1) * piece])
+            assert bo.n_cuts == c1 - c0
+            e0, e1 = b.row_ptr[c0], b.row_ptr[c1]
+            assert np.array_equal(bo.row_id + k * piece, b.row_id[c0:c1]) and np.array_equal(bo.row_ptr, b.row_ptr[c0:c1 + 1] - e0)
+            for f, sl in (("col", slice(e0, e1)), ("val", slice(e0, e1)), ("lo", slice(c0, c1)), ("hi", slice(c0, c1)), ("g", slice(c0, c1)),
+                          ("viol", slice(c0, c1)), ("bconst", slice(c0, c1))):
+                assert bits_equal(getattr(bo, f), getattr(b, f)[sl]), (k, f)
+            assert bits_equal(ho.get_g(), g[k * piece:(k + 1) * piece])
+            ho.close()
+    finally:
+        os.environ.pop("KTN_ORACLE_THREADS", None)
