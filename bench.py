@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--violated", dest="v", type=float, default=0.1, help="violated fraction of the rows at x* (not --v: torchrun's own parser claims that prefix)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=4, help="e2e leg: shards per device whose cut downloads overlap the following shards' kernels (1 = one plain handle)")
     ap.add_argument("--skip-e2e", action="store_true", help="exchange sweeps only: skip the end-to-end leg and the sharded parity check (the line then carries no e2e)")
     ap.add_argument("--topk", type=int, default=0, help="build extension: keep only the k most violated rows per round (0 = reference behaviour: all)")
     args = ap.parse_args()
@@ -330,18 +331,27 @@ def main():
     x_host = x0.copy()
     e2e_steps = max(3, min(args.steps, 20))
     if world == 1:
-        sep = KatanaGPUSeparator(); sep.handle = h; sep.num_var, sep.num_constr = nv, rows
-        e2e_call = "KatanaGPUSeparator.separate(xstar) -> CutBatch (ktn_separate + ktn_fetch_cuts_view: x* from host memory, cuts into the library's pinned buffer)"
+        # the separator as a Katana user creates it for a large model: the rows in `args.pipeline` consecutive shards on the one device, every
+        # shard's cuts downloaded as soon as it has finished (KTN_FLAG_EAGER_VIEW)
+        sep = KatanaGPUSeparator(devices=[local], pipeline=args.pipeline)
+        if args.pipeline > 1:
+            hp = lib.create(**sep.handle_options()); hp.load(nv, w); hp.set_bounds(w.lb, ub)
+        else:
+            hp = h
+        sep.handle = hp; sep.num_var, sep.num_constr = nv, rows
+        e2e_call = (f"KatanaGPUSeparator(pipeline={args.pipeline}).separate(xstar) -> CutBatch (ktn_separate + ktn_fetch_cuts_view: x* from host memory, cuts into the "
+                    "library's pinned buffer; the rows run as consecutive shards whose downloads overlap the later shards' kernels)")
     elif rank == 0:
         # ONE separator in ONE process over all world*rows rows, as the reference owns it (src/Katana.jl:18): ktn_options.ngpus
-        hg = lib.create(flags=FLAG_LEAN_VIEW, ngpus=world, devices=list(range(world)))
+        sepg = KatanaGPUSeparator(ngpus=world, pipeline=args.pipeline)
+        hg = lib.create(**sepg.handle_options())
         hg.load_begin(nv, world * rows)
         for r in range(world):
             hg.add_rows(r * rows, w if r == 0 else lib.synth_rows(kind, seed, nv, r * rows, rows))
         hg.load_end()
         hg.set_bounds(np.full(world * rows, -np.inf), np.repeat(np.array(ubs), rows))
-        sep = KatanaGPUSeparator(ngpus=world); sep.handle = hg; sep.num_var, sep.num_constr = nv, world * rows
-        e2e_call = (f"KatanaGPUSeparator(ngpus={world}).separate(xstar) -> ONE CutBatch of all {world} devices' cuts in host memory (single process: x* uploaded to every "
+        sep = sepg; sep.handle = hg; sep.num_var, sep.num_constr = nv, world * rows
+        e2e_call = (f"KatanaGPUSeparator(ngpus={world}, pipeline={args.pipeline}).separate(xstar) -> ONE CutBatch of all {world} devices' cuts in host memory (single process: x* uploaded to every "
                     "device, rounds side by side, every device downloads its cuts over its own PCIe link into one pinned buffer)")
     e2e_dt, batch = None, None
     if world == 1 or rank == 0:

@@ -99,6 +99,11 @@ typedef struct ktn_options {
 enum {
     KTN_FLAG_LEAN_VIEW = 1, /* ktn_fetch_cuts_view downloads only what the LP needs (row_id, row_ptr, col, val, lo, hi);
                                g, viol and bconst come back NULL: 11 % less PCIe traffic per round */
+    KTN_FLAG_EAGER_VIEW = 4,  /* multi-device handles (ktn_options.ngpus > 1; the same device may be listed several times to pipeline ONE
+                               device): ktn_separate starts every shard's cut download the moment that shard has finished, into a
+                               pinned buffer laid out for the worst case (every nonlinear row cut: 32 bytes per nonlinear row + 12 per
+                               Jacobian entry, twice); ktn_fetch_cuts_view then only waits.  The download of the first shards overlaps
+                               the kernels of the later ones.  Ignored when that buffer would exceed 1 GiB. */
     KTN_FLAG_TIME_KERNELS = 2 /* ktn_timings.compact_ms / cut_ms are timed separately (one more CUDA event per round, between the
                                compaction and the cut kernel); otherwise compact_ms covers both and cut_ms is 0 */
 };

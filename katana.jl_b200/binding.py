@@ -20,6 +20,7 @@ ROW_NL, ROW_DENSE = 1, 2
 KTN_OK, KTN_NUMERIC_NONFINITE = 0, 1
 FLAG_LEAN_VIEW = 1          # ktn_options.flags: cut views carry only what the LP needs
 FLAG_TIME_KERNELS = 2       # compaction and cut kernel timed separately (one more event per round)
+FLAG_EAGER_VIEW = 4         # multi-device / pipelined handles: every shard's cuts are downloaded as soon as that shard has finished
 SYNTH_QCQP, SYNTH_LSE, SYNTH_SOC = 0, 1, 2
 
 

@@ -629,7 +629,7 @@ static void group_destroy(ktn_handle* f) {
     f->shards.clear();
     cudaSetDevice(f->device);
     if (f->g_hx) cudaFreeHost(f->g_hx);
-    for (int i = 0; i < 2; ++i) if (f->h_view[i]) cudaFreeHost(f->h_view[i]);
+    for (int i = 0; i < 2; ++i) { if (f->h_view[i]) cudaFreeHost(f->h_view[i]); if (f->g_eager[i]) cudaFreeHost(f->g_eager[i]); }
     delete f;
 }
 
@@ -643,6 +643,8 @@ static int group_load_begin(ktn_handle* f, int64_t num_var, int64_t num_constr) 
     }
     cudaSetDevice(f->device);
     if (f->g_hx) { cudaFreeHost(f->g_hx); f->g_hx = nullptr; }
+    for (int i = 0; i < 2; ++i) if (f->g_eager[i]) { cudaFreeHost(f->g_eager[i]); f->g_eager[i] = nullptr; }
+    f->eager_valid = false; f->eager_cap_cuts = f->eager_cap_nnz = 0;
     CK(f, cudaHostAlloc(&f->g_hx, 8 * ((size_t)num_var + 1), cudaHostAllocPortable));
     f->loading = true;
     return KTN_OK;
@@ -674,6 +676,16 @@ static int group_load_end(ktn_handle* f) {
     for (std::thread& t : th) t.join();
     for (size_t s = 0; s < n; ++s) if (rc[s]) return group_fail(f, f->shards[s], rc[s]);
     f->loading = false; f->loaded = true;
+    if (f->opt.flags & KTN_FLAG_EAGER_VIEW) {       // worst-case layout of the combined batch: every nonlinear row cut
+        int64_t cc = 0, zz = 0;
+        for (ktn_handle* s : f->shards) for (int64_t i = 0; i < s->prob.num_constr; ++i) if (s->prob.flags[i] & KTN_ROW_NL) { ++cc; zz += s->prob.jac_ptr[i + 1] - s->prob.jac_ptr[i]; }
+        const size_t total = (size_t)ktn_pack_layout((unsigned long long)cc, (unsigned long long)zz).total;
+        if (total <= ((size_t)1 << 30)) {
+            cudaSetDevice(f->device);
+            for (int i = 0; i < 2; ++i) CK(f, cudaHostAlloc(&f->g_eager[i], total + 64, cudaHostAllocPortable));
+            f->eager_cap_cuts = cc; f->eager_cap_nnz = zz;
+        }
+    }
     return KTN_OK;
 }
 
@@ -699,16 +711,42 @@ static int group_round(ktn_handle* f, const double* x, const int64_t* rows, int6
         int rc = enqueue_round(h, h->x.as<double>(), rows ? KTN_MODE_FORCE : KTN_MODE_SEPARATE, do_round); if (rc) return group_fail(f, h, rc);
     }
     int64_t tc = 0, tz = 0, er = -1; bool stopped = false;
+    const bool eager = f->g_eager[0] != nullptr && !rows;      // separation rounds only: the unconditional rounds may select rows outside nlconstr_ixs
+    const bool lean = (f->opt.flags & KTN_FLAG_LEAN_VIEW) != 0;
+    unsigned char* ebuf = nullptr; KtnPackLayout EL;
+    if (eager) { f->eager_cur ^= 1; ebuf = f->g_eager[f->eager_cur]; EL = ktn_pack_layout((unsigned long long)f->eager_cap_cuts, (unsigned long long)f->eager_cap_nnz); }
+    f->eager_valid = false;
     for (size_t s = 0; s < n; ++s) {
         ktn_handle* h = f->shards[s];
         cudaSetDevice(h->device);
         int64_t c = 0, z = 0, e = -1;
         int rc = finish_round(h, &c, &z, &e); if (rc < 0) return group_fail(f, h, rc);
+        if (eager && !stopped && c > 0) {      // this shard's cuts go to their final place now; the later shards are still computing
+            const KtnPackLayout S = ktn_pack_layout((unsigned long long)h->lay_cuts, (unsigned long long)h->lay_nnz);
+            const unsigned char* src = h->out_blob[h->out_cur].as<unsigned char>();
+            const size_t cb = (size_t)tc, zb = (size_t)tz, cs = (size_t)c, zs = (size_t)z;
+            if (h->rp_shift.bytes < 8 * (cs + 1)) CK(f, h->rp_shift.alloc(8 * (cs + 1) + 8 * (cs + 1) / 4));
+            ktn_launch_shift(reinterpret_cast<const int64_t*>(src + S.row_ptr), h->rp_shift.as<int64_t>(), (int64_t)cs, (int64_t)zb, h->stream);
+            CK(f, cudaMemcpyAsync(ebuf + EL.row_id + 8 * cb, src + S.row_id, 8 * cs, cudaMemcpyDeviceToHost, h->stream));
+            CK(f, cudaMemcpyAsync(ebuf + EL.row_ptr + 8 * cb, h->rp_shift.p, 8 * cs, cudaMemcpyDeviceToHost, h->stream));
+            CK(f, cudaMemcpyAsync(ebuf + EL.lo + 8 * cb, src + S.lo, 8 * cs, cudaMemcpyDeviceToHost, h->stream));
+            CK(f, cudaMemcpyAsync(ebuf + EL.hi + 8 * cb, src + S.hi, 8 * cs, cudaMemcpyDeviceToHost, h->stream));
+            if (!lean) {
+                CK(f, cudaMemcpyAsync(ebuf + EL.g + 8 * cb, src + S.g, 8 * cs, cudaMemcpyDeviceToHost, h->stream));
+                CK(f, cudaMemcpyAsync(ebuf + EL.viol + 8 * cb, src + S.viol, 8 * cs, cudaMemcpyDeviceToHost, h->stream));
+                CK(f, cudaMemcpyAsync(ebuf + EL.b + 8 * cb, src + S.b, 8 * cs, cudaMemcpyDeviceToHost, h->stream));
+            }
+            if (zs) {
+                CK(f, cudaMemcpyAsync(ebuf + EL.col + 4 * zb, src + S.col, 4 * zs, cudaMemcpyDeviceToHost, h->stream));
+                CK(f, cudaMemcpyAsync(ebuf + EL.val + 8 * zb, src + S.val, 8 * zs, cudaMemcpyDeviceToHost, h->stream));
+            }
+        }
         float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->tm.h2d_ms = ms;
         if (stopped) { c = 0; z = 0; }                         // the reference never reaches the rows behind the first non-finite cut
         f->sh_cuts[s] = c; f->sh_nnz[s] = z; tc += c; tz += z;
         if (!stopped && e >= 0) { er = e + f->shard_begin[s]; stopped = true; }
     }
+    f->eager_valid = eager;
     f->n_cuts = tc; f->nnz_cuts = tz; f->err_row = er; f->have_round = true;
     if (n_cuts) *n_cuts = tc;
     if (nnz) *nnz = tz;
@@ -721,6 +759,34 @@ static int group_fetch(ktn_handle* f, ktn_cut_view* view, int64_t* row_id, int64
     if (!f->have_round) return fail(f, KTN_ERR_USAGE, "no round has run");
     const size_t nc = (size_t)f->n_cuts, nz = (size_t)f->nnz_cuts;
     const bool lean = view && (f->opt.flags & KTN_FLAG_LEAN_VIEW) != 0;
+    if (f->eager_valid) {       // the copies were started by ktn_separate, shard by shard: wait for them
+        for (ktn_handle* h : f->shards) { cudaSetDevice(h->device); CK(f, cudaStreamSynchronize(h->stream)); }
+        unsigned char* buf = f->g_eager[f->eager_cur];
+        const KtnPackLayout EL = ktn_pack_layout((unsigned long long)f->eager_cap_cuts, (unsigned long long)f->eager_cap_nnz);
+        const bool lv = (f->opt.flags & KTN_FLAG_LEAN_VIEW) != 0;
+        reinterpret_cast<int64_t*>(buf + EL.row_ptr)[nc] = (int64_t)nz;
+        if (view) {
+            view->n_cuts = (int64_t)nc; view->nnz = (int64_t)nz;
+            view->row_id = reinterpret_cast<const int64_t*>(buf + EL.row_id); view->row_ptr = reinterpret_cast<const int64_t*>(buf + EL.row_ptr);
+            view->col = reinterpret_cast<const int32_t*>(buf + EL.col); view->val = reinterpret_cast<const double*>(buf + EL.val);
+            view->lo = reinterpret_cast<const double*>(buf + EL.lo); view->hi = reinterpret_cast<const double*>(buf + EL.hi);
+            view->g = lv ? nullptr : reinterpret_cast<const double*>(buf + EL.g); view->viol = lv ? nullptr : reinterpret_cast<const double*>(buf + EL.viol);
+            view->bconst = lv ? nullptr : reinterpret_cast<const double*>(buf + EL.b);
+            return KTN_OK;
+        }
+        if (!lv) {      // caller buffers: from the pinned copy (a lean handle has no g / viol / bconst there: fall through to the device copies)
+            if (row_id) memcpy(row_id, buf + EL.row_id, 8 * nc);
+            if (row_ptr) memcpy(row_ptr, buf + EL.row_ptr, 8 * (nc + 1));
+            if (col) memcpy(col, buf + EL.col, 4 * nz);
+            if (val) memcpy(val, buf + EL.val, 8 * nz);
+            if (lo) memcpy(lo, buf + EL.lo, 8 * nc);
+            if (hi) memcpy(hi, buf + EL.hi, 8 * nc);
+            if (g) memcpy(g, buf + EL.g, 8 * nc);
+            if (viol) memcpy(viol, buf + EL.viol, 8 * nc);
+            if (bconst) memcpy(bconst, buf + EL.b, 8 * nc);
+            return KTN_OK;
+        }
+    }
     if (view) {
         const KtnPackLayout L = ktn_pack_layout(nc, nz);
         f->view_cur ^= 1;

@@ -89,6 +89,10 @@ struct ktn_handle {
     std::vector<int64_t> sh_cuts, sh_nnz;           // last round: cuts / nnz every shard contributes to the combined batch
     int64_t g_num_var = 0, g_num_constr = 0;
     double* g_hx = nullptr;                         // pinned staging of x* (all devices upload from it)
+    // eager download (KTN_FLAG_EAGER_VIEW): two pinned buffers whose sections are laid out for the WORST case (every nonlinear row cut),
+    // so a shard's cuts can be copied to their final place as soon as that shard has finished, while later shards still compute
+    unsigned char* g_eager[2] = {nullptr, nullptr}; int eager_cur = 0; bool eager_valid = false;
+    int64_t eager_cap_cuts = 0, eager_cap_nnz = 0;
     DevBuf rp_shift;                                // shard: row_ptr of the last round shifted to the combined batch's entry offsets
 };
 

@@ -7,7 +7,7 @@ state (g, Jacobian rows, xstar) on the device behind the C ABI of include/ktn.h.
 """
 import numpy as np
 
-from .binding import FLAG_LEAN_VIEW, KTN_NUMERIC_NONFINITE, load_cuda_library
+from .binding import FLAG_EAGER_VIEW, FLAG_LEAN_VIEW, KTN_NUMERIC_NONFINITE, load_cuda_library
 from .nlpeval import rows_to_wire
 
 
@@ -46,12 +46,14 @@ class KatanaGPUSeparator(AbstractKatanaSeparator):
     another implementation of the same C ABI as the checker).
     """
 
-    def __init__(self, library=None, topk=0, ngpus=1, devices=None):
+    def __init__(self, library=None, topk=0, ngpus=1, devices=None, pipeline=1):
         """ngpus > 1: the ONE separator of the model shards its rows over `ngpus` devices of this process (ktn_options.ngpus);
-        `separate` still returns one combined batch in ascending row order to the one LP master."""
+        `separate` still returns one combined batch in ascending row order to the one LP master.
+        pipeline = S > 1: every device's rows are split into S consecutive shards whose cut downloads start as soon as each
+        shard has finished (KTN_FLAG_EAGER_VIEW): the PCIe transfer of the first shards overlaps the kernels of the later ones."""
         self._lib = library
         self.topk = topk
-        self.ngpus, self.devices = ngpus, devices
+        self.ngpus, self.devices, self.pipeline = ngpus, devices, pipeline
         self.handle = None
         self.last = None           # CutBatch of the last precompute!
         self.xstar = None
@@ -65,13 +67,20 @@ class KatanaGPUSeparator(AbstractKatanaSeparator):
         if self.handle is not None:                            # one separator is reused across models (test/runtests.jl:24)
             self.handle.close()
         # lean views: optimize! hands (row_ptr, col, val, lo, hi) to the LP; g / viol / bconst stay on the device
-        self.handle = lib.create(f_tol=f_tol, cut_coef_rng=cut_coef_rng, topk=self.topk, flags=FLAG_LEAN_VIEW,
-                                 ngpus=self.ngpus if self.ngpus > 1 else 0, devices=self.devices)
+        self.handle = lib.create(f_tol=f_tol, cut_coef_rng=cut_coef_rng, topk=self.topk, **self.handle_options())
         self.num_var, self.num_constr = num_var, num_constr
         lb = np.full(num_constr, -np.inf); ub = np.full(num_constr, np.inf)
         self.handle.load(num_var, rows_to_wire(oracle, num_constr, lb, ub))
         self.l_constr, self.u_constr = lb, ub
         self.last = self.g = self.xstar = None
+
+    def handle_options(self):
+        """ktn_options of this separator: lean views (optimize! hands row_ptr, col, val, lo, hi to the LP), the device list, eager downloads."""
+        devs = list(self.devices) if self.devices else list(range(max(self.ngpus, 1)))
+        shards = [d for d in devs for _ in range(max(self.pipeline, 1))]
+        if len(shards) <= 1:
+            return dict(flags=FLAG_LEAN_VIEW, device=devs[0] if self.devices else -1)
+        return dict(flags=FLAG_LEAN_VIEW | (FLAG_EAGER_VIEW if self.pipeline > 1 else 0), ngpus=len(shards), devices=shards)
 
     def set_params(self, f_tol, cut_coef_rng):
         self.handle.set_params(f_tol, cut_coef_rng, self.topk)

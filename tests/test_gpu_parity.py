@@ -499,3 +499,44 @@ def test_ten_million_rows(oracle_lib, cuda_lib):
             ho.close()
     finally:
         os.environ.pop("KTN_ORACLE_THREADS", None)
+
+
+def test_eager_view_pipelined_download(oracle_lib, cuda_lib):
+    """KTN_FLAG_EAGER_VIEW: ktn_separate starts every shard's cut download when that shard has finished, into a pinned buffer laid out
+    for the worst case; the view (and the copy) must equal the oracle's batch bit for bit -- full and lean views, empty and full
+    rounds, several rounds in a row (the two pinned buffers alternate), a non-finite row on the middle shard, and reload."""
+    from katana_jl_b200.binding import FLAG_EAGER_VIEW, FLAG_LEAN_VIEW
+    lean_fields = ("row_id", "row_ptr", "col", "val", "lo", "hi")
+    for kind, nv, nr in ((1, 4000, 9001), (2, 2000, 3000)):
+        w = cuda_lib.synth_rows(kind, 91 + kind, nv, 0, nr); x0 = cuda_lib.synth_point(kind, 91 + kind, nv)
+        ho = oracle_lib.create(); ho.load(nv, w)
+        g = ho.eval_g(x0)
+        for flags in (FLAG_EAGER_VIEW, FLAG_EAGER_VIEW | FLAG_LEAN_VIEW):
+            hs = cuda_lib.create(ngpus=4, devices=[0, 0, 0, 0], flags=flags); hs.load(nv, w)
+            for v in (0.0, 0.07, 1.0, 0.3):
+                ub = np.full(nr, np.quantile(g, 1 - v) if v > 0 else g.max() + 1.0)
+                ho.set_bounds(w.lb, ub); hs.set_bounds(w.lb, ub)
+                bo = ho.separate(x0)
+                bv = hs.separate(x0, view=True)
+                assert bo.status == bv.status and bo.err_row == bv.err_row and bo.n_cuts == bv.n_cuts
+                for f in (lean_fields if flags & FLAG_LEAN_VIEW else BATCH_FIELDS):
+                    assert bits_equal(getattr(bo, f), getattr(bv, f)), (kind, flags, v, f)
+                assert_batches_identical(bo, hs.separate(x0), f"eager, copy, kind {kind} v {v}")
+            rows = np.arange(0, nr, 17, dtype=np.int64)
+            assert_batches_identical(ho.gencut_rows(x0, rows, True), hs.gencut_rows(x0, rows, True), "eager handle, gencut")
+            hs.close()
+        ho.close()
+    x, y, z = E.var(0), E.var(1), E.var(2)
+    exprs = [x**2 + y**2 - 1.0] * 50 + [E.sqrt(x**2 + y**2) - (z - 0.25)] + [x**2 + y**2 - 1.0] * 39
+    m = len(exprs)
+    w = E.to_wire(exprs, np.full(m, -np.inf), np.full(m, -2.0), [ROW_NL] * m)
+    ho = oracle_lib.create(); ho.load(3, w)
+    hs = cuda_lib.create(ngpus=3, devices=[0, 0, 0], flags=FLAG_EAGER_VIEW); hs.load(3, w)
+    bo = ho.separate(np.zeros(3))
+    assert bo.status == KTN_NUMERIC_NONFINITE and bo.n_cuts == 50
+    assert_batches_identical(bo, hs.separate(np.zeros(3), view=True), "eager view, truncated on the middle shard")
+    assert_batches_identical(ho.separate(np.ones(3)), hs.separate(np.ones(3), view=True))
+    nv2, w2, pts = kat_problem()
+    ho.load(nv2, w2); hs.load(nv2, w2)
+    for p in pts:
+        assert_batches_identical(ho.separate(p), hs.separate(p, view=True), "eager KAT")
