@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--violated", dest="v", type=float, default=0.1, help="violated fraction of the rows at x* (not --v: torchrun's own parser claims that prefix)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=4, help="e2e leg: shards per device whose cut downloads overlap the following shards' kernels (1 = one plain handle)")
+    ap.add_argument("--pipeline", type=int, default=1, help="e2e leg: shards per device whose cut downloads overlap the following shards' kernels (KTN_FLAG_EAGER_VIEW). Measured on the B200 box, 10^6 LSE rows: 1 (one plain handle): 0.65 ms, 2: 0.68, 4: 0.77, 8: 1.02 -- the per-shard launches and copies cost the host more than the overlap saves, so the default is 1")
     ap.add_argument("--skip-e2e", action="store_true", help="exchange sweeps only: skip the end-to-end leg and the sharded parity check (the line then carries no e2e)")
     ap.add_argument("--topk", type=int, default=0, help="build extension: keep only the k most violated rows per round (0 = reference behaviour: all)")
     args = ap.parse_args()
@@ -339,8 +339,9 @@ def main():
         else:
             hp = h
         sep.handle = hp; sep.num_var, sep.num_constr = nv, rows
-        e2e_call = (f"KatanaGPUSeparator(pipeline={args.pipeline}).separate(xstar) -> CutBatch (ktn_separate + ktn_fetch_cuts_view: x* from host memory, cuts into the "
-                    "library's pinned buffer; the rows run as consecutive shards whose downloads overlap the later shards' kernels)")
+        e2e_call = "KatanaGPUSeparator.separate(xstar) -> CutBatch (ktn_separate + ktn_fetch_cuts_view: x* from host memory, cuts into the library's pinned buffer)"
+        if args.pipeline > 1:
+            e2e_call += f"; pipeline={args.pipeline}: the rows run as consecutive shards whose downloads overlap the later shards' kernels"
     elif rank == 0:
         # ONE separator in ONE process over all world*rows rows, as the reference owns it (src/Katana.jl:18): ktn_options.ngpus
         sepg = KatanaGPUSeparator(ngpus=world, pipeline=args.pipeline)
