@@ -109,11 +109,11 @@ enum {
 };
 
 typedef struct ktn_timings {
-    double h2d_ms;        /* x* upload */
+    double h2d_ms;        /* x* upload (timed with KTN_FLAG_TIME_KERNELS only: two CUDA events per call otherwise saved) */
     double kernel_ms;     /* separation kernels, CUDA events on the library stream */
     double exchange_ms;   /* sharded handles: the last synced exchange's transfer on the exchange stream (the push kernel / the
                              ncclAllGather, CUDA events; it runs beside the following rounds, so it is NOT part of kernel_ms) */
-    double d2h_ms;        /* cut download in ktn_fetch_cuts */
+    double d2h_ms;        /* cut download in ktn_fetch_cuts (KTN_FLAG_TIME_KERNELS only) */
     int64_t launches;     /* kernels launched by this library since creation */
     int64_t rounds;       /* separation rounds run since creation */
     double eval_ms;       /* last round: evaluation kernel(s) (K1) */

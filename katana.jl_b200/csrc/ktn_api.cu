@@ -343,9 +343,9 @@ static int finish_round(ktn_handle* h, int64_t* n_cuts, int64_t* nnz, int64_t* e
 
 static int upload_x(ktn_handle* h, const double* x) {
     memcpy(h->h_x, x, 8 * (size_t)h->prob.num_var);
-    CK(h, cudaEventRecord(h->ev0, h->stream));
+    if (h->opt.flags & KTN_FLAG_TIME_KERNELS) CK(h, cudaEventRecord(h->ev0, h->stream));
     CK(h, cudaMemcpyAsync(h->x.p, h->h_x, 8 * (size_t)h->prob.num_var, cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaEventRecord(h->ev1, h->stream));
+    if (h->opt.flags & KTN_FLAG_TIME_KERNELS) CK(h, cudaEventRecord(h->ev1, h->stream));
     return KTN_OK;
 }
 
@@ -356,7 +356,7 @@ extern "C" int ktn_separate(ktn_handle* h, const double* xstar, int64_t* n_cuts,
     int rc = upload_x(h, xstar); if (rc) return rc;
     rc = enqueue_round(h, h->x.as<double>(), KTN_MODE_SEPARATE, 1); if (rc) return rc;
     rc = finish_round(h, n_cuts, nnz, err_row);
-    float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->tm.h2d_ms = ms;
+    float ms = 0.f; if ((h->opt.flags & KTN_FLAG_TIME_KERNELS) && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->tm.h2d_ms = ms;
     return rc;
 }
 
@@ -434,7 +434,7 @@ extern "C" int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, 
     const size_t nc = (size_t)h->n_cuts, nz = (size_t)h->nnz_cuts;
     const KtnPackLayout S = ktn_pack_layout((unsigned long long)h->lay_cuts, (unsigned long long)h->lay_nnz);      // where K2 put the sections
     const unsigned char* src = h->out_blob[h->out_cur].as<unsigned char>();
-    CK(h, cudaEventRecord(h->ev2, h->stream));
+    if (h->opt.flags & KTN_FLAG_TIME_KERNELS) CK(h, cudaEventRecord(h->ev2, h->stream));
     if (row_id && nc) CK(h, cudaMemcpyAsync(row_id, src + S.row_id, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
     if (row_ptr) { if (nc) CK(h, cudaMemcpyAsync(row_ptr, src + S.row_ptr, 8 * nc, cudaMemcpyDeviceToHost, h->stream)); }
     if (col && nz) CK(h, cudaMemcpyAsync(col, src + S.col, 4 * nz, cudaMemcpyDeviceToHost, h->stream));
@@ -444,10 +444,10 @@ extern "C" int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, 
     if (g && nc) CK(h, cudaMemcpyAsync(g, src + S.g, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
     if (viol && nc) CK(h, cudaMemcpyAsync(viol, src + S.viol, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
     if (bconst && nc) CK(h, cudaMemcpyAsync(bconst, src + S.b, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaEventRecord(h->ev3, h->stream));
+    if (h->opt.flags & KTN_FLAG_TIME_KERNELS) CK(h, cudaEventRecord(h->ev3, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     if (row_ptr) row_ptr[nc] = (int64_t)nz;   // the device array ends at the untruncated total
-    float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev2, h->ev3) == cudaSuccess) h->tm.d2h_ms = ms;
+    float ms = 0.f; if ((h->opt.flags & KTN_FLAG_TIME_KERNELS) && cudaEventElapsedTime(&ms, h->ev2, h->ev3) == cudaSuccess) h->tm.d2h_ms = ms;
     return KTN_OK;
 }
 
@@ -473,7 +473,7 @@ extern "C" int ktn_fetch_cuts_view(ktn_handle* h, ktn_cut_view* out) {
     }
     const KtnPackLayout S = ktn_pack_layout((unsigned long long)h->lay_cuts, (unsigned long long)h->lay_nnz);      // where K2 put the sections
     const unsigned char* src = h->out_blob[h->out_cur].as<unsigned char>();
-    CK(h, cudaEventRecord(h->ev2, h->stream));
+    if (h->opt.flags & KTN_FLAG_TIME_KERNELS) CK(h, cudaEventRecord(h->ev2, h->stream));
     if ((size_t)h->lay_cuts == nc && (size_t)h->lay_nnz == nz) {      // no truncation: source and view layouts coincide
         if (!lean) { if (nc) CK(h, cudaMemcpyAsync(buf + L.row_id, src + S.row_id, L.total - L.row_id, cudaMemcpyDeviceToHost, h->stream)); }
         else if (nc) {
@@ -497,10 +497,10 @@ extern "C" int ktn_fetch_cuts_view(ktn_handle* h, ktn_cut_view* out) {
             CK(h, cudaMemcpyAsync(buf + L.val, src + S.val, 8 * nz, cudaMemcpyDeviceToHost, h->stream));
         }
     }
-    CK(h, cudaEventRecord(h->ev3, h->stream));
+    if (h->opt.flags & KTN_FLAG_TIME_KERNELS) CK(h, cudaEventRecord(h->ev3, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     reinterpret_cast<int64_t*>(buf + L.row_ptr)[nc] = (int64_t)nz;   // the device array ends at the untruncated total
-    float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev2, h->ev3) == cudaSuccess) h->tm.d2h_ms = ms;
+    float ms = 0.f; if ((h->opt.flags & KTN_FLAG_TIME_KERNELS) && cudaEventElapsedTime(&ms, h->ev2, h->ev3) == cudaSuccess) h->tm.d2h_ms = ms;
     out->n_cuts = (int64_t)nc; out->nnz = (int64_t)nz;
     out->row_id = reinterpret_cast<const int64_t*>(buf + L.row_id); out->row_ptr = reinterpret_cast<const int64_t*>(buf + L.row_ptr);
     out->col = reinterpret_cast<const int32_t*>(buf + L.col); out->val = reinterpret_cast<const double*>(buf + L.val);
@@ -705,9 +705,9 @@ static int group_round(ktn_handle* f, const double* x, const int64_t* rows, int6
             CK(f, cudaStreamSynchronize(h->stream));
             CK(f, cudaMemcpy(h->force.p, mask.data(), (size_t)m, cudaMemcpyHostToDevice));
         }
-        CK(f, cudaEventRecord(h->ev0, h->stream));
+        if (f->opt.flags & KTN_FLAG_TIME_KERNELS) CK(f, cudaEventRecord(h->ev0, h->stream));
         CK(f, cudaMemcpyAsync(h->x.p, f->g_hx, 8 * (size_t)f->g_num_var, cudaMemcpyHostToDevice, h->stream));
-        CK(f, cudaEventRecord(h->ev1, h->stream));
+        if (f->opt.flags & KTN_FLAG_TIME_KERNELS) CK(f, cudaEventRecord(h->ev1, h->stream));
         int rc = enqueue_round(h, h->x.as<double>(), rows ? KTN_MODE_FORCE : KTN_MODE_SEPARATE, do_round); if (rc) return group_fail(f, h, rc);
     }
     int64_t tc = 0, tz = 0, er = -1; bool stopped = false;
@@ -741,7 +741,7 @@ static int group_round(ktn_handle* f, const double* x, const int64_t* rows, int6
                 CK(f, cudaMemcpyAsync(ebuf + EL.val + 8 * zb, src + S.val, 8 * zs, cudaMemcpyDeviceToHost, h->stream));
             }
         }
-        float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->tm.h2d_ms = ms;
+        float ms = 0.f; if ((h->opt.flags & KTN_FLAG_TIME_KERNELS) && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->tm.h2d_ms = ms;
         if (stopped) { c = 0; z = 0; }                         // the reference never reaches the rows behind the first non-finite cut
         f->sh_cuts[s] = c; f->sh_nnz[s] = z; tc += c; tz += z;
         if (!stopped && e >= 0) { er = e + f->shard_begin[s]; stopped = true; }
@@ -813,7 +813,7 @@ static int group_fetch(ktn_handle* f, ktn_cut_view* view, int64_t* row_id, int64
         cudaSetDevice(h->device);
         const KtnPackLayout S = ktn_pack_layout((unsigned long long)h->lay_cuts, (unsigned long long)h->lay_nnz);
         const unsigned char* src = h->out_blob[h->out_cur].as<unsigned char>();
-        CK(f, cudaEventRecord(h->ev2, h->stream));
+        if (f->opt.flags & KTN_FLAG_TIME_KERNELS) CK(f, cudaEventRecord(h->ev2, h->stream));
         if (row_id) CK(f, cudaMemcpyAsync(row_id + cb, src + S.row_id, 8 * c, cudaMemcpyDeviceToHost, h->stream));
         if (row_ptr) {     // the shard's entry offsets start at 0: shifted on the device to the combined batch's
             if (h->rp_shift.bytes < 8 * (c + 1)) CK(f, h->rp_shift.alloc(8 * (c + 1) + 8 * (c + 1) / 4));
@@ -827,7 +827,7 @@ static int group_fetch(ktn_handle* f, ktn_cut_view* view, int64_t* row_id, int64
         if (bconst) CK(f, cudaMemcpyAsync(bconst + cb, src + S.b, 8 * c, cudaMemcpyDeviceToHost, h->stream));
         if (col && z) CK(f, cudaMemcpyAsync(col + zb, src + S.col, 4 * z, cudaMemcpyDeviceToHost, h->stream));
         if (val && z) CK(f, cudaMemcpyAsync(val + zb, src + S.val, 8 * z, cudaMemcpyDeviceToHost, h->stream));
-        CK(f, cudaEventRecord(h->ev3, h->stream));
+        if (f->opt.flags & KTN_FLAG_TIME_KERNELS) CK(f, cudaEventRecord(h->ev3, h->stream));
         cb += c; zb += z;
     }
     for (size_t s = 0; s < f->shards.size(); ++s) {
@@ -835,7 +835,7 @@ static int group_fetch(ktn_handle* f, ktn_cut_view* view, int64_t* row_id, int64
         if (f->sh_cuts[s] == 0) continue;
         cudaSetDevice(h->device);
         CK(f, cudaStreamSynchronize(h->stream));
-        float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev2, h->ev3) == cudaSuccess) h->tm.d2h_ms = ms;
+        float ms = 0.f; if ((h->opt.flags & KTN_FLAG_TIME_KERNELS) && cudaEventElapsedTime(&ms, h->ev2, h->ev3) == cudaSuccess) h->tm.d2h_ms = ms;
     }
     if (row_ptr) row_ptr[nc] = (int64_t)nz;
     if (view) {
