@@ -189,7 +189,8 @@ def main():
     ap.add_argument("--violated", dest="v", type=float, default=0.1, help="violated fraction of the rows at x* (not --v: torchrun's own parser claims that prefix)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=1, help="e2e leg: shards per device whose cut downloads overlap the following shards' kernels (KTN_FLAG_EAGER_VIEW). Measured on the B200 box, 10^6 LSE rows: 1 (one plain handle): 0.65 ms, 2: 0.68, 4: 0.77, 8: 1.02 -- the per-shard launches and copies cost the host more than the overlap saves, so the default is 1")
+    ap.add_argument("--pipeline", type=int, default=0, help="e2e leg: shards per device whose cut transfers overlap the following shards' kernels (KTN_FLAG_EAGER_VIEW); 0 = KatanaGPUSeparator's own measured default (one device: two shards from 400 000 rows on -- 10^6 LSE rows: 1 shard 0.604 ms, 2: 0.575, 3: 0.587, 4: 0.632, 8: 0.76; several devices: 1)")
+    ap.add_argument("--direct", type=int, default=0, help="e2e leg at one GPU, one shard: 1 = the round's kernels store the cuts straight into the pinned host buffer (KTN_FLAG_DIRECT_VIEW; measured 0.622 ms against 0.604); 0 = the separator's default: device blob + one download after the round")
     ap.add_argument("--skip-e2e", action="store_true", help="exchange sweeps only: skip the end-to-end leg and the sharded parity check (the line then carries no e2e)")
     ap.add_argument("--topk", type=int, default=0, help="build extension: keep only the k most violated rows per round (0 = reference behaviour: all)")
     args = ap.parse_args()
@@ -333,26 +334,31 @@ def main():
     if world == 1:
         # the separator as a Katana user creates it for a large model: the rows in `args.pipeline` consecutive shards on the one device, every
         # shard's cuts downloaded as soon as it has finished (KTN_FLAG_EAGER_VIEW)
-        sep = KatanaGPUSeparator(devices=[local], pipeline=args.pipeline)
-        if args.pipeline > 1:
-            hp = lib.create(**sep.handle_options()); hp.load(nv, w); hp.set_bounds(w.lb, ub)
+        sep = KatanaGPUSeparator(devices=[local], pipeline=args.pipeline or None, direct=bool(args.direct))
+        per = sep.shards_per_device(rows)
+        if per > 1 or args.direct:
+            hp = lib.create(**sep.handle_options(rows)); hp.load(nv, w); hp.set_bounds(w.lb, ub)
         else:
             hp = h
         sep.handle = hp; sep.num_var, sep.num_constr = nv, rows
         e2e_call = "KatanaGPUSeparator.separate(xstar) -> CutBatch (ktn_separate + ktn_fetch_cuts_view: x* from host memory, cuts into the library's pinned buffer)"
-        if args.pipeline > 1:
-            e2e_call += f"; pipeline={args.pipeline}: the rows run as consecutive shards whose downloads overlap the later shards' kernels"
+        if args.direct and per <= 1:
+            e2e_call = ("KatanaGPUSeparator.separate(xstar) -> CutBatch (ktn_separate + ktn_fetch_cuts_view: x* from host memory; KTN_FLAG_DIRECT_VIEW: the cut kernels "
+                        "store the batch over PCIe straight into the library's pinned host buffer while they build it, no copy afterwards)")
+        if per > 1:
+            e2e_call += (f"; pipeline={per}{'' if args.pipeline else ' (the separator default at this size)'}: the rows run as consecutive shards on one stream, a small kernel per shard "
+                         "stores its cuts into the pinned batch while the next shard computes, one host synchronisation per round")
     elif rank == 0:
         # ONE separator in ONE process over all world*rows rows, as the reference owns it (src/Katana.jl:18): ktn_options.ngpus
-        sepg = KatanaGPUSeparator(ngpus=world, pipeline=args.pipeline)
-        hg = lib.create(**sepg.handle_options())
+        sepg = KatanaGPUSeparator(ngpus=world, pipeline=args.pipeline or None)
+        hg = lib.create(**sepg.handle_options(world * rows))
         hg.load_begin(nv, world * rows)
         for r in range(world):
             hg.add_rows(r * rows, w if r == 0 else lib.synth_rows(kind, seed, nv, r * rows, rows))
         hg.load_end()
         hg.set_bounds(np.full(world * rows, -np.inf), np.repeat(np.array(ubs), rows))
         sep = sepg; sep.handle = hg; sep.num_var, sep.num_constr = nv, world * rows
-        e2e_call = (f"KatanaGPUSeparator(ngpus={world}, pipeline={args.pipeline}).separate(xstar) -> ONE CutBatch of all {world} devices' cuts in host memory (single process: x* uploaded to every "
+        e2e_call = (f"KatanaGPUSeparator(ngpus={world}).separate(xstar) -> ONE CutBatch of all {world} devices' cuts in host memory (single process: x* uploaded to every "
                     "device, rounds side by side, every device downloads its cuts over its own PCIe link into one pinned buffer)")
     e2e_dt, batch = None, None
     if world == 1 or rank == 0:

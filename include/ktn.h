@@ -104,6 +104,11 @@ enum {
                                pinned buffer laid out for the worst case (every nonlinear row cut: 32 bytes per nonlinear row + 12 per
                                Jacobian entry, twice); ktn_fetch_cuts_view then only waits.  The download of the first shards overlaps
                                the kernels of the later ones.  Ignored when that buffer would exceed 1 GiB. */
+    KTN_FLAG_DIRECT_VIEW = 8, /* single-device handles without a communicator: the round's kernels store the cut batch straight into
+                               mapped pinned host memory (two buffers of the worst-case size -- every row cut -- alternate) instead of
+                               device memory, so the PCIe transfer runs WHILE the cuts are built and ktn_fetch_cuts_view copies
+                               nothing.  With KTN_FLAG_LEAN_VIEW the g | viol | b sections are not produced at all.  Ignored when
+                               the two buffers would exceed 2 GiB, on multi-device handles, and once ktn_comm_init has been called. */
     KTN_FLAG_TIME_KERNELS = 2 /* ktn_timings.compact_ms / cut_ms are timed separately (one more CUDA event per round, between the
                                compaction and the cut kernel); otherwise compact_ms covers both and cut_ms is 0 */
 };

@@ -21,6 +21,7 @@ KTN_OK, KTN_NUMERIC_NONFINITE = 0, 1
 FLAG_LEAN_VIEW = 1          # ktn_options.flags: cut views carry only what the LP needs
 FLAG_TIME_KERNELS = 2       # compaction and cut kernel timed separately (one more event per round)
 FLAG_EAGER_VIEW = 4         # multi-device / pipelined handles: every shard's cuts are downloaded as soon as that shard has finished
+FLAG_DIRECT_VIEW = 8        # single-device handles: the kernels store the cut batch straight into mapped pinned host memory
 SYNTH_QCQP, SYNTH_LSE, SYNTH_SOC = 0, 1, 2
 
 

@@ -36,6 +36,8 @@ static void free_problem(ktn_handle* h) {
                      &h->blk_cnt, &h->topk_key, &h->topk_state, &h->topk_eqcnt, &h->table, &h->out_blob[0], &h->out_blob[1], &h->out_blob[2]};
     for (DevBuf* b : all) b->release();
     if (h->h_x) { cudaFreeHost(h->h_x); h->h_x = nullptr; }
+    for (int i = 0; i < 2; ++i) { if (h->h_direct[i]) cudaFreeHost(h->h_direct[i]); h->h_direct[i] = h->d_direct[i] = nullptr; }
+    h->direct = false;
     h->prob = KtnProblem();
     h->loaded = h->loading = h->round_pending = h->have_round = h->forced_last = false;
     h->n_cuts = h->nnz_cuts = 0; h->err_row = -1;
@@ -178,7 +180,7 @@ extern "C" int ktn_load_end(ktn_handle* h) {
     CK(h, upload(h->jac_ptr, P.jac_ptr)); CK(h, upload(h->jac_col, P.jac_col));
     CK(h, upload(h->row_lb, P.lb)); CK(h, upload(h->row_ub, P.ub)); CK(h, upload(h->row_slot, P.row_slot));
     { std::vector<uint8_t> nl(P.flags.size()); for (size_t i = 0; i < nl.size(); ++i) nl[i] = (P.flags[i] & KTN_ROW_NL) ? 1 : 0; CK(h, upload(h->row_nl, nl)); }
-    CK(h, h->rec.alloc(32 * (m + 1))); CK(h, h->worklist.alloc(8 * (m + 1)));
+    CK(h, h->rec.alloc(32 * (m + 1))); CK(h, h->worklist.alloc(8 * (m + 1))); CK(h, h->park.alloc(32 * (m + 1))); CK(h, h->cut_off.alloc(8 * (m + 2)));
     CK(h, upload(h->chunk_jp, P.chunk_jp)); CK(h, h->dump.alloc(24 * (N + 1)));
     CK(h, h->x.alloc(8 * ((size_t)P.num_var + 1))); CK(h, h->force.alloc(m + 16));
     CK(h, h->g_row.alloc(8 * (m + 1))); CK(h, h->b_row.alloc(8 * (m + 1))); CK(h, h->sel.alloc(4 * (m + 1)));
@@ -194,6 +196,16 @@ extern "C" int ktn_load_end(ktn_handle* h) {
     CK(h, h->out_blob[0].alloc(h->out_cap)); h->out_blob[1].release(); h->out_blob[2].release();     // [1], [2]: sharded handles, on first use
     CK(h, cudaMemset(h->out_blob[0].p, 0, 128));       // a shard without rows never runs K2: its blob header must read "nothing"
     CK(h, cudaMallocHost(&h->h_x, 8 * ((size_t)P.num_var + 1)));
+    if ((h->opt.flags & KTN_FLAG_DIRECT_VIEW) && 2 * h->out_cap <= ((size_t)2 << 30)) {      // the cut blob in mapped pinned host memory
+        for (int i = 0; i < 2; ++i) {
+            void* q = nullptr; void* d = nullptr;
+            CK(h, cudaHostAlloc(&q, h->out_cap, cudaHostAllocMapped));
+            h->h_direct[i] = static_cast<unsigned char*>(q); memset(q, 0, 128);
+            CK(h, cudaHostGetDevicePointer(&d, q, 0));
+            h->d_direct[i] = static_cast<unsigned char*>(d);
+        }
+        h->direct = true; h->direct_cur = 0;
+    }
     // the packed blob lives on the device now
     std::vector<uint8_t>().swap(P.blob);
     h->loading = false; h->loaded = true;
@@ -262,7 +274,7 @@ KtnRoundParams ktn_make_params(ktn_handle* h, const double* d_x, int mode, int d
     p.jac_ptr = h->jac_ptr.as<int64_t>(); p.jac_col = h->jac_col.as<int32_t>();
     p.row_lb = h->row_lb.as<double>(); p.row_ub = h->row_ub.as<double>(); p.row_slot = h->row_slot.as<int32_t>();
     p.chunk_jp = h->chunk_jp.as<uint32_t>(); p.dump = h->dump.as<double>(); p.dump_nnz = (uint64_t)h->prob.jac_ptr[h->prob.num_constr];
-    p.rec = h->rec.as<double4>(); p.worklist = h->worklist.as<unsigned long long>(); p.errpos = h->errpos.as<unsigned long long>(); p.blk_off = h->blk_off.as<unsigned long long>();
+    p.rec = h->rec.as<double4>(); p.park = h->park.as<double4>(); p.cut_off = h->cut_off.as<unsigned long long>(); p.worklist = h->worklist.as<unsigned long long>(); p.errpos = h->errpos.as<unsigned long long>(); p.blk_off = h->blk_off.as<unsigned long long>();
     for (int f = 0; f <= KTN_FAM__COUNT; ++f) p.fam_begin[f] = h->prob.fam_begin[f];
     memcpy(p.cls_begin, h->prob.cls_begin, sizeof p.cls_begin); memcpy(p.cls_blob_off, h->prob.cls_blob_off, sizeof p.cls_blob_off);
     p.x = d_x; p.force = h->force.as<uint8_t>();
@@ -278,6 +290,10 @@ KtnRoundParams ktn_make_params(ktn_handle* h, const double* d_x, int mode, int d
     p.row_offset = h->row_offset;
     p.table = h->table.as<unsigned char>(); p.table_bytes = h->table_bytes; p.table_prog_off = h->table_prog_off; p.epoch = h->epoch;
     p.out_blob = h->out_blob[h->out_cur].as<unsigned char>();
+    if (h->direct && !h->comm) {       // forced rounds (gencut) keep every section: their callers fetch copies with g / viol / b
+        p.out_blob = h->d_direct[h->direct_cur]; p.lean_out = ((h->opt.flags & KTN_FLAG_LEAN_VIEW) && mode == KTN_MODE_SEPARATE) ? 1 : 0;
+        h->round_lean = p.lean_out != 0;
+    }
     return p;
 }
 
@@ -304,6 +320,7 @@ static int enqueue_round(ktn_handle* h, const double* d_x, int mode, int do_roun
         { int rc = ktn_comm_release_blob(h, h->out_cur); if (rc) return rc; }
     }
     h->epoch = (h->epoch % 0x3ffffff0u) + 1u;
+    if (h->direct && !h->comm) h->direct_cur ^= 1;      // a view stays valid until the round after the next one
     KtnRoundParams p = ktn_make_params(h, d_x, mode, do_round);
     p.clear_unselected = h->forced_last ? 1 : 0; h->forced_last = mode == KTN_MODE_FORCE;
     cudaError_t e = cudaSuccess;
@@ -317,6 +334,7 @@ static int enqueue_round(ktn_handle* h, const double* d_x, int mode, int do_roun
     ktn_comm_plan_blocks(h);
     int sms = h->num_sms;
     if (h->comm && h->px.on && h->px.reserve && sms > 2 * h->px.blocks) sms -= h->px.blocks;
+    if (h->reserve_sms > 0 && sms > 2 * h->reserve_sms) sms -= h->reserve_sms;
     int n = ktn_launch_round(p, make_plan(h), sms, h->max_smem, h->epoch, h->stream, ev[1], (h->opt.flags & KTN_FLAG_TIME_KERNELS) ? ev[3] : nullptr, &e);
     h->tm.launches += n;
     if (e != cudaSuccess) return fail(h, KTN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -434,6 +452,21 @@ extern "C" int ktn_fetch_cuts(ktn_handle* h, int64_t* row_id, int64_t* row_ptr, 
     const size_t nc = (size_t)h->n_cuts, nz = (size_t)h->nnz_cuts;
     const KtnPackLayout S = ktn_pack_layout((unsigned long long)h->lay_cuts, (unsigned long long)h->lay_nnz);      // where K2 put the sections
     const unsigned char* src = h->out_blob[h->out_cur].as<unsigned char>();
+    if (h->direct && !h->comm) {       // the batch is in host memory already (the round has been waited for)
+        const unsigned char* b = h->h_direct[h->direct_cur];
+        const bool lean = h->round_lean;
+        if ((g || viol || bconst) && lean) return fail(h, KTN_ERR_USAGE, "g, viol and bconst are not produced with KTN_FLAG_DIRECT_VIEW | KTN_FLAG_LEAN_VIEW");
+        if (row_id) memcpy(row_id, b + S.row_id, 8 * nc);
+        if (row_ptr) { memcpy(row_ptr, b + S.row_ptr, 8 * nc); row_ptr[nc] = (int64_t)nz; }
+        if (col) memcpy(col, b + S.col, 4 * nz);
+        if (val) memcpy(val, b + S.val, 8 * nz);
+        if (lo) memcpy(lo, b + S.lo, 8 * nc);
+        if (hi) memcpy(hi, b + S.hi, 8 * nc);
+        if (g) memcpy(g, b + S.g, 8 * nc);
+        if (viol) memcpy(viol, b + S.viol, 8 * nc);
+        if (bconst) memcpy(bconst, b + S.b, 8 * nc);
+        return KTN_OK;
+    }
     if (h->opt.flags & KTN_FLAG_TIME_KERNELS) CK(h, cudaEventRecord(h->ev2, h->stream));
     if (row_id && nc) CK(h, cudaMemcpyAsync(row_id, src + S.row_id, 8 * nc, cudaMemcpyDeviceToHost, h->stream));
     if (row_ptr) { if (nc) CK(h, cudaMemcpyAsync(row_ptr, src + S.row_ptr, 8 * nc, cudaMemcpyDeviceToHost, h->stream)); }
@@ -462,6 +495,18 @@ extern "C" int ktn_fetch_cuts_view(ktn_handle* h, ktn_cut_view* out) {
     const size_t nc = (size_t)h->n_cuts, nz = (size_t)h->nnz_cuts;
     const KtnPackLayout L = ktn_pack_layout(nc, nz);
     const bool lean = (h->opt.flags & KTN_FLAG_LEAN_VIEW) != 0;
+    if (h->direct && !h->comm) {       // the kernels stored the batch in host memory: nothing to copy, the sections are where K2 laid them out
+        const KtnPackLayout S = ktn_pack_layout((unsigned long long)h->lay_cuts, (unsigned long long)h->lay_nnz);
+        unsigned char* b = h->h_direct[h->direct_cur];
+        h->tm.d2h_ms = 0.0;
+        out->n_cuts = (int64_t)nc; out->nnz = (int64_t)nz;     // a truncated round: row_ptr[nc] is the first entry of the cut the batch ends before = nz
+        out->row_id = reinterpret_cast<const int64_t*>(b + S.row_id); out->row_ptr = reinterpret_cast<const int64_t*>(b + S.row_ptr);
+        out->col = reinterpret_cast<const int32_t*>(b + S.col); out->val = reinterpret_cast<const double*>(b + S.val);
+        out->lo = reinterpret_cast<const double*>(b + S.lo); out->hi = reinterpret_cast<const double*>(b + S.hi);
+        out->g = lean ? nullptr : reinterpret_cast<const double*>(b + S.g); out->viol = lean ? nullptr : reinterpret_cast<const double*>(b + S.viol);
+        out->bconst = lean ? nullptr : reinterpret_cast<const double*>(b + S.b);
+        return KTN_OK;
+    }
     h->view_cur ^= 1;
     unsigned char*& buf = h->h_view[h->view_cur]; size_t& cap = h->h_view_cap[h->view_cur];
     if (cap < L.total) {
@@ -612,7 +657,7 @@ static int group_create(ktn_handle* f, ktn_handle** out) {
     if (f->opt.topk > 0) { fprintf(stderr, "libktn: topk is not available on a multi-device handle\n"); delete f; return KTN_ERR_UNSUPPORTED; }
     for (int s = 0; s < n; ++s) {
         ktn_options o = f->opt;
-        o.struct_size = (int32_t)sizeof(ktn_options); o.ngpus = 0; o.device = f->opt.devices[s] >= 0 ? f->opt.devices[s] : s;
+        o.struct_size = (int32_t)sizeof(ktn_options); o.ngpus = 0; o.flags &= ~KTN_FLAG_DIRECT_VIEW; o.device = f->opt.devices[s] >= 0 ? f->opt.devices[s] : s;
         ktn_handle* sh = nullptr;
         const int rc = ktn_create(&o, &sh);
         if (rc != KTN_OK) { for (ktn_handle* q : f->shards) ktn_destroy(q); f->shards.clear(); delete f; return rc; }
@@ -620,16 +665,37 @@ static int group_create(ktn_handle* f, ktn_handle** out) {
     }
     f->shard_begin.assign((size_t)n + 1, 0); f->sh_cuts.assign((size_t)n, 0); f->sh_nnz.assign((size_t)n, 0);
     f->device = f->shards[0]->device;
+    bool one_device = true;
+    for (ktn_handle* q : f->shards) one_device = one_device && q->device == f->device;
+    if (one_device && (f->opt.flags & KTN_FLAG_EAGER_VIEW) && n <= KTN_HP_MAX_PREV && !(getenv("KTN_HOSTPUSH") && !strcmp(getenv("KTN_HOSTPUSH"), "0"))) {
+        // one device, several shards: one stream for all of them (they run back to back anyway), a second one for the host pushes
+        cudaSetDevice(f->device);
+        for (ktn_handle* q : f->shards) q->stream = f->shards[0]->own_stream;
+        bool ok = cudaStreamCreateWithFlags(&f->g_copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+        f->g_done.assign((size_t)n, nullptr);
+        for (int s = 0; ok && s < n; ++s) ok = cudaEventCreateWithFlags(&f->g_done[s], cudaEventDisableTiming) == cudaSuccess;
+        void* q = nullptr; void* d = nullptr;
+        ok = ok && cudaHostAlloc(&q, 32 * (size_t)n, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&d, q, 0) == cudaSuccess;
+        if (!ok) { group_destroy(f); return KTN_ERR_CUDA; }
+        f->g_hdr = static_cast<unsigned long long*>(q); f->g_hdr_d = static_cast<unsigned long long*>(d);
+        if (getenv("KTN_HOSTPUSH_GBS")) { const double r = atof(getenv("KTN_HOSTPUSH_GBS")); if (r >= 0.0 && r < 1000.0) f->push_pace = (float)r; }
+        if (getenv("KTN_HOSTPUSH_BLOCKS")) { const int b = atoi(getenv("KTN_HOSTPUSH_BLOCKS")); if (b >= 1 && b <= 64) f->push_blocks = b; }
+        f->push_view = true;
+    }
     *out = f;
     return KTN_OK;
 }
 
 static void group_destroy(ktn_handle* f) {
+    if (f->push_view) { cudaSetDevice(f->device); cudaDeviceSynchronize(); for (ktn_handle* s : f->shards) s->stream = s->own_stream; }
     for (ktn_handle* s : f->shards) ktn_destroy(s);
     f->shards.clear();
     cudaSetDevice(f->device);
     if (f->g_hx) cudaFreeHost(f->g_hx);
     for (int i = 0; i < 2; ++i) { if (f->h_view[i]) cudaFreeHost(f->h_view[i]); if (f->g_eager[i]) cudaFreeHost(f->g_eager[i]); }
+    if (f->g_hdr) cudaFreeHost(f->g_hdr);
+    for (cudaEvent_t e : f->g_done) if (e) cudaEventDestroy(e);
+    if (f->g_copy_stream) cudaStreamDestroy(f->g_copy_stream);
     delete f;
 }
 
@@ -682,11 +748,71 @@ static int group_load_end(ktn_handle* f) {
         const size_t total = (size_t)ktn_pack_layout((unsigned long long)cc, (unsigned long long)zz).total;
         if (total <= ((size_t)1 << 30)) {
             cudaSetDevice(f->device);
-            for (int i = 0; i < 2; ++i) CK(f, cudaHostAlloc(&f->g_eager[i], total + 64, cudaHostAllocPortable));
+            for (int i = 0; i < 2; ++i) {
+                CK(f, cudaHostAlloc(&f->g_eager[i], total + 64, cudaHostAllocPortable | (f->push_view ? cudaHostAllocMapped : 0)));
+                if (f->push_view) { void* d = nullptr; CK(f, cudaHostGetDevicePointer(&d, f->g_eager[i], 0)); f->g_eager_d[i] = static_cast<unsigned char*>(d); }
+            }
             f->eager_cap_cuts = cc; f->eager_cap_nnz = zz;
         }
     }
     return KTN_OK;
+}
+
+// Separation round of a pipelined single-device handle: x* goes up once; the shards' rounds are enqueued back to back on one stream;
+// behind every shard a small kernel on a second stream stores that shard's cuts into the combined batch in mapped pinned memory (the
+// PCIe transfer of shard s runs beside the kernels of shard s + 1, whose K1 leaves the push kernel's SMs free).  The host enqueues
+// everything without waiting and synchronises ONCE.
+void ktn_launch_hostpush(const KtnHostPushParams& q, int blocks, cudaStream_t stream);
+static int group_round_pushed(ktn_handle* f, int do_round, int64_t* n_cuts, int64_t* nnz, int64_t* err_row) {
+    const size_t n = f->shards.size();
+    ktn_handle* h0 = f->shards[0];
+    cudaSetDevice(f->device);
+    f->eager_valid = false;
+    f->eager_cur ^= 1;
+    const bool lean = (f->opt.flags & KTN_FLAG_LEAN_VIEW) != 0;
+    const KtnPackLayout EL = ktn_pack_layout((unsigned long long)f->eager_cap_cuts, (unsigned long long)f->eager_cap_nnz);
+    static const bool trace = getenv("KTN_HOSTPUSH_TRACE") != nullptr;       // stderr: when every shard's kernels and push ended (microseconds after the upload began)
+    static std::vector<cudaEvent_t> tev;
+    if (trace && tev.size() < 3 * n + 1) { tev.resize(3 * n + 1); for (cudaEvent_t& e : tev) cudaEventCreate(&e); }
+    if (trace) cudaEventRecord(tev[3 * n], h0->stream);
+    CK(f, cudaMemcpyAsync(h0->x.p, f->g_hx, 8 * (size_t)f->g_num_var, cudaMemcpyHostToDevice, h0->stream));
+    for (size_t s = 0; s < n; ++s) {
+        ktn_handle* h = f->shards[s];
+        h->reserve_sms = s ? f->push_blocks : 0;
+        int rc = enqueue_round(h, h0->x.as<double>(), KTN_MODE_SEPARATE, do_round); if (rc) return group_fail(f, h, rc);
+        if (trace) cudaEventRecord(tev[3 * s], h->stream);
+        CK(f, cudaEventRecord(f->g_done[s], h->stream));
+        CK(f, cudaStreamWaitEvent(f->g_copy_stream, f->g_done[s], 0));
+        if (trace) cudaEventRecord(tev[3 * s + 1], f->g_copy_stream);
+        KtnHostPushParams q; memset(&q, 0, sizeof q);
+        q.src = h->out_blob[h->out_cur].as<unsigned char>(); q.counts = h->counts.as<unsigned long long>();
+        for (size_t k = 0; k < s; ++k) q.prev[k] = f->shards[k]->counts.as<unsigned long long>();
+        q.pace = f->push_pace; q.nprev = (int)s; q.lean = lean ? 1 : 0; q.dst = f->g_eager_d[f->eager_cur]; q.EL = EL; q.hdr = f->g_hdr_d + 4 * s;
+        ktn_launch_hostpush(q, f->push_blocks, f->g_copy_stream);
+        CK(f, cudaGetLastError());
+        h->tm.launches += 1;
+        if (trace) cudaEventRecord(tev[3 * s + 2], f->g_copy_stream);
+    }
+    CK(f, cudaStreamSynchronize(f->g_copy_stream));
+    if (trace) {
+        for (size_t s = 0; s < n; ++s) {
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, tev[3 * n], tev[3 * s]); cudaEventElapsedTime(&b, tev[3 * n], tev[3 * s + 1]); cudaEventElapsedTime(&c, tev[3 * n], tev[3 * s + 2]);
+            fprintf(stderr, "libktn hostpush: shard %zu kernels done %.0f us, push %.0f .. %.0f us (%llu cuts)\n", s, 1e3 * a, 1e3 * b, 1e3 * c, (unsigned long long)f->g_hdr[4 * s]);
+        }
+    }
+    int64_t tc = 0, tz = 0, er = -1;
+    for (size_t s = 0; s < n; ++s) {
+        const unsigned long long* hd = f->g_hdr + 4 * s;
+        f->sh_cuts[s] = (int64_t)hd[0]; f->sh_nnz[s] = (int64_t)hd[1]; tc += f->sh_cuts[s]; tz += f->sh_nnz[s];
+        if (er < 0 && hd[2] != ~0ull) er = (int64_t)hd[2] - 1 + f->shard_begin[s];
+    }
+    f->eager_valid = true;
+    f->n_cuts = tc; f->nnz_cuts = tz; f->err_row = er; f->have_round = true;
+    if (n_cuts) *n_cuts = tc;
+    if (nnz) *nnz = tz;
+    if (err_row) *err_row = er;
+    return er >= 0 ? KTN_NUMERIC_NONFINITE : KTN_OK;
 }
 
 // One round on every device: rows == nullptr: separation (violated rows); else unconditional cuts of the listed rows.
@@ -694,6 +820,8 @@ static int group_round(ktn_handle* f, const double* x, const int64_t* rows, int6
     if (!f->loaded) return fail(f, KTN_ERR_USAGE, "no problem loaded");
     const size_t n = f->shards.size();
     memcpy(f->g_hx, x, 8 * (size_t)f->g_num_var);
+    if (f->push_view && f->g_eager[0] && !rows) return group_round_pushed(f, do_round, n_cuts, nnz, err_row);
+    for (ktn_handle* h : f->shards) h->reserve_sms = 0;
     std::vector<uint8_t> mask;
     for (size_t s = 0; s < n; ++s) {       // enqueue everywhere first: the devices run side by side
         ktn_handle* h = f->shards[s];
@@ -760,7 +888,7 @@ static int group_fetch(ktn_handle* f, ktn_cut_view* view, int64_t* row_id, int64
     const size_t nc = (size_t)f->n_cuts, nz = (size_t)f->nnz_cuts;
     const bool lean = view && (f->opt.flags & KTN_FLAG_LEAN_VIEW) != 0;
     if (f->eager_valid) {       // the copies were started by ktn_separate, shard by shard: wait for them
-        for (ktn_handle* h : f->shards) { cudaSetDevice(h->device); CK(f, cudaStreamSynchronize(h->stream)); }
+        if (!f->push_view) for (ktn_handle* h : f->shards) { cudaSetDevice(h->device); CK(f, cudaStreamSynchronize(h->stream)); }
         unsigned char* buf = f->g_eager[f->eager_cur];
         const KtnPackLayout EL = ktn_pack_layout((unsigned long long)f->eager_cap_cuts, (unsigned long long)f->eager_cap_nnz);
         const bool lv = (f->opt.flags & KTN_FLAG_LEAN_VIEW) != 0;
@@ -787,6 +915,7 @@ static int group_fetch(ktn_handle* f, ktn_cut_view* view, int64_t* row_id, int64
             return KTN_OK;
         }
     }
+    for (ktn_handle* h : f->shards) if (h->round_pending) { cudaSetDevice(h->device); int rc = finish_round(h, nullptr, nullptr, nullptr); if (rc < 0) return group_fail(f, h, rc); }
     if (view) {
         const KtnPackLayout L = ktn_pack_layout(nc, nz);
         f->view_cur ^= 1;

@@ -36,7 +36,7 @@ struct ktn_handle {
     KtnProblem prob;
     bool loading = false, loaded = false, round_pending = false, have_round = false;
     bool forced_last = false;              // the last round was unconditional (ktn_gencut_rows): rows outside nlconstr_ixs may carry selection flags
-    DevBuf chunks, shapes, prog, blob, chunk_rows, chunk_lb, chunk_ub, jac_ptr, jac_col, row_lb, row_ub, row_slot, row_nl, ladder, rec, worklist, errpos, blk_off, chunk_jp, dump;
+    DevBuf chunks, shapes, prog, blob, chunk_rows, chunk_lb, chunk_ub, jac_ptr, jac_col, row_lb, row_ub, row_slot, row_nl, ladder, rec, worklist, park, cut_off, errpos, blk_off, chunk_jp, dump;
     DevBuf topk_key, topk_state, topk_eqcnt;      // top-k selection (allocated when ktn_options.topk > 0)
     DevBuf x, force, g_row, b_row, sel, stage_val, big_scratch, ticket, blk_cnt, counts, table;
     // the round's cuts: one blob written by K2 (ktn_pack_layout).  Sharded handles rotate three blobs, so that the exchange of
@@ -48,6 +48,8 @@ struct ktn_handle {
     unsigned long long* h_counts = nullptr;  // pinned [8]
     int64_t n_cuts = 0, nnz_cuts = 0, err_row = -1;
     unsigned char* h_view[2] = {nullptr, nullptr}; size_t h_view_cap[2] = {0, 0}; int view_cur = 0;   // pinned buffers behind ktn_fetch_cuts_view
+    // KTN_FLAG_DIRECT_VIEW: the cut blob itself lives in mapped pinned HOST memory (two alternate), K2 / K3 store the batch over PCIe
+    unsigned char* h_direct[2] = {nullptr, nullptr}; unsigned char* d_direct[2] = {nullptr, nullptr}; int direct_cur = 0; bool direct = false, round_lean = false;
     uint32_t warp_bytes = 0, blob_cap = 0, table_bytes = 0, table_prog_off = 0, epoch = 0, blk_stride = 0;
     ktn_timings tm;
     std::string err;
@@ -93,6 +95,13 @@ struct ktn_handle {
     // so a shard's cuts can be copied to their final place as soon as that shard has finished, while later shards still compute
     unsigned char* g_eager[2] = {nullptr, nullptr}; int eager_cur = 0; bool eager_valid = false;
     int64_t eager_cap_cuts = 0, eager_cap_nnz = 0;
+    // every shard on ONE device (KatanaGPUSeparator(pipeline = S)): the shards share a stream, x* is uploaded once, and a small kernel per
+    // shard stores that shard's cuts into the combined batch in mapped pinned memory while the next shards compute (group_round)
+    bool push_view = false; int push_blocks = 12; float push_pace = 0.f;      // KTN_HOSTPUSH_GBS: bytes per nanosecond the push may store, 0 = unpaced (measured best: the SM store path, 43-46 GB/s, is the bottleneck either way)
+    unsigned char* g_eager_d[2] = {nullptr, nullptr};
+    unsigned long long* g_hdr = nullptr; unsigned long long* g_hdr_d = nullptr;
+    cudaStream_t g_copy_stream = nullptr; std::vector<cudaEvent_t> g_done;
+    int reserve_sms = 0;                            // (a shard) K1 leaves that many SMs to the host push of the shard before it
     DevBuf rp_shift;                                // shard: row_ptr of the last round shifted to the combined batch's entry offsets
 };
 

@@ -634,7 +634,8 @@ __global__ void __launch_bounds__(KTN_CBLOCK, KTN_CBPS) ktn_compact_kernel(const
     double* const out_g = reinterpret_cast<double*>(p.out_blob + L.g); double* const out_viol = reinterpret_cast<double*>(p.out_blob + L.viol);
     double* const out_b = reinterpret_cast<double*>(p.out_blob + L.b);
     int32_t* const out_col = reinterpret_cast<int32_t*>(p.out_blob + L.col); double* const out_val = reinterpret_cast<double*>(p.out_blob + L.val);
-    if (bid == nblocks - 1 && threadIdx.x == 0) out_ptr[s_tot_n] = (int64_t)s_tot_nz;
+    if (bid == nblocks - 1 && threadIdx.x == 0) { out_ptr[s_tot_n] = (int64_t)s_tot_nz; p.cut_off[s_tot_n] = s_tot_nz; }
+    const bool full = !p.lean_out;
     // compact list of the block's selected rows: local row index (+ flags) and nnz offset
     bool copy = false;
 #pragma unroll
@@ -649,21 +650,23 @@ __global__ void __launch_bounds__(KTN_CBLOCK, KTN_CBPS) ktn_compact_kernel(const
     if (threadIdx.x == 0) s_off[ta] = (uint32_t)tb;
     const int any_copy = __syncthreads_or(copy ? 1 : 0);
     // one thread per SELECTED row: where it goes.  Rows whose cut K1 built get their scalars here; a family row gets an entry of
-    // the cut kernel's work list (slot, nnz) with its record {g, aux, lb, ub} parked in the cut's own scalar arrays (so that the
-    // cut kernel starts from coalesced loads), and the sectors of the chunk blob that hold the row are requested into L2.
+    // the cut kernel's work list (slot, nnz) with its record {g, aux, lb, ub} parked at the cut's index (so that the cut kernel
+    // starts from coalesced loads), and the sectors of the chunk blob that hold the row are requested into L2.
     unsigned long long* const wl = p.worklist;
     for (uint32_t k = threadIdx.x; k < ta; k += KTN_CBLOCK) {
         const uint32_t rl = s_rowl[k];
         const int64_t i = row0 + (rl & 0x3fffu);
         const int64_t cidx = (int64_t)cbase + k, o = (int64_t)(nbase + s_off[k]);
-        out_row[cidx] = i + p.row_offset; out_ptr[cidx] = o;
+        out_row[cidx] = i + p.row_offset; out_ptr[cidx] = o; p.cut_off[cidx] = (unsigned long long)o;
         if (!(rl & 0x4000u)) {
             s_src[k] = (uint32_t)p.jac_ptr[i];
             const double g = p.g_row[i], bcst = p.b_row[i], lb = p.row_lb[i], ub = p.row_ub[i];
             out_lo[cidx] = lb - bcst; out_hi[cidx] = ub - bcst;     // src/model.jl:74-75
-            out_g[cidx] = g; out_b[cidx] = bcst;
-            const double v1 = lb - g, v2 = g - ub;
-            out_viol[cidx] = (g == g) ? (v1 > v2 ? v1 : v2) : g;
+            if (full) {
+                out_g[cidx] = g; out_b[cidx] = bcst;
+                const double v1 = lb - g, v2 = g - ub;
+                out_viol[cidx] = (g == g) ? (v1 > v2 ? v1 : v2) : g;
+            }
             wl[cidx] = 0ull;
             if (rl & 0x8000u) atomicMin(&p.counts[2 + (epoch & 1u)], (unsigned long long)cidx);      // first non-finite cut of the round
         } else {
@@ -674,7 +677,7 @@ __global__ void __launch_bounds__(KTN_CBLOCK, KTN_CBPS) ktn_compact_kernel(const
             const unsigned char* blob = p.blob + p.cls_blob_off[fam][nu] + (size_t)(c - p.cls_begin[fam][nu]) * KTN_FAM_BLOB_BYTES(nu);
             for (uint32_t gq = 0; gq < KTN_FAM_PGROUPS(nu) + KTN_FAM_CGROUPS(nu); ++gq) prefetch_l2(blob + gq * 1024u + ln * 32u);
             prefetch_l2(blob + KTN_FAM_ORD_OFF(nu) + ln * 8u);
-            out_g[cidx] = rc.x; out_b[cidx] = rc.y; out_lo[cidx] = rc.z; out_hi[cidx] = rc.w;
+            p.park[cidx] = rc;
             wl[cidx] = ((unsigned long long)(nu | ((uint32_t)fam << 8) | 0x10000u) << 32) | slot;
         }
     }
@@ -750,20 +753,23 @@ __global__ void __launch_bounds__(KTN_XBLOCK, KTN_XBPS) ktn_cut_kernel(const Ktn
     __shared__ unsigned long long s_e0, s_e1; __shared__ uint32_t s_last;
     const unsigned long long ca = __ldcg(&p.counts[4]), na = __ldcg(&p.counts[5]);
     const KtnPackLayout L = ktn_pack_layout(ca, na);
-    const int64_t* const out_row = reinterpret_cast<const int64_t*>(p.out_blob + L.row_id); const int64_t* const out_ptr = reinterpret_cast<const int64_t*>(p.out_blob + L.row_ptr);
+    const int64_t* const out_row = reinterpret_cast<const int64_t*>(p.out_blob + L.row_id);
     double* const out_lo = reinterpret_cast<double*>(p.out_blob + L.lo); double* const out_hi = reinterpret_cast<double*>(p.out_blob + L.hi);
     double* const out_g = reinterpret_cast<double*>(p.out_blob + L.g); double* const out_viol = reinterpret_cast<double*>(p.out_blob + L.viol);
     double* const out_b = reinterpret_cast<double*>(p.out_blob + L.b); double* const out_val = reinterpret_cast<double*>(p.out_blob + L.val);
     int32_t* const out_col = reinterpret_cast<int32_t*>(p.out_blob + L.col);
+    const bool full = !p.lean_out;
     for (unsigned long long c0 = (unsigned long long)blockIdx.x * KTN_XBLOCK; c0 < ca; c0 += (unsigned long long)gridDim.x * KTN_XBLOCK) {
         const unsigned long long cidx = c0 + threadIdx.x;
         const bool active = cidx < ca;
         int64_t o = 0; unsigned long long w = 0ull; double g = 0.0, aux = 0.0, lb = 0.0, ub = 0.0;
-        if (active) {      // one round trip: the work-list entry and the row's record, parked by the compaction kernel in the cut's own scalar arrays
-            w = __ldcg(p.worklist + cidx); o = __ldcg(out_ptr + cidx);
-            g = __ldcg(out_g + cidx); aux = __ldcg(out_b + cidx); lb = __ldcg(out_lo + cidx); ub = __ldcg(out_hi + cidx);
+        if (active) {      // one round trip: the work-list entry, the cut's place in the CSR and the row's record, all parked by the compaction kernel
+            w = __ldcg(p.worklist + cidx); o = (int64_t)__ldcg(p.cut_off + cidx);
+            const double2* const pk = reinterpret_cast<const double2*>(p.park + cidx);
+            const double2 r0 = __ldcg(pk), r1 = __ldcg(pk + 1);
+            g = r0.x; aux = r0.y; lb = r1.x; ub = r1.y;
         }
-        if (threadIdx.x == 0) { s_e0 = (unsigned long long)o; const unsigned long long cend = c0 + KTN_XBLOCK < ca ? c0 + KTN_XBLOCK : ca; s_e1 = (unsigned long long)__ldcg(out_ptr + cend); }
+        if (threadIdx.x == 0) { s_e0 = (unsigned long long)o; const unsigned long long cend = c0 + KTN_XBLOCK < ca ? c0 + KTN_XBLOCK : ca; s_e1 = __ldcg(p.cut_off + cend); }
         const bool mine = active && w != 0ull;
         // the block's slice of the CSR is staged when every cut of the block is a family cut (else: straight to the CSR)
 #ifndef KTN_X_NOSTAGE
@@ -784,9 +790,11 @@ __global__ void __launch_bounds__(KTN_XBLOCK, KTN_XBPS) ktn_cut_kernel(const Ktn
             else if (fam == KTN_FAM_QUAD) bad = ktn_family_cut_terms<KTN_FAM_QUAD>(r, nu, rw, s, g, aux, p.do_round != 0, p.rng, bcst);
             else bad = ktn_family_cut_terms<KTN_FAM_SOC>(r, nu, rw, s, g, aux, p.do_round != 0, p.rng, bcst);
             out_lo[cidx] = lb - bcst; out_hi[cidx] = ub - bcst;     // src/model.jl:74-75
-            out_b[cidx] = bcst;
-            const double v1 = lb - g, v2 = g - ub;
-            out_viol[cidx] = (g == g) ? (v1 > v2 ? v1 : v2) : g;
+            if (full) {
+                out_g[cidx] = g; out_b[cidx] = bcst;
+                const double v1 = lb - g, v2 = g - ub;
+                out_viol[cidx] = (g == g) ? (v1 > v2 ? v1 : v2) : g;
+            }
             if (bad) atomicMin(&p.counts[2 + (epoch & 1u)], cidx);      // first non-finite cut of the round
         }
         __syncthreads();
@@ -802,7 +810,7 @@ __global__ void __launch_bounds__(KTN_XBLOCK, KTN_XBPS) ktn_cut_kernel(const Ktn
         unsigned long long* const hdr = reinterpret_cast<unsigned long long*>(p.out_blob);
         const unsigned long long errc = __ldcg(&p.counts[2 + (epoch & 1u)]);      // the reference stops at the first non-finite cut (src/model.jl:278): cuts before it stand
         unsigned long long n = ca, nz = na, err = ~0ull;
-        if (errc != ~0ull) { n = errc; nz = (unsigned long long)__ldcg(out_ptr + errc); err = (unsigned long long)(__ldcg(out_row + errc) - p.row_offset) + 1ull; }
+        if (errc != ~0ull) { n = errc; nz = __ldcg(p.cut_off + errc); err = (unsigned long long)(__ldcg(out_row + errc) - p.row_offset) + 1ull; }
         p.counts[0] = n; p.counts[1] = nz; p.counts[6] = err;
         p.counts[2 + ((epoch & 1u) ^ 1u)] = ~0ull;                    // re-arm the slot the NEXT round uses
         p.counts[7] = 0ull;
@@ -1063,6 +1071,64 @@ void ktn_launch_shift(const int64_t* in, int64_t* out, int64_t n, int64_t add, c
     const int64_t blocks = (n + 255) / 256;
     ktn_shift_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, stream>>>(in, out, n, add);
 }
+
+// Host push (KtnHostPushParams): the sections of one shard's batch go to their place in the combined batch in pinned host memory.
+// Every warp stores whole 128-byte lines of the destination (the loops are aligned to the DESTINATION: misaligned stores cost
+// 14 % of the PCIe rate, profiles/microbench/mb8.log); four loads are in flight per thread before the first store.  The fp64
+// sections travel as 64-bit integers (x + 0.0 would turn a -0.0 coefficient into +0.0).
+namespace {
+struct HpPace {     // stores to host memory are posted: unpaced, they fill the queues between the L2 and the PCIe port and every other kernel's
+                    // memory traffic waits behind them (measured: the next shard's kernels ran 2.3x slower).  The grid therefore never runs
+                    // ahead of `rate` bytes per nanosecond.
+    unsigned long long t0; float rate; unsigned long long sent;
+    __device__ __forceinline__ void wait(unsigned long long grid_bytes) {
+        sent += grid_bytes;
+        if (rate <= 0.f) return;
+        const unsigned long long due = (unsigned long long)((float)sent / rate);
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        while (t - t0 < due) { __nanosleep(200); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); }
+    }
+};
+template <typename T> __device__ __forceinline__ void hp_section(T* dst, const T* __restrict__ src, unsigned long long n, T add, HpPace& pace) {
+    const unsigned long long mis = (reinterpret_cast<unsigned long long>(dst) & 127ull) / sizeof(T);
+    const unsigned long long total = n + mis, stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; j + 3 * stride < total; j += 4 * stride) {
+        T v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const unsigned long long q = j + k * stride; v[k] = q >= mis ? src[q - mis] : T(0); }
+        pace.wait(4ull * stride * sizeof(T));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const unsigned long long q = j + k * stride; if (q >= mis) dst[q - mis] = v[k] + add; }
+    }
+    pace.wait((total - (j - ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x))) * sizeof(T));
+    for (; j < total; j += stride) if (j >= mis) dst[j - mis] = src[j - mis] + add;
+}
+__global__ void __launch_bounds__(512) ktn_hostpush_kernel(const KtnHostPushParams q) {
+    unsigned long long n = __ldcg(q.counts), nz = __ldcg(q.counts + 1);
+    const unsigned long long err = __ldcg(q.counts + 6);
+    const KtnPackLayout S = ktn_pack_layout(__ldcg(q.counts + 4), __ldcg(q.counts + 5));
+    unsigned long long cb = 0, zb = 0; bool stopped = false;      // the reference never reaches the rows behind the first non-finite cut
+    for (int k = 0; k < q.nprev; ++k) { cb += __ldcg(q.prev[k]); zb += __ldcg(q.prev[k] + 1); stopped = stopped || __ldcg(q.prev[k] + 6) != ~0ull; }
+    if (stopped) { n = 0; nz = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { q.hdr[0] = n; q.hdr[1] = nz; q.hdr[2] = stopped ? ~0ull : err; q.hdr[3] = 0ull; }
+    if (n == 0) return;
+    const KtnPackLayout& E = q.EL;
+    HpPace pace; pace.rate = q.pace; pace.sent = 0ull; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pace.t0));
+    hp_section<long long>(reinterpret_cast<long long*>(q.dst + E.val) + zb, reinterpret_cast<const long long*>(q.src + S.val), nz, 0ll, pace);
+    hp_section<int32_t>(reinterpret_cast<int32_t*>(q.dst + E.col) + zb, reinterpret_cast<const int32_t*>(q.src + S.col), nz, 0, pace);
+    hp_section<long long>(reinterpret_cast<long long*>(q.dst + E.row_id) + cb, reinterpret_cast<const long long*>(q.src + S.row_id), n, 0ll, pace);
+    hp_section<long long>(reinterpret_cast<long long*>(q.dst + E.row_ptr) + cb, reinterpret_cast<const long long*>(q.src + S.row_ptr), n, (long long)zb, pace);
+    hp_section<long long>(reinterpret_cast<long long*>(q.dst + E.lo) + cb, reinterpret_cast<const long long*>(q.src + S.lo), n, 0ll, pace);
+    hp_section<long long>(reinterpret_cast<long long*>(q.dst + E.hi) + cb, reinterpret_cast<const long long*>(q.src + S.hi), n, 0ll, pace);
+    if (!q.lean) {
+        hp_section<long long>(reinterpret_cast<long long*>(q.dst + E.g) + cb, reinterpret_cast<const long long*>(q.src + S.g), n, 0ll, pace);
+        hp_section<long long>(reinterpret_cast<long long*>(q.dst + E.viol) + cb, reinterpret_cast<const long long*>(q.src + S.viol), n, 0ll, pace);
+        hp_section<long long>(reinterpret_cast<long long*>(q.dst + E.b) + cb, reinterpret_cast<const long long*>(q.src + S.b), n, 0ll, pace);
+    }
+}
+}
+void ktn_launch_hostpush(const KtnHostPushParams& q, int blocks, cudaStream_t stream) { ktn_hostpush_kernel<<<blocks, 512, 0, stream>>>(q); }
 
 // boundroutine's ladder (ktn_separate_ladder): x = scale * ray, and "is any nonlinear row violated at the point just evaluated?"
 namespace {

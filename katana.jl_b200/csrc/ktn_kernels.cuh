@@ -57,6 +57,10 @@ struct KtnRoundParams {
     // by K2.  Two copies indexed by epoch parity; K2 zeroes the copy the next round adds into.
     unsigned long long* blk_cnt; uint32_t blk_stride;
     unsigned long long* blk_off;       // large problems: exclusive scan of blk_cnt (ktn_blkscan_kernel), 2 words per block + totals
+    double4* park;             // per cut of the compacted list: the record of a family row, parked by K2 where K3 reads it coalesced
+    unsigned long long* cut_off;       // per cut of the compacted list (+ 1): first entry of the cut in the round's CSR (device copy of row_ptr: the cut
+                                       // blob may live in HOST memory, KTN_FLAG_DIRECT_VIEW, and is then never read back by a kernel)
+    int lean_out;                      // 1: g | viol | b sections of the cut blob are not written (KTN_FLAG_DIRECT_VIEW with KTN_FLAG_LEAN_VIEW)
     unsigned long long* worklist;      // per cut of the compacted list: 0 = cut built by K1, else (nnz | family << 8 | 1 << 16) << 32 | chunk slot (cut kernel)
     unsigned long long* errpos;        // per compaction block: (cut index, entry offset) of the block's first non-finite row (K2)
     // [0] n_cuts [1] nnz (both truncated at the first non-finite row) [2],[3] first-error row + 1 of even / odd epochs
@@ -106,4 +110,18 @@ inline KtnPackLayout ktn_pack_layout(unsigned long long n, unsigned long long nz
     L.total = o;
     return L;
 }
+// Pipelined single-device handles (KTN_FLAG_EAGER_VIEW, every shard on one device): a shard's cuts are stored by a small kernel
+// straight into the combined batch in mapped pinned HOST memory, at the place the cuts of the shards before it end (ktn_api.cu).
+#define KTN_HP_MAX_PREV 16
+struct KtnHostPushParams {
+    const unsigned char* src;                          // the shard's cut blob (device)
+    const unsigned long long* counts;                  // the shard's round counters (device): [0] cuts, [1] entries, [4] / [5] layout totals, [6] first non-finite row + 1
+    const unsigned long long* prev[KTN_HP_MAX_PREV];   // the counters of the shards before it (same device; their rounds precede this kernel in stream order)
+    int nprev, lean;
+    unsigned char* dst;                                // the combined batch (device alias of the pinned buffer)
+    KtnPackLayout EL;                                  // its sections: laid out for the worst case, filled compactly
+    float pace;                                        // bytes per nanosecond the whole grid may store (0: unpaced), see ktn_hostpush_kernel
+    unsigned long long* hdr;                           // host-mapped: {cuts, entries, first non-finite row + 1 (or ~0), 0} of this shard as it enters the batch
+};
+
 #endif

@@ -7,7 +7,7 @@ state (g, Jacobian rows, xstar) on the device behind the C ABI of include/ktn.h.
 """
 import numpy as np
 
-from .binding import FLAG_EAGER_VIEW, FLAG_LEAN_VIEW, KTN_NUMERIC_NONFINITE, load_cuda_library
+from .binding import FLAG_DIRECT_VIEW, FLAG_EAGER_VIEW, FLAG_LEAN_VIEW, KTN_NUMERIC_NONFINITE, load_cuda_library
 from .nlpeval import rows_to_wire
 
 
@@ -46,14 +46,20 @@ class KatanaGPUSeparator(AbstractKatanaSeparator):
     another implementation of the same C ABI as the checker).
     """
 
-    def __init__(self, library=None, topk=0, ngpus=1, devices=None, pipeline=1):
+    def __init__(self, library=None, topk=0, ngpus=1, devices=None, pipeline=None, direct=False):
         """ngpus > 1: the ONE separator of the model shards its rows over `ngpus` devices of this process (ktn_options.ngpus);
         `separate` still returns one combined batch in ascending row order to the one LP master.
         pipeline = S > 1: every device's rows are split into S consecutive shards whose cut downloads start as soon as each
-        shard has finished (KTN_FLAG_EAGER_VIEW): the PCIe transfer of the first shards overlaps the kernels of the later ones."""
+        shard has finished (KTN_FLAG_EAGER_VIEW): the PCIe transfer of the first shards overlaps the kernels of the later ones.
+        On ONE device the shards share a stream and a small kernel per shard stores its cuts into the pinned batch (ktn_api.cu
+        group_round_pushed).  pipeline = None: the measured default (B200, 10^6 log-sum-exp rows, 10^5 cuts per round: one shard
+        0.604 ms, two 0.575, three 0.587, four 0.632, eight 0.76): two shards from PIPELINE_MIN_ROWS rows on, else one.
+        direct (one device, one shard): the round's kernels store the batch straight into the pinned host buffer the views point
+        into (KTN_FLAG_DIRECT_VIEW); measured no faster than the download (0.622 against 0.604 ms: stores from the SMs reach
+        43-48 GB/s over PCIe, the copy engine 56), so it is off by default."""
         self._lib = library
         self.topk = topk
-        self.ngpus, self.devices, self.pipeline = ngpus, devices, pipeline
+        self.ngpus, self.devices, self.pipeline, self.direct = ngpus, devices, pipeline, direct
         self.handle = None
         self.last = None           # CutBatch of the last precompute!
         self.xstar = None
@@ -67,20 +73,28 @@ class KatanaGPUSeparator(AbstractKatanaSeparator):
         if self.handle is not None:                            # one separator is reused across models (test/runtests.jl:24)
             self.handle.close()
         # lean views: optimize! hands (row_ptr, col, val, lo, hi) to the LP; g / viol / bconst stay on the device
-        self.handle = lib.create(f_tol=f_tol, cut_coef_rng=cut_coef_rng, topk=self.topk, **self.handle_options())
+        self.handle = lib.create(f_tol=f_tol, cut_coef_rng=cut_coef_rng, topk=self.topk, **self.handle_options(num_constr))
         self.num_var, self.num_constr = num_var, num_constr
         lb = np.full(num_constr, -np.inf); ub = np.full(num_constr, np.inf)
         self.handle.load(num_var, rows_to_wire(oracle, num_constr, lb, ub))
         self.l_constr, self.u_constr = lb, ub
         self.last = self.g = self.xstar = None
 
-    def handle_options(self):
+    PIPELINE_MIN_ROWS = 400_000
+
+    def shards_per_device(self, num_constr):
+        if self.pipeline is not None:
+            return max(int(self.pipeline), 1)
+        return 2 if num_constr >= self.PIPELINE_MIN_ROWS and not self.topk else 1
+
+    def handle_options(self, num_constr=0):
         """ktn_options of this separator: lean views (optimize! hands row_ptr, col, val, lo, hi to the LP), the device list, eager downloads."""
         devs = list(self.devices) if self.devices else list(range(max(self.ngpus, 1)))
-        shards = [d for d in devs for _ in range(max(self.pipeline, 1))]
+        per = self.shards_per_device(num_constr) if len(devs) == 1 else max(int(self.pipeline or 1), 1)      # the measured default is a one-device result
+        shards = [d for d in devs for _ in range(per)]
         if len(shards) <= 1:
-            return dict(flags=FLAG_LEAN_VIEW, device=devs[0] if self.devices else -1)
-        return dict(flags=FLAG_LEAN_VIEW | (FLAG_EAGER_VIEW if self.pipeline > 1 else 0), ngpus=len(shards), devices=shards)
+            return dict(flags=FLAG_LEAN_VIEW | (FLAG_DIRECT_VIEW if self.direct else 0), device=devs[0] if self.devices else -1)
+        return dict(flags=FLAG_LEAN_VIEW | (FLAG_EAGER_VIEW if per > 1 else 0), ngpus=len(shards), devices=shards)
 
     def set_params(self, f_tol, cut_coef_rng):
         self.handle.set_params(f_tol, cut_coef_rng, self.topk)

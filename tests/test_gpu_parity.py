@@ -501,10 +501,68 @@ def test_ten_million_rows(oracle_lib, cuda_lib):
         os.environ.pop("KTN_ORACLE_THREADS", None)
 
 
-def test_eager_view_pipelined_download(oracle_lib, cuda_lib):
+def test_direct_view_cuts_stored_in_host_memory(oracle_lib, cuda_lib):
+    """KTN_FLAG_DIRECT_VIEW: K2 / K3 store the batch straight into mapped pinned host memory; views and copies must equal the oracle's
+    batch bit for bit -- family rows (LSE, SOC), interpreter rows (KAT problem), full and lean, empty / partial / full rounds, views
+    staying valid across the next round, forced rounds (gencut), a truncated round, reload, and the boundroutine ladder."""
+    from katana_jl_b200.binding import FLAG_DIRECT_VIEW, FLAG_LEAN_VIEW
+    lean_fields = ("row_id", "row_ptr", "col", "val", "lo", "hi")
+    for kind, nv, nr in ((1, 4000, 9001), (2, 2000, 3000), (0, 3000, 5000)):
+        w = cuda_lib.synth_rows(kind, 71 + kind, nv, 0, nr); x0 = cuda_lib.synth_point(kind, 71 + kind, nv)
+        ho = oracle_lib.create(); ho.load(nv, w)
+        g = ho.eval_g(x0)
+        for flags in (FLAG_DIRECT_VIEW, FLAG_DIRECT_VIEW | FLAG_LEAN_VIEW):
+            hd = cuda_lib.create(flags=flags); hd.load(nv, w)
+            prev = None
+            for v in (0.0, 0.07, 1.0, 0.3):
+                ub = np.full(nr, np.quantile(g, 1 - v) if v > 0 else g.max() + 1.0)
+                ho.set_bounds(w.lb, ub); hd.set_bounds(w.lb, ub)
+                bo = ho.separate(x0)
+                bv = hd.separate(x0, view=True)
+                assert bo.status == bv.status and bo.err_row == bv.err_row and bo.n_cuts == bv.n_cuts
+                for f in (lean_fields if flags & FLAG_LEAN_VIEW else BATCH_FIELDS):
+                    assert bits_equal(getattr(bo, f), getattr(bv, f)), (kind, flags, v, f)
+                if prev is not None:       # the view of the round before is still intact (two host buffers alternate)
+                    for f in lean_fields:
+                        assert bits_equal(getattr(prev[0], f), getattr(prev[1], f)), ("previous view", kind, flags, v, f)
+                prev = (bo, bv)
+            if not flags & FLAG_LEAN_VIEW:
+                assert_batches_identical(bo, hd.separate(x0), f"direct, copy, kind {kind}")
+            rows = np.arange(0, nr, 17, dtype=np.int64)
+            assert_batches_identical(ho.gencut_rows(x0, rows, True), hd.gencut_rows(x0, rows, True), "direct handle, gencut")
+            hd.close()
+        ho.close()
+    x, y, z = E.var(0), E.var(1), E.var(2)
+    exprs = [x**2 + y**2 - 1.0] * 50 + [E.sqrt(x**2 + y**2) - (z - 0.25)] + [x**2 + y**2 - 1.0] * 39
+    m = len(exprs)
+    w = E.to_wire(exprs, np.full(m, -np.inf), np.full(m, -2.0), [ROW_NL] * m)
+    ho = oracle_lib.create(); ho.load(3, w)
+    hd = cuda_lib.create(flags=FLAG_DIRECT_VIEW); hd.load(3, w)
+    bo = ho.separate(np.zeros(3))
+    assert bo.status == KTN_NUMERIC_NONFINITE and bo.n_cuts == 50
+    assert_batches_identical(bo, hd.separate(np.zeros(3), view=True), "direct view, truncated round")
+    assert_batches_identical(bo, hd.separate(np.zeros(3)), "direct copy, truncated round")
+    assert_batches_identical(ho.separate(np.ones(3)), hd.separate(np.ones(3), view=True))
+    nv2, w2, pts = kat_problem()
+    ho.load(nv2, w2); hd.load(nv2, w2)
+    for p in pts:
+        assert_batches_identical(ho.separate(p), hd.separate(p, view=True), "direct KAT")
+    ray = np.array([0.25, -0.5, 0.125] + [0.0] * (nv2 - 3))[:nv2]
+    no, bo = ho.separate_ladder(ray, 2, 40)
+    nd, bd = hd.separate_ladder(ray, 2, 40, view=True)
+    assert no == nd
+    assert_batches_identical(bo, bd, "direct ladder")
+    ho.close(); hd.close()
+
+
+@pytest.mark.parametrize("hostpush", ["1", "0"])
+def test_eager_view_pipelined_download(oracle_lib, cuda_lib, monkeypatch, hostpush):
     """KTN_FLAG_EAGER_VIEW: ktn_separate starts every shard's cut download when that shard has finished, into a pinned buffer laid out
     for the worst case; the view (and the copy) must equal the oracle's batch bit for bit -- full and lean views, empty and full
-    rounds, several rounds in a row (the two pinned buffers alternate), a non-finite row on the middle shard, and reload."""
+    rounds, several rounds in a row (the two pinned buffers alternate), a non-finite row on the middle shard, and reload.
+    hostpush 1 (default when every shard is on one device): a kernel per shard stores the cuts into the mapped pinned batch, one
+    host synchronisation per round; 0: copy-engine downloads started by the host shard by shard (the multi-device path)."""
+    monkeypatch.setenv("KTN_HOSTPUSH", hostpush)
     from katana_jl_b200.binding import FLAG_EAGER_VIEW, FLAG_LEAN_VIEW
     lean_fields = ("row_id", "row_ptr", "col", "val", "lo", "hi")
     for kind, nv, nr in ((1, 4000, 9001), (2, 2000, 3000)):
