@@ -46,7 +46,9 @@ enum {
     KTN_OP_LOG   = 9,
     KTN_OP_SQRT  = 10,
     KTN_OP_ABS   = 11,
-    KTN_OP__COUNT = 12
+    KTN_OP_SIN   = 12,
+    KTN_OP_COS   = 13,
+    KTN_OP__COUNT = 14
 };
 
 /* per-row flags */

@@ -34,7 +34,7 @@ check(sep, rc, what) = rc < 0 && error("$what failed ($rc): " *
     unsafe_string(ccall((:ktn_last_error, libktn), Cstring, (Ptr{Cvoid},), sep.handle)))
 
 # op codes of the wire format (include/ktn.h KTN_OP_*)
-const KTN_OPS = Dict(:+ => 2, :- => 3, :* => 4, :/ => 5, :^ => 6, :exp => 8, :log => 9, :sqrt => 10, :abs => 11)
+const KTN_OPS = Dict(:+ => 2, :- => 3, :* => 4, :/ => 5, :^ => 6, :exp => 8, :log => 9, :sqrt => 10, :abs => 11, :sin => 12, :cos => 13)
 
 # Flatten one expression tree over x[i] (MathProgBase constr_expr / obj_expr) into prefix arrays.
 function flatten!(op::Vector{Int32}, arg::Vector{Int32}, val::Vector{Float64}, ex)

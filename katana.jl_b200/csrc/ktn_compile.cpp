@@ -34,7 +34,7 @@ static int arity(int op) {
         case KTN_OP_CONST: case KTN_OP_VAR: return 0;
         case KTN_OP_ADD: case KTN_OP_MUL: return -1;
         case KTN_OP_SUB: case KTN_OP_DIV: case KTN_OP_POW: return 2;
-        case KTN_OP_NEG: case KTN_OP_EXP: case KTN_OP_LOG: case KTN_OP_SQRT: case KTN_OP_ABS: return 1;
+        case KTN_OP_NEG: case KTN_OP_EXP: case KTN_OP_LOG: case KTN_OP_SQRT: case KTN_OP_ABS: case KTN_OP_SIN: case KTN_OP_COS: return 1;
         default: return -2;
     }
 }
@@ -135,7 +135,7 @@ struct ShapeCompiler {
             std::vector<int> ch = children(k);
             switch (n.op) {
                 case KTN_OP_EXP: case KTN_OP_SQRT: n.need_value = true; break;
-                case KTN_OP_LOG: case KTN_OP_ABS: t[ch[0]].need_value = true; break;
+                case KTN_OP_LOG: case KTN_OP_ABS: case KTN_OP_SIN: case KTN_OP_COS: t[ch[0]].need_value = true; break;
                 case KTN_OP_POW: if (t[ch[1]].expclass == 2 && t[ch[0]].has_var) t[ch[0]].need_value = true; break;
                 case KTN_OP_MUL:
                     if (n.nc == 2) { if (t[ch[0]].has_var) t[ch[1]].need_value = true; if (t[ch[1]].has_var) t[ch[0]].need_value = true; }
@@ -235,6 +235,8 @@ struct ShapeCompiler {
             case KTN_OP_LOG: gen_fwd(ch[0]); emit(KF_LOG); break;
             case KTN_OP_SQRT: gen_fwd(ch[0]); emit(KF_SQRT); break;
             case KTN_OP_ABS: gen_fwd(ch[0]); emit(KF_ABS); break;
+            case KTN_OP_SIN: gen_fwd(ch[0]); emit(KF_SIN); break;
+            case KTN_OP_COS: gen_fwd(ch[0]); emit(KF_COS); break;
             default: err = "unknown op in gen_fwd";
         }
         persist(k);
@@ -302,6 +304,8 @@ struct ShapeCompiler {
                 case KTN_OP_LOG: emit(KR_MULRCP, t[c].val); break;
                 case KTN_OP_SQRT: emit(KR_MULHRCP, n.val); break;
                 case KTN_OP_ABS: emit(KR_MULSGN, t[c].val); break;
+                case KTN_OP_SIN: emit(KR_MULCOS, t[c].val); break;
+                case KTN_OP_COS: emit(KR_MULNSIN, t[c].val); break;
                 default: err = "unknown op in gen_rev";
             }
             gen_rev(c);

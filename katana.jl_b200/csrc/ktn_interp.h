@@ -203,6 +203,8 @@ KTN_HD double run_program(const KtnIns* prog, uint32_t pc, uint32_t end, M& m, u
             case KF_LOG: acc = ktn_log(acc); break;
             case KF_SQRT: acc = ktn_sqrt(acc); break;
             case KF_ABS: acc = ktn_fabs(acc); break;
+            case KF_SIN: acc = ktn_sin(acc); break;
+            case KF_COS: acc = ktn_cos(acc); break;
             case KF_STORE:
                 if (kind == KTN_K_S) m.sts(idx, acc); else if (kind == KTN_K_R1) r1 = acc; else r2 = acc;
                 break;
@@ -221,6 +223,8 @@ KTN_HD double run_program(const KtnIns* prog, uint32_t pc, uint32_t end, M& m, u
             case KR_MULRCP: acc = revmul(acc, 1.0 / src); break;
             case KR_MULHRCP: acc = revmul(acc, 0.5 / src); break;
             case KR_MULSGN: acc = revmul(acc, src >= 0.0 ? 1.0 : -1.0); break;
+            case KR_MULCOS: acc = revmul(acc, ktn_cos(src)); break;
+            case KR_MULNSIN: acc = revmul(acc, -ktn_sin(src)); break;
             case KR_JSET: m.jst(idx, 0.0 + acc); break;
             case KR_JACC: m.jst(idx, m.jld(idx) + acc); break;
             case KF_TERMS: acc = terms_fwd(m, kind & 0xfu, w.x >> 16, idx, w.z, w.w, (kind & KTN_TF_FIRST) != 0, (kind & KTN_TF_SAVEBLOB) != 0, acc); break;

@@ -9,7 +9,7 @@
 // host `-ffp-contract=off`, device `--fmad=false` (no implicit contraction).
 //
 // Accuracy (checked in tests/test_math.py against mpmath): exp, log < 1 ulp;
-// pow <= 2 ulp for |y*log(x)| <= 64.  That is far inside the 1e-12 relative
+// sin, cos < 1 ulp for |x| <= 1.6e6; pow <= 2 ulp for |y*log(x)| <= 64.  That is far inside the 1e-12 relative
 // agreement the north star asks for against Julia's libm.
 #ifndef KTN_MATH_H
 #define KTN_MATH_H
@@ -257,6 +257,72 @@ KTN_HD double ktn_pow(double x, double y) {
     if (ph < -745.2) return sign * 0.0;
     double e = ktn_exp(ph);
     return sign * ktn_fma(e, pl, e);
+}
+
+// sin(x), cos(x).  n = round(x * 2/pi); r = x - n * pi/2 with pi/2 = P1 + P2 + P3 (33 + 33 + 53 bits: the two fma steps are exact for
+// |n| < 2^20, the differences are compensated: r = rh + rl); on |r| <= pi/4 Taylor polynomials through r^17 (sin)
+// and r^16 (cos), with the first-order correction for rl; the quadrant n mod 4 picks function and sign.  Measured against mpmath
+// (tests/test_math.py): < 1 ulp for |x| <= 1.6e6 (2^20 * pi/2).  Beyond that the reduction loses accuracy gradually (absolute
+// error about |x| * 2^-86); |x| >= 2^45, +-inf and NaN give NaN -- a row evaluated there is reported as not finite.
+#define KTN_2_OVER_PI 6.36619772367581382433e-01 /* 0x3FE45F306DC9C883 */
+#define KTN_PIO2_1 1.57079632673412561417e+00    /* 0x3FF921FB54400000: first 33 bits of pi/2 */
+#define KTN_PIO2_2 6.07710050630396597660e-11    /* 0x3DD0B4611A600000: next 33 bits */
+#define KTN_PIO2_3 2.02226624879595063154e-21    /* 0x3BA3198A2E037073: pi/2 - P1 - P2 */
+KTN_HD double ktn_sin_kernel(double rh, double rl) {
+    const double z = rh * rh;
+    double p = 2.81145725434552059811e-15;                 /*  1/17! */
+    p = ktn_fma(p, z, -7.64716373181981640551e-13);        /* -1/15! */
+    p = ktn_fma(p, z, 1.60590438368216133409e-10);         /*  1/13! */
+    p = ktn_fma(p, z, -2.50521083854417202239e-08);        /* -1/11! */
+    p = ktn_fma(p, z, 2.75573192239858925110e-06);         /*  1/9!  */
+    p = ktn_fma(p, z, -1.98412698412698412526e-04);        /* -1/7!  */
+    p = ktn_fma(p, z, 8.33333333333333321769e-03);         /*  1/5!  */
+    p = ktn_fma(p, z, -1.66666666666666657415e-01);        /* -1/3!  */
+    const double corr = ktn_fma(-0.5 * z, rl, rl);         /* rl * cos(rh), first order */
+    return rh + ktn_fma(z * rh, p, corr);
+}
+KTN_HD double ktn_cos_kernel(double rh, double rl) {
+    const double z = rh * rh;
+    double p = 4.77947733238738525345e-14;                 /*  1/16! */
+    p = ktn_fma(p, z, -1.14707455977297245073e-11);        /* -1/14! */
+    p = ktn_fma(p, z, 2.08767569878681001866e-09);         /*  1/12! */
+    p = ktn_fma(p, z, -2.75573192239858882758e-07);        /* -1/10! */
+    p = ktn_fma(p, z, 2.48015873015873015658e-05);         /*  1/8!  */
+    p = ktn_fma(p, z, -1.38888888888888894189e-03);        /* -1/6!  */
+    p = ktn_fma(p, z, 4.16666666666666643537e-02);         /*  1/4!  */
+    const double hz = 0.5 * z, w = 1.0 - hz;
+    const double tail = ktn_fma(z * z, p, -(rh * rl));     /* z^2 P(z) - rl * sin(rh), first order */
+    return w + (((1.0 - w) - hz) + tail);                  /* 1 - z/2 without losing the bits of z/2 */
+}
+// quadrant (0..3) and remainder; returns -1 when x is outside the supported range
+KTN_HD int ktn_rem_pio2(double x, double* rh, double* rl) {
+    if (!(ktn_fabs(x) < 35184372088832.0)) return -1;      /* 2^45; also NaN and +-inf */
+    const double SHIFT = 6755399441055744.0;               /* 1.5 * 2^52 */
+    const double ts = x * KTN_2_OVER_PI + SHIFT;
+    const double nd = ts - SHIFT;
+    const double r1 = ktn_fma(-nd, KTN_PIO2_1, x);         /* exact for |n| < 2^20 */
+    const double w = nd * KTN_PIO2_2;                      /* exact for |n| < 2^20 */
+    const double h = r1 - w, b1 = h - r1;                  /* two-sum: r1 - w = h + l */
+    const double l = (r1 - (h - b1)) - (w + b1);
+    const double t = l - nd * KTN_PIO2_3;
+    const double s = h + t, b2 = s - h;                    /* two-sum: h + t = s + e */
+    *rh = s; *rl = (h - (s - b2)) + (t - b2);
+    return (int)(ktn_d2bits(ts) & 3ull);
+}
+KTN_HD double ktn_sin(double x) {
+    if (x == 0.0) return x;                                /* keeps -0.0 */
+    double rh, rl;
+    const int q = ktn_rem_pio2(x, &rh, &rl);
+    if (q < 0) return ktn_nan();
+    const double v = (q & 1) ? ktn_cos_kernel(rh, rl) : ktn_sin_kernel(rh, rl);
+    return (q & 2) ? -v : v;
+}
+KTN_HD double ktn_cos(double x) {
+    double rh, rl;
+    const int q = ktn_rem_pio2(x, &rh, &rl);
+    if (q < 0) return ktn_nan();
+    const double v = (q & 1) ? ktn_sin_kernel(rh, rl) : ktn_cos_kernel(rh, rl);
+    return ((q + 1) & 2) ? -v : v;
 }
 
 // Julia's max(): NaN-propagating (used by round_coefs, reference src/model.jl:201).

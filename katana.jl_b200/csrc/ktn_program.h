@@ -42,7 +42,7 @@ enum {
     KF_RDIV,       // aux = 1/acc;  acc = src * aux      (denominator in acc)
     KF_FDIV,       // acc = acc / src                   (true division: n-ary product partials)
     KF_POW2,       // acc = acc * acc
-    KF_NEG, KF_EXP, KF_LOG, KF_SQRT, KF_ABS,
+    KF_NEG, KF_EXP, KF_LOG, KF_SQRT, KF_ABS, KF_SIN, KF_COS,
     KF_STORE,      // dst(kind, idx) = acc      kind in {S, R1, R2}
     KF_LDAUX,      // aux = src
     KF_STAUX,      // S[idx] = aux
@@ -60,6 +60,8 @@ enum {
     KR_MULRCP,     // acc = revmul(acc, 1.0 / src)
     KR_MULHRCP,    // acc = revmul(acc, 0.5 / src)
     KR_MULSGN,     // acc = revmul(acc, src >= 0 ? 1.0 : -1.0)
+    KR_MULCOS,     // acc = revmul(acc, cos(src))                (d sin)
+    KR_MULNSIN,    // acc = revmul(acc, -sin(src))               (d cos)
     KR_JSET,       // J[idx] = 0.0 + acc
     KR_JACC,       // J[idx] = J[idx] + acc
     // ---- fused runs of identical terms inside an n-ary sum: the same arithmetic as the primitive

@@ -9,7 +9,7 @@ import math
 
 import numpy as np
 
-from .binding import (OP_ABS, OP_ADD, OP_CONST, OP_DIV, OP_EXP, OP_LOG, OP_MUL, OP_NEG, OP_POW, OP_SQRT, OP_SUB, OP_VAR,
+from .binding import (OP_ABS, OP_ADD, OP_CONST, OP_COS, OP_SIN, OP_DIV, OP_EXP, OP_LOG, OP_MUL, OP_NEG, OP_POW, OP_SQRT, OP_SUB, OP_VAR,
                       ROW_DENSE, ROW_NL, WireRows)
 
 _NARY = (OP_ADD, OP_MUL)
@@ -70,6 +70,8 @@ def exp(a): return call(OP_EXP, a)
 def log(a): return call(OP_LOG, a)
 def sqrt(a): return call(OP_SQRT, a)
 def abs_(a): return call(OP_ABS, a)
+def sin(a): return call(OP_SIN, a)
+def cos(a): return call(OP_COS, a)
 
 
 def sum_(terms):
@@ -141,6 +143,8 @@ def evaluate(node, x):
     if op == OP_LOG: return math.log(c[0]) if c[0] > 0 else (-math.inf if c[0] == 0 else math.nan)
     if op == OP_SQRT: return math.sqrt(c[0]) if c[0] >= 0 else math.nan
     if op == OP_ABS: return abs(c[0])
+    if op == OP_SIN: return math.sin(c[0]) if math.isfinite(c[0]) else math.nan
+    if op == OP_COS: return math.cos(c[0]) if math.isfinite(c[0]) else math.nan
     raise ValueError(f"unknown op {op}")
 
 
@@ -212,5 +216,5 @@ def to_quadform(node):
     raise ValueError("expression is not polynomial; use the NL form")
 
 
-__all__ = ["Node", "var", "const", "call", "exp", "log", "sqrt", "abs_", "sum_", "prod_", "to_wire", "flatten_into", "evaluate",
+__all__ = ["Node", "var", "const", "call", "exp", "log", "sqrt", "abs_", "sin", "cos", "sum_", "prod_", "to_wire", "flatten_into", "evaluate",
            "variables", "QuadForm", "to_quadform", "wrap", "ROW_NL", "ROW_DENSE"]

@@ -118,7 +118,7 @@ static int arity(int op) {
         case KTN_OP_CONST: case KTN_OP_VAR: return 0;
         case KTN_OP_ADD: case KTN_OP_MUL: return -1;
         case KTN_OP_SUB: case KTN_OP_DIV: case KTN_OP_POW: return 2;
-        case KTN_OP_NEG: case KTN_OP_EXP: case KTN_OP_LOG: case KTN_OP_SQRT: case KTN_OP_ABS: return 1;
+        case KTN_OP_NEG: case KTN_OP_EXP: case KTN_OP_LOG: case KTN_OP_SQRT: case KTN_OP_ABS: case KTN_OP_SIN: case KTN_OP_COS: return 1;
         default: return -2;
     }
 }
@@ -259,6 +259,8 @@ static double forward_row(const ktn_handle* h, int64_t row, const double* x, dou
             case KTN_OP_LOG: st[k] = ktn_log(st[k + 1]); pa[k + 1] = 1.0 / st[k + 1]; break;
             case KTN_OP_SQRT: st[k] = ktn_sqrt(st[k + 1]); pa[k + 1] = 0.5 / st[k]; break; /* Calculus.jl: 1 / 2 / sqrt(x) */
             case KTN_OP_ABS: st[k] = ktn_fabs(st[k + 1]); pa[k + 1] = (st[k + 1] >= 0.0) ? 1.0 : -1.0; break;
+            case KTN_OP_SIN: st[k] = ktn_sin(st[k + 1]); pa[k + 1] = ktn_cos(st[k + 1]); break;      /* Calculus.jl: cos(x) */
+            case KTN_OP_COS: st[k] = ktn_cos(st[k + 1]); pa[k + 1] = -ktn_sin(st[k + 1]); break;     /* Calculus.jl: -sin(x) */
         }
     }
     return st[0];

@@ -274,4 +274,6 @@ extern "C" int ktn_emu_shape_prog(ktn_handle* h, int64_t sid, uint32_t* out /* 4
 // vectorised access to the shared math header for tests/test_math.py
 extern "C" void ktn_test_exp(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ktn_exp(x[i]); }
 extern "C" void ktn_test_log(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ktn_log(x[i]); }
+extern "C" void ktn_test_sin(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ktn_sin(x[i]); }
+extern "C" void ktn_test_cos(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ktn_cos(x[i]); }
 extern "C" void ktn_test_pow(const double* x, const double* p, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ktn_pow(x[i], p[i]); }

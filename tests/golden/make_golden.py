@@ -41,6 +41,8 @@ def to_sympy(w, r, xs):
         if op == E.OP_LOG: return sp.log(ch[0])
         if op == E.OP_SQRT: return sp.sqrt(ch[0])
         if op == E.OP_ABS: return sp.Abs(ch[0])
+        if op == E.OP_SIN: return sp.sin(ch[0])
+        if op == E.OP_COS: return sp.cos(ch[0])
         raise ValueError(op)
     return rec()
 

@@ -51,6 +51,9 @@ def kat_problem():
         1.0 / x + x / (y + z),
         (x * y)**2 / z,
         E.sqrt(E.sum_([E.var(i)**2 for i in range(3)])),   # test/misc.jl:39
+        E.sin(-x - 1.0) + x / 2.0 + 0.5 - y,               # test/2d.jl:367 (case 106, commented out upstream: not convex on the box)
+        y - (E.cos(x - 0.5) + x / 4.0 - 0.5),              # test/2d.jl:368
+        E.sin(x * y) * E.cos(z) + E.cos(E.exp(x)),          # sin / cos under products and of transcendental arguments
         E.sum_([E.var(i)**2 for i in range(3)]) - z,       # dense epigraph-style row, last
     ]
     m = len(exprs)
@@ -65,7 +68,7 @@ def random_tree(rng, nvar, depth):
     """A random expression over nvar variables using every operator of the wire format."""
     if depth == 0 or rng.random() < 0.25:
         return E.var(int(rng.integers(nvar))) if rng.random() < 0.7 else E.const(float(np.round(rng.uniform(-2, 2), 3)))
-    k = rng.integers(12)
+    k = rng.integers(14)
     sub = lambda: random_tree(rng, nvar, depth - 1)
     if k == 0: return E.sum_([sub() for _ in range(int(rng.integers(1, 5)))])
     if k == 1: return E.prod_([sub() for _ in range(int(rng.integers(1, 4)))])
@@ -78,4 +81,6 @@ def random_tree(rng, nvar, depth):
     if k == 8: return E.log(sub())
     if k == 9: return E.sqrt(sub())
     if k == 10: return E.abs_(sub())
+    if k == 11: return E.sin(sub())
+    if k == 12: return E.cos(sub())
     return -sub()

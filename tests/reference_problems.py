@@ -63,6 +63,15 @@ def explog(obj):
     return build
 
 
+def trig_cap(m):
+    """sin / cos rows that ARE convex on the box (the reference's own 106 cases, test/2d.jl:357-401, are commented out upstream as
+    non-convex): max y under y <= sin(x), y <= cos(x - 0.5), 0.2 <= x <= 2: both concave there; optimum where the curves cross."""
+    x, y = m.variable(0.2, 2.0), m.variable(-1.0, 2.0)
+    m.objective("Min", -y + 0 * x)
+    m.nlconstraint(E.sin(x), ">=", y); m.nlconstraint(E.cos(x - 0.5), ">=", y)
+    return [x, y]
+
+
 def b_108_01(m):
     x, y = m.variable(0, INF), m.variable(0, INF)
     m.objective("Min", (x - 1.0)**2 + (y - 0.75)**2)
@@ -150,6 +159,7 @@ PROBLEMS = [
     _p("105_04", "test/2d.jl:338-354", explog(lambda x, y: -x + y), -3 / 2, [2.0, 1 / 2]),
     _p("107_01", "test/2d.jl:405-420", disk("Min", lambda x, y: (x - 0.5)**2 + (y - 0.5)**2, False), 0.0, [0.5, 0.5]),
     _p("107_02", "test/2d.jl:423-438", disk("Min", lambda x, y: (x - 1.0)**2 + (y - 1.0)**2, False), 0.17157287363083387, [1 / r2, 1 / r2]),
+    _p("106_xx", "sin/cos front-end ops; convex variant of test/2d.jl:357-401", trig_cap, -0.8600655610487502, [1.0353981633974483, 0.8600655610487502]),
     _p("108_01", "test/2d.jl:460-476", b_108_01, 0.0, [1.0, 0.75]),
     _p("110_01", "test/2d.jl:603-618", nlobj_disk(lambda x, y: E.const(e)**x), e**-1, [-1.0, 0.0]),
     _p("110_02", "test/2d.jl:621-636", nlobj_disk(lambda x, y: E.const(e)**x + E.const(e)**y), 2 * e**(-1 / r2), [-1 / r2, -1 / r2]),

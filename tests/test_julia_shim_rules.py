@@ -20,8 +20,8 @@ from katana_jl_b200.binding import ROW_DENSE, ROW_NL, WireRows
 from katana_jl_b200.nlpeval import EpigraphNLPEvaluator, ExprNLPEvaluator, rows_to_wire
 from reference_problems import PROBLEMS
 
-KTN_OPS = {"+": 2, "-": 3, "*": 4, "/": 5, "^": 6, "exp": 8, "log": 9, "sqrt": 10, "abs": 11}     # shim: const KTN_OPS
-SYM = {E.OP_ADD: "+", E.OP_SUB: "-", E.OP_MUL: "*", E.OP_DIV: "/", E.OP_POW: "^", E.OP_EXP: "exp", E.OP_LOG: "log", E.OP_SQRT: "sqrt", E.OP_ABS: "abs"}
+KTN_OPS = {"+": 2, "-": 3, "*": 4, "/": 5, "^": 6, "exp": 8, "log": 9, "sqrt": 10, "abs": 11, "sin": 12, "cos": 13}     # shim: const KTN_OPS
+SYM = {E.OP_ADD: "+", E.OP_SUB: "-", E.OP_MUL: "*", E.OP_DIV: "/", E.OP_POW: "^", E.OP_EXP: "exp", E.OP_LOG: "log", E.OP_SQRT: "sqrt", E.OP_ABS: "abs", E.OP_SIN: "sin", E.OP_COS: "cos"}
 
 
 def julia_expr(n):
