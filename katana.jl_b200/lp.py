@@ -16,6 +16,7 @@ class HighsLP:
         self.lb, self.ub = [], []
         self.c = np.zeros(0); self.c0 = 0.0; self.sense = "Min"
         self.rows = []          # (cols int array, vals float array, lo, hi)
+        self.managed = []       # per row: -1 = permanent (model rows, vertex / bounding cuts); >= 0: a loop cut, solves in a row it has been slack
         self.x = None; self.objval = np.nan; self.status = "None"
 
     # --- model building -------------------------------------------------------------------
@@ -37,12 +38,48 @@ class HighsLP:
     def addconstr(self, cols, vals, lo, hi):
         """MathProgBase.addconstr!(m, varidx, coef, lb, ub): one LP row lo <= a.x <= hi."""
         self.rows.append((np.asarray(cols, np.int64), np.asarray(vals, np.float64), float(lo), float(hi)))
+        self.managed.append(-1)
 
-    def addconstrs_csr(self, row_ptr, col, val, lo, hi):
-        """Batched hand-off of a CutBatch (the fast path that bypasses AffExpr objects)."""
+    def addconstrs_csr(self, row_ptr, col, val, lo, hi, managed=False, skip=None):
+        """Batched hand-off of a CutBatch (the fast path that bypasses AffExpr objects).  managed: the rows may be purged later
+        (purge_slack_rows); skip: boolean mask of cuts NOT to add (duplicate filter)."""
         for c in range(len(lo)):
+            if skip is not None and skip[c]:
+                continue
             s, e = row_ptr[c], row_ptr[c + 1]
             self.rows.append((col[s:e].astype(np.int64), val[s:e].copy(), float(lo[c]), float(hi[c])))
+            self.managed.append(0 if managed else -1)
+
+    def purge_slack_rows(self, age, tol):
+        """Cut management (an extension: the reference keeps every cut, src/model.jl:215).  After a solve: a managed row whose
+        slack at x* exceeds tol * max(1, |bound|) has been inactive one more solve; rows inactive `age` solves in a row are
+        removed.  Returns the number of rows removed."""
+        if self.x is None:
+            return 0
+        keep_rows, keep_tag, removed = [], [], 0
+        if not hasattr(self, "purged"):
+            self.purged = []    # every row removed so far: put back (for good) by restore_purged if the LP loses its bound
+        for (cols, vals, lo, hi), tag in zip(self.rows, self.managed):
+            if tag >= 0:
+                a = float(vals @ self.x[cols])
+                slack = min(hi - a if np.isfinite(hi) else np.inf, a - lo if np.isfinite(lo) else np.inf)
+                ref = max(1.0, abs(hi) if np.isfinite(hi) else 0.0, abs(lo) if np.isfinite(lo) else 0.0)
+                tag = tag + 1 if slack > tol * ref else 0
+                if tag >= age:
+                    removed += 1
+                    self.purged.append((cols, vals, lo, hi))
+                    continue
+            keep_rows.append((cols, vals, lo, hi)); keep_tag.append(tag)
+        self.rows, self.managed = keep_rows, keep_tag
+        return removed
+
+    def restore_purged(self):
+        """Puts every purged row back as a permanent row; returns how many."""
+        rows = getattr(self, "purged", [])
+        for r in rows:
+            self.rows.append(r); self.managed.append(-1)
+        self.purged = []
+        return len(rows)
 
     # --- solving ---------------------------------------------------------------------------
     def _matrices(self):

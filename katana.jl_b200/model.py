@@ -17,9 +17,14 @@ from .separators import AffExpr, KatanaGPUSeparator
 
 
 class KatanaModelParams:                                       # src/Katana.jl:12-19
-    def __init__(self, f_tol, iter_cap, log_level, cut_coef_rng, obj_eps, separator):
+    def __init__(self, f_tol, iter_cap, log_level, cut_coef_rng, obj_eps, separator, cut_purge_age=0, cut_filter_duplicates=False):
         self.f_tol, self.iter_cap, self.log_level = f_tol, iter_cap, log_level
         self.cut_coef_rng, self.obj_eps, self.separator = cut_coef_rng, obj_eps, separator
+        # cut management, SURVEY 8(f) item 2 -- extensions, OFF by default (the reference never removes or filters cuts, src/model.jl:215):
+        # cut_purge_age = A > 0: a loop cut that has been slack at A consecutive LP optima is removed from the LP, but only after a
+        # round in which the LP bound moved (a master whose bound is monotone and strictly moving cannot cycle);
+        # cut_filter_duplicates: a cut whose (columns, coefficients, bounds) are bit-identical to one added earlier is not added again.
+        self.cut_purge_age, self.cut_filter_duplicates = cut_purge_age, cut_filter_duplicates
 
 
 def round_coefs(cut, cut_coef_rng):                            # src/model.jl:200-207
@@ -44,9 +49,12 @@ class KatanaNonlinearModel:                                    # src/model.jl:9-
         self.nlconstr_ixs = []
         self.linear_cuts, self.lp_sols = [], []
         self.iter = 0
+        self.in_loop = False
         self.numcuts = 0
         self.soltime = 0.0
         self.round_log = []                                    # per-round timers
+        self.cut_keys = set()                                  # duplicate filter (params.cut_filter_duplicates)
+        self.cuts_purged = self.cuts_filtered = 0
 
     # _addcut(m, cut, lb, ub) -- src/model.jl:68-79
     def _addcut(self, cut, lb, ub):
@@ -62,8 +70,20 @@ class KatanaNonlinearModel:                                    # src/model.jl:9-
 
     def _addbatch(self, batch):
         """Batched _addcut over a CutBatch: lo/hi already carry lb - c, ub - c (src/model.jl:74-75)."""
-        self.linear_model.addconstrs_csr(batch.row_ptr, batch.col, batch.val, batch.lo, batch.hi)
-        self.numcuts += batch.n_cuts
+        skip = None
+        if self.params.cut_filter_duplicates and batch.n_cuts:
+            skip = np.zeros(batch.n_cuts, bool)
+            for c in range(batch.n_cuts):
+                s, e = batch.row_ptr[c], batch.row_ptr[c + 1]
+                key = (batch.col[s:e].tobytes(), batch.val[s:e].tobytes(), float(batch.lo[c]), float(batch.hi[c]))
+                if key in self.cut_keys: skip[c] = True
+                else: self.cut_keys.add(key)
+            self.cuts_filtered += int(skip.sum())
+        if skip is not None or self.params.cut_purge_age > 0:
+            self.linear_model.addconstrs_csr(batch.row_ptr, batch.col, batch.val, batch.lo, batch.hi, managed=self.in_loop and self.params.cut_purge_age > 0, skip=skip)
+        else:
+            self.linear_model.addconstrs_csr(batch.row_ptr, batch.col, batch.val, batch.lo, batch.hi)
+        self.numcuts += batch.n_cuts - (int(skip.sum()) if skip is not None else 0)
         if self.features["VisData"]:
             for c in range(batch.n_cuts):
                 cols, vals = batch.row(c)
@@ -194,16 +214,32 @@ class KatanaNonlinearModel:                                    # src/model.jl:9-
             return self.status
         if self.params.log_level > 0: self.print_header()
         allsat = False
+        self.in_loop = True                                    # cuts added from here on may be purged (cut_purge_age)
+        self.purge_enabled, self.purge_bound = True, -math.inf
         cuts_lastprnt, max_viol, obj_prev = 0, 0, math.inf
         while not allsat and self.iter < self.params.iter_cap:     # :257
             self.iter += 1
             t0 = time.perf_counter()
             status = lm.solve()                                # :259
+            if status == "Unbounded" and self.params.cut_purge_age > 0 and hasattr(lm, "restore_purged"):
+                back = lm.restore_purged()                     # a purged cut was bounding the LP: all of them return for good,
+                if back:                                       # and nothing is purged any more
+                    self.cuts_purged -= back
+                    self.purge_enabled = False
+                    status = lm.solve()
             lp_s = time.perf_counter() - t0
             if status != "Optimal":                            # :261-263
                 self.status = status
                 return self.status
             xstar = lm.getsolution()                           # :265
+            if self.params.cut_purge_age > 0 and self.purge_enabled and hasattr(lm, "purge_slack_rows"):
+                # the LP bound only tightens while cuts are only added; a purge may loosen it.  The next purge waits until the bound
+                # has passed the value it had at the last one: every purge is separated by strict progress, so the loop cannot cycle
+                bound = lm.getobjval() if lm.sense == "Min" else -lm.getobjval()
+                if bound > self.purge_bound + 1e-9 * max(1.0, abs(bound)):
+                    n = lm.purge_slack_rows(self.params.cut_purge_age, 1e-7)
+                    self.cuts_purged += n
+                    if n: self.purge_bound = bound
             if self.features["VisData"]: self.lp_sols.append(xstar)
             allsat, cuts_viol = self._separate_round(xstar)    # :268-283
             if self.round_log: self.round_log[-1]["lp_s"] = lp_s

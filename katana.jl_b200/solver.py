@@ -17,11 +17,12 @@ from .separators import KatanaGPUSeparator
 
 class KatanaSolver:                                            # src/solver.jl:6-10,34-43
     def __init__(self, lp_solver=HighsLP, separator=None, features=(), f_tol=1e-6, cut_coef_rng=1e9,
-                 log_level=10, iter_cap=10000, obj_eps=-1.0):
+                 log_level=10, iter_cap=10000, obj_eps=-1.0, cut_purge_age=0, cut_filter_duplicates=False):
         self.lp_solver = lp_solver
         self.features = list(features)
         self.model_params = KatanaModelParams(f_tol, iter_cap, log_level, cut_coef_rng, obj_eps,
-                                              separator if separator is not None else KatanaGPUSeparator())
+                                              separator if separator is not None else KatanaGPUSeparator(),
+                                              cut_purge_age=cut_purge_age, cut_filter_duplicates=cut_filter_duplicates)
 
 
 def NonlinearModel(s):                                         # src/model.jl:63-65

@@ -71,3 +71,39 @@ def test_error_status_on_undefined_gradient(oracle_lib):
         return [x, y, z]
     m, _, status = solve_problem(oracle_lib, build)
     assert status == "Error"
+
+
+def test_cut_management_keeps_the_optimum_with_a_smaller_lp(oracle_lib):
+    """Cut purging and duplicate filtering (extensions, off by default -- the reference never removes a cut,
+    src/model.jl:215): same optima within the reference's tolerances, fewer rows left in the LP master, every removal counted."""
+    by_name = {p[0]: p for p in PROBLEMS}
+    shrunk = rows0 = rows1 = 0
+    for name in ("101_01", "103_03", "105_01", "202_03", "210_02", "501_01_n8", "501_02_n13"):
+        _, cite, build, obj, sol = by_name[name]
+        m0, _, s0 = solve_problem(oracle_lib, build)
+        m1, v1, s1 = solve_problem(oracle_lib, build, cut_purge_age=2, cut_filter_duplicates=True)
+        assert s0 == s1 == "Optimal", (name, s0, s1)
+        assert np.isclose(m1.getobjectivevalue(), obj, rtol=OPT_TOL, atol=OPT_TOL), (name, m1.getobjectivevalue(), obj)
+        if sol is not None:
+            assert np.allclose([m1.getvalue(v) for v in v1], sol, rtol=SOL_TOL, atol=SOL_TOL), name
+        k0, k1 = m0.internal, m1.internal
+        assert len(k1.linear_model.rows) == len(k0.linear_model.rows) - (k0.numcuts - k1.numcuts) - k1.cuts_purged
+        rows0 += len(k0.linear_model.rows); rows1 += len(k1.linear_model.rows)       # (a single problem may take a few more rounds)
+        shrunk += k1.cuts_purged
+    assert shrunk > 0 and rows1 < rows0 / 1.5
+
+
+def test_duplicate_cuts_are_filtered(oracle_lib):
+    """The same constraint stated twice yields bit-identical cuts every round: the filter adds each of them once."""
+    def build(m):
+        x, y = m.variable(-2, 2), m.variable(-2, 2)
+        m.objective("Min", -x - y)
+        m.nlconstraint(x**2 + y**2, "<=", 1.0); m.nlconstraint(x**2 + y**2, "<=", 1.0)
+        return [x, y]
+    m0, _, s0 = solve_problem(oracle_lib, build)
+    m1, _, s1 = solve_problem(oracle_lib, build, cut_filter_duplicates=True)
+    assert s0 == s1 == "Optimal"
+    assert np.isclose(m0.getobjectivevalue(), m1.getobjectivevalue(), rtol=1e-9)
+    k0, k1 = m0.internal, m1.internal
+    assert k1.cuts_filtered > 0 and k1.numcuts + k1.cuts_filtered == k0.numcuts
+    assert k0.iter == k1.iter                 # the LP is the same polyhedron: same iterates
