@@ -66,6 +66,44 @@ MathProgBase.constr_expr(d::EpigraphNLPEvaluator, i) = i < d.num_constr ? MathPr
     Expr(:call, :<=, Expr(:call, :-, MathProgBase.obj_expr(d.nlpeval), Expr(:ref, :x, d.num_var)), 0.0)
 MathProgBase.isconstrlinear(d::EpigraphNLPEvaluator, i) = i < d.num_constr && MathProgBase.isconstrlinear(d.nlpeval, i)
 
+# LP / QP / QCQP route (src/solver.jl:46): a model without @NL macros arrives wrapped in MathProgBase's NonlinearToLPQPBridge, whose
+# evaluator LPQPEvaluator offers [:Grad, :Jac, :Hess] only.  A and Q are captured directly and handed out as expression graphs of
+# the shape JuMP prints for quadratic expressions, +(q*x[i]*x[j] ..., a*x[k] ...), merged and sorted.  (Field names as in MathProgBase
+# 0.7 SolverInterface/nonlinear_to_lpqp.jl -- third-party, not vendored in the reference: adjust to the installed version.  The
+# reference's Jacobian on this route has two entries per quadratic term in COO order; here a cut's columns are the merged row.)
+const LPQPEvaluator = MathProgBase.SolverInterface.LPQPEvaluator
+MathProgBase.features_available(d::LPQPEvaluator) = [:Grad, :Jac, :Hess, :ExprGraph]
+MathProgBase.initialize(d::LPQPEvaluator, feats::Vector{Symbol}) =
+    all(f -> f in MathProgBase.features_available(d), feats) || error("Unsupported feature in $feats")
+function lpqp_expr(lin::Dict{Int,Float64}, quad::Dict{Tuple{Int,Int},Float64})
+    ex = Expr(:call, :+)
+    for k in sort(collect(keys(quad))); push!(ex.args, Expr(:call, :*, quad[k], Expr(:ref, :x, k[1]), Expr(:ref, :x, k[2]))); end
+    for k in sort(collect(keys(lin))); push!(ex.args, Expr(:call, :*, lin[k], Expr(:ref, :x, k))); end
+    length(ex.args) == 1 && push!(ex.args, 0.0)
+    ex
+end
+function MathProgBase.constr_expr(d::LPQPEvaluator, i)
+    lin, quad = Dict{Int,Float64}(), Dict{Tuple{Int,Int},Float64}()
+    nlin = size(d.A, 1)
+    if i <= nlin                                               # row i of A
+        rows, vals = rowvals(d.A), nonzeros(d.A)
+        for j in 1:size(d.A, 2), p in nzrange(d.A, j)
+            rows[p] == i && (lin[j] = get(lin, j, 0.0) + vals[p])
+        end
+    else                                                       # addquadconstr!: sum linearval * x + sum quadval * x[row] * x[col], entries as given
+        q = d.Qconstr[i - nlin]
+        for (j, v) in zip(q.linearidx, q.linearval); lin[j] = get(lin, j, 0.0) + v; end
+        for (a, b, v) in zip(q.quadrowidx, q.quadcolidx, q.quadval); k = (min(a, b), max(a, b)); quad[k] = get(quad, k, 0.0) + v; end
+    end
+    Expr(:call, :<=, lpqp_expr(lin, quad), 0.0)                # only the body is read (constr_body); bounds travel separately
+end
+function MathProgBase.obj_expr(d::LPQPEvaluator)               # c'x + 0.5 x'Qx, Q given by one triangle (setquadobj!)
+    lin = Dict{Int,Float64}(j => v for (j, v) in enumerate(d.c) if v != 0.0)
+    quad = Dict{Tuple{Int,Int},Float64}()
+    for (a, b, v) in zip(d.Qi, d.Qj, d.Qv); k = (min(a, b), max(a, b)); quad[k] = get(quad, k, 0.0) + (a == b ? 0.5 * v : v); end
+    lpqp_expr(lin, quad)
+end
+
 # initialize!(sep, linear_model, num_var, num_constr, oracle)           -- src/separators.jl:81-107
 function initialize!(sep::KatanaGPUSeparator, linear_model, num_var::Int, num_constr::Int, oracle)
     MathProgBase.initialize(oracle, [:ExprGraph])              # the separator initialises the oracle itself (:88)

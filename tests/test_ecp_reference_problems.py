@@ -107,3 +107,40 @@ def test_duplicate_cuts_are_filtered(oracle_lib):
     k0, k1 = m0.internal, m1.internal
     assert k1.cuts_filtered > 0 and k1.numcuts + k1.cuts_filtered == k0.numcuts
     assert k0.iter == k1.iter                 # the LP is the same polyhedron: same iterates
+
+
+def test_models_without_nl_macros_take_the_lpqp_bridge(oracle_lib):
+    """src/solver.jl:46: LP / QP / QCQP models reach Katana through NonlinearToLPQPBridge.  The mirror captures A and Q from the
+    LinearQuadratic calls and hands them out as expression graphs; MathProgBase's conventions (0.5 x'Qx with one triangle given,
+    addquadconstr! entries as given, no objective constant in the LP form) are checked on a worked example."""
+    from katana_jl_b200 import expr as E
+    from katana_jl_b200.lpqp import LPQPEvaluator, NonlinearToLPQPBridge
+    from katana_jl_b200.solver import LinearQuadraticModel, getKatanaModel
+    m = K.Model(K.KatanaSolver(separator=K.KatanaGPUSeparator(library=oracle_lib), log_level=0))
+    x, y = m.variable(-2, 2), m.variable(-2, 2)
+    m.objective("Min", 3 * x**2 + x * y + 2 * y**2 - x + 7.0)
+    m.constraint(x + 2 * y, ">=", -1.0); m.constraint(x**2 + 2 * x * y + 4 * y**2 + y, "<=", 3.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert m.solve() == "Optimal"
+    b = m.bridge
+    assert isinstance(b, NonlinearToLPQPBridge) and getKatanaModel(b) is b.nlpmodel is m.internal
+    assert isinstance(LinearQuadraticModel(m.solver), NonlinearToLPQPBridge)
+    assert b.qobj == ([0, 0, 1], [0, 1, 1], [6.0, 1.0, 4.0])                     # 0.5 x'Qx: diagonal entries doubled
+    assert b.qcons == [([0, 1], [0.0, 1.0], [0, 0, 1], [0, 1, 1], [1.0, 2.0, 4.0])] or b.qcons == [([1], [1.0], [0, 0, 1], [0, 1, 1], [1.0, 2.0, 4.0])]
+    assert b.qbounds == [(-np.inf, 3.0)] and list(b.c) == [-1.0, 0.0]
+    d = LPQPEvaluator(2, b.A_rows, b.c, b.qobj, b.qcons)
+    assert d.features_available() == ["ExprGraph"] and d.isconstrlinear(0) and not d.isconstrlinear(1) and not d.isobjlinear()
+    p = np.array([0.3, -0.7])
+    assert np.isclose(d.eval_f(p), 3 * 0.09 + 0.3 * -0.7 + 2 * 0.49 - 0.3)       # no constant: JuMP adds the 7 back
+    assert np.isclose(E.evaluate(d.constr_expr(1), p), 0.09 + 2 * 0.3 * -0.7 + 4 * 0.49 - 0.7)
+    assert np.isclose(E.evaluate(d.constr_expr(0), p), 0.3 - 1.4)
+    # unconstrained minimiser of the objective (13/23, -... ) is feasible here: check against the closed form
+    H = np.array([[6.0, 1.0], [1.0, 4.0]]); xs = np.linalg.solve(H, [1.0, 0.0])
+    assert np.isclose(m.getobjectivevalue(), 0.5 * xs @ H @ xs - xs[0] + 7.0, rtol=1e-5, atol=1e-5)
+    # a model WITH an @NL macro stays on the NonlinearModel route
+    m2 = K.Model(K.KatanaSolver(separator=K.KatanaGPUSeparator(library=oracle_lib), log_level=0))
+    u = m2.variable(-1, 1); m2.objective("Min", -u); m2.nlconstraint(u**2, "<=", 0.25)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert m2.solve() == "Optimal" and not hasattr(m2, "bridge")

@@ -110,7 +110,7 @@ class Capture:
 
     def evaluator(self):
         m = self.m
-        rows = [(e, True) for e, _, _ in m.lin] + [(e, False) for e, _, _ in m.quad] + [(e, False) for e, _, _ in m.nl]
+        rows = [(r[0], True) for r in m.lin] + [(r[0], False) for r in m.quad] + [(e, False) for e, _, _ in m.nl]
         allc = m.lin + m.quad + m.nl
         return ExprNLPEvaluator(len(m.lb), rows, m.obj, m.obj_lin), [c[1] for c in allc], [c[2] for c in allc]
 
