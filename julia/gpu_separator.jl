@@ -108,7 +108,12 @@ end
 function initialize!(sep::KatanaGPUSeparator, linear_model, num_var::Int, num_constr::Int, oracle)
     MathProgBase.initialize(oracle, [:ExprGraph])              # the separator initialises the oracle itself (:88)
     if sep.handle == C_NULL                                    # one separator is reused across models (test/runtests.jl:24)
-        o = Ref(KtnOptions(sizeof(KtnOptions), -1, 1e-6, 1e9, 0, 1, 0, sep.ngpus > 1 ? sep.ngpus : 0, ntuple(_ -> Int32(-1), 16)))   # flags = 1: lean views
+        # flags: 1 = lean views.  Large models on ONE device run as two pipelined shards of that device (flags |= 4, the device listed
+        # twice): the transfer of the first shard's cuts overlaps the second shard's kernels (measured default of the Python twin,
+        # katana.jl_b200/separators.py: from 400 000 rows on; decided by the first model the separator sees)
+        pipe = sep.ngpus <= 1 && num_constr >= 400_000
+        devs = ntuple(i -> Int32(pipe && i <= 2 ? 0 : -1), 16)
+        o = Ref(KtnOptions(sizeof(KtnOptions), -1, 1e-6, 1e9, 0, pipe ? 5 : 1, 0, pipe ? 2 : (sep.ngpus > 1 ? sep.ngpus : 0), devs))
         h = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:ktn_create, libktn), Cint, (Ref{KtnOptions}, Ref{Ptr{Cvoid}}), o, h)
         rc == 0 || error("ktn_create failed ($rc): no B200 / CUDA device?")
