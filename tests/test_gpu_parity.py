@@ -555,6 +555,31 @@ def test_direct_view_cuts_stored_in_host_memory(oracle_lib, cuda_lib):
     ho.close(); hd.close()
 
 
+def test_sin_cos_edge_values_on_gpu(oracle_lib, cuda_lib):
+    """sin / cos rows on the device at the edges of the shared implementation (csrc/ktn_math.h): zeros of either sign, multiples of
+    pi/2, the end of the exact-reduction range (2^20 pi/2), arguments up to 2^44 (reduced with growing error, identically on both
+    sides), 2^45 and beyond / inf / NaN (NaN: the row is reported as not finite), with and without coefficient rounding."""
+    x, y, z = E.var(0), E.var(1), E.var(2)
+    exprs = [E.sin(x), E.cos(x), E.sin(x) * E.cos(y) + z, E.cos(x * y) - E.sin(z / 3.0), E.sin(E.cos(x)) + y * y, E.exp(E.sin(x)) + E.cos(y)**2,
+             x * E.sin(y) - z * E.cos(x), E.sin(x + y + z) + E.cos(x - y)] * 40          # enough rows of each shape to fill warps
+    m = len(exprs)
+    w = E.to_wire(exprs, np.full(m, -np.inf), np.full(m, -5.0), [ROW_NL] * m)              # every finite row is violated
+    pts = [np.zeros(3), np.array([-0.0, 0.0, -0.0]), np.array([np.pi / 2, np.pi, -np.pi / 2]), np.array([1647099.0, -1647099.5, 3.0]),
+           np.array([1e9, -1e12, 2.0**44]), np.array([1e-300, 5e-324, -1e-308]), np.array([0.5, 2.0**45, 1.0]), np.array([np.inf, 1.0, 1.0]),
+           np.array([1.0, np.nan, 1.0]), np.array([1.0, 1.0, -np.inf]), np.array([355.0, 22.0 / 7.0, 1e5])]
+    for rng_ in (1e9, 10.0):
+        ho, hc = both(oracle_lib, cuda_lib, 3, w, cut_coef_rng=rng_)
+        for p_ in pts:
+            bo, bc = ho.separate(p_), hc.separate(p_)
+            assert_batches_identical(bo, bc, f"sin/cos at {p_}, rng {rng_}")
+            assert bits_equal(ho.eval_g(p_), hc.eval_g(p_))
+        rows = np.arange(0, m, 3, dtype=np.int64)
+        assert_batches_identical(ho.gencut_rows(pts[3], rows, True), hc.gencut_rows(pts[3], rows, True))
+        ho.close(); hc.close()
+    ho, hc = both(oracle_lib, cuda_lib, 3, w)
+    assert ho.separate(pts[6]).status == KTN_NUMERIC_NONFINITE           # 2^45: outside the supported range on both sides
+
+
 @pytest.mark.parametrize("hostpush", ["1", "0"])
 def test_eager_view_pipelined_download(oracle_lib, cuda_lib, monkeypatch, hostpush):
     """KTN_FLAG_EAGER_VIEW: ktn_separate starts every shard's cut download when that shard has finished, into a pinned buffer laid out
