@@ -572,6 +572,8 @@ __global__ void __launch_bounds__(1024) ktn_blkscan_kernel(const KtnRoundParams 
 // One block = KTN_CBLOCK threads x KTN_CRPT consecutive rows per thread = KTN_CROWS rows.
 #define KTN_CRPT (KTN_CROWS / KTN_CBLOCK)
 __global__ void __launch_bounds__(KTN_CBLOCK, KTN_CBPS) ktn_compact_kernel(const KtnRoundParams p, uint32_t nblocks, uint32_t epoch, int scanned) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // programmatic dependent launch: the kernel may have been placed while K1 was draining
+
     __shared__ uint32_t s_cnt_base; __shared__ unsigned long long s_nnz_base, s_tot_n, s_tot_nz;
     __shared__ unsigned long long s_red[4][32];
     __shared__ uint32_t s_off[KTN_CROWS + 1];        // exclusive nnz offsets of the block's selected rows (compact list)
@@ -739,6 +741,8 @@ struct CutSink {    // coefficients and columns: the row's slice of the block's 
 };
 
 __global__ void __launch_bounds__(KTN_XBLOCK, KTN_XBPS) ktn_cut_kernel(const KtnRoundParams p, uint32_t epoch) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
 #ifndef KTN_X_NOSTAGE
     __shared__ double s_val[KTN_XBLOCK * KTN_FAM_REGS];      // coefficients of the block's cuts, in CSR order
 #else
@@ -1051,11 +1055,24 @@ int ktn_launch_round(const KtnRoundParams& p, const KtnLaunchPlan& plan, int num
     if (nblocks > 0) {
         const int scanned = nblocks > 1024u ? 1 : 0;
         if (scanned) { ktn_blkscan_kernel<<<1, 1024, 0, stream>>>(p, nblocks, epoch); ++launches; }
-        ktn_compact_kernel<<<nblocks, KTN_CBLOCK, 0, stream>>>(p, nblocks, epoch, scanned);
-        if (after_compact) cudaEventRecord(after_compact, stream);
         uint32_t xblocks = (uint32_t)((p.num_rows + KTN_XBLOCK - 1) / KTN_XBLOCK);
         if (xblocks > (uint32_t)num_sms * KTN_XBPS) xblocks = (uint32_t)num_sms * KTN_XBPS;      // resident blocks: every block loops over its share of the cuts
-        ktn_cut_kernel<<<xblocks, KTN_XBLOCK, 0, stream>>>(p, epoch);
+        // programmatic dependent launch (KTN_PDL=0 turns it off): K2 / K3 are placed while their predecessor drains and wait in
+        // griddepcontrol.wait.  Measured (10^6 log-sum-exp rows): 125.7 -> 122.6 us per round; with the K1 | K2 event sampled: 118.0
+        static const bool pdl = !(getenv("KTN_PDL") && atoi(getenv("KTN_PDL")) == 0);
+        if (pdl) {
+            cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+            cudaLaunchConfig_t cfg = {}; cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = 1;
+            cfg.gridDim = dim3(nblocks); cfg.blockDim = dim3(KTN_CBLOCK);
+            cudaLaunchKernelEx(&cfg, ktn_compact_kernel, p, nblocks, epoch, scanned);
+            if (after_compact) cudaEventRecord(after_compact, stream);
+            cfg.gridDim = dim3(xblocks); cfg.blockDim = dim3(KTN_XBLOCK);
+            cudaLaunchKernelEx(&cfg, ktn_cut_kernel, p, epoch);
+        } else {
+            ktn_compact_kernel<<<nblocks, KTN_CBLOCK, 0, stream>>>(p, nblocks, epoch, scanned);
+            if (after_compact) cudaEventRecord(after_compact, stream);
+            ktn_cut_kernel<<<xblocks, KTN_XBLOCK, 0, stream>>>(p, epoch);
+        }
         launches += 2;
     }
     *err = cudaGetLastError();

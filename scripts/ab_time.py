@@ -1,6 +1,7 @@
 """A/B timing of library variants: K1 / K2 device times of one separation round per workload.  Run under gpurun:
 python scripts/ab_time.py build/variants/libktn_a.so build/variants/libktn_b.so ..."""
 import hashlib, os, sys
+os.environ.setdefault("KTN_K1_EVENT_EVERY", "1")      # per-round K1 times (the library samples the K1 | K2 event by default)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from katana_jl_b200.binding import KtnLibrary
