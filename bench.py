@@ -214,6 +214,8 @@ def main():
     nv, rows = args.vars, args.rows
     row_begin = rank * rows               # weak scaling: every GPU owns `rows` rows of an instance with world*rows rows
     w, x0 = make_instance(lib, kind, seed, nv, row_begin, rows)
+    if args.steps < 64:      # the library samples the K1 | K2 timing event (one round in eight): a short run needs it in every round
+        os.environ.setdefault("KTN_K1_EVENT_EVERY", "1")
     h = lib.create(device=local, flags=FLAG_LEAN_VIEW)        # as KatanaGPUSeparator creates it: cut views carry what the LP needs
     h.load(nv, w)
     h.set_row_offset(row_begin)
