@@ -115,8 +115,8 @@ enum {
                                compaction and the cut kernel); otherwise compact_ms covers both and cut_ms is 0 */
 };
 
-/* eval_ms / compact_ms / cut_ms are SAMPLED: the event between the evaluation kernel and the compaction kernel is recorded in one
-   round of eight (KTN_K1_EVENT_EVERY; every round with KTN_FLAG_TIME_KERNELS); kernel_ms is measured in every round. */
+/* kernel_ms / eval_ms / compact_ms / cut_ms are SAMPLED: the CUDA events around and between the kernels of a round are recorded in
+   one round of eight (KTN_K1_EVENT_EVERY; every round with KTN_FLAG_TIME_KERNELS). */
 typedef struct ktn_timings {
     double h2d_ms;        /* x* upload (timed with KTN_FLAG_TIME_KERNELS only: two CUDA events per call otherwise saved) */
     double kernel_ms;     /* separation kernels, CUDA events on the library stream */

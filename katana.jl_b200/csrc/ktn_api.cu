@@ -304,9 +304,7 @@ static void drain_ring(ktn_handle* h, bool all) {
         if (!all && cudaEventQuery(e[2]) != cudaSuccess) break;
         float a = 0.f, b = 0.f, c = 0.f;      // K1 | K2 + K3 | K2 alone (KTN_FLAG_TIME_KERNELS: an event is recorded between K2 and K3, which costs the round a few microseconds)
         const bool detail = (h->opt.flags & KTN_FLAG_TIME_KERNELS) != 0;
-        if (!h->ring_mid[h->ring_tail % ktn_handle::RING]) {      // a round without the K1 | K2 event: only its total is known
-            if (cudaEventElapsedTime(&a, e[0], e[2]) == cudaSuccess) h->tm.kernel_ms = a;
-        } else if (cudaEventElapsedTime(&a, e[0], e[1]) == cudaSuccess && cudaEventElapsedTime(&b, e[1], e[2]) == cudaSuccess && (!detail || cudaEventElapsedTime(&c, e[1], e[3]) == cudaSuccess)) {
+        if (cudaEventElapsedTime(&a, e[0], e[1]) == cudaSuccess && cudaEventElapsedTime(&b, e[1], e[2]) == cudaSuccess && (!detail || cudaEventElapsedTime(&c, e[1], e[3]) == cudaSuccess)) {
             if (!detail) c = b;
             h->eval_ms_sum += a; h->compact_ms_sum += c; h->cut_ms_sum += b - c; h->rounds_timed++;
             h->tm.kernel_ms = a + b; h->tm.eval_ms = a; h->tm.compact_ms = c; h->tm.cut_ms = b - c;
@@ -328,25 +326,24 @@ static int enqueue_round(ktn_handle* h, const double* d_x, int mode, int do_roun
     p.clear_unselected = h->forced_last ? 1 : 0; h->forced_last = mode == KTN_MODE_FORCE;
     cudaError_t e = cudaSuccess;
     (void)cudaGetLastError();   // a stale non-sticky error must not be blamed on this round's launches
-    if (h->ring_head - h->ring_tail >= ktn_handle::RING) drain_ring(h, false);
-    if (h->ring_head - h->ring_tail >= ktn_handle::RING) { CK(h, cudaEventSynchronize(h->ring[h->ring_tail % ktn_handle::RING][2])); drain_ring(h, false); }
+    // the kernels of a round are timed with CUDA events around and between them in one round of mid_every (KTN_K1_EVENT_EVERY; every
+    // round with KTN_FLAG_TIME_KERNELS): the records cost 2-4 us per round and keep the next kernel from being placed early
+    const bool detail = (h->opt.flags & KTN_FLAG_TIME_KERNELS) != 0;
+    const bool mid = detail || h->mid_every <= 1 || (h->tm.rounds % h->mid_every) == 0;
+    if (mid && h->ring_head - h->ring_tail >= ktn_handle::RING) drain_ring(h, false);
+    if (mid && h->ring_head - h->ring_tail >= ktn_handle::RING) { CK(h, cudaEventSynchronize(h->ring[h->ring_tail % ktn_handle::RING][2])); drain_ring(h, false); }
     cudaEvent_t* ev = h->ring[h->ring_head % ktn_handle::RING];
-    CK(h, cudaEventRecord(ev[0], h->stream));
+    if (mid) CK(h, cudaEventRecord(ev[0], h->stream));
     // peer-push exchange: the persistent K1 leaves the push kernel's SMs free, so that the push of the previous round starts at once
     // beside this round instead of queueing behind K1's resident blocks (K1 owns every register of the SMs it runs on)
     ktn_comm_plan_blocks(h);
     int sms = h->num_sms;
     if (h->comm && h->px.on && h->px.reserve && sms > 2 * h->px.blocks) sms -= h->px.blocks;
     if (h->reserve_sms > 0 && sms > 2 * h->reserve_sms) sms -= h->reserve_sms;
-    // the event between K1 and K2 is what ktn_timings.eval_ms is measured with; it is recorded in one round of mid_every (KTN_K1_EVENT_EVERY)
-    const bool detail = (h->opt.flags & KTN_FLAG_TIME_KERNELS) != 0;
-    const bool mid = detail || h->mid_every <= 1 || (h->tm.rounds % h->mid_every) == 0;
-    h->ring_mid[h->ring_head % ktn_handle::RING] = mid;
     int n = ktn_launch_round(p, make_plan(h), sms, h->max_smem, h->epoch, h->stream, mid ? ev[1] : nullptr, detail ? ev[3] : nullptr, &e);
     h->tm.launches += n;
     if (e != cudaSuccess) return fail(h, KTN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
-    CK(h, cudaEventRecord(ev[2], h->stream));
-    h->ring_head++;
+    if (mid) { CK(h, cudaEventRecord(ev[2], h->stream)); h->ring_head++; }
     h->round_pending = true; h->tm.rounds++;      // the counts are read back when somebody asks for them (finish_round): no copy between back-to-back rounds
     return KTN_OK;
 }

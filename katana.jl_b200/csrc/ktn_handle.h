@@ -30,8 +30,7 @@ struct ktn_handle {
     // per-round kernel timing: ring of (start, after K1, after K3, after K2) events, drained by ktn_timings_get
     static const int RING = 128;
     cudaEvent_t ring[RING][4];
-    bool ring_mid[RING] = {};      // the round recorded the event between K1 and K2 (it is sampled: see enqueue_round)
-    int mid_every = 8;             // measured: an event between K1 and K2 in every round costs 2-4 us per round (it also keeps K2 from being placed early)
+    int mid_every = 8;             // the timing events of a round are recorded in one round of mid_every (enqueue_round)
     int ring_head = 0, ring_tail = 0;      // [tail, head) not yet drained
     double eval_ms_sum = 0, compact_ms_sum = 0, cut_ms_sum = 0; int64_t rounds_timed = 0;
     double exchange_ms_sum = 0; int64_t exchanges_timed = 0;

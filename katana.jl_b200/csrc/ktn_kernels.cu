@@ -235,6 +235,8 @@ __device__ __forceinline__ void family_class(const KtnRoundParams& p, uint32_t l
 
 template <int FAM>
 __global__ void __launch_bounds__(KTN_FP_WARPS * 32, 1) ktn_family_kernel(const KtnRoundParams p) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // launched programmatically behind the previous round's cut kernel
+
     const uint32_t lane = threadIdx.x & 31u;
     unsigned int* tickets = p.ticket + p.ticket_idx;
     const uint32_t my_n = lane < KTN_FAM_NCLS ? p.cls_begin[FAM][lane + 1] - p.cls_begin[FAM][lane] : 0u;     // lane k: chunks of class k
@@ -1001,7 +1003,13 @@ static void launch_family(KtnRoundParams p, const KtnLaunchPlan& plan, uint32_t 
     uint32_t blocks = (uint32_t)num_sms;      // persistent: one block per SM
     const uint32_t need = (end - begin + KTN_FP_WARPS - 1) / KTN_FP_WARPS;
     if (blocks > need) blocks = need;
-    ktn_family_kernel<FAM><<<blocks, KTN_FP_WARPS * 32, KTN_FP_SMEM, stream>>>(p);
+    static const bool pdl = !(getenv("KTN_PDL") && atoi(getenv("KTN_PDL")) == 0);
+    if (pdl) {
+        cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg = {}; cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = 1;
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(KTN_FP_WARPS * 32); cfg.dynamicSmemBytes = KTN_FP_SMEM;
+        cudaLaunchKernelEx(&cfg, ktn_family_kernel<FAM>, p);
+    } else ktn_family_kernel<FAM><<<blocks, KTN_FP_WARPS * 32, KTN_FP_SMEM, stream>>>(p);
 }
 
 template <bool EVAL>
