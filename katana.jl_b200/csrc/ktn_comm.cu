@@ -411,13 +411,14 @@ int ktn_comm_launch_pending(ktn_handle* h) {
 // Called by the round launcher (peer-push transport) before it sizes K1's grid: how many SMs the push kernel gets.
 // MEASURED defaults (10^6 log-sum-exp rows per GPU, v = 0.1; profiles/scale_r02_{4,8}gpu.log): 2 GPUs: 16 blocks (151 us per
 // round); 4 GPUs: 32 blocks 180 us (16: 187, 24: 188, 8: 246); 8 GPUs: 32 blocks 323 us = 508 GB/s inbound per GPU (16: 391,
-// 48: 350).  More blocks push faster but are taken from K1.  A volume-driven rule shipped unmeasured in round 1 and cost the
+// 48: 350); final build (faster kernels, scripts/scale_final8.sh, one box): 24: 350 us, 32: 335, 40: 301 -> 40 blocks from 8 GPUs on.
+// More blocks push faster but are taken from K1.  A volume-driven rule shipped unmeasured in round 1 and cost the
 // 4- and 8-GPU runs a factor 1.8; it is available as KTN_PUSH_PLAN=volume for experiments, KTN_PUSH_BLOCKS fixes the grid.
 void ktn_comm_plan_blocks(ktn_handle* h) {
     ktn_handle::PeerExchange& px = h->px;
     if (!h->comm || !px.on || px.blocks_fixed || !h->have_round) return;
     static const bool by_volume = getenv("KTN_PUSH_PLAN") && !strcmp(getenv("KTN_PUSH_PLAN"), "volume");
-    if (!by_volume) { px.blocks = h->nranks <= 2 ? 16 : 32; return; }
+    if (!by_volume) { px.blocks = h->nranks <= 2 ? 16 : h->nranks < 8 ? 32 : 40; return; }
     const double out = (double)ktn_pack_layout((unsigned long long)h->lay_cuts, (unsigned long long)h->lay_nnz).total * (double)h->nranks;
     int b = (int)(out / 3.0e6) + 1;
     const int hi = h->num_sms / 3 < 48 ? h->num_sms / 3 : 48;
