@@ -172,7 +172,7 @@ void ktn_comm_release(ktn_handle* h) {
     if (h->comm && N.ok) N.CommDestroy((ncclComm_t)h->comm);
     h->comm = nullptr;
     for (auto& x : h->xch) {
-        x.gathered.release(); x.all_counts.release();
+        x.gathered.release(); x.all_counts.release(); x.stage.release();
         if (x.h_all_counts) { cudaFreeHost(x.h_all_counts); x.h_all_counts = nullptr; }
         if (x.packed) { cudaEventDestroy(x.packed); cudaEventDestroy(x.sizes); cudaEventDestroy(x.t0); cudaEventDestroy(x.t1); x.packed = x.sizes = x.t0 = x.t1 = nullptr; }
         x.state = 0;
@@ -359,9 +359,17 @@ static int launch_payload(ktn_handle* h, ktn_handle::Exchange& x) {
     const size_t off = slot * (size_t)h->nranks;
     x.gathered_bytes = (int64_t)off;
     if (x.gathered.bytes < off) { CK(h, cudaStreamSynchronize(h->comm_stream)); CK(h, x.gathered.alloc(off + off / 4)); }
-    if (h->out_cap < slot) return fail(h, KTN_ERR_NCCL, "exchange slot larger than this rank's cut blob (very unbalanced shards)");
+    // very unbalanced shards: the common slot may be larger than this rank's blob buffer.  No rank may bail out between collective
+    // calls (the others would wait in the all-gather forever): the blob is staged into a buffer of the slot size instead
+    const void* send = h->out_blob[x.src_idx].p;
+    if (h->out_cap < slot) {
+        if (x.stage.bytes < slot) { CK(h, cudaStreamSynchronize(h->comm_stream)); CK(h, x.stage.alloc(slot + slot / 4)); }
+        const size_t mine = (size_t)x.g_bytes[h->rank] < h->out_cap ? (size_t)x.g_bytes[h->rank] : h->out_cap;
+        CK(h, cudaMemcpyAsync(x.stage.p, h->out_blob[x.src_idx].p, mine, cudaMemcpyDeviceToDevice, h->comm_stream));
+        send = x.stage.p;
+    }
     CK(h, cudaEventRecord(x.t0, h->comm_stream));
-    NK(h, N.AllGather(h->out_blob[x.src_idx].p, x.gathered.p, slot, ncclUint8, comm, h->comm_stream));
+    NK(h, N.AllGather(send, x.gathered.p, slot, ncclUint8, comm, h->comm_stream));
     CK(h, cudaEventRecord(x.t1, h->comm_stream));
     CK(h, cudaEventRecord(h->blob_ev[x.src_idx], h->comm_stream)); h->blob_busy[x.src_idx] = true;
     x.state = 2;

@@ -59,7 +59,7 @@ struct ktn_handle {
     void* comm = nullptr; int nranks = 1, rank = 0;
     cudaStream_t comm_stream = nullptr;
     struct Exchange {
-        DevBuf gathered, all_counts;
+        DevBuf gathered, all_counts, stage;             // stage: send buffer of the common slot size when this rank's own blob is smaller
         unsigned long long* h_all_counts = nullptr;     // pinned [8 * nranks]: the blob headers of all ranks
         std::vector<int64_t> g_cuts, g_nnz, g_off;      // per rank, once the headers are on the host (ranks behind the first non-finite cut: 0)
         int64_t g_err_row = -1;                         // global index of the first non-finite row of the gathered batch (-1: none)

@@ -101,6 +101,8 @@ def flatten_into(node, ops, args, vals):
 
 def to_wire(exprs, lb, ub, flags):
     """Flatten a list of expression trees into one WireRows batch."""
+    if not (len(lb) == len(ub) == len(flags) == len(exprs)):
+        raise ValueError(f"to_wire: {len(exprs)} rows but {len(lb)} lower bounds, {len(ub)} upper bounds, {len(flags)} flags")
     ops, args, vals, ptr = [], [], [], [0]
     for e in exprs:
         flatten_into(wrap(e), ops, args, vals)

@@ -57,7 +57,8 @@ def kat_problem():
         E.sum_([E.var(i)**2 for i in range(3)]) - z,       # dense epigraph-style row, last
     ]
     m = len(exprs)
-    ub = np.array([1.0, 0, 0, 0, 0, 0, 0, 1, 1, 5, 2, 1, 0, 0.5, 1, 0, 4, 3, 1, 1, 0.0])
+    ub = np.array([1.0, 0, 0, 0, 0, 0, 0, 1, 1, 5, 2, 1, 0, 0.5, 1, 0, 4, 3, 1, 1, 0.5, -0.25, 0.75, 0.0])
+    assert len(ub) == m
     flags = [ROW_NL] * (m - 1) + [ROW_NL | ROW_DENSE]
     w = E.to_wire(exprs, np.full(m, -np.inf), ub, flags)
     pts = [np.array(p, float) for p in ([2, 2, 1], [0.5, 1.5, 0.25], [0.3, 0.7, 2.0], [-1, 3, 2], [1, 0.5, 2], [3, -2, 0.5], [0, 0, 0], [1, 0, 2])]
