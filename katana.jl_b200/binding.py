@@ -243,7 +243,7 @@ class Handle:
                      (w.lb, np.float64), (w.ub, np.float64), (w.flags, np.uint8)):
             assert a.dtype == t and a.flags.c_contiguous
         n, ne = w.nrows, int(w.expr_ptr[-1])       # the C side reads exactly these many entries: short arrays would be read past their end
-        if not (len(w.lb) == len(w.ub) == len(w.flags) == n and len(w.op) == len(w.arg) == len(w.val) == ne):
+        if not (len(w.lb) == len(w.ub) == len(w.flags) == n == len(w.expr_ptr) - 1 and len(w.op) == len(w.arg) == len(w.val) == ne):
             raise ValueError(f"wire rows: {n} rows / {ne} nodes, but lb {len(w.lb)}, ub {len(w.ub)}, flags {len(w.flags)}, op {len(w.op)}, arg {len(w.arg)}, val {len(w.val)}")
         self._ck(self.dll.ktn_add_rows(self.h, first_row, w.nrows, _ptr(w.expr_ptr), _ptr(w.op), _ptr(w.arg), _ptr(w.val),
                                        _ptr(w.lb), _ptr(w.ub), _ptr(w.flags)), "ktn_add_rows")
