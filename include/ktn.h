@@ -48,7 +48,14 @@ enum {
     KTN_OP_ABS   = 11,
     KTN_OP_SIN   = 12,
     KTN_OP_COS   = 13,
-    KTN_OP__COUNT = 14
+    KTN_OP_IFELSE = 14, /* ifelse(cond, a, b): a where cond == 1.0, else b; BOTH branches are evaluated (JuMP's tape is linear); the
+                           unselected branch and the condition receive a zero partial */
+    KTN_OP_LE    = 15,  /* binary comparisons (JuMP allows them as ifelse conditions): 1.0 / 0.0, NaN compares false; zero partials */
+    KTN_OP_LT    = 16,
+    KTN_OP_GE    = 17,
+    KTN_OP_GT    = 18,
+    KTN_OP_EQ    = 19,
+    KTN_OP__COUNT = 20
 };
 
 /* per-row flags */

@@ -34,7 +34,8 @@ check(sep, rc, what) = rc < 0 && error("$what failed ($rc): " *
     unsafe_string(ccall((:ktn_last_error, libktn), Cstring, (Ptr{Cvoid},), sep.handle)))
 
 # op codes of the wire format (include/ktn.h KTN_OP_*)
-const KTN_OPS = Dict(:+ => 2, :- => 3, :* => 4, :/ => 5, :^ => 6, :exp => 8, :log => 9, :sqrt => 10, :abs => 11, :sin => 12, :cos => 13)
+const KTN_OPS = Dict(:+ => 2, :- => 3, :* => 4, :/ => 5, :^ => 6, :exp => 8, :log => 9, :sqrt => 10, :abs => 11, :sin => 12, :cos => 13,
+                     :ifelse => 14, :<= => 15, :< => 16, :>= => 17, :> => 18, :(==) => 19)
 
 # Flatten one expression tree over x[i] (MathProgBase constr_expr / obj_expr) into prefix arrays.
 function flatten!(op::Vector{Int32}, arg::Vector{Int32}, val::Vector{Float64}, ex)
@@ -42,6 +43,9 @@ function flatten!(op::Vector{Int32}, arg::Vector{Int32}, val::Vector{Float64}, e
         push!(op, 0); push!(arg, 0); push!(val, Float64(ex))
     elseif ex isa Expr && ex.head == :ref                     # x[i]
         push!(op, 1); push!(arg, Int32(ex.args[2] - 1)); push!(val, 0.0)
+    elseif ex isa Expr && ex.head == :comparison && length(ex.args) == 3     # a <= b inside ifelse (Julia 0.5 / 0.6 parse it as :comparison)
+        push!(op, KTN_OPS[ex.args[2]]); push!(arg, 2); push!(val, 0.0)
+        flatten!(op, arg, val, ex.args[1]); flatten!(op, arg, val, ex.args[3])
     elseif ex isa Expr && ex.head == :call
         f, a = ex.args[1], ex.args[2:end]
         if f == :- && length(a) == 1                           # unary minus

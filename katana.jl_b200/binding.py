@@ -15,7 +15,8 @@ SYNTH_LIB_PATH = os.path.join(_HERE, "libktn_synth.so")
 CUDA_LIB_PATH = os.environ.get("KTN_LIB") or os.path.join(_HERE, "libktn.so")      # KTN_LIB: an A/B variant build of the CUDA library (scripts/build_variants.sh)
 
 # wire-format constants (include/ktn.h)
-OP_CONST, OP_VAR, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_NEG, OP_EXP, OP_LOG, OP_SQRT, OP_ABS, OP_SIN, OP_COS = range(14)
+(OP_CONST, OP_VAR, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_NEG, OP_EXP, OP_LOG, OP_SQRT, OP_ABS, OP_SIN, OP_COS,
+ OP_IFELSE, OP_LE, OP_LT, OP_GE, OP_GT, OP_EQ) = range(20)
 ROW_NL, ROW_DENSE = 1, 2
 KTN_OK, KTN_NUMERIC_NONFINITE = 0, 1
 FLAG_LEAN_VIEW = 1          # ktn_options.flags: cut views carry only what the LP needs

@@ -33,8 +33,9 @@ static int arity(int op) {
     switch (op) {
         case KTN_OP_CONST: case KTN_OP_VAR: return 0;
         case KTN_OP_ADD: case KTN_OP_MUL: return -1;
-        case KTN_OP_SUB: case KTN_OP_DIV: case KTN_OP_POW: return 2;
+        case KTN_OP_SUB: case KTN_OP_DIV: case KTN_OP_POW: case KTN_OP_LE: case KTN_OP_LT: case KTN_OP_GE: case KTN_OP_GT: case KTN_OP_EQ: return 2;
         case KTN_OP_NEG: case KTN_OP_EXP: case KTN_OP_LOG: case KTN_OP_SQRT: case KTN_OP_ABS: case KTN_OP_SIN: case KTN_OP_COS: return 1;
+        case KTN_OP_IFELSE: return 3;
         default: return -2;
     }
 }
@@ -136,6 +137,7 @@ struct ShapeCompiler {
             switch (n.op) {
                 case KTN_OP_EXP: case KTN_OP_SQRT: n.need_value = true; break;
                 case KTN_OP_LOG: case KTN_OP_ABS: case KTN_OP_SIN: case KTN_OP_COS: t[ch[0]].need_value = true; break;
+                case KTN_OP_IFELSE: t[ch[0]].need_value = true; break;      // the reverse sweep re-reads the condition
                 case KTN_OP_POW: if (t[ch[1]].expclass == 2 && t[ch[0]].has_var) t[ch[0]].need_value = true; break;
                 case KTN_OP_MUL:
                     if (n.nc == 2) { if (t[ch[0]].has_var) t[ch[1]].need_value = true; if (t[ch[1]].has_var) t[ch[0]].need_value = true; }
@@ -237,6 +239,22 @@ struct ShapeCompiler {
             case KTN_OP_ABS: gen_fwd(ch[0]); emit(KF_ABS); break;
             case KTN_OP_SIN: gen_fwd(ch[0]); emit(KF_SIN); break;
             case KTN_OP_COS: gen_fwd(ch[0]); emit(KF_COS); break;
+            case KTN_OP_IFELSE: {       // both branches are evaluated (JuMP's tape is linear); acc = then, aux = else, select on cond == 1
+                const int C = ch[0], A = ch[1], B = ch[2];
+                Src cs; bool ctemp = false;
+                if (t[C].is_leaf) cs = t[C].val;
+                else { gen_fwd(C); if (t[C].has_val) cs = t[C].val; else { cs = push_temp(); emit(KF_STORE, cs); ctemp = true; } }
+                if (t[B].is_leaf) { gen_fwd(A); emit(KF_LDAUX, t[B].val); }
+                else { gen_fwd(B); Src T = push_temp(); emit(KF_STORE, T); gen_fwd(A); emit(KF_LDAUX, T); pop_temp(); }
+                emit(KF_SEL1, cs);
+                if (ctemp) pop_temp();
+                break; }
+            case KTN_OP_LE: case KTN_OP_LT: case KTN_OP_GE: case KTN_OP_GT: case KTN_OP_EQ: {   // acc = (L cmp R) ? 1 : 0, L as the operand, R in acc
+                const int L = ch[0], R = ch[1];
+                const uint16_t cmp = (uint16_t)(n.op - KTN_OP_LE);
+                if (t[L].is_leaf) { gen_fwd(R); emit(KF_CMP, t[L].val, cmp); }
+                else { gen_fwd(L); Src T = push_temp(); emit(KF_STORE, T); gen_fwd(R); emit(KF_CMP, T, cmp); pop_temp(); }
+                break; }
             default: err = "unknown op in gen_fwd";
         }
         persist(k);
@@ -306,6 +324,10 @@ struct ShapeCompiler {
                 case KTN_OP_ABS: emit(KR_MULSGN, t[c].val); break;
                 case KTN_OP_SIN: emit(KR_MULCOS, t[c].val); break;
                 case KTN_OP_COS: emit(KR_MULNSIN, t[c].val); break;
+                case KTN_OP_IFELSE:
+                    if (ci == 0) emit(KR_MULZERO); else emit(ci == 1 ? KR_MULEQ1 : KR_MULNE1, t[ch[0]].val);
+                    break;
+                case KTN_OP_LE: case KTN_OP_LT: case KTN_OP_GE: case KTN_OP_GT: case KTN_OP_EQ: emit(KR_MULZERO); break;
                 default: err = "unknown op in gen_rev";
             }
             gen_rev(c);

@@ -215,6 +215,10 @@ KTN_HD double run_program(const KtnIns* prog, uint32_t pc, uint32_t end, M& m, u
             case KF_POWPB: m.sts(idx, pow_dbase(acc, aux)); break;
             case KF_POWPE: m.sts(idx, pow_value(acc, aux) * ktn_log(acc)); break;
             case KF_SELZ: acc = (src == 0.0) ? aux : acc; break;
+            case KF_SEL1: acc = (src == 1.0) ? acc : aux; break;
+            case KF_CMP: { const uint32_t cmp = w.x >> 16;
+                const bool r = cmp == 0u ? src <= acc : cmp == 1u ? src < acc : cmp == 2u ? src >= acc : cmp == 3u ? src > acc : src == acc;
+                acc = r ? 1.0 : 0.0; break; }
             case KF_SKIPNZ: if (!KTN_ANY_LANE(mask, src == 0.0)) pc += (w.x >> 16); break;
             case KR_ONE: acc = 1.0; break;
             case KR_MUL: acc = revmul(acc, src); break;
@@ -225,6 +229,9 @@ KTN_HD double run_program(const KtnIns* prog, uint32_t pc, uint32_t end, M& m, u
             case KR_MULSGN: acc = revmul(acc, src >= 0.0 ? 1.0 : -1.0); break;
             case KR_MULCOS: acc = revmul(acc, ktn_cos(src)); break;
             case KR_MULNSIN: acc = revmul(acc, -ktn_sin(src)); break;
+            case KR_MULZERO: acc = revmul(acc, 0.0); break;
+            case KR_MULEQ1: acc = revmul(acc, src == 1.0 ? 1.0 : 0.0); break;
+            case KR_MULNE1: acc = revmul(acc, src == 1.0 ? 0.0 : 1.0); break;
             case KR_JSET: m.jst(idx, 0.0 + acc); break;
             case KR_JACC: m.jst(idx, m.jld(idx) + acc); break;
             case KF_TERMS: acc = terms_fwd(m, kind & 0xfu, w.x >> 16, idx, w.z, w.w, (kind & KTN_TF_FIRST) != 0, (kind & KTN_TF_SAVEBLOB) != 0, acc); break;

@@ -51,6 +51,8 @@ enum {
     KF_POWPB,      // S[idx] = aux * pow(acc, aux - 1)  (d/d base; before KF_POWG)
     KF_POWPE,      // S[idx] = pow(acc, aux) * log(acc) (d/d exponent; before KF_POWG)
     KF_SELZ,       // acc = (src == 0) ? aux : acc
+    KF_SEL1,       // acc = (src == 1) ? acc : aux          (ifelse: then-branch in acc, else-branch in aux)
+    KF_CMP,        // acc = (src CMP acc) ? 1.0 : 0.0       (n: 0 <=, 1 <, 2 >=, 3 >, 4 ==; src = left operand)
     KF_SKIPNZ,     // if no lane of the warp has src == 0: skip the next n instructions
     // ---- reverse: acc holds the adjoint; revmul(a, p) = (a == 0 && !finite(p)) ? a : a * p ----
     KR_ONE,        // acc = 1.0
@@ -62,6 +64,9 @@ enum {
     KR_MULSGN,     // acc = revmul(acc, src >= 0 ? 1.0 : -1.0)
     KR_MULCOS,     // acc = revmul(acc, cos(src))                (d sin)
     KR_MULNSIN,    // acc = revmul(acc, -sin(src))               (d cos)
+    KR_MULZERO,    // acc = revmul(acc, 0.0)                     (conditions and comparison operands)
+    KR_MULEQ1,     // acc = revmul(acc, src == 1 ? 1.0 : 0.0)    (ifelse, then-branch)
+    KR_MULNE1,     // acc = revmul(acc, src == 1 ? 0.0 : 1.0)    (ifelse, else-branch)
     KR_JSET,       // J[idx] = 0.0 + acc
     KR_JACC,       // J[idx] = J[idx] + acc
     // ---- fused runs of identical terms inside an n-ary sum: the same arithmetic as the primitive

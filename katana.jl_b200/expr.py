@@ -9,7 +9,7 @@ import math
 
 import numpy as np
 
-from .binding import (OP_ABS, OP_ADD, OP_CONST, OP_COS, OP_SIN, OP_DIV, OP_EXP, OP_LOG, OP_MUL, OP_NEG, OP_POW, OP_SQRT, OP_SUB, OP_VAR,
+from .binding import (OP_ABS, OP_ADD, OP_CONST, OP_COS, OP_SIN, OP_IFELSE, OP_LE, OP_LT, OP_GE, OP_GT, OP_EQ, OP_DIV, OP_EXP, OP_LOG, OP_MUL, OP_NEG, OP_POW, OP_SQRT, OP_SUB, OP_VAR,
                       ROW_DENSE, ROW_NL, WireRows)
 
 _NARY = (OP_ADD, OP_MUL)
@@ -72,6 +72,12 @@ def sqrt(a): return call(OP_SQRT, a)
 def abs_(a): return call(OP_ABS, a)
 def sin(a): return call(OP_SIN, a)
 def cos(a): return call(OP_COS, a)
+def ifelse(cond, a, b): return call(OP_IFELSE, cond, a, b)      # JuMP: ifelse(x <= 1, x^2, 2x - 1); both branches are evaluated
+def le(a, b): return call(OP_LE, a, b)
+def lt(a, b): return call(OP_LT, a, b)
+def ge(a, b): return call(OP_GE, a, b)
+def gt(a, b): return call(OP_GT, a, b)
+def eq(a, b): return call(OP_EQ, a, b)
 
 
 def sum_(terms):
@@ -147,6 +153,12 @@ def evaluate(node, x):
     if op == OP_ABS: return abs(c[0])
     if op == OP_SIN: return math.sin(c[0]) if math.isfinite(c[0]) else math.nan
     if op == OP_COS: return math.cos(c[0]) if math.isfinite(c[0]) else math.nan
+    if op == OP_IFELSE: return c[1] if c[0] == 1.0 else c[2]
+    if op == OP_LE: return 1.0 if c[0] <= c[1] else 0.0
+    if op == OP_LT: return 1.0 if c[0] < c[1] else 0.0
+    if op == OP_GE: return 1.0 if c[0] >= c[1] else 0.0
+    if op == OP_GT: return 1.0 if c[0] > c[1] else 0.0
+    if op == OP_EQ: return 1.0 if c[0] == c[1] else 0.0
     raise ValueError(f"unknown op {op}")
 
 
@@ -218,5 +230,5 @@ def to_quadform(node):
     raise ValueError("expression is not polynomial; use the NL form")
 
 
-__all__ = ["Node", "var", "const", "call", "exp", "log", "sqrt", "abs_", "sin", "cos", "sum_", "prod_", "to_wire", "flatten_into", "evaluate",
+__all__ = ["Node", "var", "const", "call", "exp", "log", "sqrt", "abs_", "sin", "cos", "ifelse", "le", "lt", "ge", "gt", "eq", "sum_", "prod_", "to_wire", "flatten_into", "evaluate",
            "variables", "QuadForm", "to_quadform", "wrap", "ROW_NL", "ROW_DENSE"]

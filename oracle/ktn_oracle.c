@@ -117,8 +117,9 @@ static int arity(int op) {
     switch (op) {
         case KTN_OP_CONST: case KTN_OP_VAR: return 0;
         case KTN_OP_ADD: case KTN_OP_MUL: return -1;
-        case KTN_OP_SUB: case KTN_OP_DIV: case KTN_OP_POW: return 2;
+        case KTN_OP_SUB: case KTN_OP_DIV: case KTN_OP_POW: case KTN_OP_LE: case KTN_OP_LT: case KTN_OP_GE: case KTN_OP_GT: case KTN_OP_EQ: return 2;
         case KTN_OP_NEG: case KTN_OP_EXP: case KTN_OP_LOG: case KTN_OP_SQRT: case KTN_OP_ABS: case KTN_OP_SIN: case KTN_OP_COS: return 1;
+        case KTN_OP_IFELSE: return 3;
         default: return -2;
     }
 }
@@ -261,6 +262,13 @@ static double forward_row(const ktn_handle* h, int64_t row, const double* x, dou
             case KTN_OP_ABS: st[k] = ktn_fabs(st[k + 1]); pa[k + 1] = (st[k + 1] >= 0.0) ? 1.0 : -1.0; break;
             case KTN_OP_SIN: st[k] = ktn_sin(st[k + 1]); pa[k + 1] = ktn_cos(st[k + 1]); break;      /* Calculus.jl: cos(x) */
             case KTN_OP_COS: st[k] = ktn_cos(st[k + 1]); pa[k + 1] = -ktn_sin(st[k + 1]); break;     /* Calculus.jl: -sin(x) */
+            case KTN_OP_IFELSE: { int64_t c1 = k + 1, c2 = se[c1], c3 = se[c2];   /* [recalled] ReverseDiffSparse forward_eval: condition == 1 */
+                int sel = st[c1] == 1.0;
+                st[k] = sel ? st[c2] : st[c3]; pa[c1] = 0.0; pa[c2] = sel ? 1.0 : 0.0; pa[c3] = sel ? 0.0 : 1.0; break; }
+            case KTN_OP_LE: case KTN_OP_LT: case KTN_OP_GE: case KTN_OP_GT: case KTN_OP_EQ: { int64_t c1 = k + 1, c2 = se[c1];
+                double a = st[c1], b = st[c2];
+                int r = op[k] == KTN_OP_LE ? a <= b : op[k] == KTN_OP_LT ? a < b : op[k] == KTN_OP_GE ? a >= b : op[k] == KTN_OP_GT ? a > b : a == b;
+                st[k] = r ? 1.0 : 0.0; pa[c1] = 0.0; pa[c2] = 0.0; break; }
         }
     }
     return st[0];

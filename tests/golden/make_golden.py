@@ -43,6 +43,12 @@ def to_sympy(w, r, xs):
         if op == E.OP_ABS: return sp.Abs(ch[0])
         if op == E.OP_SIN: return sp.sin(ch[0])
         if op == E.OP_COS: return sp.cos(ch[0])
+        if op == E.OP_IFELSE: return sp.Piecewise((ch[1], ch[0]), (ch[2], True))
+        if op == E.OP_LE: return sp.Le(ch[0], ch[1])
+        if op == E.OP_LT: return sp.Lt(ch[0], ch[1])
+        if op == E.OP_GE: return sp.Ge(ch[0], ch[1])
+        if op == E.OP_GT: return sp.Gt(ch[0], ch[1])
+        if op == E.OP_EQ: return sp.Eq(ch[0], ch[1])
         raise ValueError(op)
     return rec()
 

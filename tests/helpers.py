@@ -54,10 +54,11 @@ def kat_problem():
         E.sin(-x - 1.0) + x / 2.0 + 0.5 - y,               # test/2d.jl:367 (case 106, commented out upstream: not convex on the box)
         y - (E.cos(x - 0.5) + x / 4.0 - 0.5),              # test/2d.jl:368
         E.sin(x * y) * E.cos(z) + E.cos(E.exp(x)),          # sin / cos under products and of transcendental arguments
+        E.ifelse(E.le(x, 1.0), x**2, 2.0 * x - 1.0) + E.ifelse(E.gt(y * z, x), E.exp(y), y + 1.0),   # ifelse with comparisons (JuMP's user-visible piecewise form)
         E.sum_([E.var(i)**2 for i in range(3)]) - z,       # dense epigraph-style row, last
     ]
     m = len(exprs)
-    ub = np.array([1.0, 0, 0, 0, 0, 0, 0, 1, 1, 5, 2, 1, 0, 0.5, 1, 0, 4, 3, 1, 1, 0.5, -0.25, 0.75, 0.0])
+    ub = np.array([1.0, 0, 0, 0, 0, 0, 0, 1, 1, 5, 2, 1, 0, 0.5, 1, 0, 4, 3, 1, 1, 0.5, -0.25, 0.75, 1.5, 0.0])
     assert len(ub) == m
     flags = [ROW_NL] * (m - 1) + [ROW_NL | ROW_DENSE]
     w = E.to_wire(exprs, np.full(m, -np.inf), ub, flags)
@@ -69,7 +70,7 @@ def random_tree(rng, nvar, depth):
     """A random expression over nvar variables using every operator of the wire format."""
     if depth == 0 or rng.random() < 0.25:
         return E.var(int(rng.integers(nvar))) if rng.random() < 0.7 else E.const(float(np.round(rng.uniform(-2, 2), 3)))
-    k = rng.integers(14)
+    k = rng.integers(15)
     sub = lambda: random_tree(rng, nvar, depth - 1)
     if k == 0: return E.sum_([sub() for _ in range(int(rng.integers(1, 5)))])
     if k == 1: return E.prod_([sub() for _ in range(int(rng.integers(1, 4)))])
@@ -84,4 +85,7 @@ def random_tree(rng, nvar, depth):
     if k == 10: return E.abs_(sub())
     if k == 11: return E.sin(sub())
     if k == 12: return E.cos(sub())
+    if k == 13:
+        cmp = [E.le, E.lt, E.ge, E.gt, E.eq][int(rng.integers(5))]
+        return E.ifelse(cmp(sub(), sub()), sub(), sub())
     return -sub()

@@ -72,6 +72,14 @@ def trig_cap(m):
     return [x, y]
 
 
+def piecewise_bowl(m):
+    """ifelse front-end op: f(x) = ifelse(x <= 1, x^2, 2x - 1) is convex and C1; min y - 1.5 x under f(x) <= y: f'(x) = 1.5 at x = 0.75."""
+    x, y = m.variable(-2.0, 3.0), m.variable(-5.0, 10.0)
+    m.objective("Min", y - 1.5 * x)
+    m.nlconstraint(E.ifelse(E.le(x, 1.0), x**2, 2.0 * x - 1.0), "<=", y)
+    return [x, y]
+
+
 def b_108_01(m):
     x, y = m.variable(0, INF), m.variable(0, INF)
     m.objective("Min", (x - 1.0)**2 + (y - 0.75)**2)
@@ -160,6 +168,7 @@ PROBLEMS = [
     _p("107_01", "test/2d.jl:405-420", disk("Min", lambda x, y: (x - 0.5)**2 + (y - 0.5)**2, False), 0.0, [0.5, 0.5]),
     _p("107_02", "test/2d.jl:423-438", disk("Min", lambda x, y: (x - 1.0)**2 + (y - 1.0)**2, False), 0.17157287363083387, [1 / r2, 1 / r2]),
     _p("106_xx", "sin/cos front-end ops; convex variant of test/2d.jl:357-401", trig_cap, -0.8600655610487502, [1.0353981633974483, 0.8600655610487502]),
+    _p("ifelse_xx", "ifelse / comparison front-end ops (SURVEY 8f item 4)", piecewise_bowl, -0.5625, [0.75, 0.5625]),
     _p("108_01", "test/2d.jl:460-476", b_108_01, 0.0, [1.0, 0.75]),
     _p("110_01", "test/2d.jl:603-618", nlobj_disk(lambda x, y: E.const(e)**x), e**-1, [-1.0, 0.0]),
     _p("110_02", "test/2d.jl:621-636", nlobj_disk(lambda x, y: E.const(e)**x + E.const(e)**y), 2 * e**(-1 / r2), [-1 / r2, -1 / r2]),

@@ -20,8 +20,10 @@ from katana_jl_b200.binding import ROW_DENSE, ROW_NL, WireRows
 from katana_jl_b200.nlpeval import EpigraphNLPEvaluator, ExprNLPEvaluator, rows_to_wire
 from reference_problems import PROBLEMS
 
-KTN_OPS = {"+": 2, "-": 3, "*": 4, "/": 5, "^": 6, "exp": 8, "log": 9, "sqrt": 10, "abs": 11, "sin": 12, "cos": 13}     # shim: const KTN_OPS
-SYM = {E.OP_ADD: "+", E.OP_SUB: "-", E.OP_MUL: "*", E.OP_DIV: "/", E.OP_POW: "^", E.OP_EXP: "exp", E.OP_LOG: "log", E.OP_SQRT: "sqrt", E.OP_ABS: "abs", E.OP_SIN: "sin", E.OP_COS: "cos"}
+KTN_OPS = {"+": 2, "-": 3, "*": 4, "/": 5, "^": 6, "exp": 8, "log": 9, "sqrt": 10, "abs": 11, "sin": 12, "cos": 13,
+           "ifelse": 14, "<=": 15, "<": 16, ">=": 17, ">": 18, "(==)": 19}     # shim: const KTN_OPS
+SYM = {E.OP_ADD: "+", E.OP_SUB: "-", E.OP_MUL: "*", E.OP_DIV: "/", E.OP_POW: "^", E.OP_EXP: "exp", E.OP_LOG: "log", E.OP_SQRT: "sqrt", E.OP_ABS: "abs", E.OP_SIN: "sin", E.OP_COS: "cos", E.OP_IFELSE: "ifelse"}
+CMP = {E.OP_LE: "<=", E.OP_LT: "<", E.OP_GE: ">=", E.OP_GT: ">", E.OP_EQ: "(==)"}
 
 
 def julia_expr(n):
@@ -32,6 +34,8 @@ def julia_expr(n):
         return ("ref", "x", n.index + 1)
     if n.op == E.OP_NEG:
         return ("call", "-", julia_expr(n.children[0]))
+    if n.op in CMP:                                              # Julia 0.5 / 0.6 parse a <= b as Expr(:comparison, a, :<=, b)
+        return ("comparison", julia_expr(n.children[0]), CMP[n.op], julia_expr(n.children[1]))
     return ("call", SYM[n.op]) + tuple(julia_expr(c) for c in n.children)
 
 
@@ -40,6 +44,9 @@ def flatten(op, arg, val, ex):                                   # shim: flatten
         op.append(0); arg.append(0); val.append(float(ex))
     elif ex[0] == "ref":
         op.append(1); arg.append(ex[2] - 1); val.append(0.0)
+    elif ex[0] == "comparison" and len(ex) == 4:
+        op.append(KTN_OPS[ex[2]]); arg.append(2); val.append(0.0)
+        flatten(op, arg, val, ex[1]); flatten(op, arg, val, ex[3])
     elif ex[0] == "call":
         f, a = ex[1], ex[2:]
         if f == "-" and len(a) == 1:
@@ -164,5 +171,5 @@ def test_shim_source_states_the_rules():
     assert "c.head == :comparison ? c.args[3] : c.args[2]" in shim
     assert re.search(r"set_bounds!\(m\.params\.separator, m\.l_constr, m\.u_constr\)", shim)
     assert "fill(NaN, length(vars))" in shim                    # gencut of a non-finite row: _addcut must see NaN (src/model.jl:69-73)
-    ops = dict(re.findall(r":(\S+) => (\d+)", re.search(r"const KTN_OPS = Dict\((.*?)\)", shim).group(1)))
+    ops = dict(re.findall(r":(\S+) => (\d+)", re.search(r"const KTN_OPS = Dict\((.*?=> 19)\)", shim, flags=re.S).group(1)))
     assert {k: int(v) for k, v in ops.items()} == KTN_OPS
