@@ -178,7 +178,7 @@ class KatanaNonlinearModel:                                    # src/model.jl:9-
     # boundroutine(m, ray) -- src/model.jl:175-197
     def boundroutine(self, ray):
         sep = self.params.separator
-        if hasattr(sep, "separate_ladder") and getattr(sep, "ngpus", 1) <= 1:
+        if hasattr(sep, "separate_ladder") and getattr(sep, "has_ladder", False):
             # the whole search in one library call: the points are evaluated on the device in batches, the cuts are made at the
             # first point that violates a row -- what the loop below does with up to 1022 sequential rounds
             n_hit, batch = sep.separate_ladder(np.asarray(ray, np.float64))

@@ -61,6 +61,7 @@ class KatanaGPUSeparator(AbstractKatanaSeparator):
         self.topk = topk
         self.ngpus, self.devices, self.pipeline, self.direct = ngpus, devices, pipeline, direct
         self.handle = None
+        self.has_ladder = True
         self.last = None           # CutBatch of the last precompute!
         self.xstar = None
         self.g = None
@@ -73,7 +74,9 @@ class KatanaGPUSeparator(AbstractKatanaSeparator):
         if self.handle is not None:                            # one separator is reused across models (test/runtests.jl:24)
             self.handle.close()
         # lean views: optimize! hands (row_ptr, col, val, lo, hi) to the LP; g / viol / bconst stay on the device
-        self.handle = lib.create(f_tol=f_tol, cut_coef_rng=cut_coef_rng, topk=self.topk, **self.handle_options(num_constr))
+        opts = self.handle_options(num_constr)
+        self.has_ladder = opts.get("ngpus", 0) <= 1        # ktn_separate_ladder runs on plain handles (one device, one shard)
+        self.handle = lib.create(f_tol=f_tol, cut_coef_rng=cut_coef_rng, topk=self.topk, **opts)
         self.num_var, self.num_constr = num_var, num_constr
         lb = np.full(num_constr, -np.inf); ub = np.full(num_constr, np.inf)
         self.handle.load(num_var, rows_to_wire(oracle, num_constr, lb, ub))
@@ -81,11 +84,12 @@ class KatanaGPUSeparator(AbstractKatanaSeparator):
         self.last = self.g = self.xstar = None
 
     PIPELINE_MIN_ROWS = 400_000
+    PIPELINE_MAX_ROWS = 4_000_000      # beyond: the worst-case pinned batch of a pipelined handle would pass the library's 1 GiB limit
 
     def shards_per_device(self, num_constr):
         if self.pipeline is not None:
             return max(int(self.pipeline), 1)
-        return 2 if num_constr >= self.PIPELINE_MIN_ROWS and not self.topk else 1
+        return 2 if self.PIPELINE_MIN_ROWS <= num_constr <= self.PIPELINE_MAX_ROWS and not self.topk else 1
 
     def handle_options(self, num_constr=0):
         """ktn_options of this separator: lean views (optimize! hands row_ptr, col, val, lo, hi to the LP), the device list, eager downloads."""

@@ -144,3 +144,21 @@ def test_models_without_nl_macros_take_the_lpqp_bridge(oracle_lib):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         assert m2.solve() == "Optimal" and not hasattr(m2, "bridge")
+
+
+def test_pipelined_separator_bounds_an_unbounded_lp_without_the_ladder_call(oracle_lib):
+    """A separator whose handle is a group of shards (pipeline > 1, several devices) has no ktn_separate_ladder: boundroutine
+    (src/model.jl:175-197) falls back to the reference's sequential search and reaches the same optimum."""
+    by_name = {p[0]: p for p in PROBLEMS}
+    _, cite, build, obj, sol = by_name["501_01_n3"]
+    sep = K.KatanaGPUSeparator(library=oracle_lib, pipeline=2)
+    m = K.Model(K.KatanaSolver(separator=sep, log_level=0))
+    vars_ = build(m)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert m.solve() == "Optimal"
+    assert not sep.has_ladder and sep.handle_options(10)["ngpus"] == 2
+    assert not any("ladder_hit" in r for r in m.internal.round_log)         # the sequential path was taken
+    assert np.isclose(m.getobjectivevalue(), obj, rtol=OPT_TOL, atol=OPT_TOL)
+    m2, _, s2 = solve_problem(oracle_lib, build)
+    assert s2 == "Optimal" and any("ladder_hit" in r for r in m2.internal.round_log)      # a plain handle uses the one-call ladder
