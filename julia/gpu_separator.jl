@@ -185,6 +185,20 @@ function gencut(sep::KatanaGPUSeparator, xstar, bounds, i)                      
     AffExpr(vars, vals, b[1])
 end
 
+# boundroutine(m, ray) (src/model.jl:175-197) as ONE call: the points 2^n * ray, n = 2 .. 1023, are evaluated on the device in batches and the
+# cuts are made at the first point that violates a row.  Plain handles only (a pipelined or multi-device handle keeps the reference's loop
+# over separate!).  Returns (status, n_hit or -1, view).
+function separate_ladder!(sep::KatanaGPUSeparator, ray::Vector{Float64}, n_first::Integer = 2, n_last::Integer = 1023)
+    hit = Ref{Int32}(-1); nc, nz, er = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0)
+    st = ccall((:ktn_separate_ladder, libktn), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32, Ref{Int32}, Ref{Int64}, Ref{Int64}, Ref{Int64}),
+               sep.handle, ray, n_first, n_last, hit, nc, nz, er)
+    check(sep, st, "ktn_separate_ladder")
+    v = Ref{KtnCutView}()
+    check(sep, ccall((:ktn_fetch_cuts_view, libktn), Cint, (Ptr{Cvoid}, Ref{KtnCutView}), sep.handle, v), "ktn_fetch_cuts_view")
+    sep.xstar = (2.0^(hit[] >= 0 ? hit[] : n_last)) .* ray; sep.have_g = false
+    return st, Int(hit[]), v[]
+end
+
 # loadproblem! (src/model.jl:172), right after `initialize!(sep, m.linear_model, m.num_var, m.num_constr, d)`:
 set_bounds!(m.params.separator, m.l_constr, m.u_constr)   # bounds are model state (src/model.jl:273-277): handed over once
 
