@@ -112,7 +112,9 @@ enum {
                                device): ktn_separate starts every shard's cut download the moment that shard has finished, into a
                                pinned buffer laid out for the worst case (every nonlinear row cut: 32 bytes per nonlinear row + 12 per
                                Jacobian entry, twice); ktn_fetch_cuts_view then only waits.  The download of the first shards overlaps
-                               the kernels of the later ones.  Ignored when that buffer would exceed 1 GiB. */
+                               the kernels of the later ones.  Ignored when that buffer would exceed 1 GiB.  When every shard is on ONE
+                               device the shards share a stream, x* is uploaded once and a small kernel per shard stores its cuts into
+                               the (mapped) pinned buffer: one host synchronisation per round. */
     KTN_FLAG_DIRECT_VIEW = 8, /* single-device handles without a communicator: the round's kernels store the cut batch straight into
                                mapped pinned host memory (two buffers of the worst-case size -- every row cut -- alternate) instead of
                                device memory, so the PCIe transfer runs WHILE the cuts are built and ktn_fetch_cuts_view copies
