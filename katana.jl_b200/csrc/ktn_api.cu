@@ -182,7 +182,7 @@ extern "C" int ktn_load_end(ktn_handle* h) {
     CK(h, upload(h->row_lb, P.lb)); CK(h, upload(h->row_ub, P.ub)); CK(h, upload(h->row_slot, P.row_slot));
     { std::vector<uint8_t> nl(P.flags.size()); for (size_t i = 0; i < nl.size(); ++i) nl[i] = (P.flags[i] & KTN_ROW_NL) ? 1 : 0; CK(h, upload(h->row_nl, nl)); }
     CK(h, h->rec.alloc(32 * (m + 1))); CK(h, h->worklist.alloc(8 * (m + 1))); CK(h, h->park.alloc(32 * (m + 1))); CK(h, h->cut_off.alloc(8 * (m + 2)));
-    CK(h, upload(h->chunk_jp, P.chunk_jp)); CK(h, h->dump.alloc(24 * (N + 1)));
+    CK(h, upload(h->chunk_jp, P.chunk_jp));
     CK(h, h->x.alloc(8 * ((size_t)P.num_var + 1))); CK(h, h->force.alloc(m + 16));
     CK(h, h->g_row.alloc(8 * (m + 1))); CK(h, h->b_row.alloc(8 * (m + 1))); CK(h, h->sel.alloc(4 * (m + 1)));
     CK(h, cudaMemset(h->sel.p, 0, 4 * (m + 1))); CK(h, cudaMemset(h->g_row.p, 0, 8 * (m + 1)));
@@ -274,7 +274,7 @@ KtnRoundParams ktn_make_params(ktn_handle* h, const double* d_x, int mode, int d
     p.chunk_lb = h->chunk_lb.as<double>(); p.chunk_ub = h->chunk_ub.as<double>();
     p.jac_ptr = h->jac_ptr.as<int64_t>(); p.jac_col = h->jac_col.as<int32_t>();
     p.row_lb = h->row_lb.as<double>(); p.row_ub = h->row_ub.as<double>(); p.row_slot = h->row_slot.as<int32_t>();
-    p.chunk_jp = h->chunk_jp.as<uint32_t>(); p.dump = h->dump.as<double>(); p.dump_nnz = (uint64_t)h->prob.jac_ptr[h->prob.num_constr];
+    p.chunk_jp = h->chunk_jp.as<uint32_t>(); p.dump = nullptr; p.dump_nnz = 0;      // (register-dump experiment of round 2, DESIGN.md section 5: measured, dropped; the buffer is no longer allocated)
     p.rec = h->rec.as<double4>(); p.park = h->park.as<double4>(); p.cut_off = h->cut_off.as<unsigned long long>(); p.worklist = h->worklist.as<unsigned long long>(); p.errpos = h->errpos.as<unsigned long long>(); p.blk_off = h->blk_off.as<unsigned long long>();
     for (int f = 0; f <= KTN_FAM__COUNT; ++f) p.fam_begin[f] = h->prob.fam_begin[f];
     memcpy(p.cls_begin, h->prob.cls_begin, sizeof p.cls_begin); memcpy(p.cls_blob_off, h->prob.cls_blob_off, sizeof p.cls_blob_off);

@@ -218,15 +218,6 @@ __device__ __forceinline__ void family_class(const KtnRoundParams& p, uint32_t l
                 p.rec[row[r]] = make_double4(g, aux, lb[r], ub[r]);
                 p.sel[row[r]] = (uint32_t)N | KTN_SEL_DEFER;
                 count_selected(p, selm, row[r], (uint32_t)N);
-#if KTN_DUMP == 1
-                double2* d2 = reinterpret_cast<double2*>(p.dump) + jp[r];
-#pragma unroll
-                for (int u = 0; u < N; ++u) d2[u] = make_double2(v[r].p1[u], v[r].x[u]);
-#elif KTN_DUMP == 2
-                double2* d2 = reinterpret_cast<double2*>(p.dump) + jp[r]; double* d1 = p.dump + 2 * (size_t)p.dump_nnz + jp[r];
-#pragma unroll
-                for (int u = 0; u < N; ++u) { d2[u] = make_double2(v[r].p0[u], v[r].p1[u]); d1[u] = v[r].x[u]; }
-#endif
             }
         }
         cur = __shfl_sync(0xffffffffu, tn, 0);
