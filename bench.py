@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--violated", dest="v", type=float, default=0.1, help="violated fraction of the rows at x* (not --v: torchrun's own parser claims that prefix)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=0, help="e2e leg: shards per device whose cut transfers overlap the following shards' kernels (KTN_FLAG_EAGER_VIEW); 0 = KatanaGPUSeparator's own measured default (one device: two shards from 400 000 rows on -- 10^6 LSE rows: 1 shard 0.604 ms, 2: 0.575, 3: 0.587, 4: 0.632, 8: 0.76; several devices: 1)")
+    ap.add_argument("--pipeline", type=int, default=0, help="e2e leg: shards per device whose cut transfers overlap the following shards' kernels (KTN_FLAG_EAGER_VIEW); 0 = KatanaGPUSeparator's own measured default (one device: two shards between 750 000 and 4 000 000 rows -- 10^6 LSE rows: 1 shard 0.604 ms, 2: 0.575, 3: 0.587, 4: 0.632, 8: 0.76; several devices: 1)")
     ap.add_argument("--direct", type=int, default=0, help="e2e leg at one GPU, one shard: 1 = the round's kernels store the cuts straight into the pinned host buffer (KTN_FLAG_DIRECT_VIEW; measured 0.622 ms against 0.604); 0 = the separator's default: device blob + one download after the round")
     ap.add_argument("--skip-e2e", action="store_true", help="exchange sweeps only: skip the end-to-end leg and the sharded parity check (the line then carries no e2e)")
     ap.add_argument("--topk", type=int, default=0, help="build extension: keep only the k most violated rows per round (0 = reference behaviour: all)")

@@ -53,7 +53,7 @@ class KatanaGPUSeparator(AbstractKatanaSeparator):
         shard has finished (KTN_FLAG_EAGER_VIEW): the PCIe transfer of the first shards overlaps the kernels of the later ones.
         On ONE device the shards share a stream and a small kernel per shard stores its cuts into the pinned batch (ktn_api.cu
         group_round_pushed).  pipeline = None: the measured default (B200, 10^6 log-sum-exp rows, 10^5 cuts per round: one shard
-        0.604 ms, two 0.575, three 0.587, four 0.632, eight 0.76): two shards from PIPELINE_MIN_ROWS rows on, else one.
+        0.604 ms, two 0.575, three 0.587, four 0.632, eight 0.76): two shards between PIPELINE_MIN_ROWS and PIPELINE_MAX_ROWS rows, else one.
         direct (one device, one shard): the round's kernels store the batch straight into the pinned host buffer the views point
         into (KTN_FLAG_DIRECT_VIEW); measured no faster than the download (0.622 against 0.604 ms: stores from the SMs reach
         43-48 GB/s over PCIe, the copy engine 56), so it is off by default."""
@@ -83,7 +83,7 @@ class KatanaGPUSeparator(AbstractKatanaSeparator):
         self.l_constr, self.u_constr = lb, ub
         self.last = self.g = self.xstar = None
 
-    PIPELINE_MIN_ROWS = 400_000
+    PIPELINE_MIN_ROWS = 750_000        # measured at 10^6 rows only (29 us gained of 604); the gain shrinks with the kernel time it overlaps
     PIPELINE_MAX_ROWS = 4_000_000      # beyond: the worst-case pinned batch of a pipelined handle would pass the library's 1 GiB limit
 
     def shards_per_device(self, num_constr):
