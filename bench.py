@@ -337,9 +337,9 @@ def main():
         # the separator as a Katana user creates it for a large model: the rows in `args.pipeline` consecutive shards on the one device, every
         # shard's cuts downloaded as soon as it has finished (KTN_FLAG_EAGER_VIEW)
         sep = KatanaGPUSeparator(devices=[local], pipeline=args.pipeline or None, direct=bool(args.direct))
-        per = sep.shards_per_device(rows)
+        per = sep.shards_per_device(nl_rows)       # the separator decides on the rows a round tests (nlconstr_ixs)
         if per > 1 or args.direct:
-            hp = lib.create(**sep.handle_options(rows)); hp.load(nv, w); hp.set_bounds(w.lb, ub)
+            hp = lib.create(**sep.handle_options(nl_rows)); hp.load(nv, w); hp.set_bounds(w.lb, ub)
         else:
             hp = h
         sep.handle = hp; sep.num_var, sep.num_constr = nv, rows
@@ -353,7 +353,7 @@ def main():
     elif rank == 0:
         # ONE separator in ONE process over all world*rows rows, as the reference owns it (src/Katana.jl:18): ktn_options.ngpus
         sepg = KatanaGPUSeparator(ngpus=world, pipeline=args.pipeline or None)
-        hg = lib.create(**sepg.handle_options(world * rows))
+        hg = lib.create(**sepg.handle_options(world * nl_rows))
         hg.load_begin(nv, world * rows)
         for r in range(world):
             hg.add_rows(r * rows, w if r == 0 else lib.synth_rows(kind, seed, nv, r * rows, rows))

@@ -115,7 +115,8 @@ function initialize!(sep::KatanaGPUSeparator, linear_model, num_var::Int, num_co
         # flags: 1 = lean views.  Large models on ONE device run as two pipelined shards of that device (flags |= 4, the device listed
         # twice): the transfer of the first shard's cuts overlaps the second shard's kernels (measured default of the Python twin,
         # katana.jl_b200/separators.py: between 750 000 and 4 000 000 rows; decided by the first model the separator sees)
-        pipe = sep.ngpus <= 1 && 750_000 <= num_constr <= 4_000_000
+        n_nl = count(i -> !MathProgBase.isconstrlinear(oracle, i), 1:num_constr)      # the rows a round tests and cuts
+        pipe = sep.ngpus <= 1 && 750_000 <= n_nl <= 4_000_000
         devs = ntuple(i -> Int32(pipe && i <= 2 ? 0 : -1), 16)
         o = Ref(KtnOptions(sizeof(KtnOptions), -1, 1e-6, 1e9, 0, pipe ? 5 : 1, 0, pipe ? 2 : (sep.ngpus > 1 ? sep.ngpus : 0), devs))
         h = Ref{Ptr{Cvoid}}(C_NULL)

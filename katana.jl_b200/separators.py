@@ -74,27 +74,28 @@ class KatanaGPUSeparator(AbstractKatanaSeparator):
         if self.handle is not None:                            # one separator is reused across models (test/runtests.jl:24)
             self.handle.close()
         # lean views: optimize! hands (row_ptr, col, val, lo, hi) to the LP; g / viol / bconst stay on the device
-        opts = self.handle_options(num_constr)
+        lb = np.full(num_constr, -np.inf); ub = np.full(num_constr, np.inf)
+        wire = rows_to_wire(oracle, num_constr, lb, ub)
+        opts = self.handle_options(int((wire.flags & 1).sum()))      # the rows a round tests and cuts (nlconstr_ixs) decide the pipelining
         self.has_ladder = opts.get("ngpus", 0) <= 1        # ktn_separate_ladder runs on plain handles (one device, one shard)
         self.handle = lib.create(f_tol=f_tol, cut_coef_rng=cut_coef_rng, topk=self.topk, **opts)
         self.num_var, self.num_constr = num_var, num_constr
-        lb = np.full(num_constr, -np.inf); ub = np.full(num_constr, np.inf)
-        self.handle.load(num_var, rows_to_wire(oracle, num_constr, lb, ub))
+        self.handle.load(num_var, wire)
         self.l_constr, self.u_constr = lb, ub
         self.last = self.g = self.xstar = None
 
     PIPELINE_MIN_ROWS = 750_000        # measured at 10^6 rows only (29 us gained of 604); the gain shrinks with the kernel time it overlaps
     PIPELINE_MAX_ROWS = 4_000_000      # beyond: the worst-case pinned batch of a pipelined handle would pass the library's 1 GiB limit
 
-    def shards_per_device(self, num_constr):
+    def shards_per_device(self, num_nl_rows):
         if self.pipeline is not None:
             return max(int(self.pipeline), 1)
-        return 2 if self.PIPELINE_MIN_ROWS <= num_constr <= self.PIPELINE_MAX_ROWS and not self.topk else 1
+        return 2 if self.PIPELINE_MIN_ROWS <= num_nl_rows <= self.PIPELINE_MAX_ROWS and not self.topk else 1
 
-    def handle_options(self, num_constr=0):
+    def handle_options(self, num_nl_rows=0):
         """ktn_options of this separator: lean views (optimize! hands row_ptr, col, val, lo, hi to the LP), the device list, eager downloads."""
         devs = list(self.devices) if self.devices else list(range(max(self.ngpus, 1)))
-        per = self.shards_per_device(num_constr) if len(devs) == 1 else max(int(self.pipeline or 1), 1)      # the measured default is a one-device result
+        per = self.shards_per_device(num_nl_rows) if len(devs) == 1 else max(int(self.pipeline or 1), 1)      # the measured default is a one-device result
         shards = [d for d in devs for _ in range(per)]
         if len(shards) <= 1:
             return dict(flags=FLAG_LEAN_VIEW | (FLAG_DIRECT_VIEW if self.direct else 0), device=devs[0] if self.devices else -1)
