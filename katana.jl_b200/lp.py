@@ -5,18 +5,55 @@ In the reference the LP master is a JuMP model on an external MathProgBase LP so
 (SURVEY.md section 2, row 9).  No GLPK/Clp exists in this image, so the Python mirror uses
 scipy's bundled HiGHS behind the handful of calls src/model.jl makes on the LP:
 solve, getsolution, getobjval, getunboundedray, addconstraint (src/model.jl:76,89-96,228-265).
+
+Batched hand-off: a CutBatch arrives as CSR and is KEPT as one CSR block (`addconstrs_csr`: three
+array copies, no per-cut Python work); the constraint matrix of a solve is assembled from the blocks with sparse row selections.
+The row order of the assembled LP is the insertion order (a two-sided row contributes its upper row, then its negated lower row),
+whether a row arrived alone or inside a block.
 """
 import numpy as np
 from scipy.optimize import linprog
-from scipy.sparse import csr_matrix
+from scipy.sparse import csr_matrix, diags, vstack
+
+
+class _Block:
+    """Consecutive LP rows lo <= A x <= hi as one CSR block.  age: None = permanent rows; else per row the number of consecutive
+    solves it has been slack (cut management, purge_slack_rows)."""
+
+    def __init__(self, indptr, col, val, lo, hi, managed):
+        self.indptr = np.asarray(indptr, np.int64) - int(indptr[0])
+        self.col, self.val = np.asarray(col, np.int64), np.asarray(val, np.float64)
+        self.lo, self.hi = np.asarray(lo, np.float64), np.asarray(hi, np.float64)
+        self.age = np.zeros(len(self.lo), np.int32) if managed else None
+
+    def __len__(self):
+        return len(self.lo)
+
+    def matrix(self, n):
+        return csr_matrix((self.val, self.col, self.indptr), shape=(len(self.lo), n))
+
+    def extend(self, o):
+        """Appends the rows of block `o` (same kind: both permanent or both managed)."""
+        self.indptr = np.concatenate([self.indptr, o.indptr[1:] + self.indptr[-1]])
+        self.col, self.val = np.concatenate([self.col, o.col]), np.concatenate([self.val, o.val])
+        self.lo, self.hi = np.concatenate([self.lo, o.lo]), np.concatenate([self.hi, o.hi])
+        if self.age is not None:
+            self.age = np.concatenate([self.age, o.age])
+
+    def take(self, keep):
+        """The block restricted to the rows of the boolean mask `keep`."""
+        A = self.matrix(int(self.col.max()) + 1 if len(self.col) else 1)[np.flatnonzero(keep)]
+        b = _Block(A.indptr, A.indices, A.data, self.lo[keep], self.hi[keep], False)
+        b.age = None if self.age is None else self.age[keep]
+        return b
 
 
 class HighsLP:
     def __init__(self):
         self.lb, self.ub = [], []
         self.c = np.zeros(0); self.c0 = 0.0; self.sense = "Min"
-        self.rows = []          # (cols int array, vals float array, lo, hi)
-        self.managed = []       # per row: -1 = permanent (model rows, vertex / bounding cuts); >= 0: a loop cut, solves in a row it has been slack
+        self.blocks = []        # _Block objects in insertion order (a single row is a block of one row)
+        self.purged = []        # blocks of rows removed by purge_slack_rows: put back (for good) by restore_purged if the LP loses its bound
         self.x = None; self.objval = np.nan; self.status = "None"
 
     # --- model building -------------------------------------------------------------------
@@ -29,6 +66,20 @@ class HighsLP:
     def numvar(self):
         return len(self.lb)
 
+    @property
+    def rows(self):
+        """The LP rows as (cols, vals, lo, hi) tuples in LP order (inspection and tests; the solver path never builds this list)."""
+        out = []
+        for b in self.blocks:
+            for i in range(len(b)):
+                s, e = b.indptr[i], b.indptr[i + 1]
+                out.append((b.col[s:e], b.val[s:e], float(b.lo[i]), float(b.hi[i])))
+        return out
+
+    @property
+    def numrows(self):
+        return sum(len(b) for b in self.blocks)
+
     def setobjective(self, sense, cols, coefs, const=0.0):
         self.sense = sense
         self.c = np.zeros(self.numvar)
@@ -37,18 +88,33 @@ class HighsLP:
 
     def addconstr(self, cols, vals, lo, hi):
         """MathProgBase.addconstr!(m, varidx, coef, lb, ub): one LP row lo <= a.x <= hi."""
-        self.rows.append((np.asarray(cols, np.int64), np.asarray(vals, np.float64), float(lo), float(hi)))
-        self.managed.append(-1)
+        cols = np.asarray(cols, np.int64)
+        self._append(_Block([0, len(cols)], cols, np.array(vals, np.float64), [float(lo)], [float(hi)], False))
+
+    def _append(self, b):
+        """Rows in insertion order; a small block joins the block before it when both are of one kind (the ECP loop of a small model
+        adds one or two cuts per round: hundreds of one-row blocks would make every solve assemble hundreds of matrices)."""
+        last = self.blocks[-1] if self.blocks else None
+        if last is not None and len(b) <= 4096 and len(last.val) <= 1 << 20 and (last.age is None) == (b.age is None):
+            last.extend(b)
+        else:
+            self.blocks.append(b)
 
     def addconstrs_csr(self, row_ptr, col, val, lo, hi, managed=False, skip=None):
-        """Batched hand-off of a CutBatch (the fast path that bypasses AffExpr objects).  managed: the rows may be purged later
-        (purge_slack_rows); skip: boolean mask of cuts NOT to add (duplicate filter)."""
-        for c in range(len(lo)):
-            if skip is not None and skip[c]:
-                continue
-            s, e = row_ptr[c], row_ptr[c + 1]
-            self.rows.append((col[s:e].astype(np.int64), val[s:e].copy(), float(lo[c]), float(hi[c])))
-            self.managed.append(0 if managed else -1)
+        """Batched hand-off of a CutBatch: the CSR arrays are copied once (they may be views of the library's pinned buffer) and kept
+        as a block.  managed: the rows may be purged later (purge_slack_rows); skip: boolean mask of cuts NOT to add (duplicate filter)."""
+        n = len(lo)
+        if n == 0:
+            return
+        s, e = int(row_ptr[0]), int(row_ptr[n])
+        b = _Block(np.array(row_ptr[:n + 1], np.int64), np.array(col[s:e], np.int64), np.array(val[s:e], np.float64),
+                   np.array(lo, np.float64), np.array(hi, np.float64), managed)
+        if skip is not None and np.any(skip):
+            keep = ~np.asarray(skip, bool)
+            if not keep.any():
+                return
+            b = b.take(keep)
+        self._append(b)
 
     def purge_slack_rows(self, age, tol):
         """Cut management (an extension: the reference keeps every cut, src/model.jl:215).  After a solve: a managed row whose
@@ -56,56 +122,73 @@ class HighsLP:
         removed.  Returns the number of rows removed."""
         if self.x is None:
             return 0
-        keep_rows, keep_tag, removed = [], [], 0
-        if not hasattr(self, "purged"):
-            self.purged = []    # every row removed so far: put back (for good) by restore_purged if the LP loses its bound
-        for (cols, vals, lo, hi), tag in zip(self.rows, self.managed):
-            if tag >= 0:
-                a = float(vals @ self.x[cols])
-                slack = min(hi - a if np.isfinite(hi) else np.inf, a - lo if np.isfinite(lo) else np.inf)
-                ref = max(1.0, abs(hi) if np.isfinite(hi) else 0.0, abs(lo) if np.isfinite(lo) else 0.0)
-                tag = tag + 1 if slack > tol * ref else 0
-                if tag >= age:
-                    removed += 1
-                    self.purged.append((cols, vals, lo, hi))
-                    continue
-            keep_rows.append((cols, vals, lo, hi)); keep_tag.append(tag)
-        self.rows, self.managed = keep_rows, keep_tag
+        removed, kept = 0, []
+        n = self.numvar
+        for b in self.blocks:
+            if b.age is None or len(b) == 0:
+                kept.append(b); continue
+            a = b.matrix(n) @ self.x
+            with np.errstate(invalid="ignore"):
+                slack = np.minimum(np.where(np.isfinite(b.hi), b.hi - a, np.inf), np.where(np.isfinite(b.lo), a - b.lo, np.inf))
+            ref = np.maximum(1.0, np.maximum(np.where(np.isfinite(b.hi), np.abs(b.hi), 0.0), np.where(np.isfinite(b.lo), np.abs(b.lo), 0.0)))
+            b.age = np.where(slack > tol * ref, b.age + 1, 0).astype(np.int32)
+            out = b.age >= age
+            if out.any():
+                removed += int(out.sum())
+                gone = b.take(out); gone.age = None
+                self.purged.append(gone)
+                if (~out).any():
+                    kept.append(b.take(~out))
+            else:
+                kept.append(b)
+        self.blocks = kept
         return removed
 
     def restore_purged(self):
         """Puts every purged row back as a permanent row; returns how many."""
-        rows = getattr(self, "purged", [])
-        for r in rows:
-            self.rows.append(r); self.managed.append(-1)
+        k = sum(len(b) for b in self.purged)
+        self.blocks.extend(self.purged)
         self.purged = []
-        return len(rows)
+        return k
 
     # --- solving ---------------------------------------------------------------------------
     def _matrices(self):
+        """(A_ub, b_ub), (A_eq, b_eq) in LP order, or None when a coefficient is not finite."""
         n = self.numvar
-        ub_rows, eq_rows = [], []
-        for cols, vals, lo, hi in self.rows:
-            if not np.all(np.isfinite(vals)):
+        ub_parts, ub_rhs, eq_parts, eq_rhs = [], [], [], []
+        for b in self.blocks:
+            if len(b) == 0:
+                continue
+            if not np.all(np.isfinite(b.val)):
                 return None
-            if np.isnan(lo) or np.isnan(hi):
-                # a cut taken where g is undefined (NaN value, finite gradient: the reference adds it, src/model.jl:69-76)
-                # has NaN bounds and constrains nothing; this stand-in drops it instead of guessing what GLPK does with NaN
-                continue
-            if lo == hi:
-                eq_rows.append((cols, vals, lo))
-                continue
-            if np.isfinite(hi): ub_rows.append((cols, vals, hi))
-            if np.isfinite(lo): ub_rows.append((cols, -vals, -lo))
+            # a cut taken where g is undefined (NaN value, finite gradient: the reference adds it, src/model.jl:69-76) has NaN bounds
+            # and constrains nothing; this stand-in drops it instead of guessing what GLPK does with NaN
+            ok = ~(np.isnan(b.lo) | np.isnan(b.hi))
+            eq = ok & (b.lo == b.hi)
+            up = ok & ~eq & np.isfinite(b.hi)
+            dn = ok & ~eq & np.isfinite(b.lo)
+            A = None
+            if eq.any():
+                A = b.matrix(n)
+                idx = np.flatnonzero(eq)
+                eq_parts.append(A[idx]); eq_rhs.append(b.lo[idx])
+            if up.any() or dn.any():
+                A = b.matrix(n) if A is None else A
+                iu, il = np.flatnonzero(up), np.flatnonzero(dn)
+                rows = np.concatenate([iu, il]); sign = np.concatenate([np.ones(len(iu)), -np.ones(len(il))])
+                rhs = np.concatenate([b.hi[iu], -b.lo[il]])
+                order = np.argsort(2 * rows + (sign < 0), kind="stable")       # a row's upper row first, then its negated lower row
+                rows, sign, rhs = rows[order], sign[order], rhs[order]
+                M = A[rows]
+                if (sign < 0).any():
+                    M = diags(sign) @ M
+                ub_parts.append(M.tocsr()); ub_rhs.append(rhs)
 
-        def build(rs):
-            if not rs:
+        def build(parts, rhs):
+            if not parts:
                 return None, None
-            indptr = np.zeros(len(rs) + 1, np.int64)
-            for i, r in enumerate(rs): indptr[i + 1] = indptr[i] + len(r[0])
-            A = csr_matrix((np.concatenate([r[1] for r in rs]), np.concatenate([r[0] for r in rs]), indptr), shape=(len(rs), n))
-            return A, np.array([r[2] for r in rs])
-        return build(ub_rows), build(eq_rows)
+            return (parts[0] if len(parts) == 1 else vstack(parts, format="csr")), np.concatenate(rhs)
+        return build(ub_parts, ub_rhs), build(eq_parts, eq_rhs)
 
     def solve(self):
         n = self.numvar
