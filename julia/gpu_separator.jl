@@ -219,6 +219,27 @@ if st == 1                                                # non-finite coefficie
 end
 allsat = v.n_cuts == 0
 
+# Cut management (an extension: the reference never removes a cut, src/model.jl:215; mirrors katana.jl_b200/lp.py purge_slack_rows and the
+# rule of model.py: purge only after the LP bound has passed its value at the last purge, put everything back if the LP loses its bound).
+# `cut_rows` are the LP row indices of the loop cuts, `cut_lo` / `cut_hi` their bounds, `slack_age` how many optima in a row each has been
+# slack.  Deletes the cuts slack for `age` consecutive optima and returns how many; the bookkeeping vectors are updated in place.
+function purge_slack_cuts!(mpb_lp, cut_rows::Vector{Int}, cut_lo::Vector{Float64}, cut_hi::Vector{Float64}, slack_age::Vector{Int}, age::Int; tol = 1e-7)
+    act = MathProgBase.getconstrsolution(mpb_lp)
+    drop = Int[]
+    for (k, r) in enumerate(cut_rows)
+        slack = min(isfinite(cut_hi[k]) ? cut_hi[k] - act[r] : Inf, isfinite(cut_lo[k]) ? act[r] - cut_lo[k] : Inf)
+        ref = max(1.0, isfinite(cut_hi[k]) ? abs(cut_hi[k]) : 0.0, isfinite(cut_lo[k]) ? abs(cut_lo[k]) : 0.0)
+        slack_age[k] = slack > tol * ref ? slack_age[k] + 1 : 0
+        slack_age[k] >= age && push!(drop, k)
+    end
+    isempty(drop) && return 0
+    gone = sort(cut_rows[drop])
+    MathProgBase.delconstrs!(mpb_lp, gone)
+    deleteat!(cut_rows, drop); deleteat!(cut_lo, drop); deleteat!(cut_hi, drop); deleteat!(slack_age, drop)
+    for k in eachindex(cut_rows); cut_rows[k] -= searchsortedlast(gone, cut_rows[k]); end      # the rows behind a deleted row move up
+    return length(gone)
+end
+
 # Sharded rounds, one process per GPU (e.g. Distributed.jl workers): rank r of nranks owns rows [row_begin, row_end).
 # (Inside ONE process, `KatanaGPUSeparator(ngpus = 8)` above needs none of this: ktn_options.ngpus.)
 # `id` is the 128-byte communicator id made on rank 0 (ktn_comm_unique_id) and sent to the others by the host's own means.
